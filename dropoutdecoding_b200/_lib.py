@@ -1,0 +1,74 @@
+"""ctypes binding of libdropdec.so (include/dropdec.h).
+
+There is no CPU fallback: if the library cannot be built or loaded, importing the ops fails
+loudly.  Loading works without a GPU (the library links cudart statically and resolves the
+driver lazily), so the CPU test-suite can check the exported symbols.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_i32p = C.c_void_p  # raw device pointers travel as integers
+_P = C.c_void_p
+
+_SIGNATURES = {
+    "dd_version": (C.c_int, []),
+    "dd_last_error": (C.c_char_p, []),
+    "dd_uncertainty_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "dd_uncertainty_project": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "dd_sample_masks": (C.c_int, [_P, _P, C.c_int, _P, C.POINTER(C.c_double), C.c_int, _P, C.c_uint64,
+                                  C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
+    "dd_philox_uniform": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, _P, _P]),
+    "dd_attention_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
+    "dd_decode_attention": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P,
+                                      C.c_size_t, _P]),
+    "dd_commit_winner": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, _P]),
+    "dd_aggregate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "dd_rmsnorm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
+    "dd_skinny_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dd_rope_stage": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "dd_embed_gather": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dd_step_advance": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
+}
+
+EXPORTED = tuple(_SIGNATURES)
+
+
+class DropDecError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load (building first if needed) libdropdec.so.  Raises if that is impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise DropDecError(f"{path} is missing: run `python -m dropoutdecoding_b200.build`")
+        path = _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+        fn.restype, fn.argtypes = res, args
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().dd_last_error().decode(errors="replace")
+        raise DropDecError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,122 @@
+// (4) Ensemble aggregation: fused per-member argmax + max-vote (or logit mean) in one launch,
+// no host sync.  Replaces select_by_vote / select_by_average (models/llava.py:22-52), whose
+// 2K `.item()` calls stall the host every token.
+//
+// HBM-bound: reads B*K*V fp32 once (+ writes B*V when out_logits is requested).
+#include "dd_common.cuh"
+
+namespace dd {
+
+constexpr int kAggThreads = 512;
+
+struct ArgMax {
+  float v;
+  int i;
+};
+// torch.argmax: the first index of the maximum
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
+  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ ArgMax block_argmax(ArgMax x, ArgMax* s_warp) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax y{__shfl_xor_sync(0xffffffffu, x.v, o), __shfl_xor_sync(0xffffffffu, x.i, o)};
+    x = better(x, y);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // s_warp may still be read from the previous call
+  if (lane == 0) s_warp[warp] = x;
+  __syncthreads();
+  ArgMax r = s_warp[0];
+  for (int w = 1; w < kAggThreads / 32; ++w) r = better(r, s_warp[w]);
+  return r;
+}
+
+__global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __restrict__ logits, int K,
+                                                                int V, int mode, int32_t* member_ids,
+                                                                int32_t* winner, int32_t* token,
+                                                                float* out_logits) {
+  __shared__ ArgMax s_warp[kAggThreads / 32];
+  __shared__ int s_ids[DD_MAX_MEMBERS];
+  __shared__ int s_win;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* base = logits + (size_t)b * K * V;
+  const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+
+  for (int m = 0; m < K; ++m) {
+    const float* row = base + (size_t)m * V;
+    ArgMax best{-INFINITY, 0x7fffffff};
+    if (vec) {
+      const float4* row4 = reinterpret_cast<const float4*>(row);
+      for (int j = tid; j < V / 4; j += kAggThreads) {
+        const float4 x = __ldg(row4 + j);
+        best = better(best, ArgMax{x.x, 4 * j});
+        best = better(best, ArgMax{x.y, 4 * j + 1});
+        best = better(best, ArgMax{x.z, 4 * j + 2});
+        best = better(best, ArgMax{x.w, 4 * j + 3});
+      }
+    } else {
+      for (int j = tid; j < V; j += kAggThreads) best = better(best, ArgMax{row[j], j});
+    }
+    best = block_argmax(best, s_warp);
+    if (tid == 0) {
+      s_ids[m] = best.i;
+      if (member_ids) member_ids[b * K + m] = best.i;
+    }
+  }
+  __syncthreads();
+
+  if (mode == DD_AGG_VOTE) {
+    if (tid == 0) {
+      // Counter.most_common(1): highest count, ties -> the id inserted first (models/llava.py:29)
+      int best_cnt = 0, best_id = s_ids[0];
+      for (int m = 0; m < K; ++m) {
+        int c = 0;
+        for (int j = 0; j < K; ++j) c += (s_ids[j] == s_ids[m]);
+        if (c > best_cnt) { best_cnt = c; best_id = s_ids[m]; }
+      }
+      int w = 0;
+      while (s_ids[w] != best_id) ++w;  // first member with that id (models/llava.py:31-33)
+      s_win = w;
+      winner[b] = w;
+      token[b] = best_id;
+    }
+    if (out_logits) {
+      __syncthreads();
+      const float* row = base + (size_t)s_win * V;
+      for (int j = tid; j < V; j += kAggThreads) out_logits[(size_t)b * V + j] = row[j];
+    }
+  } else {  // DD_AGG_MEAN: numpy mean(axis=0) in fp32 = sequential row sum, then / K
+    ArgMax best{-INFINITY, 0x7fffffff};
+    const float inv_k = (float)K;
+    for (int j = tid; j < V; j += kAggThreads) {
+      float s = base[j];
+      for (int m = 1; m < K; ++m) s = __fadd_rn(s, base[(size_t)m * V + j]);
+      s = __fdiv_rn(s, inv_k);
+      out_logits[(size_t)b * V + j] = s;
+      best = better(best, ArgMax{s, j});
+    }
+    best = block_argmax(best, s_warp);
+    if (tid == 0) {
+      winner[b] = 0;  // member 0's output carries the mean (models/llava.py:39,50)
+      token[b] = best.i;
+    }
+  }
+}
+
+}  // namespace dd
+
+extern "C" int dd_aggregate(const float* logits, int B, int K, int V, int mode, int32_t* member_ids,
+                            int32_t* winner, int32_t* token, float* out_logits, dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(logits && winner && token, "dd_aggregate: null pointer");
+  DD_CHECK_ARG(K >= 1 && K <= DD_MAX_MEMBERS, "dd_aggregate: K=%d out of [1,%d]", K, DD_MAX_MEMBERS);
+  DD_CHECK_ARG(V >= 1 && B >= 0, "dd_aggregate: bad shape B=%d V=%d", B, V);
+  DD_CHECK_ARG(mode == DD_AGG_VOTE || mode == DD_AGG_MEAN, "dd_aggregate: bad mode %d", mode);
+  DD_CHECK_ARG(mode != DD_AGG_MEAN || out_logits, "dd_aggregate: mean mode needs out_logits");
+  if (B == 0) return DD_OK;
+  aggregate_kernel<<<B, kAggThreads, 0, (cudaStream_t)stream>>>(logits, K, V, mode, member_ids, winner, token,
+                                                                out_logits);
+  DD_CHECK_LAUNCH();
+  return DD_OK;
+}

@@ -1,0 +1,19 @@
+// Error plumbing and version of the C ABI (include/dropdec.h).
+#include <string>
+
+#include "dd_common.cuh"
+
+namespace dd {
+static thread_local std::string g_last_error;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+}  // namespace dd
+
+extern "C" int dd_version(void) { return 100; }  // 0.1.0
+extern "C" const char* dd_last_error(void) { return dd::g_last_error.c_str(); }

@@ -1,0 +1,379 @@
+// (3) Decode attention for M masked contexts over ONE shared prefix KV cache.
+// Replaces the K+1 KV deep copies and the K+1 masked single-query SDPA calls of the reference
+// (models/llava.py:292,343 and :294-303,350-359), see include/dropdec.h.
+//
+// HBM-bound design (algorithmic bytes per sequence/layer/pass = 2*S*H_kv*D*2):
+//   grid = (kv splits, H_kv, B); a CTA streams its slice of K and V exactly once through a
+//   3-stage cp.async ring (128-bit, fully coalesced: a kv-head's rows are contiguous) into
+//   XOR-swizzled shared memory and scores it against ALL R = M * (H/H_kv) query rows of that
+//   (sequence, kv head) -- members x GQA group -- with mma.sync m16n8k16 (queries are the M=16
+//   operand, 16 keys per warp per tile).  Member m's visual-token bitmask is applied to the score
+//   fragments in registers; masked keys get -inf exactly like the reference's additive
+//   finfo.min mask (their softmax weight is exactly 0).
+//   P is split into bf16 hi + lo parts so that P.V is accurate to ~2^-17 relative: the result is
+//   then independent of the online-softmax rescaling order and matches an fp32 softmax.
+//   Split-KV partials (m, l, unnormalised O) go to a workspace; the merge kernel folds in each
+//   member's own new-token row (k_new / v_new, never written to the cache before the vote).
+#include "dd_common.cuh"
+
+namespace dd {
+
+constexpr int kAttnWarps = 4;
+constexpr int kAttnThreads = kAttnWarps * 32;
+constexpr int kTileKeys = 16 * kAttnWarps;  // 64 keys per pipeline stage
+constexpr int kStages = 3;
+constexpr int kMaxMaskWords = 256;  // n_vis <= 8192
+
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+struct AttnParams {
+  const __nv_bfloat16 *q, *k_cache, *v_cache;
+  const int32_t *seq_lens, *vis_start;
+  const uint32_t* bitmask;
+  float *part_o, *part_ml;  // [B,H_kv,splits,R,D], [B,H_kv,splits,R,2]
+  int B, M, H, H_kv, S_max, n_vis, mask_words, num_splits;
+  float scale_log2;  // scale * log2(e)
+};
+
+// smem row = one key/query row of D bf16 = D/8 chunks of 16 B; chunk c of row r lives at
+// physical chunk c ^ (r & 7): ldmatrix's 8 row addresses then hit 8 distinct 16-byte bank groups.
+template <int D>
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {
+  return (uint32_t)(row * (D * 2) + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int D, int QT>
+__global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnParams p) {
+  constexpr int CH = D / 8;            // 16-byte chunks per row
+  constexpr int ROW_B = D * 2;         // bytes per row
+  constexpr int TILE_B = kTileKeys * ROW_B;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sK = smem;                           // [kStages][64][D]
+  uint8_t* sV = smem + kStages * TILE_B;        // [kStages][64][D]
+  uint8_t* sQ = smem + 2 * kStages * TILE_B;    // [16*QT][D]
+  uint32_t* sMask = reinterpret_cast<uint32_t*>(sQ + 16 * QT * ROW_B);  // [M][mask_words]
+
+  const int split = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int G = p.H / p.H_kv, R = p.M * G;
+  const int S = p.seq_lens[b];
+  const int vis0 = p.vis_start ? p.vis_start[b] : 0;
+  const int vis1 = p.bitmask ? vis0 + p.n_vis : vis0;  // empty span when unmasked
+
+  // this CTA's key range
+  const int per = ((S + p.num_splits - 1) / p.num_splits + kTileKeys - 1) / kTileKeys * kTileKeys;
+  const int k_beg = split * per;
+  const int k_end = min(S, k_beg + per);
+  const int ntiles = k_end > k_beg ? (k_end - k_beg + kTileKeys - 1) / kTileKeys : 0;
+
+  const __nv_bfloat16* Kg = p.k_cache + ((size_t)b * p.H_kv + hkv) * (size_t)p.S_max * D;
+  const __nv_bfloat16* Vg = p.v_cache + ((size_t)b * p.H_kv + hkv) * (size_t)p.S_max * D;
+
+  auto load_tile = [&](int tile, int stage) {
+    const int key0 = k_beg + tile * kTileKeys;
+    const uint32_t kb = smem_u32(sK + stage * TILE_B), vb = smem_u32(sV + stage * TILE_B);
+#pragma unroll
+    for (int i = 0; i < kTileKeys * CH / kAttnThreads; ++i) {
+      const int idx = i * kAttnThreads + tid;
+      const int row = idx / CH, c = idx % CH;
+      const int key = min(key0 + row, S - 1);  // clamp the tail: rows >= k_end are masked later
+      cp_async_16(kb + swz<D>(row, c), Kg + (size_t)key * D + c * 8);
+      cp_async_16(vb + swz<D>(row, c), Vg + (size_t)key * D + c * 8);
+    }
+  };
+
+  // ---- prologue: start the ring, stage Q and the member bitmasks -------------------------------
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (s < ntiles) load_tile(s, s);
+    cp_async_commit();
+  }
+  for (int idx = tid; idx < 16 * QT * CH; idx += kAttnThreads) {
+    const int r = idx / CH, c = idx % CH;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < R) {
+      const int m = r / G, h = hkv * G + (r % G);
+      v = *reinterpret_cast<const uint4*>(p.q + (((size_t)b * p.M + m) * p.H + h) * D + c * 8);
+    }
+    *reinterpret_cast<uint4*>(sQ + swz<D>(r, c)) = v;
+  }
+  if (p.bitmask)
+    for (int idx = tid; idx < p.M * p.mask_words; idx += kAttnThreads)
+      sMask[idx] = p.bitmask[(size_t)b * p.M * p.mask_words + idx];
+
+  float o[QT][D / 8][4];
+  float m_run[QT][2], l_run[QT][2];
+#pragma unroll
+  for (int qt = 0; qt < QT; ++qt) {
+    m_run[qt][0] = m_run[qt][1] = -INFINITY;
+    l_run[qt][0] = l_run[qt][1] = 0.f;
+#pragma unroll
+    for (int n = 0; n < D / 8; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[qt][n][c] = 0.f;
+  }
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    cp_async_wait<kStages - 2>();
+    __syncthreads();  // tile `tile` landed for everyone; everyone is done with the stage refilled next
+    {
+      const int nt = tile + kStages - 1;
+      if (nt < ntiles) load_tile(nt, nt % kStages);
+      cp_async_commit();
+    }
+    const int stage = tile % kStages;
+    const uint32_t kb = smem_u32(sK + stage * TILE_B), vb = smem_u32(sV + stage * TILE_B);
+    const int key0 = k_beg + tile * kTileKeys + warp * 16;  // this warp's 16 keys
+    if (key0 >= k_end) continue;                            // warp-uniform
+    const bool need_mask = (key0 + 16 > k_end) || (key0 < vis1 && key0 + 16 > vis0);
+
+#pragma unroll
+    for (int qt = 0; qt < QT; ++qt) {
+      // ---- S = Q K^T for 16 query rows x 16 keys --------------------------------------------
+      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks) {
+        uint32_t a[4], kf[4];
+        ldmatrix_x4(a, smem_u32(sQ) + swz<D>(qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)));
+        ldmatrix_x4(kf, kb + swz<D>(warp * 16 + (lane & 7) + ((lane >> 4) << 3), 2 * ks + ((lane >> 3) & 1)));
+        mma_bf16_16816(s[0], a[0], a[1], a[2], a[3], kf[0], kf[1]);
+        mma_bf16_16816(s[1], a[0], a[1], a[2], a[3], kf[2], kf[3]);
+      }
+      // ---- scale, mask (registers), online softmax ---------------------------------------------
+      // fragment: s[j][0..1] -> row g, keys 8j+2t,+1 ; s[j][2..3] -> row g+8
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[j][c] *= p.scale_log2;
+      if (need_mask) {
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const int r = qt * 16 + g + hr * 8;
+          const uint32_t* mw = sMask + (r < R ? r / G : 0) * p.mask_words;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int key = key0 + 8 * j + 2 * t + e;
+              bool dead = key >= k_end;
+              const int vp = key - vis0;
+              if (key < vis1 && vp >= 0) dead |= (mw[vp >> 5] >> (vp & 31)) & 1u;
+              if (dead) s[j][hr * 2 + e] = -INFINITY;
+            }
+        }
+      }
+      float alpha[2];
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        float mx = fmaxf(fmaxf(s[0][hr * 2], s[0][hr * 2 + 1]), fmaxf(s[1][hr * 2], s[1][hr * 2 + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run[qt][hr], mx);
+        const float m_safe = m_new == -INFINITY ? 0.f : m_new;  // all keys masked so far
+        alpha[hr] = exp2f(m_run[qt][hr] - m_safe);
+        m_run[qt][hr] = m_new;
+        float rs = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pv = exp2f(s[j][hr * 2 + e] - m_safe);
+            s[j][hr * 2 + e] = pv;
+            rs += pv;
+          }
+        l_run[qt][hr] = l_run[qt][hr] * alpha[hr] + rs;  // per-thread partial; quad-reduced at the end
+      }
+      // ---- O = alpha * O + P V with P = P_hi + P_lo (both bf16) -----------------------------
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const float p0 = s[j][hr * 2], p1 = s[j][hr * 2 + 1];
+          const float h0 = bf16_round(p0), h1 = bf16_round(p1);
+          ph[j * 2 + hr] = pack_bf16x2(h0, h1);  // a0a1: row g keys 2t.. (j=0) | a2a3: row g+8 | a4a5: j=1 ...
+          pl[j * 2 + hr] = pack_bf16x2(p0 - h0, p1 - h1);
+        }
+#pragma unroll
+      for (int n = 0; n < D / 8; ++n) {
+        o[qt][n][0] *= alpha[0];
+        o[qt][n][1] *= alpha[0];
+        o[qt][n][2] *= alpha[1];
+        o[qt][n][3] *= alpha[1];
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < D / 16; ++n2) {
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, vb + swz<D>(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * n2 + (lane >> 4)));
+        mma_bf16_16816(o[qt][2 * n2], ph[0], ph[1], ph[2], ph[3], vf[0], vf[1]);
+        mma_bf16_16816(o[qt][2 * n2 + 1], ph[0], ph[1], ph[2], ph[3], vf[2], vf[3]);
+        mma_bf16_16816(o[qt][2 * n2], pl[0], pl[1], pl[2], pl[3], vf[0], vf[1]);
+        mma_bf16_16816(o[qt][2 * n2 + 1], pl[0], pl[1], pl[2], pl[3], vf[2], vf[3]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // ring is idle: reuse it for the cross-warp merge
+
+  // ---- merge the 4 warps (disjoint key subsets) and write the split partial ---------------------
+  float* sO = reinterpret_cast<float*>(smem);                       // [warps][16*QT][D]
+  float* sML = sO + kAttnWarps * 16 * QT * D;                        // [warps][16*QT][2]
+#pragma unroll
+  for (int qt = 0; qt < QT; ++qt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      float l = l_run[qt][hr];
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      const int r = qt * 16 + g + hr * 8;
+      if (t == 0) {
+        sML[(warp * 16 * QT + r) * 2] = m_run[qt][hr];
+        sML[(warp * 16 * QT + r) * 2 + 1] = l;
+      }
+#pragma unroll
+      for (int n = 0; n < D / 8; ++n) {
+        float* dst = sO + ((size_t)(warp * 16 * QT + r)) * D + n * 8 + 2 * t;
+        dst[0] = o[qt][n][hr * 2];
+        dst[1] = o[qt][n][hr * 2 + 1];
+      }
+    }
+  __syncthreads();
+  const size_t pbase = (((size_t)b * p.H_kv + hkv) * p.num_splits + split) * R;
+  for (int idx = tid; idx < R * D; idx += kAttnThreads) {
+    const int r = idx / D, dcol = idx % D;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) mx = fmaxf(mx, sML[(w * 16 * QT + r) * 2]);
+    const float ms = mx == -INFINITY ? 0.f : mx;
+    float acc = 0.f, l = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) {
+      const float f = exp2f(sML[(w * 16 * QT + r) * 2] - ms);
+      acc += f * sO[((size_t)(w * 16 * QT + r)) * D + dcol];
+      l += f * sML[(w * 16 * QT + r) * 2 + 1];
+    }
+    p.part_o[(pbase + r) * D + dcol] = acc;
+    if (dcol == 0) {
+      p.part_ml[(pbase + r) * 2] = mx;
+      p.part_ml[(pbase + r) * 2 + 1] = l;
+    }
+  }
+}
+
+// out[b,m,h,:] = merge(split partials, own new-token row).  One CTA of D threads per (b,m,h).
+template <int D>
+__global__ void __launch_bounds__(D) attn_merge_kernel(const AttnParams p, const __nv_bfloat16* __restrict__ k_new,
+                                                       const __nv_bfloat16* __restrict__ v_new,
+                                                       __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_part[D / 32];
+  const int h = blockIdx.x, m = blockIdx.y, b = blockIdx.z, d = threadIdx.x;
+  const int G = p.H / p.H_kv, hkv = h / G, r = m * G + (h % G), R = p.M * G;
+  const size_t qoff = (((size_t)b * p.M + m) * p.H + h) * D;
+  const size_t kvoff = (((size_t)b * p.M + m) * p.H_kv + hkv) * D;
+  // score of the member's own new token (always attended: it is the query position itself)
+  float dot = __bfloat162float(p.q[qoff + d]) * __bfloat162float(k_new[kvoff + d]);
+  dot = warp_sum(dot);
+  if ((d & 31) == 0) s_part[d >> 5] = dot;
+  __syncthreads();
+  float s_self = 0.f;
+#pragma unroll
+  for (int w = 0; w < D / 32; ++w) s_self += s_part[w];
+  s_self *= p.scale_log2;
+
+  const size_t pbase = (((size_t)b * p.H_kv + hkv) * p.num_splits) * R + r;
+  float mx = s_self;
+  for (int s = 0; s < p.num_splits; ++s) mx = fmaxf(mx, p.part_ml[(pbase + (size_t)s * R) * 2]);
+  const float f_self = exp2f(s_self - mx);
+  float acc = f_self * __bfloat162float(v_new[kvoff + d]);
+  float l = f_self;
+  for (int s = 0; s < p.num_splits; ++s) {
+    const size_t i = pbase + (size_t)s * R;
+    const float f = exp2f(p.part_ml[i * 2] - mx);
+    acc += f * p.part_o[i * D + d];
+    l += f * p.part_ml[i * 2 + 1];
+  }
+  out[qoff + d] = __float2bfloat16_rn(acc / l);
+}
+
+template <int D, int QT>
+static size_t attn_smem_bytes(int M, int mask_words) {
+  const size_t ring = 2ull * kStages * kTileKeys * D * 2;
+  const size_t merge = (size_t)kAttnWarps * 16 * QT * (D + 2) * sizeof(float);
+  const size_t main_b = ring + 16ull * QT * D * 2 + (size_t)M * mask_words * 4;
+  return main_b > merge ? main_b : merge;
+}
+
+template <int D, int QT>
+static int launch_attn(const AttnParams& p, const void* k_new, const void* v_new, void* out, cudaStream_t st) {
+  const size_t smem = attn_smem_bytes<D, QT>(p.M, p.bitmask ? p.mask_words : 0);
+  DD_CHECK_CUDA(cudaFuncSetAttribute(attn_partial_kernel<D, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  attn_partial_kernel<D, QT><<<dim3(p.num_splits, p.H_kv, p.B), kAttnThreads, smem, st>>>(p);
+  DD_CHECK_LAUNCH();
+  attn_merge_kernel<D><<<dim3(p.H, p.M, p.B), D, 0, st>>>(p, (const __nv_bfloat16*)k_new,
+                                                          (const __nv_bfloat16*)v_new, (__nv_bfloat16*)out);
+  DD_CHECK_LAUNCH();
+  return DD_OK;
+}
+
+}  // namespace dd
+
+extern "C" size_t dd_attention_workspace_bytes(int B, int M, int H, int D, int num_splits) {
+  // part_o [B,H_kv,splits,R,D] + part_ml [..,2] with H_kv * R = M * H
+  return (size_t)B * M * H * num_splits * (D + 2) * sizeof(float);
+}
+
+extern "C" int dd_decode_attention(const void* q, const void* k_new, const void* v_new, const void* k_cache,
+                                   const void* v_cache, const int32_t* seq_lens, const int32_t* vis_start,
+                                   const uint32_t* bitmask, int B, int M, int H, int H_kv, int D, int S_max,
+                                   int n_vis, int mask_words, float scale, int num_splits, void* out,
+                                   void* workspace, size_t workspace_bytes, dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(q && k_new && v_new && k_cache && v_cache && seq_lens && out && workspace,
+               "dd_decode_attention: null pointer");
+  DD_CHECK_ARG(D == 64 || D == 128, "dd_decode_attention: D=%d unsupported (64 or 128)", D);
+  DD_CHECK_ARG(H_kv >= 1 && H % H_kv == 0, "dd_decode_attention: H=%d not a multiple of H_kv=%d", H, H_kv);
+  DD_CHECK_ARG(M >= 1 && M <= DD_MAX_MEMBERS && M * (H / H_kv) <= 32,
+               "dd_decode_attention: M*(H/H_kv)=%d exceeds 32 query rows per kv head", M * (H / H_kv));
+  DD_CHECK_ARG(num_splits >= 1 && num_splits <= 256, "dd_decode_attention: num_splits=%d out of [1,256]",
+               num_splits);
+  DD_CHECK_ARG(!bitmask || (vis_start && mask_words * 32 >= n_vis && mask_words <= kMaxMaskWords),
+               "dd_decode_attention: bitmask needs vis_start and n_vis <= 32*mask_words <= %d",
+               32 * kMaxMaskWords);
+  if (workspace_bytes < dd_attention_workspace_bytes(B, M, H, D, num_splits)) {
+    set_error("dd_decode_attention: workspace %zu < %zu bytes", workspace_bytes,
+              dd_attention_workspace_bytes(B, M, H, D, num_splits));
+    return DD_ERR_WORKSPACE;
+  }
+  if (B == 0) return DD_OK;
+  AttnParams p{};
+  p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
+  p.seq_lens = seq_lens; p.vis_start = vis_start; p.bitmask = bitmask;
+  p.part_o = (float*)workspace;
+  p.part_ml = p.part_o + (size_t)B * M * H * num_splits * D;
+  p.B = B; p.M = M; p.H = H; p.H_kv = H_kv; p.S_max = S_max; p.n_vis = n_vis; p.mask_words = mask_words;
+  p.num_splits = num_splits;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const int R = M * (H / H_kv);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 128) return R <= 16 ? launch_attn<128, 1>(p, k_new, v_new, out, st) : launch_attn<128, 2>(p, k_new, v_new, out, st);
+  return R <= 16 ? launch_attn<64, 1>(p, k_new, v_new, out, st) : launch_attn<64, 2>(p, k_new, v_new, out, st);
+}

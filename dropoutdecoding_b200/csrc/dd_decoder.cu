@@ -1,0 +1,181 @@
+// Decoder support kernels for the single-token forwards of the ensemble (RMSNorm, RoPE + member
+// staging, embedding gather, winner commit, step bookkeeping).  They follow the HF Llama decoder
+// the reference calls through `self.language_model(...)` (models/llava.py:294-303,350-359;
+// models/llama.py:27-47).  All are small and latency-bound; the weight-streaming GEMM lives in
+// dd_skinny_gemm.cu and the attention in dd_attention.cu.
+#include "dd_common.cuh"
+
+namespace dd {
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm: y = bf16( bf16(x * rsqrt(mean(x^2) + eps)) * w )   (LlamaRMSNorm rounding points)
+// ---------------------------------------------------------------------------------------------
+constexpr int kNormThreads = 256;
+
+__global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const __nv_bfloat16* __restrict__ w, int d,
+                                                              float eps, __nv_bfloat16* __restrict__ y) {
+  __shared__ float s_part[kNormThreads / 32];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)row * d);
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+  uint4* y4 = reinterpret_cast<uint4*>(y + (size_t)row * d);
+  const int nvec = d / 8;
+  float ss = 0.f;
+  for (int j = tid; j < nvec; j += kNormThreads) {
+    const uint4 v = x4[j];
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = bf16x2_to_float2(u[k]);
+      ss = fmaf(f.x, f.x, ss);
+      ss = fmaf(f.y, f.y, ss);
+    }
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) s_part[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < kNormThreads / 32; ++k) tot += s_part[k];
+  const float rstd = rsqrtf(tot / (float)d + eps);
+  for (int j = tid; j < nvec; j += kNormThreads) {
+    const uint4 v = x4[j], g = w4[j];
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w}, gw[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = bf16x2_to_float2(u[k]), ww = bf16x2_to_float2(gw[k]);
+      o[k] = pack_bf16x2(bf16_round(f.x * rstd) * ww.x, bf16_round(f.y * rstd) * ww.y);
+    }
+    y4[j] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoPE (rotate-half) + member staging.  One CTA per (b*M + m) row.
+// ---------------------------------------------------------------------------------------------
+__global__ void rope_stage_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_tab,
+                                  const float* __restrict__ sin_tab, const int32_t* __restrict__ seq_lens,
+                                  int M, int H, int H_kv, int D, __nv_bfloat16* __restrict__ q_out,
+                                  __nv_bfloat16* __restrict__ k_new, __nv_bfloat16* __restrict__ v_new) {
+  const int row = blockIdx.x;  // b*M + m
+  const int b = row / M;
+  const int pos = seq_lens[b];
+  const int half = D / 2;
+  const __nv_bfloat16* src = qkv + (size_t)row * (H + 2 * H_kv) * D;
+  const float* c = cos_tab + (size_t)pos * half;
+  const float* s = sin_tab + (size_t)pos * half;
+  // q and k heads: pairs (i, i + D/2)
+  for (int idx = threadIdx.x; idx < (H + H_kv) * half; idx += blockDim.x) {
+    const int head = idx / half, i = idx % half;
+    const float x1 = __bfloat162float(src[head * D + i]);
+    const float x2 = __bfloat162float(src[head * D + i + half]);
+    const float o1 = x1 * c[i] - x2 * s[i];
+    const float o2 = x2 * c[i] + x1 * s[i];
+    __nv_bfloat16* dst = head < H ? q_out + ((size_t)row * H + head) * D
+                                  : k_new + ((size_t)row * H_kv + (head - H)) * D;
+    dst[i] = __float2bfloat16_rn(o1);
+    dst[i + half] = __float2bfloat16_rn(o2);
+  }
+  for (int idx = threadIdx.x; idx < H_kv * D; idx += blockDim.x)
+    v_new[(size_t)row * H_kv * D + idx] = src[(size_t)(H + H_kv) * D + idx];
+}
+
+__global__ void embed_gather_kernel(const uint4* __restrict__ embed, const int32_t* __restrict__ token, int M,
+                                    int dvec, uint4* __restrict__ x) {
+  const int row = blockIdx.x;  // b*M + m
+  const int t = token[row / M];
+  for (int j = threadIdx.x; j < dvec; j += blockDim.x) x[(size_t)row * dvec + j] = embed[(size_t)t * dvec + j];
+}
+
+__global__ void step_advance_kernel(const int32_t* __restrict__ token, int32_t* tokens_out, int max_steps,
+                                    int32_t* seq_lens, int32_t* step, int B) {
+  const int st = *step;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    if (tokens_out && st < max_steps) tokens_out[(size_t)b * max_steps + st] = token[b];
+    seq_lens[b] += 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *step = st + 1;
+}
+
+// winner's new-token K/V rows of every layer -> cache row seq_lens[b].  grid (L, B), 16B per thread.
+__global__ void commit_winner_kernel(const uint4* __restrict__ k_new, const uint4* __restrict__ v_new,
+                                     const int32_t* __restrict__ winner, const int32_t* __restrict__ seq_lens,
+                                     uint4* __restrict__ k_cache, uint4* __restrict__ v_cache, int B, int M,
+                                     int H_kv, int dvec, int S_max) {
+  const int l = blockIdx.x, b = blockIdx.y;
+  const int w = winner[b], pos = seq_lens[b];
+  if (pos >= S_max) return;
+  const size_t src = (((size_t)l * B + b) * M + w) * H_kv * dvec;
+  for (int idx = threadIdx.x; idx < H_kv * dvec; idx += blockDim.x) {
+    const int h = idx / dvec, j = idx % dvec;
+    const size_t dst = ((((size_t)l * B + b) * H_kv + h) * S_max + pos) * dvec + j;
+    k_cache[dst] = k_new[src + idx];
+    v_cache[dst] = v_new[src + idx];
+  }
+}
+
+}  // namespace dd
+
+extern "C" int dd_rmsnorm(const void* x, const void* w, int M, int d, float eps, void* y, dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(x && w && y, "dd_rmsnorm: null pointer");
+  DD_CHECK_ARG(M >= 0 && d > 0 && d % 8 == 0, "dd_rmsnorm: d=%d must be a positive multiple of 8", d);
+  if (M == 0) return DD_OK;
+  rmsnorm_kernel<<<M, kNormThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                                               d, eps, (__nv_bfloat16*)y);
+  DD_CHECK_LAUNCH();
+  return DD_OK;
+}
+
+extern "C" int dd_rope_stage(const void* qkv, const float* cos_tab, const float* sin_tab,
+                             const int32_t* seq_lens, int B, int M, int H, int H_kv, int D, void* q_out,
+                             void* k_new, void* v_new, dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(qkv && cos_tab && sin_tab && seq_lens && q_out && k_new && v_new, "dd_rope_stage: null pointer");
+  DD_CHECK_ARG(D % 2 == 0 && H >= 1 && H_kv >= 1, "dd_rope_stage: bad head shape");
+  if (B * M == 0) return DD_OK;
+  rope_stage_kernel<<<B * M, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)qkv, cos_tab, sin_tab, seq_lens, M, H, H_kv, D, (__nv_bfloat16*)q_out,
+      (__nv_bfloat16*)k_new, (__nv_bfloat16*)v_new);
+  DD_CHECK_LAUNCH();
+  return DD_OK;
+}
+
+extern "C" int dd_embed_gather(const void* embed, const int32_t* token, int B, int M, int d, void* x,
+                               dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(embed && token && x, "dd_embed_gather: null pointer");
+  DD_CHECK_ARG(d % 8 == 0, "dd_embed_gather: d=%d must be a multiple of 8", d);
+  if (B * M == 0) return DD_OK;
+  embed_gather_kernel<<<B * M, 128, 0, (cudaStream_t)stream>>>((const uint4*)embed, token, M, d / 8, (uint4*)x);
+  DD_CHECK_LAUNCH();
+  return DD_OK;
+}
+
+extern "C" int dd_step_advance(const int32_t* token, int32_t* tokens_out, int max_steps, int32_t* seq_lens,
+                               int32_t* step, int B, dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(token && seq_lens && step, "dd_step_advance: null pointer");
+  if (B == 0) return DD_OK;
+  step_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(token, tokens_out, max_steps, seq_lens, step, B);
+  DD_CHECK_LAUNCH();
+  return DD_OK;
+}
+
+extern "C" int dd_commit_winner(const void* k_new_all, const void* v_new_all, const int32_t* winner,
+                                const int32_t* seq_lens, void* k_cache_all, void* v_cache_all, int L, int B,
+                                int M, int H_kv, int D, int S_max, dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(k_new_all && v_new_all && winner && seq_lens && k_cache_all && v_cache_all,
+               "dd_commit_winner: null pointer");
+  DD_CHECK_ARG(D % 8 == 0, "dd_commit_winner: D=%d must be a multiple of 8", D);
+  if (L * B == 0) return DD_OK;
+  commit_winner_kernel<<<dim3(L, B), 128, 0, (cudaStream_t)stream>>>(
+      (const uint4*)k_new_all, (const uint4*)v_new_all, winner, seq_lens, (uint4*)k_cache_all,
+      (uint4*)v_cache_all, B, M, H_kv, D / 8, S_max);
+  DD_CHECK_LAUNCH();
+  return DD_OK;
+}

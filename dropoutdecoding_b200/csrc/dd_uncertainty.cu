@@ -1,0 +1,616 @@
+// (1) Visual-token uncertainty stage on the 5th-gen tensor cores.
+// Replaces lm_head over the visual rows + get_image_logits + get_topk_token_id +
+// calculate_vision_uncertainty (models/llava.py:412-441, 710-756), see include/dropdec.h.
+//
+// logits[i,v] = <h_vis[i,:], w_lm[v,:]> is a [n_vis x vocab] GEMM (151 GFLOP per LLaVA-1.5 image)
+// whose result the reference materialises in fp32 (74 MB + >=6 same-size temporaries).  Here the
+// logits only ever exist as TMEM accumulators:
+//
+//   work item = (image, vocab strip of BN=96 columns); the CTA holds the strip for ALL visual rows
+//   of the image at once -- NUM_MT row tiles of 128 -> NUM_MT*96 <= 480 of the 512 TMEM columns.
+//   That is what makes the epistemic term single-sweep: it needs p_avg[v] = mean_i p[i,v], a
+//   column reduction over every row of the image, before sum_v p[i,v] log(p_avg[v]) can be formed.
+//
+//   warp 4   : TMA producer.  Per k-block (64 bf16 = one 128B-swizzle row) it loads the W strip tile
+//              [96 x 64] and NUM_MT activation tiles [128 x 64] into a ring of 16 KB slots.
+//   warp 5   : MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128 N=96 K=16,
+//              both operands K-major SWIZZLE_128B straight from the TMA-written slots; slots are
+//              released with tcgen05.commit.
+//   warps 0-3: epilogue.  tcgen05.ld 32x32b: one thread = one visual row, so softmax statistics are
+//              thread-local; the column sums are a butterfly over the warp plus 4 smem rows.
+//
+// Two sweeps of the same pipeline (the row normaliser Z_i must be complete before p exists):
+//   STATS : per row running max / sum-exp and the top-k ids                     (sweep 1)
+//   FUSED : p = exp(l - m)/Z;  A_i = sum p log(p+eps), Q_i = sum (p-1/V)^2, column sums ->
+//           log(p_avg+eps) -> C_i = sum p log(p_avg+eps)                        (sweep 2)
+//   finalize: alea = -A, epi = A - C, var = Q/(V-1).
+// Algorithmic FLOPs = 2*n_vis*d*V per image, counted once although two sweeps run.
+#include <cuda.h>
+
+#include "dd_common.cuh"
+
+namespace dd {
+
+constexpr int BM = 128, BN = 96, BK = 64, UMMA_K = 16;
+constexpr int kSlotBytes = BM * BK * 2;  // 16 KB: one [128 x 64] bf16 tile (W tile uses 12 KB of it)
+constexpr int kNumSlots = 13;
+constexpr int kEpiThreads = 128;
+constexpr int kUncThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kEps = 1e-10f;  // models/llava.py:735,739
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major) | SBO>>4 [32,46) = 8 rows * 128 B |
+// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, A/B K-major,
+// N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  __syncwarp();  // .sync.aligned: rows past n_vis skip the math, so reconverge first
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+struct UncParams {
+  int n_images, n_vis, d, vocab, topk, round_bf16;
+  int n_strips, parts;     // strips per image; CTAs (partials) per image
+  float* part_stats;       // [img][parts][n_vis][2]      (m, z)
+  float* part_topv;        // [img][parts][n_vis][topk]
+  int32_t* part_topi;      // [img][parts][n_vis][topk]
+  const float* row_stats;  // [img][n_vis][2]             (m, 1/Z)  FUSED input
+  float* part_acq;         // [img][parts][n_vis][3]      (A, Q, C) FUSED output
+};
+
+enum { MODE_STATS = 0, MODE_FUSED = 1 };
+
+template <int NUM_MT, int MODE, int KT>
+__global__ void __launch_bounds__(kUncThreads, 1)
+uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                   const UncParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B tiles (the dynamic smem base is only 16-byte aligned by contract)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kNumSlots * kSlotBytes);
+  // bars: full[kNumSlots] | empty[kNumSlots] | tmem_full | tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumSlots + 2);
+  float* s_col = reinterpret_cast<float*>(tmem_slot + 4);  // [4][BN]
+  float* s_logp = s_col + 4 * BN;                            // [BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.y, part = blockIdx.x;
+  const int spc = (p.n_strips + p.parts - 1) / p.parts;
+  const int strip_beg = part * spc;
+  const int strip_end = min(p.n_strips, strip_beg + spc);
+  const int num_kb = p.d / BK;
+
+  const uint32_t ring = smem_u32(smem);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kNumSlots;
+  const uint32_t bar_tfull = bar_full + 16 * kNumSlots, bar_tempty = bar_tfull + 8;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumSlots; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, kEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {  // TMEM: 512 columns, whole warp, then give the permit back
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int strip = strip_beg; strip < strip_end; ++strip) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+          mbar_expect_tx(bar_full + 8 * slot, BN * BK * 2);
+          tma_load_2d(ring + slot * kSlotBytes, &tmap_w, bar_full + 8 * slot, kb * BK, strip * BN);
+          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+#pragma unroll 1
+          for (int mt = 0; mt < NUM_MT; ++mt) {
+            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+            mbar_expect_tx(bar_full + 8 * slot, BM * BK * 2);
+            tma_load_3d(ring + slot * kSlotBytes, &tmap_a, bar_full + 8 * slot, kb * BK, mt * BM, img);
+            if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0, it = 0;
+      for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
+        mbar_wait(bar_tempty, (it & 1) ^ 1);  // epilogue has drained the accumulators
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * slot, phase);
+          tc_fence_after();
+          const int slot_b = slot;
+          const uint64_t b_desc = make_smem_desc(ring + slot * kSlotBytes);
+          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+#pragma unroll 1
+          for (int mt = 0; mt < NUM_MT; ++mt) {
+            mbar_wait(bar_full + 8 * slot, phase);
+            tc_fence_after();
+            const uint64_t a_desc = make_smem_desc(ring + slot * kSlotBytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+              umma_bf16(tmem_base + mt * BN, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (kb | k) != 0);
+            umma_commit(bar_empty + 8 * slot);  // A slot free once these MMAs retire
+            if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+          }
+          umma_commit(bar_empty + 8 * slot_b);  // W slot free after the last row tile used it
+        }
+        umma_commit(bar_tfull);  // strip accumulators complete
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 0-3) ===========================
+    const int tid = threadIdx.x;  // 0..127 = TMEM lane = row inside each 128-row tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float inv_v = 1.0f / (float)p.vocab;
+
+    float st_m[NUM_MT], st_z[NUM_MT];          // STATS: running max, sum-exp | FUSED: m, 1/Z
+    float acc_a[NUM_MT], acc_q[NUM_MT], acc_c[NUM_MT];
+    float topv[MODE == MODE_STATS ? NUM_MT : 1][KT];
+    int topi[MODE == MODE_STATS ? NUM_MT : 1][KT];
+#pragma unroll
+    for (int mt = 0; mt < NUM_MT; ++mt) {
+      const int row = mt * BM + tid;
+      acc_a[mt] = acc_q[mt] = acc_c[mt] = 0.f;
+      if (MODE == MODE_STATS) {
+        st_m[mt] = -INFINITY;
+        st_z[mt] = 0.f;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) { topv[mt][j] = -INFINITY; topi[mt][j] = 0x7fffffff; }
+      } else {
+        const bool ok = row < p.n_vis;
+        st_m[mt] = ok ? p.row_stats[((size_t)img * p.n_vis + row) * 2] : 0.f;
+        st_z[mt] = ok ? p.row_stats[((size_t)img * p.n_vis + row) * 2 + 1] : 0.f;
+      }
+    }
+
+    uint32_t it = 0;
+    for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
+      const int col0 = strip * BN;
+      mbar_wait(bar_tfull, it & 1);
+      tc_fence_after();
+
+      if (MODE == MODE_STATS) {
+#pragma unroll
+        for (int mt = 0; mt < NUM_MT; ++mt) {
+          const bool ok = mt * BM + tid < p.n_vis;
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            float v[32];
+            tmem_ld32(lane_addr + mt * BN + c * 32, v);
+            if (ok) {
+            const int cbase = col0 + c * 32;
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (p.round_bf16) v[i] = bf16_round(v[i]);
+              if (cbase + i >= p.vocab) v[i] = -INFINITY;
+              cmax = fmaxf(cmax, v[i]);
+            }
+            if (cmax > st_m[mt]) {
+              st_z[mt] *= exp2f((st_m[mt] - cmax) * kLog2e);
+              st_m[mt] = cmax;
+            }
+            float zs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              zs += exp2f((v[i] - st_m[mt]) * kLog2e);
+              if (v[i] > topv[mt][KT - 1]) {  // rare: insert into the sorted top-k list
+                topv[mt][KT - 1] = v[i];
+                topi[mt][KT - 1] = cbase + i;
+#pragma unroll
+                for (int j = KT - 1; j > 0; --j) {
+                  if (topv[mt][j] > topv[mt][j - 1]) {
+                    const float tv = topv[mt][j]; topv[mt][j] = topv[mt][j - 1]; topv[mt][j - 1] = tv;
+                    const int ti = topi[mt][j]; topi[mt][j] = topi[mt][j - 1]; topi[mt][j - 1] = ti;
+                  }
+                }
+              }
+            }
+            st_z[mt] += zs;
+            }
+          }
+        }
+      } else {
+        // ---- pass 1: p, A, Q and the column sums ------------------------------------------
+        float colsum[BN];
+#pragma unroll
+        for (int i = 0; i < BN; ++i) colsum[i] = 0.f;
+#pragma unroll
+        for (int mt = 0; mt < NUM_MT; ++mt) {
+          const bool ok = mt * BM + tid < p.n_vis;
+          const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            float v[32];
+            tmem_ld32(lane_addr + mt * BN + c * 32, v);
+            if (ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float x = v[i];
+                if (p.round_bf16) x = bf16_round(x);
+                float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
+                if (col0 + c * 32 + i >= p.vocab) pr = 0.f;  // padded vocab columns of the last strip
+                colsum[c * 32 + i] += pr;
+                acc_a[mt] = fmaf(pr, __logf(pr + kEps), acc_a[mt]);
+                const float dv = pr - inv_v;
+                acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
+              }
+            }
+          }
+        }
+        // ---- column sums over all rows of the image: warp butterfly, then 4 smem rows ---------
+#pragma unroll
+        for (int i = 0; i < BN; ++i) {
+          float s = colsum[i];
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          if (lane == (i & 31)) s_col[warp * BN + i] = s;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (tid < BN) {
+          const float tot = s_col[tid] + s_col[BN + tid] + s_col[2 * BN + tid] + s_col[3 * BN + tid];
+          s_logp[tid] = __logf(tot / (float)p.n_vis + kEps);  // log(p_avg + eps), models/llava.py:732-735
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        // ---- pass 2: C_i = sum_v p log(p_avg + eps) -------------------------------------------
+#pragma unroll
+        for (int mt = 0; mt < NUM_MT; ++mt) {
+          const bool ok = mt * BM + tid < p.n_vis;
+          const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            float v[32];
+            tmem_ld32(lane_addr + mt * BN + c * 32, v);
+            if (ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float x = v[i];
+                if (p.round_bf16) x = bf16_round(x);
+                float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
+                if (col0 + c * 32 + i >= p.vocab) pr = 0.f;
+                acc_c[mt] = fmaf(pr, s_logp[c * 32 + i], acc_c[mt]);
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // s_col / s_logp reusable
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty);  // accumulators may be overwritten by the next strip
+    }
+
+    // ---- per-CTA partials --------------------------------------------------------------------
+#pragma unroll
+    for (int mt = 0; mt < NUM_MT; ++mt) {
+      const int row = mt * BM + tid;
+      if (row >= p.n_vis) continue;
+      const size_t pr = ((size_t)img * p.parts + part) * p.n_vis + row;
+      if (MODE == MODE_STATS) {
+        p.part_stats[pr * 2] = st_m[mt];
+        p.part_stats[pr * 2 + 1] = st_z[mt];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+          if (j < p.topk) {
+            p.part_topv[pr * p.topk + j] = topv[mt][j];
+            p.part_topi[pr * p.topk + j] = topi[mt][j];
+          }
+        }
+      } else {
+        p.part_acq[pr * 3] = acc_a[mt];
+        p.part_acq[pr * 3 + 1] = acc_q[mt];
+        p.part_acq[pr * 3 + 2] = acc_c[mt];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// merge the per-CTA (m, z, top-k) partials of one row: row_stats = (m, 1/Z), ids sorted descending
+__global__ void stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats,
+                                      int32_t* __restrict__ topk_ids) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
+  if (row >= p.n_vis) return;
+  float m = -INFINITY;
+  for (int q = 0; q < p.parts; ++q)
+    m = fmaxf(m, p.part_stats[(((size_t)img * p.parts + q) * p.n_vis + row) * 2]);
+  float z = 0.f;
+  float tv[DD_MAX_TOPK];
+  int ti[DD_MAX_TOPK];
+  for (int j = 0; j < p.topk; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+  for (int q = 0; q < p.parts; ++q) {
+    const size_t pr = ((size_t)img * p.parts + q) * p.n_vis + row;
+    const float pm = p.part_stats[pr * 2];
+    if (pm > -INFINITY) z += p.part_stats[pr * 2 + 1] * exp2f((pm - m) * kLog2e);
+    for (int j = 0; j < p.topk; ++j) {
+      const float v = p.part_topv[pr * p.topk + j];
+      const int id = p.part_topi[pr * p.topk + j];
+      const int last = p.topk - 1;
+      if (v > tv[last] || (v == tv[last] && id < ti[last])) {
+        tv[last] = v; ti[last] = id;
+        for (int k = last; k > 0; --k) {
+          if (tv[k] > tv[k - 1] || (tv[k] == tv[k - 1] && ti[k] < ti[k - 1])) {
+            const float a = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = a;
+            const int b = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = b;
+          } else break;
+        }
+      }
+    }
+  }
+  row_stats[((size_t)img * p.n_vis + row) * 2] = m;
+  row_stats[((size_t)img * p.n_vis + row) * 2 + 1] = 1.0f / z;
+  for (int j = 0; j < p.topk; ++j) topk_ids[((size_t)img * p.n_vis + row) * p.topk + j] = ti[j];
+}
+
+__global__ void fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restrict__ alea,
+                                      float* __restrict__ var) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
+  if (row >= p.n_vis) return;
+  float a = 0.f, q = 0.f, c = 0.f;
+  for (int s = 0; s < p.parts; ++s) {
+    const size_t pr = ((size_t)img * p.parts + s) * p.n_vis + row;
+    a += p.part_acq[pr * 3];
+    q += p.part_acq[pr * 3 + 1];
+    c += p.part_acq[pr * 3 + 2];
+  }
+  const size_t o = (size_t)img * p.n_vis + row;
+  alea[o] = -a;                         // models/llava.py:739
+  epi[o] = a - c;                       // models/llava.py:735
+  var[o] = q / (float)(p.vocab - 1);    // torch.var (unbiased), models/llava.py:728
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+struct UncLayout {
+  int n_strips, parts;
+  size_t off_stats, off_topv, off_topi, off_rowstats, off_acq, total;
+};
+static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
+  UncLayout L;
+  L.n_strips = ceil_div(vocab, BN);
+  int parts = ceil_div(num_sms(), n_images > 0 ? n_images : 1);
+  L.parts = parts < 1 ? 1 : (parts > L.n_strips ? L.n_strips : parts);
+  const size_t rows = (size_t)n_images * L.parts * n_vis;
+  size_t o = 0;
+  L.off_stats = o; o = align_up(o + rows * 2 * sizeof(float), 256);
+  L.off_topv = o; o = align_up(o + rows * topk * sizeof(float), 256);
+  L.off_topi = o; o = align_up(o + rows * topk * sizeof(int32_t), 256);
+  L.off_rowstats = o; o = align_up(o + (size_t)n_images * n_vis * 2 * sizeof(float), 256);
+  L.off_acq = o; o = align_up(o + rows * 3 * sizeof(float), 256);
+  L.total = o;
+  return L;
+}
+
+constexpr size_t kUncSmem = 1024 + (size_t)kNumSlots * kSlotBytes + (2 * kNumSlots + 2) * 8 + 16 + 5 * BN * sizeof(float);
+
+template <int NUM_MT, int MODE, int KT>
+static int launch_unc(const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, cudaStream_t st) {
+  auto kern = uncertainty_kernel<NUM_MT, MODE, KT>;
+  DD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUncSmem));
+  kern<<<dim3(p.parts, p.n_images), kUncThreads, kUncSmem, st>>>(ta, tw, p);
+  DD_CHECK_LAUNCH();
+  return DD_OK;
+}
+
+template <int NUM_MT>
+static int launch_unc_mt(const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, int mode,
+                         cudaStream_t st) {
+  if (mode == MODE_FUSED) return launch_unc<NUM_MT, MODE_FUSED, 1>(ta, tw, p, st);
+  if (p.topk <= 5) return launch_unc<NUM_MT, MODE_STATS, 5>(ta, tw, p, st);
+  if (p.topk <= 10) return launch_unc<NUM_MT, MODE_STATS, 10>(ta, tw, p, st);
+  return launch_unc<NUM_MT, MODE_STATS, DD_MAX_TOPK>(ta, tw, p, st);
+}
+
+static int launch_unc_any(int num_mt, const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, int mode,
+                          cudaStream_t st) {
+  if (num_mt == 1) return launch_unc_mt<1>(ta, tw, p, mode, st);
+  if (num_mt <= 3) return launch_unc_mt<3>(ta, tw, p, mode, st);
+  return launch_unc_mt<5>(ta, tw, p, mode, st);
+}
+
+}  // namespace dd
+
+extern "C" size_t dd_uncertainty_workspace_bytes(int n_images, int n_vis, int vocab, int topk) {
+  if (n_images <= 0 || n_vis <= 0 || vocab <= 0 || topk <= 0) return 0;
+  return dd::unc_layout(n_images, n_vis, vocab, topk).total;
+}
+
+extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n_images, int n_vis, int d,
+                                      int vocab, int topk, int round_logits_bf16, float* epi, float* alea,
+                                      float* var, int32_t* topk_ids, void* workspace, size_t workspace_bytes,
+                                      dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(h_vis && w_lm && epi && alea && var && topk_ids && workspace, "dd_uncertainty_project: null pointer");
+  DD_CHECK_ARG(n_images >= 0 && n_vis >= 1 && n_vis <= 5 * BM, "dd_uncertainty_project: n_vis=%d out of [1,%d]",
+               n_vis, 5 * BM);
+  DD_CHECK_ARG(d >= BK && d % BK == 0, "dd_uncertainty_project: d=%d must be a multiple of %d", d, BK);
+  DD_CHECK_ARG(vocab >= 2, "dd_uncertainty_project: vocab=%d", vocab);
+  DD_CHECK_ARG(topk >= 1 && topk <= DD_MAX_TOPK && topk <= vocab, "dd_uncertainty_project: topk=%d out of [1,%d]",
+               topk, DD_MAX_TOPK);
+  DD_CHECK_ARG(((uintptr_t)h_vis & 15) == 0 && ((uintptr_t)w_lm & 15) == 0,
+               "dd_uncertainty_project: operands must be 16-byte aligned");
+  if (n_images == 0) return DD_OK;
+  const UncLayout L = unc_layout(n_images, n_vis, vocab, topk);
+  if (workspace_bytes < L.total) {
+    set_error("dd_uncertainty_project: workspace %zu < %zu bytes", workspace_bytes, L.total);
+    return DD_ERR_WORKSPACE;
+  }
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    set_error("dd_uncertainty_project: cuTensorMapEncodeTiled unavailable (driver too old?)");
+    return DD_ERR_CUDA;
+  }
+  CUtensorMap ta, tw;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)n_vis, (cuuint64_t)n_images};
+    const cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)n_vis * d * 2};
+    const cuuint32_t box[3] = {BK, BM, 1}, es[3] = {1, 1, 1};
+    const CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(h_vis), dims, strides, box,
+                              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(h_vis) failed: %d", (int)r); return DD_ERR_CUDA; }
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)vocab};
+    const cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+    const cuuint32_t box[2] = {BK, BN}, es[2] = {1, 1};
+    const CUresult r = encode(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_lm), dims, strides, box,
+                              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(w_lm) failed: %d", (int)r); return DD_ERR_CUDA; }
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  UncParams p{};
+  p.n_images = n_images; p.n_vis = n_vis; p.d = d; p.vocab = vocab; p.topk = topk; p.round_bf16 = round_logits_bf16;
+  p.n_strips = L.n_strips; p.parts = L.parts;
+  p.part_stats = reinterpret_cast<float*>(ws + L.off_stats);
+  p.part_topv = reinterpret_cast<float*>(ws + L.off_topv);
+  p.part_topi = reinterpret_cast<int32_t*>(ws + L.off_topi);
+  float* row_stats = reinterpret_cast<float*>(ws + L.off_rowstats);
+  p.row_stats = row_stats;
+  p.part_acq = reinterpret_cast<float*>(ws + L.off_acq);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int num_mt = ceil_div(n_vis, BM);
+  const dim3 fgrid(ceil_div(n_vis, 128), n_images);
+  int rc = launch_unc_any(num_mt, ta, tw, p, MODE_STATS, st);
+  if (rc) return rc;
+  stats_finalize_kernel<<<fgrid, 128, 0, st>>>(p, row_stats, topk_ids);
+  DD_CHECK_LAUNCH();
+  rc = launch_unc_any(num_mt, ta, tw, p, MODE_FUSED, st);
+  if (rc) return rc;
+  fused_finalize_kernel<<<fgrid, 128, 0, st>>>(p, epi, alea, var);
+  DD_CHECK_LAUNCH();
+  return DD_OK;
+}

@@ -1,0 +1,224 @@
+"""Torch-tensor front end of the C ABI (include/dropdec.h).
+
+Every function checks dtype / device / contiguity, passes raw device pointers and torch's current
+CUDA stream to libdropdec.so, and raises DropDecError on a non-zero return code.  Nothing here
+computes on the CPU and nothing falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DropDecError, check
+
+MASK_CUMULATIVE, MASK_INDEPENDENT, MASK_QUANTILE = 0, 1, 2
+AGG_VOTE, AGG_MEAN = 0, 1
+EPI_NONE, EPI_RESIDUAL, EPI_F32, EPI_SWIGLU = 0, 1, 2, 3
+MASK_MODES = {"cumulative": MASK_CUMULATIVE, "independent": MASK_INDEPENDENT, "quantile": MASK_QUANTILE}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise DropDecError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise DropDecError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise DropDecError(f"{name} must be contiguous")
+    return t
+
+
+def mask_words(n_vis: int) -> int:
+    return (n_vis + 31) // 32
+
+
+# --------------------------------------------------------------------------------------------
+def uncertainty_project(h_vis: torch.Tensor, w_lm: torch.Tensor, topk: int = 5, round_logits: bool = False,
+                        workspace: Optional[torch.Tensor] = None):
+    """h_vis bf16 [n_img, n_vis, d], w_lm bf16 [V, d] -> (epi, alea, var fp32 [n_img, n_vis], topk_ids int32)."""
+    L = _lib.load()
+    _need(h_vis, torch.bfloat16, "h_vis"); _need(w_lm, torch.bfloat16, "w_lm")
+    if h_vis.dim() == 2:
+        h_vis = h_vis[None]
+    n_img, n_vis, d = h_vis.shape
+    V = w_lm.shape[0]
+    if w_lm.shape[1] != d:
+        raise DropDecError("w_lm and h_vis disagree on d")
+    dev = h_vis.device
+    epi = torch.empty(n_img, n_vis, dtype=torch.float32, device=dev)
+    alea, var = torch.empty_like(epi), torch.empty_like(epi)
+    ids = torch.empty(n_img, n_vis, topk, dtype=torch.int32, device=dev)
+    need = L.dd_uncertainty_workspace_bytes(n_img, n_vis, V, topk)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    check(L.dd_uncertainty_project(_ptr(h_vis), _ptr(w_lm), n_img, n_vis, d, V, topk, int(round_logits),
+                                   _ptr(epi), _ptr(alea), _ptr(var), _ptr(ids), _ptr(workspace),
+                                   workspace.numel() * workspace.element_size(), _stream()),
+          "dd_uncertainty_project")
+    return epi, alea, var, ids
+
+
+def sample_masks(epi: torch.Tensor, topk_ids: Optional[torch.Tensor], y_init: Optional[torch.Tensor],
+                 probs: Sequence[float], mode: str = "cumulative", keep_relevant: bool = True,
+                 uniforms: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
+                 step: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                 n_masked: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """epi fp32 [B, n_vis] -> (bitmask uint32-as-int32 [B, K, words], n_masked int32 [B, K])."""
+    L = _lib.load()
+    _need(epi, torch.float32, "epi")
+    B, n_vis = epi.shape
+    K = len(probs)
+    words = mask_words(n_vis)
+    topk = 0
+    if keep_relevant:
+        if topk_ids is None or y_init is None:
+            raise DropDecError("keep_relevant needs topk_ids and y_init")
+        _need(topk_ids, torch.int32, "topk_ids"); _need(y_init, torch.int32, "y_init")
+        topk = topk_ids.shape[-1]
+    if uniforms is not None:
+        _need(uniforms, torch.float32, "uniforms")
+        if tuple(uniforms.shape) != (B, K, n_vis):
+            raise DropDecError(f"uniforms must be [{B},{K},{n_vis}]")
+    if out is None:
+        out = torch.empty(B, K, words, dtype=torch.int32, device=epi.device)
+    if n_masked is None:
+        n_masked = torch.empty(B, K, dtype=torch.int32, device=epi.device)
+    if step is not None:
+        _need(step, torch.int32, "step")
+    probs_c = (C.c_double * K)(*[float(p) for p in probs])
+    check(L.dd_sample_masks(_ptr(epi), _ptr(topk_ids) if keep_relevant else None, topk,
+                            _ptr(y_init) if keep_relevant else None, probs_c, K, _ptr(uniforms), seed, offset,
+                            _ptr(step), MASK_MODES[mode], int(keep_relevant), B, n_vis, _ptr(out), out.shape[-1],
+                            _ptr(n_masked), _stream()), "dd_sample_masks")
+    return out, n_masked
+
+
+def philox_uniform(seed: int, offset: int, n: int, device="cuda") -> torch.Tensor:
+    L = _lib.load()
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    check(L.dd_philox_uniform(seed, offset, n, _ptr(out), _stream()), "dd_philox_uniform")
+    return out
+
+
+def attention_workspace(B: int, M: int, H: int, D: int, num_splits: int, device) -> torch.Tensor:
+    L = _lib.load()
+    return torch.empty(max(L.dd_attention_workspace_bytes(B, M, H, D, num_splits), 1), dtype=torch.uint8,
+                       device=device)
+
+
+def decode_attention(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, k_cache: torch.Tensor,
+                     v_cache: torch.Tensor, seq_lens: torch.Tensor, vis_start: Optional[torch.Tensor],
+                     bitmask: Optional[torch.Tensor], n_vis: int, scale: float, num_splits: int = 1,
+                     out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B,M,H,D], k_new/v_new [B,M,H_kv,D], caches [B,H_kv,S_max,D] (bf16) -> out [B,M,H,D] bf16."""
+    L = _lib.load()
+    for t, n in ((q, "q"), (k_new, "k_new"), (v_new, "v_new"), (k_cache, "k_cache"), (v_cache, "v_cache")):
+        _need(t, torch.bfloat16, n)
+    _need(seq_lens, torch.int32, "seq_lens")
+    B, M, H, D = q.shape
+    H_kv, S_max = k_cache.shape[1], k_cache.shape[2]
+    words = 0
+    if bitmask is not None:
+        _need(bitmask, torch.int32, "bitmask"); _need(vis_start, torch.int32, "vis_start")
+        words = bitmask.shape[-1]
+    if out is None:
+        out = torch.empty_like(q)
+    if workspace is None:
+        workspace = attention_workspace(B, M, H, D, num_splits, q.device)
+    check(L.dd_decode_attention(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(k_cache), _ptr(v_cache), _ptr(seq_lens),
+                                _ptr(vis_start), _ptr(bitmask), B, M, H, H_kv, D, S_max, n_vis, words,
+                                float(scale), num_splits, _ptr(out), _ptr(workspace),
+                                workspace.numel() * workspace.element_size(), _stream()), "dd_decode_attention")
+    return out
+
+
+def commit_winner(k_new_all: torch.Tensor, v_new_all: torch.Tensor, winner: torch.Tensor, seq_lens: torch.Tensor,
+                  k_cache_all: torch.Tensor, v_cache_all: torch.Tensor) -> None:
+    """k_new_all [L,B,M,H_kv,D] -> caches [L,B,H_kv,S_max,D] at row seq_lens[b] of the winner member."""
+    L = _lib.load()
+    _need(k_new_all, torch.bfloat16, "k_new_all"); _need(k_cache_all, torch.bfloat16, "k_cache_all")
+    _need(v_new_all, torch.bfloat16, "v_new_all"); _need(v_cache_all, torch.bfloat16, "v_cache_all")
+    _need(winner, torch.int32, "winner"); _need(seq_lens, torch.int32, "seq_lens")
+    Ln, B, M, H_kv, D = k_new_all.shape
+    S_max = k_cache_all.shape[3]
+    check(L.dd_commit_winner(_ptr(k_new_all), _ptr(v_new_all), _ptr(winner), _ptr(seq_lens), _ptr(k_cache_all),
+                             _ptr(v_cache_all), Ln, B, M, H_kv, D, S_max, _stream()), "dd_commit_winner")
+
+
+def aggregate(logits: torch.Tensor, mode: str = "vote", want_logits: bool = False,
+              member_ids: Optional[torch.Tensor] = None, winner: Optional[torch.Tensor] = None,
+              token: Optional[torch.Tensor] = None, out_logits: Optional[torch.Tensor] = None):
+    """logits fp32 [B, K, V] -> (member_ids [B,K], winner [B], token [B], out_logits [B,V] | None)."""
+    L = _lib.load()
+    _need(logits, torch.float32, "logits")
+    B, K, V = logits.shape
+    dev = logits.device
+    member_ids = torch.empty(B, K, dtype=torch.int32, device=dev) if member_ids is None else member_ids
+    winner = torch.empty(B, dtype=torch.int32, device=dev) if winner is None else winner
+    token = torch.empty(B, dtype=torch.int32, device=dev) if token is None else token
+    if out_logits is None and (want_logits or mode == "mean"):
+        out_logits = torch.empty(B, V, dtype=torch.float32, device=dev)
+    check(L.dd_aggregate(_ptr(logits), B, K, V, AGG_VOTE if mode == "vote" else AGG_MEAN, _ptr(member_ids),
+                         _ptr(winner), _ptr(token), _ptr(out_logits), _stream()), "dd_aggregate")
+    return member_ids, winner, token, out_logits
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    L = _lib.load()
+    _need(x, torch.bfloat16, "x"); _need(w, torch.bfloat16, "w")
+    M, d = x.shape
+    out = torch.empty_like(x) if out is None else out
+    check(L.dd_rmsnorm(_ptr(x), _ptr(w), M, d, float(eps), _ptr(out), _stream()), "dd_rmsnorm")
+    return out
+
+
+def skinny_gemm(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_NONE, residual: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 [M,K] (M <= 32), w bf16 [N,K] ([2N,K] for SwiGLU) -> y [M,N] (fp32 for EPI_F32, else bf16)."""
+    L = _lib.load()
+    _need(x, torch.bfloat16, "x"); _need(w, torch.bfloat16, "w")
+    M, K = x.shape
+    N = w.shape[0] // 2 if epilogue == EPI_SWIGLU else w.shape[0]
+    if w.shape[1] != K:
+        raise DropDecError("skinny_gemm: x and w disagree on K")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if epilogue == EPI_F32 else torch.bfloat16, device=x.device)
+    if residual is not None:
+        _need(residual, torch.bfloat16, "residual")
+    check(L.dd_skinny_gemm(_ptr(x), _ptr(w), _ptr(residual), M, N, K, epilogue, _ptr(out), _stream()),
+          "dd_skinny_gemm")
+    return out
+
+
+def rope_stage(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_lens: torch.Tensor, B: int, M: int,
+               H: int, H_kv: int, D: int, q_out: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor) -> None:
+    L = _lib.load()
+    _need(qkv, torch.bfloat16, "qkv"); _need(cos, torch.float32, "cos"); _need(sin, torch.float32, "sin")
+    check(L.dd_rope_stage(_ptr(qkv), _ptr(cos), _ptr(sin), _ptr(seq_lens), B, M, H, H_kv, D, _ptr(q_out),
+                          _ptr(k_new), _ptr(v_new), _stream()), "dd_rope_stage")
+
+
+def embed_gather(embed: torch.Tensor, token: torch.Tensor, M: int, out: torch.Tensor) -> torch.Tensor:
+    L = _lib.load()
+    _need(embed, torch.bfloat16, "embed"); _need(token, torch.int32, "token")
+    check(L.dd_embed_gather(_ptr(embed), _ptr(token), token.shape[0], M, embed.shape[1], _ptr(out), _stream()),
+          "dd_embed_gather")
+    return out
+
+
+def step_advance(token: torch.Tensor, tokens_out: Optional[torch.Tensor], seq_lens: torch.Tensor,
+                 step: torch.Tensor) -> None:
+    L = _lib.load()
+    max_steps = 0 if tokens_out is None else tokens_out.shape[1]
+    check(L.dd_step_advance(_ptr(token), _ptr(tokens_out), max_steps, _ptr(seq_lens), _ptr(step), token.shape[0],
+                            _stream()), "dd_step_advance")

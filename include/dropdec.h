@@ -1,0 +1,195 @@
+/*
+ * dropdec.h -- C ABI of libdropdec.so: the B200 (sm_100a) kernels of the
+ * Dropout-Decoding inference hot path.
+ *
+ * The reference (kigb/DropoutDecoding) has no FFI: its hot path is Python inside
+ * three HuggingFace model wrappers.  The entry points below are what a maintainer
+ * would bind (ctypes) to replace the cited reference code.
+ * All `file:line` citations are relative to the reference tree.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - bf16 tensors are passed as `const void*` (2 bytes/element), row-major, dense;
+ *   - the caller allocates all outputs and workspaces (query the *_workspace_bytes
+ *     function first); functions are stateless and re-entrant;
+ *   - work is enqueued on `stream` (a cudaStream_t); nothing synchronises the host,
+ *     so every entry point is CUDA-graph capturable;
+ *   - return value: 0 on success, a negative DD_ERR_* code otherwise (never throws);
+ *     dd_last_error() gives the message for the calling thread.
+ */
+#ifndef DROPDEC_H
+#define DROPDEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dd_stream_t; /* cudaStream_t */
+
+#define DD_OK 0
+#define DD_ERR_INVALID_ARG (-1)
+#define DD_ERR_UNSUPPORTED (-2)
+#define DD_ERR_WORKSPACE (-3)
+#define DD_ERR_CUDA (-4)
+
+#define DD_MAX_MEMBERS 16  /* K, the number of masked ensemble members        */
+#define DD_MAX_TOPK 16     /* k of the per-visual-token top-k id table         */
+
+/* mask sampler modes */
+#define DD_MASK_CUMULATIVE 0  /* LLaVA-1.5: mask not restored between members (models/llava.py:342-346) */
+#define DD_MASK_INDEPENDENT 1 /* LLaVA-NeXT: restored between members (models/llavanext.py:544-551)     */
+#define DD_MASK_QUANTILE 2    /* InstructBLIP: deterministic quantile threshold (models/instructblip.py:447-460) */
+
+/* aggregation modes */
+#define DD_AGG_VOTE 0 /* select_by_vote    models/llava.py:22-36 */
+#define DD_AGG_MEAN 1 /* select_by_average models/llava.py:37-52 */
+
+int dd_version(void);
+const char* dd_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Visual-token uncertainty stage.
+ * Replaces: lm_head over the visual rows + get_image_logits (models/llava.py:412-426),
+ * get_topk_token_id (models/llava.py:428-441) and calculate_vision_uncertainty
+ * (models/llava.py:710-756; twins llavanext.py:878-924, instructblip.py:511-557).
+ *
+ * logits[i,v] = <h_vis[img,i,:], w_lm[v,:]> is produced tile by tile on the tcgen05 tensor
+ * cores (TMA -> smem -> UMMA -> TMEM) and reduced in the epilogue; the [n_vis x vocab]
+ * logits never exist in HBM.  Per image:
+ *   p = softmax(logits), p_avg[v] = mean_i p[i,v]
+ *   epi[i]  = sum_v p (log(p+1e-10) - log(p_avg+1e-10))
+ *   alea[i] = -sum_v p log(p+1e-10)
+ *   var[i]  = unbiased variance of p[i,:]
+ *   topk_ids[i,:] = ids of the topk largest logits of row i (descending)
+ * round_logits_bf16 != 0 rounds each logit to bf16 before the softmax, which is what the
+ * reference's `lm_head(...)` in half precision followed by `.float()` does
+ * (models/llama.py:46-47).
+ * Limits: d % 64 == 0, n_vis <= 640 per image, topk <= DD_MAX_TOPK.
+ * ------------------------------------------------------------------------------------------ */
+size_t dd_uncertainty_workspace_bytes(int n_images, int n_vis, int vocab, int topk);
+int dd_uncertainty_project(const void* h_vis /* bf16 [n_images, n_vis, d] */,
+                           const void* w_lm /* bf16 [vocab, d] */, int n_images, int n_vis, int d,
+                           int vocab, int topk, int round_logits_bf16,
+                           float* epi /* [n_images, n_vis] */, float* alea, float* var,
+                           int32_t* topk_ids /* [n_images, n_vis, topk] */, void* workspace,
+                           size_t workspace_bytes, dd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Uncertainty-guided mask sampling.
+ * Replaces: get_overlap_image_tokens (models/llava.py:443-482) + get_image_attention_mask
+ * method "epis" / "epis_no_overlap" (models/llava.py:589-683, llavanext.py:779-829) and the
+ * InstructBLIP quantile variant (models/instructblip.py:447-460), for all K members at once.
+ *
+ * Output bit (b,m,i) = 1  <=>  visual token i of sequence b is hidden from member m.
+ *   p_i    = 0.1f + (float)(prob_m - 0.1) * (epi_i - min) / (max - min)     (fp32, op by op)
+ *   draw_m = { i : u[b,m,i] < p_i }
+ *   cumulative : bits_m = (draw_0 | .. | draw_m) \ relevant
+ *   independent: bits_m = draw_m \ relevant
+ *   quantile   : bits_m = { i : epi_i >= quantile(epi, 1 - prob_m) } \ relevant
+ *   relevant   = { i : y_init[b] in topk_ids[b,i,:] }   (skipped when keep_relevant == 0)
+ * u comes from `uniforms` when it is non-NULL (parity mode: the caller supplies the same
+ * numbers the reference's torch.rand_like would draw), otherwise from Philox4x32-10 keyed
+ * by (seed, offset0 + *step * K, sequence, member, token).
+ * n_masked[b,m] = popcount(bits_m)   (the reference's masked_numbers, models/llava.py:661).
+ * ------------------------------------------------------------------------------------------ */
+int dd_sample_masks(const float* epi /* [B, n_vis] */, const int32_t* topk_ids /* [B, n_vis, topk] */,
+                    int topk, const int32_t* y_init /* [B] */, const double* probs_host /* [K] */,
+                    int K, const float* uniforms /* [B, K, n_vis] or NULL */, uint64_t seed,
+                    uint64_t offset0, const int32_t* step /* device scalar or NULL */, int mode,
+                    int keep_relevant, int B, int n_vis, uint32_t* bitmask /* [B, K, mask_words] */,
+                    int mask_words, int32_t* n_masked /* [B, K] */, dd_stream_t stream);
+
+/* Test hook: out[i] = first uniform of Philox subsequence i at `offset` -- the layout
+ * torch.rand(n, device="cuda") uses for n <= 256 * #blocks. */
+int dd_philox_uniform(uint64_t seed, uint64_t offset, int n, float* out, dd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Decode attention for the M masked contexts over one shared prefix KV cache.
+ * Replaces: the K+1 `copy.deepcopy(past_key_values)` (models/llava.py:292,343) and the masked
+ * SDPA of the K+1 single-token forwards (models/llava.py:294-303,350-359 -> HF Llama attention).
+ *
+ * The prefix K/V of (sequence b, kv head h) is read from HBM ONCE and scored against the
+ * queries of all M members (and all H/H_kv query heads of the group); member m's bitmask is
+ * applied to the scores of the visual span [vis_start[b], vis_start[b]+n_vis) in registers.
+ * Each member also attends to its own new-token row (k_new/v_new), which is not in the cache.
+ *   out[b,m,h,:] = softmax( [q.K_prefix^T masked_m , q.k_new[m]] * scale ) [V_prefix ; v_new[m]]
+ * bitmask == NULL means no masking (the preliminary pass, M = 1).
+ * Limits: D in {64,128}; M * (H / H_kv) <= 32.
+ * ------------------------------------------------------------------------------------------ */
+size_t dd_attention_workspace_bytes(int B, int M, int H, int D, int num_splits);
+int dd_decode_attention(const void* q /* bf16 [B, M, H, D] */, const void* k_new /* bf16 [B, M, H_kv, D] */,
+                        const void* v_new, const void* k_cache /* bf16 [B, H_kv, S_max, D] */,
+                        const void* v_cache, const int32_t* seq_lens /* [B] committed tokens */,
+                        const int32_t* vis_start /* [B] */, const uint32_t* bitmask /* [B, M, mask_words] */,
+                        int B, int M, int H, int H_kv, int D, int S_max, int n_vis, int mask_words,
+                        float scale, int num_splits, void* out /* bf16 [B, M, H, D] */, void* workspace,
+                        size_t workspace_bytes, dd_stream_t stream);
+
+/* Commit the winning member's new-token K/V rows of every layer into the shared cache at
+ * position seq_lens[b] (replaces "the winner's cache becomes the live cache",
+ * models/llava.py:370-376).  seq_lens is NOT advanced here (see dd_step_advance). */
+int dd_commit_winner(const void* k_new_all /* bf16 [L, B, M, H_kv, D] */, const void* v_new_all,
+                     const int32_t* winner /* [B] */, const int32_t* seq_lens /* [B] */,
+                     void* k_cache_all /* bf16 [L, B, H_kv, S_max, D] */, void* v_cache_all, int L, int B,
+                     int M, int H_kv, int D, int S_max, dd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) Ensemble aggregation.
+ * Replaces: select_by_vote (models/llava.py:22-36, llavanext.py:26-39) and select_by_average
+ * (models/llava.py:37-52); with K = 1 it is the plain argmax that yields y_init.
+ *   member_ids[b,m] = argmax_v logits[b,m,:]          (first index on ties, as torch.argmax)
+ *   vote: winner[b] = first member whose id is the most frequent one (ties between ids ->
+ *         the id seen first); token[b] = that id; out_logits[b,:] = logits[b,winner,:]
+ *   mean: out_logits[b,:] = mean_m logits[b,m,:] (fp32); token = argmax; winner = 0
+ * out_logits may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int dd_aggregate(const float* logits /* [B, K, V] */, int B, int K, int V, int mode,
+                 int32_t* member_ids /* [B, K] */, int32_t* winner /* [B] */, int32_t* token /* [B] */,
+                 float* out_logits /* [B, V] or NULL */, dd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Decoder support for the single-token forwards of the ensemble (models/llama.py:27-47 and the
+ * HF Llama decoder layer it calls).  Small-M, weight-streaming (HBM-bound) kernels.
+ * ------------------------------------------------------------------------------------------ */
+
+/* y[m,:] = bf16( bf16(x[m,:] * rsqrt(mean(x^2)+eps)) * w ) */
+int dd_rmsnorm(const void* x /* bf16 [M, d] */, const void* w /* bf16 [d] */, int M, int d, float eps,
+               void* y /* bf16 [M, d] */, dd_stream_t stream);
+
+/* Skinny GEMM  y[m,n] = sum_k x[m,k] * w[n,k]   (M <= 32; N % 16 == 0; K % 256 == 0)
+ * epilogue: DD_EPI_NONE     y            = bf16(acc)
+ *           DD_EPI_RESIDUAL y            = bf16(float(bf16(acc)) + residual[m,n])
+ *           DD_EPI_F32      y (float32)  = float(bf16(acc))      (lm_head + .float())
+ *           DD_EPI_SWIGLU   w is [2N, K] = [gate ; up];  y = bf16( bf16(silu(bf16(g))) * bf16(u) )
+ */
+#define DD_EPI_NONE 0
+#define DD_EPI_RESIDUAL 1
+#define DD_EPI_F32 2
+#define DD_EPI_SWIGLU 3
+int dd_skinny_gemm(const void* x /* bf16 [M, K] */, const void* w /* bf16 [N(,2N), K] */,
+                   const void* residual /* bf16 [M, N] or NULL */, int M, int N, int K, int epilogue,
+                   void* y, dd_stream_t stream);
+
+/* RoPE (rotate-half) on the new token's q and k, and staging of the member rows:
+ *   qkv [B*M, (H + 2 H_kv) * D] (q | k | v) -> q_out [B,M,H,D], k_new [B,M,H_kv,D], v_new [B,M,H_kv,D]
+ * position of sequence b = seq_lens[b]; cos/sin tables are fp32 [max_pos, D/2]. */
+int dd_rope_stage(const void* qkv, const float* cos_tab, const float* sin_tab, const int32_t* seq_lens,
+                  int B, int M, int H, int H_kv, int D, void* q_out, void* k_new, void* v_new,
+                  dd_stream_t stream);
+
+/* x[b*M + m, :] = embed[token[b], :]  for m < M */
+int dd_embed_gather(const void* embed /* bf16 [V, d] */, const int32_t* token /* [B] */, int B, int M,
+                    int d, void* x /* bf16 [B*M, d] */, dd_stream_t stream);
+
+/* End of one ensemble step: tokens_out[b, *step] = token[b]; seq_lens[b] += 1; *step += 1. */
+int dd_step_advance(const int32_t* token /* [B] */, int32_t* tokens_out /* [B, max_steps] */,
+                    int max_steps, int32_t* seq_lens /* [B] */, int32_t* step /* scalar */, int B,
+                    dd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DROPDEC_H */

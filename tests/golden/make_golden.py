@@ -81,20 +81,8 @@ def close(a, b, what, rtol=1e-5, atol=1e-6):
 # ----------------------------------------------------------------------------------------
 # 1. uncertainty stage: h_vis, lm_head from seeds -> logits -> reference functions
 # ----------------------------------------------------------------------------------------
-UNCERT_CASES = [
-    # name, n_vis, d, V, h_scale, head_std, topk
-    ("llava_tiny", 576, 256, 32064, 1.0, 0.08, 5),       # config 1 shapes
-    ("blip_small", 32, 256, 32001, 1.0, 0.08, 10),       # InstructBLIP: 32 tokens, V=32001, k=10
-    ("peaked", 200, 128, 4096, 4.0, 0.25, 5),            # sharp distributions, p < 1e-10 present
-    ("ragged", 77, 64, 1000, 1.0, 0.3, 10),              # nothing a multiple of anything
-]
-
-
-def uncert_inputs(name, n_vis, d, V, h_scale, head_std, seed=1234):
-    g = torch.Generator().manual_seed(seed + sum(map(ord, name)))
-    h = oracle.bf16r(torch.randn(n_vis, d, generator=g) * h_scale)
-    w = oracle.bf16r(torch.randn(V, d, generator=g) * head_std)
-    return h, w
+sys.path.insert(0, os.path.join(REPO, "tests"))
+from golden_cases import UNCERT_CASES, uncert_inputs, aggregate_inputs  # noqa: E402
 
 
 def gold_uncertainty():
@@ -232,22 +220,9 @@ def gold_masks():
 # ----------------------------------------------------------------------------------------
 
 def gold_aggregate():
-    g = torch.Generator().manual_seed(7)
-    V = 32064
     rows = []
-    for case in range(40):
-        K = [1, 2, 3, 3, 4, 8][case % 6]
-        l = torch.randn(K, V, generator=g)
-        # force specific vote patterns: all agree / 2-1 splits / all differ / ties
-        pat = case % 5
-        if pat == 0:
-            l[:, 123] += 20
-        elif pat == 1 and K >= 3:
-            l[0, 5] += 20; l[1:, 9] += 20
-        elif pat == 2 and K >= 2:
-            l[0, 5] += 20; l[1, 9] += 20           # tie 1-1(-1): earliest member wins
-        elif pat == 3 and K >= 4:
-            l[0, 1] += 20; l[1, 2] += 20; l[2, 2] += 20; l[3, 1] += 20   # 2-2 tie -> id of member 0
+    V = 32064
+    for K, l in aggregate_inputs():
         outs = [(l[m][None, None],) for m in range(K)]       # output[0][-1] -> [1, V]
         ref_out, ref_idx = ref_llava.select_by_vote(outs)
         idx, tok = oracle.select_by_vote([l[m] for m in range(K)])

@@ -1,0 +1,329 @@
+"""Parity of every CUDA kernel, called through the C ABI, against the golden fixtures minted
+from the reference's own code (tests/golden/*.npz) and against fp32 restatements.
+
+Bars (BASELINE.json north_star): mask index sets / votes / argmax bit-exact; per-token epistemic
+uncertainty within 1e-3 relative; bf16 tensors within bf16 rounding of an fp32 computation.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_cases import UNCERT_CASES, aggregate_inputs, uncert_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from dropoutdecoding_b200 import ops as _ops
+    return _ops
+
+
+def unpack_bits(words: torch.Tensor, n: int) -> np.ndarray:
+    """int32 words [..., W] -> bool [..., n] (bit i of word i//32)."""
+    w = words.cpu().numpy().astype(np.uint32)
+    bits = ((w[..., :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)
+    return bits.reshape(*w.shape[:-1], -1)[..., :n]
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) mask sampler vs the reference's get_image_attention_mask (golden)
+# ---------------------------------------------------------------------------------------------
+def test_sampler_matches_reference_masks(ops, cuda, golden_dir):
+    z = np.load(os.path.join(golden_dir, "masks.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    for c in meta:
+        name, n_vis, steps = c["name"], c["n_vis"], c["steps"]
+        epis = torch.from_numpy(z[f"{name}.epis"]).to(cuda)[None].contiguous()
+        ids = torch.from_numpy(z[f"{name}.topk_ids"]).to(cuda)[None].contiguous()
+        probs = z[f"{name}.probs"].tolist()
+        for t in range(steps):
+            y = torch.tensor([int(z[f"{name}.y_init"][t])], dtype=torch.int32, device=cuda)
+            U = torch.from_numpy(z[f"{name}.uniforms"][t]).to(cuda)[None].contiguous()
+            for mode, key, keep in (("cumulative", "cumulative", True), ("independent", "independent", True),
+                                    ("independent", "no_overlap", False), ("quantile", "quantile", True)):
+                bm, cnt = ops.sample_masks(epis, ids, y, probs, mode=mode, keep_relevant=keep, uniforms=U)
+                got = unpack_bits(bm[0], n_vis)
+                want = z[f"{name}.{key}"][t]
+                assert np.array_equal(got, want), f"{name} step {t} mode {key}: mask index sets differ"
+                assert cnt[0].tolist() == want.sum(-1).tolist()
+
+
+def test_sampler_batched_and_padded_words(ops, cuda, golden_dir):
+    """B > 1 with per-sequence y_init, and a mask_words larger than needed (padding must be zero)."""
+    z = np.load(os.path.join(golden_dir, "masks.npz"))
+    name, n_vis = "small", 33
+    epis = torch.from_numpy(z[f"{name}.epis"]).to(cuda)
+    ids = torch.from_numpy(z[f"{name}.topk_ids"]).to(cuda)
+    B = 4
+    y = torch.from_numpy(z[f"{name}.y_init"][:B].astype(np.int32)).to(cuda)
+    U = torch.from_numpy(z[f"{name}.uniforms"][:B]).to(cuda).contiguous()
+    out = torch.full((B, 3, 4), -1, dtype=torch.int32, device=cuda)
+    bm, _ = ops.sample_masks(epis[None].repeat(B, 1).contiguous(), ids[None].repeat(B, 1, 1).contiguous(), y,
+                             z[f"{name}.probs"].tolist(), mode="cumulative", uniforms=U, out=out)
+    got = unpack_bits(bm, 128)
+    for b in range(B):
+        assert np.array_equal(got[b][:, :n_vis], z[f"{name}.cumulative"][b])
+    assert not got[:, :, n_vis:].any()
+
+
+def test_philox_stream_equals_torch_cuda_rand(ops, cuda):
+    """The in-kernel Philox reproduces torch.rand on the device, so drop-in mode
+    draws the numbers the reference's rand_like would draw on a GPU."""
+    for n in (576, 32, 2880):
+        torch.cuda.manual_seed(24)
+        a = torch.rand(n, device=cuda)
+        b = torch.rand(n, device=cuda)
+        assert torch.equal(ops.philox_uniform(24, 0, n), a)
+        assert torch.equal(ops.philox_uniform(24, 4, n), b)
+
+
+def test_sampler_philox_mode_consistent(ops, cuda):
+    """Philox mode == uniforms mode fed with the same Philox numbers, step counter included."""
+    n_vis, K = 576, 3
+    g = torch.Generator().manual_seed(3)
+    epi = (torch.rand(1, n_vis, generator=g) * 0.3 + 0.6).to(cuda)
+    ids = torch.randint(0, 32064, (1, n_vis, 5), generator=g, dtype=torch.int32).to(cuda)
+    y = torch.tensor([17], dtype=torch.int32, device=cuda)
+    probs = [0.3, 0.5, 0.7]
+    step = torch.tensor([5], dtype=torch.int32, device=cuda)
+    bm, _ = ops.sample_masks(epi, ids, y, probs, uniforms=None, seed=24, offset=8, step=step)
+    U = torch.stack([ops.philox_uniform(24, 8 + 4 * (5 * K + m), n_vis) for m in range(K)])[None].contiguous()
+    bm2, _ = ops.sample_masks(epi, ids, y, probs, uniforms=U)
+    assert torch.equal(bm, bm2)
+
+
+# ---------------------------------------------------------------------------------------------
+# (4) aggregation vs select_by_vote / select_by_average (golden)
+# ---------------------------------------------------------------------------------------------
+def test_aggregate_matches_reference(ops, cuda, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "aggregate.npz"))["cases"]
+    for (K, l), (gK, gidx, gtok, gavg) in zip(aggregate_inputs(), gold):
+        assert K == gK
+        lg = l.to(cuda)[None].contiguous()
+        mids, win, tok, out = ops.aggregate(lg, "vote", want_logits=True)
+        assert mids[0].tolist() == torch.argmax(l, dim=-1).tolist()
+        assert int(win[0]) == gidx and int(tok[0]) == gtok
+        assert torch.equal(out[0].cpu(), l[gidx])
+        _, win_m, tok_m, out_m = ops.aggregate(lg, "mean")
+        want = torch.tensor(l.numpy().mean(axis=0))
+        assert torch.equal(out_m[0].cpu(), want), "mean logits must equal numpy's fp32 mean bit for bit"
+        assert int(tok_m[0]) == gavg and int(win_m[0]) == 0
+
+
+def test_aggregate_batched_unaligned_vocab(ops, cuda):
+    g = torch.Generator().manual_seed(5)
+    l = torch.randn(5, 3, 32001, generator=g)
+    l[2, :, 77] = 9.0
+    l[2, :, 31] = 9.0            # exact tie inside a row: first index wins, like torch.argmax
+    mids, win, tok, _ = ops.aggregate(l.to(cuda))
+    assert torch.equal(mids.cpu().long(), torch.argmax(l, dim=-1))
+    assert tok[2].item() == 31
+
+
+# ---------------------------------------------------------------------------------------------
+# (3) decode attention vs an fp32 restatement of K+1 masked single-query SDPA calls
+# ---------------------------------------------------------------------------------------------
+def ref_attention(q, k_new, v_new, kc, vc, seq_lens, vis_start, dropped, scale):
+    """All fp32 on CPU.  dropped: bool [B, M, n_vis] or None."""
+    B, M, H, D = q.shape
+    H_kv = kc.shape[1]
+    G = H // H_kv
+    out = torch.zeros(B, M, H, D)
+    for b in range(B):
+        S = int(seq_lens[b])
+        for m in range(M):
+            keep = torch.ones(S + 1, dtype=torch.bool)
+            if dropped is not None:
+                n_vis = dropped.shape[-1]
+                keep[vis_start[b]:vis_start[b] + n_vis] = ~dropped[b, m]
+            for h in range(H):
+                K = torch.cat([kc[b, h // G, :S], k_new[b, m, h // G][None]], 0)
+                V = torch.cat([vc[b, h // G, :S], v_new[b, m, h // G][None]], 0)
+                s = (K @ q[b, m, h]) * scale
+                s = s.masked_fill(~keep, float("-inf"))
+                out[b, m, h] = torch.softmax(s, -1) @ V
+    return out
+
+
+@pytest.mark.parametrize("B,M,H,H_kv,D,S_max,lens,n_vis,splits", [
+    (1, 3, 32, 32, 128, 700, [593], 576, 1),          # LLaVA-1.5-7B heads, K=3
+    (1, 3, 32, 32, 128, 700, [650], 576, 9),          # split-KV
+    (1, 1, 32, 32, 128, 700, [593], 0, 4),            # preliminary pass: M=1, no mask
+    (3, 3, 8, 8, 128, 300, [57, 200, 64], 40, 3),     # ragged batch, short sequences, empty splits
+    (2, 8, 32, 8, 128, 400, [333, 129], 250, 2),      # Mistral GQA, K=8 -> 32 query rows (2 row tiles)
+    (2, 3, 4, 4, 64, 700, [593, 624], 576, 2),        # tiny config: D=64
+    (1, 4, 4, 2, 64, 128, [1], 1, 1),                 # single cached key
+])
+def test_decode_attention(ops, cuda, B, M, H, H_kv, D, S_max, lens, n_vis, splits):
+    g = torch.Generator().manual_seed(B * 1000 + M * 100 + D + splits)
+    bf = lambda *s: (torch.randn(*s, generator=g)).to(torch.bfloat16)
+    q, k_new, v_new = bf(B, M, H, D), bf(B, M, H_kv, D), bf(B, M, H_kv, D)
+    kc, vc = bf(B, H_kv, S_max, D), bf(B, H_kv, S_max, D)
+    seq_lens = torch.tensor(lens, dtype=torch.int32)
+    scale = 1.0 / math.sqrt(D)
+    if n_vis > 0:
+        vis_start = torch.tensor([min(5, max(0, l - n_vis)) for l in lens], dtype=torch.int32)
+        dropped = torch.rand(B, M, n_vis, generator=g) < 0.5
+        dropped[0, 0, :] = True                      # a member that hides the whole image
+        words = ops.mask_words(n_vis)
+        bits = np.zeros((B, M, words * 32), dtype=bool)
+        bits[..., :n_vis] = dropped.numpy()
+        packed = (bits.reshape(B, M, words, 32) * (1 << np.arange(32, dtype=np.uint64))).sum(-1).astype(np.uint32)
+        bm = torch.from_numpy(packed.view(np.int32)).to(cuda)
+        vs = vis_start.to(cuda)
+    else:
+        vis_start, dropped, bm, vs = torch.zeros(B, dtype=torch.int32), None, None, None
+    out = ops.decode_attention(q.to(cuda), k_new.to(cuda), v_new.to(cuda), kc.to(cuda), vc.to(cuda),
+                               seq_lens.to(cuda), vs, bm, n_vis, scale, num_splits=splits)
+    want = ref_attention(q.float(), k_new.float(), v_new.float(), kc.float(), vc.float(), seq_lens, vis_start,
+                         dropped, scale)
+    err = (out.float().cpu() - want).abs().max().item()
+    # output is rounded to bf16 (2^-9 relative); everything upstream is fp32-accurate
+    assert err <= 2 ** -8 * want.abs().max().item() + 1e-6, f"max abs err {err}"
+
+
+def test_commit_winner_and_step_advance(ops, cuda):
+    L, B, M, H_kv, D, S_max = 3, 2, 3, 4, 64, 16
+    g = torch.Generator().manual_seed(0)
+    kn = torch.randn(L, B, M, H_kv, D, generator=g).to(torch.bfloat16).to(cuda)
+    vn = torch.randn(L, B, M, H_kv, D, generator=g).to(torch.bfloat16).to(cuda)
+    kc = torch.zeros(L, B, H_kv, S_max, D, dtype=torch.bfloat16, device=cuda)
+    vc = torch.zeros_like(kc)
+    winner = torch.tensor([2, 0], dtype=torch.int32, device=cuda)
+    seq = torch.tensor([5, 9], dtype=torch.int32, device=cuda)
+    ops.commit_winner(kn, vn, winner, seq, kc, vc)
+    for b, (w, s) in enumerate([(2, 5), (0, 9)]):
+        assert torch.equal(kc[:, b, :, s], kn[:, b, w]) and torch.equal(vc[:, b, :, s], vn[:, b, w])
+    assert kc.float().abs().sum(dim=(0, 2, 4))[0].count_nonzero() == 1   # only one row per sequence written
+    tok = torch.tensor([11, 22], dtype=torch.int32, device=cuda)
+    hist = torch.zeros(B, 4, dtype=torch.int32, device=cuda)
+    step = torch.tensor([1], dtype=torch.int32, device=cuda)
+    ops.step_advance(tok, hist, seq, step)
+    assert seq.tolist() == [6, 10] and step.item() == 2 and hist[:, 1].tolist() == [11, 22]
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder support kernels vs fp32 restatements with the same bf16 rounding points
+# ---------------------------------------------------------------------------------------------
+def r16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 4096, 4096), (3, 4096, 4096), (4, 12288, 4096), (8, 4096, 11008),
+                                   (12, 256, 256), (32, 512, 256), (3, 32064, 256), (17, 1024, 512)])
+def test_skinny_gemm_all_epilogues(ops, cuda, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    x = r16(torch.randn(M, K, generator=g))
+    w = r16(torch.randn(N, K, generator=g) / math.sqrt(K))
+    res = r16(torch.randn(M, N, generator=g))
+    acc = (x.double() @ w.double().T).float()
+    xg, wg, rg = x.to(cuda).bfloat16(), w.to(cuda).bfloat16(), res.to(cuda).bfloat16()
+    tol = 2 ** -7        # one bf16 ulp of the largest value class; fp32 accumulation order is free
+
+    def close(got, want):
+        assert (got.float().cpu() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+
+    close(ops.skinny_gemm(xg, wg), r16(acc))
+    close(ops.skinny_gemm(xg, wg, ops.EPI_RESIDUAL, residual=rg), r16(r16(acc) + res))
+    y32 = ops.skinny_gemm(xg, wg, ops.EPI_F32)
+    assert y32.dtype == torch.float32
+    close(y32, r16(acc))
+    if N % 32 == 0:
+        gate, up = r16(acc[:, :N // 2]), r16(acc[:, N // 2:])
+        close(ops.skinny_gemm(xg, wg, ops.EPI_SWIGLU), r16(r16(torch.nn.functional.silu(gate)) * up))
+
+
+def test_skinny_gemm_exact_small_integers(ops, cuda):
+    """Integer-valued inputs make every product and partial sum exact: any lane / k-permutation
+    mistake shows up as a wrong integer, not as a tolerance question."""
+    g = torch.Generator().manual_seed(1)
+    M, N, K = 5, 64, 512
+    x = torch.randint(-3, 4, (M, K), generator=g).float()
+    w = torch.randint(-3, 4, (N, K), generator=g).float()
+    y = ops.skinny_gemm(x.to(cuda).bfloat16(), w.to(cuda).bfloat16(), ops.EPI_F32)
+    assert torch.equal(y.cpu(), x @ w.T)
+
+
+def test_rmsnorm_rope_embed(ops, cuda):
+    g = torch.Generator().manual_seed(2)
+    M, d = 6, 4096
+    x, w = r16(torch.randn(M, d, generator=g) * 3), r16(torch.rand(d, generator=g) + 0.5)
+    y = ops.rmsnorm(x.to(cuda).bfloat16(), w.to(cuda).bfloat16(), 1e-5)
+    want = r16(r16(x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5)) * w)
+    assert (y.float().cpu() - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
+
+    B, Mm, H, H_kv, D = 2, 3, 8, 4, 128
+    from oracle import rope_table
+    cos, sin = rope_table(D, 10000.0, 64, faithful=True)
+    qkv = r16(torch.randn(B * Mm, (H + 2 * H_kv) * D, generator=g))
+    seq = torch.tensor([7, 33], dtype=torch.int32)
+    q_out = torch.empty(B, Mm, H, D, dtype=torch.bfloat16, device=cuda)
+    k_new = torch.empty(B, Mm, H_kv, D, dtype=torch.bfloat16, device=cuda)
+    v_new = torch.empty_like(k_new)
+    ops.rope_stage(qkv.to(cuda).bfloat16(), cos.to(cuda), sin.to(cuda), seq.to(cuda), B, Mm, H, H_kv, D, q_out,
+                   k_new, v_new)
+    rows = qkv.view(B, Mm, H + 2 * H_kv, D)
+
+    def rope(xh, pos):
+        x1, x2 = xh[..., :D // 2], xh[..., D // 2:]
+        c, s = cos[pos], sin[pos]
+        return r16(torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], -1))
+
+    for b in range(B):
+        assert (q_out[b].float().cpu() - rope(rows[b, :, :H], int(seq[b]))).abs().max() <= 2 ** -6
+        assert (k_new[b].float().cpu() - rope(rows[b, :, H:H + H_kv], int(seq[b]))).abs().max() <= 2 ** -6
+        assert torch.equal(v_new[b].float().cpu(), rows[b, :, H + H_kv:])
+
+    emb = r16(torch.randn(100, 256, generator=g)).to(cuda).bfloat16()
+    tok = torch.tensor([3, 99], dtype=torch.int32, device=cuda)
+    out = torch.empty(2 * 3, 256, dtype=torch.bfloat16, device=cuda)
+    ops.embed_gather(emb, tok, 3, out)
+    assert torch.equal(out.view(2, 3, 256), emb[tok.long()][:, None].expand(2, 3, 256))
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) uncertainty stage (tcgen05) vs calculate_vision_uncertainty / get_topk_token_id (golden)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", UNCERT_CASES, ids=[c[0] for c in UNCERT_CASES])
+def test_uncertainty_matches_reference(ops, cuda, golden_dir, case):
+    name, n_vis, d, V, hs, ws, k = case
+    z = np.load(os.path.join(golden_dir, "uncertainty.npz"))
+    h, w = uncert_inputs(name, n_vis, d, V, hs, ws)
+    epi, alea, var, ids = ops.uncertainty_project(h.to(cuda).bfloat16()[None].contiguous(),
+                                                  w.to(cuda).bfloat16().contiguous(), topk=k)
+    torch.cuda.synchronize()
+    for got, key, rtol in ((epi, "epi", 1e-3), (alea, "alea", 1e-3), (var, "var", 2e-3)):
+        want = z[f"{name}.{key}"]
+        rel = np.abs(got[0].cpu().numpy() - want) / np.maximum(np.abs(want), 1e-12)
+        assert rel.max() <= rtol, f"{name}.{key}: max rel err {rel.max():.3e}"
+    # top-k id SETS are exact wherever the k-th / (k+1)-th logits are not a numerical tie
+    safe = z[f"{name}.topk_gap"] > 1e-4 * np.maximum(1.0, np.abs(z[f"{name}.row_max"]))
+    got_ids, want_ids = np.sort(ids[0].cpu().numpy(), -1), np.sort(z[f"{name}.topk_ids"], -1)
+    assert safe.mean() > 0.95
+    assert np.array_equal(got_ids[safe], want_ids[safe]), f"{name}: top-{k} id sets differ"
+
+
+def test_uncertainty_batched_images_and_bf16_rounding(ops, cuda):
+    """Several images in one launch give the per-image results; round_logits reproduces the
+    half-precision lm_head + .float() of the reference (models/llama.py:46-47)."""
+    from oracle import calculate_vision_uncertainty
+    g = torch.Generator().manual_seed(11)
+    n_img, n_vis, d, V = 3, 150, 128, 5000
+    h = r16(torch.randn(n_img, n_vis, d, generator=g))
+    w = r16(torch.randn(V, d, generator=g) * 0.2)
+    for rnd in (False, True):
+        epi, alea, var, ids = ops.uncertainty_project(h.to(cuda).bfloat16(), w.to(cuda).bfloat16(), topk=5,
+                                                      round_logits=rnd)
+        for i in range(n_img):
+            logits = h[i] @ w.T
+            if rnd:
+                logits = r16(logits)
+            ref = calculate_vision_uncertainty(logits[None])
+            for got, key in ((epi, "epis_uncert_per_token"), (alea, "alea_uncert_per_token")):
+                want = ref[key][0]
+                assert ((got[i].cpu() - want).abs() / want.abs()).max() <= 1e-3

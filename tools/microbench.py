@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmarks on one B200 (CUDA events, L2 flushed between iterations).
+
+    python tools/microbench.py [attention|gemm|uncertainty|all]
+
+Prints one JSON line per measurement with the achieved fraction of the measured peak
+(MEASURED_PEAKS.json, else the fallback of the profiling guide).
+"""
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dropoutdecoding_b200 import ops  # noqa: E402
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p["hbm_gbs"], p["bf16_tflops"], "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+HBM, TF, SRC = peaks()
+dev = torch.device("cuda:0")
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    _flush.zero_()
+
+
+def timeit(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def bench_attention():
+    for (B, M, H, H_kv, D, S, n_vis, splits) in [
+            (1, 3, 32, 32, 128, 849, 576, 9), (1, 1, 32, 32, 128, 849, 0, 9),
+            (8, 3, 32, 32, 128, 849, 576, 2), (64, 3, 32, 32, 128, 849, 576, 1),
+            (64, 1, 32, 32, 128, 849, 0, 1), (64, 3, 32, 32, 128, 849, 576, 2),
+            (16, 8, 32, 8, 128, 3000, 2880, 4)]:
+        S_max = S + 8
+        q = torch.randn(B, M, H, D, device=dev).bfloat16()
+        kn = torch.randn(B, M, H_kv, D, device=dev).bfloat16()
+        vn = torch.randn_like(kn)
+        kc = torch.randn(B, H_kv, S_max, D, device=dev).bfloat16()
+        vc = torch.randn_like(kc)
+        sl = torch.full((B,), S, dtype=torch.int32, device=dev)
+        vs = torch.full((B,), 5, dtype=torch.int32, device=dev)
+        bm = None
+        if n_vis:
+            bm = torch.randint(-2 ** 31, 2 ** 31 - 1, (B, M, ops.mask_words(n_vis)), dtype=torch.int32, device=dev)
+        ws = ops.attention_workspace(B, M, H, D, splits, dev)
+        out = torch.empty_like(q)
+        fn = lambda: ops.decode_attention(q, kn, vn, kc, vc, sl, vs, bm, n_vis, 1 / math.sqrt(D), splits, out, ws)
+        med, best = timeit(fn)
+        algo = 2 * S * H_kv * D * 2 * B + 2 * M * H * D * 2 * B + (M * ((n_vis + 7) // 8) * B)
+        print(json.dumps(dict(kernel="decode_attention(+merge)", B=B, M=M, H=H, H_kv=H_kv, D=D, S=S, splits=splits,
+                              us=round(med * 1e6, 2), best_us=round(best * 1e6, 2), GBps=round(algo / med / 1e9, 1),
+                              frac_hbm=round(algo / med / 1e9 / HBM, 3), peak=SRC)))
+
+
+def bench_gemm():
+    for (M, N, K, epi) in [(1, 4096, 4096, ops.EPI_NONE), (3, 4096, 4096, ops.EPI_NONE), (1, 12288, 4096, ops.EPI_NONE),
+                           (3, 12288, 4096, ops.EPI_NONE), (3, 22016, 4096, ops.EPI_SWIGLU),
+                           (3, 4096, 11008, ops.EPI_RESIDUAL), (3, 32064, 4096, ops.EPI_F32),
+                           (8, 12288, 4096, ops.EPI_NONE), (24, 12288, 4096, ops.EPI_NONE),
+                           (32, 4096, 11008, ops.EPI_RESIDUAL)]:
+        x = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+        Nout = N // 2 if epi == ops.EPI_SWIGLU else N
+        res = torch.randn(M, Nout, device=dev).bfloat16()
+        out = torch.empty(M, Nout, dtype=torch.float32 if epi == ops.EPI_F32 else torch.bfloat16, device=dev)
+        fn = lambda: ops.skinny_gemm(x, w, epi, residual=res, out=out)
+        med, best = timeit(fn)
+        algo = N * K * 2
+        tfn = lambda: torch.matmul(x, w.T)
+        tmed, _ = timeit(tfn)
+        print(json.dumps(dict(kernel="skinny_gemm", M=M, N=N, K=K, epi=epi, us=round(med * 1e6, 2),
+                              best_us=round(best * 1e6, 2), GBps=round(algo / med / 1e9, 1),
+                              frac_hbm=round(algo / med / 1e9 / HBM, 3), cublas_us=round(tmed * 1e6, 2), peak=SRC)))
+
+
+def bench_uncertainty():
+    for (n_img, n_vis, d, V, k) in [(1, 576, 4096, 32064, 5), (4, 576, 4096, 32064, 5), (8, 576, 4096, 32064, 5),
+                                    (32, 32, 4096, 32001, 10)]:
+        h = torch.randn(n_img, n_vis, d, device=dev).bfloat16()
+        w = (torch.randn(V, d, device=dev) * 0.02).bfloat16()
+        fn = lambda: ops.uncertainty_project(h, w, topk=k)
+        med, best = timeit(fn, iters=10)
+        flops = 2.0 * n_img * n_vis * d * V
+        tfn = lambda: torch.matmul(h.view(-1, d), w.T)
+        tmed, _ = timeit(tfn, iters=10)
+        print(json.dumps(dict(kernel="uncertainty_project(2 sweeps+finalize)", n_img=n_img, n_vis=n_vis, d=d, V=V,
+                              us=round(med * 1e6, 1), best_us=round(best * 1e6, 1), TFLOPs=round(flops / med / 1e12, 1),
+                              frac_tensor=round(flops / med / 1e12 / TF, 3), cublas_gemm_only_us=round(tmed * 1e6, 1),
+                              peak=SRC)))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    with torch.no_grad():
+        if which in ("attention", "all"):
+            bench_attention()
+        if which in ("gemm", "all"):
+            bench_gemm()
+        if which in ("uncertainty", "all"):
+            bench_uncertainty()
