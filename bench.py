@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Headline benchmark: LLaVA-1.5-7B Dropout Decoding (K=3 masks) tokens/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): LLaVA-1.5-7B shapes, random-init bf16, one synthetic 336px
+image per sequence, 18-token prompt (593 positions after the 576 visual tokens are spliced in),
+K=3 masked contexts with rates [0.3,0.5,0.7], 64 new tokens, EOS ignored.  Under N GPUs every rank
+decodes its own sequences (batch sharding, SURVEY.md 8e: no per-step collective) -> weak scaling.
+
+One "step" = one complete dropout-decode of the rank's batch: uncertainty stage + first token +
+63 ensemble steps (each: preliminary pass, mask sampling, K masked passes over one shared KV cache,
+vote, commit).  `value` times that with the prefix KV cache and the visual hidden states resident
+in HBM (the prompt prefill is outside the hot path, reported as prefill_ms); `e2e` times the public
+API `model.generate(...)` from pinned host tensors to host tokens: vision tower, projector, prefill,
+hot path, and both copies.
+
+--impl reference times the reference's algorithm (the CPU oracle: sequential members, one deep
+copy of the KV cache per member, fp32) on the host cores; each step is a bounded sample of the
+same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PROMPT_LEN, N_VIS, NEW_TOKENS, PROBS = 18, 576, 64, [0.3, 0.5, 0.7]
+IMAGE_POS = 5
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_llava15_7b(device, tiny: bool = False):
+    from transformers import CLIPVisionConfig, LlamaConfig, LlavaConfig
+    from dropoutdecoding_b200.models.llava import CustomLlavaForConditionalGeneration
+    if tiny:
+        vc = CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2,
+                              image_size=336, patch_size=14)
+        tc = LlamaConfig(vocab_size=32064, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=4, rms_norm_eps=1e-5, max_position_embeddings=4096)
+    else:
+        vc = CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                              image_size=336, patch_size=14)
+        tc = LlamaConfig(vocab_size=32064, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                         num_attention_heads=32, num_key_value_heads=32, rms_norm_eps=1e-5, max_position_embeddings=4096)
+    cfg = LlavaConfig(vision_config=vc, text_config=tc, image_token_index=32000, vision_feature_layer=-2,
+                      vision_feature_select_strategy="default")
+    torch.manual_seed(0)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(device):
+            model = CustomLlavaForConditionalGeneration(cfg)
+    finally:
+        torch.set_default_dtype(old)
+    return model.to(device=device, dtype=torch.bfloat16).eval()
+
+
+def synthetic_inputs(batch: int, seed0: int):
+    """Pinned host tensors, like a processor would hand over (one <image> id per prompt)."""
+    ids, px = [], []
+    for b in range(batch):
+        g = torch.Generator().manual_seed(seed0 + b)
+        row = torch.randint(3, 30000, (PROMPT_LEN,), generator=g)
+        row[0] = 1
+        row[IMAGE_POS] = 32000
+        ids.append(row)
+        img = torch.rand(3, 336, 336, generator=g)
+        mean = torch.tensor([0.4815, 0.4578, 0.4082])[:, None, None]
+        std = torch.tensor([0.2686, 0.2613, 0.2758])[:, None, None]
+        px.append((img - mean) / std)
+    return torch.stack(ids).pin_memory(), torch.stack(px).pin_memory()
+
+
+def run_ours(args):
+    from dropoutdecoding_b200 import ops
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    hbm, tf, peak_src = measured_peaks()
+    B, T = args.batch, args.new_tokens
+
+    model = build_llava15_7b(dev, tiny=args.tiny)
+    ids_h, px_h = synthetic_inputs(B, seed0=1 + rank * B)
+
+    with torch.no_grad():
+        # ---- setup for `value`: prefill once, keep the hot path's inputs resident ------------------
+        t0 = time.perf_counter()
+        merged, start, n_vis = model._merge(ids_h.to(dev), px_h.to(dev, torch.bfloat16))
+        S0 = merged.shape[1]
+        eng = model._engine(B, n_vis, S0 + T, est_seq=S0 + T // 2)
+        hidden = eng.prefill(merged.to(torch.bfloat16), [start] * B)
+        vis_hidden = hidden[:, start:start + n_vis].contiguous()
+        last_hidden = hidden[:, -1].contiguous()
+        torch.cuda.synchronize()
+        prefill_ms = (time.perf_counter() - t0) * 1e3
+
+        def hot_path():
+            eng.seq_lens.fill_(S0)
+            eng.uncertainty_stage(vis_hidden)
+            eng.first_token(last_hidden)
+            eng.decode(T - 1, use_graph=True)
+
+        for _ in range(args.warmup):
+            hot_path()
+        torch.cuda.synchronize()
+        launches_per_ens_step = eng.launches_per_step
+
+        def barrier():
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        clocks = ClockSampler(local)
+        barrier()
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            hot_path()
+        e1.record()
+        barrier()
+        dt = e0.elapsed_time(e1) * 1e-3
+        clk = clocks.stop()
+        tokens_check = eng.generated().clone()
+
+        # ---- e2e: the public API, host tensors in, host tokens out ---------------------------------
+        for _ in range(max(1, args.warmup - 1)):
+            model.generate(input_ids=ids_h, pixel_values=px_h, max_new_tokens=T).cpu()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            out = model.generate(input_ids=ids_h, pixel_values=px_h, max_new_tokens=T).cpu()
+        f1.record()
+        barrier()
+        dt_e2e = f0.elapsed_time(f1) * 1e-3
+        assert out.shape == (B, PROMPT_LEN + T)
+
+        # ---- roofline of the dominant kernel, measured live: one eager ensemble step with CUDA
+        #      events around every dd_skinny_gemm launch on the launching stream
+        roof = profile_dominant_kernel(eng, hbm, peak_src)
+
+    if dist is not None:
+        t = torch.tensor([dt, dt_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = t.tolist()
+    total_tokens = B * T * args.steps * world
+    line = {
+        "metric": "LLaVA-1.5-7B dropout-decode tokens/s (K=3 masks)", "value": round(total_tokens / dt, 2),
+        "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"llava-1.5-7b random-init bf16, {B} synthetic 336px image(s) per GPU, K=3 masks "
+                               f"[0.3,0.5,0.7], {T} new tokens, prompt 18 ids -> {S0} positions" +
+                               (" [TINY SHAPES]" if args.tiny else ""),
+                   "batch_per_gpu": B, "new_tokens": T, "K": 3, "n_vis": n_vis,
+                   "l2": "inputs larger than L2 (13.2 GB of weights streamed twice per token)",
+                   "parallelism": f"batch-sharded x{world}, no per-step collective"},
+        "e2e": {"value": round(total_tokens / dt_e2e, 2), "unit": "tokens/s",
+                "h2d_bytes_per_step": int(ids_h.numel() * ids_h.element_size() + px_h.numel() * px_h.element_size()),
+                "d2h_bytes_per_step": int(out.numel() * out.element_size())},
+        "gpu_launches": int(args.steps * ((T - 1) * launches_per_ens_step + 6)),
+        "prefill_ms": round(prefill_ms, 2),
+        "ms_per_token": round(dt / args.steps / T * 1e3, 4),
+        "clocks": clk, "roofline": roof,
+        "token_checksum": int(tokens_check.long().sum().item()),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_sample_steps)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def profile_dominant_kernel(eng, hbm, peak_src):
+    """Time every dd_skinny_gemm launch of one eager ensemble step with CUDA events on torch's
+    current stream (the stream the C ABI launches on)."""
+    from dropoutdecoding_b200 import ops
+    recs = []
+    orig = ops.skinny_gemm
+
+    def timed(x, w, epilogue=ops.EPI_NONE, residual=None, out=None):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = orig(x, w, epilogue, residual=residual, out=out)
+        b.record()
+        recs.append((a, b, w.numel() * w.element_size()))
+        return r
+
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    snap = eng._snapshot()
+    ops.skinny_gemm = timed
+    try:
+        eng.step()                      # warm
+        recs.clear()
+        torch.cuda.synchronize()
+        t_all0.record()
+        eng.step()
+        t_all1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops.skinny_gemm = orig
+        eng._restore(snap)
+    if not recs:
+        return {"bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None, "traffic": None,
+                "note": "no dd_skinny_gemm launches (rows > 32: library GEMMs)"}
+    secs = sum(a.elapsed_time(b) for a, b, _ in recs) * 1e-3
+    byts = sum(n for _, _, n in recs)
+    ach = byts / secs / 1e9
+    return {"bound": "hbm", "kernel": "dd::skinny_gemm_kernel (all weight GEMMs of one ensemble step)",
+            "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None,
+            "peak_source": peak_src, "launches": len(recs), "algorithmic_bytes_per_step": int(byts),
+            "avg_launch_us": round(secs / len(recs) * 1e6, 2),
+            "share_of_eager_step": round(secs / (t_all0.elapsed_time(t_all1) * 1e-3), 3)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle) on the host cores
+# ------------------------------------------------------------------------------------------------
+def _oracle_setup(tiny: bool):
+    import oracle
+    cfg = oracle.LMConfig.tiny() if tiny else oracle.LMConfig.llava15_7b()
+    torch.manual_seed(0)
+    w = {"embed": torch.empty(cfg.vocab, cfg.d_model).normal_(std=0.02)}
+    for l in range(cfg.n_layers):
+        p = f"l{l}."
+        w[p + "ln1"] = torch.ones(cfg.d_model); w[p + "ln2"] = torch.ones(cfg.d_model)
+        for name, shape in (("wq", (cfg.n_heads * cfg.head_dim, cfg.d_model)),
+                            ("wk", (cfg.n_kv_heads * cfg.head_dim, cfg.d_model)),
+                            ("wv", (cfg.n_kv_heads * cfg.head_dim, cfg.d_model)),
+                            ("wo", (cfg.d_model, cfg.n_heads * cfg.head_dim)),
+                            ("wg", (cfg.d_ff, cfg.d_model)), ("wu", (cfg.d_ff, cfg.d_model)),
+                            ("wd", (cfg.d_model, cfg.d_ff))):
+            w[p + name] = torch.empty(*shape).normal_(std=0.02)
+    w["norm"] = torch.ones(cfg.d_model)
+    w["lm_head"] = torch.empty(cfg.vocab, cfg.d_model).normal_(std=0.02)
+    lm = oracle.OracleLM(cfg, w, faithful=False, max_pos=2048)
+    S0 = PROMPT_LEN - 1 + N_VIS
+    cache = oracle.OracleCache(cfg.n_layers)
+    g = torch.Generator().manual_seed(1)
+    for l in range(cfg.n_layers):       # a prefilled prefix: random K/V of the right shape
+        cache.k[l] = torch.randn(cfg.n_kv_heads, S0, cfg.head_dim, generator=g)
+        cache.v[l] = torch.randn(cfg.n_kv_heads, S0, cfg.head_dim, generator=g)
+    epis = torch.rand(N_VIS, generator=g) * 0.2 + 0.75
+    topk_ids = torch.randint(0, cfg.vocab, (1, N_VIS, 5), generator=g)
+    return oracle, lm, cache, epis, topk_ids
+
+
+def _oracle_sample(oracle, lm, cache, epis, topk_ids, n_tokens: int) -> float:
+    import copy
+    g = torch.Generator().manual_seed(24)
+    U = torch.rand(n_tokens, len(PROBS), N_VIS, generator=g)
+    c = copy.deepcopy(cache)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        oracle.ensemble_steps(lm, c, 1234, epis, topk_ids, IMAGE_POS, N_VIS, n_tokens, PROBS, U)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(args, sample_steps: int):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle, lm, cache, epis, topk_ids = _oracle_setup(args.tiny)
+    _oracle_sample(oracle, lm, cache, epis, topk_ids, 1)              # warm-up token
+    dt = _oracle_sample(oracle, lm, cache, epis, topk_ids, sample_steps)
+    return {"value": round(sample_steps / dt, 4), "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_steps} ensemble steps (1 preliminary + 3 masked fp32 forwards, 4 KV deep copies "
+                      f"each) of the same workload from a 593-token prefix, decode phase only, torch CPU"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle, lm, cache, epis, topk_ids = _oracle_setup(args.tiny)
+    n_tok = args.cpu_sample_steps
+    for _ in range(min(args.warmup, 1)):
+        _oracle_sample(oracle, lm, cache, epis, topk_ids, 1)
+    dt = 0.0
+    for _ in range(args.steps):
+        dt += _oracle_sample(oracle, lm, cache, epis, topk_ids, n_tok)
+    val = round(n_tok * args.steps / dt, 4)
+    sample = (f"each step = {n_tok} ensemble tokens (1 preliminary + 3 masked fp32 forwards, 4 KV deep copies per "
+              f"token) of the same workload from a 593-token prefix, decode phase only")
+    print(json.dumps({
+        "impl": "reference", "metric": "LLaVA-1.5-7B dropout-decode tokens/s (K=3 masks)", "value": val,
+        "unit": "tokens/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "llava-1.5-7b random-init, 1 synthetic image, K=3 masks [0.3,0.5,0.7], reference "
+                               "algorithm on the host CPU" + (" [TINY SHAPES]" if args.tiny else "")},
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="sequences per GPU")
+    ap.add_argument("--new-tokens", type=int, default=NEW_TOKENS)
+    ap.add_argument("--tiny", action="store_true", help="tiny shapes (debugging; not a valid bench line)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -324,8 +324,12 @@ static size_t attn_smem_bytes(int M, int mask_words) {
 template <int D, int QT>
 static int launch_attn(const AttnParams& p, const void* k_new, const void* v_new, void* out, cudaStream_t st) {
   const size_t smem = attn_smem_bytes<D, QT>(p.M, p.bitmask ? p.mask_words : 0);
-  DD_CHECK_CUDA(cudaFuncSetAttribute(attn_partial_kernel<D, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+  static size_t configured = 0;  // opt in to > 48 KB dynamic smem once per instantiation (grow-only)
+  if (smem > configured) {
+    DD_CHECK_CUDA(cudaFuncSetAttribute(attn_partial_kernel<D, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    configured = smem;
+  }
   attn_partial_kernel<D, QT><<<dim3(p.num_splits, p.H_kv, p.B), kAttnThreads, smem, st>>>(p);
   DD_CHECK_LAUNCH();
   attn_merge_kernel<D><<<dim3(p.H, p.M, p.B), D, 0, st>>>(p, (const __nv_bfloat16*)k_new,

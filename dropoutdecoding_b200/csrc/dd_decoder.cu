@@ -93,7 +93,7 @@ __global__ void step_advance_kernel(const int32_t* __restrict__ token, int32_t* 
                                     int32_t* seq_lens, int32_t* step, int B) {
   const int st = *step;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    if (tokens_out && st < max_steps) tokens_out[(size_t)b * max_steps + st] = token[b];
+    if (tokens_out && st + 1 < max_steps) tokens_out[(size_t)b * max_steps + st + 1] = token[b];
     seq_lens[b] += 1;
   }
   __syncthreads();

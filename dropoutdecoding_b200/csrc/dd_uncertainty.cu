@@ -325,10 +325,10 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 float x = v[i];
                 if (p.round_bf16) x = bf16_round(x);
                 float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
-                if (col0 + c * 32 + i >= p.vocab) pr = 0.f;  // padded vocab columns of the last strip
+                float dv = pr - inv_v;
+                if (col0 + c * 32 + i >= p.vocab) pr = dv = 0.f;  // padded vocab columns of the last strip
                 colsum[c * 32 + i] += pr;
                 acc_a[mt] = fmaf(pr, __logf(pr + kEps), acc_a[mt]);
-                const float dv = pr - inv_v;
                 acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
               }
             }

@@ -1,0 +1,380 @@
+"""Decode engine of the Dropout-Decoding hot path on one B200.
+
+What the reference does per generated token (models/llava.py:218-388): a
+preliminary unmasked forward, then K masked forwards run sequentially, each on a deep copy of the
+whole KV cache, with >= 3K host syncs.  Here one ensemble step is two batched passes over a
+single shared cache, with no host sync at all, replayed as one CUDA graph:
+
+    pass A  (rows = B)      embed -> L x [RMSNorm, QKV, RoPE, attention(M=1), O, RMSNorm, SwiGLU, down]
+                            -> lm_head -> argmax = y_init                       (dd_aggregate, K=1)
+    masks                   relevant set + K uncertainty-guided bitmasks         (dd_sample_masks)
+    pass B  (rows = B*K)    same layers; attention reads the prefix K/V ONCE for all K members and
+                            applies each member's bitmask in registers; every member keeps its own
+                            new-token K/V row per layer in a staging buffer       (dd_decode_attention)
+    vote / mean             member argmax ids, winner, next token                 (dd_aggregate)
+    commit                  winner's staged K/V rows -> cache row seq_len, seq_len += 1
+
+Weight GEMMs with <= 32 rows use the weight-streaming dd_skinny_gemm; above that they are plain
+library GEMMs (torch / cuBLAS), as is the prompt prefill, which is not part of the hot path
+(SURVEY.md 8f-3).  All tensors are bf16 with fp32 accumulation; rounding points follow the HF
+Llama decoder so that the CPU oracle's 'bf16-faithful' mode is comparable token for token.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+@dataclass
+class DecoderConfig:
+    n_layers: int
+    d_model: int
+    n_heads: int
+    n_kv_heads: int
+    head_dim: int
+    d_ff: int
+    vocab: int
+    rms_eps: float = 1e-5
+    rope_theta: float = 10000.0
+
+    @staticmethod
+    def llava15_7b() -> "DecoderConfig":
+        return DecoderConfig(32, 4096, 32, 32, 128, 11008, 32064, 1e-5, 10000.0)
+
+    @staticmethod
+    def llava_next_mistral_7b() -> "DecoderConfig":
+        return DecoderConfig(32, 4096, 32, 8, 128, 14336, 32064, 1e-5, 1000000.0)
+
+    @staticmethod
+    def tiny() -> "DecoderConfig":
+        return DecoderConfig(2, 256, 4, 4, 64, 512, 32064, 1e-5, 10000.0)
+
+
+def rope_table(head_dim: int, theta: float, max_pos: int):
+    """cos/sin [max_pos, head_dim/2], computed on the CPU in fp32 and rounded to bf16 like
+    transformers' `cos.to(x.dtype)`; returned as fp32 holding bf16 values."""
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    ang = torch.arange(max_pos, dtype=torch.float32)[:, None] * inv[None, :]
+    return ang.cos().to(torch.bfloat16).float(), ang.sin().to(torch.bfloat16).float()
+
+
+class DecoderWeights:
+    """bf16 device tensors; QKV and gate/up are stored concatenated ([q;k;v], [gate;up]) so that one
+    weight stream feeds one fused GEMM."""
+
+    def __init__(self, cfg: DecoderConfig, embed, layers: List[Dict[str, torch.Tensor]], norm, lm_head):
+        self.cfg, self.embed, self.layers, self.norm, self.lm_head = cfg, embed, layers, norm, lm_head
+
+    @staticmethod
+    def from_named(cfg: DecoderConfig, w: Dict[str, torch.Tensor], device) -> "DecoderWeights":
+        """w uses the oracle's naming (embed, l{i}.ln1/wq/wk/wv/wo/ln2/wg/wu/wd, norm, lm_head)."""
+        cv = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
+        layers = []
+        for l in range(cfg.n_layers):
+            p = f"l{l}."
+            layers.append(dict(
+                ln1=cv(w[p + "ln1"]), ln2=cv(w[p + "ln2"]),
+                wqkv=cv(torch.cat([w[p + "wq"], w[p + "wk"], w[p + "wv"]], 0)),
+                wo=cv(w[p + "wo"]), wgu=cv(torch.cat([w[p + "wg"], w[p + "wu"]], 0)), wd=cv(w[p + "wd"])))
+        return DecoderWeights(cfg, cv(w["embed"]), layers, cv(w["norm"]), cv(w["lm_head"]))
+
+    @staticmethod
+    def random(cfg: DecoderConfig, device, seed: int = 0, std: float = 0.02, head_std: float = 0.02
+               ) -> "DecoderWeights":
+        """Seeded random init directly on the device (benchmarks: no checkpoint is available)."""
+        g = torch.Generator(device=device).manual_seed(seed)
+
+        def n(*shape, s=std):
+            return (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * s).to(torch.bfloat16)
+
+        ones = lambda k: torch.ones(k, dtype=torch.bfloat16, device=device)
+        qkv_rows = (cfg.n_heads + 2 * cfg.n_kv_heads) * cfg.head_dim
+        layers = [dict(ln1=ones(cfg.d_model), ln2=ones(cfg.d_model), wqkv=n(qkv_rows, cfg.d_model),
+                       wo=n(cfg.d_model, cfg.n_heads * cfg.head_dim), wgu=n(2 * cfg.d_ff, cfg.d_model),
+                       wd=n(cfg.d_model, cfg.d_ff)) for _ in range(cfg.n_layers)]
+        return DecoderWeights(cfg, n(cfg.vocab, cfg.d_model), layers, ones(cfg.d_model),
+                              n(cfg.vocab, cfg.d_model, s=head_std))
+
+    def nbytes(self) -> int:
+        tot = self.embed.numel() + self.norm.numel() + self.lm_head.numel()
+        for l in self.layers:
+            tot += sum(t.numel() for t in l.values())
+        return 2 * tot
+
+    def stream_bytes_per_pass(self) -> int:
+        """Weight bytes one single-token pass has to read (embedding rows excluded)."""
+        return self.nbytes() - 2 * self.embed.numel()
+
+
+@dataclass
+class _PassBuffers:
+    M: int
+    x: torch.Tensor
+    x2: torch.Tensor
+    xn: torch.Tensor
+    qkv: torch.Tensor
+    q: torch.Tensor
+    k_new: torch.Tensor     # [L, B, M, H_kv, D]
+    v_new: torch.Tensor
+    attn: torch.Tensor
+    act: torch.Tensor
+    logits: torch.Tensor    # fp32 [B, M, V]
+    ws: torch.Tensor
+    splits: int
+
+
+class DropoutDecodeEngine:
+    """Static-shape engine for a batch of B sequences with the same number of visual tokens."""
+
+    def __init__(self, weights: DecoderWeights, batch: int, n_vis: int, max_seq: int,
+                 probs: Sequence[float] = (0.3, 0.5, 0.7), mode: str = "cumulative", keep_relevant: bool = True,
+                 topk: int = 5, aggregate: str = "vote", seed: int = 24, max_steps: int = 1024,
+                 round_logits: bool = True, est_seq: Optional[int] = None):
+        cfg = weights.cfg
+        if cfg.vocab % 16 or cfg.d_model % 256 or cfg.d_ff % 256:
+            raise ops.DropDecError("engine needs vocab % 16 == 0 and d_model, d_ff % 256 == 0")
+        self.w, self.cfg = weights, cfg
+        self.B, self.K, self.n_vis, self.S_max = batch, len(probs), n_vis, max_seq
+        self.probs, self.mode, self.keep_relevant = [float(p) for p in probs], mode, keep_relevant
+        self.topk, self.aggregate, self.seed, self.round_logits = topk, aggregate, seed, round_logits
+        self.dev = weights.embed.device
+        dev, B, L = self.dev, batch, cfg.n_layers
+        H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.k_cache = torch.zeros(L, B, Hkv, max_seq, D, **bf)
+        self.v_cache = torch.zeros(L, B, Hkv, max_seq, D, **bf)
+        self.seq_lens = torch.zeros(B, **i32)
+        self.vis_start = torch.zeros(B, **i32)
+        self.step_ctr = torch.zeros(1, **i32)
+        self.max_steps = max_steps
+        self.tokens_out = torch.zeros(B, max_steps, **i32)
+        self.cur_token = torch.zeros(B, **i32)
+        self.next_token = torch.zeros(B, **i32)
+        self.y_init = torch.zeros(B, **i32)
+        self.winner = torch.zeros(B, **i32)
+        self.winner_a = torch.zeros(B, **i32)
+        self.member_ids = torch.zeros(B, self.K, **i32)
+        self.member_ids_a = torch.zeros(B, 1, **i32)
+        self.words = ops.mask_words(n_vis)
+        self.bitmask = torch.zeros(B, self.K, self.words, **i32)
+        self.n_masked = torch.zeros(B, self.K, **i32)
+        self.out_logits = torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev)
+        self.uniforms: Optional[torch.Tensor] = None      # parity mode: [steps, B, K, n_vis]
+        self._u_step: Optional[torch.Tensor] = None
+        self.epi = torch.zeros(B, n_vis, dtype=torch.float32, device=dev)
+        self.alea = torch.zeros_like(self.epi)
+        self.var = torch.zeros_like(self.epi)
+        self.topk_ids = torch.zeros(B, n_vis, topk, **i32)
+        cos, sin = rope_table(D, cfg.rope_theta, max_seq + 1)
+        self.cos, self.sin = cos.to(dev), sin.to(dev)
+        self.scale = 1.0 / math.sqrt(D)
+        est = est_seq or max_seq
+        self.pa = self._alloc_pass(1, est)
+        self.pb = self._alloc_pass(self.K, est)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------
+    def _alloc_pass(self, M: int, est_seq: int) -> _PassBuffers:
+        cfg, B, dev = self.cfg, self.B, self.dev
+        rows = B * M
+        H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        target_ctas = 2 * torch.cuda.get_device_properties(dev).multi_processor_count
+        splits = max(1, min(-(-target_ctas // (B * Hkv)), max(1, est_seq // 128), 32))
+        return _PassBuffers(
+            M=M, x=torch.empty(rows, cfg.d_model, **bf), x2=torch.empty(rows, cfg.d_model, **bf),
+            xn=torch.empty(rows, cfg.d_model, **bf), qkv=torch.empty(rows, (H + 2 * Hkv) * D, **bf),
+            q=torch.empty(B, M, H, D, **bf), k_new=torch.empty(cfg.n_layers, B, M, Hkv, D, **bf),
+            v_new=torch.empty(cfg.n_layers, B, M, Hkv, D, **bf), attn=torch.empty(B, M, H, D, **bf),
+            act=torch.empty(rows, cfg.d_ff, **bf), logits=torch.empty(B, M, cfg.vocab, dtype=torch.float32, device=dev),
+            ws=ops.attention_workspace(B, M, H, D, splits, dev), splits=splits)
+
+    # weight GEMM with the HF rounding points; <= 32 rows: our weight-streaming kernel
+    def _linear(self, x, w, epi, out, residual=None):
+        self.launches_per_step += 1
+        if x.shape[0] <= 32:
+            return ops.skinny_gemm(x, w, epi, residual=residual, out=out)
+        if epi == ops.EPI_NONE:
+            return torch.matmul(x, w.T, out=out)
+        if epi == ops.EPI_RESIDUAL:
+            return torch.add(F.linear(x, w), residual, out=out)
+        if epi == ops.EPI_F32:
+            out.copy_(F.linear(x, w))
+            return out
+        gu = F.linear(x, w)
+        n = gu.shape[1] // 2
+        return torch.mul(F.silu(gu[:, :n]), gu[:, n:], out=out)
+
+    def _forward(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor]) -> torch.Tensor:
+        cfg, B, M = self.cfg, self.B, pb.M
+        H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
+        rows = B * M
+        ops.embed_gather(self.w.embed, self.cur_token, M, pb.x)
+        x, x2 = pb.x, pb.x2
+        for l, lw in enumerate(self.w.layers):
+            ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pb.xn)
+            self._linear(pb.xn, lw["wqkv"], ops.EPI_NONE, pb.qkv)
+            ops.rope_stage(pb.qkv, self.cos, self.sin, self.seq_lens, B, M, H, Hkv, D, pb.q, pb.k_new[l], pb.v_new[l])
+            ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
+                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws)
+            self._linear(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, x2, residual=x)
+            ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pb.xn)
+            self._linear(pb.xn, lw["wgu"], ops.EPI_SWIGLU, pb.act)
+            self._linear(pb.act, lw["wd"], ops.EPI_RESIDUAL, x, residual=x2)
+            self.launches_per_step += 5     # 2 rmsnorm, rope_stage, attention partial + merge
+        ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pb.xn)
+        self._linear(pb.xn, self.w.lm_head, ops.EPI_F32, pb.logits.view(rows, cfg.vocab))
+        self.launches_per_step += 2         # embed gather, final norm
+        return pb.logits
+
+    # ------------------------------------------------------------------------------------
+    def step(self) -> None:
+        """One ensemble step for every sequence; asynchronous, no host sync, graph-capturable."""
+        self.launches_per_step = 0
+        logits_a = self._forward(self.pa, None)                                    # models/llava.py:294-305
+        ops.aggregate(logits_a, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.y_init)
+        u = None
+        if self.uniforms is not None:
+            # parity mode: this step's pre-drawn numbers (device-side gather keeps the graph static)
+            self._u_step.copy_(self.uniforms.index_select(0, self.step_ctr.long().clamp(max=self.uniforms.shape[0] - 1))[0])
+            u = self._u_step
+        ops.sample_masks(self.epi, self.topk_ids, self.y_init, self.probs, mode=self.mode,      # :342-346
+                         keep_relevant=self.keep_relevant, uniforms=u, seed=self.seed, offset=0,
+                         step=self.step_ctr, out=self.bitmask, n_masked=self.n_masked)
+        logits_b = self._forward(self.pb, self.bitmask)                            # :350-359
+        ops.aggregate(logits_b, self.aggregate, member_ids=self.member_ids, winner=self.winner,   # :361
+                      token=self.next_token, out_logits=self.out_logits if self.aggregate == "mean" else None)
+        ops.commit_winner(self.pb.k_new, self.pb.v_new, self.winner, self.seq_lens, self.k_cache, self.v_cache)
+        ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
+        self.cur_token.copy_(self.next_token)
+        self.launches_per_step += 6
+
+    def capture(self) -> None:
+        """Warm up once eagerly (restoring the state), then capture one step into a CUDA graph."""
+        snap = self._snapshot()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(snap)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step()
+        torch.cuda.synchronize()
+        self._restore(snap)
+        self._graph = g
+
+    def _snapshot(self):
+        pos = self.seq_lens.clone()
+        rows_k = [self.k_cache[:, b, :, int(pos[b])].clone() for b in range(self.B)]
+        rows_v = [self.v_cache[:, b, :, int(pos[b])].clone() for b in range(self.B)]
+        return dict(seq=pos, step=self.step_ctr.clone(), cur=self.cur_token.clone(), tok=self.tokens_out.clone(),
+                    rows_k=rows_k, rows_v=rows_v)
+
+    def _restore(self, s) -> None:
+        for b in range(self.B):
+            self.k_cache[:, b, :, int(s["seq"][b])] = s["rows_k"][b]
+            self.v_cache[:, b, :, int(s["seq"][b])] = s["rows_v"][b]
+        self.seq_lens.copy_(s["seq"]); self.step_ctr.copy_(s["step"]); self.cur_token.copy_(s["cur"])
+        self.tokens_out.copy_(s["tok"])
+
+    def decode(self, n_steps: int, use_graph: bool = True) -> None:
+        """Run n_steps ensemble steps (asynchronously)."""
+        if int(self.seq_lens.max()) + n_steps > self.S_max:
+            raise ops.DropDecError("decode would overflow the KV cache")
+        if use_graph and self._graph is None:
+            self.capture()
+        for _ in range(n_steps):
+            if use_graph:
+                self._graph.replay()
+            else:
+                self.step()
+
+    # ------------------------------------------------------------------------------------
+    # prefill: library ops (not the hot path)
+    # ------------------------------------------------------------------------------------
+    def _norm_t(self, x, w):
+        xf = x.float()
+        xn = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.cfg.rms_eps)).to(torch.bfloat16)
+        return xn * w
+
+    def prefill(self, embeds: torch.Tensor, vis_start: Sequence[int]) -> torch.Tensor:
+        """embeds bf16 [B, S0, d] (merged text|visual|text).  Fills the cache and returns the
+        final-norm hidden states [B, S0, d]."""
+        cfg, B = self.cfg, self.B
+        H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
+        S0 = embeds.shape[1]
+        cos, sin = self.cos[:S0, None, :], self.sin[:S0, None, :]
+
+        def rope(t):                                   # [B, S0, heads, D]
+            t = t.float()
+            x1, x2 = t[..., :D // 2], t[..., D // 2:]
+            return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], -1).to(torch.bfloat16)
+
+        x = embeds.to(torch.bfloat16)
+        for l, lw in enumerate(self.w.layers):
+            h = self._norm_t(x, lw["ln1"])
+            qkv = F.linear(h, lw["wqkv"])
+            q, k, v = qkv.split([H * D, Hkv * D, Hkv * D], dim=-1)
+            q, k = rope(q.view(B, S0, H, D)), rope(k.view(B, S0, Hkv, D))
+            v = v.view(B, S0, Hkv, D)
+            self.k_cache[l, :, :, :S0] = k.transpose(1, 2)
+            self.v_cache[l, :, :, :S0] = v.transpose(1, 2)
+            a = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                               is_causal=True, enable_gqa=(H != Hkv))
+            x = x + F.linear(a.transpose(1, 2).reshape(B, S0, H * D), lw["wo"])
+            h = self._norm_t(x, lw["ln2"])
+            gu = F.linear(h, lw["wgu"])
+            x = x + F.linear(F.silu(gu[..., :cfg.d_ff]) * gu[..., cfg.d_ff:], lw["wd"])
+        self.seq_lens.fill_(S0)
+        self.vis_start.copy_(torch.as_tensor(list(vis_start), dtype=torch.int32))
+        self.step_ctr.zero_()
+        return self._norm_t(x, self.w.norm)
+
+    def load_prefill(self, k: torch.Tensor, v: torch.Tensor, vis_start: Sequence[int]) -> None:
+        """Inject an externally computed prefix cache: k, v [L, B, H_kv, S0, D] (parity tests)."""
+        S0 = k.shape[3]
+        self.k_cache[:, :, :, :S0] = k.to(self.dev, torch.bfloat16)
+        self.v_cache[:, :, :, :S0] = v.to(self.dev, torch.bfloat16)
+        self.seq_lens.fill_(S0)
+        self.vis_start.copy_(torch.as_tensor(list(vis_start), dtype=torch.int32))
+        self.step_ctr.zero_()
+
+    def uncertainty_stage(self, vis_hidden: torch.Tensor) -> None:
+        """vis_hidden bf16 [B, n_vis, d] (final-norm hidden states of the visual rows)."""
+        e, a, v, ids = ops.uncertainty_project(vis_hidden.contiguous(), self.w.lm_head, topk=self.topk,
+                                               round_logits=self.round_logits)
+        self.epi.copy_(e); self.alea.copy_(a); self.var.copy_(v); self.topk_ids.copy_(ids)
+
+    def first_token(self, last_hidden: torch.Tensor) -> None:
+        """The first generated token is the plain argmax of the unmasked prefill
+        (models/llava.py:382-388); last_hidden bf16 [B, d], final-norm."""
+        B, V = self.B, self.cfg.vocab
+        logits = self.pa.logits.view(B, V)
+        self._linear(last_hidden.contiguous(), self.w.lm_head, ops.EPI_F32, logits)
+        ops.aggregate(self.pa.logits, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.cur_token)
+        self.tokens_out[:, 0] = self.cur_token
+        self.step_ctr.zero_()          # ensemble steps done; also the sampler's Philox call index / K
+
+    def set_uniforms(self, u: Optional[torch.Tensor]) -> None:
+        """Parity mode: u [steps, B, K, n_vis] replaces the Philox draws (step s uses u[s])."""
+        self._graph = None
+        if u is None:
+            self.uniforms = self._u_step = None
+            return
+        self.uniforms = u.to(self.dev, torch.float32).contiguous()
+        self._u_step = torch.empty(self.B, self.K, self.n_vis, dtype=torch.float32, device=self.dev)
+
+    def generated(self) -> torch.Tensor:
+        """Tokens generated so far, int32 [B, n]."""
+        return self.tokens_out[:, :int(self.step_ctr.item()) + 1]

@@ -184,7 +184,9 @@ int dd_rope_stage(const void* qkv, const float* cos_tab, const float* sin_tab, c
 int dd_embed_gather(const void* embed /* bf16 [V, d] */, const int32_t* token /* [B] */, int B, int M,
                     int d, void* x /* bf16 [B*M, d] */, dd_stream_t stream);
 
-/* End of one ensemble step: tokens_out[b, *step] = token[b]; seq_lens[b] += 1; *step += 1. */
+/* End of one ensemble step (*step = ensemble steps done so far, 0-based):
+ * tokens_out[b, *step + 1] = token[b]  (column 0 holds the un-ensembled first token,
+ * models/llava.py:382-388); seq_lens[b] += 1; *step += 1. */
 int dd_step_advance(const int32_t* token /* [B] */, int32_t* tokens_out /* [B, max_steps] */,
                     int max_steps, int32_t* seq_lens /* [B] */, int32_t* step /* scalar */, int B,
                     dd_stream_t stream);

@@ -33,7 +33,7 @@ __all__ = [
     "calculate_vision_uncertainty", "topk_token_ids", "relevant_visual_tokens",
     "drop_probabilities", "sample_mask_epis", "quantile_threshold",
     "sample_mask_quantile", "select_by_vote", "select_by_average",
-    "entropy_varentropy", "dropout_decode", "DecodeTrace", "bf16r",
+    "entropy_varentropy", "dropout_decode", "ensemble_steps", "DecodeTrace", "bf16r",
     "rope_table",
 ]
 
@@ -387,8 +387,23 @@ def dropout_decode(lm: OracleLM, prompt_embeds: torch.Tensor, vis_start: int, n_
         tr.vis_hidden, tr.last_hidden = vis_hidden.clone(), hidden[-1].clone()
         tr.prefill_cache = copy.deepcopy(cache)
 
+    ensemble_steps(lm, cache, tok, epis, tr.topk_ids, vis_start, n_vis, max_new_tokens - 1, probs, uniforms,
+                   mode=mode, keep_relevant=keep_relevant, aggregate=aggregate, eos_token_id=eos_token_id,
+                   keep_logits=keep_logits, trace=tr)
+    return tr
+
+
+def ensemble_steps(lm: OracleLM, cache: OracleCache, tok: int, epis: torch.Tensor, topk_ids: torch.Tensor,
+                   vis_start: int, n_vis: int, n_steps: int, probs: Sequence[float],
+                   uniforms: Optional[torch.Tensor], mode: str = "cumulative", keep_relevant: bool = True,
+                   aggregate: str = "vote", eos_token_id: Optional[int] = None, keep_logits: bool = False,
+                   trace: Optional[DecodeTrace] = None) -> DecodeTrace:
+    """The decode branch of forward() (models/llava.py:254-283, 292-376) driven by the HF greedy
+    loop: per token one preliminary forward, K masked forwards each on a deep copy of the whole
+    cache, then the vote.  Starts from `cache` (prefix already filled) and the last token `tok`."""
+    tr = trace if trace is not None else DecodeTrace(tokens=[tok])
     step = 0
-    while len(tr.tokens) < max_new_tokens and (eos_token_id is None or tok != eos_token_id):
+    while step < n_steps and (eos_token_id is None or tok != eos_token_id):
         S = cache.seq_len()
         x = lm.embed(torch.tensor([tok]))                    # :229
         ones = torch.ones(S + 1, dtype=torch.long)           # :266-283
@@ -397,7 +412,7 @@ def dropout_decode(lm: OracleLM, prompt_embeds: torch.Tensor, vis_start: int, n_
         prelim = lm.logits(lm.forward(x, cache, ones, pos))  # :294-305 (cache mutated, then dropped)
         y0 = int(torch.argmax(prelim[0]).item())
         tr.y_init.append(y0)
-        rel = relevant_visual_tokens(prelim[None], tr.topk_ids) if keep_relevant else None
+        rel = relevant_visual_tokens(prelim[None], topk_ids) if keep_relevant else None
         tr.relevant.append([] if rel is None else rel.tolist())
 
         member_logits, member_caches, dropped_sets, masked_n = [], [], [], []

@@ -82,7 +82,8 @@ def close(a, b, what, rtol=1e-5, atol=1e-6):
 # 1. uncertainty stage: h_vis, lm_head from seeds -> logits -> reference functions
 # ----------------------------------------------------------------------------------------
 sys.path.insert(0, os.path.join(REPO, "tests"))
-from golden_cases import UNCERT_CASES, uncert_inputs, aggregate_inputs  # noqa: E402
+from golden_cases import (UNCERT_CASES, uncert_inputs, aggregate_inputs, tiny_decode_inputs,  # noqa: E402
+                          tiny_uniforms, TINY_N_VIS, TINY_T, TINY_PROBS, TINY_SEED)
 
 
 def gold_uncertainty():
@@ -322,27 +323,21 @@ def ref_generate(model, lm, input_ids, attention_mask, max_new_tokens, seed):
 
 def gold_decode():
     cfg = LMConfig.tiny()
-    n_vis, T, probs, seed = 576, 32, [0.3, 0.5, 0.7], 24
+    n_vis, T, probs, seed = TINY_N_VIS, TINY_T, TINY_PROBS, TINY_SEED
     out = {}
     summary = {}
     for faithful in (False, True):
         tag = "bf16" if faithful else "fp32"
         w = init_lm_weights(cfg, seed=0, std=0.02, head_std=0.08)
         lm = OracleLM(cfg, w, faithful=faithful)
-        g = torch.Generator().manual_seed(1)
-        image_token = cfg.vocab - 1                         # like LLaVA's out-of-text-vocab <image> id 32000
-        prompt = torch.randint(3, 30000, (1, 18), generator=g)
-        prompt[0, 0] = 1
-        prompt[0, 5] = image_token                          # start_image_pos = 5
-        feats = oracle.bf16r(torch.randn(1, n_vis, cfg.d_model, generator=g))
+        prompt, feats, image_token = tiny_decode_inputs(cfg.vocab, cfg.d_model)
         model = make_ref_model(lm, feats, image_token, pad_token=-1)
         ref = ref_generate(model, lm, prompt, torch.ones_like(prompt), T, seed)
         assert model.start_image_pos == [5] and model.end_image_pos == [5 + n_vis - 1]
         # the merged prompt embedding sequence, as _merge builds it (models/llava.py:74-153)
         emb = lm.w["embed"][prompt[0].clamp(max=cfg.vocab - 1)]
         merged = torch.cat([emb[:5], feats[0], emb[6:]], dim=0)
-        torch.manual_seed(seed)
-        U = torch.rand(T - 1, len(probs), n_vis)
+        U = tiny_uniforms()
         tr = dropout_decode(lm, merged, 5, n_vis, T, probs, U, mode="cumulative", topk=5, keep_logits=True)
         assert tr.tokens == ref["tokens"], (tr.tokens, ref["tokens"])
         for t in range(T - 1):

@@ -41,3 +41,25 @@ def aggregate_inputs():
         elif pat == 3 and K >= 4:
             l[0, 1] += 20; l[1, 2] += 20; l[2, 2] += 20; l[3, 1] += 20   # 2-2 tie -> id of member 0
         yield K, l
+
+
+# ---- config 1 (BASELINE.json configs[0]): tiny LLaVA-1.5, one image, K=3, 32 new tokens -------------
+TINY_N_VIS, TINY_T, TINY_PROBS, TINY_SEED, TINY_VIS_START = 576, 32, [0.3, 0.5, 0.7], 24, 5
+
+
+def tiny_decode_inputs(cfg_vocab=32064, d_model=256):
+    """prompt ids [1,18] (BOS first, <image> at index 5) and projected image features [1,576,d]."""
+    g = torch.Generator().manual_seed(1)
+    image_token = cfg_vocab - 1
+    prompt = torch.randint(3, 30000, (1, 18), generator=g)
+    prompt[0, 0] = 1
+    prompt[0, TINY_VIS_START] = image_token
+    feats = bf16r(torch.randn(1, TINY_N_VIS, d_model, generator=g))
+    return prompt, feats, image_token
+
+
+def tiny_uniforms():
+    """The numbers K x 31 consecutive torch.rand_like(epis) calls draw after torch.manual_seed(24)
+    (models/llava.py:16-18, 650)."""
+    g = torch.Generator().manual_seed(TINY_SEED)
+    return torch.rand(TINY_T - 1, len(TINY_PROBS), TINY_N_VIS, generator=g)

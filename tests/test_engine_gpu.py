@@ -1,0 +1,155 @@
+"""End-to-end parity of the B200 decode engine against the CPU oracle on BASELINE.json config 1
+(tiny random-init LLaVA-1.5: 2 layers, d=256, 576 visual tokens, K=3, 32 new tokens).
+
+The oracle runs in its 'bf16-faithful' (fp32-accumulate) mode, i.e. the same rounding points as
+the engine, and the golden fixture tests/golden/decode_tiny.npz was checked against the
+reference's real forward() (tests/golden/make_golden.py).  Bars: mask index sets, member argmax
+ids, vote winners and the greedy token sequence are bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_cases import (TINY_N_VIS, TINY_PROBS, TINY_T, TINY_VIS_START, tiny_decode_inputs, tiny_uniforms)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tiny(cuda):
+    """Oracle prefill on the host CPU + an engine holding the same weights."""
+    import oracle
+    from dropoutdecoding_b200.engine import DecoderConfig, DecoderWeights, DropoutDecodeEngine
+    ocfg = oracle.LMConfig.tiny()
+    w = oracle.init_lm_weights(ocfg, seed=0, std=0.02, head_std=0.08)
+    lm = oracle.OracleLM(ocfg, w, faithful=True)
+    prompt, feats, image_token = tiny_decode_inputs(ocfg.vocab, ocfg.d_model)
+    emb = lm.w["embed"][prompt[0].clamp(max=ocfg.vocab - 1)]
+    merged = torch.cat([emb[:TINY_VIS_START], feats[0], emb[TINY_VIS_START + 1:]], dim=0)
+    U = tiny_uniforms()
+    with torch.no_grad():
+        tr = oracle.dropout_decode(lm, merged, TINY_VIS_START, TINY_N_VIS, TINY_T, TINY_PROBS, U,
+                                   mode="cumulative", topk=5, keep_logits=True, keep_prefill=True)
+    weights = DecoderWeights.from_named(DecoderConfig.tiny(), w, cuda)
+    return dict(lm=lm, merged=merged, U=U, trace=tr, weights=weights, Engine=DropoutDecodeEngine)
+
+
+def make_engine(t, cuda, **kw):
+    return t["Engine"](t["weights"], batch=1, n_vis=TINY_N_VIS, max_seq=640, probs=TINY_PROBS, mode="cumulative",
+                       topk=5, seed=24, max_steps=64, **kw)
+
+
+def inject_oracle_prefill(eng, t, cuda):
+    tr = t["trace"]
+    k = torch.stack(tr.prefill_cache.k)[:, None]        # [L, 1, H_kv, S0, D]
+    v = torch.stack(tr.prefill_cache.v)[:, None]
+    eng.load_prefill(k, v, [TINY_VIS_START])
+    eng.set_uniforms(t["U"][:, None].contiguous())       # [steps, B=1, K, n_vis]
+
+
+def test_oracle_trace_matches_committed_golden(tiny, golden_dir):
+    """The oracle run on this box's CPU reproduces the fixture minted in the build container."""
+    z = np.load(os.path.join(golden_dir, "decode_tiny.npz"))
+    tr = tiny["trace"]
+    assert tr.tokens == z["bf16.tokens"].tolist()
+    assert tr.winner == z["bf16.winner"].tolist()
+    assert tr.masked_numbers == z["bf16.masked_numbers"].tolist()
+
+
+def test_uncertainty_stage_and_first_token(tiny, cuda):
+    eng = make_engine(tiny, cuda)
+    tr = tiny["trace"]
+    inject_oracle_prefill(eng, tiny, cuda)
+    eng.uncertainty_stage(tr.vis_hidden.to(cuda).bfloat16()[None])
+    eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None])
+    torch.cuda.synchronize()
+    want = tr.uncert["epis_uncert_per_token"][0]
+    rel = ((eng.epi[0].cpu() - want).abs() / want.abs()).max().item()
+    assert rel <= 1e-3, f"epistemic rel err {rel:.2e}"
+    assert np.array_equal(np.sort(eng.topk_ids[0].cpu().numpy(), -1), np.sort(tr.topk_ids[0].numpy(), -1))
+    assert int(eng.cur_token[0]) == tr.tokens[0]
+
+
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "cuda_graph"])
+def test_ensemble_decode_bit_exact(tiny, cuda, use_graph):
+    """Teacher-forced at the sampler inputs (oracle epi / top-k table, so that a 1e-6 difference in
+    epi cannot move a draw across its threshold); everything downstream is the CUDA path."""
+    eng = make_engine(tiny, cuda)
+    tr = tiny["trace"]
+    inject_oracle_prefill(eng, tiny, cuda)
+    eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda))
+    eng.topk_ids.copy_(tr.topk_ids.to(cuda).int())
+    eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None])
+    n_steps = TINY_T - 1
+    if use_graph:
+        eng.decode(n_steps, use_graph=True)
+        torch.cuda.synchronize()
+        assert eng.generated()[0].tolist() == tr.tokens
+        return
+    for s in range(n_steps):
+        eng.decode(1, use_graph=False)
+        torch.cuda.synchronize()
+        assert int(eng.y_init[0]) == tr.y_init[s], f"step {s}: y_init"
+        assert eng.n_masked[0].tolist() == tr.masked_numbers[s], f"step {s}: masked_numbers"
+        w = eng.bitmask[0].cpu().numpy().astype(np.uint32)
+        for m in range(3):
+            bits = ((w[m][:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(-1)[:TINY_N_VIS]
+            assert np.nonzero(bits)[0].tolist() == tr.dropped[s][m], f"step {s} member {m}: mask index set"
+        assert eng.member_ids[0].tolist() == tr.member_ids[s], f"step {s}: member argmax ids"
+        assert int(eng.winner[0]) == tr.winner[s], f"step {s}: vote winner"
+        assert int(eng.next_token[0]) == tr.tokens[s + 1], f"step {s}: token"
+    assert eng.generated()[0].tolist() == tr.tokens
+
+
+def test_member_logits_close_to_oracle(tiny, cuda):
+    """Aggregated (winner) logits of the first ensemble step within 2e-2 absolute (north_star bar)."""
+    eng = make_engine(tiny, cuda)
+    tr = tiny["trace"]
+    inject_oracle_prefill(eng, tiny, cuda)
+    eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda))
+    eng.topk_ids.copy_(tr.topk_ids.to(cuda).int())
+    eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None])
+    eng.decode(1, use_graph=False)
+    torch.cuda.synchronize()
+    got = eng.pb.logits[0, int(eng.winner[0])].cpu()
+    assert (got - tr.step_logits[1]).abs().max().item() <= 2e-2
+
+
+def test_full_gpu_pipeline_prefill_to_tokens(tiny, cuda):
+    """Nothing injected: GPU prefill (library ops) -> tcgen05 uncertainty stage -> ensemble decode.
+    The prefill is a different summation order from the oracle's, so intermediate bf16 roundings
+    may flip; the bars here are the uncertainty tolerance and agreement of the token prefix."""
+    eng = make_engine(tiny, cuda)
+    tr = tiny["trace"]
+    hidden = eng.prefill(tiny["merged"].to(cuda).bfloat16()[None], [TINY_VIS_START])
+    eng.set_uniforms(tiny["U"][:, None].contiguous())
+    eng.uncertainty_stage(hidden[:, TINY_VIS_START:TINY_VIS_START + TINY_N_VIS])
+    eng.first_token(hidden[:, -1])
+    eng.decode(TINY_T - 1, use_graph=True)
+    torch.cuda.synchronize()
+    want = tr.uncert["epis_uncert_per_token"][0]
+    rel = ((eng.epi[0].cpu() - want).abs() / want.abs()).max().item()
+    assert rel <= 5e-3, f"epistemic rel err after a bf16 GPU prefill {rel:.2e}"
+    got = eng.generated()[0].tolist()
+    agree = next((i for i, (a, b) in enumerate(zip(got, tr.tokens)) if a != b), len(got))
+    assert agree >= 4, f"token sequences diverge at {agree}: {got[:8]} vs {tr.tokens[:8]}"
+
+
+def test_batch_is_independent_of_batch_size(tiny, cuda):
+    """B=3 copies of the same image give three times the B=1 result (no cross-sequence leakage)."""
+    tr = tiny["trace"]
+    eng = tiny["Engine"](tiny["weights"], batch=3, n_vis=TINY_N_VIS, max_seq=640, probs=TINY_PROBS,
+                         mode="cumulative", topk=5, seed=24, max_steps=64)
+    k = torch.stack(tr.prefill_cache.k)[:, None].expand(-1, 3, -1, -1, -1)
+    v = torch.stack(tr.prefill_cache.v)[:, None].expand(-1, 3, -1, -1, -1)
+    eng.load_prefill(k, v, [TINY_VIS_START] * 3)
+    eng.set_uniforms(tiny["U"][:, None].expand(-1, 3, -1, -1).contiguous())
+    eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda).expand(3, -1))
+    eng.topk_ids.copy_(tr.topk_ids.to(cuda).int().expand(3, -1, -1))
+    eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None].expand(3, -1).contiguous())
+    eng.decode(10, use_graph=True)
+    torch.cuda.synchronize()
+    for b in range(3):
+        assert eng.generated()[b].tolist() == tr.tokens[:11]

@@ -155,7 +155,7 @@ def ref_attention(q, k_new, v_new, kc, vc, seq_lens, vis_start, dropped, scale):
     (1, 3, 32, 32, 128, 700, [650], 576, 9),          # split-KV
     (1, 1, 32, 32, 128, 700, [593], 0, 4),            # preliminary pass: M=1, no mask
     (3, 3, 8, 8, 128, 300, [57, 200, 64], 40, 3),     # ragged batch, short sequences, empty splits
-    (2, 8, 32, 8, 128, 400, [333, 129], 250, 2),      # Mistral GQA, K=8 -> 32 query rows (2 row tiles)
+    (2, 8, 32, 8, 128, 400, [333, 290], 250, 2),      # Mistral GQA, K=8 -> 32 query rows (2 row tiles)
     (2, 3, 4, 4, 64, 700, [593, 624], 576, 2),        # tiny config: D=64
     (1, 4, 4, 2, 64, 128, [1], 1, 1),                 # single cached key
 ])
@@ -204,7 +204,7 @@ def test_commit_winner_and_step_advance(ops, cuda):
     hist = torch.zeros(B, 4, dtype=torch.int32, device=cuda)
     step = torch.tensor([1], dtype=torch.int32, device=cuda)
     ops.step_advance(tok, hist, seq, step)
-    assert seq.tolist() == [6, 10] and step.item() == 2 and hist[:, 1].tolist() == [11, 22]
+    assert seq.tolist() == [6, 10] and step.item() == 2 and hist[:, 2].tolist() == [11, 22]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -297,9 +297,13 @@ def test_uncertainty_matches_reference(ops, cuda, golden_dir, case):
     epi, alea, var, ids = ops.uncertainty_project(h.to(cuda).bfloat16()[None].contiguous(),
                                                   w.to(cuda).bfloat16().contiguous(), topk=k)
     torch.cuda.synchronize()
-    for got, key, rtol in ((epi, "epi", 1e-3), (alea, "alea", 1e-3), (var, "var", 2e-3)):
+    # epistemic: the north-star bar, 1e-3 relative.  aleatoric / variance: same relative bar plus an
+    # absolute floor of a few fp32 ulps of the O(1) terms they are sums of -- for a peaked row
+    # (p_max ~ 1 - 1e-5) alea is ~1e-5 and the reference's own fp32 softmax is only that accurate.
+    for got, key, rtol, atol in ((epi, "epi", 1e-3, 0.0), (alea, "alea", 1e-3, 2e-6), (var, "var", 1e-3, 1e-9)):
         want = z[f"{name}.{key}"]
-        rel = np.abs(got[0].cpu().numpy() - want) / np.maximum(np.abs(want), 1e-12)
+        err = np.abs(got[0].cpu().numpy() - want) - atol
+        rel = err / np.maximum(np.abs(want), 1e-30)
         assert rel.max() <= rtol, f"{name}.{key}: max rel err {rel.max():.3e}"
     # top-k id SETS are exact wherever the k-th / (k+1)-th logits are not a numerical tie
     safe = z[f"{name}.topk_gap"] > 1e-4 * np.maximum(1.0, np.abs(z[f"{name}.row_max"]))

@@ -117,8 +117,39 @@ def bench_uncertainty():
                               peak=SRC)))
 
 
+def one_shot(which):
+    """Single launches for ncu (no timing loop)."""
+    if which == "uncertainty1":
+        h = torch.randn(1, 576, 4096, device=dev).bfloat16()
+        w = (torch.randn(32064, 4096, device=dev) * 0.02).bfloat16()
+        for _ in range(2):
+            ops.uncertainty_project(h, w, topk=5)
+    elif which == "attention64":
+        B, M, H, D, S = 64, 3, 32, 128, 849
+        q = torch.randn(B, M, H, D, device=dev).bfloat16()
+        kn = torch.randn(B, M, H, D, device=dev).bfloat16(); vn = torch.randn_like(kn)
+        kc = torch.randn(B, H, S + 8, D, device=dev).bfloat16(); vc = torch.randn_like(kc)
+        sl = torch.full((B,), S, dtype=torch.int32, device=dev); vs = torch.full((B,), 5, dtype=torch.int32, device=dev)
+        bm = torch.randint(-2 ** 31, 2 ** 31 - 1, (B, M, 18), dtype=torch.int32, device=dev)
+        for _ in range(3):
+            ops.decode_attention(q, kn, vn, kc, vc, sl, vs, bm, 576, 1 / math.sqrt(D), 1)
+    elif which == "gemm1":
+        for (M, N, K, epi) in [(3, 4096, 4096, ops.EPI_NONE), (3, 12288, 4096, ops.EPI_NONE),
+                               (3, 22016, 4096, ops.EPI_SWIGLU), (3, 4096, 11008, ops.EPI_NONE)]:
+            x = torch.randn(M, K, device=dev).bfloat16()
+            w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+            for _ in range(2):
+                flush_l2()
+                ops.skinny_gemm(x, w, epi)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("uncertainty1", "attention64", "gemm1"):
+        with torch.no_grad():
+            one_shot(which)
+        sys.exit(0)
     with torch.no_grad():
         if which in ("attention", "all"):
             bench_attention()
