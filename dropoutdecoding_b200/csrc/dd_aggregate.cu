@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __r
   __shared__ ArgMax s_warp[kAggThreads / 32];
   __shared__ int s_ids[DD_MAX_MEMBERS];
   __shared__ int s_win;
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* base = logits + (size_t)b * K * V;
   const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
@@ -115,8 +117,7 @@ extern "C" int dd_aggregate(const float* logits, int B, int K, int V, int mode, 
   DD_CHECK_ARG(mode == DD_AGG_VOTE || mode == DD_AGG_MEAN, "dd_aggregate: bad mode %d", mode);
   DD_CHECK_ARG(mode != DD_AGG_MEAN || out_logits, "dd_aggregate: mean mode needs out_logits");
   if (B == 0) return DD_OK;
-  aggregate_kernel<<<B, kAggThreads, 0, (cudaStream_t)stream>>>(logits, K, V, mode, member_ids, winner, token,
-                                                                out_logits);
-  DD_CHECK_LAUNCH();
+  DD_LAUNCH_CHAIN(aggregate_kernel, dim3(B), dim3(kAggThreads), 0, (cudaStream_t)stream, logits, K, V, mode,
+                  member_ids, winner, token, out_logits);
   return DD_OK;
 }

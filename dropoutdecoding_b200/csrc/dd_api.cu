@@ -1,4 +1,5 @@
 // Error plumbing and version of the C ABI (include/dropdec.h).
+#include <cstdlib>
 #include <string>
 
 #include "dd_common.cuh"
@@ -12,6 +13,13 @@ void set_error(const char* fmt, ...) {
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
   g_last_error = buf;
+}
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DD_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 }  // namespace dd
 

@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnPa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int G = p.H / p.H_kv, R = p.M * G;
+  pdl_trigger();
+  pdl_wait();
   const int S = p.seq_lens[b];
   const int vis0 = p.vis_start ? p.vis_start[b] : 0;
   const int vis1 = p.bitmask ? vis0 + p.n_vis : vis0;  // empty span when unmasked
@@ -284,6 +286,8 @@ __global__ void __launch_bounds__(D) attn_merge_kernel(const AttnParams p, const
                                                        const __nv_bfloat16* __restrict__ v_new,
                                                        __nv_bfloat16* __restrict__ out) {
   __shared__ float s_part[D / 32];
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, m = blockIdx.y, b = blockIdx.z, d = threadIdx.x;
   const int G = p.H / p.H_kv, hkv = h / G, r = m * G + (h % G), R = p.M * G;
   const size_t qoff = (((size_t)b * p.M + m) * p.H + h) * D;
@@ -330,11 +334,9 @@ static int launch_attn(const AttnParams& p, const void* k_new, const void* v_new
                                        (int)smem));
     configured = smem;
   }
-  attn_partial_kernel<D, QT><<<dim3(p.num_splits, p.H_kv, p.B), kAttnThreads, smem, st>>>(p);
-  DD_CHECK_LAUNCH();
-  attn_merge_kernel<D><<<dim3(p.H, p.M, p.B), D, 0, st>>>(p, (const __nv_bfloat16*)k_new,
-                                                          (const __nv_bfloat16*)v_new, (__nv_bfloat16*)out);
-  DD_CHECK_LAUNCH();
+  DD_LAUNCH_CHAIN(attn_partial_kernel<D, QT>, dim3(p.num_splits, p.H_kv, p.B), dim3(kAttnThreads), smem, st, p);
+  DD_LAUNCH_CHAIN(attn_merge_kernel<D>, dim3(p.H, p.M, p.B), dim3(D), 0, st, p, (const __nv_bfloat16*)k_new,
+                  (const __nv_bfloat16*)v_new, (__nv_bfloat16*)out);
   return DD_OK;
 }
 

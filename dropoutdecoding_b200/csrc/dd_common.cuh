@@ -33,7 +33,39 @@ void set_error(const char* fmt, ...);
 #define DD_CHECK_LAUNCH() DD_CHECK_CUDA(cudaGetLastError())
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  One ensemble step is a chain of ~600 short kernels; with
+// plain stream order every boundary costs a launch + ramp-up bubble in which HBM idles.  All chain
+// kernels are launched with programmaticStreamSerialization: a kernel's CTAs may become resident
+// while its predecessor is still running, do work that does not depend on it (address setup, the
+// first batch of weight loads) and then block in pdl_wait() until the predecessor has completed
+// and flushed.  Rule: nothing written by an earlier kernel is touched before pdl_wait(), and
+// nothing is written before it either.  DD_PDL=0 in the environment falls back to plain launches.
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#define DD_LAUNCH_CHAIN(...) DD_CHECK_CUDA(::dd::launch_chain(__VA_ARGS__))
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 

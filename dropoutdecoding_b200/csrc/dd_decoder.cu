@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const __nv_bfloat
                                                               const __nv_bfloat16* __restrict__ w, int d,
                                                               float eps, __nv_bfloat16* __restrict__ y) {
   __shared__ float s_part[kNormThreads / 32];
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x, tid = threadIdx.x;
   const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)row * d);
   const uint4* w4 = reinterpret_cast<const uint4*>(w);
@@ -59,6 +61,8 @@ __global__ void rope_stage_kernel(const __nv_bfloat16* __restrict__ qkv, const f
                                   const float* __restrict__ sin_tab, const int32_t* __restrict__ seq_lens,
                                   int M, int H, int H_kv, int D, __nv_bfloat16* __restrict__ q_out,
                                   __nv_bfloat16* __restrict__ k_new, __nv_bfloat16* __restrict__ v_new) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;  // b*M + m
   const int b = row / M;
   const int pos = seq_lens[b];
@@ -84,6 +88,8 @@ __global__ void rope_stage_kernel(const __nv_bfloat16* __restrict__ qkv, const f
 
 __global__ void embed_gather_kernel(const uint4* __restrict__ embed, const int32_t* __restrict__ token, int M,
                                     int dvec, uint4* __restrict__ x) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;  // b*M + m
   const int t = token[row / M];
   for (int j = threadIdx.x; j < dvec; j += blockDim.x) x[(size_t)row * dvec + j] = embed[(size_t)t * dvec + j];
@@ -91,6 +97,8 @@ __global__ void embed_gather_kernel(const uint4* __restrict__ embed, const int32
 
 __global__ void step_advance_kernel(const int32_t* __restrict__ token, int32_t* tokens_out, int max_steps,
                                     int32_t* seq_lens, int32_t* step, int B) {
+  pdl_trigger();
+  pdl_wait();
   const int st = *step;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     if (tokens_out && st + 1 < max_steps) tokens_out[(size_t)b * max_steps + st + 1] = token[b];
@@ -105,6 +113,8 @@ __global__ void commit_winner_kernel(const uint4* __restrict__ k_new, const uint
                                      const int32_t* __restrict__ winner, const int32_t* __restrict__ seq_lens,
                                      uint4* __restrict__ k_cache, uint4* __restrict__ v_cache, int B, int M,
                                      int H_kv, int dvec, int S_max) {
+  pdl_trigger();
+  pdl_wait();
   const int l = blockIdx.x, b = blockIdx.y;
   const int w = winner[b], pos = seq_lens[b];
   if (pos >= S_max) return;
@@ -124,9 +134,8 @@ extern "C" int dd_rmsnorm(const void* x, const void* w, int M, int d, float eps,
   DD_CHECK_ARG(x && w && y, "dd_rmsnorm: null pointer");
   DD_CHECK_ARG(M >= 0 && d > 0 && d % 8 == 0, "dd_rmsnorm: d=%d must be a positive multiple of 8", d);
   if (M == 0) return DD_OK;
-  rmsnorm_kernel<<<M, kNormThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
-                                                               d, eps, (__nv_bfloat16*)y);
-  DD_CHECK_LAUNCH();
+  DD_LAUNCH_CHAIN(rmsnorm_kernel, dim3(M), dim3(kNormThreads), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x,
+                  (const __nv_bfloat16*)w, d, eps, (__nv_bfloat16*)y);
   return DD_OK;
 }
 
@@ -137,10 +146,9 @@ extern "C" int dd_rope_stage(const void* qkv, const float* cos_tab, const float*
   DD_CHECK_ARG(qkv && cos_tab && sin_tab && seq_lens && q_out && k_new && v_new, "dd_rope_stage: null pointer");
   DD_CHECK_ARG(D % 2 == 0 && H >= 1 && H_kv >= 1, "dd_rope_stage: bad head shape");
   if (B * M == 0) return DD_OK;
-  rope_stage_kernel<<<B * M, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv, cos_tab, sin_tab, seq_lens, M, H, H_kv, D, (__nv_bfloat16*)q_out,
-      (__nv_bfloat16*)k_new, (__nv_bfloat16*)v_new);
-  DD_CHECK_LAUNCH();
+  DD_LAUNCH_CHAIN(rope_stage_kernel, dim3(B * M), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)qkv,
+                  cos_tab, sin_tab, seq_lens, M, H, H_kv, D, (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_new,
+                  (__nv_bfloat16*)v_new);
   return DD_OK;
 }
 
@@ -150,8 +158,8 @@ extern "C" int dd_embed_gather(const void* embed, const int32_t* token, int B, i
   DD_CHECK_ARG(embed && token && x, "dd_embed_gather: null pointer");
   DD_CHECK_ARG(d % 8 == 0, "dd_embed_gather: d=%d must be a multiple of 8", d);
   if (B * M == 0) return DD_OK;
-  embed_gather_kernel<<<B * M, 128, 0, (cudaStream_t)stream>>>((const uint4*)embed, token, M, d / 8, (uint4*)x);
-  DD_CHECK_LAUNCH();
+  DD_LAUNCH_CHAIN(embed_gather_kernel, dim3(B * M), dim3(128), 0, (cudaStream_t)stream, (const uint4*)embed, token,
+                  M, d / 8, (uint4*)x);
   return DD_OK;
 }
 
@@ -160,8 +168,8 @@ extern "C" int dd_step_advance(const int32_t* token, int32_t* tokens_out, int ma
   using namespace dd;
   DD_CHECK_ARG(token && seq_lens && step, "dd_step_advance: null pointer");
   if (B == 0) return DD_OK;
-  step_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(token, tokens_out, max_steps, seq_lens, step, B);
-  DD_CHECK_LAUNCH();
+  DD_LAUNCH_CHAIN(step_advance_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, token, tokens_out, max_steps,
+                  seq_lens, step, B);
   return DD_OK;
 }
 
@@ -173,9 +181,8 @@ extern "C" int dd_commit_winner(const void* k_new_all, const void* v_new_all, co
                "dd_commit_winner: null pointer");
   DD_CHECK_ARG(D % 8 == 0, "dd_commit_winner: D=%d must be a multiple of 8", D);
   if (L * B == 0) return DD_OK;
-  commit_winner_kernel<<<dim3(L, B), 128, 0, (cudaStream_t)stream>>>(
-      (const uint4*)k_new_all, (const uint4*)v_new_all, winner, seq_lens, (uint4*)k_cache_all,
-      (uint4*)v_cache_all, B, M, H_kv, D / 8, S_max);
-  DD_CHECK_LAUNCH();
+  DD_LAUNCH_CHAIN(commit_winner_kernel, dim3(L, B), dim3(128), 0, (cudaStream_t)stream, (const uint4*)k_new_all,
+                  (const uint4*)v_new_all, winner, seq_lens, (uint4*)k_cache_all, (uint4*)v_cache_all, B, M, H_kv,
+                  D / 8, S_max);
   return DD_OK;
 }

@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_kernel(const SamplerP
   __shared__ float s_below[DD_MAX_MEMBERS], s_above[DD_MAX_MEMBERS];
   __shared__ int s_count[DD_MAX_MEMBERS];
 
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.n_vis;
   const int chunks = (n + kSamplerThreads - 1) / kSamplerThreads;
@@ -210,8 +212,7 @@ extern "C" int dd_sample_masks(const float* epi, const int32_t* topk_ids, int to
   p.topk = topk; p.K = K; p.mode = mode; p.keep_relevant = keep_relevant; p.B = B; p.n_vis = n_vis;
   p.mask_words = mask_words;
   const size_t smem = mode == DD_MASK_QUANTILE ? (size_t)n_vis * sizeof(float) : 0;
-  sampler_kernel<<<B, kSamplerThreads, smem, (cudaStream_t)stream>>>(p);
-  DD_CHECK_LAUNCH();
+  DD_LAUNCH_CHAIN(sampler_kernel, dim3(B), dim3(kSamplerThreads), smem, (cudaStream_t)stream, p);
   return DD_OK;
 }
 

@@ -20,6 +20,51 @@ constexpr int kGemmWarps = 8;
 constexpr int kGemmThreads = kGemmWarps * 32;
 constexpr int kUnroll = 4;  // k-steps (of 32) whose loads are in flight per warp
 
+// kUnroll k-steps of this warp's weight rows -> registers (guards the tail of the k-slice)
+template <int NW>
+__device__ __forceinline__ void load_w_batch(uint4 (&dst)[kUnroll][NW][2], const __nv_bfloat16* const (&wrow)[NW][2],
+                                             int s0, int steps) {
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    if (s0 + u < steps) {
+      const int ko = (s0 + u) * 32;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        dst[u][i][0] = ld_stream_128(wrow[i][0] + ko);
+        dst[u][i][1] = ld_stream_128(wrow[i][1] + ko);
+      }
+    }
+  }
+}
+
+template <int MT, int NW>
+__device__ __forceinline__ void mma_batch(float (&acc)[NW][MT][4], const uint4 (&wa)[kUnroll][NW][2],
+                                          const __nv_bfloat16* const (&xrow)[MT], const bool (&xok)[MT], int s0,
+                                          int steps) {
+  uint4 xv[kUnroll][MT];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    if (s0 + u < steps) {
+      const int ko = (s0 + u) * 32;
+#pragma unroll
+      for (int j = 0; j < MT; ++j)
+        xv[u][j] = xok[j] ? *reinterpret_cast<const uint4*>(xrow[j] + ko) : make_uint4(0, 0, 0, 0);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    if (s0 + u < steps) {
+#pragma unroll
+      for (int i = 0; i < NW; ++i)
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          mma_bf16_16816(acc[i][j], wa[u][i][0].x, wa[u][i][1].x, wa[u][i][0].y, wa[u][i][1].y, xv[u][j].x, xv[u][j].y);
+          mma_bf16_16816(acc[i][j], wa[u][i][0].z, wa[u][i][1].z, wa[u][i][0].w, wa[u][i][1].w, xv[u][j].z, xv[u][j].w);
+        }
+    }
+  }
+}
+
 template <int MT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bfloat16* __restrict__ x,
                                                                    const __nv_bfloat16* __restrict__ w,
@@ -60,36 +105,18 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
 
-  for (int s0 = 0; s0 < steps; s0 += kUnroll) {
-    uint4 wa[kUnroll][NW][2];
-    uint4 xv[kUnroll][MT];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      if (s0 + u < steps) {
-        const int ko = (s0 + u) * 32;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-          wa[u][i][0] = ld_stream_128(wrow[i][0] + ko);
-          wa[u][i][1] = ld_stream_128(wrow[i][1] + ko);
-        }
-#pragma unroll
-        for (int j = 0; j < MT; ++j)
-          xv[u][j] = xok[j] ? *reinterpret_cast<const uint4*>(xrow[j] + ko) : make_uint4(0, 0, 0, 0);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      if (s0 + u < steps) {
-#pragma unroll
-        for (int i = 0; i < NW; ++i)
-#pragma unroll
-          for (int j = 0; j < MT; ++j) {
-            mma_bf16_16816(acc[i][j], wa[u][i][0].x, wa[u][i][1].x, wa[u][i][0].y, wa[u][i][1].y, xv[u][j].x,
-                           xv[u][j].y);
-            mma_bf16_16816(acc[i][j], wa[u][i][0].z, wa[u][i][1].z, wa[u][i][0].w, wa[u][i][1].w, xv[u][j].z,
-                           xv[u][j].w);
-          }
-      }
+  // PDL: the weights do not depend on the previous kernel -- put the first batch of the stream in
+  // flight, let the next kernel's CTAs become resident, and only then wait for our activations.
+  uint4 wa0[kUnroll][NW][2], wa1[kUnroll][NW][2];
+  load_w_batch<NW>(wa0, wrow, 0, steps);
+  pdl_trigger();
+  pdl_wait();
+  for (int s0 = 0; s0 < steps; s0 += 2 * kUnroll) {  // software-pipelined: next batch loads under the MMAs
+    if (s0 + kUnroll < steps) load_w_batch<NW>(wa1, wrow, s0 + kUnroll, steps);
+    mma_batch<MT, NW>(acc, wa0, xrow, xok, s0, steps);
+    if (s0 + kUnroll < steps) {
+      if (s0 + 2 * kUnroll < steps) load_w_batch<NW>(wa0, wrow, s0 + 2 * kUnroll, steps);
+      mma_batch<MT, NW>(acc, wa1, xrow, xok, s0 + kUnroll, steps);
     }
   }
 
@@ -141,13 +168,12 @@ static int launch_mt(int epi, const void* x, const void* w, const void* residual
   auto W = (const __nv_bfloat16*)w;
   auto R = (const __nv_bfloat16*)residual;
   switch (epi) {
-    case DD_EPI_NONE: skinny_gemm_kernel<MT, DD_EPI_NONE><<<grid, block, 0, st>>>(X, W, R, M, N, K, y); break;
-    case DD_EPI_RESIDUAL: skinny_gemm_kernel<MT, DD_EPI_RESIDUAL><<<grid, block, 0, st>>>(X, W, R, M, N, K, y); break;
-    case DD_EPI_F32: skinny_gemm_kernel<MT, DD_EPI_F32><<<grid, block, 0, st>>>(X, W, R, M, N, K, y); break;
-    case DD_EPI_SWIGLU: skinny_gemm_kernel<MT, DD_EPI_SWIGLU><<<grid, block, 0, st>>>(X, W, R, M, N, K, y); break;
+    case DD_EPI_NONE: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_NONE>, grid, block, 0, st, X, W, R, M, N, K, y); break;
+    case DD_EPI_RESIDUAL: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_RESIDUAL>, grid, block, 0, st, X, W, R, M, N, K, y); break;
+    case DD_EPI_F32: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_F32>, grid, block, 0, st, X, W, R, M, N, K, y); break;
+    case DD_EPI_SWIGLU: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_SWIGLU>, grid, block, 0, st, X, W, R, M, N, K, y); break;
     default: set_error("dd_skinny_gemm: bad epilogue %d", epi); return DD_ERR_INVALID_ARG;
   }
-  DD_CHECK_LAUNCH();
   return DD_OK;
 }
 

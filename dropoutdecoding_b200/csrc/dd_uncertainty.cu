@@ -37,6 +37,7 @@ constexpr int kNumSlots = 13;
 constexpr int kEpiThreads = 128;
 constexpr int kUncThreads = 192;
 constexpr int kTmemCols = 512;
+constexpr int kMaxMT = 5;  // row tiles of 128 per image (n_vis <= 640)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kEps = 1e-10f;  // models/llava.py:735,739
 
@@ -65,6 +66,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (spin > (1u << 28)) __trap();
   }
+}
+// One lane of a converged warp.  The surrounding loops run warp-converged so that slot indices and
+// descriptors stay in uniform registers; only the single-thread instructions sit under the predicate
+// (a `lane == 0` region makes ptxas wrap every UTMALDG / UTCHMMA in a waterfall loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -144,8 +157,8 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   // 1024-byte alignment for SWIZZLE_128B tiles (the dynamic smem base is only 16-byte aligned by contract)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kNumSlots * kSlotBytes);
-  // bars: full[kNumSlots] | empty[kNumSlots] | tmem_full | tmem_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumSlots + 2);
+  // bars: full[kNumSlots] | empty[kNumSlots] | tmem_full | tmem_empty[kMaxMT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumSlots + 1 + kMaxMT);
   float* s_col = reinterpret_cast<float*>(tmem_slot + 4);  // [4][BN]
   float* s_logp = s_col + 4 * BN;                            // [BN]
 
@@ -166,7 +179,7 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(bar_empty + 8 * i, 1);
     }
     mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, kEpiThreads);
+    for (int i = 0; i < kMaxMT; ++i) mbar_init(bar_tempty + 8 * i, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {  // TMEM: 512 columns, whole warp, then give the permit back
@@ -181,56 +194,64 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // =========================== TMA producer (warp-converged, one elected lane issues) =========
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int strip = strip_beg; strip < strip_end; ++strip) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+    }
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int strip = strip_beg; strip < strip_end; ++strip) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(bar_full + 8 * slot, BN * BK * 2);
           tma_load_2d(ring + slot * kSlotBytes, &tmap_w, bar_full + 8 * slot, kb * BK, strip * BN);
-          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
-#pragma unroll 1
-          for (int mt = 0; mt < NUM_MT; ++mt) {
-            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        }
+        __syncwarp();
+        if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+#pragma unroll
+        for (int mt = 0; mt < NUM_MT; ++mt) {
+          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(bar_full + 8 * slot, BM * BK * 2);
             tma_load_3d(ring + slot * kSlotBytes, &tmap_a, bar_full + 8 * slot, kb * BK, mt * BM, img);
-            if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 5) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t phase = 0, it = 0;
-      for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
-        mbar_wait(bar_tempty, (it & 1) ^ 1);  // epilogue has drained the accumulators
-        tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
+    // =========================== MMA issuer (warp-converged, one elected lane issues) ==========
+    int slot = 0;
+    uint32_t phase = 0, it = 0;
+    for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_full + 8 * slot, phase);
+        const int slot_b = slot;
+        const uint64_t b_desc = make_smem_desc(ring + slot * kSlotBytes);
+        if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+#pragma unroll
+        for (int mt = 0; mt < NUM_MT; ++mt) {
+          // first k-block of a strip: the epilogue must have drained this row tile's accumulators
+          if (kb == 0) mbar_wait(bar_tempty + 8 * mt, (it & 1) ^ 1);
           mbar_wait(bar_full + 8 * slot, phase);
           tc_fence_after();
-          const int slot_b = slot;
-          const uint64_t b_desc = make_smem_desc(ring + slot * kSlotBytes);
-          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
-#pragma unroll 1
-          for (int mt = 0; mt < NUM_MT; ++mt) {
-            mbar_wait(bar_full + 8 * slot, phase);
-            tc_fence_after();
-            const uint64_t a_desc = make_smem_desc(ring + slot * kSlotBytes);
+          const uint64_t a_desc = make_smem_desc(ring + slot * kSlotBytes);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
               umma_bf16(tmem_base + mt * BN, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (kb | k) != 0);
             umma_commit(bar_empty + 8 * slot);  // A slot free once these MMAs retire
-            if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+            if (mt == NUM_MT - 1) {
+              umma_commit(bar_empty + 8 * slot_b);          // W slot free after the last row tile used it
+              if (kb == num_kb - 1) umma_commit(bar_tfull);  // strip accumulators complete
+            }
           }
-          umma_commit(bar_empty + 8 * slot_b);  // W slot free after the last row tile used it
+          __syncwarp();
+          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull);  // strip accumulators complete
       }
     }
   } else {
@@ -305,6 +326,8 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             st_z[mt] += zs;
             }
           }
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
         }
       } else {
         // ---- pass 1: p, A, Q and the column sums ------------------------------------------
@@ -371,11 +394,11 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               }
             }
           }
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // s_col / s_logp reusable
       }
-      tc_fence_before();
-      mbar_arrive(bar_tempty);  // accumulators may be overwritten by the next strip
     }
 
     // ---- per-CTA partials --------------------------------------------------------------------
@@ -513,7 +536,7 @@ static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   return L;
 }
 
-constexpr size_t kUncSmem = 1024 + (size_t)kNumSlots * kSlotBytes + (2 * kNumSlots + 2) * 8 + 16 + 5 * BN * sizeof(float);
+constexpr size_t kUncSmem = 1024 + (size_t)kNumSlots * kSlotBytes + (2 * kNumSlots + 1 + kMaxMT) * 8 + 16 + 5 * BN * sizeof(float);
 
 template <int NUM_MT, int MODE, int KT>
 static int launch_unc(const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, cudaStream_t st) {
