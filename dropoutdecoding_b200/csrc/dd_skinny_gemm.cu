@@ -18,10 +18,11 @@ namespace dd {
 
 constexpr int kGemmWarps = 8;
 constexpr int kGemmThreads = kGemmWarps * 32;
-constexpr int kUnroll = 4;  // k-steps (of 32) whose loads are in flight per warp
+// k-steps (of 32) per register batch; two batches are in flight per warp (software pipeline)
+
 
 // kUnroll k-steps of this warp's weight rows -> registers (guards the tail of the k-slice)
-template <int NW>
+template <int NW, int kUnroll>
 __device__ __forceinline__ void load_w_batch(uint4 (&dst)[kUnroll][NW][2], const __nv_bfloat16* const (&wrow)[NW][2],
                                              int s0, int steps) {
 #pragma unroll
@@ -37,7 +38,7 @@ __device__ __forceinline__ void load_w_batch(uint4 (&dst)[kUnroll][NW][2], const
   }
 }
 
-template <int MT, int NW>
+template <int MT, int NW, int kUnroll>
 __device__ __forceinline__ void mma_batch(float (&acc)[NW][MT][4], const uint4 (&wa)[kUnroll][NW][2],
                                           const __nv_bfloat16* const (&xrow)[MT], const bool (&xok)[MT], int s0,
                                           int steps) {
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
                                                                    const __nv_bfloat16* __restrict__ residual,
                                                                    int M, int N, int K, void* __restrict__ y) {
   constexpr int NW = (EPI == DD_EPI_SWIGLU) ? 2 : 1;  // weight row tiles per CTA
+  constexpr int kUnroll = (MT * NW >= 3) ? 2 : 4;
   __shared__ float s_red[kGemmWarps][NW][MT][16][8 + 1];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -108,15 +110,15 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
   // PDL: the weights do not depend on the previous kernel -- put the first batch of the stream in
   // flight, let the next kernel's CTAs become resident, and only then wait for our activations.
   uint4 wa0[kUnroll][NW][2], wa1[kUnroll][NW][2];
-  load_w_batch<NW>(wa0, wrow, 0, steps);
+  load_w_batch<NW, kUnroll>(wa0, wrow, 0, steps);
   pdl_trigger();
   pdl_wait();
   for (int s0 = 0; s0 < steps; s0 += 2 * kUnroll) {  // software-pipelined: next batch loads under the MMAs
-    if (s0 + kUnroll < steps) load_w_batch<NW>(wa1, wrow, s0 + kUnroll, steps);
-    mma_batch<MT, NW>(acc, wa0, xrow, xok, s0, steps);
+    if (s0 + kUnroll < steps) load_w_batch<NW, kUnroll>(wa1, wrow, s0 + kUnroll, steps);
+    mma_batch<MT, NW, kUnroll>(acc, wa0, xrow, xok, s0, steps);
     if (s0 + kUnroll < steps) {
-      if (s0 + 2 * kUnroll < steps) load_w_batch<NW>(wa0, wrow, s0 + 2 * kUnroll, steps);
-      mma_batch<MT, NW>(acc, wa1, xrow, xok, s0 + kUnroll, steps);
+      if (s0 + 2 * kUnroll < steps) load_w_batch<NW, kUnroll>(wa0, wrow, s0 + 2 * kUnroll, steps);
+      mma_batch<MT, NW, kUnroll>(acc, wa1, xrow, xok, s0 + kUnroll, steps);
     }
   }
 
