@@ -31,7 +31,7 @@ _SIGNATURES = {
                                       C.c_size_t, _P]),
     "dd_commit_winner": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, _P]),
-    "dd_aggregate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "dd_aggregate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "dd_rmsnorm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "dd_skinny_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dd_rope_stage": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
@@ -55,7 +55,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
+    path = os.environ.get("DD_LIB") or _build.LIB      # DD_LIB: an experiment build (build.py --variant=)
     if not os.path.exists(path):
         if not build_if_missing:
             raise DropDecError(f"{path} is missing: run `python -m dropoutdecoding_b200.build`")

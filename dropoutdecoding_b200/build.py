@@ -38,17 +38,21 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OUT, exist_ok=True)
-    stamp = os.path.join(OUT, "stamp")
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return LIB
+def build(force: bool = False, verbose: bool = False, extra_flags=(), variant: str = "") -> str:
+    """variant != "" builds an experiment library (libdropdec_<variant>.so) with extra -D flags;
+    select it at run time with DD_LIB=<path>."""
+    out = os.path.join(OUT, variant) if variant else OUT
+    lib = os.path.join(OUT, f"libdropdec_{variant}.so") if variant else LIB
+    os.makedirs(out, exist_ok=True)
+    stamp = os.path.join(out, "stamp")
+    dig = _digest() + " ".join(extra_flags)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return lib
     nvcc = _nvcc()
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OUT, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(out, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -58,14 +62,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+    r = subprocess.run([nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    args = [a for a in sys.argv[1:] if a != "--force"]
+    variant = next((a.split("=", 1)[1] for a in args if a.startswith("--variant=")), "")
+    flags = [a for a in args if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose=True, extra_flags=tuple(flags), variant=variant))

@@ -33,7 +33,7 @@ __device__ __forceinline__ ArgMax block_argmax(ArgMax x, ArgMax* s_warp) {
 }
 
 __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __restrict__ logits, int K,
-                                                                int V, int mode, int32_t* member_ids,
+                                                                int V, int ld, int mode, int32_t* member_ids,
                                                                 int32_t* winner, int32_t* token,
                                                                 float* out_logits) {
   __shared__ ArgMax s_warp[kAggThreads / 32];
@@ -42,11 +42,11 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __r
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* base = logits + (size_t)b * K * V;
-  const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+  const float* base = logits + (size_t)b * K * ld;
+  const bool vec = (V % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
 
   for (int m = 0; m < K; ++m) {
-    const float* row = base + (size_t)m * V;
+    const float* row = base + (size_t)m * ld;
     ArgMax best{-INFINITY, 0x7fffffff};
     if (vec) {
       const float4* row4 = reinterpret_cast<const float4*>(row);
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __r
     }
     if (out_logits) {
       __syncthreads();
-      const float* row = base + (size_t)s_win * V;
+      const float* row = base + (size_t)s_win * ld;
       for (int j = tid; j < V; j += kAggThreads) out_logits[(size_t)b * V + j] = row[j];
     }
   } else {  // DD_AGG_MEAN: numpy mean(axis=0) in fp32 = sequential row sum, then / K
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __r
     const float inv_k = (float)K;
     for (int j = tid; j < V; j += kAggThreads) {
       float s = base[j];
-      for (int m = 1; m < K; ++m) s = __fadd_rn(s, base[(size_t)m * V + j]);
+      for (int m = 1; m < K; ++m) s = __fadd_rn(s, base[(size_t)m * ld + j]);
       s = __fdiv_rn(s, inv_k);
       out_logits[(size_t)b * V + j] = s;
       best = better(best, ArgMax{s, j});
@@ -108,16 +108,16 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __r
 
 }  // namespace dd
 
-extern "C" int dd_aggregate(const float* logits, int B, int K, int V, int mode, int32_t* member_ids,
+extern "C" int dd_aggregate(const float* logits, int B, int K, int V, int ld, int mode, int32_t* member_ids,
                             int32_t* winner, int32_t* token, float* out_logits, dd_stream_t stream) {
   using namespace dd;
   DD_CHECK_ARG(logits && winner && token, "dd_aggregate: null pointer");
   DD_CHECK_ARG(K >= 1 && K <= DD_MAX_MEMBERS, "dd_aggregate: K=%d out of [1,%d]", K, DD_MAX_MEMBERS);
-  DD_CHECK_ARG(V >= 1 && B >= 0, "dd_aggregate: bad shape B=%d V=%d", B, V);
+  DD_CHECK_ARG(V >= 1 && B >= 0 && ld >= V, "dd_aggregate: bad shape B=%d V=%d ld=%d", B, V, ld);
   DD_CHECK_ARG(mode == DD_AGG_VOTE || mode == DD_AGG_MEAN, "dd_aggregate: bad mode %d", mode);
   DD_CHECK_ARG(mode != DD_AGG_MEAN || out_logits, "dd_aggregate: mean mode needs out_logits");
   if (B == 0) return DD_OK;
-  DD_LAUNCH_CHAIN(aggregate_kernel, dim3(B), dim3(kAggThreads), 0, (cudaStream_t)stream, logits, K, V, mode,
+  DD_LAUNCH_CHAIN(aggregate_kernel, dim3(B), dim3(kAggThreads), 0, (cudaStream_t)stream, logits, K, V, ld, mode,
                   member_ids, winner, token, out_logits);
   return DD_OK;
 }

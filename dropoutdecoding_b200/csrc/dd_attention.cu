@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnPa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int G = p.H / p.H_kv, R = p.M * G;
-  pdl_trigger();
+  pdl_trigger_stream_entry();
   pdl_wait();
   const int S = p.seq_lens[b];
   const int vis0 = p.vis_start ? p.vis_start[b] : 0;
@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnPa
     }
   }
   cp_async_wait<0>();
+  pdl_trigger_stream_tail();
   __syncthreads();  // ring is idle: reuse it for the cross-warp merge
 
   // ---- merge the 4 warps (disjoint key subsets) and write the split partial ---------------------

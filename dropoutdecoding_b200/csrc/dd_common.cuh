@@ -64,8 +64,26 @@ static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3
 #define DD_LAUNCH_CHAIN(...) DD_CHECK_CUDA(::dd::launch_chain(__VA_ARGS__))
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// DD_PDL_TRIGGER: where kernels let their dependents start (build-time knob for experiments)
+//   0 = never explicitly (dependents start when the grid has drained)
+//   1 = at kernel entry everywhere (deep pile-up of waiting grids: measured slower)
+//   2 = small kernels at entry, streaming kernels (GEMM, attention) after their main loop  [default]
+#ifndef DD_PDL_TRIGGER
+#define DD_PDL_TRIGGER 2
+#endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger_now() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// entry of a small kernel
+__device__ __forceinline__ void pdl_trigger() {
+  if (DD_PDL_TRIGGER >= 1) pdl_trigger_now();
+}
+// entry / end-of-main-loop of a streaming kernel
+__device__ __forceinline__ void pdl_trigger_stream_entry() {
+  if (DD_PDL_TRIGGER == 1) pdl_trigger_now();
+}
+__device__ __forceinline__ void pdl_trigger_stream_tail() {
+  if (DD_PDL_TRIGGER == 2) pdl_trigger_now();
+}
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 

@@ -14,6 +14,10 @@
 // Algorithmic bytes per launch: N*K*2 (x2 for SwiGLU) -- the weights, read exactly once.
 #include "dd_common.cuh"
 
+#ifndef DD_GEMM_PIPE
+#define DD_GEMM_PIPE 0  // 1: two register batches in flight (measured slower: occupancy)
+#endif
+
 namespace dd {
 
 constexpr int kGemmWarps = 8;
@@ -72,7 +76,10 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
                                                                    const __nv_bfloat16* __restrict__ residual,
                                                                    int M, int N, int K, void* __restrict__ y) {
   constexpr int NW = (EPI == DD_EPI_SWIGLU) ? 2 : 1;  // weight row tiles per CTA
-  constexpr int kUnroll = (MT * NW >= 3) ? 2 : 4;
+#ifndef DD_GEMM_UNROLL
+#define DD_GEMM_UNROLL 4
+#endif
+  constexpr int kUnroll = (DD_GEMM_PIPE && MT * NW >= 3) ? 2 : DD_GEMM_UNROLL;
   __shared__ float s_red[kGemmWarps][NW][MT][16][8 + 1];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -108,10 +115,11 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
       for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
 
   // PDL: the weights do not depend on the previous kernel -- put the first batch of the stream in
-  // flight, let the next kernel's CTAs become resident, and only then wait for our activations.
+  // flight before waiting for our activations.
+#if DD_GEMM_PIPE
   uint4 wa0[kUnroll][NW][2], wa1[kUnroll][NW][2];
   load_w_batch<NW, kUnroll>(wa0, wrow, 0, steps);
-  pdl_trigger();
+  pdl_trigger_stream_entry();
   pdl_wait();
   for (int s0 = 0; s0 < steps; s0 += 2 * kUnroll) {  // software-pipelined: next batch loads under the MMAs
     if (s0 + kUnroll < steps) load_w_batch<NW, kUnroll>(wa1, wrow, s0 + kUnroll, steps);
@@ -121,6 +129,17 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
       mma_batch<MT, NW, kUnroll>(acc, wa1, xrow, xok, s0 + kUnroll, steps);
     }
   }
+#else
+  uint4 wa[kUnroll][NW][2];
+  load_w_batch<NW, kUnroll>(wa, wrow, 0, steps);
+  pdl_trigger_stream_entry();
+  pdl_wait();
+  for (int s0 = 0; s0 < steps; s0 += kUnroll) {
+    if (s0 > 0) load_w_batch<NW, kUnroll>(wa, wrow, s0, steps);
+    mma_batch<MT, NW, kUnroll>(acc, wa, xrow, xok, s0, steps);
+  }
+#endif
+  pdl_trigger_stream_tail();
 
   // C fragment: c0,c1 = C[row g][tok 2t,2t+1]; c2,c3 = C[row g+8][tok 2t,2t+1]
 #pragma unroll

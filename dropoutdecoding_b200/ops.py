@@ -157,18 +157,21 @@ def commit_winner(k_new_all: torch.Tensor, v_new_all: torch.Tensor, winner: torc
 
 def aggregate(logits: torch.Tensor, mode: str = "vote", want_logits: bool = False,
               member_ids: Optional[torch.Tensor] = None, winner: Optional[torch.Tensor] = None,
-              token: Optional[torch.Tensor] = None, out_logits: Optional[torch.Tensor] = None):
-    """logits fp32 [B, K, V] -> (member_ids [B,K], winner [B], token [B], out_logits [B,V] | None)."""
+              token: Optional[torch.Tensor] = None, out_logits: Optional[torch.Tensor] = None,
+              vocab: Optional[int] = None):
+    """logits fp32 [B, K, ld] (first `vocab` entries of each row valid; default all) ->
+    (member_ids [B,K], winner [B], token [B], out_logits [B,vocab] | None)."""
     L = _lib.load()
     _need(logits, torch.float32, "logits")
-    B, K, V = logits.shape
+    B, K, ld = logits.shape
+    V = ld if vocab is None else vocab
     dev = logits.device
     member_ids = torch.empty(B, K, dtype=torch.int32, device=dev) if member_ids is None else member_ids
     winner = torch.empty(B, dtype=torch.int32, device=dev) if winner is None else winner
     token = torch.empty(B, dtype=torch.int32, device=dev) if token is None else token
     if out_logits is None and (want_logits or mode == "mean"):
         out_logits = torch.empty(B, V, dtype=torch.float32, device=dev)
-    check(L.dd_aggregate(_ptr(logits), B, K, V, AGG_VOTE if mode == "vote" else AGG_MEAN, _ptr(member_ids),
+    check(L.dd_aggregate(_ptr(logits), B, K, V, ld, AGG_VOTE if mode == "vote" else AGG_MEAN, _ptr(member_ids),
                          _ptr(winner), _ptr(token), _ptr(out_logits), _stream()), "dd_aggregate")
     return member_ids, winner, token, out_logits
 

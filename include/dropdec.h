@@ -144,9 +144,10 @@ int dd_commit_winner(const void* k_new_all /* bf16 [L, B, M, H_kv, D] */, const 
  *   vote: winner[b] = first member whose id is the most frequent one (ties between ids ->
  *         the id seen first); token[b] = that id; out_logits[b,:] = logits[b,winner,:]
  *   mean: out_logits[b,:] = mean_m logits[b,m,:] (fp32); token = argmax; winner = 0
- * out_logits may be NULL.
+ * out_logits may be NULL.  ld >= V is the row pitch of `logits` in elements (a vocabulary padded to a
+ * GEMM-friendly size: only the first V entries of each row take part).
  * ------------------------------------------------------------------------------------------ */
-int dd_aggregate(const float* logits /* [B, K, V] */, int B, int K, int V, int mode,
+int dd_aggregate(const float* logits /* [B, K, ld] */, int B, int K, int V, int ld, int mode,
                  int32_t* member_ids /* [B, K] */, int32_t* winner /* [B] */, int32_t* token /* [B] */,
                  float* out_logits /* [B, V] or NULL */, dd_stream_t stream);
 
