@@ -145,9 +145,15 @@ struct UncParams {
   int32_t* part_topi;      // [img][parts][n_vis][topk]
   const float* row_stats;  // [img][n_vis][2]             (m, 1/Z)  FUSED input
   float* part_acq;         // [img][parts][n_vis][3]      (A, Q, C) FUSED output
+  int n_chunks;            // row chunks of kMaxMT*128 rows per image (> 1 when n_vis > 640)
+  float* colpart;          // [img][chunk][n_strips*BN]   column sums of p over one row chunk (COLSUM -> logpavg)
+  float* logpavg;          // [img][n_strips*BN]          log(p_avg + eps)                    (CROSS input)
 };
 
-enum { MODE_STATS = 0, MODE_FUSED = 1 };
+// n_vis <= 640: STATS, FUSED.  Larger images (LLaVA-NeXT anyres, up to ~2.9k rows) do not fit the 512
+// TMEM columns, so the column mean needs its own sweep: STATS, COLSUM (p, A, Q, per-chunk column sums),
+// a tiny log(p_avg) kernel, CROSS (C = sum_v p log(p_avg+eps)).
+enum { MODE_STATS = 0, MODE_FUSED = 1, MODE_COLSUM = 2, MODE_CROSS = 3 };
 
 template <int NUM_MT, int MODE, int KT>
 __global__ void __launch_bounds__(kUncThreads, 1)
@@ -163,7 +169,8 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   float* s_logp = s_col + 4 * BN;                            // [BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.y, part = blockIdx.x;
+  const int img = blockIdx.y / p.n_chunks, chunk = blockIdx.y % p.n_chunks, part = blockIdx.x;
+  const int row0 = chunk * (kMaxMT * BM);  // first row of this CTA's row chunk
   const int spc = (p.n_strips + p.parts - 1) / p.parts;
   const int strip_beg = part * spc;
   const int strip_end = min(p.n_strips, strip_beg + spc);
@@ -215,7 +222,7 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           mbar_wait(bar_empty + 8 * slot, phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(bar_full + 8 * slot, BM * BK * 2);
-            tma_load_3d(ring + slot * kSlotBytes, &tmap_a, bar_full + 8 * slot, kb * BK, mt * BM, img);
+            tma_load_3d(ring + slot * kSlotBytes, &tmap_a, bar_full + 8 * slot, kb * BK, row0 + mt * BM, img);
           }
           __syncwarp();
           if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
@@ -266,7 +273,7 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     int topi[MODE == MODE_STATS ? NUM_MT : 1][KT];
 #pragma unroll
     for (int mt = 0; mt < NUM_MT; ++mt) {
-      const int row = mt * BM + tid;
+      const int row = row0 + mt * BM + tid;
       acc_a[mt] = acc_q[mt] = acc_c[mt] = 0.f;
       if (MODE == MODE_STATS) {
         st_m[mt] = -INFINITY;
@@ -289,7 +296,7 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (MODE == MODE_STATS) {
 #pragma unroll
         for (int mt = 0; mt < NUM_MT; ++mt) {
-          const bool ok = mt * BM + tid < p.n_vis;
+          const bool ok = row0 + mt * BM + tid < p.n_vis;
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
             float v[32];
@@ -330,81 +337,96 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
         }
       } else {
-        // ---- pass 1: p, A, Q and the column sums ------------------------------------------
-        float colsum[BN];
+        if (MODE == MODE_FUSED || MODE == MODE_COLSUM) {
+          // ---- pass 1: p, A, Q and the column sums ----------------------------------------
+          float colsum[BN];
 #pragma unroll
-        for (int i = 0; i < BN; ++i) colsum[i] = 0.f;
+          for (int i = 0; i < BN; ++i) colsum[i] = 0.f;
 #pragma unroll
-        for (int mt = 0; mt < NUM_MT; ++mt) {
-          const bool ok = mt * BM + tid < p.n_vis;
-          const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
+          for (int mt = 0; mt < NUM_MT; ++mt) {
+            const bool ok = row0 + mt * BM + tid < p.n_vis;
+            const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c) {
-            float v[32];
-            tmem_ld32(lane_addr + mt * BN + c * 32, v);
-            if (ok) {
+            for (int c = 0; c < BN / 32; ++c) {
+              float v[32];
+              tmem_ld32(lane_addr + mt * BN + c * 32, v);
+              if (ok) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float x = v[i];
-                if (p.round_bf16) x = bf16_round(x);
-                float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
-                float dv = pr - inv_v;
-                if (col0 + c * 32 + i >= p.vocab) pr = dv = 0.f;  // padded vocab columns of the last strip
-                colsum[c * 32 + i] += pr;
-                acc_a[mt] = fmaf(pr, __logf(pr + kEps), acc_a[mt]);
-                acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
+                for (int i = 0; i < 32; ++i) {
+                  float x = v[i];
+                  if (p.round_bf16) x = bf16_round(x);
+                  float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
+                  float dv = pr - inv_v;
+                  if (col0 + c * 32 + i >= p.vocab) pr = dv = 0.f;  // padded vocab columns of the last strip
+                  colsum[c * 32 + i] += pr;
+                  acc_a[mt] = fmaf(pr, __logf(pr + kEps), acc_a[mt]);
+                  acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
+                }
               }
             }
+            if (MODE == MODE_COLSUM) {  // no second pass over TMEM in this mode
+              tc_fence_before();
+              mbar_arrive(bar_tempty + 8 * mt);
+            }
           }
-        }
-        // ---- column sums over all rows of the image: warp butterfly, then 4 smem rows ---------
+          // ---- column sums over the rows held by this CTA: warp butterfly, then 4 smem rows ----
 #pragma unroll
-        for (int i = 0; i < BN; ++i) {
-          float s = colsum[i];
-          s += __shfl_xor_sync(0xffffffffu, s, 16);
-          s += __shfl_xor_sync(0xffffffffu, s, 8);
-          s += __shfl_xor_sync(0xffffffffu, s, 4);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          if (lane == (i & 31)) s_col[warp * BN + i] = s;
+          for (int i = 0; i < BN; ++i) {
+            float s = colsum[i];
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (lane == (i & 31)) s_col[warp * BN + i] = s;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          if (tid < BN) {
+            const float tot = s_col[tid] + s_col[BN + tid] + s_col[2 * BN + tid] + s_col[3 * BN + tid];
+            if (MODE == MODE_FUSED)
+              s_logp[tid] = __logf(tot / (float)p.n_vis + kEps);  // log(p_avg + eps), models/llava.py:732-735
+            else
+              p.colpart[((size_t)img * p.n_chunks + chunk) * ((size_t)p.n_strips * BN) + col0 + tid] = tot;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        if (tid < BN) {
-          const float tot = s_col[tid] + s_col[BN + tid] + s_col[2 * BN + tid] + s_col[3 * BN + tid];
-          s_logp[tid] = __logf(tot / (float)p.n_vis + kEps);  // log(p_avg + eps), models/llava.py:732-735
+        if (MODE == MODE_CROSS) {
+          if (tid < BN) s_logp[tid] = p.logpavg[(size_t)img * ((size_t)p.n_strips * BN) + col0 + tid];
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        // ---- pass 2: C_i = sum_v p log(p_avg + eps) -------------------------------------------
+        if (MODE == MODE_FUSED || MODE == MODE_CROSS) {
+          // ---- pass 2: C_i = sum_v p log(p_avg + eps) ---------------------------------------
 #pragma unroll
-        for (int mt = 0; mt < NUM_MT; ++mt) {
-          const bool ok = mt * BM + tid < p.n_vis;
-          const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
+          for (int mt = 0; mt < NUM_MT; ++mt) {
+            const bool ok = row0 + mt * BM + tid < p.n_vis;
+            const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            float v[32];
-            tmem_ld32(lane_addr + mt * BN + c * 32, v);
-            if (ok) {
+            for (int c = 0; c < BN / 32; ++c) {
+              float v[32];
+              tmem_ld32(lane_addr + mt * BN + c * 32, v);
+              if (ok) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float x = v[i];
-                if (p.round_bf16) x = bf16_round(x);
-                float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
-                if (col0 + c * 32 + i >= p.vocab) pr = 0.f;
-                acc_c[mt] = fmaf(pr, s_logp[c * 32 + i], acc_c[mt]);
+                for (int i = 0; i < 32; ++i) {
+                  float x = v[i];
+                  if (p.round_bf16) x = bf16_round(x);
+                  float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
+                  if (col0 + c * 32 + i >= p.vocab) pr = 0.f;
+                  acc_c[mt] = fmaf(pr, s_logp[c * 32 + i], acc_c[mt]);
+                }
               }
             }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
           }
-          tc_fence_before();
-          mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // s_col / s_logp reusable
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // s_col / s_logp reusable
       }
     }
 
     // ---- per-CTA partials --------------------------------------------------------------------
 #pragma unroll
     for (int mt = 0; mt < NUM_MT; ++mt) {
-      const int row = mt * BM + tid;
+      const int row = row0 + mt * BM + tid;
       if (row >= p.n_vis) continue;
       const size_t pr = ((size_t)img * p.parts + part) * p.n_vis + row;
       if (MODE == MODE_STATS) {
@@ -418,9 +440,11 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
       } else {
-        p.part_acq[pr * 3] = acc_a[mt];
-        p.part_acq[pr * 3 + 1] = acc_q[mt];
-        p.part_acq[pr * 3 + 2] = acc_c[mt];
+        if (MODE != MODE_CROSS) {
+          p.part_acq[pr * 3] = acc_a[mt];
+          p.part_acq[pr * 3 + 1] = acc_q[mt];
+        }
+        if (MODE != MODE_COLSUM) p.part_acq[pr * 3 + 2] = acc_c[mt];
       }
     }
   }
@@ -467,6 +491,16 @@ __global__ void stats_finalize_kernel(const UncParams p, float* __restrict__ row
   row_stats[((size_t)img * p.n_vis + row) * 2] = m;
   row_stats[((size_t)img * p.n_vis + row) * 2 + 1] = 1.0f / z;
   for (int j = 0; j < p.topk; ++j) topk_ids[((size_t)img * p.n_vis + row) * p.topk + j] = ti[j];
+}
+
+// log(p_avg + eps) from the per-chunk column sums (n_vis > 640 path)
+__global__ void logpavg_kernel(const UncParams p) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
+  const int vp = p.n_strips * BN;
+  if (v >= vp) return;
+  float tot = 0.f;
+  for (int c = 0; c < p.n_chunks; ++c) tot += p.colpart[((size_t)img * p.n_chunks + c) * vp + v];
+  p.logpavg[(size_t)img * vp + v] = __logf(tot / (float)p.n_vis + kEps);
 }
 
 __global__ void fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restrict__ alea,
@@ -517,13 +551,14 @@ static int num_sms() {
 }
 
 struct UncLayout {
-  int n_strips, parts;
-  size_t off_stats, off_topv, off_topi, off_rowstats, off_acq, total;
+  int n_strips, parts, n_chunks;
+  size_t off_stats, off_topv, off_topi, off_rowstats, off_acq, off_colpart, off_logpavg, total;
 };
 static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   UncLayout L;
   L.n_strips = ceil_div(vocab, BN);
-  int parts = ceil_div(num_sms(), n_images > 0 ? n_images : 1);
+  L.n_chunks = ceil_div(n_vis, kMaxMT * BM);
+  int parts = ceil_div(num_sms(), (n_images > 0 ? n_images : 1) * L.n_chunks);
   L.parts = parts < 1 ? 1 : (parts > L.n_strips ? L.n_strips : parts);
   const size_t rows = (size_t)n_images * L.parts * n_vis;
   size_t o = 0;
@@ -532,6 +567,9 @@ static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   L.off_topi = o; o = align_up(o + rows * topk * sizeof(int32_t), 256);
   L.off_rowstats = o; o = align_up(o + (size_t)n_images * n_vis * 2 * sizeof(float), 256);
   L.off_acq = o; o = align_up(o + rows * 3 * sizeof(float), 256);
+  const size_t vp = (size_t)L.n_strips * BN;
+  L.off_colpart = o; o = align_up(o + (L.n_chunks > 1 ? (size_t)n_images * L.n_chunks * vp * sizeof(float) : 0), 256);
+  L.off_logpavg = o; o = align_up(o + (L.n_chunks > 1 ? (size_t)n_images * vp * sizeof(float) : 0), 256);
   L.total = o;
   return L;
 }
@@ -542,7 +580,7 @@ template <int NUM_MT, int MODE, int KT>
 static int launch_unc(const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, cudaStream_t st) {
   auto kern = uncertainty_kernel<NUM_MT, MODE, KT>;
   DD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUncSmem));
-  kern<<<dim3(p.parts, p.n_images), kUncThreads, kUncSmem, st>>>(ta, tw, p);
+  kern<<<dim3(p.parts, p.n_images * p.n_chunks), kUncThreads, kUncSmem, st>>>(ta, tw, p);
   DD_CHECK_LAUNCH();
   return DD_OK;
 }
@@ -551,6 +589,8 @@ template <int NUM_MT>
 static int launch_unc_mt(const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, int mode,
                          cudaStream_t st) {
   if (mode == MODE_FUSED) return launch_unc<NUM_MT, MODE_FUSED, 1>(ta, tw, p, st);
+  if (mode == MODE_COLSUM) return launch_unc<NUM_MT, MODE_COLSUM, 1>(ta, tw, p, st);
+  if (mode == MODE_CROSS) return launch_unc<NUM_MT, MODE_CROSS, 1>(ta, tw, p, st);
   if (p.topk <= 5) return launch_unc<NUM_MT, MODE_STATS, 5>(ta, tw, p, st);
   if (p.topk <= 10) return launch_unc<NUM_MT, MODE_STATS, 10>(ta, tw, p, st);
   return launch_unc<NUM_MT, MODE_STATS, DD_MAX_TOPK>(ta, tw, p, st);
@@ -576,8 +616,8 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
                                       dd_stream_t stream) {
   using namespace dd;
   DD_CHECK_ARG(h_vis && w_lm && epi && alea && var && topk_ids && workspace, "dd_uncertainty_project: null pointer");
-  DD_CHECK_ARG(n_images >= 0 && n_vis >= 1 && n_vis <= 5 * BM, "dd_uncertainty_project: n_vis=%d out of [1,%d]",
-               n_vis, 5 * BM);
+  DD_CHECK_ARG(n_images >= 0 && n_vis >= 1 && n_vis <= 8192, "dd_uncertainty_project: n_vis=%d out of [1,8192]",
+               n_vis);
   DD_CHECK_ARG(d >= BK && d % BK == 0, "dd_uncertainty_project: d=%d must be a multiple of %d", d, BK);
   DD_CHECK_ARG(vocab >= 2, "dd_uncertainty_project: vocab=%d", vocab);
   DD_CHECK_ARG(topk >= 1 && topk <= DD_MAX_TOPK && topk <= vocab, "dd_uncertainty_project: topk=%d out of [1,%d]",
@@ -617,7 +657,9 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   UncParams p{};
   p.n_images = n_images; p.n_vis = n_vis; p.d = d; p.vocab = vocab; p.topk = topk; p.round_bf16 = round_logits_bf16;
-  p.n_strips = L.n_strips; p.parts = L.parts;
+  p.n_strips = L.n_strips; p.parts = L.parts; p.n_chunks = L.n_chunks;
+  p.colpart = reinterpret_cast<float*>(ws + L.off_colpart);
+  p.logpavg = reinterpret_cast<float*>(ws + L.off_logpavg);
   p.part_stats = reinterpret_cast<float*>(ws + L.off_stats);
   p.part_topv = reinterpret_cast<float*>(ws + L.off_topv);
   p.part_topi = reinterpret_cast<int32_t*>(ws + L.off_topi);
@@ -625,14 +667,23 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
   p.row_stats = row_stats;
   p.part_acq = reinterpret_cast<float*>(ws + L.off_acq);
   cudaStream_t st = (cudaStream_t)stream;
-  const int num_mt = ceil_div(n_vis, BM);
+  const int num_mt = L.n_chunks > 1 ? kMaxMT : ceil_div(n_vis, BM);
   const dim3 fgrid(ceil_div(n_vis, 128), n_images);
   int rc = launch_unc_any(num_mt, ta, tw, p, MODE_STATS, st);
   if (rc) return rc;
   stats_finalize_kernel<<<fgrid, 128, 0, st>>>(p, row_stats, topk_ids);
   DD_CHECK_LAUNCH();
-  rc = launch_unc_any(num_mt, ta, tw, p, MODE_FUSED, st);
-  if (rc) return rc;
+  if (L.n_chunks == 1) {
+    rc = launch_unc_any(num_mt, ta, tw, p, MODE_FUSED, st);
+    if (rc) return rc;
+  } else {
+    rc = launch_unc_any(num_mt, ta, tw, p, MODE_COLSUM, st);
+    if (rc) return rc;
+    logpavg_kernel<<<dim3(ceil_div(L.n_strips * BN, 256), n_images), 256, 0, st>>>(p);
+    DD_CHECK_LAUNCH();
+    rc = launch_unc_any(num_mt, ta, tw, p, MODE_CROSS, st);
+    if (rc) return rc;
+  }
   fused_finalize_kernel<<<fgrid, 128, 0, st>>>(p, epi, alea, var);
   DD_CHECK_LAUNCH();
   return DD_OK;

@@ -69,7 +69,17 @@ class DecoderWeights:
     weight stream feeds one fused GEMM."""
 
     def __init__(self, cfg: DecoderConfig, embed, layers: List[Dict[str, torch.Tensor]], norm, lm_head):
-        self.cfg, self.embed, self.layers, self.norm, self.lm_head = cfg, embed, layers, norm, lm_head
+        self.cfg, self.embed, self.layers, self.norm = cfg, embed, layers, norm
+        # the weight-streaming GEMM wants N % 16 == 0: pad the head with zero rows (InstructBLIP: V = 32001);
+        # `lm_head` is the exact [V, d] view, `lm_head_padded` what the GEMM streams
+        V = lm_head.shape[0]
+        self.vocab_padded = -(-V // 16) * 16
+        if self.vocab_padded != V:
+            pad = torch.zeros(self.vocab_padded, lm_head.shape[1], dtype=lm_head.dtype, device=lm_head.device)
+            pad[:V] = lm_head
+            self.lm_head_padded, self.lm_head = pad, pad[:V]
+        else:
+            self.lm_head_padded = self.lm_head = lm_head
 
     @staticmethod
     def from_named(cfg: DecoderConfig, w: Dict[str, torch.Tensor], device) -> "DecoderWeights":
@@ -135,14 +145,18 @@ class DropoutDecodeEngine:
     def __init__(self, weights: DecoderWeights, batch: int, n_vis: int, max_seq: int,
                  probs: Sequence[float] = (0.3, 0.5, 0.7), mode: str = "cumulative", keep_relevant: bool = True,
                  topk: int = 5, aggregate: str = "vote", seed: int = 24, max_steps: int = 1024,
-                 round_logits: bool = True, est_seq: Optional[int] = None):
+                 round_logits: bool = True, est_seq: Optional[int] = None, vote_on: str = "logits"):
         cfg = weights.cfg
-        if cfg.vocab % 16 or cfg.d_model % 256 or cfg.d_ff % 256:
-            raise ops.DropDecError("engine needs vocab % 16 == 0 and d_model, d_ff % 256 == 0")
+        if cfg.d_model % 256 or cfg.d_ff % 256:
+            raise ops.DropDecError("engine needs d_model % 256 == 0 and d_ff % 256 == 0")
+        if vote_on not in ("logits", "hidden"):
+            raise ValueError(vote_on)
         self.w, self.cfg = weights, cfg
         self.B, self.K, self.n_vis, self.S_max = batch, len(probs), n_vis, max_seq
         self.probs, self.mode, self.keep_relevant = [float(p) for p in probs], mode, keep_relevant
         self.topk, self.aggregate, self.seed, self.round_logits = topk, aggregate, seed, round_logits
+        self.vote_on = vote_on          # "hidden": InstructBLIP votes on the argmax of the final hidden state
+        self.Vp = weights.vocab_padded
         self.dev = weights.embed.device
         dev, B, L = self.dev, batch, cfg.n_layers
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
@@ -165,7 +179,7 @@ class DropoutDecodeEngine:
         self.words = ops.mask_words(n_vis)
         self.bitmask = torch.zeros(B, self.K, self.words, **i32)
         self.n_masked = torch.zeros(B, self.K, **i32)
-        self.out_logits = torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev)
+        self.out_logits = torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev)   # mean mode / forward() API
         self.uniforms: Optional[torch.Tensor] = None      # parity mode: [steps, B, K, n_vis]
         self._u_step: Optional[torch.Tensor] = None
         self.epi = torch.zeros(B, n_vis, dtype=torch.float32, device=dev)
@@ -178,6 +192,11 @@ class DropoutDecodeEngine:
         est = est_seq or max_seq
         self.pa = self._alloc_pass(1, est)
         self.pb = self._alloc_pass(self.K, est)
+        if vote_on == "hidden":
+            self._hid32 = torch.zeros(B, self.K, cfg.d_model, dtype=torch.float32, device=dev)
+            self._hid_tok = torch.zeros(B, **i32)
+            self._win_h = torch.zeros(B, cfg.d_model, **bf)
+            self._arange = torch.arange(B, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
 
@@ -194,7 +213,7 @@ class DropoutDecodeEngine:
             xn=torch.empty(rows, cfg.d_model, **bf), qkv=torch.empty(rows, (H + 2 * Hkv) * D, **bf),
             q=torch.empty(B, M, H, D, **bf), k_new=torch.empty(cfg.n_layers, B, M, Hkv, D, **bf),
             v_new=torch.empty(cfg.n_layers, B, M, Hkv, D, **bf), attn=torch.empty(B, M, H, D, **bf),
-            act=torch.empty(rows, cfg.d_ff, **bf), logits=torch.empty(B, M, cfg.vocab, dtype=torch.float32, device=dev),
+            act=torch.empty(rows, cfg.d_ff, **bf), logits=torch.empty(B, M, self.Vp, dtype=torch.float32, device=dev),
             ws=ops.attention_workspace(B, M, H, D, splits, dev), splits=splits)
 
     # weight GEMM with the HF rounding points; <= 32 rows: our weight-streaming kernel
@@ -213,7 +232,7 @@ class DropoutDecodeEngine:
         n = gu.shape[1] // 2
         return torch.mul(F.silu(gu[:, :n]), gu[:, n:], out=out)
 
-    def _forward(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor]) -> torch.Tensor:
+    def _forward(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool = True) -> torch.Tensor:
         cfg, B, M = self.cfg, self.B, pb.M
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         rows = B * M
@@ -231,8 +250,9 @@ class DropoutDecodeEngine:
             self._linear(pb.act, lw["wd"], ops.EPI_RESIDUAL, x, residual=x2)
             self.launches_per_step += 5     # 2 rmsnorm, rope_stage, attention partial + merge
         ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pb.xn)
-        self._linear(pb.xn, self.w.lm_head, ops.EPI_F32, pb.logits.view(rows, cfg.vocab))
         self.launches_per_step += 2         # embed gather, final norm
+        if head:
+            self._linear(pb.xn, self.w.lm_head_padded, ops.EPI_F32, pb.logits.view(rows, self.Vp))
         return pb.logits
 
     # ------------------------------------------------------------------------------------
@@ -240,7 +260,8 @@ class DropoutDecodeEngine:
         """One ensemble step for every sequence; asynchronous, no host sync, graph-capturable."""
         self.launches_per_step = 0
         logits_a = self._forward(self.pa, None)                                    # models/llava.py:294-305
-        ops.aggregate(logits_a, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.y_init)
+        ops.aggregate(logits_a, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.y_init,
+                      vocab=self.cfg.vocab)
         u = None
         if self.uniforms is not None:
             # parity mode: this step's pre-drawn numbers (device-side gather keeps the graph static)
@@ -249,9 +270,23 @@ class DropoutDecodeEngine:
         ops.sample_masks(self.epi, self.topk_ids, self.y_init, self.probs, mode=self.mode,      # :342-346
                          keep_relevant=self.keep_relevant, uniforms=u, seed=self.seed, offset=0,
                          step=self.step_ctr, out=self.bitmask, n_masked=self.n_masked)
-        logits_b = self._forward(self.pb, self.bitmask)                            # :350-359
-        ops.aggregate(logits_b, self.aggregate, member_ids=self.member_ids, winner=self.winner,   # :361
-                      token=self.next_token, out_logits=self.out_logits if self.aggregate == "mean" else None)
+        if self.vote_on == "logits":
+            logits_b = self._forward(self.pb, self.bitmask)                        # :350-359
+            ops.aggregate(logits_b, self.aggregate, member_ids=self.member_ids, winner=self.winner,   # :361
+                          token=self.next_token, out_logits=self.out_logits if self.aggregate == "mean" else None,
+                          vocab=self.cfg.vocab)
+        else:
+            # InstructBLIP (models/instructblip.py:125-140): members run the decoder WITHOUT the head, the
+            # vote is taken on argmax of the final hidden state [.., d], lm_head is applied to the winner only
+            self._forward(self.pb, self.bitmask, head=False)
+            B, K, d = self.B, self.K, self.cfg.d_model
+            self._hid32.copy_(self.pb.xn.view(B, K, d))
+            ops.aggregate(self._hid32, "vote", member_ids=self.member_ids, winner=self.winner, token=self._hid_tok)
+            self._win_h.copy_(self.pb.xn.view(B, K, d)[self._arange, self.winner.long()])
+            self._linear(self._win_h, self.w.lm_head_padded, ops.EPI_F32, self.pa.logits.view(B, self.Vp))
+            ops.aggregate(self.pa.logits, "vote", member_ids=self.member_ids_a, winner=self.winner_a,
+                          token=self.next_token, vocab=self.cfg.vocab)
+            self.launches_per_step += 4
         ops.commit_winner(self.pb.k_new, self.pb.v_new, self.winner, self.seq_lens, self.k_cache, self.v_cache)
         ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
         self.cur_token.copy_(self.next_token)
@@ -359,10 +394,11 @@ class DropoutDecodeEngine:
     def first_token(self, last_hidden: torch.Tensor) -> None:
         """The first generated token is the plain argmax of the unmasked prefill
         (models/llava.py:382-388); last_hidden bf16 [B, d], final-norm."""
-        B, V = self.B, self.cfg.vocab
-        logits = self.pa.logits.view(B, V)
-        self._linear(last_hidden.contiguous(), self.w.lm_head, ops.EPI_F32, logits)
-        ops.aggregate(self.pa.logits, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.cur_token)
+        B = self.B
+        logits = self.pa.logits.view(B, self.Vp)
+        self._linear(last_hidden.contiguous(), self.w.lm_head_padded, ops.EPI_F32, logits)
+        ops.aggregate(self.pa.logits, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.cur_token,
+                      vocab=self.cfg.vocab)
         self.tokens_out[:, 0] = self.cur_token
         self.step_ctr.zero_()          # ensemble steps done; also the sampler's Philox call index / K
 
@@ -374,6 +410,21 @@ class DropoutDecodeEngine:
             return
         self.uniforms = u.to(self.dev, torch.float32).contiguous()
         self._u_step = torch.empty(self.B, self.K, self.n_vis, dtype=torch.float32, device=self.dev)
+
+    def step_logits(self) -> torch.Tensor:
+        """fp32 [B, V]: what the reference's forward() returns after a decode step -- the winning
+        member's logits (models/llava.py:370-376) or the member mean (select_by_average)."""
+        V = self.cfg.vocab
+        if self.aggregate == "mean":
+            return self.out_logits
+        if self.vote_on == "hidden":
+            return self.pa.logits[:, 0, :V]
+        return self.pb.logits[self._rows(), self.winner.long(), :V]
+
+    def _rows(self) -> torch.Tensor:
+        if not hasattr(self, "_row_idx"):
+            self._row_idx = torch.arange(self.B, device=self.dev)
+        return self._row_idx
 
     def generated(self) -> torch.Tensor:
         """Tokens generated so far, int32 [B, n]."""

@@ -24,8 +24,8 @@ from transformers import LlavaForConditionalGeneration
 from transformers.models.llava.modeling_llava import LlavaCausalLMOutputWithPast
 
 from .. import ops
-from ..engine import DecoderConfig, DecoderWeights, DropoutDecodeEngine
-from .config import settings
+from ._mixin import DropoutDecodeCache, DropoutDecodingMixin, decoder_weights_from_hf  # noqa: F401
+from .config import settings  # noqa: F401
 
 seed = 24  # models/llava.py:16
 
@@ -49,231 +49,15 @@ def select_by_average(outputs_all):
     return out
 
 
-def decoder_weights_from_hf(lm, lm_head, device) -> DecoderWeights:
-    """Fuse q|k|v and gate|up of an HF Llama/Mistral decoder into single weight streams.  The HF
-    parameters are re-pointed at views of the fused tensors, so no weight exists twice."""
-    c = lm.config
-    D = getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads
-    rope_theta = getattr(c, "rope_theta", None)
-    if rope_theta is None:
-        rp = getattr(c, "rope_parameters", None) or {}
-        rope_theta = rp.get("rope_theta", 10000.0)
-    cfg = DecoderConfig(c.num_hidden_layers, c.hidden_size, c.num_attention_heads, c.num_key_value_heads, D,
-                        c.intermediate_size, lm_head.weight.shape[0], c.rms_norm_eps, float(rope_theta))
-    cv = lambda t: t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
-    layers = []
-    for layer in lm.layers:
-        a, m = layer.self_attn, layer.mlp
-        wqkv = cv(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0))
-        wgu = cv(torch.cat([m.gate_proj.weight, m.up_proj.weight], 0))
-        nq, nk = a.q_proj.weight.shape[0], a.k_proj.weight.shape[0]
-        a.q_proj.weight.data, a.k_proj.weight.data, a.v_proj.weight.data = wqkv[:nq], wqkv[nq:nq + nk], wqkv[nq + nk:]
-        nf = m.gate_proj.weight.shape[0]
-        m.gate_proj.weight.data, m.up_proj.weight.data = wgu[:nf], wgu[nf:]
-        layers.append(dict(ln1=cv(layer.input_layernorm.weight), ln2=cv(layer.post_attention_layernorm.weight),
-                           wqkv=wqkv, wo=cv(a.o_proj.weight), wgu=wgu, wd=cv(m.down_proj.weight)))
-    return DecoderWeights(cfg, cv(lm.embed_tokens.weight), layers, cv(lm.norm.weight), cv(lm_head.weight))
-
-
-class CustomLlavaForConditionalGeneration(LlavaForConditionalGeneration):
-    topk = 5                    # models/llava.py:408
-    mask_mode = "cumulative"    # the mask is not restored between members, models/llava.py:342-346
+class CustomLlavaForConditionalGeneration(DropoutDecodingMixin, LlavaForConditionalGeneration):
+    """LLaVA-1.5 flavour: top-5 ids (models/llava.py:408), cumulative masks (:342-346), vote on logits,
+    mask seed 24 (:16)."""
+    topk = 5
+    mask_mode = "cumulative"
+    vote_on = "logits"
+    default_seed = seed
+    output_cls = LlavaCausalLMOutputWithPast
 
     def __init__(self, config):
         super().__init__(config)
-        # introspection state, same names as the reference (models/llava.py:57-72)
-        self.start_generation_pos = 0
-        self.start_image_pos: List[int] = []
-        self.end_image_pos: List[int] = []
-        self.is_first_generation = False
-        self.image_features = None          # (values, ids) of the per-visual-token top-k
-        self.logits_mask_prob: List[float] = []
-        self.all_outputs: list = []
-        self.int_array: list = []
-        self.token_entropies: List[float] = []
-        self.token_ventropies: List[float] = []
-        self.vision_uncert_dict: Optional[Dict[str, torch.Tensor]] = None
-        self.ag_mask_ids = None
-        self.image_logits = None
-        self.masked_numbers: List[int] = []
-        self.mask_seed = seed
-        self._weights: Optional[DecoderWeights] = None
-        self._engines: Dict[Tuple, DropoutDecodeEngine] = {}
-
-    # ------------------------------------------------------------------------------------------
-    def _lm(self):
-        return self.model.language_model
-
-    def decoder_weights(self) -> DecoderWeights:
-        if self._weights is None:
-            dev = self.lm_head.weight.device
-            if dev.type != "cuda":
-                raise ops.DropDecError("Dropout Decoding runs on a CUDA device only (no CPU path): move the "
-                                       "model to cuda first")
-            self._weights = decoder_weights_from_hf(self._lm(), self.lm_head, dev)
-        return self._weights
-
-    def _engine(self, batch: int, n_vis: int, max_seq: int, est_seq: int) -> DropoutDecodeEngine:
-        probs = tuple(float(p) for p in settings['voting_numbers'])
-        agg = "mean" if settings.get('use_avg') else "vote"
-        key = (batch, n_vis, max_seq, probs, agg, self.mask_mode, self._keep_relevant())
-        eng = self._engines.get(key)
-        if eng is None:
-            self._engines.clear()            # one live KV cache at a time
-            eng = DropoutDecodeEngine(self.decoder_weights(), batch, n_vis, max_seq, probs=probs,
-                                      mode=self.mask_mode, keep_relevant=self._keep_relevant(), topk=self.topk,
-                                      aggregate=agg, seed=self.mask_seed, max_steps=max_seq, est_seq=est_seq)
-            self._engines[key] = eng
-        return eng
-
-    def _keep_relevant(self) -> bool:
-        return True
-
-    # ------------------------------------------------------------------------------------------
-    def _merge(self, input_ids: torch.Tensor, pixel_values: torch.Tensor, **vision_kwargs):
-        """[text | visual | text] embeddings; records start/end_image_pos like
-        _merge_input_ids_with_image_features (models/llava.py:74-78)."""
-        img_tok = self.config.image_token_id if hasattr(self.config, "image_token_id") else self.config.image_token_index
-        feats = self.model.get_image_features(pixel_values=pixel_values, return_dict=True, **vision_kwargs).pooler_output
-        feats = torch.stack(list(feats)) if not torch.is_tensor(feats) else feats      # [B, n_vis, d]
-        B, n_vis, d = feats.shape
-        is_img = input_ids == img_tok
-        counts = is_img.sum(-1)
-        if not bool((counts == counts[0]).all()) or int(counts[0]) not in (1, n_vis):
-            raise ValueError(
-                f"The input provided to the model are wrong. The number of image tokens is {int(is_img.sum())} while"
-                f" the number of image given to the model is {B}. This prevents correct indexing and breaks batch "
-                f"generation.")                                  # models/llava.py:134-138
-        start = is_img.float().argmax(-1)
-        if not bool((start == start[0]).all()):
-            raise ValueError("batched prompts must place the image at the same position")
-        start = int(start[0])
-        emb = self.get_input_embeddings()(input_ids.masked_fill(is_img, 0)).to(feats.dtype)
-        tail = start + int(counts[0])
-        merged = torch.cat([emb[:, :start], feats, emb[:, tail:]], dim=1)
-        self.start_image_pos = [start]
-        self.end_image_pos = [start + n_vis - 1]
-        return merged, start, n_vis
-
-    @torch.no_grad()
-    def generate(self, input_ids: torch.LongTensor = None, pixel_values: torch.FloatTensor = None,
-                 attention_mask: Optional[torch.Tensor] = None, max_new_tokens: int = 20, num_beams: int = 1,
-                 pad_token_id: Optional[int] = None, eos_token_id: Optional[int] = None,
-                 uniforms: Optional[torch.Tensor] = None, use_cuda_graph: bool = True, **kwargs) -> torch.LongTensor:
-        """Greedy Dropout Decoding (reference call: chair_test/chair_test.py:341-346).  Returns
-        [B, S_in + T] token ids, prompt included.  Without pixel_values this is the parent's generate."""
-        if pixel_values is None:
-            return super().generate(input_ids=input_ids, attention_mask=attention_mask, max_new_tokens=max_new_tokens,
-                                    num_beams=num_beams, pad_token_id=pad_token_id, eos_token_id=eos_token_id, **kwargs)
-        if num_beams != 1:
-            raise ValueError("Dropout Decoding is greedy: num_beams must be 1")
-        if attention_mask is not None and not bool(attention_mask.all()):
-            raise ValueError("padded prompts are not supported: pass prompts of equal length")
-        dev = self.lm_head.weight.device
-        input_ids = input_ids.to(dev, non_blocking=True)
-        pixel_values = pixel_values.to(dev, self.lm_head.weight.dtype, non_blocking=True)
-        if eos_token_id is None:
-            eos_token_id = getattr(self.generation_config, "eos_token_id", None)
-        if isinstance(eos_token_id, (list, tuple)):
-            eos_token_id = eos_token_id[0] if eos_token_id else None
-        if pad_token_id is None:
-            pad_token_id = eos_token_id if eos_token_id is not None else 0
-        vis_kw = {k: kwargs[k] for k in ("vision_feature_layer", "vision_feature_select_strategy", "image_sizes")
-                  if kwargs.get(k) is not None}
-
-        merged, start, n_vis = self._merge(input_ids, pixel_values, **vis_kw)
-        B, S0, _ = merged.shape
-        self.is_first_generation = True
-        self.start_generation_pos = S0                                   # models/llava.py:285-286
-        eng = self._engine(B, n_vis, S0 + max_new_tokens, est_seq=S0 + max_new_tokens // 2)
-        eng.set_uniforms(uniforms)
-        hidden = eng.prefill(merged.to(torch.bfloat16), [start] * B)
-        eng.uncertainty_stage(hidden[:, start:start + n_vis])             # models/llava.py:306-314
-        eng.first_token(hidden[:, -1])
-        self._publish_uncertainty(eng)
-
-        steps_left = max_new_tokens - 1
-        chunk = 16 if eos_token_id is not None else steps_left
-        while steps_left > 0:
-            n = min(chunk, steps_left)
-            eng.decode(n, use_graph=use_cuda_graph)
-            steps_left -= n
-            if eos_token_id is not None and bool((eng.generated() == eos_token_id).any(-1).all()):
-                break
-        self.is_first_generation = False
-        new = eng.generated().long()
-        self.masked_numbers = eng.n_masked[0].tolist()
-        if eos_token_id is not None:                                    # finished rows emit pad (HF greedy)
-            done = (new == eos_token_id).cumsum(-1) > 0
-            after = torch.cat([torch.zeros_like(done[:, :1]), done[:, :-1]], dim=-1)
-            new = new.masked_fill(after, pad_token_id)
-            keep = int((~after).any(0).sum())
-            new = new[:, :keep]
-        return torch.cat([input_ids, new], dim=-1)
-
-    def _publish_uncertainty(self, eng: DropoutDecodeEngine) -> None:
-        """Expose the stage-1 results under the reference's names (models/llava.py:747-756, 408-410)."""
-        self.vision_uncert_dict = {
-            "variance_per_token": eng.var.clone(), "epis_uncert_per_token": eng.epi.clone(),
-            "alea_uncert_per_token": eng.alea.clone(), "variance": eng.var.mean(-1),
-            "epis_uncert": eng.epi.mean(-1), "alea_uncert": eng.alea.mean(-1)}
-        self.image_features = (None, eng.topk_ids.long())
-
-    # ---- public helpers kept from the reference -----------------------------------------------
-    def calculate_vision_uncertainty(self, logits: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """Reference signature (models/llava.py:710-756) takes materialised logits [B, L, V]; the
-        hot path never builds them (see project_vision_uncertainty).  This helper exists for API
-        compatibility and evaluates the same formulas with torch ops on the logits' device."""
-        probs = torch.softmax(logits.float(), dim=-1)
-        p_avg = probs.mean(dim=1, keepdim=True)
-        epi = (probs * (torch.log(probs + 1e-10) - torch.log(p_avg + 1e-10))).sum(-1)
-        alea = -(probs * torch.log(probs + 1e-10)).sum(-1)
-        var = probs.var(dim=-1)
-        return {"variance_per_token": var, "epis_uncert_per_token": epi, "alea_uncert_per_token": alea,
-                "variance": var.mean(-1), "epis_uncert": epi.mean(-1), "alea_uncert": alea.mean(-1)}
-
-    def project_vision_uncertainty(self, vis_hidden: torch.Tensor, round_logits: bool = True):
-        """Fused lm_head projection + uncertainty of final-norm visual hidden states [B, n_vis, d]
-        (dd_uncertainty_project): the logits are never materialised."""
-        w = self.decoder_weights()
-        epi, alea, var, ids = ops.uncertainty_project(vis_hidden.to(torch.bfloat16).contiguous(), w.lm_head,
-                                                      topk=self.topk, round_logits=round_logits)
-        return {"variance_per_token": var, "epis_uncert_per_token": epi, "alea_uncert_per_token": alea,
-                "variance": var.mean(-1), "epis_uncert": epi.mean(-1), "alea_uncert": alea.mean(-1)}, ids
-
-    def get_image_logits(self, logits, start_image_pos, end_image_pos):      # models/llava.py:412-426
-        return logits[:, start_image_pos:end_image_pos + 1]
-
-    def get_topk_token_id(self, image_logits, topk=5):                      # models/llava.py:428-441
-        return torch.topk(image_logits, topk, dim=-1)
-
-    def get_overlap_image_tokens(self, logits, id=-1):                       # models/llava.py:443-482
-        max_id = torch.argmax(logits, dim=-1)[0] if id == -1 else torch.tensor([id], device=logits.device)
-        ids = self.image_features[1][0]
-        hit = (ids == max_id.reshape(-1)[-1]).any(dim=1)
-        return torch.nonzero(hit).squeeze() + self.start_image_pos[0]
-
-    def get_image_attention_mask(self, logits, attention_mask, method="epis", prob=0.5, ids=[]):
-        """'epis' / 'epis_no_overlap' of the reference (models/llava.py:589-683) for ONE member, on the
-        device sampler: zeros `attention_mask` in place at the drawn visual positions (cumulative with
-        whatever is already zero) and restores the relevant tokens."""
-        if method not in ("epis", "epis_no_overlap"):
-            raise NotImplementedError(f"mask method {method!r} is dead code in the reference and not provided")
-        epi = self.vision_uncert_dict["epis_uncert_per_token"][:1].float().contiguous()
-        n_vis, start = epi.shape[1], self.start_image_pos[0]
-        y = torch.argmax(logits.reshape(-1, logits.shape[-1])[-1:], dim=-1).int()
-        keep = method == "epis"
-        self._mask_calls = getattr(self, "_mask_calls", 0)
-        bm, cnt = ops.sample_masks(epi, self.image_features[1][:1].int().contiguous(), y, [prob], mode="independent",
-                                   keep_relevant=False, seed=self.mask_seed, offset=4 * self._mask_calls)
-        self._mask_calls += 1
-        words = bm[0, 0].cpu().numpy().astype("uint32")
-        import numpy as np
-        bits = ((words[:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(-1)[:n_vis]
-        drop = torch.from_numpy(bits).to(attention_mask.device)
-        attention_mask[:, start:start + n_vis][:, drop] = 0
-        if keep:
-            rel = self.get_overlap_image_tokens(logits).reshape(-1)
-            attention_mask[:, rel] = 1
-            self.masked_numbers.append(int((attention_mask[0] == 0).sum()))
-        return attention_mask
+        self._dd_init_state()

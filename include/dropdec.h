@@ -67,7 +67,8 @@ const char* dd_last_error(void);
  * round_logits_bf16 != 0 rounds each logit to bf16 before the softmax, which is what the
  * reference's `lm_head(...)` in half precision followed by `.float()` does
  * (models/llama.py:46-47).
- * Limits: d % 64 == 0, n_vis <= 640 per image, topk <= DD_MAX_TOPK.
+ * Limits: d % 64 == 0, n_vis <= 8192 per image, topk <= DD_MAX_TOPK.  Images of up to 640 visual tokens
+ * take two GEMM sweeps; larger ones (LLaVA-NeXT anyres) three, because p_avg then needs its own sweep.
  * ------------------------------------------------------------------------------------------ */
 size_t dd_uncertainty_workspace_bytes(int n_images, int n_vis, int vocab, int topk);
 int dd_uncertainty_project(const void* h_vis /* bf16 [n_images, n_vis, d] */,

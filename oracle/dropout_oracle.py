@@ -353,7 +353,7 @@ def dropout_decode(lm: OracleLM, prompt_embeds: torch.Tensor, vis_start: int, n_
                    max_new_tokens: int, probs: Sequence[float], uniforms: Optional[torch.Tensor],
                    mode: str = "cumulative", keep_relevant: bool = True, topk: int = 5,
                    aggregate: str = "vote", eos_token_id: Optional[int] = None,
-                   keep_logits: bool = False, keep_prefill: bool = False) -> DecodeTrace:
+                   keep_logits: bool = False, keep_prefill: bool = False, vote_on: str = "logits") -> DecodeTrace:
     """One image, batch 1: prefill + uncertainty stage + (T-1) ensemble steps.
 
     prompt_embeds [S0, d] is the merged [text | visual | text] embedding sequence
@@ -389,7 +389,7 @@ def dropout_decode(lm: OracleLM, prompt_embeds: torch.Tensor, vis_start: int, n_
 
     ensemble_steps(lm, cache, tok, epis, tr.topk_ids, vis_start, n_vis, max_new_tokens - 1, probs, uniforms,
                    mode=mode, keep_relevant=keep_relevant, aggregate=aggregate, eos_token_id=eos_token_id,
-                   keep_logits=keep_logits, trace=tr)
+                   keep_logits=keep_logits, trace=tr, vote_on=vote_on)
     return tr
 
 
@@ -397,7 +397,7 @@ def ensemble_steps(lm: OracleLM, cache: OracleCache, tok: int, epis: torch.Tenso
                    vis_start: int, n_vis: int, n_steps: int, probs: Sequence[float],
                    uniforms: Optional[torch.Tensor], mode: str = "cumulative", keep_relevant: bool = True,
                    aggregate: str = "vote", eos_token_id: Optional[int] = None, keep_logits: bool = False,
-                   trace: Optional[DecodeTrace] = None) -> DecodeTrace:
+                   trace: Optional[DecodeTrace] = None, vote_on: str = "logits") -> DecodeTrace:
     """The decode branch of forward() (models/llava.py:254-283, 292-376) driven by the HF greedy
     loop: per token one preliminary forward, K masked forwards each on a deep copy of the whole
     cache, then the vote.  Starts from `cache` (prefix already filled) and the last token `tok`."""
@@ -430,7 +430,7 @@ def ensemble_steps(lm: OracleLM, cache: OracleCache, tok: int, epis: torch.Tenso
             mask[vis_start:vis_start + n_vis][d] = 0         # :657-660
             masked_n.append(int((mask == 0).sum().item()))   # :661
             h = lm.forward(x, cache_m, mask, pos)            # :350-359
-            member_logits.append(lm.logits(h)[0])
+            member_logits.append(h[0] if vote_on == "hidden" else lm.logits(h)[0])
             member_caches.append(cache_m)
             dropped_sets.append(torch.nonzero(d).reshape(-1).tolist())
         tr.dropped.append(dropped_sets)
@@ -440,6 +440,8 @@ def ensemble_steps(lm: OracleLM, cache: OracleCache, tok: int, epis: torch.Tenso
         if aggregate == "vote":
             win, _ = select_by_vote(member_logits)           # :361
             out_logits = member_logits[win]
+            if vote_on == "hidden":                          # instructblip.py:137-140
+                out_logits = lm.logits(out_logits[None])[0]
         elif aggregate == "mean":
             win = 0                                          # :39 (member 0's output / cache)
             out_logits = select_by_average(member_logits)

@@ -382,9 +382,88 @@ def gold_decode():
     json.dump(summary, open(os.path.join(HERE, "decode_tiny.json"), "w"), indent=1)
 
 
+# ----------------------------------------------------------------------------------------
+# 5. InstructBLIP flavour: the reference's real patched LM forward (models/instructblip.py:43-165)
+#    on a stub self vs oracle.dropout_decode(mode="quantile", vote_on="hidden", topk=10)
+# ----------------------------------------------------------------------------------------
+from golden_cases import BLIP_N_VIS, BLIP_T, BLIP_VOCAB, blip_merged  # noqa: E402
+
+
+def blip_inputs():
+    cfg = LMConfig(2, 256, 4, 4, 64, 512, BLIP_VOCAB)
+    w = init_lm_weights(cfg, seed=2, std=0.02, head_std=0.08)
+    return cfg, w, blip_merged(cfg.d_model)
+
+
+class _BlipModelOut:
+    def __init__(self, hidden, cache):
+        self.last_hidden_state, self.past_key_values = hidden, cache
+        self.hidden_states, self.attentions = None, None
+
+    def __getitem__(self, i):
+        assert i == 0
+        return self.last_hidden_state
+
+
+def gold_decode_blip():
+    cfg, w, merged = blip_inputs()
+    out = {}
+    for faithful in (False, True):
+        tag = "bf16" if faithful else "fp32"
+        lm = OracleLM(cfg, w, faithful=faithful)
+        s = SimpleNamespace()
+        for a in ("start_image_pos", "end_image_pos", "token_entropies", "token_ventropies", "logits_mask_prob"):
+            setattr(s, a, [])
+        s.start_generation_pos, s.image_features, s.first_generation = -1, None, True
+        s.vision_uncert_dict, s.image_logits = None, None
+
+        def model(input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                  inputs_embeds=None, **kw):
+            x = inputs_embeds[0] if inputs_embeds is not None else lm.embed(input_ids[0])
+            h = lm.forward(x, past_key_values.oc, attention_mask[0], position_ids[0])
+            return _BlipModelOut(h[None], past_key_values)
+
+        s.model = model
+        s.lm_head = lambda h: lm.logits(h)
+        for name in ("get_image_features", "get_image_logits", "get_topk_token_id", "get_overlap_image_tokens",
+                     "get_image_attention_mask", "calculate_vision_uncertainty", "calculate_entropy_varentropy"):
+            setattr(s, name, types.MethodType(getattr(RB, name), s))
+        # the reference passes the image span through module globals (models/instructblip.py:23-27, 599-651)
+        S0 = merged.shape[0]
+        ref_blip.start_img_pos, ref_blip.end_img_pos = 0, BLIP_N_VIS - 1
+        ref_blip.start_generation_pos, ref_blip.first_generation = S0, True
+        cache = _RefCache(cfg.n_layers)
+        toks, masked = [], []
+        o = RB.forward(s, input_ids=None, attention_mask=torch.ones(1, S0, dtype=torch.long),
+                       position_ids=torch.arange(S0)[None], past_key_values=cache, inputs_embeds=merged[None],
+                       use_cache=True)
+        tok = int(torch.argmax(o.logits[0, -1]))
+        toks.append(tok)
+        for t in range(BLIP_T - 1):
+            S = cache.oc.seq_len()
+            # a fresh all-ones mask every step: the HF-4.44 aliasing quirk (SURVEY 8a note) is not reproduced
+            o = RB.forward(s, input_ids=torch.tensor([[tok]]), attention_mask=torch.ones(1, S + 1, dtype=torch.long),
+                           position_ids=torch.tensor([[S]]), past_key_values=cache, use_cache=True)
+            cache = o.past_key_values
+            tok = int(torch.argmax(o.logits[0, -1]))
+            toks.append(tok)
+        tr = dropout_decode(lm, merged, 0, BLIP_N_VIS, BLIP_T, [0.3, 0.5, 0.7], None, mode="quantile", topk=10,
+                            vote_on="hidden", keep_logits=True)
+        assert tr.tokens == toks, (tr.tokens, toks)
+        close(tr.uncert["epis_uncert_per_token"], s.vision_uncert_dict["epis_uncert_per_token"], "blip epis",
+              **(dict(rtol=1e-3, atol=0) if faithful else {}))
+        print(f"[decode_blip/{tag}] tokens {toks[:8]}... winners {tr.winner} masked {tr.masked_numbers[0]}")
+        out[f"{tag}.tokens"] = np.asarray(tr.tokens, dtype=np.int32)
+        out[f"{tag}.winner"] = np.asarray(tr.winner, dtype=np.int32)
+        out[f"{tag}.member_ids"] = np.asarray(tr.member_ids, dtype=np.int32)
+        out[f"{tag}.masked_numbers"] = np.asarray(tr.masked_numbers, dtype=np.int32)
+        out[f"{tag}.epi"] = tr.uncert["epis_uncert_per_token"][0].numpy()
+    np.savez_compressed(os.path.join(HERE, "decode_blip_tiny.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["uncertainty", "masks", "aggregate", "decode"]
+    which = sys.argv[1:] or ["uncertainty", "masks", "aggregate", "decode", "decode_blip"]
     with torch.no_grad():
         for wname in which:
             globals()["gold_" + wname]()

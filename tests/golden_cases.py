@@ -63,3 +63,12 @@ def tiny_uniforms():
     (models/llava.py:16-18, 650)."""
     g = torch.Generator().manual_seed(TINY_SEED)
     return torch.rand(TINY_T - 1, len(TINY_PROBS), TINY_N_VIS, generator=g)
+
+
+# ---- InstructBLIP flavour, tiny: 32 visual tokens first, V = 32001, quantile masks, hidden-state vote ----
+BLIP_N_VIS, BLIP_T, BLIP_VOCAB = 32, 16, 32001
+
+
+def blip_merged(d_model=256):
+    g = torch.Generator().manual_seed(5)
+    return bf16r(torch.randn(BLIP_N_VIS + 9, d_model, generator=g))   # 32 Q-Former tokens + 9 prompt embeds

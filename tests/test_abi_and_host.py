@@ -48,8 +48,8 @@ def test_argument_validation_never_touches_the_gpu(lib):
     assert rc == -1 and b"M=33" in lib.dd_last_error()
     rc = lib.dd_skinny_gemm(one, one, None, 3, 4096, 4100, 0, one, None)
     assert rc == -1 and b"K=4100" in lib.dd_last_error()
-    rc = lib.dd_uncertainty_project(one, one, 1, 700, 4096, 32064, 5, 0, one, one, one, one, one, 1 << 30, None)
-    assert rc == -1 and b"n_vis=700" in lib.dd_last_error()
+    rc = lib.dd_uncertainty_project(one, one, 1, 9000, 4096, 32064, 5, 0, one, one, one, one, one, 1 << 30, None)
+    assert rc == -1 and b"n_vis=9000" in lib.dd_last_error()
     rc = lib.dd_aggregate(one, 1, 17, 100, 100, 0, one, one, one, None, None)
     assert rc == -1 and b"K=17" in lib.dd_last_error()
     assert lib.dd_attention_workspace_bytes(2, 3, 32, 128, 4) == 2 * 3 * 32 * 4 * 130 * 4

@@ -169,3 +169,66 @@ def test_batch_is_independent_of_batch_size(tiny, cuda):
     torch.cuda.synchronize()
     for b in range(3):
         assert eng.generated()[b].tolist() == tr.tokens[:11]
+
+
+# ---------------------------------------------------------------------------------------------
+# the other flavours of the reference: LLaVA-NeXT (independent masks, top-10), logit averaging,
+# InstructBLIP (quantile masks, vote on the hidden state, V = 32001 -> padded head)
+# ---------------------------------------------------------------------------------------------
+def _run_flavour(cuda, lm, w, cfg_engine, merged, vis_start, n_vis, T, mode, topk, aggregate, vote_on, U):
+    import oracle
+    from dropoutdecoding_b200.engine import DecoderWeights, DropoutDecodeEngine
+    with torch.no_grad():
+        tr = oracle.dropout_decode(lm, merged, vis_start, n_vis, T, TINY_PROBS, U, mode=mode, topk=topk,
+                                   aggregate=aggregate, vote_on=vote_on, keep_prefill=True, keep_logits=True)
+    eng = DropoutDecodeEngine(DecoderWeights.from_named(cfg_engine, w, cuda), batch=1, n_vis=n_vis, max_seq=700,
+                              probs=TINY_PROBS, mode=mode, topk=topk, aggregate=aggregate, vote_on=vote_on,
+                              max_steps=64)
+    eng.load_prefill(torch.stack(tr.prefill_cache.k)[:, None], torch.stack(tr.prefill_cache.v)[:, None], [vis_start])
+    if U is not None:
+        eng.set_uniforms(U[:, None].contiguous())
+    eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda))
+    eng.topk_ids.copy_(tr.topk_ids.to(cuda).int())
+    eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None])
+    for s in range(T - 1):
+        eng.decode(1, use_graph=False)
+        torch.cuda.synchronize()
+        assert eng.n_masked[0].tolist() == tr.masked_numbers[s], f"step {s}: masked_numbers"
+        assert eng.member_ids[0].tolist() == tr.member_ids[s], f"step {s}: member ids"
+        assert int(eng.winner[0]) == tr.winner[s], f"step {s}: winner"
+        assert int(eng.next_token[0]) == tr.tokens[s + 1], f"step {s}: token"
+        assert (eng.step_logits()[0].cpu() - tr.step_logits[s + 1]).abs().max().item() <= 2e-2
+    # and the same thing replayed as a CUDA graph from the start
+    eng.load_prefill(torch.stack(tr.prefill_cache.k)[:, None], torch.stack(tr.prefill_cache.v)[:, None], [vis_start])
+    eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None])
+    eng.decode(T - 1, use_graph=True)
+    torch.cuda.synchronize()
+    assert eng.generated()[0].tolist() == tr.tokens
+    return tr
+
+
+@pytest.mark.parametrize("mode,topk,aggregate", [("independent", 10, "vote"), ("cumulative", 5, "mean")],
+                         ids=["llava_next_flavour", "logit_mean"])
+def test_other_llava_flavours_bit_exact(tiny, cuda, mode, topk, aggregate, golden_dir):
+    from dropoutdecoding_b200.engine import DecoderConfig
+    tr = _run_flavour(cuda, tiny["lm"], tiny["lm"].w, DecoderConfig.tiny(), tiny["merged"], TINY_VIS_START,
+                      TINY_N_VIS, 12, mode, topk, aggregate, "logits", tiny["U"])
+    z = np.load(os.path.join(golden_dir, "decode_tiny.npz"))
+    key = "bf16.independent.tokens" if mode == "independent" else "bf16.mean.tokens"
+    assert tr.tokens == z[key].tolist()
+
+
+def test_instructblip_flavour_bit_exact(cuda, golden_dir):
+    """Quantile masks + vote on argmax of the hidden state + lm_head on the winner only
+    (models/instructblip.py:43-165), vocabulary 32001 (padded to 32016 for the weight stream)."""
+    import oracle
+    from golden_cases import BLIP_N_VIS, BLIP_T, BLIP_VOCAB, blip_merged
+    from dropoutdecoding_b200.engine import DecoderConfig
+    ocfg = oracle.LMConfig(2, 256, 4, 4, 64, 512, BLIP_VOCAB)
+    w = oracle.init_lm_weights(ocfg, seed=2, std=0.02, head_std=0.08)
+    lm = oracle.OracleLM(ocfg, w, faithful=True)
+    ecfg = DecoderConfig(2, 256, 4, 4, 64, 512, BLIP_VOCAB)
+    tr = _run_flavour(cuda, lm, w, ecfg, blip_merged(), 0, BLIP_N_VIS, BLIP_T, "quantile", 10, "vote", "hidden", None)
+    z = np.load(os.path.join(golden_dir, "decode_blip_tiny.npz"))
+    assert tr.tokens == z["bf16.tokens"].tolist() and tr.winner == z["bf16.winner"].tolist()
+    assert tr.masked_numbers[0] == [10, 16, 22]

@@ -331,3 +331,28 @@ def test_uncertainty_batched_images_and_bf16_rounding(ops, cuda):
             for got, key in ((epi, "epis_uncert_per_token"), (alea, "alea_uncert_per_token")):
                 want = ref[key][0]
                 assert ((got[i].cpu() - want).abs() / want.abs()).max() <= 1e-3
+
+
+@pytest.mark.parametrize("n_img,n_vis,d,V,k", [(1, 1500, 128, 3000, 10), (2, 700, 64, 1111, 5)],
+                         ids=["next_1500_rows_3_chunks", "two_images_700_rows"])
+def test_uncertainty_more_rows_than_tmem_holds(ops, cuda, n_img, n_vis, d, V, k):
+    """LLaVA-NeXT anyres yields up to ~2.9k visual tokens; beyond 640 rows the column mean p_avg is
+    formed in its own sweep (STATS -> COLSUM -> CROSS) instead of inside one TMEM-resident strip."""
+    from oracle import calculate_vision_uncertainty, topk_token_ids
+    g = torch.Generator().manual_seed(n_vis)
+    h = r16(torch.randn(n_img, n_vis, d, generator=g))
+    w = r16(torch.randn(V, d, generator=g) * 0.25)
+    epi, alea, var, ids = ops.uncertainty_project(h.to(cuda).bfloat16(), w.to(cuda).bfloat16(), topk=k)
+    for i in range(n_img):
+        logits = h[i] @ w.T
+        ref = calculate_vision_uncertainty(logits[None])
+        for got, key, atol in ((epi, "epis_uncert_per_token", 0.0), (alea, "alea_uncert_per_token", 2e-6),
+                               (var, "variance_per_token", 1e-9)):
+            want = ref[key][0]
+            rel = ((got[i].cpu() - want).abs() - atol) / want.abs()
+            assert rel.max() <= 1e-3, f"{key}: {rel.max():.2e}"
+        srt = torch.sort(logits, dim=-1, descending=True).values
+        safe = (srt[:, k - 1] - srt[:, k]) > 1e-4 * srt[:, 0].abs().clamp(min=1)
+        want_ids = torch.sort(topk_token_ids(logits[None], k)[1][0], -1).values
+        got_ids = torch.sort(ids[i].cpu().long(), -1).values
+        assert torch.equal(got_ids[safe], want_ids[safe])
