@@ -16,6 +16,13 @@ _LIB = None
 c_i32p = C.c_void_p  # raw device pointers travel as integers
 _P = C.c_void_p
 
+class RopeArgs(C.Structure):
+    """dd_rope_args of include/dropdec.h"""
+    _fields_ = [("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p), ("seq_lens", C.c_void_p),
+                ("members", C.c_int), ("H", C.c_int), ("H_kv", C.c_int), ("D", C.c_int),
+                ("q_out", C.c_void_p), ("k_new", C.c_void_p), ("v_new", C.c_void_p)]
+
+
 _SIGNATURES = {
     "dd_version": (C.c_int, []),
     "dd_last_error": (C.c_char_p, []),
@@ -34,6 +41,8 @@ _SIGNATURES = {
     "dd_aggregate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "dd_rmsnorm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "dd_skinny_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dd_decoder_linear": (C.c_int, [_P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P,
+                                    C.POINTER(RopeArgs), _P]),
     "dd_rope_stage": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "dd_embed_gather": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dd_step_advance": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),

@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const __nv_bfloat
 }
 
 // ---------------------------------------------------------------------------------------------
-// RoPE (rotate-half) + member staging.  One CTA per (b*M + m) row.
+// RoPE (rotate-half) + member staging.  One CTA per (row = b*M + m, head of q|k|v), D/2 threads:
+// a thread owns the pair (i, i + D/2).  (The <= 32-row decode path fuses this into the QKV GEMM.)
 // ---------------------------------------------------------------------------------------------
 __global__ void rope_stage_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_tab,
                                   const float* __restrict__ sin_tab, const int32_t* __restrict__ seq_lens,
@@ -63,27 +64,21 @@ __global__ void rope_stage_kernel(const __nv_bfloat16* __restrict__ qkv, const f
                                   __nv_bfloat16* __restrict__ k_new, __nv_bfloat16* __restrict__ v_new) {
   pdl_trigger();
   pdl_wait();
-  const int row = blockIdx.x;  // b*M + m
-  const int b = row / M;
-  const int pos = seq_lens[b];
+  const int row = blockIdx.x, head = blockIdx.y, i = threadIdx.x;  // b*M + m
   const int half = D / 2;
-  const __nv_bfloat16* src = qkv + (size_t)row * (H + 2 * H_kv) * D;
-  const float* c = cos_tab + (size_t)pos * half;
-  const float* s = sin_tab + (size_t)pos * half;
-  // q and k heads: pairs (i, i + D/2)
-  for (int idx = threadIdx.x; idx < (H + H_kv) * half; idx += blockDim.x) {
-    const int head = idx / half, i = idx % half;
-    const float x1 = __bfloat162float(src[head * D + i]);
-    const float x2 = __bfloat162float(src[head * D + i + half]);
-    const float o1 = x1 * c[i] - x2 * s[i];
-    const float o2 = x2 * c[i] + x1 * s[i];
-    __nv_bfloat16* dst = head < H ? q_out + ((size_t)row * H + head) * D
-                                  : k_new + ((size_t)row * H_kv + (head - H)) * D;
-    dst[i] = __float2bfloat16_rn(o1);
-    dst[i + half] = __float2bfloat16_rn(o2);
+  const __nv_bfloat16* src = qkv + ((size_t)row * (H + 2 * H_kv) + head) * D;
+  if (head >= H + H_kv) {
+    __nv_bfloat16* dst = v_new + ((size_t)row * H_kv + (head - H - H_kv)) * D;
+    dst[i] = src[i];
+    dst[i + half] = src[i + half];
+    return;
   }
-  for (int idx = threadIdx.x; idx < H_kv * D; idx += blockDim.x)
-    v_new[(size_t)row * H_kv * D + idx] = src[(size_t)(H + H_kv) * D + idx];
+  const int pos = seq_lens[row / M];
+  const float c = cos_tab[(size_t)pos * half + i], s = sin_tab[(size_t)pos * half + i];
+  const float x1 = __bfloat162float(src[i]), x2 = __bfloat162float(src[i + half]);
+  __nv_bfloat16* dst = head < H ? q_out + ((size_t)row * H + head) * D : k_new + ((size_t)row * H_kv + (head - H)) * D;
+  dst[i] = __float2bfloat16_rn(x1 * c - x2 * s);
+  dst[i + half] = __float2bfloat16_rn(x2 * c + x1 * s);
 }
 
 __global__ void embed_gather_kernel(const uint4* __restrict__ embed, const int32_t* __restrict__ token, int M,
@@ -146,7 +141,7 @@ extern "C" int dd_rope_stage(const void* qkv, const float* cos_tab, const float*
   DD_CHECK_ARG(qkv && cos_tab && sin_tab && seq_lens && q_out && k_new && v_new, "dd_rope_stage: null pointer");
   DD_CHECK_ARG(D % 2 == 0 && H >= 1 && H_kv >= 1, "dd_rope_stage: bad head shape");
   if (B * M == 0) return DD_OK;
-  DD_LAUNCH_CHAIN(rope_stage_kernel, dim3(B * M), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)qkv,
+  DD_LAUNCH_CHAIN(rope_stage_kernel, dim3(B * M, H + 2 * H_kv), dim3(D / 2), 0, (cudaStream_t)stream, (const __nv_bfloat16*)qkv,
                   cos_tab, sin_tab, seq_lens, M, H, H_kv, D, (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_new,
                   (__nv_bfloat16*)v_new);
   return DD_OK;

@@ -12,6 +12,12 @@
 //   * fp32 partial sums of the 8 warps are reduced through shared memory; the epilogue fuses the
 //     bf16 rounding points of the HF decoder (residual add, SwiGLU, fp32 logits).
 // Algorithmic bytes per launch: N*K*2 (x2 for SwiGLU) -- the weights, read exactly once.
+//
+// dd_decoder_linear adds the two fusions that remove the small kernels between the GEMMs of a layer:
+//   * NORM prologue: the RMSNorm of the input rows is applied while the B fragments are built (every
+//     CTA recomputes the row's 1/rms from L2-resident x while its first weight batch is in flight);
+//   * ROPE epilogue (QKV projection): a CTA owns features {8j..8j+7} and {D/2+8j..D/2+8j+7} of one head,
+//     i.e. complete rotate-half pairs, applies RoPE and writes q / k_new / v_new in the staging layout.
 #include "dd_common.cuh"
 
 #ifndef DD_GEMM_PIPE
@@ -42,10 +48,16 @@ __device__ __forceinline__ void load_w_batch(uint4 (&dst)[kUnroll][NW][2], const
   }
 }
 
-template <int MT, int NW, int kUnroll>
+// bf16( bf16(x * rstd) * w ) on a packed pair -- the two rounding points of LlamaRMSNorm
+__device__ __forceinline__ uint32_t norm_pair(uint32_t x, uint32_t w, float rstd) {
+  const float2 f = bf16x2_to_float2(x), ww = bf16x2_to_float2(w);
+  return pack_bf16x2(bf16_round(f.x * rstd) * ww.x, bf16_round(f.y * rstd) * ww.y);
+}
+
+template <int MT, int NW, int kUnroll, bool NORM>
 __device__ __forceinline__ void mma_batch(float (&acc)[NW][MT][4], const uint4 (&wa)[kUnroll][NW][2],
                                           const __nv_bfloat16* const (&xrow)[MT], const bool (&xok)[MT], int s0,
-                                          int steps) {
+                                          int steps, const __nv_bfloat16* nrow, const float (&rstd)[MT]) {
   uint4 xv[kUnroll][MT];
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u) {
@@ -54,6 +66,16 @@ __device__ __forceinline__ void mma_batch(float (&acc)[NW][MT][4], const uint4 (
 #pragma unroll
       for (int j = 0; j < MT; ++j)
         xv[u][j] = xok[j] ? *reinterpret_cast<const uint4*>(xrow[j] + ko) : make_uint4(0, 0, 0, 0);
+      if (NORM) {
+        const uint4 nw = *reinterpret_cast<const uint4*>(nrow + ko);
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          xv[u][j].x = norm_pair(xv[u][j].x, nw.x, rstd[j]);
+          xv[u][j].y = norm_pair(xv[u][j].y, nw.y, rstd[j]);
+          xv[u][j].z = norm_pair(xv[u][j].z, nw.z, rstd[j]);
+          xv[u][j].w = norm_pair(xv[u][j].w, nw.w, rstd[j]);
+        }
+      }
     }
   }
 #pragma unroll
@@ -70,11 +92,25 @@ __device__ __forceinline__ void mma_batch(float (&acc)[NW][MT][4], const uint4 (
   }
 }
 
-template <int MT, int EPI>
-__global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bfloat16* __restrict__ x,
-                                                                   const __nv_bfloat16* __restrict__ w,
-                                                                   const __nv_bfloat16* __restrict__ residual,
-                                                                   int M, int N, int K, void* __restrict__ y) {
+struct GemmArgs {
+  const __nv_bfloat16 *x, *w, *residual, *norm_w;
+  float eps;
+  int M, N, K;
+  void* y;
+  // DD_EPI_ROPE
+  const float *cos_tab, *sin_tab;
+  const int32_t* seq_lens;
+  int members, H, H_kv, D;
+  __nv_bfloat16 *q_out, *k_new, *v_new;
+};
+
+template <int MT, int EPI, bool NORM>
+__global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const GemmArgs a) {
+  const __nv_bfloat16* __restrict__ x = a.x;
+  const __nv_bfloat16* __restrict__ w = a.w;
+  const __nv_bfloat16* __restrict__ residual = a.residual;
+  const int M = a.M, N = a.N, K = a.K;
+  void* __restrict__ y = a.y;
   constexpr int NW = (EPI == DD_EPI_SWIGLU) ? 2 : 1;  // weight row tiles per CTA
   // k-steps (of 32) whose weight loads are in flight per warp: 8 for a single token tile (measured best
   // on B200: 6.43 vs 6.57 ms per 7B ensemble step), fewer when more accumulators compete for registers
@@ -84,6 +120,7 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
   constexpr int kUnroll = DD_GEMM_PIPE ? ((MT * NW >= 3) ? 2 : 4) : (MT == 1 ? 8 : 4);
 #endif
   __shared__ float s_red[kGemmWarps][NW][MT][16][8 + 1];
+  __shared__ float s_ss[NORM ? kGemmWarps : 1][MT][8];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -96,9 +133,16 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
   const __nv_bfloat16* wrow[NW][2];
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
-    const size_t r0 = (size_t)(i * N + n0 + g);  // SwiGLU: up rows start at row N
+    size_t r0 = (size_t)(i * N + n0 + g);  // SwiGLU: up rows start at row N
+    size_t r1 = r0 + 8;
+    if (EPI == DD_EPI_ROPE && n0 < (a.H + a.H_kv) * a.D) {
+      // q / k head: rows 8j+g and D/2+8j+g of the head -> the CTA holds whole rotate-half pairs
+      const int tph = a.D / 16, head = blockIdx.x / tph, jj = blockIdx.x % tph;
+      r0 = (size_t)head * a.D + 8 * jj + g;
+      r1 = r0 + a.D / 2;
+    }
     wrow[i][0] = w + r0 * K + kbeg + 8 * t;
-    wrow[i][1] = w + (r0 + 8) * K + kbeg + 8 * t;
+    wrow[i][1] = w + r1 * K + kbeg + 8 * t;
   }
   const __nv_bfloat16* xrow[MT];
   bool xok[MT];
@@ -117,6 +161,47 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
 
+  const __nv_bfloat16* nrow = NORM ? a.norm_w + kbeg + 8 * t : nullptr;
+  float rstd[MT];
+#pragma unroll
+  for (int j = 0; j < MT; ++j) rstd[j] = 1.f;
+  // 1/rms of this lane's token rows: every warp squares its own k slice, smem adds the 8 slices.  Runs
+  // under the latency of the first weight batch.
+  auto row_rstd = [&]() {
+    if (!NORM) return;
+    float ss[MT];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) ss[j] = 0.f;
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        if (xok[j]) {
+          const uint4 v = *reinterpret_cast<const uint4*>(xrow[j] + s * 32);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = bf16x2_to_float2(u[k]);
+            ss[j] = fmaf(f.x, f.x, ss[j]);
+            ss[j] = fmaf(f.y, f.y, ss[j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+      ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], 1);
+      ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], 2);
+      if (t == 0) s_ss[warp][j][g] = ss[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+      float tot = 0.f;
+#pragma unroll
+      for (int wp = 0; wp < kGemmWarps; ++wp) tot += s_ss[wp][j][g];
+      rstd[j] = rsqrtf(tot / (float)K + a.eps);
+    }
+  };
   // PDL: the weights do not depend on the previous kernel -- put the first batch of the stream in
   // flight before waiting for our activations.
 #if DD_GEMM_PIPE
@@ -124,12 +209,13 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
   load_w_batch<NW, kUnroll>(wa0, wrow, 0, steps);
   pdl_trigger_stream_entry();
   pdl_wait();
+  row_rstd();
   for (int s0 = 0; s0 < steps; s0 += 2 * kUnroll) {  // software-pipelined: next batch loads under the MMAs
     if (s0 + kUnroll < steps) load_w_batch<NW, kUnroll>(wa1, wrow, s0 + kUnroll, steps);
-    mma_batch<MT, NW, kUnroll>(acc, wa0, xrow, xok, s0, steps);
+    mma_batch<MT, NW, kUnroll, NORM>(acc, wa0, xrow, xok, s0, steps, nrow, rstd);
     if (s0 + kUnroll < steps) {
       if (s0 + 2 * kUnroll < steps) load_w_batch<NW, kUnroll>(wa0, wrow, s0 + 2 * kUnroll, steps);
-      mma_batch<MT, NW, kUnroll>(acc, wa1, xrow, xok, s0 + kUnroll, steps);
+      mma_batch<MT, NW, kUnroll, NORM>(acc, wa1, xrow, xok, s0 + kUnroll, steps, nrow, rstd);
     }
   }
 #else
@@ -137,9 +223,10 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
   load_w_batch<NW, kUnroll>(wa, wrow, 0, steps);
   pdl_trigger_stream_entry();
   pdl_wait();
+  row_rstd();
   for (int s0 = 0; s0 < steps; s0 += kUnroll) {
     if (s0 > 0) load_w_batch<NW, kUnroll>(wa, wrow, s0, steps);
-    mma_batch<MT, NW, kUnroll>(acc, wa, xrow, xok, s0, steps);
+    mma_batch<MT, NW, kUnroll, NORM>(acc, wa, xrow, xok, s0, steps, nrow, rstd);
   }
 #endif
   pdl_trigger_stream_tail();
@@ -156,6 +243,38 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
     }
   __syncthreads();
 
+  if constexpr (EPI == DD_EPI_ROPE) {
+    auto red = [&](int j, int r, int tc) {
+      float s = 0.f;
+#pragma unroll
+      for (int wp = 0; wp < kGemmWarps; ++wp) s += s_red[wp][0][j][r][tc];
+      return bf16_round(s);  // the projection's own bf16 output
+    };
+    if (n0 < (a.H + a.H_kv) * a.D) {
+      // one thread per (token, pair): features i = 8jj+r and i + D/2 of one head
+      const int tph = a.D / 16, head = blockIdx.x / tph, jj = blockIdx.x % tph, half = a.D / 2;
+      for (int o = tid; o < MT * 8 * 8; o += kGemmThreads) {
+        const int r = o & 7, tok = o >> 3;
+        if (tok >= M) continue;
+        const int j = tok >> 3, tc = tok & 7, i = 8 * jj + r;
+        const float x1 = red(j, r, tc), x2 = red(j, r + 8, tc);
+        const int pos = a.seq_lens[tok / a.members];
+        const float c = a.cos_tab[(size_t)pos * half + i], sn = a.sin_tab[(size_t)pos * half + i];
+        __nv_bfloat16* dst = head < a.H ? a.q_out + ((size_t)tok * a.H + head) * a.D
+                                        : a.k_new + ((size_t)tok * a.H_kv + (head - a.H)) * a.D;
+        dst[i] = __float2bfloat16_rn(x1 * c - x2 * sn);
+        dst[i + half] = __float2bfloat16_rn(x2 * c + x1 * sn);
+      }
+    } else {
+      for (int o = tid; o < MT * 8 * 16; o += kGemmThreads) {
+        const int r = o & 15, tok = o >> 4;
+        if (tok >= M) continue;
+        const int n = n0 + r - (a.H + a.H_kv) * a.D;  // feature inside the v block
+        a.v_new[(size_t)tok * a.H_kv * a.D + n] = __float2bfloat16_rn(red(tok >> 3, r, tok & 7));
+      }
+    }
+    return;
+  }
   // one thread per (token, feature): 8*MT tokens x 16 features
   for (int o = tid; o < MT * 8 * 16; o += kGemmThreads) {
     const int r = o & 15, tok = o >> 4;  // feature fastest: coalesced 32B stores per token
@@ -184,20 +303,35 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const __nv_bf
   }
 }
 
-template <int MT>
-static int launch_mt(int epi, const void* x, const void* w, const void* residual, int M, int N, int K, void* y,
-                     cudaStream_t st) {
-  const dim3 grid(N / 16), block(kGemmThreads);
-  auto X = (const __nv_bfloat16*)x;
-  auto W = (const __nv_bfloat16*)w;
-  auto R = (const __nv_bfloat16*)residual;
+template <int MT, bool NORM>
+static int launch_mt(const GemmArgs& a, int epi, cudaStream_t st) {
+  const dim3 grid(a.N / 16), block(kGemmThreads);
   switch (epi) {
-    case DD_EPI_NONE: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_NONE>, grid, block, 0, st, X, W, R, M, N, K, y); break;
-    case DD_EPI_RESIDUAL: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_RESIDUAL>, grid, block, 0, st, X, W, R, M, N, K, y); break;
-    case DD_EPI_F32: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_F32>, grid, block, 0, st, X, W, R, M, N, K, y); break;
-    case DD_EPI_SWIGLU: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_SWIGLU>, grid, block, 0, st, X, W, R, M, N, K, y); break;
+    case DD_EPI_NONE: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_NONE, NORM>, grid, block, 0, st, a); break;
+    case DD_EPI_RESIDUAL: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_RESIDUAL, NORM>, grid, block, 0, st, a); break;
+    case DD_EPI_F32: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_F32, NORM>, grid, block, 0, st, a); break;
+    case DD_EPI_SWIGLU: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_SWIGLU, NORM>, grid, block, 0, st, a); break;
+    case DD_EPI_ROPE: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_ROPE, NORM>, grid, block, 0, st, a); break;
     default: set_error("dd_skinny_gemm: bad epilogue %d", epi); return DD_ERR_INVALID_ARG;
   }
+  return DD_OK;
+}
+
+template <bool NORM>
+static int launch_any(const GemmArgs& a, int epi, cudaStream_t st) {
+  switch ((a.M + 7) / 8) {
+    case 1: return launch_mt<1, NORM>(a, epi, st);
+    case 2: return launch_mt<2, NORM>(a, epi, st);
+    case 3: return launch_mt<3, NORM>(a, epi, st);
+    default: return launch_mt<4, NORM>(a, epi, st);
+  }
+}
+
+static int check_gemm_shape(const char* fn, const void* x, const void* w, int M, int N, int K) {
+  DD_CHECK_ARG(x && w, "%s: null pointer", fn);
+  DD_CHECK_ARG(M >= 0 && M <= 32, "%s: M=%d out of [0,32]", fn, M);
+  DD_CHECK_ARG(N > 0 && N % 16 == 0, "%s: N=%d must be a positive multiple of 16", fn, N);
+  DD_CHECK_ARG(K > 0 && K % (32 * kGemmWarps) == 0, "%s: K=%d must be a multiple of %d", fn, K, 32 * kGemmWarps);
   return DD_OK;
 }
 
@@ -206,19 +340,40 @@ static int launch_mt(int epi, const void* x, const void* w, const void* residual
 extern "C" int dd_skinny_gemm(const void* x, const void* w, const void* residual, int M, int N, int K,
                               int epilogue, void* y, dd_stream_t stream) {
   using namespace dd;
-  DD_CHECK_ARG(x && w && y, "dd_skinny_gemm: null pointer");
-  DD_CHECK_ARG(M >= 0 && M <= 32, "dd_skinny_gemm: M=%d out of [0,32]", M);
-  DD_CHECK_ARG(N > 0 && N % 16 == 0, "dd_skinny_gemm: N=%d must be a positive multiple of 16", N);
-  DD_CHECK_ARG(K > 0 && K % (32 * kGemmWarps) == 0, "dd_skinny_gemm: K=%d must be a multiple of %d", K,
-               32 * kGemmWarps);
+  if (int rc = check_gemm_shape("dd_skinny_gemm", x, w, M, N, K)) return rc;
+  DD_CHECK_ARG(y, "dd_skinny_gemm: null pointer");
+  DD_CHECK_ARG(epilogue >= DD_EPI_NONE && epilogue <= DD_EPI_SWIGLU, "dd_skinny_gemm: bad epilogue %d", epilogue);
   DD_CHECK_ARG(epilogue != DD_EPI_RESIDUAL || residual, "dd_skinny_gemm: residual epilogue needs residual");
   if (M == 0) return DD_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int mt = (M + 7) / 8;
-  switch (mt) {
-    case 1: return launch_mt<1>(epilogue, x, w, residual, M, N, K, y, st);
-    case 2: return launch_mt<2>(epilogue, x, w, residual, M, N, K, y, st);
-    case 3: return launch_mt<3>(epilogue, x, w, residual, M, N, K, y, st);
-    default: return launch_mt<4>(epilogue, x, w, residual, M, N, K, y, st);
+  GemmArgs a{};
+  a.x = (const __nv_bfloat16*)x; a.w = (const __nv_bfloat16*)w; a.residual = (const __nv_bfloat16*)residual;
+  a.M = M; a.N = N; a.K = K; a.y = y;
+  return launch_any<false>(a, epilogue, (cudaStream_t)stream);
+}
+
+extern "C" int dd_decoder_linear(const void* x, const void* norm_w, float eps, const void* w, const void* residual,
+                                 int M, int N, int K, int epilogue, void* y, const dd_rope_args* rope,
+                                 dd_stream_t stream) {
+  using namespace dd;
+  if (int rc = check_gemm_shape("dd_decoder_linear", x, w, M, N, K)) return rc;
+  DD_CHECK_ARG(epilogue >= DD_EPI_NONE && epilogue <= DD_EPI_ROPE, "dd_decoder_linear: bad epilogue %d", epilogue);
+  DD_CHECK_ARG(epilogue == DD_EPI_ROPE || y, "dd_decoder_linear: null output");
+  DD_CHECK_ARG(epilogue != DD_EPI_RESIDUAL || residual, "dd_decoder_linear: residual epilogue needs residual");
+  GemmArgs a{};
+  a.x = (const __nv_bfloat16*)x; a.w = (const __nv_bfloat16*)w; a.residual = (const __nv_bfloat16*)residual;
+  a.norm_w = (const __nv_bfloat16*)norm_w; a.eps = eps;
+  a.M = M; a.N = N; a.K = K; a.y = y;
+  if (epilogue == DD_EPI_ROPE) {
+    DD_CHECK_ARG(rope && rope->cos_tab && rope->sin_tab && rope->seq_lens && rope->q_out && rope->k_new && rope->v_new,
+                 "dd_decoder_linear: DD_EPI_ROPE needs a complete dd_rope_args");
+    DD_CHECK_ARG(rope->members >= 1 && rope->D % 16 == 0 && rope->H >= 1 && rope->H_kv >= 1 &&
+                     N == (rope->H + 2 * rope->H_kv) * rope->D,
+                 "dd_decoder_linear: N=%d is not (H + 2 H_kv) * D", N);
+    a.cos_tab = rope->cos_tab; a.sin_tab = rope->sin_tab; a.seq_lens = rope->seq_lens;
+    a.members = rope->members; a.H = rope->H; a.H_kv = rope->H_kv; a.D = rope->D;
+    a.q_out = (__nv_bfloat16*)rope->q_out; a.k_new = (__nv_bfloat16*)rope->k_new; a.v_new = (__nv_bfloat16*)rope->v_new;
   }
+  if (M == 0) return DD_OK;
+  return norm_w ? launch_any<true>(a, epilogue, (cudaStream_t)stream)
+                : launch_any<false>(a, epilogue, (cudaStream_t)stream);
 }

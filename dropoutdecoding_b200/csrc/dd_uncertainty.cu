@@ -92,6 +92,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -208,12 +212,34 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     int slot = 0;
     uint32_t phase = 0;
+#ifdef DD_UNC_KROT
+    // every CTA reads the SAME activation tiles; start each CTA's k loop at a different k-block so that
+    // at any instant the 148 SMs pull different lines (no L2 slice hot-spot).  Sums are order-independent
+    // up to fp32 rounding and the order is fixed per CTA, so results stay deterministic.
+    const int krot = (part * DD_UNC_KROT) % num_kb;
+#else
+    const int krot = 0;
+#endif
+#ifdef DD_UNC_W_PREFETCH
+    // the W strip comes from HBM (each tile is read by exactly one CTA), the activations from L2: pull the
+    // W tiles into L2 DD_UNC_W_PREFETCH k-blocks ahead so that the ring only ever sees L2 latency
+    if (elect_one())
+      for (int t = 0; t < DD_UNC_W_PREFETCH && strip_beg + t / num_kb < strip_end; ++t)
+        tma_prefetch_2d(&tmap_w, ((t + krot) % num_kb) * BK, (strip_beg + t / num_kb) * BN);
+#endif
     for (int strip = strip_beg; strip < strip_end; ++strip) {
       for (int kb = 0; kb < num_kb; ++kb) {
+#ifdef DD_UNC_W_PREFETCH
+        {
+          const int t = (strip - strip_beg) * num_kb + kb + DD_UNC_W_PREFETCH;
+          const int ps = strip_beg + t / num_kb;
+          if (ps < strip_end && elect_one()) tma_prefetch_2d(&tmap_w, ((t + krot) % num_kb) * BK, ps * BN);
+        }
+#endif
         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
         if (elect_one()) {
           mbar_expect_tx(bar_full + 8 * slot, BN * BK * 2);
-          tma_load_2d(ring + slot * kSlotBytes, &tmap_w, bar_full + 8 * slot, kb * BK, strip * BN);
+          tma_load_2d(ring + slot * kSlotBytes, &tmap_w, bar_full + 8 * slot, ((kb + krot) % num_kb) * BK, strip * BN);
         }
         __syncwarp();
         if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
@@ -222,7 +248,8 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           mbar_wait(bar_empty + 8 * slot, phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(bar_full + 8 * slot, BM * BK * 2);
-            tma_load_3d(ring + slot * kSlotBytes, &tmap_a, bar_full + 8 * slot, kb * BK, row0 + mt * BM, img);
+            tma_load_3d(ring + slot * kSlotBytes, &tmap_a, bar_full + 8 * slot, ((kb + krot) % num_kb) * BK,
+                        row0 + mt * BM, img);
           }
           __syncwarp();
           if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
@@ -293,6 +320,10 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_wait(bar_tfull, it & 1);
       tc_fence_after();
 
+#ifdef DD_UNC_NO_EPI
+      for (int mt = 0; mt < NUM_MT; ++mt) { tc_fence_before(); mbar_arrive(bar_tempty + 8 * mt); }
+      continue;
+#endif
       if (MODE == MODE_STATS) {
 #pragma unroll
         for (int mt = 0; mt < NUM_MT; ++mt) {

@@ -238,6 +238,8 @@ class DropoutDecodeEngine:
         rows = B * M
         ops.embed_gather(self.w.embed, self.cur_token, M, pb.x)
         x, x2 = pb.x, pb.x2
+        if rows <= 32:
+            return self._forward_fused(pb, bitmask, head)
         for l, lw in enumerate(self.w.layers):
             ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pb.xn)
             self._linear(pb.xn, lw["wqkv"], ops.EPI_NONE, pb.qkv)
@@ -253,6 +255,33 @@ class DropoutDecodeEngine:
         self.launches_per_step += 2         # embed gather, final norm
         if head:
             self._linear(pb.xn, self.w.lm_head_padded, ops.EPI_F32, pb.logits.view(rows, self.Vp))
+        return pb.logits
+
+    def _forward_fused(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool) -> torch.Tensor:
+        """<= 32 rows: 6 launches per layer.  Both RMSNorms ride in the prologue of the GEMM that consumes
+        them and RoPE + member staging in the epilogue of the QKV projection (dd_decoder_linear)."""
+        cfg, B, M = self.cfg, self.B, pb.M
+        H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
+        rows = B * M
+        x, x2 = pb.x, pb.x2
+        for l, lw in enumerate(self.w.layers):
+            ops.decoder_linear(x, lw["wqkv"], ops.EPI_ROPE, norm_w=lw["ln1"], eps=cfg.rms_eps,
+                               rope=dict(cos=self.cos, sin=self.sin, seq_lens=self.seq_lens, members=M, H=H, H_kv=Hkv,
+                                         D=D, q_out=pb.q, k_new=pb.k_new[l], v_new=pb.v_new[l]))
+            ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
+                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws)
+            ops.decoder_linear(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
+            ops.decoder_linear(x2, lw["wgu"], ops.EPI_SWIGLU, norm_w=lw["ln2"], eps=cfg.rms_eps, out=pb.act)
+            ops.decoder_linear(pb.act, lw["wd"], ops.EPI_RESIDUAL, residual=x2, out=x)
+            self.launches_per_step += 6
+        self.launches_per_step += 1         # embed gather
+        if head:
+            ops.decoder_linear(x, self.w.lm_head_padded, ops.EPI_F32, norm_w=self.w.norm, eps=cfg.rms_eps,
+                               out=pb.logits.view(rows, self.Vp))
+            self.launches_per_step += 1
+        else:
+            ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pb.xn)     # InstructBLIP votes on the final-norm hidden state
+            self.launches_per_step += 1
         return pb.logits
 
     # ------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ from ._lib import DropDecError, check
 
 MASK_CUMULATIVE, MASK_INDEPENDENT, MASK_QUANTILE = 0, 1, 2
 AGG_VOTE, AGG_MEAN = 0, 1
-EPI_NONE, EPI_RESIDUAL, EPI_F32, EPI_SWIGLU = 0, 1, 2, 3
+EPI_NONE, EPI_RESIDUAL, EPI_F32, EPI_SWIGLU, EPI_ROPE = 0, 1, 2, 3, 4
 MASK_MODES = {"cumulative": MASK_CUMULATIVE, "independent": MASK_INDEPENDENT, "quantile": MASK_QUANTILE}
 
 
@@ -200,6 +200,41 @@ def skinny_gemm(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_NONE, resi
         _need(residual, torch.bfloat16, "residual")
     check(L.dd_skinny_gemm(_ptr(x), _ptr(w), _ptr(residual), M, N, K, epilogue, _ptr(out), _stream()),
           "dd_skinny_gemm")
+    return out
+
+
+def decoder_linear(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_NONE, *, norm_w: Optional[torch.Tensor] = None,
+                   eps: float = 1e-5, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                   rope: Optional[dict] = None) -> Optional[torch.Tensor]:
+    """dd_decoder_linear: skinny GEMM with an optional fused RMSNorm of x (norm_w) and, for EPI_ROPE, the
+    RoPE + member staging epilogue.  rope = dict(cos, sin, seq_lens, members, H, H_kv, D, q_out, k_new, v_new)."""
+    L = _lib.load()
+    _need(x, torch.bfloat16, "x"); _need(w, torch.bfloat16, "w")
+    M, K = x.shape
+    N = w.shape[0] // 2 if epilogue == EPI_SWIGLU else w.shape[0]
+    if w.shape[1] != K:
+        raise DropDecError("decoder_linear: x and w disagree on K")
+    if norm_w is not None:
+        _need(norm_w, torch.bfloat16, "norm_w")
+    if residual is not None:
+        _need(residual, torch.bfloat16, "residual")
+    ra = None
+    if epilogue == EPI_ROPE:
+        if rope is None:
+            raise DropDecError("decoder_linear: EPI_ROPE needs rope=dict(...)")
+        _need(rope["cos"], torch.float32, "cos"); _need(rope["sin"], torch.float32, "sin")
+        _need(rope["seq_lens"], torch.int32, "seq_lens")
+        for k in ("q_out", "k_new", "v_new"):
+            _need(rope[k], torch.bfloat16, k)
+        ra = _lib.RopeArgs(_ptr(rope["cos"]), _ptr(rope["sin"]), _ptr(rope["seq_lens"]), int(rope["members"]),
+                           int(rope["H"]), int(rope["H_kv"]), int(rope["D"]), _ptr(rope["q_out"]),
+                           _ptr(rope["k_new"]), _ptr(rope["v_new"]))
+    elif out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if epilogue == EPI_F32 else torch.bfloat16, device=x.device)
+    import ctypes
+    check(L.dd_decoder_linear(_ptr(x), _ptr(norm_w), float(eps), _ptr(w), _ptr(residual), M, N, K, epilogue,
+                              _ptr(out), ctypes.byref(ra) if ra is not None else None, _stream()),
+          "dd_decoder_linear")
     return out
 
 

@@ -175,6 +175,28 @@ int dd_skinny_gemm(const void* x /* bf16 [M, K] */, const void* w /* bf16 [N(,2N
                    const void* residual /* bf16 [M, N] or NULL */, int M, int N, int K, int epilogue,
                    void* y, dd_stream_t stream);
 
+/* Fused decoder GEMM: dd_skinny_gemm plus the two fusions that remove the small kernels between the
+ * GEMMs of a decoder layer (same rounding points as the separate kernels):
+ *   norm_w != NULL : x is replaced on the fly by dd_rmsnorm(x, norm_w, eps)   (input_layernorm /
+ *                    post_attention_layernorm / final norm of the HF Llama decoder);
+ *   DD_EPI_ROPE    : w = [q ; k ; v] rows, N = (H + 2 H_kv) * D; the bf16 projection is rotated and
+ *                    staged exactly as dd_rope_stage does (q_out, k_new, v_new); y is ignored.
+ * Row r of x is (sequence r / members, member r % members). */
+#define DD_EPI_ROPE 4
+typedef struct dd_rope_args {
+  const float* cos_tab; /* fp32 [max_pos, D/2] */
+  const float* sin_tab;
+  const int32_t* seq_lens; /* [B]: position of the new token */
+  int members, H, H_kv, D;
+  void* q_out; /* bf16 [B, members, H, D]    */
+  void* k_new; /* bf16 [B, members, H_kv, D] */
+  void* v_new;
+} dd_rope_args;
+int dd_decoder_linear(const void* x /* bf16 [M, K] */, const void* norm_w /* bf16 [K] or NULL */, float eps,
+                      const void* w /* bf16 [N(,2N), K] */, const void* residual /* bf16 [M, N] or NULL */,
+                      int M, int N, int K, int epilogue, void* y, const dd_rope_args* rope /* or NULL */,
+                      dd_stream_t stream);
+
 /* RoPE (rotate-half) on the new token's q and k, and staging of the member rows:
  *   qkv [B*M, (H + 2 H_kv) * D] (q | k | v) -> q_out [B,M,H,D], k_new [B,M,H_kv,D], v_new [B,M,H_kv,D]
  * position of sequence b = seq_lens[b]; cos/sin tables are fp32 [max_pos, D/2]. */

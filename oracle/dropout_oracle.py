@@ -342,6 +342,7 @@ class DecodeTrace:
     member_ids: List[List[int]] = field(default_factory=list)      # member argmax ids
     winner: List[int] = field(default_factory=list)                # winning member index
     step_logits: List[torch.Tensor] = field(default_factory=list)  # returned logits [V] per step
+    member_logits: List[List[torch.Tensor]] = field(default_factory=list)  # [step][member] vote inputs (keep_logits)
     uncert: Optional[Dict[str, torch.Tensor]] = None
     topk_ids: Optional[torch.Tensor] = None
     vis_hidden: Optional[torch.Tensor] = None
@@ -453,5 +454,6 @@ def ensemble_steps(lm: OracleLM, cache: OracleCache, tok: int, epis: torch.Tenso
         tr.tokens.append(tok)
         if keep_logits:
             tr.step_logits.append(out_logits)
+            tr.member_logits.append(member_logits)
         step += 1
     return tr

@@ -36,6 +36,21 @@ def tiny(cuda):
     return dict(lm=lm, merged=merged, U=U, trace=tr, weights=weights, Engine=DropoutDecodeEngine)
 
 
+def check_member_ids(got, want, member_logits, where, flips):
+    """Member argmax ids must equal the oracle's, except at a genuine near-tie: the vote inputs are
+    bf16-quantised, so two candidates one bf16 ulp apart in the ORACLE's own logits can swap when the
+    GPU sums the same fp32 products in another order.  Such a swap is counted (and capped by the
+    caller); anything further apart is a failure."""
+    for m, (g, w) in enumerate(zip(got, want)):
+        if g == w:
+            continue
+        l = member_logits[m]
+        gap = float(l[w] - l[g])
+        ulp = 2.0 ** (np.floor(np.log2(max(abs(float(l[w])), 1e-30))) - 7)     # bf16: 8 significant bits
+        assert 0.0 <= gap <= 2 * ulp, f"{where} member {m}: id {g} vs {w}, oracle gap {gap:.3e} > 2 ulp ({ulp:.3e})"
+        flips.append((where, m, g, w))
+
+
 def make_engine(t, cuda, **kw):
     return t["Engine"](t["weights"], batch=1, n_vis=TINY_N_VIS, max_seq=640, probs=TINY_PROBS, mode="cumulative",
                        topk=5, seed=24, max_steps=64, **kw)
@@ -95,6 +110,7 @@ def test_ensemble_decode_bit_exact(tiny, cuda, use_graph):
         torch.cuda.synchronize()
         assert eng.generated()[0].tolist() == tr.tokens
         return
+    flips = []
     for s in range(n_steps):
         eng.decode(1, use_graph=False)
         torch.cuda.synchronize()
@@ -104,9 +120,10 @@ def test_ensemble_decode_bit_exact(tiny, cuda, use_graph):
         for m in range(3):
             bits = ((w[m][:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(-1)[:TINY_N_VIS]
             assert np.nonzero(bits)[0].tolist() == tr.dropped[s][m], f"step {s} member {m}: mask index set"
-        assert eng.member_ids[0].tolist() == tr.member_ids[s], f"step {s}: member argmax ids"
+        check_member_ids(eng.member_ids[0].tolist(), tr.member_ids[s], tr.member_logits[s], f"step {s}", flips)
         assert int(eng.winner[0]) == tr.winner[s], f"step {s}: vote winner"
         assert int(eng.next_token[0]) == tr.tokens[s + 1], f"step {s}: token"
+    assert len(flips) <= 2, f"too many near-tie swaps: {flips}"
     assert eng.generated()[0].tolist() == tr.tokens
 
 
@@ -190,14 +207,16 @@ def _run_flavour(cuda, lm, w, cfg_engine, merged, vis_start, n_vis, T, mode, top
     eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda))
     eng.topk_ids.copy_(tr.topk_ids.to(cuda).int())
     eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None])
+    flips = []
     for s in range(T - 1):
         eng.decode(1, use_graph=False)
         torch.cuda.synchronize()
         assert eng.n_masked[0].tolist() == tr.masked_numbers[s], f"step {s}: masked_numbers"
-        assert eng.member_ids[0].tolist() == tr.member_ids[s], f"step {s}: member ids"
+        check_member_ids(eng.member_ids[0].tolist(), tr.member_ids[s], tr.member_logits[s], f"step {s}", flips)
         assert int(eng.winner[0]) == tr.winner[s], f"step {s}: winner"
         assert int(eng.next_token[0]) == tr.tokens[s + 1], f"step {s}: token"
         assert (eng.step_logits()[0].cpu() - tr.step_logits[s + 1]).abs().max().item() <= 2e-2
+    assert len(flips) <= 2, f"too many near-tie swaps: {flips}"
     # and the same thing replayed as a CUDA graph from the start
     eng.load_prefill(torch.stack(tr.prefill_cache.k)[:, None], torch.stack(tr.prefill_cache.v)[:, None], [vis_start])
     eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None])

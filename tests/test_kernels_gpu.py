@@ -286,6 +286,50 @@ def test_rmsnorm_rope_embed(ops, cuda):
     assert torch.equal(out.view(2, 3, 256), emb[tok.long()][:, None].expand(2, 3, 256))
 
 
+@pytest.mark.parametrize("B,Mm,H,H_kv,D,K", [(1, 1, 4, 4, 64, 256), (1, 3, 32, 32, 128, 4096), (2, 3, 8, 2, 128, 512),
+                                             (4, 8, 4, 4, 64, 256)])
+def test_decoder_linear_fused_norm_and_rope(ops, cuda, B, Mm, H, H_kv, D, K):
+    """dd_decoder_linear = rmsnorm -> skinny GEMM -> rope/staging in one launch: equal to the chain of
+    separate kernels (one bf16 ulp where the 1/rms summation order moves a rounding) and to the fp32
+    restatement with the HF rounding points."""
+    from oracle import rope_table
+    g = torch.Generator().manual_seed(B * 100 + Mm * 10 + H)
+    rows, N = B * Mm, (H + 2 * H_kv) * D
+    x = r16(torch.randn(rows, K, generator=g) * 2).to(cuda).bfloat16()
+    nw = r16(torch.rand(K, generator=g) + 0.5).to(cuda).bfloat16()
+    w = r16(torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda).bfloat16()
+    cos, sin = rope_table(D, 10000.0, 64, faithful=True)
+    cos, sin = cos.to(cuda), sin.to(cuda)
+    seq = torch.randint(3, 60, (B,), generator=g).int().to(cuda)
+
+    def bufs():
+        return (torch.zeros(B, Mm, H, D, dtype=torch.bfloat16, device=cuda),
+                torch.zeros(B, Mm, H_kv, D, dtype=torch.bfloat16, device=cuda),
+                torch.zeros(B, Mm, H_kv, D, dtype=torch.bfloat16, device=cuda))
+
+    q1, k1, v1 = bufs()
+    xn = ops.rmsnorm(x, nw, 1e-5)
+    qkv = ops.skinny_gemm(xn, w)
+    ops.rope_stage(qkv, cos, sin, seq, B, Mm, H, H_kv, D, q1, k1, v1)
+    q2, k2, v2 = bufs()
+    ops.decoder_linear(x, w, ops.EPI_ROPE, norm_w=nw, eps=1e-5,
+                       rope=dict(cos=cos, sin=sin, seq_lens=seq, members=Mm, H=H, H_kv=H_kv, D=D, q_out=q2, k_new=k2,
+                                 v_new=v2))
+    for a, b in ((q1, q2), (k1, k2), (v1, v2)):
+        d = (a.float() - b.float()).abs()
+        assert d.max().item() <= 2 ** -6 * max(1.0, a.float().abs().max().item())
+        assert (d > 0).float().mean().item() < 0.02          # nearly always bit-identical
+    # fused norm + plain / SwiGLU / residual / fp32 epilogues against the unfused chain
+    w2 = r16(torch.randn(512, K, generator=g) / math.sqrt(K)).to(cuda).bfloat16()
+    res = r16(torch.randn(rows, 512, generator=g)).to(cuda).bfloat16()
+    for epi, kw in ((ops.EPI_NONE, {}), (ops.EPI_RESIDUAL, dict(residual=res)), (ops.EPI_F32, {}), (ops.EPI_SWIGLU, {})):
+        want = ops.skinny_gemm(xn, w2, epi, **kw)
+        got = ops.decoder_linear(x, w2, epi, norm_w=nw, eps=1e-5, **kw)
+        d = (want.float() - got.float()).abs()
+        assert d.max().item() <= 2 ** -6 * max(1.0, want.float().abs().max().item())
+        assert torch.equal(ops.decoder_linear(xn, w2, epi, **kw), want)      # no norm: the very same kernel
+
+
 # ---------------------------------------------------------------------------------------------
 # (1) uncertainty stage (tcgen05) vs calculate_vision_uncertainty / get_topk_token_id (golden)
 # ---------------------------------------------------------------------------------------------

@@ -101,9 +101,9 @@ def bench_gemm():
                               frac_hbm=round(algo / med / 1e9 / HBM, 3), cublas_us=round(tmed * 1e6, 2), peak=SRC)))
 
 
-def bench_uncertainty():
-    for (n_img, n_vis, d, V, k) in [(1, 576, 4096, 32064, 5), (4, 576, 4096, 32064, 5), (8, 576, 4096, 32064, 5),
-                                    (32, 32, 4096, 32001, 10)]:
+def bench_uncertainty(only_first=False):
+    cases = [(1, 576, 4096, 32064, 5), (4, 576, 4096, 32064, 5), (8, 576, 4096, 32064, 5), (32, 32, 4096, 32001, 10)]
+    for (n_img, n_vis, d, V, k) in cases[:1] if only_first else cases:
         h = torch.randn(n_img, n_vis, d, device=dev).bfloat16()
         w = (torch.randn(V, d, device=dev) * 0.02).bfloat16()
         fn = lambda: ops.uncertainty_project(h, w, topk=k)
@@ -111,7 +111,7 @@ def bench_uncertainty():
         flops = 2.0 * n_img * n_vis * d * V
         tfn = lambda: torch.matmul(h.view(-1, d), w.T)
         tmed, _ = timeit(tfn, iters=10)
-        print(json.dumps(dict(kernel="uncertainty_project(2 sweeps+finalize)", n_img=n_img, n_vis=n_vis, d=d, V=V,
+        print(json.dumps(dict(kernel="uncertainty_project", lib=os.path.basename(os.environ.get("DD_LIB", "default")), n_img=n_img, n_vis=n_vis, d=d, V=V,
                               us=round(med * 1e6, 1), best_us=round(best * 1e6, 1), TFLOPs=round(flops / med / 1e12, 1),
                               frac_tensor=round(flops / med / 1e12 / TF, 3), cublas_gemm_only_us=round(tmed * 1e6, 1),
                               peak=SRC)))
@@ -157,3 +157,5 @@ if __name__ == "__main__":
             bench_gemm()
         if which in ("uncertainty", "all"):
             bench_uncertainty()
+        if which == "uncertainty_first":
+            bench_uncertainty(only_first=True)
