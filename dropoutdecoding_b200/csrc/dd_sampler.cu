@@ -23,7 +23,7 @@ struct SamplerParams {
   uint64_t seed, offset0;
   float coef[DD_MAX_MEMBERS];  // (float)(prob - 0.1)      models/llava.py:646
   float q32[DD_MAX_MEMBERS];   // (float)(1 - prob)        models/instructblip.py:450
-  int topk, K, mode, keep_relevant, B, n_vis, mask_words;
+  int topk, K, mode, keep_relevant, B, n_vis, mask_words, seq_base;
 };
 
 // Philox4x32-10, bit-compatible with cuRAND's curand_init(seed, subsequence, offset) +
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_kernel(const SamplerP
             u = p.uniforms[((size_t)b * p.K + m) * n + i];
           } else {
             const uint64_t call = (uint64_t)step * p.K + m;  // one rand_like call per member per step
-            u = philox_uniform(p.seed, ((uint64_t)b << 32) | (uint32_t)i, p.offset0 + 4ull * call);
+            u = philox_uniform(p.seed, ((uint64_t)(p.seq_base + b) << 32) | (uint32_t)i, p.offset0 + 4ull * call);
           }
           drop = u < pr;  // NaN (max == min) compares false: nothing dropped
         }
@@ -189,7 +189,7 @@ __global__ void philox_uniform_kernel(uint64_t seed, uint64_t offset, int n, flo
 extern "C" int dd_sample_masks(const float* epi, const int32_t* topk_ids, int topk, const int32_t* y_init,
                                const double* probs_host, int K, const float* uniforms, uint64_t seed,
                                uint64_t offset0, const int32_t* step, int mode, int keep_relevant, int B,
-                               int n_vis, uint32_t* bitmask, int mask_words, int32_t* n_masked,
+                               int n_vis, int seq_base, uint32_t* bitmask, int mask_words, int32_t* n_masked,
                                dd_stream_t stream) {
   using namespace dd;
   DD_CHECK_ARG(epi && bitmask && probs_host, "dd_sample_masks: null pointer");
@@ -210,7 +210,7 @@ extern "C" int dd_sample_masks(const float* epi, const int32_t* topk_ids, int to
     p.q32[m] = (float)(1.0 - probs_host[m]);
   }
   p.topk = topk; p.K = K; p.mode = mode; p.keep_relevant = keep_relevant; p.B = B; p.n_vis = n_vis;
-  p.mask_words = mask_words;
+  p.mask_words = mask_words; p.seq_base = seq_base;
   const size_t smem = mode == DD_MASK_QUANTILE ? (size_t)n_vis * sizeof(float) : 0;
   DD_LAUNCH_CHAIN(sampler_kernel, dim3(B), dim3(kSamplerThreads), smem, (cudaStream_t)stream, p);
   return DD_OK;

@@ -165,33 +165,35 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const GemmArg
   float rstd[MT];
 #pragma unroll
   for (int j = 0; j < MT; ++j) rstd[j] = 1.f;
-  // 1/rms of this lane's token rows: every warp squares its own k slice, smem adds the 8 slices.  Runs
-  // under the latency of the first weight batch.
+  // 1/rms of the token rows, computed by the whole CTA with every load independent (one L2 round trip,
+  // hidden under the first weight batch): thread -> 16-byte pieces tid, tid+256, ... of each row.
   auto row_rstd = [&]() {
     if (!NORM) return;
-    float ss[MT];
+    const int nvec = K / 8;
+    for (int m0 = 0; m0 < M; m0 += 4) {  // 4 rows at a time bounds the registers
+      float ss[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < MT; ++j) ss[j] = 0.f;
-    for (int s = 0; s < steps; ++s) {
+      for (int r = 0; r < 4; ++r) {
+        if (m0 + r < M) {
+          const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)(m0 + r) * K);
+#pragma unroll 4
+          for (int v = tid; v < nvec; v += kGemmThreads) {
+            const uint4 q = xr[v];
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        if (xok[j]) {
-          const uint4 v = *reinterpret_cast<const uint4*>(xrow[j] + s * 32);
-          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 f = bf16x2_to_float2(u[k]);
-            ss[j] = fmaf(f.x, f.x, ss[j]);
-            ss[j] = fmaf(f.y, f.y, ss[j]);
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = bf16x2_to_float2(u[k]);
+              ss[r] = fmaf(f.x, f.x, ss[r]);
+              ss[r] = fmaf(f.y, f.y, ss[r]);
+            }
           }
         }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < MT; ++j) {
-      ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], 1);
-      ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], 2);
-      if (t == 0) s_ss[warp][j][g] = ss[j];
+      for (int r = 0; r < 4; ++r) {
+        const float tot = warp_sum(ss[r]);
+        if (lane == 0 && m0 + r < M) s_ss[warp][(m0 + r) >> 3][(m0 + r) & 7] = tot;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const GemmArg
       float tot = 0.f;
 #pragma unroll
       for (int wp = 0; wp < kGemmWarps; ++wp) tot += s_ss[wp][j][g];
-      rstd[j] = rsqrtf(tot / (float)K + a.eps);
+      rstd[j] = xok[j] ? rsqrtf(tot / (float)K + a.eps) : 0.f;
     }
   };
   // PDL: the weights do not depend on the previous kernel -- put the first batch of the stream in

@@ -12,10 +12,14 @@
 //   column reduction over every row of the image, before sum_v p[i,v] log(p_avg[v]) can be formed.
 //
 //   warp 4   : TMA producer.  Per k-block (64 bf16 = one 128B-swizzle row) it loads the W strip tile
-//              [96 x 64] and NUM_MT activation tiles [128 x 64] into a ring of 16 KB slots.
+//              [96 x 64] (HBM stream) and the activation tile of the LAST row tile into a 3-stage ring.
+//   warps 6-9: cp.async loaders for the other (up to 4) activation tiles [128 x 64] per k-block, written
+//              in the SWIZZLE_128B layout by hand (16-byte chunk c of row r -> chunk c ^ (r & 7)).
+//              Measured on B200 (tools/umma_probe.cu, profiles/r01): one SM ingests 35 B/clk through TMA
+//              boxes of this shape but 57-65 B/clk through cp.async, and this kernel needs 81 B/clk to
+//              keep the tensor core busy -- so the L2-resident activations use both paths at once.
 //   warp 5   : MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128 N=96 K=16,
-//              both operands K-major SWIZZLE_128B straight from the TMA-written slots; slots are
-//              released with tcgen05.commit.
+//              both operands K-major SWIZZLE_128B; slots are released with tcgen05.commit.
 //   warps 0-3: epilogue.  tcgen05.ld 32x32b: one thread = one visual row, so softmax statistics are
 //              thread-local; the column sums are a butterfly over the warp plus 4 smem rows.
 //
@@ -32,10 +36,16 @@
 namespace dd {
 
 constexpr int BM = 128, BN = 96, BK = 64, UMMA_K = 16;
-constexpr int kSlotBytes = BM * BK * 2;  // 16 KB: one [128 x 64] bf16 tile (W tile uses 12 KB of it)
-constexpr int kNumSlots = 13;
+constexpr int kSlotBytes = BM * BK * 2;  // 16 KB: one [128 x 64] bf16 activation tile
+constexpr int kWBytes = BN * BK * 2;     // 12 KB: one [96 x 64] bf16 W tile
+constexpr int kCpTiles = 4;              // row tiles 0..3 of a k-block arrive through cp.async, the rest through TMA
+constexpr int kCpSlots = 8;              // cp.async ring (16 KB slots): two k-blocks deep
+constexpr int kTmaStages = 3;            // TMA ring: stage = W tile + one activation tile
+constexpr int kTmaStageBytes = kWBytes + kSlotBytes;
+constexpr int kCpThreads = 128;
 constexpr int kEpiThreads = 128;
-constexpr int kUncThreads = 192;
+constexpr int kUncThreads = 192 + kCpThreads;
+constexpr int kNumBars = 2 * kCpSlots + 2 * kTmaStages + 1 + 5;
 constexpr int kTmemCols = 512;
 constexpr int kMaxMT = 5;  // row tiles of 128 per image (n_vis <= 640)
 constexpr float kLog2e = 1.4426950408889634f;
@@ -96,6 +106,15 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1)
                : "memory");
 }
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills (rows past n_vis)
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -149,6 +168,7 @@ struct UncParams {
   int32_t* part_topi;      // [img][parts][n_vis][topk]
   const float* row_stats;  // [img][n_vis][2]             (m, 1/Z)  FUSED input
   float* part_acq;         // [img][parts][n_vis][3]      (A, Q, C) FUSED output
+  const __nv_bfloat16* h_vis;  // [img][n_vis][d] (cp.async path of the activation tiles)
   int n_chunks;            // row chunks of kMaxMT*128 rows per image (> 1 when n_vis > 640)
   float* colpart;          // [img][chunk][n_strips*BN]   column sums of p over one row chunk (COLSUM -> logpavg)
   float* logpavg;          // [img][n_strips*BN]          log(p_avg + eps)                    (CROSS input)
@@ -166,9 +186,12 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles (the dynamic smem base is only 16-byte aligned by contract)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kNumSlots * kSlotBytes);
-  // bars: full[kNumSlots] | empty[kNumSlots] | tmem_full | tmem_empty[kMaxMT]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNumSlots + 1 + kMaxMT);
+  constexpr int NCP = NUM_MT < kCpTiles ? NUM_MT : kCpTiles;  // row tiles per k-block through cp.async
+  constexpr bool kTmaA = NUM_MT > NCP;                          // the last row tile rides with the W tile
+  uint8_t* tma_ring_p = smem + kCpSlots * kSlotBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tma_ring_p + kTmaStages * kTmaStageBytes);
+  // bars: cp_full[kCpSlots] | cp_empty[kCpSlots] | tma_full[kTmaStages] | tma_empty[kTmaStages] | tmem_full | tmem_empty[5]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   float* s_col = reinterpret_cast<float*>(tmem_slot + 4);  // [4][BN]
   float* s_logp = s_col + 4 * BN;                            // [BN]
 
@@ -180,12 +203,17 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int strip_end = min(p.n_strips, strip_beg + spc);
   const int num_kb = p.d / BK;
 
-  const uint32_t ring = smem_u32(smem);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kNumSlots;
-  const uint32_t bar_tfull = bar_full + 16 * kNumSlots, bar_tempty = bar_tfull + 8;
+  const uint32_t cp_ring = smem_u32(smem), tma_ring = smem_u32(tma_ring_p);
+  const uint32_t bar_cpfull = smem_u32(bars), bar_cpempty = bar_cpfull + 8 * kCpSlots;
+  const uint32_t bar_full = bar_cpempty + 8 * kCpSlots, bar_empty = bar_full + 8 * kTmaStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kTmaStages, bar_tempty = bar_tfull + 8;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumSlots; ++i) {
+    for (int i = 0; i < kCpSlots; ++i) {
+      mbar_init(bar_cpfull + 8 * i, kCpThreads);  // (first 2 used) one cp.async-completion arrival per loader thread per k-block
+      mbar_init(bar_cpempty + 8 * i, 1);
+    }
+    for (int i = 0; i < kTmaStages; ++i) {
       mbar_init(bar_full + 8 * i, 1);
       mbar_init(bar_empty + 8 * i, 1);
     }
@@ -210,82 +238,84 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     }
-    int slot = 0;
+    int stage = 0;
     uint32_t phase = 0;
-#ifdef DD_UNC_KROT
-    // every CTA reads the SAME activation tiles; start each CTA's k loop at a different k-block so that
-    // at any instant the 148 SMs pull different lines (no L2 slice hot-spot).  Sums are order-independent
-    // up to fp32 rounding and the order is fixed per CTA, so results stay deterministic.
-    const int krot = (part * DD_UNC_KROT) % num_kb;
-#else
-    const int krot = 0;
-#endif
-#ifdef DD_UNC_W_PREFETCH
-    // the W strip comes from HBM (each tile is read by exactly one CTA), the activations from L2: pull the
-    // W tiles into L2 DD_UNC_W_PREFETCH k-blocks ahead so that the ring only ever sees L2 latency
-    if (elect_one())
-      for (int t = 0; t < DD_UNC_W_PREFETCH && strip_beg + t / num_kb < strip_end; ++t)
-        tma_prefetch_2d(&tmap_w, ((t + krot) % num_kb) * BK, (strip_beg + t / num_kb) * BN);
-#endif
     for (int strip = strip_beg; strip < strip_end; ++strip) {
       for (int kb = 0; kb < num_kb; ++kb) {
-#ifdef DD_UNC_W_PREFETCH
-        {
-          const int t = (strip - strip_beg) * num_kb + kb + DD_UNC_W_PREFETCH;
-          const int ps = strip_beg + t / num_kb;
-          if (ps < strip_end && elect_one()) tma_prefetch_2d(&tmap_w, ((t + krot) % num_kb) * BK, ps * BN);
-        }
-#endif
-        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(bar_full + 8 * slot, BN * BK * 2);
-          tma_load_2d(ring + slot * kSlotBytes, &tmap_w, bar_full + 8 * slot, ((kb + krot) % num_kb) * BK, strip * BN);
+          const uint32_t dst = tma_ring + stage * kTmaStageBytes;
+          mbar_expect_tx(bar_full + 8 * stage, kWBytes + (kTmaA ? kSlotBytes : 0));
+          tma_load_2d(dst, &tmap_w, bar_full + 8 * stage, kb * BK, strip * BN);
+          if (kTmaA) tma_load_3d(dst + kWBytes, &tmap_a, bar_full + 8 * stage, kb * BK, row0 + NCP * BM, img);
         }
         __syncwarp();
-        if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
-#pragma unroll
-        for (int mt = 0; mt < NUM_MT; ++mt) {
-          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(bar_full + 8 * slot, BM * BK * 2);
-            tma_load_3d(ring + slot * kSlotBytes, &tmap_a, bar_full + 8 * slot, ((kb + krot) % num_kb) * BK,
-                        row0 + mt * BM, img);
-          }
-          __syncwarp();
-          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
-        }
+        if (++stage == kTmaStages) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (warp >= 6) {
+    // =========================== cp.async loaders (warps 6-9): row tiles 0..NCP-1 ================
+    const int t = threadIdx.x - 192;   // 0..127
+    const int c = t & 7, r_in = t >> 3;  // 16-byte chunk of the 128 B row; row inside a group of 16
+    const __nv_bfloat16* gbase = p.h_vis + (size_t)img * p.n_vis * p.d + c * 8;
+    // group = the NCP tiles of one k-block: per-tile empty barriers (fine-grained refill), ONE full barrier per
+    // group (the MMA warp pays one wait + one proxy fence per k-block instead of one per tile)
+    uint32_t g = 0;
+    for (int strip = strip_beg; strip < strip_end; ++strip) {
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const uint32_t gslot = g & 1, gphase = (g >> 1) & 1;
+#pragma unroll
+        for (int mt = 0; mt < NCP; ++mt) {
+          const uint32_t slot = gslot * kCpTiles + mt;
+          mbar_wait(bar_cpempty + 8 * slot, gphase ^ 1);
+          const uint32_t dst = cp_ring + slot * kSlotBytes;
+#pragma unroll
+          for (int i = 0; i < BM / 16; ++i) {
+            const int row = i * 16 + r_in, grow = row0 + mt * BM + row;
+            const bool ok = grow < p.n_vis;
+            cp_async_16_zfill(dst + row * 128 + ((c ^ (row & 7)) << 4),
+                              gbase + (size_t)(ok ? grow : 0) * p.d + kb * BK, ok ? 16u : 0u);
+          }
+        }
+        cp_async_arrive_noinc(bar_cpfull + 8 * gslot);
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 5) {
     // =========================== MMA issuer (warp-converged, one elected lane issues) ==========
-    int slot = 0;
-    uint32_t phase = 0, it = 0;
+    int stage = 0;
+    uint32_t phase = 0, it = 0, g = 0;
     for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(bar_full + 8 * slot, phase);
-        const int slot_b = slot;
-        const uint64_t b_desc = make_smem_desc(ring + slot * kSlotBytes);
-        if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const uint32_t gslot = g & 1, gphase = (g >> 1) & 1;
+        mbar_wait(bar_full + 8 * stage, phase);
+        mbar_wait(bar_cpfull + 8 * gslot, gphase);
+        fence_proxy_async();  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+        tc_fence_after();
+        const uint32_t wbase = tma_ring + stage * kTmaStageBytes;
+        const uint64_t b_desc = make_smem_desc(wbase);
 #pragma unroll
         for (int mt = 0; mt < NUM_MT; ++mt) {
           // first k-block of a strip: the epilogue must have drained this row tile's accumulators
-          if (kb == 0) mbar_wait(bar_tempty + 8 * mt, (it & 1) ^ 1);
-          mbar_wait(bar_full + 8 * slot, phase);
-          tc_fence_after();
-          const uint64_t a_desc = make_smem_desc(ring + slot * kSlotBytes);
+          if (kb == 0) {
+            mbar_wait(bar_tempty + 8 * mt, (it & 1) ^ 1);
+            tc_fence_after();
+          }
+          const uint32_t abase = mt < NCP ? cp_ring + (gslot * kCpTiles + mt) * kSlotBytes : wbase + kWBytes;
+          const uint64_t a_desc = make_smem_desc(abase);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
               umma_bf16(tmem_base + mt * BN, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (kb | k) != 0);
-            umma_commit(bar_empty + 8 * slot);  // A slot free once these MMAs retire
+            if (mt < NCP) umma_commit(bar_cpempty + 8 * (gslot * kCpTiles + mt));  // activation slot free once read
             if (mt == NUM_MT - 1) {
-              umma_commit(bar_empty + 8 * slot_b);          // W slot free after the last row tile used it
+              umma_commit(bar_empty + 8 * stage);            // W (+ last activation) stage free
               if (kb == num_kb - 1) umma_commit(bar_tfull);  // strip accumulators complete
             }
           }
           __syncwarp();
-          if (++slot == kNumSlots) { slot = 0; phase ^= 1; }
         }
+        if (++stage == kTmaStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -369,16 +399,17 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       } else {
         if (MODE == MODE_FUSED || MODE == MODE_COLSUM) {
-          // ---- pass 1: p, A, Q and the column sums ----------------------------------------
-          float colsum[BN];
+          // ---- pass 1: p, A, Q and the column sums (32 columns at a time over all row tiles, so that
+          //      the running column sums stay in 32 registers) ------------------------------------
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            float colsum[32];
 #pragma unroll
-          for (int i = 0; i < BN; ++i) colsum[i] = 0.f;
+            for (int i = 0; i < 32; ++i) colsum[i] = 0.f;
 #pragma unroll
-          for (int mt = 0; mt < NUM_MT; ++mt) {
-            const bool ok = row0 + mt * BM + tid < p.n_vis;
-            const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
-#pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int mt = 0; mt < NUM_MT; ++mt) {
+              const bool ok = row0 + mt * BM + tid < p.n_vis;
+              const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
               float v[32];
               tmem_ld32(lane_addr + mt * BN + c * 32, v);
               if (ok) {
@@ -389,27 +420,27 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                   float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
                   float dv = pr - inv_v;
                   if (col0 + c * 32 + i >= p.vocab) pr = dv = 0.f;  // padded vocab columns of the last strip
-                  colsum[c * 32 + i] += pr;
+                  colsum[i] += pr;
                   acc_a[mt] = fmaf(pr, __logf(pr + kEps), acc_a[mt]);
                   acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
                 }
               }
+              if (MODE == MODE_COLSUM && c == BN / 32 - 1) {  // no second pass over TMEM in this mode
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * mt);
+              }
             }
-            if (MODE == MODE_COLSUM) {  // no second pass over TMEM in this mode
-              tc_fence_before();
-              mbar_arrive(bar_tempty + 8 * mt);
-            }
-          }
-          // ---- column sums over the rows held by this CTA: warp butterfly, then 4 smem rows ----
+            // column sums over the rows held by this CTA: warp butterfly, then 4 smem rows
 #pragma unroll
-          for (int i = 0; i < BN; ++i) {
-            float s = colsum[i];
-            s += __shfl_xor_sync(0xffffffffu, s, 16);
-            s += __shfl_xor_sync(0xffffffffu, s, 8);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (lane == (i & 31)) s_col[warp * BN + i] = s;
+            for (int i = 0; i < 32; ++i) {
+              float s = colsum[i];
+              s += __shfl_xor_sync(0xffffffffu, s, 16);
+              s += __shfl_xor_sync(0xffffffffu, s, 8);
+              s += __shfl_xor_sync(0xffffffffu, s, 4);
+              s += __shfl_xor_sync(0xffffffffu, s, 2);
+              s += __shfl_xor_sync(0xffffffffu, s, 1);
+              if (lane == i) s_col[warp * BN + c * 32 + i] = s;
+            }
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
           if (tid < BN) {
@@ -605,7 +636,8 @@ static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   return L;
 }
 
-constexpr size_t kUncSmem = 1024 + (size_t)kNumSlots * kSlotBytes + (2 * kNumSlots + 1 + kMaxMT) * 8 + 16 + 5 * BN * sizeof(float);
+constexpr size_t kUncSmem = 1024 + (size_t)kCpSlots * kSlotBytes + (size_t)kTmaStages * kTmaStageBytes + kNumBars * 8 + 16 +
+                            5 * BN * sizeof(float);
 
 template <int NUM_MT, int MODE, int KT>
 static int launch_unc(const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, cudaStream_t st) {
@@ -689,6 +721,7 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
   UncParams p{};
   p.n_images = n_images; p.n_vis = n_vis; p.d = d; p.vocab = vocab; p.topk = topk; p.round_bf16 = round_logits_bf16;
   p.n_strips = L.n_strips; p.parts = L.parts; p.n_chunks = L.n_chunks;
+  p.h_vis = static_cast<const __nv_bfloat16*>(h_vis);
   p.colpart = reinterpret_cast<float*>(ws + L.off_colpart);
   p.logpavg = reinterpret_cast<float*>(ws + L.off_logpavg);
   p.part_stats = reinterpret_cast<float*>(ws + L.off_stats);

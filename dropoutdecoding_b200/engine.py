@@ -22,6 +22,7 @@ Llama decoder so that the CPU oracle's 'bf16-faithful' mode is comparable token 
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -145,7 +146,8 @@ class DropoutDecodeEngine:
     def __init__(self, weights: DecoderWeights, batch: int, n_vis: int, max_seq: int,
                  probs: Sequence[float] = (0.3, 0.5, 0.7), mode: str = "cumulative", keep_relevant: bool = True,
                  topk: int = 5, aggregate: str = "vote", seed: int = 24, max_steps: int = 1024,
-                 round_logits: bool = True, est_seq: Optional[int] = None, vote_on: str = "logits"):
+                 round_logits: bool = True, est_seq: Optional[int] = None, vote_on: str = "logits",
+                 seq_base: int = 0):
         cfg = weights.cfg
         if cfg.d_model % 256 or cfg.d_ff % 256:
             raise ops.DropDecError("engine needs d_model % 256 == 0 and d_ff % 256 == 0")
@@ -155,6 +157,8 @@ class DropoutDecodeEngine:
         self.B, self.K, self.n_vis, self.S_max = batch, len(probs), n_vis, max_seq
         self.probs, self.mode, self.keep_relevant = [float(p) for p in probs], mode, keep_relevant
         self.topk, self.aggregate, self.seed, self.round_logits = topk, aggregate, seed, round_logits
+        self.fuse_norm = os.environ.get("DD_FUSE_NORM", "0") == "1"
+        self.seq_base = int(seq_base)   # global index of sequence 0 (batch sharded over GPUs)
         self.vote_on = vote_on          # "hidden": InstructBLIP votes on the argmax of the final hidden state
         self.Vp = weights.vocab_padded
         self.dev = weights.embed.device
@@ -258,30 +262,44 @@ class DropoutDecodeEngine:
         return pb.logits
 
     def _forward_fused(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool) -> torch.Tensor:
-        """<= 32 rows: 6 launches per layer.  Both RMSNorms ride in the prologue of the GEMM that consumes
-        them and RoPE + member staging in the epilogue of the QKV projection (dd_decoder_linear)."""
+        """<= 32 rows: RoPE + member staging ride in the epilogue of the QKV projection (dd_decoder_linear,
+        DD_EPI_ROPE) -- 8 launches per layer.  With fuse_norm the two RMSNorms also move into the prologue of
+        the GEMM that consumes them (6 launches per layer); measured slower on B200 because every one of the
+        ~1400 CTAs of a GEMM then re-normalises the same rows, so it is off by default (DD_FUSE_NORM=1)."""
         cfg, B, M = self.cfg, self.B, pb.M
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         rows = B * M
         x, x2 = pb.x, pb.x2
+        fuse = self.fuse_norm
         for l, lw in enumerate(self.w.layers):
-            ops.decoder_linear(x, lw["wqkv"], ops.EPI_ROPE, norm_w=lw["ln1"], eps=cfg.rms_eps,
-                               rope=dict(cos=self.cos, sin=self.sin, seq_lens=self.seq_lens, members=M, H=H, H_kv=Hkv,
-                                         D=D, q_out=pb.q, k_new=pb.k_new[l], v_new=pb.v_new[l]))
+            rope = dict(cos=self.cos, sin=self.sin, seq_lens=self.seq_lens, members=M, H=H, H_kv=Hkv, D=D, q_out=pb.q,
+                        k_new=pb.k_new[l], v_new=pb.v_new[l])
+            if fuse:
+                ops.decoder_linear(x, lw["wqkv"], ops.EPI_ROPE, norm_w=lw["ln1"], eps=cfg.rms_eps, rope=rope)
+            else:
+                ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pb.xn)
+                ops.decoder_linear(pb.xn, lw["wqkv"], ops.EPI_ROPE, rope=rope)
             ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
                                  self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws)
             ops.decoder_linear(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
-            ops.decoder_linear(x2, lw["wgu"], ops.EPI_SWIGLU, norm_w=lw["ln2"], eps=cfg.rms_eps, out=pb.act)
+            if fuse:
+                ops.decoder_linear(x2, lw["wgu"], ops.EPI_SWIGLU, norm_w=lw["ln2"], eps=cfg.rms_eps, out=pb.act)
+            else:
+                ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pb.xn)
+                ops.decoder_linear(pb.xn, lw["wgu"], ops.EPI_SWIGLU, out=pb.act)
             ops.decoder_linear(pb.act, lw["wd"], ops.EPI_RESIDUAL, residual=x2, out=x)
-            self.launches_per_step += 6
+            self.launches_per_step += 6 if fuse else 8
         self.launches_per_step += 1         # embed gather
-        if head:
+        if head and fuse:
             ops.decoder_linear(x, self.w.lm_head_padded, ops.EPI_F32, norm_w=self.w.norm, eps=cfg.rms_eps,
                                out=pb.logits.view(rows, self.Vp))
             self.launches_per_step += 1
         else:
-            ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pb.xn)     # InstructBLIP votes on the final-norm hidden state
+            ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pb.xn)     # (InstructBLIP votes on this final-norm hidden state)
             self.launches_per_step += 1
+            if head:
+                ops.decoder_linear(pb.xn, self.w.lm_head_padded, ops.EPI_F32, out=pb.logits.view(rows, self.Vp))
+                self.launches_per_step += 1
         return pb.logits
 
     # ------------------------------------------------------------------------------------
@@ -298,7 +316,7 @@ class DropoutDecodeEngine:
             u = self._u_step
         ops.sample_masks(self.epi, self.topk_ids, self.y_init, self.probs, mode=self.mode,      # :342-346
                          keep_relevant=self.keep_relevant, uniforms=u, seed=self.seed, offset=0,
-                         step=self.step_ctr, out=self.bitmask, n_masked=self.n_masked)
+                         step=self.step_ctr, out=self.bitmask, n_masked=self.n_masked, seq_base=self.seq_base)
         if self.vote_on == "logits":
             logits_b = self._forward(self.pb, self.bitmask)                        # :350-359
             ops.aggregate(logits_b, self.aggregate, member_ids=self.member_ids, winner=self.winner,   # :361

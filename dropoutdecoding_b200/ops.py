@@ -72,8 +72,9 @@ def sample_masks(epi: torch.Tensor, topk_ids: Optional[torch.Tensor], y_init: Op
                  probs: Sequence[float], mode: str = "cumulative", keep_relevant: bool = True,
                  uniforms: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
                  step: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                 n_masked: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """epi fp32 [B, n_vis] -> (bitmask uint32-as-int32 [B, K, words], n_masked int32 [B, K])."""
+                 n_masked: Optional[torch.Tensor] = None, seq_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """epi fp32 [B, n_vis] -> (bitmask uint32-as-int32 [B, K, words], n_masked int32 [B, K]).
+    seq_base: global index of row 0 (keys the Philox stream, so sharded batches draw the same numbers)."""
     L = _lib.load()
     _need(epi, torch.float32, "epi")
     B, n_vis = epi.shape
@@ -98,7 +99,7 @@ def sample_masks(epi: torch.Tensor, topk_ids: Optional[torch.Tensor], y_init: Op
     probs_c = (C.c_double * K)(*[float(p) for p in probs])
     check(L.dd_sample_masks(_ptr(epi), _ptr(topk_ids) if keep_relevant else None, topk,
                             _ptr(y_init) if keep_relevant else None, probs_c, K, _ptr(uniforms), seed, offset,
-                            _ptr(step), MASK_MODES[mode], int(keep_relevant), B, n_vis, _ptr(out), out.shape[-1],
+                            _ptr(step), MASK_MODES[mode], int(keep_relevant), B, n_vis, int(seq_base), _ptr(out), out.shape[-1],
                             _ptr(n_masked), _stream()), "dd_sample_masks")
     return out, n_masked
 

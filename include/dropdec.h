@@ -93,14 +93,15 @@ int dd_uncertainty_project(const void* h_vis /* bf16 [n_images, n_vis, d] */,
  *   relevant   = { i : y_init[b] in topk_ids[b,i,:] }   (skipped when keep_relevant == 0)
  * u comes from `uniforms` when it is non-NULL (parity mode: the caller supplies the same
  * numbers the reference's torch.rand_like would draw), otherwise from Philox4x32-10 keyed
- * by (seed, offset0 + *step * K, sequence, member, token).
+ * by (seed, offset0 + *step * K, seq_base + sequence, member, token): seq_base is the global index of this
+ * call's first sequence, so a batch sharded over several GPUs draws the same numbers as on one.
  * n_masked[b,m] = popcount(bits_m)   (the reference's masked_numbers, models/llava.py:661).
  * ------------------------------------------------------------------------------------------ */
 int dd_sample_masks(const float* epi /* [B, n_vis] */, const int32_t* topk_ids /* [B, n_vis, topk] */,
                     int topk, const int32_t* y_init /* [B] */, const double* probs_host /* [K] */,
                     int K, const float* uniforms /* [B, K, n_vis] or NULL */, uint64_t seed,
                     uint64_t offset0, const int32_t* step /* device scalar or NULL */, int mode,
-                    int keep_relevant, int B, int n_vis, uint32_t* bitmask /* [B, K, mask_words] */,
+                    int keep_relevant, int B, int n_vis, int seq_base, uint32_t* bitmask /* [B, K, mask_words] */,
                     int mask_words, int32_t* n_masked /* [B, K] */, dd_stream_t stream);
 
 /* Test hook: out[i] = first uniform of Philox subsequence i at `offset` -- the layout

@@ -31,9 +31,9 @@ def test_argument_validation_never_touches_the_gpu(lib):
     """Bad arguments return DD_ERR_INVALID_ARG with a message before any CUDA call."""
     probs = (C.c_double * 3)(0.3, 0.5, 0.7)
     one = C.c_void_p(16)     # never dereferenced
-    rc = lib.dd_sample_masks(one, one, 5, one, probs, 0, None, 0, 0, None, 0, 1, 1, 576, one, 18, one, None)
+    rc = lib.dd_sample_masks(one, one, 5, one, probs, 0, None, 0, 0, None, 0, 1, 1, 576, 0, one, 18, one, None)
     assert rc == -1 and b"K=0" in lib.dd_last_error()
-    rc = lib.dd_sample_masks(one, one, 5, one, probs, 3, None, 0, 0, None, 0, 1, 1, 576, one, 4, one, None)
+    rc = lib.dd_sample_masks(one, one, 5, one, probs, 3, None, 0, 0, None, 0, 1, 1, 576, 0, one, 4, one, None)
     assert rc == -1 and b"mask_words" in lib.dd_last_error()
     rc = lib.dd_decode_attention(one, one, one, one, one, one, one, None, 1, 3, 32, 32, 96, 100, 0, 0, 0.1, 1, one,
                                  one, 1 << 30, None)

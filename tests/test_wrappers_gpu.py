@@ -143,6 +143,9 @@ def test_instructblip_wrapper(cuda):
     with torch.device(cuda):
         m = CustomInstructBlipForConditionalGeneration(cfg)
     m = m.to(cuda, torch.bfloat16).eval()
+    # HF initialises the Q-Former query tokens to zero: 32 identical visual tokens -> identical uncertainties
+    # -> the quantile threshold drops everything.  Give the random-init model distinct queries.
+    m.query_tokens.data.normal_(std=1.0, generator=torch.Generator(device=cuda).manual_seed(3))
     assert isinstance(m.language_model, CustomLlamaForCausalLM)
     g = torch.Generator().manual_seed(4)
     px = torch.randn(2, 3, 56, 56, generator=g)

@@ -159,6 +159,97 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap, int mode, int mma_iters, 
   }
 }
 
+// ---- mode 4: cluster multicast.  Each CTA of a cluster of C issues 1/C of every [128 x 64] box (a
+// [128/C x 64] slice) with .multicast::cluster to all C CTAs; a slot is rewritten only after all C CTAs
+// released it (remote mbarrier arrives), i.e. the real producer/consumer protocol of a multicast GEMM.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_bar), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(128, 1)
+probe_mc_kernel(const __grid_constant__ CUtensorMap tmap_slice, int tma_iters, int rows_total, ProbeOut* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bars[2 * kTmaSlots];
+  const int warp = threadIdx.x >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const uint32_t ring = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kTmaSlots;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTmaSlots; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, C); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const int nbox_k = 64, row_tiles = rows_total / 128;
+  if (warp == 0) {  // producer
+    const long long t0 = clock64();
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < tma_iters; ++it) {
+      mbar_wait(empty0 + 8 * slot, phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(full0 + 8 * slot, kSlotBytes);
+        tma_load_2d_mc(ring + slot * kSlotBytes + rank * (kSlotBytes / C), &tmap_slice, full0 + 8 * slot,
+                       (it % nbox_k) * 64, ((it / nbox_k) % row_tiles) * 128 + rank * (128 / C), (uint16_t)((1u << C) - 1));
+      }
+      __syncwarp();
+      if (++slot == kTmaSlots) { slot = 0; phase ^= 1; }
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x].tma_cycles = (unsigned long long)(t1 - t0);
+  } else if (warp == 1) {  // consumer: wait for the box, release the slot on every CTA of the cluster
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < tma_iters; ++it) {
+      mbar_wait(full0 + 8 * slot, phase);
+      if ((threadIdx.x & 31) < C) mbar_arrive_remote(empty0 + 8 * slot, threadIdx.x & 31);
+      __syncwarp();
+      if (++slot == kTmaSlots) { slot = 0; phase ^= 1; }
+    }
+  }
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- mode 5: the LSU path.  NT threads stream the same [128 x 64] boxes with cp.async (16 B per thread per
+// request, manual XOR swizzle like SWIZZLE_128B), 4 groups in flight.
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) probe_cpasync_kernel(const __nv_bfloat16* a, int d, int iters, int rows_total,
+                                                              ProbeOut* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t ring = smem_u32(smem);
+  const int nbox_k = d / 64, row_tiles = rows_total / 128;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    const int kb = it % nbox_k, rt = (it / nbox_k) % row_tiles;
+    const uint32_t dst = ring + (it % kTmaSlots) * kSlotBytes;
+#pragma unroll
+    for (int i = 0; i < 1024 / NT; ++i) {
+      const int idx = i * NT + threadIdx.x, row = idx >> 3, c = idx & 7;
+      const __nv_bfloat16* src = a + (size_t)(rt * 128 + row) * d + kb * 64 + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + row * 128 + ((c ^ (row & 7)) << 4)), "l"(src));
+    }
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group %0;" ::"n"(kTmaSlots - 2));
+  }
+  asm volatile("cp.async.wait_group 0;");
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x].tma_cycles = (unsigned long long)(t1 - t0);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -193,6 +284,79 @@ static void run(const CUtensorMap& tm, int mode, int sms, int rows_total, ProbeO
          "\"ideal_cycles_per_mma\": %.1f, \"mma_tflops_if_alone\": %.1f, \"tma_bytes_per_cycle_per_sm\": %.1f, "
          "\"tma_chip_TBps\": %.2f}\n",
          label, N, mode, sms, ms, cyc_per_mma, N / 2.0, tflops, bpc, tbs);
+  fflush(stdout);
+}
+
+template <int C>
+static void run_mc(EncodeTiledFn encode, void* a, int d, int rows_total, int sms, ProbeOut* d_out) {
+  CUtensorMap tm;
+  const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows_total};
+  const cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+  const cuuint32_t box[2] = {64, 128 / C}, es[2] = {1, 1};
+  if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+      CUDA_SUCCESS) {
+    fprintf(stderr, "encode (mc) failed\n");
+    return;
+  }
+  const int tma_iters = 4096;
+  const size_t smem = 1024 + kTmaSlots * kSlotBytes;
+  CK(cudaFuncSetAttribute(probe_mc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = sms / C * C;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int max_clusters = 0;
+  cudaOccupancyMaxActiveClusters(&max_clusters, probe_mc_kernel<C>, &cfg);
+  if (max_clusters * C < grid) { grid = max_clusters * C; cfg.gridDim = dim3(grid); }
+  CK(cudaMemset(d_out, 0, sizeof(ProbeOut) * 256));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaLaunchKernelEx(&cfg, probe_mc_kernel<C>, tm, tma_iters, rows_total, d_out));
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  CK(cudaLaunchKernelEx(&cfg, probe_mc_kernel<C>, tm, tma_iters, rows_total, d_out));
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  std::vector<ProbeOut> h(grid);
+  CK(cudaMemcpy(h.data(), d_out, sizeof(ProbeOut) * grid, cudaMemcpyDeviceToHost));
+  double tc = 0;
+  for (auto& o : h) tc += o.tma_cycles;
+  tc /= grid;
+  printf("{\"probe\": \"tma_multicast_shared\", \"cluster\": %d, \"ctas\": %d, \"max_active_clusters\": %d, \"ms\": %.4f, "
+         "\"landed_bytes_per_cycle_per_sm\": %.1f, \"issued_bytes_per_cycle_per_sm\": %.1f, \"landed_chip_TBps\": %.2f}\n",
+         C, grid, max_clusters, ms, (double)tma_iters * kSlotBytes / tc, (double)tma_iters * kSlotBytes / C / tc,
+         (double)tma_iters * kSlotBytes * grid / (ms * 1e-3) / 1e12);
+  fflush(stdout);
+}
+
+template <int NT>
+static void run_cpasync(const __nv_bfloat16* a, int d, int rows_total, int sms, ProbeOut* d_out) {
+  const int iters = 4096;
+  const size_t smem = 1024 + kTmaSlots * kSlotBytes;
+  CK(cudaFuncSetAttribute(probe_cpasync_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  probe_cpasync_kernel<NT><<<sms, NT, smem>>>(a, d, iters, rows_total, d_out);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  probe_cpasync_kernel<NT><<<sms, NT, smem>>>(a, d, iters, rows_total, d_out);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  std::vector<ProbeOut> h(sms);
+  CK(cudaMemcpy(h.data(), d_out, sizeof(ProbeOut) * sms, cudaMemcpyDeviceToHost));
+  double tc = 0;
+  for (auto& o : h) tc += o.tma_cycles;
+  tc /= sms;
+  printf("{\"probe\": \"cp_async_shared_5MB\", \"threads\": %d, \"ctas\": %d, \"ms\": %.4f, \"bytes_per_cycle_per_sm\": %.1f, "
+         "\"chip_TBps\": %.2f}\n", NT, sms, ms, (double)iters * kSlotBytes / tc, (double)iters * kSlotBytes * sms / (ms * 1e-3) / 1e12);
   fflush(stdout);
 }
 
@@ -234,6 +398,13 @@ int main() {
       run<96>(tm, 1, 16, rows_total, d_out, "tma_shared_5MB_16cta");
       run<96>(tm, 2, sms, rows_total, d_out, "mma+tma_shared");
       run<256>(tm, 2, sms, rows_total, d_out, "mma+tma_shared");
+      run_cpasync<128>(a, d, rows_total, sms, d_out);
+      run_cpasync<256>(a, d, rows_total, sms, d_out);
+      run_cpasync<512>(a, d, rows_total, sms, d_out);
+      run_mc<1>(encode, a, d, rows_total, sms, d_out);
+      run_mc<2>(encode, a, d, rows_total, sms, d_out);
+      run_mc<4>(encode, a, d, rows_total, sms, d_out);
+      run_mc<8>(encode, a, d, rows_total, sms, d_out);
     } else {
       run<96>(tm, 3, sms, rows_total, d_out, "tma_distinct_hbm");
     }
