@@ -201,6 +201,7 @@ def run_ours(args):
         # ---- roofline of the dominant kernel, measured live: one eager ensemble step with CUDA
         #      events around every dd_skinny_gemm launch on the launching stream
         roof = profile_dominant_kernel(eng, hbm, peak_src)
+        stages = profile_stages(eng, vis_hidden, S0, hbm, tf)
 
     if dist is not None:
         t = torch.tensor([dt, dt_e2e], device=dev, dtype=torch.float64)
@@ -224,7 +225,7 @@ def run_ours(args):
         "gpu_launches": int(args.steps * ((T - 1) * launches_per_ens_step + 6)),
         "prefill_ms": round(prefill_ms, 2),
         "ms_per_token": round(dt / args.steps / T * 1e3, 4),
-        "clocks": clk, "roofline": roof,
+        "clocks": clk, "roofline": roof, "stage_rooflines": stages,
         "token_checksum": int(tokens_check.long().sum().item()),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -236,23 +237,26 @@ def run_ours(args):
 
 
 def profile_dominant_kernel(eng, hbm, peak_src):
-    """Time every dd_skinny_gemm launch of one eager ensemble step with CUDA events on torch's
-    current stream (the stream the C ABI launches on)."""
+    """Time every weight-streaming GEMM launch (dd::skinny_gemm_kernel, through dd_skinny_gemm /
+    dd_decoder_linear) of one eager ensemble step with CUDA events on torch's current stream (the stream
+    the C ABI launches on)."""
     from dropoutdecoding_b200 import ops
     recs = []
-    orig = ops.skinny_gemm
+    orig_sg, orig_dl = ops.skinny_gemm, ops.decoder_linear
 
-    def timed(x, w, epilogue=ops.EPI_NONE, residual=None, out=None):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = orig(x, w, epilogue, residual=residual, out=out)
-        b.record()
-        recs.append((a, b, w.numel() * w.element_size()))
-        return r
+    def timed(orig):
+        def f(x, w, *args, **kw):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig(x, w, *args, **kw)
+            b.record()
+            recs.append((a, b, w.numel() * w.element_size()))
+            return r
+        return f
 
     t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     snap = eng._snapshot()
-    ops.skinny_gemm = timed
+    ops.skinny_gemm, ops.decoder_linear = timed(orig_sg), timed(orig_dl)
     try:
         eng.step()                      # warm
         recs.clear()
@@ -262,19 +266,56 @@ def profile_dominant_kernel(eng, hbm, peak_src):
         t_all1.record()
         torch.cuda.synchronize()
     finally:
-        ops.skinny_gemm = orig
+        ops.skinny_gemm, ops.decoder_linear = orig_sg, orig_dl
         eng._restore(snap)
     if not recs:
         return {"bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None, "traffic": None,
-                "note": "no dd_skinny_gemm launches (rows > 32: library GEMMs)"}
+                "note": "no dd::skinny_gemm_kernel launches (rows > 32: library GEMMs)"}
     secs = sum(a.elapsed_time(b) for a, b, _ in recs) * 1e-3
     byts = sum(n for _, _, n in recs)
     ach = byts / secs / 1e9
     return {"bound": "hbm", "kernel": "dd::skinny_gemm_kernel (all weight GEMMs of one ensemble step)",
-            "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None,
+            "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4),
+            "traffic": "ncu dram__bytes_read+write per launch = 1.00-1.04 x the weight bytes (profiles/r01/ncu_full_summary.json)",
             "peak_source": peak_src, "launches": len(recs), "algorithmic_bytes_per_step": int(byts),
             "avg_launch_us": round(secs / len(recs) * 1e6, 2),
             "share_of_eager_step": round(secs / (t_all0.elapsed_time(t_all1) * 1e-3), 3)}
+
+
+def profile_stages(eng, vis_hidden, S0, hbm, tf):
+    """The other two north_star kernels at this workload's shapes, CUDA events, L2 flushed before each:
+    the tcgen05 uncertainty stage (tensor roofline, FLOPs counted once) and one decode-attention call
+    (HBM roofline, K and V of every (sequence, kv head) read once)."""
+    from dropoutdecoding_b200 import ops
+    cfg, B = eng.cfg, eng.B
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.dev)
+
+    def timeit(fn, iters=5):
+        fn(); torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b) * 1e-3)
+        return best
+
+    t_unc = timeit(lambda: eng.uncertainty_stage(vis_hidden))
+    flops = 2.0 * B * vis_hidden.shape[1] * cfg.d_model * cfg.vocab
+    pb = eng.pb
+    eng.seq_lens.fill_(S0)
+    t_att = timeit(lambda: ops.decode_attention(pb.q, pb.k_new[0], pb.v_new[0], eng.k_cache[0], eng.v_cache[0],
+                                                eng.seq_lens, eng.vis_start, eng.bitmask, eng.n_vis, eng.scale,
+                                                pb.splits, pb.attn, pb.ws))
+    kv = 2 * S0 * cfg.n_kv_heads * cfg.head_dim * 2 * B
+    return {"uncertainty_stage": {"bound": "tensor", "ms": round(t_unc * 1e3, 4), "achieved": round(flops / t_unc / 1e12, 1),
+                                  "peak": tf, "unit": "TFLOP/s", "frac": round(flops / t_unc / 1e12 / tf, 4),
+                                  "algorithmic_flops": flops},
+            "decode_attention_K3": {"bound": "hbm", "us": round(t_att * 1e6, 2), "achieved": round(kv / t_att / 1e9, 1),
+                                    "peak": hbm, "unit": "GB/s", "frac": round(kv / t_att / 1e9 / hbm, 4),
+                                    "algorithmic_bytes": kv,
+                                    "note": "latency-bound at this batch; the HBM-bound shape (B=64) is in profiles/"}}
 
 
 # ------------------------------------------------------------------------------------------------

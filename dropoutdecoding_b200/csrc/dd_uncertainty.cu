@@ -31,6 +31,8 @@
 // Algorithmic FLOPs = 2*n_vis*d*V per image, counted once although two sweeps run.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "dd_common.cuh"
 
 namespace dd {
@@ -283,39 +285,56 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 5) {
     // =========================== MMA issuer (warp-converged, one elected lane issues) ==========
-    int stage = 0;
-    uint32_t phase = 0, it = 0, g = 0;
-    for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
-      for (int kb = 0; kb < num_kb; ++kb, ++g) {
-        const uint32_t gslot = g & 1, gphase = (g >> 1) & 1;
-        mbar_wait(bar_full + 8 * stage, phase);
-        mbar_wait(bar_cpfull + 8 * gslot, gphase);
-        fence_proxy_async();  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
-        tc_fence_after();
+    // The issuing thread must stay ahead of a tensor pipe that retires one M128 x N96 x K16 MMA every ~57
+    // cycles, so the body of a k-block is instantiated for each (cp.async slot pair, TMA stage) combination:
+    // every shared-memory descriptor is then "ring base + compile-time constant", one elected region issues
+    // all NUM_MT x 4 MMAs of the k-block, and the per-k-block cost is two mbarrier waits and one proxy fence.
+    auto issue_group = [&](auto GS, auto ST, uint32_t gphase, uint32_t tphase, bool first_kb, bool last_kb,
+                           uint32_t tempty_parity) {
+      constexpr uint32_t gslot = decltype(GS)::value, stage = decltype(ST)::value;
+      mbar_wait(bar_full + 8 * stage, tphase);
+      mbar_wait(bar_cpfull + 8 * gslot, gphase);
+      fence_proxy_async();  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+      if (first_kb) {       // the epilogue must have drained the previous strip's accumulators
+#pragma unroll
+        for (int mt = 0; mt < NUM_MT; ++mt) mbar_wait(bar_tempty + 8 * mt, tempty_parity);
+      }
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t wbase = tma_ring + stage * kTmaStageBytes;
         const uint64_t b_desc = make_smem_desc(wbase);
+        const uint32_t acc = first_kb ? 0u : 1u;
 #pragma unroll
         for (int mt = 0; mt < NUM_MT; ++mt) {
-          // first k-block of a strip: the epilogue must have drained this row tile's accumulators
-          if (kb == 0) {
-            mbar_wait(bar_tempty + 8 * mt, (it & 1) ^ 1);
-            tc_fence_after();
-          }
           const uint32_t abase = mt < NCP ? cp_ring + (gslot * kCpTiles + mt) * kSlotBytes : wbase + kWBytes;
           const uint64_t a_desc = make_smem_desc(abase);
-          if (elect_one()) {
+          umma_bf16(tmem_base + mt * BN, a_desc, b_desc, kIdesc, acc);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
-              umma_bf16(tmem_base + mt * BN, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (kb | k) != 0);
-            if (mt < NCP) umma_commit(bar_cpempty + 8 * (gslot * kCpTiles + mt));  // activation slot free once read
-            if (mt == NUM_MT - 1) {
-              umma_commit(bar_empty + 8 * stage);            // W (+ last activation) stage free
-              if (kb == num_kb - 1) umma_commit(bar_tfull);  // strip accumulators complete
-            }
-          }
-          __syncwarp();
+          for (int k = 1; k < BK / UMMA_K; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+            umma_bf16(tmem_base + mt * BN, a_desc + 2 * k, b_desc + 2 * k, kIdesc, 1u);
+          if (mt < NCP) umma_commit(bar_cpempty + 8 * (gslot * kCpTiles + mt));  // activation slot free once read
         }
-        if (++stage == kTmaStages) { stage = 0; phase ^= 1; }
+        umma_commit(bar_empty + 8 * stage);     // W (+ last activation) stage free
+        if (last_kb) umma_commit(bar_tfull);    // strip accumulators complete
+      }
+      __syncwarp();
+    };
+    using std::integral_constant;
+    uint32_t it = 0, g = 0, g6 = 0, g3 = 0, tphase = 0;  // g6 = g % 6, g3 = g % 3
+    for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const uint32_t gphase = (g >> 1) & 1, tp = (it & 1) ^ 1;
+        const bool f = kb == 0, l = kb == num_kb - 1;
+        switch (g6) {
+          case 0: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 0>{}, gphase, tphase, f, l, tp); break;
+          case 1: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 1>{}, gphase, tphase, f, l, tp); break;
+          case 2: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 2>{}, gphase, tphase, f, l, tp); break;
+          case 3: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 0>{}, gphase, tphase, f, l, tp); break;
+          case 4: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 1>{}, gphase, tphase, f, l, tp); break;
+          default: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 2>{}, gphase, tphase, f, l, tp); break;
+        }
+        if (++g6 == 6) g6 = 0;
+        if (++g3 == 3) { g3 = 0; tphase ^= 1; }
       }
     }
   } else {

@@ -83,16 +83,16 @@ struct ProbeOut {
 template <int N>
 __global__ void __launch_bounds__(192, 1)
 probe_kernel(const __grid_constant__ CUtensorMap tmap, int mode, int mma_iters, int tma_iters, int rows_total,
-             ProbeOut* out) {
+             ProbeOut* out, int commit_every, int n_acc) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bars[kTmaSlots + 1];
+  __shared__ uint64_t bars[kTmaSlots + 2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5;
   const uint32_t base = smem_u32(smem);
   const uint32_t bar0 = smem_u32(bars);
   if (threadIdx.x == 0) {
-    for (int i = 0; i <= kTmaSlots; ++i) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i <= kTmaSlots + 1; ++i) mbar_init(bar0 + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -140,7 +140,9 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap, int mode, int mma_iters, 
       if (elect_one()) {
         for (int j = 0; j < 64; ++j) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + ((j & 1) * N), a_desc + 2 * k, b_desc + 2 * k, idesc, 1);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + ((j % n_acc) * N), a_desc + 2 * k, b_desc + 2 * k, idesc, 1);
+          // a commit to a barrier nobody waits on: does the arrive-on-completion stall the tensor pipe?
+          if (commit_every && (j % commit_every) == commit_every - 1) umma_commit(bar_done + 8);
         }
         umma_commit(bar_done);
       }
@@ -176,51 +178,46 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 
+constexpr int kMcSlots = 12;
 template <int C>
 __global__ void __launch_bounds__(128, 1)
 probe_mc_kernel(const __grid_constant__ CUtensorMap tmap_slice, int tma_iters, int rows_total, ProbeOut* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bars[2 * kTmaSlots];
-  const int warp = threadIdx.x >> 5;
+  __shared__ uint64_t bars[kMcSlots];
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const uint32_t ring = smem_u32(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kTmaSlots;
+  const uint32_t full0 = smem_u32(bars);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kTmaSlots; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, C); }
+    for (int i = 0; i < kMcSlots; ++i) mbar_init(full0 + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   const int nbox_k = 64, row_tiles = rows_total / 128;
-  if (warp == 0) {  // producer
-    const long long t0 = clock64();
-    int slot = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < tma_iters; ++it) {
-      mbar_wait(empty0 + 8 * slot, phase ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(full0 + 8 * slot, kSlotBytes);
-        tma_load_2d_mc(ring + slot * kSlotBytes + rank * (kSlotBytes / C), &tmap_slice, full0 + 8 * slot,
-                       (it % nbox_k) * 64, ((it / nbox_k) % row_tiles) * 128 + rank * (128 / C), (uint16_t)((1u << C) - 1));
+  const long long t0 = clock64();
+  uint32_t phase = 0;
+  // rounds of kMcSlots boxes: every CTA issues its 1/C slice of each box (multicast to the whole cluster),
+  // waits until all kMcSlots boxes have fully landed in ITS smem, then the cluster synchronises (so that
+  // no CTA re-arms a slot while a peer's slice of the previous round is still in flight)
+  for (int it0 = 0; it0 < tma_iters; it0 += kMcSlots) {
+    if (threadIdx.x < 32) {
+      for (int sl = 0; sl < kMcSlots; ++sl) {
+        const int it = it0 + sl;
+        if (elect_one()) {
+          mbar_expect_tx(full0 + 8 * sl, kSlotBytes);
+          tma_load_2d_mc(ring + sl * kSlotBytes + rank * (kSlotBytes / C), &tmap_slice, full0 + 8 * sl, (it % nbox_k) * 64,
+                         ((it / nbox_k) % row_tiles) * 128 + rank * (128 / C), (uint16_t)((1u << C) - 1));
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      if (++slot == kTmaSlots) { slot = 0; phase ^= 1; }
+      for (int sl = 0; sl < kMcSlots; ++sl) mbar_wait(full0 + 8 * sl, phase);
     }
-    const long long t1 = clock64();
-    if (threadIdx.x == 0) out[blockIdx.x].tma_cycles = (unsigned long long)(t1 - t0);
-  } else if (warp == 1) {  // consumer: wait for the box, release the slot on every CTA of the cluster
-    int slot = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < tma_iters; ++it) {
-      mbar_wait(full0 + 8 * slot, phase);
-      if ((threadIdx.x & 31) < C) mbar_arrive_remote(empty0 + 8 * slot, threadIdx.x & 31);
-      __syncwarp();
-      if (++slot == kTmaSlots) { slot = 0; phase ^= 1; }
-    }
+    phase ^= 1;
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
-  __syncthreads();
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x].tma_cycles = (unsigned long long)(t1 - t0);
 }
 
 // ---- mode 5: the LSU path.  NT threads stream the same [128 x 64] boxes with cp.async (16 B per thread per
@@ -255,7 +252,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 template <int N>
-static void run(const CUtensorMap& tm, int mode, int sms, int rows_total, ProbeOut* d_out, const char* label) {
+static void run(const CUtensorMap& tm, int mode, int sms, int rows_total, ProbeOut* d_out, const char* label,
+                int commit_every = 0, int n_acc = 2) {
   const int mma_iters = 4096, tma_iters = 4096;
   const size_t smem = 1024 + (3 + kTmaSlots) * kSlotBytes;
   CK(cudaFuncSetAttribute(probe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -263,10 +261,10 @@ static void run(const CUtensorMap& tm, int mode, int sms, int rows_total, ProbeO
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  probe_kernel<N><<<sms, 192, smem>>>(tm, mode, mma_iters, tma_iters, rows_total, d_out);  // warm
+  probe_kernel<N><<<sms, 192, smem>>>(tm, mode, mma_iters, tma_iters, rows_total, d_out, commit_every, n_acc);  // warm
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  probe_kernel<N><<<sms, 192, smem>>>(tm, mode, mma_iters, tma_iters, rows_total, d_out);
+  probe_kernel<N><<<sms, 192, smem>>>(tm, mode, mma_iters, tma_iters, rows_total, d_out, commit_every, n_acc);
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms = 0;
@@ -280,10 +278,10 @@ static void run(const CUtensorMap& tm, int mode, int sms, int rows_total, ProbeO
   const double bpc = tc > 0 ? (double)tma_iters * kSlotBytes / tc : 0;
   const double tflops = mc > 0 ? 2.0 * 128 * N * 16 * mma_iters * 4.0 * sms / (ms * 1e-3) / 1e12 : 0;
   const double tbs = tc > 0 ? (double)tma_iters * kSlotBytes * sms / (ms * 1e-3) / 1e12 : 0;
-  printf("{\"probe\": \"%s\", \"N\": %d, \"mode\": %d, \"ctas\": %d, \"ms\": %.4f, \"cycles_per_mma\": %.1f, "
+  printf("{\"probe\": \"%s\", \"commit_every_4mma_groups\": %d, \"accumulators\": %d, \"N\": %d, \"mode\": %d, \"ctas\": %d, \"ms\": %.4f, \"cycles_per_mma\": %.1f, "
          "\"ideal_cycles_per_mma\": %.1f, \"mma_tflops_if_alone\": %.1f, \"tma_bytes_per_cycle_per_sm\": %.1f, "
          "\"tma_chip_TBps\": %.2f}\n",
-         label, N, mode, sms, ms, cyc_per_mma, N / 2.0, tflops, bpc, tbs);
+         label, commit_every, n_acc, N, mode, sms, ms, cyc_per_mma, N / 2.0, tflops, bpc, tbs);
   fflush(stdout);
 }
 
@@ -299,8 +297,8 @@ static void run_mc(EncodeTiledFn encode, void* a, int d, int rows_total, int sms
     fprintf(stderr, "encode (mc) failed\n");
     return;
   }
-  const int tma_iters = 4096;
-  const size_t smem = 1024 + kTmaSlots * kSlotBytes;
+  const int tma_iters = 4092;  // multiple of kMcSlots
+  const size_t smem = 1024 + kMcSlots * kSlotBytes;
   CK(cudaFuncSetAttribute(probe_mc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sms / C * C;
   cudaLaunchConfig_t cfg{};
@@ -393,6 +391,11 @@ int main() {
       run<192>(tm, 0, sms, rows_total, d_out, "mma_only");
       run<256>(tm, 0, sms, rows_total, d_out, "mma_only");
       run<96>(tm, 0, 1, rows_total, d_out, "mma_only_1cta");
+      run<96>(tm, 0, sms, rows_total, d_out, "mma_commit_each_tile", 1, 2);
+      run<96>(tm, 0, sms, rows_total, d_out, "mma_5_accumulators", 0, 5);
+      run<96>(tm, 0, sms, rows_total, d_out, "mma_commit_each_tile_5acc", 1, 5);
+      run<96>(tm, 0, sms, rows_total, d_out, "mma_commit_every_5_tiles_5acc", 5, 5);
+      run<256>(tm, 0, sms, rows_total, d_out, "mma_commit_each_tile", 1, 2);
       run<96>(tm, 1, sms, rows_total, d_out, "tma_shared_5MB");
       run<96>(tm, 1, 1, rows_total, d_out, "tma_shared_5MB_1cta");
       run<96>(tm, 1, 16, rows_total, d_out, "tma_shared_5MB_16cta");
