@@ -24,10 +24,15 @@
 //              thread-local; the column sums are a butterfly over the warp plus 4 smem rows.
 //
 // Two sweeps of the same pipeline (the row normaliser Z_i must be complete before p exists):
-//   STATS : per row running max / sum-exp and the top-k ids                     (sweep 1)
+//   STATS : per row running max / sum-exp, and the row's maximum inside every strip       (sweep 1)
 //   FUSED : p = exp(l - m)/Z;  A_i = sum p log(p+eps), Q_i = sum (p-1/V)^2, column sums ->
 //           log(p_avg+eps) -> C_i = sum p log(p_avg+eps)                        (sweep 2)
 //   finalize: alea = -A, epi = A - C, var = Q/(V-1).
+// Top-k ids without per-thread sorted lists in the hot loop: tau_i = the k-th largest of row i's per-strip
+// maxima is a lower bound of its k-th largest logit, so sweep 2 (which recomputes bit-identical logits)
+// only has to append the few elements >= tau_i to a per-row candidate list (one predictable compare per
+// element); the finalize kernel sorts the candidates (value descending, id ascending).  Without ties at
+// most 96*k elements can pass the threshold; the list holds 96*k + 64.
 // Algorithmic FLOPs = 2*n_vis*d*V per image, counted once although two sweeps run.
 #include <cuda.h>
 
@@ -161,13 +166,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ------------------------------------------------------------------------------------------
 struct UncParams {
   int n_images, n_vis, d, vocab, topk, round_bf16;
   int n_strips, parts;     // strips per image; CTAs (partials) per image
   float* part_stats;       // [img][parts][n_vis][2]      (m, z)
-  float* part_topv;        // [img][parts][n_vis][topk]
-  int32_t* part_topi;      // [img][parts][n_vis][topk]
+  float* strip_max;        // [img][n_strips][n_vis]      STATS output: row maximum inside each strip
+  const float* tau;        // [img][n_vis]                candidate threshold (FUSED / COLSUM input)
+  int32_t* cand_cnt;       // [img][n_vis]
+  float* cand_val;         // [img][n_vis][cap]
+  int32_t* cand_idx;       // [img][n_vis][cap]
+  int cap;
   const float* row_stats;  // [img][n_vis][2]             (m, 1/Z)  FUSED input
   float* part_acq;         // [img][parts][n_vis][3]      (A, Q, C) FUSED output
   const __nv_bfloat16* h_vis;  // [img][n_vis][d] (cp.async path of the activation tiles)
@@ -175,6 +195,34 @@ struct UncParams {
   float* colpart;          // [img][chunk][n_strips*BN]   column sums of p over one row chunk (COLSUM -> logpavg)
   float* logpavg;          // [img][n_strips*BN]          log(p_avg + eps)                    (CROSS input)
 };
+
+// Rare path of sweep 2 (whole warp, warp-uniform call): some row of this warp has a top-k candidate inside the
+// 32 columns at `taddr`.  Re-reads them from TMEM 8 at a time and appends every logit >= the row's threshold.
+struct CandSink {
+  int32_t* cnt;
+  float* val;
+  int32_t* idx;
+  int cap, vocab, round_bf16;
+};
+__device__ __noinline__ void append_candidates(const CandSink p, uint32_t taddr, float tau, int col_base, size_t r) {
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    float v[8];
+    tmem_ld8(taddr + j * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = p.round_bf16 ? bf16_round(v[i]) : v[i];
+      const int col = col_base + j * 8 + i;
+      if (col < p.vocab && x >= tau) {
+        const int slot = atomicAdd(&p.cnt[r], 1);
+        if (slot < p.cap) {
+          p.val[r * p.cap + slot] = x;
+          p.idx[r * p.cap + slot] = col;
+        }
+      }
+    }
+  }
+}
 
 // n_vis <= 640: STATS, FUSED.  Larger images (LLaVA-NeXT anyres, up to ~2.9k rows) do not fit the 512
 // TMEM columns, so the column mean needs its own sweep: STATS, COLSUM (p, A, Q, per-chunk column sums),
@@ -345,21 +393,20 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
     float st_m[NUM_MT], st_z[NUM_MT];          // STATS: running max, sum-exp | FUSED: m, 1/Z
     float acc_a[NUM_MT], acc_q[NUM_MT], acc_c[NUM_MT];
-    float topv[MODE == MODE_STATS ? NUM_MT : 1][KT];
-    int topi[MODE == MODE_STATS ? NUM_MT : 1][KT];
+    float st_tau[NUM_MT];                      // FUSED / COLSUM: top-k candidate threshold of the row
 #pragma unroll
     for (int mt = 0; mt < NUM_MT; ++mt) {
       const int row = row0 + mt * BM + tid;
       acc_a[mt] = acc_q[mt] = acc_c[mt] = 0.f;
+      st_tau[mt] = INFINITY;
       if (MODE == MODE_STATS) {
         st_m[mt] = -INFINITY;
         st_z[mt] = 0.f;
-#pragma unroll
-        for (int j = 0; j < KT; ++j) { topv[mt][j] = -INFINITY; topi[mt][j] = 0x7fffffff; }
       } else {
         const bool ok = row < p.n_vis;
         st_m[mt] = ok ? p.row_stats[((size_t)img * p.n_vis + row) * 2] : 0.f;
         st_z[mt] = ok ? p.row_stats[((size_t)img * p.n_vis + row) * 2 + 1] : 0.f;
+        if (ok && MODE != MODE_CROSS) st_tau[mt] = p.tau[(size_t)img * p.n_vis + row];
       }
     }
 
@@ -376,43 +423,35 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (MODE == MODE_STATS) {
 #pragma unroll
         for (int mt = 0; mt < NUM_MT; ++mt) {
-          const bool ok = row0 + mt * BM + tid < p.n_vis;
+          const int row = row0 + mt * BM + tid;
+          const bool ok = row < p.n_vis;
+          float smax = -INFINITY;  // this row's maximum inside the strip
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
             float v[32];
             tmem_ld32(lane_addr + mt * BN + c * 32, v);
             if (ok) {
-            const int cbase = col0 + c * 32;
-            float cmax = -INFINITY;
+              const int cbase = col0 + c * 32;
+              float cmax = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (p.round_bf16) v[i] = bf16_round(v[i]);
-              if (cbase + i >= p.vocab) v[i] = -INFINITY;
-              cmax = fmaxf(cmax, v[i]);
-            }
-            if (cmax > st_m[mt]) {
-              st_z[mt] *= exp2f((st_m[mt] - cmax) * kLog2e);
-              st_m[mt] = cmax;
-            }
-            float zs = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              zs += exp2f((v[i] - st_m[mt]) * kLog2e);
-              if (v[i] > topv[mt][KT - 1]) {  // rare: insert into the sorted top-k list
-                topv[mt][KT - 1] = v[i];
-                topi[mt][KT - 1] = cbase + i;
-#pragma unroll
-                for (int j = KT - 1; j > 0; --j) {
-                  if (topv[mt][j] > topv[mt][j - 1]) {
-                    const float tv = topv[mt][j]; topv[mt][j] = topv[mt][j - 1]; topv[mt][j - 1] = tv;
-                    const int ti = topi[mt][j]; topi[mt][j] = topi[mt][j - 1]; topi[mt][j - 1] = ti;
-                  }
-                }
+              for (int i = 0; i < 32; ++i) {
+                if (p.round_bf16) v[i] = bf16_round(v[i]);
+                if (cbase + i >= p.vocab) v[i] = -INFINITY;
+                cmax = fmaxf(cmax, v[i]);
               }
-            }
-            st_z[mt] += zs;
+              smax = fmaxf(smax, cmax);
+              if (cmax > st_m[mt]) {
+                st_z[mt] *= exp2f((st_m[mt] - cmax) * kLog2e);
+                st_m[mt] = cmax;
+              }
+              const float mneg = -st_m[mt] * kLog2e;
+              float zs = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) zs += exp2f(fmaf(v[i], kLog2e, mneg));
+              st_z[mt] += zs;
             }
           }
+          if (ok) p.strip_max[((size_t)img * p.n_strips + strip) * p.n_vis + row] = smax;
           tc_fence_before();
           mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
         }
@@ -431,11 +470,13 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
               float v[32];
               tmem_ld32(lane_addr + mt * BN + c * 32, v);
+              float cm = -INFINITY;  // chunk maximum of this row: any top-k candidate in here?
               if (ok) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                   float x = v[i];
                   if (p.round_bf16) x = bf16_round(x);
+                  cm = fmaxf(cm, x);
                   float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
                   float dv = pr - inv_v;
                   if (col0 + c * 32 + i >= p.vocab) pr = dv = 0.f;  // padded vocab columns of the last strip
@@ -444,6 +485,10 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                   acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
                 }
               }
+              if (__any_sync(0xffffffffu, cm >= st_tau[mt]))  // warp-uniform, ~1 chunk in 4
+                append_candidates(CandSink{p.cand_cnt, p.cand_val, p.cand_idx, p.cap, p.vocab, p.round_bf16},
+                                  lane_addr + mt * BN + c * 32, st_tau[mt], col0 + c * 32,
+                                  (size_t)img * p.n_vis + row0 + mt * BM + tid);
               if (MODE == MODE_COLSUM && c == BN / 32 - 1) {  // no second pass over TMEM in this mode
                 tc_fence_before();
                 mbar_arrive(bar_tempty + 8 * mt);
@@ -513,13 +558,6 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (MODE == MODE_STATS) {
         p.part_stats[pr * 2] = st_m[mt];
         p.part_stats[pr * 2 + 1] = st_z[mt];
-#pragma unroll
-        for (int j = 0; j < KT; ++j) {
-          if (j < p.topk) {
-            p.part_topv[pr * p.topk + j] = topv[mt][j];
-            p.part_topi[pr * p.topk + j] = topi[mt][j];
-          }
-        }
       } else {
         if (MODE != MODE_CROSS) {
           p.part_acq[pr * 3] = acc_a[mt];
@@ -538,40 +576,38 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
-// merge the per-CTA (m, z, top-k) partials of one row: row_stats = (m, 1/Z), ids sorted descending
-__global__ void stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats,
-                                      int32_t* __restrict__ topk_ids) {
+// merge the per-CTA (m, z) partials of one row: row_stats = (m, 1/Z); tau = k-th largest per-strip maximum
+// (a lower bound of the row's k-th largest logit; -inf when there are fewer than k strips); reset the
+// candidate counter for sweep 2
+__global__ void stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats, float* __restrict__ tau) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
   if (row >= p.n_vis) return;
   float m = -INFINITY;
   for (int q = 0; q < p.parts; ++q)
     m = fmaxf(m, p.part_stats[(((size_t)img * p.parts + q) * p.n_vis + row) * 2]);
   float z = 0.f;
-  float tv[DD_MAX_TOPK];
-  int ti[DD_MAX_TOPK];
-  for (int j = 0; j < p.topk; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
   for (int q = 0; q < p.parts; ++q) {
     const size_t pr = ((size_t)img * p.parts + q) * p.n_vis + row;
     const float pm = p.part_stats[pr * 2];
     if (pm > -INFINITY) z += p.part_stats[pr * 2 + 1] * exp2f((pm - m) * kLog2e);
-    for (int j = 0; j < p.topk; ++j) {
-      const float v = p.part_topv[pr * p.topk + j];
-      const int id = p.part_topi[pr * p.topk + j];
-      const int last = p.topk - 1;
-      if (v > tv[last] || (v == tv[last] && id < ti[last])) {
-        tv[last] = v; ti[last] = id;
-        for (int k = last; k > 0; --k) {
-          if (tv[k] > tv[k - 1] || (tv[k] == tv[k - 1] && ti[k] < ti[k - 1])) {
-            const float a = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = a;
-            const int b = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = b;
-          } else break;
-        }
+  }
+  float tv[DD_MAX_TOPK];  // the k largest strip maxima, descending
+  for (int j = 0; j < DD_MAX_TOPK; ++j) tv[j] = -INFINITY;
+  const int last = p.topk - 1;
+  for (int s = 0; s < p.n_strips; ++s) {
+    const float v = p.strip_max[((size_t)img * p.n_strips + s) * p.n_vis + row];
+    if (v > tv[last]) {
+      tv[last] = v;
+      for (int k = last; k > 0 && tv[k] > tv[k - 1]; --k) {
+        const float t = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = t;
       }
     }
   }
-  row_stats[((size_t)img * p.n_vis + row) * 2] = m;
-  row_stats[((size_t)img * p.n_vis + row) * 2 + 1] = 1.0f / z;
-  for (int j = 0; j < p.topk; ++j) topk_ids[((size_t)img * p.n_vis + row) * p.topk + j] = ti[j];
+  const size_t o = (size_t)img * p.n_vis + row;
+  row_stats[o * 2] = m;
+  row_stats[o * 2 + 1] = 1.0f / z;
+  tau[o] = tv[last];
+  p.cand_cnt[o] = 0;
 }
 
 // log(p_avg + eps) from the per-chunk column sums (n_vis > 640 path)
@@ -585,9 +621,29 @@ __global__ void logpavg_kernel(const UncParams p) {
 }
 
 __global__ void fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restrict__ alea,
-                                      float* __restrict__ var) {
+                                      float* __restrict__ var, int32_t* __restrict__ topk_ids) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
   if (row >= p.n_vis) return;
+  {  // top-k ids from the candidate list: k selection passes, value descending, id ascending on ties
+    const size_t r = (size_t)img * p.n_vis + row;
+    const int n = min(p.cand_cnt[r], p.cap);
+    const float* cv = p.cand_val + r * p.cap;
+    const int32_t* ci = p.cand_idx + r * p.cap;
+    float pv = INFINITY;
+    int pi = -1;
+    for (int j = 0; j < p.topk; ++j) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int e = 0; e < n; ++e) {
+        const float v = cv[e];
+        const int id = ci[e];
+        const bool after_prev = v < pv || (v == pv && id > pi);   // strictly after the previous pick
+        if (after_prev && (v > bv || (v == bv && id < bi))) { bv = v; bi = id; }
+      }
+      topk_ids[r * p.topk + j] = bi == 0x7fffffff ? 0 : bi;
+      pv = bv; pi = bi;
+    }
+  }
   float a = 0.f, q = 0.f, c = 0.f;
   for (int s = 0; s < p.parts; ++s) {
     const size_t pr = ((size_t)img * p.parts + s) * p.n_vis + row;
@@ -633,7 +689,8 @@ static int num_sms() {
 
 struct UncLayout {
   int n_strips, parts, n_chunks;
-  size_t off_stats, off_topv, off_topi, off_rowstats, off_acq, off_colpart, off_logpavg, total;
+  int cap;
+  size_t off_stats, off_smax, off_tau, off_ccnt, off_cval, off_cidx, off_rowstats, off_acq, off_colpart, off_logpavg, total;
 };
 static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   UncLayout L;
@@ -644,8 +701,13 @@ static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   const size_t rows = (size_t)n_images * L.parts * n_vis;
   size_t o = 0;
   L.off_stats = o; o = align_up(o + rows * 2 * sizeof(float), 256);
-  L.off_topv = o; o = align_up(o + rows * topk * sizeof(float), 256);
-  L.off_topi = o; o = align_up(o + rows * topk * sizeof(int32_t), 256);
+  const size_t nrow = (size_t)n_images * n_vis;
+  L.cap = BN * topk + 64;  // without ties at most BN*topk elements reach the threshold
+  L.off_smax = o; o = align_up(o + nrow * L.n_strips * sizeof(float), 256);
+  L.off_tau = o; o = align_up(o + nrow * sizeof(float), 256);
+  L.off_ccnt = o; o = align_up(o + nrow * sizeof(int32_t), 256);
+  L.off_cval = o; o = align_up(o + nrow * L.cap * sizeof(float), 256);
+  L.off_cidx = o; o = align_up(o + nrow * L.cap * sizeof(int32_t), 256);
   L.off_rowstats = o; o = align_up(o + (size_t)n_images * n_vis * 2 * sizeof(float), 256);
   L.off_acq = o; o = align_up(o + rows * 3 * sizeof(float), 256);
   const size_t vp = (size_t)L.n_strips * BN;
@@ -673,9 +735,7 @@ static int launch_unc_mt(const CUtensorMap& ta, const CUtensorMap& tw, const Unc
   if (mode == MODE_FUSED) return launch_unc<NUM_MT, MODE_FUSED, 1>(ta, tw, p, st);
   if (mode == MODE_COLSUM) return launch_unc<NUM_MT, MODE_COLSUM, 1>(ta, tw, p, st);
   if (mode == MODE_CROSS) return launch_unc<NUM_MT, MODE_CROSS, 1>(ta, tw, p, st);
-  if (p.topk <= 5) return launch_unc<NUM_MT, MODE_STATS, 5>(ta, tw, p, st);
-  if (p.topk <= 10) return launch_unc<NUM_MT, MODE_STATS, 10>(ta, tw, p, st);
-  return launch_unc<NUM_MT, MODE_STATS, DD_MAX_TOPK>(ta, tw, p, st);
+  return launch_unc<NUM_MT, MODE_STATS, 1>(ta, tw, p, st);
 }
 
 static int launch_unc_any(int num_mt, const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, int mode,
@@ -744,8 +804,13 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
   p.colpart = reinterpret_cast<float*>(ws + L.off_colpart);
   p.logpavg = reinterpret_cast<float*>(ws + L.off_logpavg);
   p.part_stats = reinterpret_cast<float*>(ws + L.off_stats);
-  p.part_topv = reinterpret_cast<float*>(ws + L.off_topv);
-  p.part_topi = reinterpret_cast<int32_t*>(ws + L.off_topi);
+  p.strip_max = reinterpret_cast<float*>(ws + L.off_smax);
+  float* tau = reinterpret_cast<float*>(ws + L.off_tau);
+  p.tau = tau;
+  p.cand_cnt = reinterpret_cast<int32_t*>(ws + L.off_ccnt);
+  p.cand_val = reinterpret_cast<float*>(ws + L.off_cval);
+  p.cand_idx = reinterpret_cast<int32_t*>(ws + L.off_cidx);
+  p.cap = L.cap;
   float* row_stats = reinterpret_cast<float*>(ws + L.off_rowstats);
   p.row_stats = row_stats;
   p.part_acq = reinterpret_cast<float*>(ws + L.off_acq);
@@ -754,7 +819,7 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
   const dim3 fgrid(ceil_div(n_vis, 128), n_images);
   int rc = launch_unc_any(num_mt, ta, tw, p, MODE_STATS, st);
   if (rc) return rc;
-  stats_finalize_kernel<<<fgrid, 128, 0, st>>>(p, row_stats, topk_ids);
+  stats_finalize_kernel<<<fgrid, 128, 0, st>>>(p, row_stats, tau);
   DD_CHECK_LAUNCH();
   if (L.n_chunks == 1) {
     rc = launch_unc_any(num_mt, ta, tw, p, MODE_FUSED, st);
@@ -767,7 +832,7 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
     rc = launch_unc_any(num_mt, ta, tw, p, MODE_CROSS, st);
     if (rc) return rc;
   }
-  fused_finalize_kernel<<<fgrid, 128, 0, st>>>(p, epi, alea, var);
+  fused_finalize_kernel<<<fgrid, 128, 0, st>>>(p, epi, alea, var, topk_ids);
   DD_CHECK_LAUNCH();
   return DD_OK;
 }

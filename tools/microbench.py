@@ -106,13 +106,20 @@ def bench_uncertainty(only_first=False):
     for (n_img, n_vis, d, V, k) in cases[:1] if only_first else cases:
         h = torch.randn(n_img, n_vis, d, device=dev).bfloat16()
         w = (torch.randn(V, d, device=dev) * 0.02).bfloat16()
-        fn = lambda: ops.uncertainty_project(h, w, topk=k)
-        med, best = timeit(fn, iters=10)
+        one = lambda: ops.uncertainty_project(h, w, topk=k)
+        med1, _ = timeit(one, iters=10)                      # one call: includes the host latency before the first launch
+
+        def fn():                                            # 4 calls back to back: the GPU never waits for the host
+            for _ in range(4):
+                one()
+        med, best = timeit(fn, iters=6)
+        med, best = med / 4, best / 4
         flops = 2.0 * n_img * n_vis * d * V
         tfn = lambda: torch.matmul(h.view(-1, d), w.T)
         tmed, _ = timeit(tfn, iters=10)
         print(json.dumps(dict(kernel="uncertainty_project", lib=os.path.basename(os.environ.get("DD_LIB", "default")), n_img=n_img, n_vis=n_vis, d=d, V=V,
-                              us=round(med * 1e6, 1), best_us=round(best * 1e6, 1), TFLOPs=round(flops / med / 1e12, 1),
+                              us=round(med * 1e6, 1), best_us=round(best * 1e6, 1), single_call_us=round(med1 * 1e6, 1),
+                              TFLOPs=round(flops / med / 1e12, 1),
                               frac_tensor=round(flops / med / 1e12 / TF, 3), cublas_gemm_only_us=round(tmed * 1e6, 1),
                               peak=SRC)))
 
