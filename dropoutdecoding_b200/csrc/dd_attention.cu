@@ -4,8 +4,9 @@
 //
 // HBM-bound design (algorithmic bytes per sequence/layer/pass = 2*S*H_kv*D*2):
 //   grid = (kv splits, H_kv, B); a CTA streams its slice of K and V exactly once through a
-//   3-stage cp.async ring (128-bit, fully coalesced: a kv-head's rows are contiguous) into
-//   XOR-swizzled shared memory and scores it against ALL R = M * (H/H_kv) query rows of that
+//   3-stage ring of TMA tiles (cp.async.bulk.tensor, [64 keys x 64 dims] boxes, SWIZZLE_128B, completion
+//   on an mbarrier: one elected thread issues, no thread spends issue slots on addresses) into
+//   shared memory and scores it against ALL R = M * (H/H_kv) query rows of that
 //   (sequence, kv head) -- members x GQA group -- with mma.sync m16n8k16 (queries are the M=16
 //   operand, 16 keys per warp per tile).  Member m's visual-token bitmask is applied to the score
 //   fragments in registers; masked keys get -inf exactly like the reference's additive
@@ -14,6 +15,8 @@
 //   then independent of the online-softmax rescaling order and matches an fp32 softmax.
 //   Split-KV partials (m, l, unnormalised O) go to a workspace; the merge kernel folds in each
 //   member's own new-token row (k_new / v_new, never written to the cache before the vote).
+#include <cuda.h>
+
 #include "dd_common.cuh"
 
 namespace dd {
@@ -24,13 +27,32 @@ constexpr int kTileKeys = 16 * kAttnWarps;  // 64 keys per pipeline stage
 constexpr int kStages = 3;
 constexpr int kMaxMaskWords = 256;  // n_vis <= 8192
 
-__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gptr) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -52,19 +74,30 @@ struct AttnParams {
   float scale_log2;  // scale * log2(e)
 };
 
-// smem row = one key/query row of D bf16 = D/8 chunks of 16 B; chunk c of row r lives at
+// Q rows (staged by the threads): one row of D bf16 = D/8 chunks of 16 B; chunk c of row r lives at
 // physical chunk c ^ (r & 7): ldmatrix's 8 row addresses then hit 8 distinct 16-byte bank groups.
 template <int D>
 __device__ __forceinline__ uint32_t swz(int row, int chunk) {
   return (uint32_t)(row * (D * 2) + ((chunk ^ (row & 7)) << 4));
 }
+// K / V tiles (written by TMA, SWIZZLE_128B): a tile of 64 keys is D/64 boxes of [64 keys x 128 B]; inside a
+// box the 16-byte chunk c of row r lives at chunk c ^ (r & 7) of the row -- the same conflict-free pattern.
+template <int D>
+__device__ __forceinline__ uint32_t swz_kv(int row, int chunk) {
+  return (uint32_t)((chunk >> 3) * (kTileKeys * 128) + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
+}
 
 template <int D, int QT>
-__global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid_constant__ CUtensorMap tmap_k,
+                                                                    const __grid_constant__ CUtensorMap tmap_v,
+                                                                    const AttnParams p) {
   constexpr int CH = D / 8;            // 16-byte chunks per row
   constexpr int ROW_B = D * 2;         // bytes per row
   constexpr int TILE_B = kTileKeys * ROW_B;
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment (the dynamic smem base is only 16-byte aligned by contract)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t s_full[kStages];
   uint8_t* sK = smem;                           // [kStages][64][D]
   uint8_t* sV = smem + kStages * TILE_B;        // [kStages][64][D]
   uint8_t* sQ = smem + 2 * kStages * TILE_B;    // [16*QT][D]
@@ -86,27 +119,31 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnPa
   const int k_end = min(S, k_beg + per);
   const int ntiles = k_end > k_beg ? (k_end - k_beg + kTileKeys - 1) / kTileKeys : 0;
 
-  const __nv_bfloat16* Kg = p.k_cache + ((size_t)b * p.H_kv + hkv) * (size_t)p.S_max * D;
-  const __nv_bfloat16* Vg = p.v_cache + ((size_t)b * p.H_kv + hkv) * (size_t)p.S_max * D;
+  const uint32_t bar_full = smem_u32(s_full);
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) mbar_init(bar_full + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
+  // one elected thread issues the D/64 + D/64 boxes of a tile; the stage's mbarrier counts the bytes
   auto load_tile = [&](int tile, int stage) {
     const int key0 = k_beg + tile * kTileKeys;
     const uint32_t kb = smem_u32(sK + stage * TILE_B), vb = smem_u32(sV + stage * TILE_B);
+    const uint32_t bar = bar_full + 8 * stage;
+    mbar_expect_tx(bar, 2 * TILE_B);
 #pragma unroll
-    for (int i = 0; i < kTileKeys * CH / kAttnThreads; ++i) {
-      const int idx = i * kAttnThreads + tid;
-      const int row = idx / CH, c = idx % CH;
-      const int key = min(key0 + row, S - 1);  // clamp the tail: rows >= k_end are masked later
-      cp_async_16(kb + swz<D>(row, c), Kg + (size_t)key * D + c * 8);
-      cp_async_16(vb + swz<D>(row, c), Vg + (size_t)key * D + c * 8);
+    for (int h = 0; h < D / 64; ++h) {
+      tma_load_3d(kb + h * (kTileKeys * 128), &tmap_k, bar, h * 64, key0, b * p.H_kv + hkv);
+      tma_load_3d(vb + h * (kTileKeys * 128), &tmap_v, bar, h * 64, key0, b * p.H_kv + hkv);
     }
   };
 
   // ---- prologue: start the ring, stage Q and the member bitmasks -------------------------------
+  if (tid == 0) {
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) {
-    if (s < ntiles) load_tile(s, s);
-    cp_async_commit();
+    for (int s = 0; s < kStages - 1; ++s)
+      if (s < ntiles) load_tile(s, s);
   }
   for (int idx = tid; idx < 16 * QT * CH; idx += kAttnThreads) {
     const int r = idx / CH, c = idx % CH;
@@ -133,15 +170,26 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnPa
       for (int c = 0; c < 4; ++c) o[qt][n][c] = 0.f;
   }
 
+  __syncthreads();  // Q and the masks are staged
   for (int tile = 0; tile < ntiles; ++tile) {
-    cp_async_wait<kStages - 2>();
-    __syncthreads();  // tile `tile` landed for everyone; everyone is done with the stage refilled next
-    {
+    const int stage = tile % kStages;
+    __syncthreads();  // everyone is done with the stage that is refilled next (it held tile - 1)
+    if (tid == 0) {
       const int nt = tile + kStages - 1;
       if (nt < ntiles) load_tile(nt, nt % kStages);
-      cp_async_commit();
     }
-    const int stage = tile % kStages;
+    mbar_wait(bar_full + 8 * stage, (tile / kStages) & 1);  // tile `tile` has landed
+    if (tile == ntiles - 1 && (k_end - k_beg) % kTileKeys != 0) {
+      // cache rows past seq_len are never written by anyone and may hold anything: a masked key has p = 0, but
+      // 0 * NaN would still poison P.V, so clear the dead V rows of the last tile
+      const int first_dead = k_end - (k_beg + tile * kTileKeys);
+      uint8_t* vt = sV + stage * TILE_B;
+      for (int idx = tid; idx < (kTileKeys - first_dead) * CH; idx += kAttnThreads) {
+        const int row = first_dead + idx / CH, c = idx % CH;
+        *reinterpret_cast<uint4*>(vt + swz_kv<D>(row, c)) = make_uint4(0, 0, 0, 0);
+      }
+      __syncthreads();
+    }
     const uint32_t kb = smem_u32(sK + stage * TILE_B), vb = smem_u32(sV + stage * TILE_B);
     const int key0 = k_beg + tile * kTileKeys + warp * 16;  // this warp's 16 keys
     if (key0 >= k_end) continue;                            // warp-uniform
@@ -155,7 +203,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnPa
       for (int ks = 0; ks < D / 16; ++ks) {
         uint32_t a[4], kf[4];
         ldmatrix_x4(a, smem_u32(sQ) + swz<D>(qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)));
-        ldmatrix_x4(kf, kb + swz<D>(warp * 16 + (lane & 7) + ((lane >> 4) << 3), 2 * ks + ((lane >> 3) & 1)));
+        ldmatrix_x4(kf, kb + swz_kv<D>(warp * 16 + (lane & 7) + ((lane >> 4) << 3), 2 * ks + ((lane >> 3) & 1)));
         mma_bf16_16816(s[0], a[0], a[1], a[2], a[3], kf[0], kf[1]);
         mma_bf16_16816(s[1], a[0], a[1], a[2], a[3], kf[2], kf[3]);
       }
@@ -224,7 +272,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnPa
 #pragma unroll
       for (int n2 = 0; n2 < D / 16; ++n2) {
         uint32_t vf[4];
-        ldmatrix_x4_trans(vf, vb + swz<D>(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * n2 + (lane >> 4)));
+        ldmatrix_x4_trans(vf, vb + swz_kv<D>(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * n2 + (lane >> 4)));
         mma_bf16_16816(o[qt][2 * n2], ph[0], ph[1], ph[2], ph[3], vf[0], vf[1]);
         mma_bf16_16816(o[qt][2 * n2 + 1], ph[0], ph[1], ph[2], ph[3], vf[2], vf[3]);
         mma_bf16_16816(o[qt][2 * n2], pl[0], pl[1], pl[2], pl[3], vf[0], vf[1]);
@@ -232,7 +280,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnPa
       }
     }
   }
-  cp_async_wait<0>();
   pdl_trigger_stream_tail();
   __syncthreads();  // ring is idle: reuse it for the cross-warp merge
 
@@ -323,11 +370,20 @@ static size_t attn_smem_bytes(int M, int mask_words) {
   const size_t ring = 2ull * kStages * kTileKeys * D * 2;
   const size_t merge = (size_t)kAttnWarps * 16 * QT * (D + 2) * sizeof(float);
   const size_t main_b = ring + 16ull * QT * D * 2 + (size_t)M * mask_words * 4;
-  return main_b > merge ? main_b : merge;
+  return 1024 + (main_b > merge ? main_b : merge);  // + slack to align the SWIZZLE_128B tiles to 1024 B
 }
 
 template <int D, int QT>
 static int launch_attn(const AttnParams& p, const void* k_new, const void* v_new, void* out, cudaStream_t st) {
+  // K / V of one layer as [B*H_kv][S_max][D]; a box is 64 keys x 64 dims (128 B rows, SWIZZLE_128B)
+  CUtensorMap tmap_k, tmap_v;
+  {
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)p.S_max, (uint64_t)p.B * p.H_kv};
+    const uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)p.S_max * D * 2};
+    const uint32_t box[3] = {64, (uint32_t)kTileKeys, 1};
+    if (int rc = make_tmap_bf16_sw128(&tmap_k, p.k_cache, 3, dims, strides, box, "dd_decode_attention(k_cache)")) return rc;
+    if (int rc = make_tmap_bf16_sw128(&tmap_v, p.v_cache, 3, dims, strides, box, "dd_decode_attention(v_cache)")) return rc;
+  }
   const size_t smem = attn_smem_bytes<D, QT>(p.M, p.bitmask ? p.mask_words : 0);
   static size_t configured = 0;  // opt in to > 48 KB dynamic smem once per instantiation (grow-only)
   if (smem > configured) {
@@ -335,7 +391,8 @@ static int launch_attn(const AttnParams& p, const void* k_new, const void* v_new
                                        (int)smem));
     configured = smem;
   }
-  DD_LAUNCH_CHAIN(attn_partial_kernel<D, QT>, dim3(p.num_splits, p.H_kv, p.B), dim3(kAttnThreads), smem, st, p);
+  DD_LAUNCH_CHAIN(attn_partial_kernel<D, QT>, dim3(p.num_splits, p.H_kv, p.B), dim3(kAttnThreads), smem, st, tmap_k,
+                  tmap_v, p);
   DD_LAUNCH_CHAIN(attn_merge_kernel<D>, dim3(p.H, p.M, p.B), dim3(D), 0, st, p, (const __nv_bfloat16*)k_new,
                   (const __nv_bfloat16*)v_new, (__nv_bfloat16*)out);
   return DD_OK;
@@ -357,6 +414,8 @@ extern "C" int dd_decode_attention(const void* q, const void* k_new, const void*
   DD_CHECK_ARG(q && k_new && v_new && k_cache && v_cache && seq_lens && out && workspace,
                "dd_decode_attention: null pointer");
   DD_CHECK_ARG(D == 64 || D == 128, "dd_decode_attention: D=%d unsupported (64 or 128)", D);
+  DD_CHECK_ARG(((uintptr_t)k_cache & 15) == 0 && ((uintptr_t)v_cache & 15) == 0,
+               "dd_decode_attention: the caches must be 16-byte aligned (TMA)");
   DD_CHECK_ARG(H_kv >= 1 && H % H_kv == 0, "dd_decode_attention: H=%d not a multiple of H_kv=%d", H, H_kv);
   DD_CHECK_ARG(M >= 1 && M <= DD_MAX_MEMBERS && M * (H / H_kv) <= 32,
                "dd_decode_attention: M*(H/H_kv)=%d exceeds 32 query rows per kv head", M * (H / H_kv));

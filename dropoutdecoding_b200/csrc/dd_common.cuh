@@ -1,5 +1,6 @@
 // Shared helpers for the libdropdec kernels (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,6 +13,12 @@
 namespace dd {
 
 void set_error(const char* fmt, ...);
+
+// cuTensorMapEncodeTiled for a dense bf16 tensor with SWIZZLE_128B boxes (driver entry point resolved through
+// the runtime, so the library does not link libcuda).  dims / box: innermost first; strides_bytes: rank - 1
+// entries.  Returns DD_OK or DD_ERR_CUDA (message set).
+int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, const char* what);
 
 #define DD_CHECK_ARG(cond, ...)            \
   do {                                     \

@@ -576,38 +576,60 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
+// The two finalize kernels run ONE WARP PER ROW (lanes split the partials): a thread per row would walk
+// hundreds of dependent L2 loads and take longer than a GEMM sweep.
+constexpr int kFinWarps = 8;
+
 // merge the per-CTA (m, z) partials of one row: row_stats = (m, 1/Z); tau = k-th largest per-strip maximum
 // (a lower bound of the row's k-th largest logit; -inf when there are fewer than k strips); reset the
 // candidate counter for sweep 2
-__global__ void stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats, float* __restrict__ tau) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
-  if (row >= p.n_vis) return;
+__global__ void __launch_bounds__(kFinWarps * 32)
+stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats, float* __restrict__ tau) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kFinWarps + (threadIdx.x >> 5), img = blockIdx.y;
+  if (row >= p.n_vis) return;  // warp-uniform
   float m = -INFINITY;
-  for (int q = 0; q < p.parts; ++q)
+  for (int q = lane; q < p.parts; q += 32)
     m = fmaxf(m, p.part_stats[(((size_t)img * p.parts + q) * p.n_vis + row) * 2]);
+  m = warp_max(m);
   float z = 0.f;
-  for (int q = 0; q < p.parts; ++q) {
+  for (int q = lane; q < p.parts; q += 32) {
     const size_t pr = ((size_t)img * p.parts + q) * p.n_vis + row;
     const float pm = p.part_stats[pr * 2];
     if (pm > -INFINITY) z += p.part_stats[pr * 2 + 1] * exp2f((pm - m) * kLog2e);
   }
-  float tv[DD_MAX_TOPK];  // the k largest strip maxima, descending
+  z = warp_sum(z);
+  // k-th largest strip maximum: every lane keeps its own values sorted (descending), then k rounds of
+  // "largest head over the warp, its owner pops"
+  float tv[DD_MAX_TOPK];
+#pragma unroll
   for (int j = 0; j < DD_MAX_TOPK; ++j) tv[j] = -INFINITY;
-  const int last = p.topk - 1;
-  for (int s = 0; s < p.n_strips; ++s) {
-    const float v = p.strip_max[((size_t)img * p.n_strips + s) * p.n_vis + row];
-    if (v > tv[last]) {
-      tv[last] = v;
-      for (int k = last; k > 0 && tv[k] > tv[k - 1]; --k) {
-        const float t = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = t;
-      }
+  for (int s = lane; s < p.n_strips; s += 32) {
+    float v = p.strip_max[((size_t)img * p.n_strips + s) * p.n_vis + row];
+#pragma unroll
+    for (int j = 0; j < DD_MAX_TOPK; ++j) {  // insertion by a chain of swaps keeps tv[] in registers
+      const float hi = fmaxf(tv[j], v);
+      v = fminf(tv[j], v);
+      tv[j] = hi;
     }
   }
-  const size_t o = (size_t)img * p.n_vis + row;
-  row_stats[o * 2] = m;
-  row_stats[o * 2 + 1] = 1.0f / z;
-  tau[o] = tv[last];
-  p.cand_cnt[o] = 0;
+  float kth = -INFINITY;
+  for (int j = 0; j < p.topk; ++j) {
+    kth = warp_max(tv[0]);
+    const unsigned owners = __ballot_sync(0xffffffffu, tv[0] == kth);
+    if (lane == __ffs(owners) - 1) {  // one owner pops its head
+#pragma unroll
+      for (int k = 0; k + 1 < DD_MAX_TOPK; ++k) tv[k] = tv[k + 1];
+      tv[DD_MAX_TOPK - 1] = -INFINITY;
+    }
+  }
+  if (lane == 0) {
+    const size_t o = (size_t)img * p.n_vis + row;
+    row_stats[o * 2] = m;
+    row_stats[o * 2 + 1] = 1.0f / z;
+    tau[o] = kth;
+    p.cand_cnt[o] = 0;
+  }
 }
 
 // log(p_avg + eps) from the per-chunk column sums (n_vis > 640 path)
@@ -620,12 +642,14 @@ __global__ void logpavg_kernel(const UncParams p) {
   p.logpavg[(size_t)img * vp + v] = __logf(tot / (float)p.n_vis + kEps);
 }
 
-__global__ void fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restrict__ alea,
-                                      float* __restrict__ var, int32_t* __restrict__ topk_ids) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
-  if (row >= p.n_vis) return;
-  {  // top-k ids from the candidate list: k selection passes, value descending, id ascending on ties
-    const size_t r = (size_t)img * p.n_vis + row;
+__global__ void __launch_bounds__(kFinWarps * 32)
+fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restrict__ alea, float* __restrict__ var,
+                      int32_t* __restrict__ topk_ids) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kFinWarps + (threadIdx.x >> 5), img = blockIdx.y;
+  if (row >= p.n_vis) return;  // warp-uniform
+  const size_t r = (size_t)img * p.n_vis + row;
+  {  // top-k ids from the candidate list: k selection rounds, value descending, id ascending on ties
     const int n = min(p.cand_cnt[r], p.cap);
     const float* cv = p.cand_val + r * p.cap;
     const int32_t* ci = p.cand_idx + r * p.cap;
@@ -634,48 +658,40 @@ __global__ void fused_finalize_kernel(const UncParams p, float* __restrict__ epi
     for (int j = 0; j < p.topk; ++j) {
       float bv = -INFINITY;
       int bi = 0x7fffffff;
-      for (int e = 0; e < n; ++e) {
+      for (int e = lane; e < n; e += 32) {
         const float v = cv[e];
         const int id = ci[e];
         const bool after_prev = v < pv || (v == pv && id > pi);   // strictly after the previous pick
         if (after_prev && (v > bv || (v == bv && id < bi))) { bv = v; bi = id; }
       }
-      topk_ids[r * p.topk + j] = bi == 0x7fffffff ? 0 : bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) topk_ids[r * p.topk + j] = bi == 0x7fffffff ? 0 : bi;
       pv = bv; pi = bi;
     }
   }
   float a = 0.f, q = 0.f, c = 0.f;
-  for (int s = 0; s < p.parts; ++s) {
+  for (int s = lane; s < p.parts; s += 32) {
     const size_t pr = ((size_t)img * p.parts + s) * p.n_vis + row;
     a += p.part_acq[pr * 3];
     q += p.part_acq[pr * 3 + 1];
     c += p.part_acq[pr * 3 + 2];
   }
-  const size_t o = (size_t)img * p.n_vis + row;
-  alea[o] = -a;                         // models/llava.py:739
-  epi[o] = a - c;                       // models/llava.py:735
-  var[o] = q / (float)(p.vocab - 1);    // torch.var (unbiased), models/llava.py:728
+  a = warp_sum(a); q = warp_sum(q); c = warp_sum(c);
+  if (lane == 0) {
+    alea[r] = -a;                         // models/llava.py:739
+    epi[r] = a - c;                       // models/llava.py:735
+    var[r] = q / (float)(p.vocab - 1);    // torch.var (unbiased), models/llava.py:728
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -772,29 +788,18 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
     set_error("dd_uncertainty_project: workspace %zu < %zu bytes", workspace_bytes, L.total);
     return DD_ERR_WORKSPACE;
   }
-  EncodeTiledFn encode = get_encode_fn();
-  if (!encode) {
-    set_error("dd_uncertainty_project: cuTensorMapEncodeTiled unavailable (driver too old?)");
-    return DD_ERR_CUDA;
-  }
   CUtensorMap ta, tw;
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)n_vis, (cuuint64_t)n_images};
-    const cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)n_vis * d * 2};
-    const cuuint32_t box[3] = {BK, BM, 1}, es[3] = {1, 1, 1};
-    const CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(h_vis), dims, strides, box,
-                              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(h_vis) failed: %d", (int)r); return DD_ERR_CUDA; }
+    const uint64_t dims[3] = {(uint64_t)d, (uint64_t)n_vis, (uint64_t)n_images};
+    const uint64_t strides[2] = {(uint64_t)d * 2, (uint64_t)n_vis * d * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    if (int rc = make_tmap_bf16_sw128(&ta, h_vis, 3, dims, strides, box, "dd_uncertainty_project(h_vis)")) return rc;
   }
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)vocab};
-    const cuuint64_t strides[1] = {(cuuint64_t)d * 2};
-    const cuuint32_t box[2] = {BK, BN}, es[2] = {1, 1};
-    const CUresult r = encode(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_lm), dims, strides, box,
-                              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(w_lm) failed: %d", (int)r); return DD_ERR_CUDA; }
+    const uint64_t dims[2] = {(uint64_t)d, (uint64_t)vocab};
+    const uint64_t strides[1] = {(uint64_t)d * 2};
+    const uint32_t box[2] = {BK, BN};
+    if (int rc = make_tmap_bf16_sw128(&tw, w_lm, 2, dims, strides, box, "dd_uncertainty_project(w_lm)")) return rc;
   }
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   UncParams p{};
@@ -816,10 +821,10 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
   p.part_acq = reinterpret_cast<float*>(ws + L.off_acq);
   cudaStream_t st = (cudaStream_t)stream;
   const int num_mt = L.n_chunks > 1 ? kMaxMT : ceil_div(n_vis, BM);
-  const dim3 fgrid(ceil_div(n_vis, 128), n_images);
+  const dim3 fgrid(ceil_div(n_vis, kFinWarps), n_images);
   int rc = launch_unc_any(num_mt, ta, tw, p, MODE_STATS, st);
   if (rc) return rc;
-  stats_finalize_kernel<<<fgrid, 128, 0, st>>>(p, row_stats, tau);
+  stats_finalize_kernel<<<fgrid, kFinWarps * 32, 0, st>>>(p, row_stats, tau);
   DD_CHECK_LAUNCH();
   if (L.n_chunks == 1) {
     rc = launch_unc_any(num_mt, ta, tw, p, MODE_FUSED, st);
@@ -832,7 +837,7 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
     rc = launch_unc_any(num_mt, ta, tw, p, MODE_CROSS, st);
     if (rc) return rc;
   }
-  fused_finalize_kernel<<<fgrid, 128, 0, st>>>(p, epi, alea, var, topk_ids);
+  fused_finalize_kernel<<<fgrid, kFinWarps * 32, 0, st>>>(p, epi, alea, var, topk_ids);
   DD_CHECK_LAUNCH();
   return DD_OK;
 }

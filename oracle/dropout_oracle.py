@@ -343,6 +343,7 @@ class DecodeTrace:
     winner: List[int] = field(default_factory=list)                # winning member index
     step_logits: List[torch.Tensor] = field(default_factory=list)  # returned logits [V] per step
     member_logits: List[List[torch.Tensor]] = field(default_factory=list)  # [step][member] vote inputs (keep_logits)
+    step_kv: List[tuple] = field(default_factory=list)   # [step] (k [L,H_kv,D], v [L,H_kv,D]): the committed (winner's) new rows
     uncert: Optional[Dict[str, torch.Tensor]] = None
     topk_ids: Optional[torch.Tensor] = None
     vis_hidden: Optional[torch.Tensor] = None
@@ -455,5 +456,6 @@ def ensemble_steps(lm: OracleLM, cache: OracleCache, tok: int, epis: torch.Tenso
         if keep_logits:
             tr.step_logits.append(out_logits)
             tr.member_logits.append(member_logits)
+            tr.step_kv.append((torch.stack([k[:, -1] for k in cache.k]), torch.stack([v[:, -1] for v in cache.v])))
         step += 1
     return tr

@@ -226,6 +226,12 @@ def _run_flavour(cuda, lm, w, cfg_engine, merged, vis_start, n_vis, T, mode, top
         assert int(eng.winner[0]) == tr.winner[s], f"step {s}: winner"
         assert int(eng.next_token[0]) == tr.tokens[s + 1], f"step {s}: token"
         logits_close(eng.step_logits()[0], tr.step_logits[s + 1])
+        # teacher-force the committed K/V rows: the bar is per step; without this a one-ulp flip in a cached row
+        # is re-read by every later step and the comparison measures accumulated drift instead
+        pos = int(eng.seq_lens[0]) - 1
+        k_rows, v_rows = tr.step_kv[s]
+        eng.k_cache[:, 0, :, pos] = k_rows.to(cuda, torch.bfloat16)
+        eng.v_cache[:, 0, :, pos] = v_rows.to(cuda, torch.bfloat16)
     assert len(flips) <= 2, f"too many near-tie swaps: {flips}"
     # and the same thing replayed as a CUDA graph from the start
     eng.load_prefill(torch.stack(tr.prefill_cache.k)[:, None], torch.stack(tr.prefill_cache.v)[:, None], [vis_start])
