@@ -55,8 +55,9 @@ def logits_close(got, want):
     """north_star bar: aggregated logits within 2e-2 absolute in bf16.  The logits ARE bf16 values, so a
     rounding flip is a full bf16 ulp, which exceeds 2e-2 once |logit| >= 2 (ulp 2^-6 .. 2^-5): the bound is
     max(2e-2, 2 ulp) per element, nearly all elements inside 2e-2, and a small mean error."""
-    d = (got.float().cpu() - want.float()).abs()
-    ulp = torch.exp2(torch.floor(torch.log2(want.float().abs().clamp_min(1e-30))) - 7)
+    g, w = got.float().cpu(), want.float()
+    d = (g - w).abs()
+    ulp = torch.exp2(torch.floor(torch.log2(torch.maximum(g.abs(), w.abs()).clamp_min(1e-30))) - 7)
     assert bool((d <= torch.maximum(torch.full_like(d, 2e-2), 2 * ulp)).all()), f"max |diff| {d.max().item():.4f}"
     assert (d > 2e-2).float().mean().item() < 2e-3 and d.mean().item() < 5e-3
 
