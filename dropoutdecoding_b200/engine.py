@@ -254,7 +254,7 @@ class DropoutDecodeEngine:
             ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pb.xn)
             self._linear(pb.xn, lw["wgu"], ops.EPI_SWIGLU, pb.act)
             self._linear(pb.act, lw["wd"], ops.EPI_RESIDUAL, x, residual=x2)
-            self.launches_per_step += 5     # 2 rmsnorm, rope_stage, attention partial + merge
+            self.launches_per_step += 4 + (pb.splits == 1)     # 2 rmsnorm, rope_stage, attention (+ merge when unsplit)
         ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pb.xn)
         self.launches_per_step += 2         # embed gather, final norm
         if head:
@@ -263,8 +263,8 @@ class DropoutDecodeEngine:
 
     def _forward_fused(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool) -> torch.Tensor:
         """<= 32 rows: RoPE + member staging ride in the epilogue of the QKV projection (dd_decoder_linear,
-        DD_EPI_ROPE) -- 8 launches per layer.  With fuse_norm the two RMSNorms also move into the prologue of
-        the GEMM that consumes them (6 launches per layer); measured slower on B200 because every one of the
+        DD_EPI_ROPE) -- 7 launches per layer.  With fuse_norm the two RMSNorms also move into the prologue of
+        the GEMM that consumes them (5 launches per layer); measured slower on B200 because every one of the
         ~1400 CTAs of a GEMM then re-normalises the same rows, so it is off by default (DD_FUSE_NORM=1)."""
         cfg, B, M = self.cfg, self.B, pb.M
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
@@ -288,7 +288,7 @@ class DropoutDecodeEngine:
                 ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pb.xn)
                 ops.decoder_linear(pb.xn, lw["wgu"], ops.EPI_SWIGLU, out=pb.act)
             ops.decoder_linear(pb.act, lw["wd"], ops.EPI_RESIDUAL, residual=x2, out=x)
-            self.launches_per_step += 6 if fuse else 8
+            self.launches_per_step += (5 if fuse else 7) + (pb.splits == 1)
         self.launches_per_step += 1         # embed gather
         if head and fuse:
             ops.decoder_linear(x, self.w.lm_head_padded, ops.EPI_F32, norm_w=self.w.norm, eps=cfg.rms_eps,
@@ -451,10 +451,12 @@ class DropoutDecodeEngine:
 
     def set_uniforms(self, u: Optional[torch.Tensor]) -> None:
         """Parity mode: u [steps, B, K, n_vis] replaces the Philox draws (step s uses u[s])."""
-        self._graph = None
         if u is None:
+            if self.uniforms is not None:
+                self._graph = None          # the captured step reads the uniforms buffer: re-capture without it
             self.uniforms = self._u_step = None
             return
+        self._graph = None
         self.uniforms = u.to(self.dev, torch.float32).contiguous()
         self._u_step = torch.empty(self.B, self.K, self.n_vis, dtype=torch.float32, device=self.dev)
 

@@ -113,7 +113,8 @@ def philox_uniform(seed: int, offset: int, n: int, device="cuda") -> torch.Tenso
 
 def attention_workspace(B: int, M: int, H: int, D: int, num_splits: int, device) -> torch.Tensor:
     L = _lib.load()
-    return torch.empty(max(L.dd_attention_workspace_bytes(B, M, H, D, num_splits), 1), dtype=torch.uint8,
+    # zeroed once: the tail holds the ticket counters of the fused split merge (each call restores them to zero)
+    return torch.zeros(max(L.dd_attention_workspace_bytes(B, M, H, D, num_splits), 1), dtype=torch.uint8,
                        device=device)
 
 

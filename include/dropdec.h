@@ -120,6 +120,8 @@ int dd_philox_uniform(uint64_t seed, uint64_t offset, int n, float* out, dd_stre
  *   out[b,m,h,:] = softmax( [q.K_prefix^T masked_m , q.k_new[m]] * scale ) [V_prefix ; v_new[m]]
  * bitmask == NULL means no masking (the preliminary pass, M = 1).
  * Limits: D in {64,128}; M * (H / H_kv) <= 32.
+ * Workspace: split-KV partials plus one ticket counter per (sequence, kv head) at its end.  The caller zeroes
+ * the workspace ONCE after allocating it; every call leaves the counters at zero again.
  * ------------------------------------------------------------------------------------------ */
 size_t dd_attention_workspace_bytes(int B, int M, int H, int D, int num_splits);
 int dd_decode_attention(const void* q /* bf16 [B, M, H, D] */, const void* k_new /* bf16 [B, M, H_kv, D] */,
