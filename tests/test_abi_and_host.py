@@ -52,7 +52,7 @@ def test_argument_validation_never_touches_the_gpu(lib):
     assert rc == -1 and b"n_vis=9000" in lib.dd_last_error()
     rc = lib.dd_aggregate(one, 1, 17, 100, 100, 0, one, one, one, None, None)
     assert rc == -1 and b"K=17" in lib.dd_last_error()
-    assert lib.dd_attention_workspace_bytes(2, 3, 32, 128, 4) == 2 * 3 * 32 * 4 * 130 * 4
+    assert lib.dd_attention_workspace_bytes(2, 3, 32, 128, 4) == 2 * 3 * 32 * 4 * 130 * 4 + 2 * 32 * 4   # partials + tickets
     assert lib.dd_uncertainty_workspace_bytes(1, 576, 32064, 5) > 0
 
 
