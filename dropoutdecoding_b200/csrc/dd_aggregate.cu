@@ -106,7 +106,85 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __r
   }
 }
 
+// a13: per-step bookkeeping of the reference on the chosen logits row of every sequence.
+//   stats = { 1 / max(logits)                                     (models/llavanext.py:584,593)
+//             entropy (bits), varentropy                          (calculate_entropy_varentropy, models/llava.py:687-708) }
+// Three passes over the row (L2-resident): max + sum-exp, entropy, varentropy -- the reference's own order of
+// operations (log_softmax, p = exp(lp), H = -sum p lp / ln2, sum p (lp/ln2 + H)^2).
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < kAggThreads / 32; ++w) t += s_red[w];
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* s_red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < kAggThreads / 32; ++w) t = fmaxf(t, s_red[w]);
+  return t;
+}
+
+__global__ void __launch_bounds__(kAggThreads) token_stats_kernel(const float* __restrict__ logits, long long seq_stride,
+                                                                  long long member_stride,
+                                                                  const int32_t* __restrict__ member, int V,
+                                                                  const int32_t* __restrict__ slot, int slot_offset,
+                                                                  int n_slots, int B, float* __restrict__ stats) {
+  __shared__ float s_red[kAggThreads / 32];
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int row = (slot ? *slot : 0) + slot_offset;
+  if (row < 0 || row >= n_slots) return;
+  const float* x = logits + (size_t)b * seq_stride + (size_t)(member ? member[b] : 0) * member_stride;
+  float mx = -INFINITY;
+  for (int j = tid; j < V; j += kAggThreads) mx = fmaxf(mx, x[j]);
+  mx = block_max(mx, s_red);
+  float z = 0.f;
+  for (int j = tid; j < V; j += kAggThreads) z += expf(x[j] - mx);
+  z = block_sum(z, s_red);
+  const float lse = mx + logf(z);
+  constexpr float kInvLn2 = 1.4426950408889634f;
+  float h = 0.f;
+  for (int j = tid; j < V; j += kAggThreads) {
+    const float lp = x[j] - lse;
+    h += expf(lp) * lp;
+  }
+  const float entropy = -block_sum(h, s_red) * kInvLn2;
+  float ve = 0.f;
+  for (int j = tid; j < V; j += kAggThreads) {
+    const float lp = x[j] - lse, t = lp * kInvLn2 + entropy;
+    ve += expf(lp) * t * t;
+  }
+  ve = block_sum(ve, s_red);
+  if (tid == 0) {
+    float* o = stats + ((size_t)row * B + b) * 3;
+    o[0] = 1.0f / mx;
+    o[1] = entropy;
+    o[2] = ve;
+  }
+}
+
 }  // namespace dd
+
+extern "C" int dd_token_stats(const float* logits, long long seq_stride, long long member_stride, const int32_t* member,
+                              int B, int V, const int32_t* slot, int slot_offset, int n_slots, float* stats,
+                              dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(logits && stats, "dd_token_stats: null pointer");
+  DD_CHECK_ARG(B >= 0 && V >= 1 && n_slots >= 1, "dd_token_stats: bad shape B=%d V=%d n_slots=%d", B, V, n_slots);
+  if (B == 0) return DD_OK;
+  DD_LAUNCH_CHAIN(token_stats_kernel, dim3(B), dim3(kAggThreads), 0, (cudaStream_t)stream, logits, seq_stride,
+                  member_stride, member, V, slot, slot_offset, n_slots, B, stats);
+  return DD_OK;
+}
 
 extern "C" int dd_aggregate(const float* logits, int B, int K, int V, int ld, int mode, int32_t* member_ids,
                             int32_t* winner, int32_t* token, float* out_logits, dd_stream_t stream) {

@@ -173,6 +173,8 @@ class DropoutDecodeEngine:
         self.step_ctr = torch.zeros(1, **i32)
         self.max_steps = max_steps
         self.tokens_out = torch.zeros(B, max_steps, **i32)
+        # a13 bookkeeping per generated token: {1/max(logits), entropy bits, varentropy} of the returned logits
+        self.token_stats = torch.zeros(max_steps, B, 3, dtype=torch.float32, device=dev)
         self.cur_token = torch.zeros(B, **i32)
         self.next_token = torch.zeros(B, **i32)
         self.y_init = torch.zeros(B, **i32)
@@ -334,10 +336,18 @@ class DropoutDecodeEngine:
             ops.aggregate(self.pa.logits, "vote", member_ids=self.member_ids_a, winner=self.winner_a,
                           token=self.next_token, vocab=self.cfg.vocab)
             self.launches_per_step += 4
+        # a13: 1/max, entropy, varentropy of the logits this step returns (llavanext.py:584, instructblip.py:141-144)
+        if self.vote_on == "hidden":
+            ops.token_stats(self.pa.logits, self.cfg.vocab, self.token_stats, slot=self.step_ctr, slot_offset=1)
+        elif self.aggregate == "mean":
+            ops.token_stats(self.out_logits, self.cfg.vocab, self.token_stats, slot=self.step_ctr, slot_offset=1)
+        else:
+            ops.token_stats(self.pb.logits, self.cfg.vocab, self.token_stats, member=self.winner, slot=self.step_ctr,
+                            slot_offset=1)
         ops.commit_winner(self.pb.k_new, self.pb.v_new, self.winner, self.seq_lens, self.k_cache, self.v_cache)
         ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
         self.cur_token.copy_(self.next_token)
-        self.launches_per_step += 6
+        self.launches_per_step += 7
 
     def capture(self) -> None:
         """Warm up once eagerly (restoring the state), then capture one step into a CUDA graph."""
@@ -447,6 +457,7 @@ class DropoutDecodeEngine:
         ops.aggregate(self.pa.logits, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.cur_token,
                       vocab=self.cfg.vocab)
         self.tokens_out[:, 0] = self.cur_token
+        ops.token_stats(self.pa.logits, self.cfg.vocab, self.token_stats)          # slot 0: the prefill token
         self.step_ctr.zero_()          # ensemble steps done; also the sampler's Philox call index / K
 
     def set_uniforms(self, u: Optional[torch.Tensor]) -> None:
@@ -474,6 +485,13 @@ class DropoutDecodeEngine:
         if not hasattr(self, "_row_idx"):
             self._row_idx = torch.arange(self.B, device=self.dev)
         return self._row_idx
+
+    def token_bookkeeping(self, b: int = 0):
+        """(logits_mask_prob, token_entropies, token_ventropies) of sequence b as Python lists, one entry per
+        generated token -- what the reference appends per forward (models/instructblip.py:141-157)."""
+        n = int(self.step_ctr.item()) + 1
+        t = self.token_stats[:n, b].cpu()
+        return t[:, 0].tolist(), t[:, 1].tolist(), t[:, 2].tolist()
 
     def generated(self) -> torch.Tensor:
         """Tokens generated so far, int32 [B, n]."""

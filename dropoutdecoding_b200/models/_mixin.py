@@ -197,6 +197,7 @@ class DropoutDecodingMixin:
         self.is_first_generation = False
         new = eng.generated().long()
         self.masked_numbers = eng.n_masked[0].tolist()
+        self.logits_mask_prob, self.token_entropies, self.token_ventropies = eng.token_bookkeeping(0)
         if eos_token_id is not None:                                    # finished rows emit pad (HF greedy)
             done = (new == eos_token_id).cumsum(-1) > 0
             after = torch.cat([torch.zeros_like(done[:, :1]), done[:, :-1]], dim=-1)
@@ -261,6 +262,7 @@ class DropoutDecodingMixin:
         eng.cur_token.copy_(input_ids[:, 0].to(torch.int32))
         eng.decode(1, use_graph=True)
         self.masked_numbers = eng.n_masked[0].tolist()                     # :338, 661-662
+        self.logits_mask_prob, self.token_entropies, self.token_ventropies = eng.token_bookkeeping(0)
         return self.output_cls(loss=None, logits=eng.step_logits()[:, None, :],
                                            past_key_values=past_key_values)
 

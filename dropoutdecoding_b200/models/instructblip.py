@@ -126,7 +126,10 @@ class CustomInstructBlipForConditionalGeneration(DropoutDecodingMixin, InstructB
             if eos_token_id is not None and bool((eng.generated() == eos_token_id).any(-1).all()):
                 break
         new = eng.generated().long()
-        self.masked_numbers = lm.masked_numbers = eng.n_masked[0].tolist()   # last step's members, :154-157
+        self.masked_numbers = lm.masked_numbers = eng.n_masked[0].tolist()   # last step's members
+        self.logits_mask_prob, self.token_entropies, self.token_ventropies = eng.token_bookkeeping(0)   # :141-157
+        lm.logits_mask_prob, lm.token_entropies, lm.token_ventropies = (self.logits_mask_prob, self.token_entropies,
+                                                                        self.token_ventropies)
         if eos_token_id is not None:
             done = (new == eos_token_id).cumsum(-1) > 0
             after = torch.cat([torch.zeros_like(done[:, :1]), done[:, :-1]], dim=-1)

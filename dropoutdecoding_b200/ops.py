@@ -178,6 +178,24 @@ def aggregate(logits: torch.Tensor, mode: str = "vote", want_logits: bool = Fals
     return member_ids, winner, token, out_logits
 
 
+def token_stats(logits: torch.Tensor, vocab: int, stats: torch.Tensor, member: Optional[torch.Tensor] = None,
+                slot: Optional[torch.Tensor] = None, slot_offset: int = 0) -> torch.Tensor:
+    """logits fp32 [B, K, ld] (or [B, ld]); stats fp32 [n_slots, B, 3] <- {1/max, entropy bits, varentropy} of row
+    member[b] (default 0) of every sequence, written at slot index *slot + slot_offset."""
+    L = _lib.load()
+    _need(logits, torch.float32, "logits"); _need(stats, torch.float32, "stats")
+    if logits.dim() == 2:
+        logits = logits[:, None, :]
+    B = logits.shape[0]
+    if member is not None:
+        _need(member, torch.int32, "member")
+    if slot is not None:
+        _need(slot, torch.int32, "slot")
+    check(L.dd_token_stats(_ptr(logits), logits.stride(0), logits.stride(1), _ptr(member), B, int(vocab), _ptr(slot),
+                           int(slot_offset), stats.shape[0], _ptr(stats), _stream()), "dd_token_stats")
+    return stats
+
+
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     L = _lib.load()
     _need(x, torch.bfloat16, "x"); _need(w, torch.bfloat16, "w")

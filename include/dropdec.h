@@ -155,6 +155,16 @@ int dd_aggregate(const float* logits /* [B, K, ld] */, int B, int K, int V, int 
                  int32_t* member_ids /* [B, K] */, int32_t* winner /* [B] */, int32_t* token /* [B] */,
                  float* out_logits /* [B, V] or NULL */, dd_stream_t stream);
 
+/* Per-token bookkeeping the reference keeps on the wrapper (models/llavanext.py:584,593;
+ * models/instructblip.py:141-144,154-157; calculate_entropy_varentropy models/llava.py:687-708), computed on the
+ * chosen logits row of every sequence without a host sync:
+ *   row(b)  = logits + b * seq_stride + (member ? member[b] : 0) * member_stride      (elements)
+ *   stats[r, b, :] = { 1 / max(row), entropy in bits, varentropy }     with r = (slot ? *slot : 0) + slot_offset
+ * (nothing is written when r is outside [0, n_slots)). */
+int dd_token_stats(const float* logits, long long seq_stride, long long member_stride,
+                   const int32_t* member /* [B] or NULL */, int B, int V, const int32_t* slot /* device scalar or NULL */,
+                   int slot_offset, int n_slots, float* stats /* [n_slots, B, 3] */, dd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Decoder support for the single-token forwards of the ensemble (models/llama.py:27-47 and the
  * HF Llama decoder layer it calls).  Small-M, weight-streaming (HBM-bound) kernels.

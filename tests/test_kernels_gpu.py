@@ -115,6 +115,27 @@ def test_aggregate_matches_reference(ops, cuda, golden_dir):
         assert int(tok_m[0]) == gavg and int(win_m[0]) == 0
 
 
+def test_token_stats_match_reference_bookkeeping(ops, cuda):
+    """a13: 1/max(logits), base-2 entropy and varentropy of the chosen row == calculate_entropy_varentropy
+    (models/llava.py:687-708) and the logits_mask_prob expression (models/llavanext.py:584)."""
+    from oracle import entropy_varentropy
+    g = torch.Generator().manual_seed(9)
+    B, K, V, ld = 3, 4, 32001, 32016
+    logits = torch.randn(B, K, ld, generator=g) * 1.5
+    logits[1, 2, 77] = 14.0                                  # one sharply peaked row
+    member = torch.tensor([1, 2, 0], dtype=torch.int32)
+    stats = torch.zeros(5, B, 3, device=cuda)
+    slot = torch.tensor([2], dtype=torch.int32, device=cuda)
+    ops.token_stats(logits.to(cuda), V, stats, member=member.to(cuda), slot=slot, slot_offset=1)
+    got = stats.cpu()
+    assert torch.count_nonzero(got[[0, 1, 2, 4]]) == 0       # only slot 2 + 1 was written
+    for b in range(B):
+        row = logits[b, member[b], :V]
+        en, ven = entropy_varentropy(row)
+        want = torch.tensor([1.0 / row.max().item(), en, ven])
+        assert torch.allclose(got[3, b], want, rtol=2e-4, atol=1e-5), (b, got[3, b], want)
+
+
 def test_aggregate_batched_unaligned_vocab(ops, cuda):
     g = torch.Generator().manual_seed(5)
     l = torch.randn(5, 3, 32001, generator=g)

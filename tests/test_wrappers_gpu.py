@@ -158,3 +158,6 @@ def test_instructblip_wrapper(cuda):
     assert m.image_features[1].shape == (2, 32, 10)
     assert m.masked_numbers[0] <= m.masked_numbers[1] <= m.masked_numbers[2] <= 22      # quantile masks: <= 10/16/22
     assert m.language_model.vision_uncert_dict is m.vision_uncert_dict
+    n_new = out.shape[1] - 1                                   # a13 bookkeeping: one entry per generated token
+    assert len(m.logits_mask_prob) == len(m.token_entropies) == len(m.token_ventropies) >= n_new >= 1
+    assert all(0.0 < e < 15.0 for e in m.token_entropies)
