@@ -42,6 +42,8 @@ _SIGNATURES = {
     "dd_token_stats": (C.c_int, [_P, C.c_longlong, C.c_longlong, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "dd_rmsnorm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "dd_skinny_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dd_stream_gemm_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "dd_stream_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "dd_decoder_linear": (C.c_int, [_P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                     C.POINTER(RopeArgs), _P]),
     "dd_rope_stage": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),

@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "_build")
 LIB = os.path.join(OUT, "libdropdec.so")
-SOURCES = ["dd_api.cu", "dd_sampler.cu", "dd_aggregate.cu", "dd_decoder.cu", "dd_skinny_gemm.cu",
+SOURCES = ["dd_api.cu", "dd_sampler.cu", "dd_aggregate.cu", "dd_decoder.cu", "dd_skinny_gemm.cu", "dd_stream_gemm.cu",
            "dd_attention.cu", "dd_uncertainty.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -32,7 +32,8 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    for name in sorted(os.listdir(CSRC)) + ["../../include/dropdec.h"]:
+    names = [n for n in sorted(os.listdir(CSRC)) if n.endswith((".cu", ".cuh", ".h"))]
+    for name in names + ["../../include/dropdec.h"]:
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(name.encode() + f.read())
     return h.hexdigest()

@@ -14,9 +14,9 @@ single shared cache, with no host sync at all, replayed as one CUDA graph:
     vote / mean             member argmax ids, winner, next token                 (dd_aggregate)
     commit                  winner's staged K/V rows -> cache row seq_len, seq_len += 1
 
-Weight GEMMs with <= 32 rows use the weight-streaming dd_skinny_gemm; above that they are plain
-library GEMMs (torch / cuBLAS), as is the prompt prefill, which is not part of the hot path
-(SURVEY.md 8f-3).  All tensors are bf16 with fp32 accumulation; rounding points follow the HF
+Weight GEMMs: <= 16 rows dd_skinny_gemm (mma.sync weight stream), 17..32 rows dd_stream_gemm (tcgen05,
+stream-K), above that library GEMMs unless gemm_backend="stream" (dd_stream_gemm up to 256 rows); the
+prompt prefill, which is not part of the hot path, uses library ops.  All tensors are bf16 with fp32 accumulation; rounding points follow the HF
 Llama decoder so that the CPU oracle's 'bf16-faithful' mode is comparable token for token.
 """
 from __future__ import annotations
@@ -147,7 +147,7 @@ class DropoutDecodeEngine:
                  probs: Sequence[float] = (0.3, 0.5, 0.7), mode: str = "cumulative", keep_relevant: bool = True,
                  topk: int = 5, aggregate: str = "vote", seed: int = 24, max_steps: int = 1024,
                  round_logits: bool = True, est_seq: Optional[int] = None, vote_on: str = "logits",
-                 seq_base: int = 0):
+                 seq_base: int = 0, gemm_backend: Optional[str] = None):
         cfg = weights.cfg
         if cfg.d_model % 256 or cfg.d_ff % 256:
             raise ops.DropDecError("engine needs d_model % 256 == 0 and d_ff % 256 == 0")
@@ -158,6 +158,14 @@ class DropoutDecodeEngine:
         self.probs, self.mode, self.keep_relevant = [float(p) for p in probs], mode, keep_relevant
         self.topk, self.aggregate, self.seed, self.round_logits = topk, aggregate, seed, round_logits
         self.fuse_norm = os.environ.get("DD_FUSE_NORM", "0") == "1"
+        # Weight GEMMs by row count (rows = sequences x members of a pass); measured on B200 (profiles/README.md 4):
+        #   rows <= 16        dd_skinny_gemm / dd_decoder_linear (mma.sync, RoPE fused into the QKV epilogue)
+        #   16 < rows <= 32   dd_stream_gemm (tcgen05, stream-K) -- 1.4-1.6x faster than the skinny kernel there
+        #   rows > 32         library GEMM by default; DD_GEMM=stream (gemm_backend="stream") runs dd_stream_gemm for every
+        #                     pass of up to 256 rows: fully native, currently 15-45 % behind cuBLAS at 64-192 rows
+        self.gemm_backend = gemm_backend or os.environ.get("DD_GEMM", "auto")
+        if self.gemm_backend not in ("auto", "stream", "library", "skinny"):
+            raise ValueError(self.gemm_backend)
         self.seq_base = int(seq_base)   # global index of sequence 0 (batch sharded over GPUs)
         self.vote_on = vote_on          # "hidden": InstructBLIP votes on the argmax of the final hidden state
         self.Vp = weights.vocab_padded
@@ -205,6 +213,13 @@ class DropoutDecodeEngine:
             self._arange = torch.arange(B, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
+        self._sg_ws = None
+        max_rows = B * self.K
+        if any(self._use_stream(r) for r in (B, max_rows)):
+            d, dff, qkv_rows = cfg.d_model, cfg.d_ff, (H + 2 * Hkv) * D
+            shapes = [(qkv_rows, d, ops.EPI_NONE), (d, H * D, ops.EPI_RESIDUAL), (dff, d, ops.EPI_SWIGLU),
+                      (d, dff, ops.EPI_RESIDUAL), (self.Vp, d, ops.EPI_F32)]
+            self._sg_ws = ops.stream_gemm_workspace(min(max_rows, 256), shapes, dev)
 
     # ------------------------------------------------------------------------------------
     def _alloc_pass(self, M: int, est_seq: int) -> _PassBuffers:
@@ -223,9 +238,19 @@ class DropoutDecodeEngine:
             ws=ops.attention_workspace(B, M, H, D, splits, dev), splits=splits)
 
     # weight GEMM with the HF rounding points; <= 32 rows: our weight-streaming kernel
+    def _use_stream(self, rows: int) -> bool:
+        if self.gemm_backend == "stream":
+            return rows <= 256
+        if self.gemm_backend == "auto":
+            return 16 < rows <= 32
+        return False
+
     def _linear(self, x, w, epi, out, residual=None):
         self.launches_per_step += 1
-        if x.shape[0] <= 32:
+        rows = x.shape[0]
+        if self._use_stream(rows):
+            return ops.stream_gemm(x, w, epi, residual=residual, out=out, workspace=self._sg_ws)
+        if rows <= 32:
             return ops.skinny_gemm(x, w, epi, residual=residual, out=out)
         if epi == ops.EPI_NONE:
             return torch.matmul(x, w.T, out=out)
@@ -244,7 +269,7 @@ class DropoutDecodeEngine:
         rows = B * M
         ops.embed_gather(self.w.embed, self.cur_token, M, pb.x)
         x, x2 = pb.x, pb.x2
-        if rows <= 32:
+        if rows <= 32 and not self._use_stream(rows):
             return self._forward_fused(pb, bitmask, head)
         for l, lw in enumerate(self.w.layers):
             ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pb.xn)
@@ -252,7 +277,11 @@ class DropoutDecodeEngine:
             ops.rope_stage(pb.qkv, self.cos, self.sin, self.seq_lens, B, M, H, Hkv, D, pb.q, pb.k_new[l], pb.v_new[l])
             ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
                                  self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws)
-            self._linear(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, x2, residual=x)
+            if rows <= 32 and self.gemm_backend == "auto":      # 33 MB o_proj: the skinny kernel is as fast up to 32 rows
+                ops.skinny_gemm(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
+                self.launches_per_step += 1
+            else:
+                self._linear(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, x2, residual=x)
             ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pb.xn)
             self._linear(pb.xn, lw["wgu"], ops.EPI_SWIGLU, pb.act)
             self._linear(pb.act, lw["wd"], ops.EPI_RESIDUAL, x, residual=x2)

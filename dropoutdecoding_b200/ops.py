@@ -223,6 +223,36 @@ def skinny_gemm(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_NONE, resi
     return out
 
 
+def stream_gemm_workspace(M: int, shapes: Sequence[Tuple[int, int, int]], device) -> torch.Tensor:
+    """One zeroed workspace large enough for dd_stream_gemm at M rows for every (N, K, epilogue) in `shapes`."""
+    L = _lib.load()
+    need = max(L.dd_stream_gemm_workspace_bytes(M, n, k, e) for n, k, e in shapes)
+    if need == 0:
+        raise DropDecError(f"stream_gemm_workspace: unsupported shape among M={M}, {list(shapes)}")
+    return torch.zeros(need, dtype=torch.uint8, device=device)
+
+
+def stream_gemm(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_NONE, residual: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tcgen05 weight-streaming GEMM: x bf16 [M,K] (M <= 256), w bf16 [N,K] ([2N,K] for SwiGLU) -> y [M,N]
+    (fp32 for EPI_F32, else bf16)."""
+    L = _lib.load()
+    _need(x, torch.bfloat16, "x"); _need(w, torch.bfloat16, "w")
+    M, K = x.shape
+    N = w.shape[0] // 2 if epilogue == EPI_SWIGLU else w.shape[0]
+    if w.shape[1] != K:
+        raise DropDecError("stream_gemm: x and w disagree on K")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if epilogue == EPI_F32 else torch.bfloat16, device=x.device)
+    if residual is not None:
+        _need(residual, torch.bfloat16, "residual")
+    if workspace is None:
+        workspace = stream_gemm_workspace(M, [(N, K, epilogue)], x.device)
+    check(L.dd_stream_gemm(_ptr(x), _ptr(w), _ptr(residual), M, N, K, epilogue, _ptr(out), _ptr(workspace),
+                           workspace.numel(), _stream()), "dd_stream_gemm")
+    return out
+
+
 def decoder_linear(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_NONE, *, norm_w: Optional[torch.Tensor] = None,
                    eps: float = 1e-5, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                    rope: Optional[dict] = None) -> Optional[torch.Tensor]:

@@ -188,6 +188,22 @@ int dd_skinny_gemm(const void* x /* bf16 [M, K] */, const void* w /* bf16 [N(,2N
                    const void* residual /* bf16 [M, N] or NULL */, int M, int N, int K, int epilogue,
                    void* y, dd_stream_t stream);
 
+/* The same GEMM and epilogues (DD_EPI_NONE / RESIDUAL / F32 / SWIGLU) for 1 <= M <= 256 rows on the tcgen05
+ * tensor cores -- the batched passes of the ensemble (rows = sequences x members; batch 64 with K = 3 members is
+ * 64 rows in the preliminary pass and 192 in the masked pass), which the reference runs as 1+K separate
+ * `self.language_model(...)` calls (models/llava.py:294-303, 350-359).  Swap-AB (the weights are the M=128 UMMA
+ * operand, the token rows the N operand, accumulators in TMEM), TMA-fed, stream-K over (256-feature tile,
+ * 64-wide k-block) units so that every SM streams the same number of weight bytes; split tiles are reduced
+ * deterministically through `workspace`.
+ * Limits: K % 64 == 0, N % 8 == 0 (SwiGLU: N % 128 == 0), x / w 16-byte aligned.
+ * Workspace: dd_stream_gemm_workspace_bytes(M, N, K, epilogue) bytes; it starts with the tile counters, which the
+ * caller zeroes ONCE after allocating (every call leaves them at zero again); one workspace sized for the largest
+ * shape can serve every call on a stream. */
+size_t dd_stream_gemm_workspace_bytes(int M, int N, int K, int epilogue);
+int dd_stream_gemm(const void* x /* bf16 [M, K] */, const void* w /* bf16 [N(,2N), K] */,
+                   const void* residual /* bf16 [M, N] or NULL */, int M, int N, int K, int epilogue, void* y,
+                   void* workspace, size_t workspace_bytes, dd_stream_t stream);
+
 /* Fused decoder GEMM: dd_skinny_gemm plus the two fusions that remove the small kernels between the
  * GEMMs of a decoder layer (same rounding points as the separate kernels):
  *   norm_w != NULL : x is replaced on the fly by dd_rmsnorm(x, norm_w, eps)   (input_layernorm /

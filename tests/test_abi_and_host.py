@@ -48,6 +48,14 @@ def test_argument_validation_never_touches_the_gpu(lib):
     assert rc == -1 and b"M=33" in lib.dd_last_error()
     rc = lib.dd_skinny_gemm(one, one, None, 3, 4096, 4100, 0, one, None)
     assert rc == -1 and b"K=4100" in lib.dd_last_error()
+    rc = lib.dd_stream_gemm(one, one, None, 257, 4096, 4096, 0, one, one, 1 << 30, None)
+    assert rc == -1 and b"M=257" in lib.dd_last_error()
+    rc = lib.dd_stream_gemm(one, one, None, 64, 4096, 4100, 0, one, one, 1 << 30, None)
+    assert rc == -1 and b"K=4100" in lib.dd_last_error()
+    rc = lib.dd_stream_gemm(one, one, None, 64, 4096, 4096, 0, one, one, 64, None)
+    assert rc == -3 and b"workspace" in lib.dd_last_error()
+    assert lib.dd_stream_gemm_workspace_bytes(64, 4096, 4096, 0) >= 16384
+    assert lib.dd_stream_gemm_workspace_bytes(300, 4096, 4096, 0) == 0
     rc = lib.dd_uncertainty_project(one, one, 1, 9000, 4096, 32064, 5, 0, one, one, one, one, one, 1 << 30, None)
     assert rc == -1 and b"n_vis=9000" in lib.dd_last_error()
     rc = lib.dd_aggregate(one, 1, 17, 100, 100, 0, one, one, one, None, None)

@@ -114,11 +114,13 @@ def test_uncertainty_stage_and_first_token(tiny, cuda):
     assert int(eng.cur_token[0]) == tr.tokens[0]
 
 
-@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "cuda_graph"])
-def test_ensemble_decode_bit_exact(tiny, cuda, use_graph):
+@pytest.mark.parametrize("use_graph,gemm", [(False, "auto"), (True, "auto"), (False, "stream"), (True, "stream")],
+                         ids=["eager", "cuda_graph", "eager_tcgen05_gemm", "cuda_graph_tcgen05_gemm"])
+def test_ensemble_decode_bit_exact(tiny, cuda, use_graph, gemm):
     """Teacher-forced at the sampler inputs (oracle epi / top-k table, so that a 1e-6 difference in
-    epi cannot move a draw across its threshold); everything downstream is the CUDA path."""
-    eng = make_engine(tiny, cuda)
+    epi cannot move a draw across its threshold); everything downstream is the CUDA path.  gemm="stream" runs every
+    weight GEMM of both passes through dd_stream_gemm (tcgen05, stream-K) instead of dd_skinny_gemm."""
+    eng = make_engine(tiny, cuda, gemm_backend=gemm)
     tr = tiny["trace"]
     inject_oracle_prefill(eng, tiny, cuda)
     eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda))
@@ -206,6 +208,27 @@ def test_batch_is_independent_of_batch_size(tiny, cuda):
     torch.cuda.synchronize()
     for b in range(3):
         assert eng.generated()[b].tolist() == tr.tokens[:11]
+
+
+def test_batch_of_eight_runs_the_masked_pass_on_the_tcgen05_gemm(tiny, cuda):
+    """B=8 -> 8 rows in the preliminary pass (dd_skinny_gemm) and 24 in the masked pass (dd_stream_gemm by default):
+    every sequence still generates the B=1 oracle tokens."""
+    tr = tiny["trace"]
+    B = 8
+    eng = tiny["Engine"](tiny["weights"], batch=B, n_vis=TINY_N_VIS, max_seq=640, probs=TINY_PROBS,
+                         mode="cumulative", topk=5, seed=24, max_steps=64)
+    assert eng._use_stream(B * 3) and not eng._use_stream(B)
+    k = torch.stack(tr.prefill_cache.k)[:, None].expand(-1, B, -1, -1, -1)
+    v = torch.stack(tr.prefill_cache.v)[:, None].expand(-1, B, -1, -1, -1)
+    eng.load_prefill(k, v, [TINY_VIS_START] * B)
+    eng.set_uniforms(tiny["U"][:, None].expand(-1, B, -1, -1).contiguous())
+    eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda).expand(B, -1))
+    eng.topk_ids.copy_(tr.topk_ids.to(cuda).int().expand(B, -1, -1))
+    eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None].expand(B, -1).contiguous())
+    eng.decode(12, use_graph=True)
+    torch.cuda.synchronize()
+    for b in range(B):
+        assert eng.generated()[b].tolist() == tr.tokens[:13]
 
 
 # ---------------------------------------------------------------------------------------------

@@ -270,6 +270,58 @@ def test_skinny_gemm_exact_small_integers(ops, cuda):
     assert torch.equal(y.cpu(), x @ w.T)
 
 
+@pytest.mark.parametrize("M,N,K", [(64, 4096, 4096), (192, 12288, 4096), (192, 4096, 11008), (33, 1024, 512),
+                                   (256, 768, 256), (24, 32064, 256), (17, 2048, 4096), (100, 32064, 1024),
+                                   (1, 256, 64), (192, 22016, 4096)])
+def test_stream_gemm_all_epilogues(ops, cuda, M, N, K):
+    """tcgen05 weight-streaming GEMM (dd_stream_gemm) vs an fp64 restatement with the HF rounding points; the
+    shapes cover whole tiles, stream-K splits (few tiles, long K), a ragged last tile (32064 = 250.5 groups),
+    row padding (M % 16 != 0) and the single-unit grid."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = r16(torch.randn(M, K, generator=g))
+    w = r16(torch.randn(N, K, generator=g) / math.sqrt(K))
+    res = r16(torch.randn(M, N, generator=g))
+    acc = (x.double() @ w.double().T).float()
+    xg, wg, rg = x.to(cuda).bfloat16(), w.to(cuda).bfloat16(), res.to(cuda).bfloat16()
+    tol = 2 ** -7
+    ws = ops.stream_gemm_workspace(M, [(N, K, ops.EPI_NONE), (N // 2, K, ops.EPI_SWIGLU)] if N % 256 == 0
+                                   else [(N, K, ops.EPI_NONE)], cuda)
+
+    def close(got, want):
+        assert (got.float().cpu() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+
+    for _ in range(2):      # the second round runs on the counters the first one left behind
+        close(ops.stream_gemm(xg, wg, workspace=ws), r16(acc))
+        close(ops.stream_gemm(xg, wg, ops.EPI_RESIDUAL, residual=rg, workspace=ws), r16(r16(acc) + res))
+        y32 = ops.stream_gemm(xg, wg, ops.EPI_F32, workspace=ws)
+        assert y32.dtype == torch.float32
+        close(y32, r16(acc))
+        if N % 256 == 0:
+            gate, up = r16(acc[:, :N // 2]), r16(acc[:, N // 2:])
+            close(ops.stream_gemm(xg, wg, ops.EPI_SWIGLU, workspace=ws), r16(r16(torch.nn.functional.silu(gate)) * up))
+    assert int(ws[:16384].view(torch.int32).abs().sum()) == 0       # counters re-armed
+
+
+def test_stream_gemm_exact_and_deterministic(ops, cuda):
+    """Integer-valued inputs: every product and partial sum is exact, so a descriptor / swizzle / split-reduction
+    mistake is a wrong integer.  Random inputs: two runs agree bit for bit (fixed reduction order), and the result
+    equals dd_skinny_gemm's up to fp32 summation order."""
+    g = torch.Generator().manual_seed(3)
+    for M, N, K in ((40, 384, 512), (192, 4096, 4096), (20, 640, 11008)):
+        x = torch.randint(-3, 4, (M, K), generator=g).float()
+        w = torch.randint(-3, 4, (N, K), generator=g).float()
+        y = ops.stream_gemm(x.to(cuda).bfloat16(), w.to(cuda).bfloat16(), ops.EPI_F32)
+        want = (x @ w.T)
+        assert torch.equal(y.cpu(), want.to(torch.bfloat16).float()), (M, N, K)
+    x = torch.randn(24, 4096, generator=g).to(cuda).bfloat16()
+    w = (torch.randn(4096, 4096, generator=g) / 64).to(cuda).bfloat16()
+    a = ops.stream_gemm(x, w, ops.EPI_F32)
+    b = ops.stream_gemm(x, w, ops.EPI_F32)
+    assert torch.equal(a, b)
+    c = ops.skinny_gemm(x, w, ops.EPI_F32)
+    assert (a - c).abs().max().item() <= 2 ** -7 * max(1.0, c.abs().max().item())
+
+
 def test_rmsnorm_rope_embed(ops, cuda):
     g = torch.Generator().manual_seed(2)
     M, d = 6, 4096

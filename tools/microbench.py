@@ -101,6 +101,55 @@ def bench_gemm():
                               frac_hbm=round(algo / med / 1e9 / HBM, 3), cublas_us=round(tmed * 1e6, 2), peak=SRC)))
 
 
+def bench_stream_gemm():
+    """dd_stream_gemm (tcgen05, stream-K) at the batched-pass shapes of LLaVA-1.5-7B: rows = 24 (B=8, K=3),
+    64 / 192 (B=64: preliminary / masked pass); library GEMM and (M <= 32) dd_skinny_gemm beside it."""
+    shapes = [(12288, 4096, ops.EPI_NONE), (4096, 4096, ops.EPI_RESIDUAL), (22016, 4096, ops.EPI_SWIGLU),
+              (4096, 11008, ops.EPI_RESIDUAL), (32064, 4096, ops.EPI_F32)]
+    quick = os.environ.get("DD_SG_QUICK")
+    for M in ((192,) if quick else (24, 64, 192)):
+        for (N, K, epi) in (shapes[:2] if quick else shapes):
+            x = torch.randn(M, K, device=dev).bfloat16()
+            R = max(2, -(-(400 << 20) // (N * K * 2)))      # rotate over > 3 x L2 worth of weight copies
+            wr = [(torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16() for _ in range(R)]
+            w = wr[0]
+            Nout = N // 2 if epi == ops.EPI_SWIGLU else N
+            res = torch.randn(M, Nout, device=dev).bfloat16()
+            out = torch.empty(M, Nout, dtype=torch.float32 if epi == ops.EPI_F32 else torch.bfloat16, device=dev)
+            ws = ops.stream_gemm_workspace(M, [(Nout, K, epi)], dev)
+
+            def burst(f, reps=3):
+                """R launches over rotating weight copies captured in one CUDA graph, replayed: us per launch
+                (no host gaps, no L2 reuse of the weights)"""
+                for wi in wr:
+                    f(wi)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for wi in wr:
+                        f(wi)
+                g.replay()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    g.replay()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) * 1e-3 / (R * reps)
+
+            med = best = burst(lambda wi: ops.stream_gemm(x, wi, epi, residual=res, out=out, workspace=ws))
+            tout = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            tmed = burst(lambda wi: torch.matmul(x, wi.T, out=tout))
+            rec = dict(kernel="stream_gemm", dbg=os.environ.get("DD_SG_DBG", "0"), M=M, N=N, K=K, epi=epi, us=round(med * 1e6, 2),
+                       GBps=round(N * K * 2 / med / 1e9, 1), frac_hbm=round(N * K * 2 / med / 1e9 / HBM, 3),
+                       cublas_us=round(tmed * 1e6, 2), peak=SRC, timing="CUDA-graph replay of launches over rotating weight copies")
+            if M <= 32:
+                smed = burst(lambda wi: ops.skinny_gemm(x, wi, epi, residual=res, out=out))
+                rec["skinny_us"] = round(smed * 1e6, 2)
+            print(json.dumps(rec), flush=True)
+
+
 def bench_uncertainty(only_first=False):
     cases = [(1, 576, 4096, 32064, 5), (4, 576, 4096, 32064, 5), (8, 576, 4096, 32064, 5), (32, 32, 4096, 32001, 10)]
     for (n_img, n_vis, d, V, k) in cases[:1] if only_first else cases:
@@ -140,6 +189,15 @@ def one_shot(which):
         bm = torch.randint(-2 ** 31, 2 ** 31 - 1, (B, M, 18), dtype=torch.int32, device=dev)
         for _ in range(3):
             ops.decode_attention(q, kn, vn, kc, vc, sl, vs, bm, 576, 1 / math.sqrt(D), 1)
+    elif which == "sgemm1":
+        for (M, N, K, epi) in [(192, 12288, 4096, ops.EPI_NONE), (192, 4096, 4096, ops.EPI_NONE),
+                               (192, 22016, 4096, ops.EPI_SWIGLU), (192, 4096, 11008, ops.EPI_NONE),
+                               (64, 12288, 4096, ops.EPI_NONE), (24, 12288, 4096, ops.EPI_NONE)]:
+            x = torch.randn(M, K, device=dev).bfloat16()
+            w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+            for _ in range(2):
+                flush_l2()
+                ops.stream_gemm(x, w, epi)
     elif which == "gemm1":
         for (M, N, K, epi) in [(3, 4096, 4096, ops.EPI_NONE), (3, 12288, 4096, ops.EPI_NONE),
                                (3, 22016, 4096, ops.EPI_SWIGLU), (3, 4096, 11008, ops.EPI_NONE)]:
@@ -153,7 +211,7 @@ def one_shot(which):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which in ("uncertainty1", "attention64", "gemm1"):
+    if which in ("uncertainty1", "attention64", "gemm1", "sgemm1"):
         with torch.no_grad():
             one_shot(which)
         sys.exit(0)
@@ -162,6 +220,8 @@ if __name__ == "__main__":
             bench_attention()
         if which in ("gemm", "all"):
             bench_gemm()
+        if which in ("stream_gemm", "all"):
+            bench_stream_gemm()
         if which in ("uncertainty", "all"):
             bench_uncertainty()
         if which == "uncertainty_first":
