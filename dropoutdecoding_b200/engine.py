@@ -227,8 +227,14 @@ class DropoutDecodeEngine:
         rows = B * M
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         bf = dict(dtype=torch.bfloat16, device=dev)
-        target_ctas = 2 * torch.cuda.get_device_properties(dev).multi_processor_count
-        splits = max(1, min(-(-target_ctas // (B * Hkv)), max(1, est_seq // 128), 32))
+        # split-KV factor (measured sweep, profiles/README.md 2): about one CTA per SM, never fewer than ~3 key tiles
+        # per CTA; (sequence, kv head) pairs that already fill the SMs stay unsplit (B >= 5 at 32 kv heads), and a
+        # long context on fewer pairs than SMs is cut at least in two so that two CTAs share an SM
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        pairs, tiles = B * Hkv, max(1, -(-est_seq // 64))
+        splits = max(1, min(int(sms / pairs + 0.5), max(1, tiles // 3), 32))
+        if splits == 1 and pairs < sms and tiles >= 16:
+            splits = 2
         return _PassBuffers(
             M=M, x=torch.empty(rows, cfg.d_model, **bf), x2=torch.empty(rows, cfg.d_model, **bf),
             xn=torch.empty(rows, cfg.d_model, **bf), qkv=torch.empty(rows, (H + 2 * Hkv) * D, **bf),

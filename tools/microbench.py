@@ -80,6 +80,52 @@ def bench_attention():
                               frac_hbm=round(algo / med / 1e9 / HBM, 3), peak=SRC)))
 
 
+def bench_attention_sweep():
+    """num_splits sweep at small / medium batch (CUDA-graph replay of 8 calls over rotating caches)."""
+    for (B, M, H, H_kv, D, S, n_vis) in [(1, 3, 32, 32, 128, 849, 576), (1, 1, 32, 32, 128, 849, 0),
+                                         (8, 3, 32, 32, 128, 849, 576), (8, 1, 32, 32, 128, 849, 0),
+                                         (16, 3, 32, 32, 128, 849, 576), (2, 8, 32, 8, 128, 3000, 2880),
+                                         (16, 8, 32, 8, 128, 3000, 2880)]:
+        S_max = S + 8
+        q = torch.randn(B, M, H, D, device=dev).bfloat16()
+        kn = torch.randn(B, M, H_kv, D, device=dev).bfloat16()
+        vn = torch.randn_like(kn)
+        R = max(2, -(-(300 << 20) // (2 * B * H_kv * S_max * D * 2)))
+        R = min(R, 64)
+        kcs = [torch.randn(B, H_kv, S_max, D, device=dev).bfloat16() for _ in range(R)]
+        vcs = [torch.randn(B, H_kv, S_max, D, device=dev).bfloat16() for _ in range(R)]
+        sl = torch.full((B,), S, dtype=torch.int32, device=dev)
+        vs = torch.full((B,), 5, dtype=torch.int32, device=dev)
+        bm = None
+        if n_vis:
+            bm = torch.randint(-2 ** 31, 2 ** 31 - 1, (B, M, ops.mask_words(n_vis)), dtype=torch.int32, device=dev)
+        out = torch.empty_like(q)
+        algo = 2 * S * H_kv * D * 2 * B + 2 * M * H * D * 2 * B + (M * ((n_vis + 7) // 8) * B)
+        res = {}
+        for splits in (1, 2, 3, 4, 6, 8, 12, 16, 24):
+            if splits > max(1, S // 64):
+                continue
+            ws = ops.attention_workspace(B, M, H, D, splits, dev)
+
+            def run():
+                for kc, vc in zip(kcs, vcs):
+                    ops.decode_attention(q, kn, vn, kc, vc, sl, vs, bm, n_vis, 1 / math.sqrt(D), splits, out, ws)
+            run(); torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+            g.replay(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                g.replay()
+            b.record(); torch.cuda.synchronize()
+            res[splits] = round(a.elapsed_time(b) * 1e3 / (3 * R), 2)
+        best = min(res, key=res.get)
+        print(json.dumps(dict(kernel="decode_attention sweep", B=B, M=M, H_kv=H_kv, S=S, us_by_splits=res, best_splits=best,
+                              best_frac_hbm=round(algo / (res[best] * 1e-6) / 1e9 / HBM, 3))), flush=True)
+
+
 def bench_gemm():
     for (M, N, K, epi) in [(1, 4096, 4096, ops.EPI_NONE), (3, 4096, 4096, ops.EPI_NONE), (1, 12288, 4096, ops.EPI_NONE),
                            (3, 12288, 4096, ops.EPI_NONE), (3, 22016, 4096, ops.EPI_SWIGLU),
@@ -218,6 +264,8 @@ if __name__ == "__main__":
     with torch.no_grad():
         if which in ("attention", "all"):
             bench_attention()
+        if which == "attention_sweep":
+            bench_attention_sweep()
         if which in ("gemm", "all"):
             bench_gemm()
         if which in ("stream_gemm", "all"):
