@@ -165,7 +165,7 @@ def run_ours(args):
         for _ in range(args.warmup):
             hot_path()
         torch.cuda.synchronize()
-        launches_per_ens_step = eng.launches_per_step
+        eng.launch_count = eng.n_spec_steps = eng.n_fallbacks = 0
 
         def barrier():
             if dist is not None:
@@ -184,6 +184,11 @@ def run_ours(args):
         dt = e0.elapsed_time(e1) * 1e-3
         clk = clocks.stop()
         tokens_check = eng.generated().clone()
+        ens_launches = eng.launch_count          # kernels of libdropdec launched by the timed ensemble steps
+        spec = {"mode": "speculative single pass (K+1 contexts per weight stream; masked pass re-run only when y_init "
+                        "restores a drawn visual token)" if eng.spec_active else "two passes per token",
+                "steps": eng.n_spec_steps, "fallback_steps": eng.n_fallbacks,
+                "fallback_rate": round(eng.n_fallbacks / max(1, eng.n_spec_steps), 4)}
 
         # ---- e2e: the public API, host tensors in, host tokens out ---------------------------------
         for _ in range(max(1, args.warmup - 1)):
@@ -222,7 +227,7 @@ def run_ours(args):
         "e2e": {"value": round(total_tokens / dt_e2e, 2), "unit": "tokens/s",
                 "h2d_bytes_per_step": int(ids_h.numel() * ids_h.element_size() + px_h.numel() * px_h.element_size()),
                 "d2h_bytes_per_step": int(out.numel() * out.element_size())},
-        "gpu_launches": int(args.steps * ((T - 1) * launches_per_ens_step + 6)),
+        "gpu_launches": int(ens_launches + args.steps * 6), "decode_schedule": spec,
         "prefill_ms": round(prefill_ms, 2),
         "ms_per_token": round(dt / args.steps / T * 1e3, 4),
         "clocks": clk, "roofline": roof, "stage_rooflines": stages,

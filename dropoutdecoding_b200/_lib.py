@@ -39,6 +39,7 @@ _SIGNATURES = {
     "dd_commit_winner": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, _P]),
     "dd_aggregate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "dd_aggregate_strided": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, _P, _P, _P, _P, _P]),
     "dd_token_stats": (C.c_int, [_P, C.c_longlong, C.c_longlong, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "dd_rmsnorm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "dd_skinny_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -33,7 +33,8 @@ __device__ __forceinline__ ArgMax block_argmax(ArgMax x, ArgMax* s_warp) {
 }
 
 __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __restrict__ logits, int K,
-                                                                int V, int ld, int mode, int32_t* member_ids,
+                                                                int V, int ld, long long seq_stride, int mode,
+                                                                int32_t* member_ids,
                                                                 int32_t* winner, int32_t* token,
                                                                 float* out_logits) {
   __shared__ ArgMax s_warp[kAggThreads / 32];
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __r
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* base = logits + (size_t)b * K * ld;
+  const float* base = logits + (size_t)b * seq_stride;
   const bool vec = (V % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
 
   for (int m = 0; m < K; ++m) {
@@ -186,16 +187,24 @@ extern "C" int dd_token_stats(const float* logits, long long seq_stride, long lo
   return DD_OK;
 }
 
-extern "C" int dd_aggregate(const float* logits, int B, int K, int V, int ld, int mode, int32_t* member_ids,
-                            int32_t* winner, int32_t* token, float* out_logits, dd_stream_t stream) {
+extern "C" int dd_aggregate_strided(const float* logits, int B, int K, int V, int ld, long long seq_stride, int mode,
+                                    int32_t* member_ids, int32_t* winner, int32_t* token, float* out_logits,
+                                    dd_stream_t stream) {
   using namespace dd;
   DD_CHECK_ARG(logits && winner && token, "dd_aggregate: null pointer");
   DD_CHECK_ARG(K >= 1 && K <= DD_MAX_MEMBERS, "dd_aggregate: K=%d out of [1,%d]", K, DD_MAX_MEMBERS);
   DD_CHECK_ARG(V >= 1 && B >= 0 && ld >= V, "dd_aggregate: bad shape B=%d V=%d ld=%d", B, V, ld);
+  DD_CHECK_ARG(seq_stride >= (long long)K * ld, "dd_aggregate: seq_stride=%lld < K*ld", seq_stride);
   DD_CHECK_ARG(mode == DD_AGG_VOTE || mode == DD_AGG_MEAN, "dd_aggregate: bad mode %d", mode);
   DD_CHECK_ARG(mode != DD_AGG_MEAN || out_logits, "dd_aggregate: mean mode needs out_logits");
   if (B == 0) return DD_OK;
-  DD_LAUNCH_CHAIN(aggregate_kernel, dim3(B), dim3(kAggThreads), 0, (cudaStream_t)stream, logits, K, V, ld, mode,
-                  member_ids, winner, token, out_logits);
+  DD_LAUNCH_CHAIN(aggregate_kernel, dim3(B), dim3(kAggThreads), 0, (cudaStream_t)stream, logits, K, V, ld, seq_stride,
+                  mode, member_ids, winner, token, out_logits);
   return DD_OK;
+}
+
+extern "C" int dd_aggregate(const float* logits, int B, int K, int V, int ld, int mode, int32_t* member_ids,
+                            int32_t* winner, int32_t* token, float* out_logits, dd_stream_t stream) {
+  return dd_aggregate_strided(logits, B, K, V, ld, (long long)K * ld, mode, member_ids, winner, token, out_logits,
+                              stream);
 }

@@ -153,6 +153,7 @@ def make_member_sharded_engine(weights, batch: int, n_vis: int, max_seq: int, pr
             self.world, self.rank = world_size(group), rank_of(group)
             self.K_total = len(probs)
             self.m_lo, self.m_hi = member_slice(self.K_total, self.world, self.rank)
+            kw.setdefault("speculative", "off")     # members live on different ranks: the reference's two-pass order
             super().__init__(weights, batch, n_vis, max_seq, probs=probs, **kw)
             if self.vote_on != "logits":
                 raise ops.DropDecError("member sharding votes on logits (the InstructBLIP hidden-state vote is not sharded)")

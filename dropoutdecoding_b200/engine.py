@@ -147,7 +147,7 @@ class DropoutDecodeEngine:
                  probs: Sequence[float] = (0.3, 0.5, 0.7), mode: str = "cumulative", keep_relevant: bool = True,
                  topk: int = 5, aggregate: str = "vote", seed: int = 24, max_steps: int = 1024,
                  round_logits: bool = True, est_seq: Optional[int] = None, vote_on: str = "logits",
-                 seq_base: int = 0, gemm_backend: Optional[str] = None):
+                 seq_base: int = 0, gemm_backend: Optional[str] = None, speculative: Optional[str] = None):
         cfg = weights.cfg
         if cfg.d_model % 256 or cfg.d_ff % 256:
             raise ops.DropDecError("engine needs d_model % 256 == 0 and d_ff % 256 == 0")
@@ -213,8 +213,35 @@ class DropoutDecodeEngine:
             self._arange = torch.arange(B, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
+        self.launch_count = 0           # kernels of this library launched by decode() so far (bench.py: gpu_launches)
+        # ---- speculative single pass (see _spec_head): "auto" = on whenever the K+1 contexts of all sequences fit the
+        #      small-batch kernels; DD_SPEC=off|on|auto overrides
+        self.speculative = speculative or os.environ.get("DD_SPEC", "auto")
+        if self.speculative not in ("auto", "on", "off"):
+            raise ValueError(self.speculative)
+        fits = vote_on == "logits" and B * (self.K + 1) <= 32 and (self.K + 1) * (H // Hkv) <= 32 and \
+            self.K + 1 <= 16
+        if self.speculative == "on" and not fits:
+            raise ops.DropDecError("speculative single pass needs vote_on='logits', B*(K+1) <= 32 and (K+1)*H/H_kv <= 32")
+        self._spec_fits = fits
+        self.spec_active = fits and self.speculative != "off"
+        self.n_spec_steps = self.n_fallbacks = 0        # cumulative over the engine's life
+        self._spec_base = (0, 0)                        # counters when the current sequence batch started
+        self._last_src = "pb"
+        self._graphs: Optional[dict] = None
+        if self.spec_active:
+            self.pc = self._alloc_pass(self.K + 1, est)
+            self.spec_draw = torch.zeros(B, self.K, self.words, **i32)
+            self.spec_mask = torch.zeros(B, self.K + 1, self.words, **i32)       # member 0 = the unmasked context
+            self._nm_spec = torch.zeros(B, self.K, **i32)
+            self.member_ids_c = torch.zeros(B, self.K + 1, **i32)
+            self.winner_c = torch.zeros(B, **i32)
+            self._tok_c = torch.zeros(B, **i32)
+            self.winner_p1 = torch.zeros(B, **i32)
+            self.need_fb = torch.zeros(1, **i32)
+            self.need_fb_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._sg_ws = None
-        max_rows = B * self.K
+        max_rows = B * (self.K + 1 if self.spec_active else self.K)
         if any(self._use_stream(r) for r in (B, max_rows)):
             d, dff, qkv_rows = cfg.d_model, cfg.d_ff, (H + 2 * Hkv) * D
             shapes = [(qkv_rows, d, ops.EPI_NONE), (d, H * D, ops.EPI_RESIDUAL), (dff, d, ops.EPI_SWIGLU),
@@ -340,20 +367,32 @@ class DropoutDecodeEngine:
         return pb.logits
 
     # ------------------------------------------------------------------------------------
+    def _step_uniforms(self) -> Optional[torch.Tensor]:
+        if self.uniforms is None:
+            return None
+        # parity mode: this step's pre-drawn numbers (device-side gather keeps the graph static)
+        self._u_step.copy_(self.uniforms.index_select(0, self.step_ctr.long().clamp(max=self.uniforms.shape[0] - 1))[0])
+        return self._u_step
+
+    def _sample(self, u, keep_relevant: bool, out, n_masked) -> None:
+        ops.sample_masks(self.epi, self.topk_ids if keep_relevant else None, self.y_init if keep_relevant else None,
+                         self.probs, mode=self.mode, keep_relevant=keep_relevant, uniforms=u, seed=self.seed, offset=0,
+                         step=self.step_ctr, out=out, n_masked=n_masked, seq_base=self.seq_base)
+        self.launches_per_step += 1
+
     def step(self) -> None:
-        """One ensemble step for every sequence; asynchronous, no host sync, graph-capturable."""
+        """One ensemble step for every sequence as the reference orders it (preliminary pass, masks, K masked
+        contexts, vote, commit); asynchronous, no host sync, graph-capturable."""
         self.launches_per_step = 0
         logits_a = self._forward(self.pa, None)                                    # models/llava.py:294-305
         ops.aggregate(logits_a, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.y_init,
                       vocab=self.cfg.vocab)
-        u = None
-        if self.uniforms is not None:
-            # parity mode: this step's pre-drawn numbers (device-side gather keeps the graph static)
-            self._u_step.copy_(self.uniforms.index_select(0, self.step_ctr.long().clamp(max=self.uniforms.shape[0] - 1))[0])
-            u = self._u_step
-        ops.sample_masks(self.epi, self.topk_ids, self.y_init, self.probs, mode=self.mode,      # :342-346
-                         keep_relevant=self.keep_relevant, uniforms=u, seed=self.seed, offset=0,
-                         step=self.step_ctr, out=self.bitmask, n_masked=self.n_masked, seq_base=self.seq_base)
+        self.launches_per_step += 1
+        self._sample(self._step_uniforms(), self.keep_relevant, self.bitmask, self.n_masked)      # :342-346
+        self._masked_pass_and_commit()
+
+    def _masked_pass_and_commit(self) -> None:
+        """K masked contexts with self.bitmask, aggregation, commit of the winner's K/V rows, step bookkeeping."""
         if self.vote_on == "logits":
             logits_b = self._forward(self.pb, self.bitmask)                        # :350-359
             ops.aggregate(logits_b, self.aggregate, member_ids=self.member_ids, winner=self.winner,   # :361
@@ -370,7 +409,7 @@ class DropoutDecodeEngine:
             self._linear(self._win_h, self.w.lm_head_padded, ops.EPI_F32, self.pa.logits.view(B, self.Vp))
             ops.aggregate(self.pa.logits, "vote", member_ids=self.member_ids_a, winner=self.winner_a,
                           token=self.next_token, vocab=self.cfg.vocab)
-            self.launches_per_step += 4
+            self.launches_per_step += 2
         # a13: 1/max, entropy, varentropy of the logits this step returns (llavanext.py:584, instructblip.py:141-144)
         if self.vote_on == "hidden":
             ops.token_stats(self.pa.logits, self.cfg.vocab, self.token_stats, slot=self.step_ctr, slot_offset=1)
@@ -382,18 +421,105 @@ class DropoutDecodeEngine:
         ops.commit_winner(self.pb.k_new, self.pb.v_new, self.winner, self.seq_lens, self.k_cache, self.v_cache)
         ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
         self.cur_token.copy_(self.next_token)
-        self.launches_per_step += 7
+        self.launches_per_step += 4
+
+    # ------------------------------------------------------------------------------------
+    # Speculative single pass.  The reference needs the preliminary forward only for y_init = argmax(unmasked
+    # logits), and y_init enters the masks only through the relevant set S = {i : y_init in topk_ids[i]} whose
+    # tokens are un-dropped (models/llava.py:443-482, 657-660).  The draws themselves do not depend on y_init.  So
+    # one pass runs K+1 contexts at once -- row 0 unmasked, rows 1..K with the draws as if S restored nothing -- at
+    # the cost of one weight stream instead of two.  y_init then comes out of row 0, the real masks are sampled, and
+    # if they equal the speculated ones (S empty, or none of its tokens was drawn: the common case) rows 1..K ARE
+    # the reference's K masked forwards, bit for bit.  Otherwise the masked pass is re-run with the real masks
+    # (the reference's own order).  The one host decision per token replaces the reference's >= 3K syncs.
+    # ------------------------------------------------------------------------------------
+    def _spec_head(self) -> None:
+        self.launches_per_step = 0
+        u = self._step_uniforms()
+        self._sample(u, False, self.spec_draw, self._nm_spec)
+        self.spec_mask[:, 1:].copy_(self.spec_draw)
+        logits_c = self._forward(self.pc, self.spec_mask)
+        ops.aggregate(logits_c, "vote", member_ids=self.member_ids_c, winner=self.winner_c, token=self._tok_c,
+                      vocab=self.cfg.vocab)                                        # per-row argmax of all K+1 contexts
+        self.launches_per_step += 1
+        self.y_init.copy_(self.member_ids_c[:, 0])
+        if self.keep_relevant:
+            self._sample(u, True, self.bitmask, self.n_masked)                     # the reference's masks
+            self.need_fb.copy_((self.bitmask != self.spec_draw).any().to(torch.int32).reshape(1))
+        else:                                                                      # epis_no_overlap: nothing to restore
+            self.bitmask.copy_(self.spec_draw)
+            self.n_masked.copy_(self._nm_spec)
+            self.need_fb.zero_()
+        self.need_fb_host.copy_(self.need_fb, non_blocking=True)
+
+    def _spec_fin(self) -> None:
+        """The speculated masks were the real ones: rows 1..K of the speculative pass are the K members."""
+        self.launches_per_step = 0
+        ops.aggregate(self.pc.logits, self.aggregate, member_ids=self.member_ids, winner=self.winner,
+                      token=self.next_token, out_logits=self.out_logits if self.aggregate == "mean" else None,
+                      vocab=self.cfg.vocab, first_member=1, members=self.K)
+        torch.add(self.winner, 1, out=self.winner_p1)
+        if self.aggregate == "mean":
+            ops.token_stats(self.out_logits, self.cfg.vocab, self.token_stats, slot=self.step_ctr, slot_offset=1)
+        else:
+            ops.token_stats(self.pc.logits, self.cfg.vocab, self.token_stats, member=self.winner_p1, slot=self.step_ctr,
+                            slot_offset=1)
+        ops.commit_winner(self.pc.k_new, self.pc.v_new, self.winner_p1, self.seq_lens, self.k_cache, self.v_cache)
+        ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
+        self.cur_token.copy_(self.next_token)
+        self.launches_per_step += 4
+
+    def _spec_fallback(self) -> None:
+        self.launches_per_step = 0
+        self._masked_pass_and_commit()
+
+    def _spec_step(self, graphs: Optional[dict]) -> None:
+        """One ensemble step through the speculative path; `graphs` = captured pieces or None (eager)."""
+        def run(name, fn):
+            if graphs is not None:
+                graphs[name][0].replay()
+                self.launch_count += graphs[name][1]
+            else:
+                fn()
+                self.launch_count += self.launches_per_step
+        run("head", self._spec_head)
+        torch.cuda.current_stream().synchronize()          # the one host decision of the step
+        self.n_spec_steps += 1
+        if int(self.need_fb_host[0]):
+            self.n_fallbacks += 1
+            self._last_src = "pb"
+            run("fallback", self._spec_fallback)
+        else:
+            self._last_src = "pc"
+            run("fin", self._spec_fin)
 
     def capture(self) -> None:
-        """Warm up once eagerly (restoring the state), then capture one step into a CUDA graph."""
+        """Warm up once eagerly (restoring the state), then capture one step into a CUDA graph (two-pass path) or
+        its three pieces -- speculative pass, finish, fallback -- into three graphs (speculative path)."""
         snap = self._snapshot()
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self.step()
+            if self.spec_active:
+                self._spec_head(); self._spec_fin()
+                self._restore(snap)
+                self._spec_head(); self._spec_fallback()
+            else:
+                self.step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._restore(snap)
+        if self.spec_active:
+            graphs = {}
+            for name, fn in (("head", self._spec_head), ("fin", self._spec_fin), ("fallback", self._spec_fallback)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                graphs[name] = (g, self.launches_per_step)
+            torch.cuda.synchronize()
+            self._restore(snap)
+            self._graphs = graphs
+            return
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.step()
@@ -416,16 +542,28 @@ class DropoutDecodeEngine:
         self.tokens_out.copy_(s["tok"])
 
     def decode(self, n_steps: int, use_graph: bool = True) -> None:
-        """Run n_steps ensemble steps (asynchronously)."""
+        """Run n_steps ensemble steps.  Two-pass path: fully asynchronous.  Speculative path: one stream
+        synchronisation per step (the fallback decision)."""
         if int(self.seq_lens.max()) + n_steps > self.S_max:
             raise ops.DropDecError("decode would overflow the KV cache")
-        if use_graph and self._graph is None:
+        if use_graph and (self._graphs is None if self.spec_active else self._graph is None):
             self.capture()
         for _ in range(n_steps):
-            if use_graph:
+            if self.spec_active:
+                self._spec_step(self._graphs if use_graph else None)
+                # adaptive: when almost every step needs the fallback (a checkpoint whose next token is nearly always
+                # one of the visual tokens' top-k ids, or a large batch), the reference's own order is cheaper
+                n, f = self.n_spec_steps - self._spec_base[0], self.n_fallbacks - self._spec_base[1]
+                if self.speculative == "auto" and n >= 32 and f > 0.8 * n:
+                    self.spec_active = False
+            elif use_graph:
+                if self._graph is None:
+                    self.capture()
                 self._graph.replay()
+                self.launch_count += self.launches_per_step
             else:
                 self.step()
+                self.launch_count += self.launches_per_step
 
     # ------------------------------------------------------------------------------------
     # prefill: library ops (not the hot path, SURVEY.md 8f-3)
@@ -494,15 +632,18 @@ class DropoutDecodeEngine:
         self.tokens_out[:, 0] = self.cur_token
         ops.token_stats(self.pa.logits, self.cfg.vocab, self.token_stats)          # slot 0: the prefill token
         self.step_ctr.zero_()          # ensemble steps done; also the sampler's Philox call index / K
+        # a new batch of sequences: re-arm the speculative schedule and its adaptive switch
+        self.spec_active = self._spec_fits and self.speculative != "off"
+        self._spec_base = (self.n_spec_steps, self.n_fallbacks)
 
     def set_uniforms(self, u: Optional[torch.Tensor]) -> None:
         """Parity mode: u [steps, B, K, n_vis] replaces the Philox draws (step s uses u[s])."""
         if u is None:
             if self.uniforms is not None:
-                self._graph = None          # the captured step reads the uniforms buffer: re-capture without it
+                self._graph = self._graphs = None   # the captured step reads the uniforms buffer: re-capture without it
             self.uniforms = self._u_step = None
             return
-        self._graph = None
+        self._graph = self._graphs = None
         self.uniforms = u.to(self.dev, torch.float32).contiguous()
         self._u_step = torch.empty(self.B, self.K, self.n_vis, dtype=torch.float32, device=self.dev)
 
@@ -514,6 +655,8 @@ class DropoutDecodeEngine:
             return self.out_logits
         if self.vote_on == "hidden":
             return self.pa.logits[:, 0, :V]
+        if self._last_src == "pc":          # the speculative pass was the real one: members are rows 1..K
+            return self.pc.logits[self._rows(), self.winner.long() + 1, :V]
         return self.pb.logits[self._rows(), self.winner.long(), :V]
 
     def _rows(self) -> torch.Tensor:

@@ -160,12 +160,16 @@ def commit_winner(k_new_all: torch.Tensor, v_new_all: torch.Tensor, winner: torc
 def aggregate(logits: torch.Tensor, mode: str = "vote", want_logits: bool = False,
               member_ids: Optional[torch.Tensor] = None, winner: Optional[torch.Tensor] = None,
               token: Optional[torch.Tensor] = None, out_logits: Optional[torch.Tensor] = None,
-              vocab: Optional[int] = None):
+              vocab: Optional[int] = None, first_member: int = 0, members: Optional[int] = None):
     """logits fp32 [B, K, ld] (first `vocab` entries of each row valid; default all) ->
-    (member_ids [B,K], winner [B], token [B], out_logits [B,vocab] | None)."""
+    (member_ids [B,K], winner [B], token [B], out_logits [B,vocab] | None).
+    first_member / members select rows [first_member, first_member + members) of every sequence."""
     L = _lib.load()
     _need(logits, torch.float32, "logits")
-    B, K, ld = logits.shape
+    B, K_all, ld = logits.shape
+    K = K_all - first_member if members is None else members
+    if first_member < 0 or K < 1 or first_member + K > K_all:
+        raise DropDecError("aggregate: member slice out of range")
     V = ld if vocab is None else vocab
     dev = logits.device
     member_ids = torch.empty(B, K, dtype=torch.int32, device=dev) if member_ids is None else member_ids
@@ -173,8 +177,9 @@ def aggregate(logits: torch.Tensor, mode: str = "vote", want_logits: bool = Fals
     token = torch.empty(B, dtype=torch.int32, device=dev) if token is None else token
     if out_logits is None and (want_logits or mode == "mean"):
         out_logits = torch.empty(B, V, dtype=torch.float32, device=dev)
-    check(L.dd_aggregate(_ptr(logits), B, K, V, ld, AGG_VOTE if mode == "vote" else AGG_MEAN, _ptr(member_ids),
-                         _ptr(winner), _ptr(token), _ptr(out_logits), _stream()), "dd_aggregate")
+    check(L.dd_aggregate_strided(logits.data_ptr() + first_member * ld * 4, B, K, V, ld, K_all * ld,
+                                 AGG_VOTE if mode == "vote" else AGG_MEAN, _ptr(member_ids), _ptr(winner), _ptr(token),
+                                 _ptr(out_logits), _stream()), "dd_aggregate")
     return member_ids, winner, token, out_logits
 
 

@@ -155,6 +155,13 @@ int dd_aggregate(const float* logits /* [B, K, ld] */, int B, int K, int V, int 
                  int32_t* member_ids /* [B, K] */, int32_t* winner /* [B] */, int32_t* token /* [B] */,
                  float* out_logits /* [B, V] or NULL */, dd_stream_t stream);
 
+/* The same over a strided view: sequence b's K rows start at logits + b * seq_stride (elements), seq_stride >= K * ld.
+ * Used when the K member rows are a slice of a larger [B, K+1, ld] buffer (speculative single pass: row 0 is the
+ * unmasked preliminary context, rows 1..K the members). */
+int dd_aggregate_strided(const float* logits, int B, int K, int V, int ld, long long seq_stride, int mode,
+                         int32_t* member_ids /* [B, K] */, int32_t* winner /* [B] */, int32_t* token /* [B] */,
+                         float* out_logits /* [B, V] or NULL */, dd_stream_t stream);
+
 /* Per-token bookkeeping the reference keeps on the wrapper (models/llavanext.py:584,593;
  * models/instructblip.py:141-144,154-157; calculate_entropy_varentropy models/llava.py:687-708), computed on the
  * chosen logits row of every sequence without a host sync:

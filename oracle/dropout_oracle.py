@@ -336,6 +336,7 @@ class OracleLM:
 class DecodeTrace:
     tokens: List[int] = field(default_factory=list)           # new tokens, first = unmasked prefill argmax
     y_init: List[int] = field(default_factory=list)           # per ensemble step
+    y_init_top2: List[tuple] = field(default_factory=list)    # per step (id1, logit1, id2, logit2) of the preliminary logits
     relevant: List[List[int]] = field(default_factory=list)   # per step, 0-based visual indices
     dropped: List[List[List[int]]] = field(default_factory=list)   # [step][member] -> sorted indices
     masked_numbers: List[List[int]] = field(default_factory=list)  # models/llava.py:661-662
@@ -414,6 +415,8 @@ def ensemble_steps(lm: OracleLM, cache: OracleCache, tok: int, epis: torch.Tenso
         prelim = lm.logits(lm.forward(x, cache, ones, pos))  # :294-305 (cache mutated, then dropped)
         y0 = int(torch.argmax(prelim[0]).item())
         tr.y_init.append(y0)
+        t2 = torch.topk(prelim[0].reshape(-1), 2)
+        tr.y_init_top2.append((int(t2.indices[0]), float(t2.values[0]), int(t2.indices[1]), float(t2.values[1])))
         rel = relevant_visual_tokens(prelim[None], topk_ids) if keep_relevant else None
         tr.relevant.append([] if rel is None else rel.tolist())
 
