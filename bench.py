@@ -166,6 +166,9 @@ def run_ours(args):
             hot_path()
         torch.cuda.synchronize()
         eng.launch_count = eng.n_spec_steps = eng.n_fallbacks = 0
+        if eng.spec_batch:
+            eng._fb_total.zero_()
+            eng._seq_steps_done = 0
 
         def barrier():
             if dist is not None:
@@ -186,9 +189,8 @@ def run_ours(args):
         tokens_check = eng.generated().clone()
         ens_launches = eng.launch_count          # kernels of libdropdec launched by the timed ensemble steps
         spec = {"mode": "speculative single pass (K+1 contexts per weight stream; masked pass re-run only when y_init "
-                        "restores a drawn visual token)" if eng.spec_active else "two passes per token",
-                "steps": eng.n_spec_steps, "fallback_steps": eng.n_fallbacks,
-                "fallback_rate": round(eng.n_fallbacks / max(1, eng.n_spec_steps), 4)}
+                        "restores a drawn visual token)" if (eng.spec_active or eng.spec_batch) else "two passes per token",
+                "steps": eng.n_spec_steps, "fallback_rate": round(eng.fallback_rate(), 4)}
 
         # ---- e2e: the public API, host tensors in, host tokens out ---------------------------------
         for _ in range(max(1, args.warmup - 1)):

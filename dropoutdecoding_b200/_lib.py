@@ -31,16 +31,23 @@ _SIGNATURES = {
                                          _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "dd_sample_masks": (C.c_int, [_P, _P, C.c_int, _P, C.POINTER(C.c_double), C.c_int, _P, C.c_uint64,
                                   C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
+    "dd_sample_masks_seq": (C.c_int, [_P, _P, C.c_int, _P, C.POINTER(C.c_double), C.c_int, _P, C.c_uint64,
+                                      C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "dd_philox_uniform": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, _P, _P]),
     "dd_attention_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "dd_decode_attention": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P,
                                       C.c_size_t, _P]),
+    "dd_decode_attention_active": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P,
+                                             C.c_size_t, _P]),
     "dd_commit_winner": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, _P]),
     "dd_aggregate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "dd_aggregate_strided": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, _P, _P, _P, _P, _P]),
     "dd_token_stats": (C.c_int, [_P, C.c_longlong, C.c_longlong, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
+    "dd_token_stats_seq": (C.c_int, [_P, C.c_longlong, C.c_longlong, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
+    "dd_step_advance_seq": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int, _P]),
     "dd_rmsnorm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "dd_skinny_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dd_stream_gemm_workspace_bytes": (C.c_size_t, [C.c_int] * 4),

@@ -136,14 +136,16 @@ __device__ __forceinline__ float block_max(float v, float* s_red) {
 __global__ void __launch_bounds__(kAggThreads) token_stats_kernel(const float* __restrict__ logits, long long seq_stride,
                                                                   long long member_stride,
                                                                   const int32_t* __restrict__ member, int V,
-                                                                  const int32_t* __restrict__ slot, int slot_offset,
-                                                                  int n_slots, int B, float* __restrict__ stats) {
+                                                                  const int32_t* __restrict__ slot, int slot_per_seq,
+                                                                  int slot_offset, int n_slots, int B,
+                                                                  float* __restrict__ stats) {
   __shared__ float s_red[kAggThreads / 32];
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int row = (slot ? *slot : 0) + slot_offset;
+  const int row = (slot ? (slot_per_seq ? slot[b] : *slot) : 0) + slot_offset;
   if (row < 0 || row >= n_slots) return;
+  if (member && member[b] < 0) return;  // block-uniform: this sequence's row lives in another buffer
   const float* x = logits + (size_t)b * seq_stride + (size_t)(member ? member[b] : 0) * member_stride;
   float mx = -INFINITY;
   for (int j = tid; j < V; j += kAggThreads) mx = fmaxf(mx, x[j]);
@@ -175,16 +177,28 @@ __global__ void __launch_bounds__(kAggThreads) token_stats_kernel(const float* _
 
 }  // namespace dd
 
-extern "C" int dd_token_stats(const float* logits, long long seq_stride, long long member_stride, const int32_t* member,
-                              int B, int V, const int32_t* slot, int slot_offset, int n_slots, float* stats,
-                              dd_stream_t stream) {
+static int token_stats_impl(const float* logits, long long seq_stride, long long member_stride, const int32_t* member,
+                            int B, int V, const int32_t* slot, int slot_per_seq, int slot_offset, int n_slots,
+                            float* stats, dd_stream_t stream) {
   using namespace dd;
   DD_CHECK_ARG(logits && stats, "dd_token_stats: null pointer");
   DD_CHECK_ARG(B >= 0 && V >= 1 && n_slots >= 1, "dd_token_stats: bad shape B=%d V=%d n_slots=%d", B, V, n_slots);
   if (B == 0) return DD_OK;
   DD_LAUNCH_CHAIN(token_stats_kernel, dim3(B), dim3(kAggThreads), 0, (cudaStream_t)stream, logits, seq_stride,
-                  member_stride, member, V, slot, slot_offset, n_slots, B, stats);
+                  member_stride, member, V, slot, slot_per_seq, slot_offset, n_slots, B, stats);
   return DD_OK;
+}
+
+extern "C" int dd_token_stats(const float* logits, long long seq_stride, long long member_stride, const int32_t* member,
+                              int B, int V, const int32_t* slot, int slot_offset, int n_slots, float* stats,
+                              dd_stream_t stream) {
+  return token_stats_impl(logits, seq_stride, member_stride, member, B, V, slot, 0, slot_offset, n_slots, stats, stream);
+}
+
+extern "C" int dd_token_stats_seq(const float* logits, long long seq_stride, long long member_stride,
+                                  const int32_t* member, int B, int V, const int32_t* slots, int slot_offset, int n_slots,
+                                  float* stats, dd_stream_t stream) {
+  return token_stats_impl(logits, seq_stride, member_stride, member, B, V, slots, 1, slot_offset, n_slots, stats, stream);
 }
 
 extern "C" int dd_aggregate_strided(const float* logits, int B, int K, int V, int ld, long long seq_stride, int mode,

@@ -69,6 +69,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
 struct AttnParams {
   const __nv_bfloat16 *q, *k_cache, *v_cache;
   const int32_t *seq_lens, *vis_start;
+  const int32_t* seq_active;  // [B] or NULL: sequences with 0 are skipped (their output rows stay untouched)
   const uint32_t* bitmask;
   float *part_o, *part_ml;  // [B,H_kv,splits,R,D], [B,H_kv,splits,R,2]
   int* tickets;             // [B,H_kv] zero on entry, zero again on exit
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
   const int G = p.H / p.H_kv, R = p.M * G;
   pdl_trigger_stream_entry();
   pdl_wait();
+  if (p.seq_active && p.seq_active[b] == 0) return;  // CTA-uniform: nothing of this sequence is read
   const int S = p.seq_lens[b];
   const int vis0 = p.vis_start ? p.vis_start[b] : 0;
   const int vis1 = p.bitmask ? vis0 + p.n_vis : vis0;  // empty span when unmasked
@@ -384,6 +386,7 @@ __global__ void __launch_bounds__(D) attn_merge_kernel(const AttnParams p) {
   pdl_trigger();
   pdl_wait();
   const int h = blockIdx.x, m = blockIdx.y, b = blockIdx.z, d = threadIdx.x;
+  if (p.seq_active && p.seq_active[b] == 0) return;
   const int G = p.H / p.H_kv, hkv = h / G, r = m * G + (h % G), R = p.M * G;
   const size_t qoff = (((size_t)b * p.M + m) * p.H + h) * D;
   const size_t kvoff = (((size_t)b * p.M + m) * p.H_kv + hkv) * D;
@@ -450,6 +453,17 @@ extern "C" int dd_decode_attention(const void* q, const void* k_new, const void*
                                    const uint32_t* bitmask, int B, int M, int H, int H_kv, int D, int S_max,
                                    int n_vis, int mask_words, float scale, int num_splits, void* out,
                                    void* workspace, size_t workspace_bytes, dd_stream_t stream) {
+  return dd_decode_attention_active(q, k_new, v_new, k_cache, v_cache, seq_lens, vis_start, bitmask, nullptr, B, M, H,
+                                    H_kv, D, S_max, n_vis, mask_words, scale, num_splits, out, workspace,
+                                    workspace_bytes, stream);
+}
+
+extern "C" int dd_decode_attention_active(const void* q, const void* k_new, const void* v_new, const void* k_cache,
+                                          const void* v_cache, const int32_t* seq_lens, const int32_t* vis_start,
+                                          const uint32_t* bitmask, const int32_t* seq_active, int B, int M, int H,
+                                          int H_kv, int D, int S_max, int n_vis, int mask_words, float scale,
+                                          int num_splits, void* out, void* workspace, size_t workspace_bytes,
+                                          dd_stream_t stream) {
   using namespace dd;
   DD_CHECK_ARG(q && k_new && v_new && k_cache && v_cache && seq_lens && out && workspace,
                "dd_decode_attention: null pointer");
@@ -472,7 +486,7 @@ extern "C" int dd_decode_attention(const void* q, const void* k_new, const void*
   if (B == 0) return DD_OK;
   AttnParams p{};
   p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
-  p.seq_lens = seq_lens; p.vis_start = vis_start; p.bitmask = bitmask;
+  p.seq_lens = seq_lens; p.vis_start = vis_start; p.bitmask = bitmask; p.seq_active = seq_active;
   p.part_o = (float*)workspace;
   p.part_ml = p.part_o + (size_t)B * M * H * num_splits * D;
   p.tickets = reinterpret_cast<int*>(p.part_ml + (size_t)B * M * H * num_splits * 2);

@@ -103,6 +103,21 @@ __global__ void step_advance_kernel(const int32_t* __restrict__ token, int32_t* 
   if (threadIdx.x == 0) *step = st + 1;
 }
 
+// per-sequence progress (asynchronous batch schedule): only sequences with advance[b] != 0 move on
+__global__ void step_advance_seq_kernel(const int32_t* __restrict__ token, const int32_t* __restrict__ advance,
+                                        int32_t* tokens_out, int max_steps, int32_t* seq_lens, int32_t* seq_steps,
+                                        int B) {
+  pdl_trigger();
+  pdl_wait();
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    if (!advance[b]) continue;
+    const int st = seq_steps[b];
+    if (tokens_out && st + 1 < max_steps) tokens_out[(size_t)b * max_steps + st + 1] = token[b];
+    seq_lens[b] += 1;
+    seq_steps[b] = st + 1;
+  }
+}
+
 // winner's new-token K/V rows of every layer -> cache row seq_lens[b].  grid (L, B), 16B per thread.
 __global__ void commit_winner_kernel(const uint4* __restrict__ k_new, const uint4* __restrict__ v_new,
                                      const int32_t* __restrict__ winner, const int32_t* __restrict__ seq_lens,
@@ -112,7 +127,7 @@ __global__ void commit_winner_kernel(const uint4* __restrict__ k_new, const uint
   pdl_wait();
   const int l = blockIdx.x, b = blockIdx.y;
   const int w = winner[b], pos = seq_lens[b];
-  if (pos >= S_max) return;
+  if (pos >= S_max || w < 0) return;  // w < 0: this sequence commits from another staging buffer
   const size_t src = (((size_t)l * B + b) * M + w) * H_kv * dvec;
   for (int idx = threadIdx.x; idx < H_kv * dvec; idx += blockDim.x) {
     const int h = idx / dvec, j = idx % dvec;
@@ -165,6 +180,16 @@ extern "C" int dd_step_advance(const int32_t* token, int32_t* tokens_out, int ma
   if (B == 0) return DD_OK;
   DD_LAUNCH_CHAIN(step_advance_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, token, tokens_out, max_steps,
                   seq_lens, step, B);
+  return DD_OK;
+}
+
+extern "C" int dd_step_advance_seq(const int32_t* token, const int32_t* advance, int32_t* tokens_out, int max_steps,
+                                   int32_t* seq_lens, int32_t* seq_steps, int B, dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(token && advance && seq_lens && seq_steps, "dd_step_advance_seq: null pointer");
+  if (B == 0) return DD_OK;
+  DD_LAUNCH_CHAIN(step_advance_seq_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, token, advance, tokens_out,
+                  max_steps, seq_lens, seq_steps, B);
   return DD_OK;
 }
 

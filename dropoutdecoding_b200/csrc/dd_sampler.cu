@@ -18,6 +18,7 @@ struct SamplerParams {
   const int32_t* y_init;
   const float* uniforms;
   const int32_t* step;
+  int step_per_seq;  // step points at [B] per-sequence counters instead of one scalar
   uint32_t* bitmask;
   int32_t* n_masked;
   uint64_t seed, offset0;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kSamplerThreads) sampler_kernel(const SamplerP
     __syncthreads();
   }
 
-  const int step = p.step ? *p.step : 0;
+  const int step = p.step ? (p.step_per_seq ? p.step[blockIdx.x] : *p.step) : 0;
   uint32_t cumulative = 0;  // bit c: token c*256+tid drawn by this or an earlier member
   for (int m = 0; m < p.K; ++m) {
     float thr = 0.f;
@@ -186,11 +187,11 @@ __global__ void philox_uniform_kernel(uint64_t seed, uint64_t offset, int n, flo
 
 }  // namespace dd
 
-extern "C" int dd_sample_masks(const float* epi, const int32_t* topk_ids, int topk, const int32_t* y_init,
-                               const double* probs_host, int K, const float* uniforms, uint64_t seed,
-                               uint64_t offset0, const int32_t* step, int mode, int keep_relevant, int B,
-                               int n_vis, int seq_base, uint32_t* bitmask, int mask_words, int32_t* n_masked,
-                               dd_stream_t stream) {
+static int sample_masks_impl(const float* epi, const int32_t* topk_ids, int topk, const int32_t* y_init,
+                             const double* probs_host, int K, const float* uniforms, uint64_t seed,
+                             uint64_t offset0, const int32_t* step, int step_per_seq, int mode, int keep_relevant,
+                             int B, int n_vis, int seq_base, uint32_t* bitmask, int mask_words, int32_t* n_masked,
+                             dd_stream_t stream) {
   using namespace dd;
   DD_CHECK_ARG(epi && bitmask && probs_host, "dd_sample_masks: null pointer");
   DD_CHECK_ARG(K >= 1 && K <= DD_MAX_MEMBERS, "dd_sample_masks: K=%d out of [1,%d]", K, DD_MAX_MEMBERS);
@@ -203,7 +204,7 @@ extern "C" int dd_sample_masks(const float* epi, const int32_t* topk_ids, int to
                "dd_sample_masks: keep_relevant needs topk_ids, y_init and 1 <= topk <= %d", DD_MAX_TOPK);
   if (B == 0) return DD_OK;
   SamplerParams p{};
-  p.epi = epi; p.topk_ids = topk_ids; p.y_init = y_init; p.uniforms = uniforms; p.step = step;
+  p.epi = epi; p.topk_ids = topk_ids; p.y_init = y_init; p.uniforms = uniforms; p.step = step; p.step_per_seq = step_per_seq;
   p.bitmask = bitmask; p.n_masked = n_masked; p.seed = seed; p.offset0 = offset0;
   for (int m = 0; m < K; ++m) {
     p.coef[m] = (float)(probs_host[m] - 0.1);  // python double arithmetic, then the fp32 tensor op
@@ -214,6 +215,24 @@ extern "C" int dd_sample_masks(const float* epi, const int32_t* topk_ids, int to
   const size_t smem = mode == DD_MASK_QUANTILE ? (size_t)n_vis * sizeof(float) : 0;
   DD_LAUNCH_CHAIN(sampler_kernel, dim3(B), dim3(kSamplerThreads), smem, (cudaStream_t)stream, p);
   return DD_OK;
+}
+
+extern "C" int dd_sample_masks(const float* epi, const int32_t* topk_ids, int topk, const int32_t* y_init,
+                               const double* probs_host, int K, const float* uniforms, uint64_t seed,
+                               uint64_t offset0, const int32_t* step, int mode, int keep_relevant, int B,
+                               int n_vis, int seq_base, uint32_t* bitmask, int mask_words, int32_t* n_masked,
+                               dd_stream_t stream) {
+  return sample_masks_impl(epi, topk_ids, topk, y_init, probs_host, K, uniforms, seed, offset0, step, 0, mode,
+                           keep_relevant, B, n_vis, seq_base, bitmask, mask_words, n_masked, stream);
+}
+
+extern "C" int dd_sample_masks_seq(const float* epi, const int32_t* topk_ids, int topk, const int32_t* y_init,
+                                   const double* probs_host, int K, const float* uniforms, uint64_t seed,
+                                   uint64_t offset0, const int32_t* seq_steps, int mode, int keep_relevant, int B,
+                                   int n_vis, int seq_base, uint32_t* bitmask, int mask_words, int32_t* n_masked,
+                                   dd_stream_t stream) {
+  return sample_masks_impl(epi, topk_ids, topk, y_init, probs_host, K, uniforms, seed, offset0, seq_steps, 1, mode,
+                           keep_relevant, B, n_vis, seq_base, bitmask, mask_words, n_masked, stream);
 }
 
 // Test hook: the first n uniforms of the (seed, offset) Philox stream, laid out as torch.rand(n)

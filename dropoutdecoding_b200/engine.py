@@ -219,17 +219,39 @@ class DropoutDecodeEngine:
         self.speculative = speculative or os.environ.get("DD_SPEC", "auto")
         if self.speculative not in ("auto", "on", "off"):
             raise ValueError(self.speculative)
-        fits = vote_on == "logits" and B * (self.K + 1) <= 32 and (self.K + 1) * (H // Hkv) <= 32 and \
-            self.K + 1 <= 16
-        if self.speculative == "on" and not fits:
-            raise ops.DropDecError("speculative single pass needs vote_on='logits', B*(K+1) <= 32 and (K+1)*H/H_kv <= 32")
+        ok = vote_on == "logits" and (self.K + 1) * (H // Hkv) <= 32 and self.K + 1 <= 16
+        fits = ok and B * (self.K + 1) <= 32        # small batch: the host decides per step whether to fall back
+        if self.speculative == "on" and not ok:
+            raise ops.DropDecError("speculative single pass needs vote_on='logits' and (K+1)*H/H_kv <= 32")
         self._spec_fits = fits
         self.spec_active = fits and self.speculative != "off"
+        # larger batches: some sequence nearly always needs the fallback, so it always runs -- but its attention
+        # only reads the K/V of the sequences that need it (per-sequence flags on the device, no host decision)
+        self.spec_batch = ok and not fits and self.speculative != "off"
         self.n_spec_steps = self.n_fallbacks = 0        # cumulative over the engine's life
+        self._seq_steps_done = 0
         self._spec_base = (0, 0)                        # counters when the current sequence batch started
         self._last_src = "pb"
         self._graphs: Optional[dict] = None
-        if self.spec_active:
+        if self.spec_batch:
+            V = cfg.vocab
+            self.seq_steps = torch.zeros(B, **i32)          # ensemble steps done, per sequence
+            self.in_fb = torch.zeros(B, **i32)              # 1: the next pass repeats this step with the real masks
+            self.target = torch.zeros(1, **i32)
+            self.active = torch.zeros(B, **i32)
+            self.adv = torch.zeros(B, **i32)
+            self._fb_total = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._mask_tmp = torch.zeros(B, self.K, self.words, **i32)
+            self._mask_real = torch.zeros(B, self.K, self.words, **i32)
+            self._nm_real = torch.zeros(B, self.K, **i32)
+            self._ids_c = torch.zeros(B, self.K, **i32)
+            self._win_c, self._tok_sc = torch.zeros(B, **i32), torch.zeros(B, **i32)
+            self._minus1 = torch.full((B,), -1, **i32)
+            self._zero = torch.zeros(B, **i32)
+            self.ret_logits = torch.zeros(B, V, dtype=torch.float32, device=dev)
+            if aggregate == "mean":
+                self._out_c = torch.zeros(B, V, dtype=torch.float32, device=dev)
+        if self.spec_active or self.spec_batch:
             self.pc = self._alloc_pass(self.K + 1, est)
             self.spec_draw = torch.zeros(B, self.K, self.words, **i32)
             self.spec_mask = torch.zeros(B, self.K + 1, self.words, **i32)       # member 0 = the unmasked context
@@ -241,7 +263,7 @@ class DropoutDecodeEngine:
             self.need_fb = torch.zeros(1, **i32)
             self.need_fb_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._sg_ws = None
-        max_rows = B * (self.K + 1 if self.spec_active else self.K)
+        max_rows = B * (self.K + 1 if (self.spec_active or self.spec_batch) else self.K)
         if any(self._use_stream(r) for r in (B, max_rows)):
             d, dff, qkv_rows = cfg.d_model, cfg.d_ff, (H + 2 * Hkv) * D
             shapes = [(qkv_rows, d, ops.EPI_NONE), (d, H * D, ops.EPI_RESIDUAL), (dff, d, ops.EPI_SWIGLU),
@@ -266,7 +288,7 @@ class DropoutDecodeEngine:
             M=M, x=torch.empty(rows, cfg.d_model, **bf), x2=torch.empty(rows, cfg.d_model, **bf),
             xn=torch.empty(rows, cfg.d_model, **bf), qkv=torch.empty(rows, (H + 2 * Hkv) * D, **bf),
             q=torch.empty(B, M, H, D, **bf), k_new=torch.empty(cfg.n_layers, B, M, Hkv, D, **bf),
-            v_new=torch.empty(cfg.n_layers, B, M, Hkv, D, **bf), attn=torch.empty(B, M, H, D, **bf),
+            v_new=torch.empty(cfg.n_layers, B, M, Hkv, D, **bf), attn=torch.zeros(B, M, H, D, **bf),
             act=torch.empty(rows, cfg.d_ff, **bf), logits=torch.empty(B, M, self.Vp, dtype=torch.float32, device=dev),
             ws=ops.attention_workspace(B, M, H, D, splits, dev), splits=splits)
 
@@ -296,20 +318,22 @@ class DropoutDecodeEngine:
         n = gu.shape[1] // 2
         return torch.mul(F.silu(gu[:, :n]), gu[:, n:], out=out)
 
-    def _forward(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool = True) -> torch.Tensor:
+    def _forward(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool = True,
+                 seq_active: Optional[torch.Tensor] = None) -> torch.Tensor:
         cfg, B, M = self.cfg, self.B, pb.M
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         rows = B * M
         ops.embed_gather(self.w.embed, self.cur_token, M, pb.x)
         x, x2 = pb.x, pb.x2
         if rows <= 32 and not self._use_stream(rows):
-            return self._forward_fused(pb, bitmask, head)
+            return self._forward_fused(pb, bitmask, head, seq_active)
         for l, lw in enumerate(self.w.layers):
             ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pb.xn)
             self._linear(pb.xn, lw["wqkv"], ops.EPI_NONE, pb.qkv)
             ops.rope_stage(pb.qkv, self.cos, self.sin, self.seq_lens, B, M, H, Hkv, D, pb.q, pb.k_new[l], pb.v_new[l])
             ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
-                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws)
+                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws,
+                                 seq_active=seq_active)
             if rows <= 32 and self.gemm_backend == "auto":      # 33 MB o_proj: the skinny kernel is as fast up to 32 rows
                 ops.skinny_gemm(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
                 self.launches_per_step += 1
@@ -325,7 +349,8 @@ class DropoutDecodeEngine:
             self._linear(pb.xn, self.w.lm_head_padded, ops.EPI_F32, pb.logits.view(rows, self.Vp))
         return pb.logits
 
-    def _forward_fused(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool) -> torch.Tensor:
+    def _forward_fused(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool,
+                       seq_active: Optional[torch.Tensor] = None) -> torch.Tensor:
         """<= 32 rows: RoPE + member staging ride in the epilogue of the QKV projection (dd_decoder_linear,
         DD_EPI_ROPE) -- 7 launches per layer.  With fuse_norm the two RMSNorms also move into the prologue of
         the GEMM that consumes them (5 launches per layer); measured slower on B200 because every one of the
@@ -344,7 +369,8 @@ class DropoutDecodeEngine:
                 ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pb.xn)
                 ops.decoder_linear(pb.xn, lw["wqkv"], ops.EPI_ROPE, rope=rope)
             ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
-                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws)
+                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws,
+                                 seq_active=seq_active)
             ops.decoder_linear(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
             if fuse:
                 ops.decoder_linear(x2, lw["wgu"], ops.EPI_SWIGLU, norm_w=lw["ln2"], eps=cfg.rms_eps, out=pb.act)
@@ -374,15 +400,21 @@ class DropoutDecodeEngine:
         self._u_step.copy_(self.uniforms.index_select(0, self.step_ctr.long().clamp(max=self.uniforms.shape[0] - 1))[0])
         return self._u_step
 
-    def _sample(self, u, keep_relevant: bool, out, n_masked) -> None:
+    def _sample(self, u, keep_relevant: bool, out, n_masked, per_seq: bool = False) -> None:
         ops.sample_masks(self.epi, self.topk_ids if keep_relevant else None, self.y_init if keep_relevant else None,
                          self.probs, mode=self.mode, keep_relevant=keep_relevant, uniforms=u, seed=self.seed, offset=0,
-                         step=self.step_ctr, out=out, n_masked=n_masked, seq_base=self.seq_base)
+                         step=self.seq_steps if per_seq else self.step_ctr, out=out, n_masked=n_masked,
+                         seq_base=self.seq_base, step_per_seq=per_seq)
         self.launches_per_step += 1
 
     def step(self) -> None:
-        """One ensemble step for every sequence as the reference orders it (preliminary pass, masks, K masked
-        contexts, vote, commit); asynchronous, no host sync, graph-capturable."""
+        """One ensemble step for every sequence; asynchronous, no host sync, graph-capturable."""
+        if self.spec_batch:
+            return self._spec_batch_step()
+        return self._two_pass_step()
+
+    def _two_pass_step(self) -> None:
+        """The reference's own order: preliminary pass, masks, K masked contexts, vote, commit."""
         self.launches_per_step = 0
         logits_a = self._forward(self.pa, None)                                    # models/llava.py:294-305
         ops.aggregate(logits_a, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.y_init,
@@ -473,6 +505,72 @@ class DropoutDecodeEngine:
         self.launches_per_step = 0
         self._masked_pass_and_commit()
 
+    def _spec_batch_step(self) -> None:
+        """Asynchronous batch schedule (larger batches; no host decision, ONE pass per call): every sequence runs K+1
+        contexts -- row 0 unmasked, rows 1..K with the draws of ITS current step, or, if its previous pass found
+        that y_init restores a drawn token, with the real masks of that step.  A sequence whose rows 1..K carried
+        its real masks votes, commits and advances; the others repeat the step in the next pass.  Sequences are
+        independent (per-sequence step counters key the Philox stream and every per-step buffer), so each one
+        produces exactly the tokens of the two-pass order while the batch pays ~(1 + fallback rate) weight and
+        K/V streams per token instead of two."""
+        self.launches_per_step = 0
+        V, K, mean = self.cfg.vocab, self.K, self.aggregate == "mean"
+        steps = self.seq_steps
+        u = None
+        if self.uniforms is not None:       # parity mode: sequence b uses the pre-drawn numbers of ITS step
+            idx = steps.long().clamp(max=self.uniforms.shape[0] - 1)
+            self._u_step.copy_(self.uniforms[idx, self._rows()])
+            u = self._u_step
+        self._sample(u, False, self.spec_draw, self._nm_spec, per_seq=True)
+        infb = self.in_fb.bool()
+        self._mask_tmp.copy_(torch.where(infb[:, None, None], self.bitmask, self.spec_draw))
+        self.spec_mask[:, 1:].copy_(self._mask_tmp)
+        act = steps < self.target
+        self.active.copy_(act.to(torch.int32))
+        logits_c = self._forward(self.pc, self.spec_mask, seq_active=self.active)
+        ops.aggregate(logits_c, "vote", member_ids=self.member_ids_c, winner=self.winner_c, token=self._tok_c, vocab=V)
+        # y_init / bitmask / n_masked stay what they were for sequences that are waiting at the target (they keep
+        # describing the sequence's last completed step) and for y_init of a sequence that is repeating its step
+        self.y_init.copy_(torch.where(act & ~infb, self.member_ids_c[:, 0], self.y_init))
+        if self.keep_relevant:
+            self._sample(u, True, self._mask_real, self._nm_real, per_seq=True)            # the reference's masks
+            ok = infb | (self._mask_real == self._mask_tmp).flatten(1).all(1)
+        else:                                                                          # epis_no_overlap
+            self._mask_real.copy_(self.spec_draw); self._nm_real.copy_(self._nm_spec)
+            ok = torch.ones_like(infb)
+        self.bitmask.copy_(torch.where(act[:, None, None], self._mask_real, self.bitmask))
+        self.n_masked.copy_(torch.where(act[:, None], self._nm_real, self.n_masked))
+        adv = ok & act
+        self.adv.copy_(adv.to(torch.int32))
+        ops.aggregate(self.pc.logits, self.aggregate, member_ids=self._ids_c, winner=self._win_c, token=self._tok_sc,
+                      out_logits=self._out_c if mean else None, vocab=V, first_member=1, members=K)
+        self.member_ids.copy_(torch.where(adv[:, None], self._ids_c, self.member_ids))
+        self.winner.copy_(torch.where(adv, self._win_c, self.winner))
+        self.next_token.copy_(torch.where(adv, self._tok_sc, self.next_token))
+        self.winner_p1.copy_(torch.where(adv, self._win_c + 1, self._minus1))
+        if mean:
+            self.out_logits.copy_(torch.where(adv[:, None], self._out_c, self.out_logits))
+            ops.token_stats(self._out_c, V, self.token_stats, member=torch.where(adv, self._zero, self._minus1),
+                            slot=steps, slot_offset=1, slot_per_seq=True)
+            self.ret_logits.copy_(self.out_logits)
+        else:
+            ops.token_stats(self.pc.logits, V, self.token_stats, member=self.winner_p1, slot=steps, slot_offset=1,
+                            slot_per_seq=True)
+            rows = self.pc.logits[self._rows(), self.winner_p1.clamp(min=0).long(), :V]
+            self.ret_logits.copy_(torch.where(adv[:, None], rows, self.ret_logits))
+        ops.commit_winner(self.pc.k_new, self.pc.v_new, self.winner_p1, self.seq_lens, self.k_cache, self.v_cache)
+        ops.step_advance_seq(self._tok_sc, self.adv, self.tokens_out, self.seq_lens, steps)
+        self.cur_token.copy_(torch.where(adv, self._tok_sc, self.cur_token))
+        self.in_fb.copy_((~ok & act).to(torch.int32))
+        self._fb_total.add_(self.in_fb.sum())
+        self.launches_per_step += 7
+
+    def fallback_rate(self) -> float:
+        """Fraction of (step, sequence) pairs whose masked pass had to be re-run with the real masks."""
+        if self.spec_batch:         # repeated (step, sequence) pairs / completed ones
+            return float(self._fb_total.item()) / max(1, self._seq_steps_done)
+        return self.n_fallbacks / max(1, self.n_spec_steps)
+
     def _spec_step(self, graphs: Optional[dict]) -> None:
         """One ensemble step through the speculative path; `graphs` = captured pieces or None (eager)."""
         def run(name, fn):
@@ -548,6 +646,8 @@ class DropoutDecodeEngine:
             raise ops.DropDecError("decode would overflow the KV cache")
         if use_graph and (self._graphs is None if self.spec_active else self._graph is None):
             self.capture()
+        if self.spec_batch:
+            return self._decode_async(n_steps, use_graph)
         for _ in range(n_steps):
             if self.spec_active:
                 self._spec_step(self._graphs if use_graph else None)
@@ -556,14 +656,42 @@ class DropoutDecodeEngine:
                 n, f = self.n_spec_steps - self._spec_base[0], self.n_fallbacks - self._spec_base[1]
                 if self.speculative == "auto" and n >= 32 and f > 0.8 * n:
                     self.spec_active = False
-            elif use_graph:
-                if self._graph is None:
-                    self.capture()
-                self._graph.replay()
-                self.launch_count += self.launches_per_step
             else:
-                self.step()
+                if use_graph:
+                    if self._graph is None:
+                        self.capture()
+                    self._graph.replay()
+                else:
+                    self.step()
                 self.launch_count += self.launches_per_step
+
+    def _decode_async(self, n_steps: int, use_graph: bool) -> None:
+        """Passes of the asynchronous batch schedule until every sequence has advanced n_steps: n_steps passes, then
+        as many more as the sequence with the most repeated steps needs (the host looks at the counters between
+        those).  On return all sequences are in lockstep again."""
+        if use_graph and self._graph is None:
+            self.seq_steps.copy_(self.step_ctr.expand(self.B)); self.in_fb.zero_()
+            self.target.copy_(self.step_ctr + 1)
+            self.capture()
+        self.seq_steps.copy_(self.step_ctr.expand(self.B))
+        self.in_fb.zero_()
+        self.target.copy_(self.step_ctr + n_steps)
+
+        def run(k):
+            for _ in range(k):
+                if use_graph:
+                    self._graph.replay()
+                else:
+                    self._spec_batch_step()
+                self.launch_count += self.launches_per_step
+                self.n_spec_steps += 1
+
+        run(n_steps)
+        while not bool((self.seq_steps >= self.target).all()):
+            run(2)
+        self.step_ctr.add_(n_steps)
+        self._seq_steps_done += n_steps * self.B
+        self._last_src = "mixed"
 
     # ------------------------------------------------------------------------------------
     # prefill: library ops (not the hot path, SURVEY.md 8f-3)
@@ -655,6 +783,8 @@ class DropoutDecodeEngine:
             return self.out_logits
         if self.vote_on == "hidden":
             return self.pa.logits[:, 0, :V]
+        if self._last_src == "mixed":       # asynchronous batch schedule: each sequence's own advancing pass
+            return self.ret_logits
         if self._last_src == "pc":          # the speculative pass was the real one: members are rows 1..K
             return self.pc.logits[self._rows(), self.winner.long() + 1, :V]
         return self.pb.logits[self._rows(), self.winner.long(), :V]

@@ -187,7 +187,9 @@ class DropoutDecodingMixin:
         self._publish_uncertainty(eng)
 
         steps_left = max_new_tokens - 1
-        chunk = 16 if eos_token_id is not None else steps_left
+        # EOS is checked between decode calls; the asynchronous batch schedule re-synchronises the sequences at the
+        # end of every call, so it gets longer calls
+        chunk = (64 if eng.spec_batch else 16) if eos_token_id is not None else steps_left
         while steps_left > 0:
             n = min(chunk, steps_left)
             eng.decode(n, use_graph=use_cuda_graph)

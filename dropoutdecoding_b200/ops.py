@@ -72,7 +72,8 @@ def sample_masks(epi: torch.Tensor, topk_ids: Optional[torch.Tensor], y_init: Op
                  probs: Sequence[float], mode: str = "cumulative", keep_relevant: bool = True,
                  uniforms: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
                  step: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                 n_masked: Optional[torch.Tensor] = None, seq_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                 n_masked: Optional[torch.Tensor] = None, seq_base: int = 0,
+                 step_per_seq: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """epi fp32 [B, n_vis] -> (bitmask uint32-as-int32 [B, K, words], n_masked int32 [B, K]).
     seq_base: global index of row 0 (keys the Philox stream, so sharded batches draw the same numbers)."""
     L = _lib.load()
@@ -97,10 +98,11 @@ def sample_masks(epi: torch.Tensor, topk_ids: Optional[torch.Tensor], y_init: Op
     if step is not None:
         _need(step, torch.int32, "step")
     probs_c = (C.c_double * K)(*[float(p) for p in probs])
-    check(L.dd_sample_masks(_ptr(epi), _ptr(topk_ids) if keep_relevant else None, topk,
+    fn = L.dd_sample_masks_seq if step_per_seq else L.dd_sample_masks      # step: [B] counters vs one scalar
+    check(fn(_ptr(epi), _ptr(topk_ids) if keep_relevant else None, topk,
                             _ptr(y_init) if keep_relevant else None, probs_c, K, _ptr(uniforms), seed, offset,
                             _ptr(step), MASK_MODES[mode], int(keep_relevant), B, n_vis, int(seq_base), _ptr(out), out.shape[-1],
-                            _ptr(n_masked), _stream()), "dd_sample_masks")
+             _ptr(n_masked), _stream()), "dd_sample_masks")
     return out, n_masked
 
 
@@ -121,8 +123,10 @@ def attention_workspace(B: int, M: int, H: int, D: int, num_splits: int, device)
 def decode_attention(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, k_cache: torch.Tensor,
                      v_cache: torch.Tensor, seq_lens: torch.Tensor, vis_start: Optional[torch.Tensor],
                      bitmask: Optional[torch.Tensor], n_vis: int, scale: float, num_splits: int = 1,
-                     out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q [B,M,H,D], k_new/v_new [B,M,H_kv,D], caches [B,H_kv,S_max,D] (bf16) -> out [B,M,H,D] bf16."""
+                     out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                     seq_active: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B,M,H,D], k_new/v_new [B,M,H_kv,D], caches [B,H_kv,S_max,D] (bf16) -> out [B,M,H,D] bf16.
+    seq_active int32 [B]: sequences with 0 are skipped (their rows of `out` stay untouched)."""
     L = _lib.load()
     for t, n in ((q, "q"), (k_new, "k_new"), (v_new, "v_new"), (k_cache, "k_cache"), (v_cache, "v_cache")):
         _need(t, torch.bfloat16, n)
@@ -137,10 +141,12 @@ def decode_attention(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, 
         out = torch.empty_like(q)
     if workspace is None:
         workspace = attention_workspace(B, M, H, D, num_splits, q.device)
-    check(L.dd_decode_attention(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(k_cache), _ptr(v_cache), _ptr(seq_lens),
-                                _ptr(vis_start), _ptr(bitmask), B, M, H, H_kv, D, S_max, n_vis, words,
-                                float(scale), num_splits, _ptr(out), _ptr(workspace),
-                                workspace.numel() * workspace.element_size(), _stream()), "dd_decode_attention")
+    if seq_active is not None:
+        _need(seq_active, torch.int32, "seq_active")
+    check(L.dd_decode_attention_active(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(k_cache), _ptr(v_cache), _ptr(seq_lens),
+                                       _ptr(vis_start), _ptr(bitmask), _ptr(seq_active), B, M, H, H_kv, D, S_max, n_vis,
+                                       words, float(scale), num_splits, _ptr(out), _ptr(workspace),
+                                       workspace.numel() * workspace.element_size(), _stream()), "dd_decode_attention")
     return out
 
 
@@ -184,7 +190,7 @@ def aggregate(logits: torch.Tensor, mode: str = "vote", want_logits: bool = Fals
 
 
 def token_stats(logits: torch.Tensor, vocab: int, stats: torch.Tensor, member: Optional[torch.Tensor] = None,
-                slot: Optional[torch.Tensor] = None, slot_offset: int = 0) -> torch.Tensor:
+                slot: Optional[torch.Tensor] = None, slot_offset: int = 0, slot_per_seq: bool = False) -> torch.Tensor:
     """logits fp32 [B, K, ld] (or [B, ld]); stats fp32 [n_slots, B, 3] <- {1/max, entropy bits, varentropy} of row
     member[b] (default 0) of every sequence, written at slot index *slot + slot_offset."""
     L = _lib.load()
@@ -196,8 +202,9 @@ def token_stats(logits: torch.Tensor, vocab: int, stats: torch.Tensor, member: O
         _need(member, torch.int32, "member")
     if slot is not None:
         _need(slot, torch.int32, "slot")
-    check(L.dd_token_stats(_ptr(logits), logits.stride(0), logits.stride(1), _ptr(member), B, int(vocab), _ptr(slot),
-                           int(slot_offset), stats.shape[0], _ptr(stats), _stream()), "dd_token_stats")
+    fn = L.dd_token_stats_seq if slot_per_seq else L.dd_token_stats
+    check(fn(_ptr(logits), logits.stride(0), logits.stride(1), _ptr(member), B, int(vocab), _ptr(slot),
+             int(slot_offset), stats.shape[0], _ptr(stats), _stream()), "dd_token_stats")
     return stats
 
 
@@ -307,6 +314,17 @@ def embed_gather(embed: torch.Tensor, token: torch.Tensor, M: int, out: torch.Te
     check(L.dd_embed_gather(_ptr(embed), _ptr(token), token.shape[0], M, embed.shape[1], _ptr(out), _stream()),
           "dd_embed_gather")
     return out
+
+
+def step_advance_seq(token: torch.Tensor, advance: torch.Tensor, tokens_out: Optional[torch.Tensor],
+                     seq_lens: torch.Tensor, seq_steps: torch.Tensor) -> None:
+    """Per-sequence progress: sequences with advance[b] != 0 record their token and move on."""
+    L = _lib.load()
+    for t, n in ((token, "token"), (advance, "advance"), (seq_lens, "seq_lens"), (seq_steps, "seq_steps")):
+        _need(t, torch.int32, n)
+    max_steps = 0 if tokens_out is None else tokens_out.shape[1]
+    check(L.dd_step_advance_seq(_ptr(token), _ptr(advance), _ptr(tokens_out), max_steps, _ptr(seq_lens),
+                                _ptr(seq_steps), token.shape[0], _stream()), "dd_step_advance_seq")
 
 
 def step_advance(token: torch.Tensor, tokens_out: Optional[torch.Tensor], seq_lens: torch.Tensor,

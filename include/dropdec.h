@@ -104,6 +104,13 @@ int dd_sample_masks(const float* epi /* [B, n_vis] */, const int32_t* topk_ids /
                     int keep_relevant, int B, int n_vis, int seq_base, uint32_t* bitmask /* [B, K, mask_words] */,
                     int mask_words, int32_t* n_masked /* [B, K] */, dd_stream_t stream);
 
+/* The same with one step counter PER SEQUENCE (seq_steps [B]): the asynchronous batch schedule lets sequences that
+ * had to repeat their masked contexts fall behind the others, and sequence b then draws the numbers of ITS step. */
+int dd_sample_masks_seq(const float* epi, const int32_t* topk_ids, int topk, const int32_t* y_init,
+                        const double* probs_host, int K, const float* uniforms, uint64_t seed, uint64_t offset0,
+                        const int32_t* seq_steps /* [B] */, int mode, int keep_relevant, int B, int n_vis, int seq_base,
+                        uint32_t* bitmask, int mask_words, int32_t* n_masked, dd_stream_t stream);
+
 /* Test hook: out[i] = first uniform of Philox subsequence i at `offset` -- the layout
  * torch.rand(n, device="cuda") uses for n <= 256 * #blocks. */
 int dd_philox_uniform(uint64_t seed, uint64_t offset, int n, float* out, dd_stream_t stream);
@@ -132,9 +139,20 @@ int dd_decode_attention(const void* q /* bf16 [B, M, H, D] */, const void* k_new
                         float scale, int num_splits, void* out /* bf16 [B, M, H, D] */, void* workspace,
                         size_t workspace_bytes, dd_stream_t stream);
 
+/* The same with a per-sequence activity flag: sequences with seq_active[b] == 0 are skipped entirely (no K/V is
+ * read, their rows of `out` stay untouched).  Used by the batched speculative schedule, where the masked pass is
+ * re-run only for the sequences whose speculated masks turned out wrong.  seq_active == NULL: all active. */
+int dd_decode_attention_active(const void* q, const void* k_new, const void* v_new, const void* k_cache,
+                               const void* v_cache, const int32_t* seq_lens, const int32_t* vis_start,
+                               const uint32_t* bitmask, const int32_t* seq_active /* [B] or NULL */, int B, int M,
+                               int H, int H_kv, int D, int S_max, int n_vis, int mask_words, float scale,
+                               int num_splits, void* out, void* workspace, size_t workspace_bytes,
+                               dd_stream_t stream);
+
 /* Commit the winning member's new-token K/V rows of every layer into the shared cache at
  * position seq_lens[b] (replaces "the winner's cache becomes the live cache",
- * models/llava.py:370-376).  seq_lens is NOT advanced here (see dd_step_advance). */
+ * models/llava.py:370-376).  seq_lens is NOT advanced here (see dd_step_advance).  winner[b] < 0 skips sequence b
+ * (it commits from another staging buffer). */
 int dd_commit_winner(const void* k_new_all /* bf16 [L, B, M, H_kv, D] */, const void* v_new_all,
                      const int32_t* winner /* [B] */, const int32_t* seq_lens /* [B] */,
                      void* k_cache_all /* bf16 [L, B, H_kv, S_max, D] */, void* v_cache_all, int L, int B,
@@ -167,10 +185,15 @@ int dd_aggregate_strided(const float* logits, int B, int K, int V, int ld, long 
  * chosen logits row of every sequence without a host sync:
  *   row(b)  = logits + b * seq_stride + (member ? member[b] : 0) * member_stride      (elements)
  *   stats[r, b, :] = { 1 / max(row), entropy in bits, varentropy }     with r = (slot ? *slot : 0) + slot_offset
- * (nothing is written when r is outside [0, n_slots)). */
+ * (nothing is written when r is outside [0, n_slots), nor for sequences with member[b] < 0). */
 int dd_token_stats(const float* logits, long long seq_stride, long long member_stride,
                    const int32_t* member /* [B] or NULL */, int B, int V, const int32_t* slot /* device scalar or NULL */,
                    int slot_offset, int n_slots, float* stats /* [n_slots, B, 3] */, dd_stream_t stream);
+
+/* dd_token_stats with a per-sequence slot: r = slots[b] + slot_offset. */
+int dd_token_stats_seq(const float* logits, long long seq_stride, long long member_stride,
+                       const int32_t* member /* [B] or NULL */, int B, int V, const int32_t* slots /* [B] */,
+                       int slot_offset, int n_slots, float* stats /* [n_slots, B, 3] */, dd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Decoder support for the single-token forwards of the ensemble (models/llama.py:27-47 and the
@@ -250,6 +273,12 @@ int dd_embed_gather(const void* embed /* bf16 [V, d] */, const int32_t* token /*
 int dd_step_advance(const int32_t* token /* [B] */, int32_t* tokens_out /* [B, max_steps] */,
                     int max_steps, int32_t* seq_lens /* [B] */, int32_t* step /* scalar */, int B,
                     dd_stream_t stream);
+
+/* Per-sequence variant: for every sequence with advance[b] != 0:
+ * tokens_out[b, seq_steps[b] + 1] = token[b]; seq_lens[b] += 1; seq_steps[b] += 1.  Others are left alone. */
+int dd_step_advance_seq(const int32_t* token /* [B] */, const int32_t* advance /* [B] */,
+                        int32_t* tokens_out /* [B, max_steps] */, int max_steps, int32_t* seq_lens /* [B] */,
+                        int32_t* seq_steps /* [B] */, int B, dd_stream_t stream);
 
 #ifdef __cplusplus
 }

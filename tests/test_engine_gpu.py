@@ -192,6 +192,53 @@ def test_speculative_pass_equals_two_pass_bit_for_bit(tiny, cuda):
     assert 0 < a.n_fallbacks < a.n_spec_steps == TINY_T - 1, (a.n_fallbacks, a.n_spec_steps)
 
 
+@pytest.mark.parametrize("aggregate", ["vote", "mean"])
+def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate):
+    """B=12 (48 contexts: above the small-batch kernels) runs the asynchronous batch schedule: one K+1-context pass
+    per call, sequences whose speculated masks were wrong repeat the step with the real masks and fall behind.
+    Different sequences see different uniforms, so they drift apart; tokens, per-token statistics and the whole
+    committed K/V cache still equal the two-pass engine's bit for bit, and every sequence decodes exactly what it
+    decodes alone (sequence 0 replays the oracle trace)."""
+    tr = tiny["trace"]
+    B, T = 12, 18
+    g = torch.Generator().manual_seed(99)
+    U = torch.rand(T, B, 3, TINY_N_VIS, generator=g)
+    U[:, 0] = tiny["U"][:T]                                    # sequence 0 replays the oracle trace
+    engs = []
+    for spec in ("auto", "off"):
+        eng = tiny["Engine"](tiny["weights"], batch=B, n_vis=TINY_N_VIS, max_seq=640, probs=TINY_PROBS,
+                             mode="cumulative", topk=5, seed=24, max_steps=64, aggregate=aggregate, speculative=spec,
+                             gemm_backend="stream")    # row-independent GEMMs: a library GEMM may sum a row in another
+        #                                                order when the row count of the pass changes (36 vs 48 rows)
+        k = torch.stack(tr.prefill_cache.k)[:, None].expand(-1, B, -1, -1, -1)
+        v = torch.stack(tr.prefill_cache.v)[:, None].expand(-1, B, -1, -1, -1)
+        eng.load_prefill(k, v, [TINY_VIS_START] * B)
+        eng.set_uniforms(U)
+        eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda).expand(B, -1))
+        eng.topk_ids.copy_(tr.topk_ids.to(cuda).int().expand(B, -1, -1))
+        eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None].expand(B, -1).contiguous())
+        engs.append(eng)
+    a, b = engs
+    assert a.spec_batch and not a.spec_active and not b.spec_batch
+    for chunk, graph in ((1, False), (5, True), (1, True), (T - 8, True)):      # lockstep again after every call
+        a.decode(chunk, use_graph=graph)
+        b.decode(chunk, use_graph=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a.seq_lens, b.seq_lens) and int(a.step_ctr) == int(b.step_ctr)
+        assert torch.equal(a.generated(), b.generated())
+        if chunk == 1:      # one step: the per-step views agree as well
+            for name in ("y_init", "bitmask", "n_masked", "member_ids", "winner", "next_token"):
+                assert torch.equal(getattr(a, name), getattr(b, name)), name
+            assert torch.equal(a.step_logits(), b.step_logits())
+    S = int(a.seq_lens[0])
+    assert torch.equal(a.k_cache[:, :, :, :S], b.k_cache[:, :, :, :S])
+    assert torch.equal(a.v_cache[:, :, :, :S], b.v_cache[:, :, :, :S])
+    assert torch.equal(a.token_stats[:T], b.token_stats[:T])
+    if aggregate == "vote":     # (up to the exact tie of the oracle's step 13, see test_ensemble_decode_bit_exact)
+        assert a.generated()[0, :12].tolist() == tr.tokens[:12]
+    assert 0.0 < a.fallback_rate() < 1.0 and a.n_spec_steps > T - 1, (a.fallback_rate(), a.n_spec_steps)
+
+
 def test_member_logits_close_to_oracle(tiny, cuda):
     """Aggregated (winner) logits of the first ensemble step within 2e-2 absolute (north_star bar)."""
     eng = make_engine(tiny, cuda)

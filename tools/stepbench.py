@@ -57,5 +57,5 @@ with torch.no_grad():
                           batch=a.batch, K=len(probs), ms_per_step=round(best, 4),
                           tokens_per_s=round(a.batch * 1e3 / best, 1),
                           step_roofline_frac=round((wbytes + kv) / (best * 1e-3) / 6551.4e9, 3),
-                          launches=eng.launches_per_step, spec=eng.spec_active, gemm=eng.gemm_backend,
-                          fallback_rate=round(eng.n_fallbacks / max(1, eng.n_spec_steps), 3))))
+                          launches=eng.launches_per_step, spec=("host" if eng.spec_active else "batch" if eng.spec_batch else "off"),
+                          gemm=eng.gemm_backend, fallback_rate=round(eng.fallback_rate(), 3))))
