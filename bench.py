@@ -135,7 +135,20 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        # NCCL may print its version banner on stdout while the communicator is created; stdout carries exactly one
+        # JSON line, so the banner goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            torch.cuda.set_device(local)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     hbm, tf, peak_src = measured_peaks()

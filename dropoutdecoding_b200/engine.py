@@ -220,13 +220,13 @@ class DropoutDecodeEngine:
         if self.speculative not in ("auto", "on", "off"):
             raise ValueError(self.speculative)
         ok = vote_on == "logits" and (self.K + 1) * (H // Hkv) <= 32 and self.K + 1 <= 16
-        fits = ok and B * (self.K + 1) <= 32        # small batch: the host decides per step whether to fall back
+        fits = ok and B == 1                        # one sequence: the host decides per step whether to fall back
         if self.speculative == "on" and not ok:
             raise ops.DropDecError("speculative single pass needs vote_on='logits' and (K+1)*H/H_kv <= 32")
         self._spec_fits = fits
         self.spec_active = fits and self.speculative != "off"
-        # larger batches: some sequence nearly always needs the fallback, so it always runs -- but its attention
-        # only reads the K/V of the sequences that need it (per-sequence flags on the device, no host decision)
+        # batches: some sequence nearly always needs the fallback, so sequences advance independently instead
+        # (asynchronous batch schedule, _spec_batch_step; per-sequence flags on the device, no host decision)
         self.spec_batch = ok and not fits and self.speculative != "off"
         self.n_spec_steps = self.n_fallbacks = 0        # cumulative over the engine's life
         self._seq_steps_done = 0
@@ -463,7 +463,8 @@ class DropoutDecodeEngine:
     # the cost of one weight stream instead of two.  y_init then comes out of row 0, the real masks are sampled, and
     # if they equal the speculated ones (S empty, or none of its tokens was drawn: the common case) rows 1..K ARE
     # the reference's K masked forwards, bit for bit.  Otherwise the masked pass is re-run with the real masks
-    # (the reference's own order).  The one host decision per token replaces the reference's >= 3K syncs.
+    # (the reference's own order).  With one sequence the host takes that decision per token (replacing the
+    # reference's >= 3K syncs); batches use the asynchronous schedule of _spec_batch_step instead.
     # ------------------------------------------------------------------------------------
     def _spec_head(self) -> None:
         self.launches_per_step = 0
@@ -506,7 +507,7 @@ class DropoutDecodeEngine:
         self._masked_pass_and_commit()
 
     def _spec_batch_step(self) -> None:
-        """Asynchronous batch schedule (larger batches; no host decision, ONE pass per call): every sequence runs K+1
+        """Asynchronous batch schedule (B >= 2; no host decision, ONE pass per call): every sequence runs K+1
         contexts -- row 0 unmasked, rows 1..K with the draws of ITS current step, or, if its previous pass found
         that y_init restores a drawn token, with the real masks of that step.  A sequence whose rows 1..K carried
         its real masks votes, commits and advances; the others repeat the step in the next pass.  Sequences are
@@ -688,7 +689,7 @@ class DropoutDecodeEngine:
 
         run(n_steps)
         while not bool((self.seq_steps >= self.target).all()):
-            run(2)
+            run(1 if self.B <= 8 else 2)
         self.step_ctr.add_(n_steps)
         self._seq_steps_done += n_steps * self.B
         self._last_src = "mixed"

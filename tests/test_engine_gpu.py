@@ -301,13 +301,13 @@ def test_batch_is_independent_of_batch_size(tiny, cuda):
 
 
 def test_batch_of_eight_runs_the_masked_pass_on_the_tcgen05_gemm(tiny, cuda):
-    """B=8 -> 8 rows in the preliminary pass (dd_skinny_gemm) and 24 in the masked pass (dd_stream_gemm by default):
-    every sequence still generates the B=1 oracle tokens."""
+    """B=8 -> 32 contexts per pass of the asynchronous batch schedule, on dd_stream_gemm by default: every sequence
+    still generates the B=1 oracle tokens."""
     tr = tiny["trace"]
     B = 8
     eng = tiny["Engine"](tiny["weights"], batch=B, n_vis=TINY_N_VIS, max_seq=640, probs=TINY_PROBS,
                          mode="cumulative", topk=5, seed=24, max_steps=64)
-    assert eng._use_stream(B * 3) and not eng._use_stream(B)
+    assert eng.spec_batch and eng._use_stream(B * 4)         # asynchronous batch schedule: 32 contexts per pass
     k = torch.stack(tr.prefill_cache.k)[:, None].expand(-1, B, -1, -1, -1)
     v = torch.stack(tr.prefill_cache.v)[:, None].expand(-1, B, -1, -1, -1)
     eng.load_prefill(k, v, [TINY_VIS_START] * B)
