@@ -219,10 +219,12 @@ class DropoutDecodeEngine:
         self.speculative = speculative or os.environ.get("DD_SPEC", "auto")
         if self.speculative not in ("auto", "on", "off"):
             raise ValueError(self.speculative)
-        ok = vote_on == "logits" and (self.K + 1) * (H // Hkv) <= 32 and self.K + 1 <= 16
-        fits = ok and B == 1                        # one sequence: the host decides per step whether to fall back
+        ok = (self.K + 1) * (H // Hkv) <= 32 and self.K + 1 <= 16
+        # one sequence: the host decides per step whether to fall back (the hidden-state vote of InstructBLIP always
+        # takes the asynchronous schedule below, also at B = 1)
+        fits = ok and B == 1 and vote_on == "logits"
         if self.speculative == "on" and not ok:
-            raise ops.DropDecError("speculative single pass needs vote_on='logits' and (K+1)*H/H_kv <= 32")
+            raise ops.DropDecError("speculative single pass needs (K+1)*H/H_kv <= 32")
         self._spec_fits = fits
         self.spec_active = fits and self.speculative != "off"
         # batches: some sequence nearly always needs the fallback, so sequences advance independently instead
@@ -251,6 +253,8 @@ class DropoutDecodeEngine:
             self.ret_logits = torch.zeros(B, V, dtype=torch.float32, device=dev)
             if aggregate == "mean":
                 self._out_c = torch.zeros(B, V, dtype=torch.float32, device=dev)
+            if vote_on == "hidden":
+                self._hid32c = torch.zeros(B, self.K + 1, cfg.d_model, dtype=torch.float32, device=dev)
         if self.spec_active or self.spec_batch:
             self.pc = self._alloc_pass(self.K + 1, est)
             self.spec_draw = torch.zeros(B, self.K, self.words, **i32)
@@ -543,8 +547,17 @@ class DropoutDecodeEngine:
         self.n_masked.copy_(torch.where(act[:, None], self._nm_real, self.n_masked))
         adv = ok & act
         self.adv.copy_(adv.to(torch.int32))
-        ops.aggregate(self.pc.logits, self.aggregate, member_ids=self._ids_c, winner=self._win_c, token=self._tok_sc,
-                      out_logits=self._out_c if mean else None, vocab=V, first_member=1, members=K)
+        if self.vote_on == "hidden":
+            # InstructBLIP (models/instructblip.py:125-140): the vote is taken on argmax of the members' final hidden
+            # states; the returned logits / token are lm_head of the winner = its row of the pass's logits
+            self._hid32c.copy_(self.pc.xn.view(self.B, K + 1, self.cfg.d_model))
+            ops.aggregate(self._hid32c, "vote", member_ids=self._ids_c, winner=self._win_c, token=self._tok_sc,
+                          first_member=1, members=K)
+            self._tok_sc.copy_(self.member_ids_c.gather(1, (self._win_c + 1).long()[:, None])[:, 0])
+        else:
+            ops.aggregate(self.pc.logits, self.aggregate, member_ids=self._ids_c, winner=self._win_c,
+                          token=self._tok_sc, out_logits=self._out_c if mean else None, vocab=V, first_member=1,
+                          members=K)
         self.member_ids.copy_(torch.where(adv[:, None], self._ids_c, self.member_ids))
         self.winner.copy_(torch.where(adv, self._win_c, self.winner))
         self.next_token.copy_(torch.where(adv, self._tok_sc, self.next_token))
@@ -780,12 +793,12 @@ class DropoutDecodeEngine:
         """fp32 [B, V]: what the reference's forward() returns after a decode step -- the winning
         member's logits (models/llava.py:370-376) or the member mean (select_by_average)."""
         V = self.cfg.vocab
+        if self._last_src == "mixed":       # asynchronous batch schedule: each sequence's own advancing pass
+            return self.ret_logits
         if self.aggregate == "mean":
             return self.out_logits
         if self.vote_on == "hidden":
             return self.pa.logits[:, 0, :V]
-        if self._last_src == "mixed":       # asynchronous batch schedule: each sequence's own advancing pass
-            return self.ret_logits
         if self._last_src == "pc":          # the speculative pass was the real one: members are rows 1..K
             return self.pc.logits[self._rows(), self.winner.long() + 1, :V]
         return self.pb.logits[self._rows(), self.winner.long(), :V]
