@@ -39,8 +39,8 @@ _SIGNATURES = {
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P,
                                       C.c_size_t, _P]),
     "dd_decode_attention_active": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
-                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P,
-                                             C.c_size_t, _P]),
+                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                             _P, _P, C.c_size_t, _P]),
     "dd_commit_winner": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, _P]),
     "dd_aggregate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

@@ -76,6 +76,7 @@ struct AttnParams {
   const __nv_bfloat16 *k_new, *v_new;
   __nv_bfloat16* out;
   int B, M, H, H_kv, S_max, n_vis, mask_words, num_splits;
+  int Mt, m0;  // the M members of this call are members m0..m0+M-1 of the Mt stored per sequence (q, k_new, v_new, out, bitmask)
   float scale_log2;  // scale * log2(e)
 };
 
@@ -156,13 +157,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
     uint4 v = make_uint4(0, 0, 0, 0);
     if (r < R) {
       const int m = r / G, h = hkv * G + (r % G);
-      v = *reinterpret_cast<const uint4*>(p.q + (((size_t)b * p.M + m) * p.H + h) * D + c * 8);
+      v = *reinterpret_cast<const uint4*>(p.q + (((size_t)b * p.Mt + p.m0 + m) * p.H + h) * D + c * 8);
     }
     *reinterpret_cast<uint4*>(sQ + swz<D>(r, c)) = v;
   }
   if (p.bitmask)
     for (int idx = tid; idx < p.M * p.mask_words; idx += kAttnThreads)
-      sMask[idx] = p.bitmask[(size_t)b * p.M * p.mask_words + idx];
+      sMask[idx] = p.bitmask[((size_t)b * p.Mt + p.m0) * p.mask_words + idx];
 
   float o[QT][D / 8][4];
   float m_run[QT][2], l_run[QT][2];
@@ -348,8 +349,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
   constexpr int DL = D / 32;  // dims per lane: one warp per query row
   for (int r = warp; r < R; r += kAttnWarps) {
     const int m = r / G, h = hkv * G + (r % G);
-    const size_t qoff = (((size_t)b * p.M + m) * p.H + h) * D + lane * DL;
-    const size_t kvoff = (((size_t)b * p.M + m) * p.H_kv + hkv) * D + lane * DL;
+    const size_t qoff = (((size_t)b * p.Mt + p.m0 + m) * p.H + h) * D + lane * DL;
+    const size_t kvoff = (((size_t)b * p.Mt + p.m0 + m) * p.H_kv + hkv) * D + lane * DL;
     // score of the member's own new token (always attended: it is the query position itself)
     float dot = 0.f, vself[DL];
 #pragma unroll
@@ -388,8 +389,8 @@ __global__ void __launch_bounds__(D) attn_merge_kernel(const AttnParams p) {
   const int h = blockIdx.x, m = blockIdx.y, b = blockIdx.z, d = threadIdx.x;
   if (p.seq_active && p.seq_active[b] == 0) return;
   const int G = p.H / p.H_kv, hkv = h / G, r = m * G + (h % G), R = p.M * G;
-  const size_t qoff = (((size_t)b * p.M + m) * p.H + h) * D;
-  const size_t kvoff = (((size_t)b * p.M + m) * p.H_kv + hkv) * D;
+  const size_t qoff = (((size_t)b * p.Mt + p.m0 + m) * p.H + h) * D;
+  const size_t kvoff = (((size_t)b * p.Mt + p.m0 + m) * p.H_kv + hkv) * D;
   // score of the member's own new token (always attended: it is the query position itself)
   float dot = __bfloat162float(p.q[qoff + d]) * __bfloat162float(p.k_new[kvoff + d]);
   dot = warp_sum(dot);
@@ -453,18 +454,21 @@ extern "C" int dd_decode_attention(const void* q, const void* k_new, const void*
                                    const uint32_t* bitmask, int B, int M, int H, int H_kv, int D, int S_max,
                                    int n_vis, int mask_words, float scale, int num_splits, void* out,
                                    void* workspace, size_t workspace_bytes, dd_stream_t stream) {
-  return dd_decode_attention_active(q, k_new, v_new, k_cache, v_cache, seq_lens, vis_start, bitmask, nullptr, B, M, H,
-                                    H_kv, D, S_max, n_vis, mask_words, scale, num_splits, out, workspace,
+  return dd_decode_attention_active(q, k_new, v_new, k_cache, v_cache, seq_lens, vis_start, bitmask, nullptr, B, M, 0,
+                                    M, H, H_kv, D, S_max, n_vis, mask_words, scale, num_splits, out, workspace,
                                     workspace_bytes, stream);
 }
 
 extern "C" int dd_decode_attention_active(const void* q, const void* k_new, const void* v_new, const void* k_cache,
                                           const void* v_cache, const int32_t* seq_lens, const int32_t* vis_start,
-                                          const uint32_t* bitmask, const int32_t* seq_active, int B, int M, int H,
-                                          int H_kv, int D, int S_max, int n_vis, int mask_words, float scale,
-                                          int num_splits, void* out, void* workspace, size_t workspace_bytes,
-                                          dd_stream_t stream) {
+                                          const uint32_t* bitmask, const int32_t* seq_active, int B, int M,
+                                          int member_offset, int members_total, int H, int H_kv, int D, int S_max,
+                                          int n_vis, int mask_words, float scale, int num_splits, void* out,
+                                          void* workspace, size_t workspace_bytes, dd_stream_t stream) {
   using namespace dd;
+  DD_CHECK_ARG(member_offset >= 0 && member_offset + M <= members_total,
+               "dd_decode_attention: members [%d, %d) outside the %d stored per sequence", member_offset,
+               member_offset + M, members_total);
   DD_CHECK_ARG(q && k_new && v_new && k_cache && v_cache && seq_lens && out && workspace,
                "dd_decode_attention: null pointer");
   DD_CHECK_ARG(D == 64 || D == 128, "dd_decode_attention: D=%d unsupported (64 or 128)", D);
@@ -478,9 +482,10 @@ extern "C" int dd_decode_attention_active(const void* q, const void* k_new, cons
   DD_CHECK_ARG(!bitmask || (vis_start && mask_words * 32 >= n_vis && mask_words <= kMaxMaskWords),
                "dd_decode_attention: bitmask needs vis_start and n_vis <= 32*mask_words <= %d",
                32 * kMaxMaskWords);
-  if (workspace_bytes < dd_attention_workspace_bytes(B, M, H, D, num_splits)) {
+  // laid out for all members_total members, so the ticket counters sit at the same place for every member window
+  if (workspace_bytes < dd_attention_workspace_bytes(B, members_total, H, D, num_splits)) {
     set_error("dd_decode_attention: workspace %zu < %zu bytes", workspace_bytes,
-              dd_attention_workspace_bytes(B, M, H, D, num_splits));
+              dd_attention_workspace_bytes(B, members_total, H, D, num_splits));
     return DD_ERR_WORKSPACE;
   }
   if (B == 0) return DD_OK;
@@ -488,10 +493,10 @@ extern "C" int dd_decode_attention_active(const void* q, const void* k_new, cons
   p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
   p.seq_lens = seq_lens; p.vis_start = vis_start; p.bitmask = bitmask; p.seq_active = seq_active;
   p.part_o = (float*)workspace;
-  p.part_ml = p.part_o + (size_t)B * M * H * num_splits * D;
-  p.tickets = reinterpret_cast<int*>(p.part_ml + (size_t)B * M * H * num_splits * 2);
+  p.part_ml = p.part_o + (size_t)B * members_total * H * num_splits * D;
+  p.tickets = reinterpret_cast<int*>(p.part_ml + (size_t)B * members_total * H * num_splits * 2);
   p.k_new = (const __nv_bfloat16*)k_new; p.v_new = (const __nv_bfloat16*)v_new; p.out = (__nv_bfloat16*)out;
-  p.B = B; p.M = M; p.H = H; p.H_kv = H_kv; p.S_max = S_max; p.n_vis = n_vis; p.mask_words = mask_words;
+  p.B = B; p.M = M; p.Mt = members_total; p.m0 = member_offset; p.H = H; p.H_kv = H_kv; p.S_max = S_max; p.n_vis = n_vis; p.mask_words = mask_words;
   p.num_splits = num_splits;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int R = M * (H / H_kv);

@@ -219,12 +219,12 @@ class DropoutDecodeEngine:
         self.speculative = speculative or os.environ.get("DD_SPEC", "auto")
         if self.speculative not in ("auto", "on", "off"):
             raise ValueError(self.speculative)
-        ok = (self.K + 1) * (H // Hkv) <= 32 and self.K + 1 <= 16
+        ok = self.K + 1 <= 16        # (more than 32 query rows per kv head: the attention runs in member groups)
         # one sequence: the host decides per step whether to fall back (the hidden-state vote of InstructBLIP always
         # takes the asynchronous schedule below, also at B = 1)
         fits = ok and B == 1 and vote_on == "logits"
         if self.speculative == "on" and not ok:
-            raise ops.DropDecError("speculative single pass needs (K+1)*H/H_kv <= 32")
+            raise ops.DropDecError("speculative single pass needs K + 1 <= 16 contexts")
         self._spec_fits = fits
         self.spec_active = fits and self.speculative != "off"
         # batches: some sequence nearly always needs the fallback, so sequences advance independently instead
@@ -322,6 +322,18 @@ class DropoutDecodeEngine:
         n = gu.shape[1] // 2
         return torch.mul(F.silu(gu[:, :n]), gu[:, n:], out=out)
 
+    def _attention(self, pb: _PassBuffers, l: int, bitmask, seq_active) -> None:
+        """dd_decode_attention of layer l; a pass with more than 32 query rows per kv head (LLaVA-NeXT: 9 contexts x
+        4 query heads) is served in member groups, each reading the K/V once."""
+        G = self.cfg.n_heads // self.cfg.n_kv_heads
+        per = max(1, 32 // G)
+        for m0 in range(0, pb.M, per):
+            ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
+                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws,
+                                 seq_active=seq_active, member_offset=m0, members=min(per, pb.M - m0))
+            if m0:
+                self.launches_per_step += 1 + (pb.splits == 1)
+
     def _forward(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool = True,
                  seq_active: Optional[torch.Tensor] = None) -> torch.Tensor:
         cfg, B, M = self.cfg, self.B, pb.M
@@ -335,9 +347,7 @@ class DropoutDecodeEngine:
             ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pb.xn)
             self._linear(pb.xn, lw["wqkv"], ops.EPI_NONE, pb.qkv)
             ops.rope_stage(pb.qkv, self.cos, self.sin, self.seq_lens, B, M, H, Hkv, D, pb.q, pb.k_new[l], pb.v_new[l])
-            ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
-                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws,
-                                 seq_active=seq_active)
+            self._attention(pb, l, bitmask, seq_active)
             if rows <= 32 and self.gemm_backend == "auto":      # 33 MB o_proj: the skinny kernel is as fast up to 32 rows
                 ops.skinny_gemm(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
                 self.launches_per_step += 1
@@ -372,9 +382,7 @@ class DropoutDecodeEngine:
             else:
                 ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pb.xn)
                 ops.decoder_linear(pb.xn, lw["wqkv"], ops.EPI_ROPE, rope=rope)
-            ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
-                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws,
-                                 seq_active=seq_active)
+            self._attention(pb, l, bitmask, seq_active)
             ops.decoder_linear(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
             if fuse:
                 ops.decoder_linear(x2, lw["wgu"], ops.EPI_SWIGLU, norm_w=lw["ln2"], eps=cfg.rms_eps, out=pb.act)

@@ -124,9 +124,11 @@ def decode_attention(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, 
                      v_cache: torch.Tensor, seq_lens: torch.Tensor, vis_start: Optional[torch.Tensor],
                      bitmask: Optional[torch.Tensor], n_vis: int, scale: float, num_splits: int = 1,
                      out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
-                     seq_active: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     seq_active: Optional[torch.Tensor] = None, member_offset: int = 0,
+                     members: Optional[int] = None) -> torch.Tensor:
     """q [B,M,H,D], k_new/v_new [B,M,H_kv,D], caches [B,H_kv,S_max,D] (bf16) -> out [B,M,H,D] bf16.
-    seq_active int32 [B]: sequences with 0 are skipped (their rows of `out` stay untouched)."""
+    seq_active int32 [B]: sequences with 0 are skipped (their rows of `out` stay untouched).
+    member_offset / members: serve only members [member_offset, member_offset + members) of the M stored."""
     L = _lib.load()
     for t, n in ((q, "q"), (k_new, "k_new"), (v_new, "v_new"), (k_cache, "k_cache"), (v_cache, "v_cache")):
         _need(t, torch.bfloat16, n)
@@ -143,9 +145,10 @@ def decode_attention(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, 
         workspace = attention_workspace(B, M, H, D, num_splits, q.device)
     if seq_active is not None:
         _need(seq_active, torch.int32, "seq_active")
+    Mc = M - member_offset if members is None else members
     check(L.dd_decode_attention_active(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(k_cache), _ptr(v_cache), _ptr(seq_lens),
-                                       _ptr(vis_start), _ptr(bitmask), _ptr(seq_active), B, M, H, H_kv, D, S_max, n_vis,
-                                       words, float(scale), num_splits, _ptr(out), _ptr(workspace),
+                                       _ptr(vis_start), _ptr(bitmask), _ptr(seq_active), B, Mc, member_offset, M, H, H_kv,
+                                       D, S_max, n_vis, words, float(scale), num_splits, _ptr(out), _ptr(workspace),
                                        workspace.numel() * workspace.element_size(), _stream()), "dd_decode_attention")
     return out
 

@@ -139,15 +139,18 @@ int dd_decode_attention(const void* q /* bf16 [B, M, H, D] */, const void* k_new
                         float scale, int num_splits, void* out /* bf16 [B, M, H, D] */, void* workspace,
                         size_t workspace_bytes, dd_stream_t stream);
 
-/* The same with a per-sequence activity flag: sequences with seq_active[b] == 0 are skipped entirely (no K/V is
- * read, their rows of `out` stay untouched).  Used by the batched speculative schedule, where the masked pass is
- * re-run only for the sequences whose speculated masks turned out wrong.  seq_active == NULL: all active. */
+/* The same with (a) a per-sequence activity flag: sequences with seq_active[b] == 0 are skipped entirely (no K/V is
+ * read, their rows of `out` stay untouched; used by the asynchronous batch schedule for sequences that wait), and
+ * (b) a member window: q, k_new, v_new, out and bitmask hold `members_total` members per sequence and this call
+ * serves members [member_offset, member_offset + M) -- a pass with more than 32 query rows per kv head (LLaVA-NeXT:
+ * 9 contexts x 4 query heads) is served by two calls; the workspace is sized (and laid out) for members_total:
+ * dd_attention_workspace_bytes(B, members_total, ...).  seq_active == NULL: all active. */
 int dd_decode_attention_active(const void* q, const void* k_new, const void* v_new, const void* k_cache,
                                const void* v_cache, const int32_t* seq_lens, const int32_t* vis_start,
                                const uint32_t* bitmask, const int32_t* seq_active /* [B] or NULL */, int B, int M,
-                               int H, int H_kv, int D, int S_max, int n_vis, int mask_words, float scale,
-                               int num_splits, void* out, void* workspace, size_t workspace_bytes,
-                               dd_stream_t stream);
+                               int member_offset, int members_total, int H, int H_kv, int D, int S_max, int n_vis,
+                               int mask_words, float scale, int num_splits, void* out, void* workspace,
+                               size_t workspace_bytes, dd_stream_t stream);
 
 /* Commit the winning member's new-token K/V rows of every layer into the shared cache at
  * position seq_lens[b] (replaces "the winner's cache becomes the live cache",

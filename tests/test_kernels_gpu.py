@@ -208,6 +208,54 @@ def test_decode_attention(ops, cuda, B, M, H, H_kv, D, S_max, lens, n_vis, split
     assert err <= 2 ** -8 * want.abs().max().item() + 1e-6, f"max abs err {err}"
 
 
+def test_decode_attention_member_windows_and_waiting_sequences(ops, cuda):
+    """dd_decode_attention_active: 9 contexts x 4 query heads per kv head (36 query rows > the kernel's 32) served as
+    member windows [0, 8) and [8, 9) equal the restated attention; a sequence flagged inactive keeps its output
+    rows; per-sequence step variants of the bookkeeping kernels."""
+    B, M, H, H_kv, D, S_max, n_vis, splits = 3, 9, 8, 2, 128, 200, 96, 2
+    lens = [150, 97, 192]
+    g = torch.Generator().manual_seed(77)
+    bf = lambda *s: (torch.randn(*s, generator=g)).to(torch.bfloat16)
+    q, k_new, v_new = bf(B, M, H, D), bf(B, M, H_kv, D), bf(B, M, H_kv, D)
+    kc, vc = bf(B, H_kv, S_max, D), bf(B, H_kv, S_max, D)
+    seq_lens = torch.tensor(lens, dtype=torch.int32)
+    vis_start = torch.tensor([1, 0, 5], dtype=torch.int32)
+    dropped = torch.rand(B, M, n_vis, generator=g) < 0.5
+    dropped[:, 0] = False                                  # member 0 = the unmasked context
+    words = ops.mask_words(n_vis)
+    bits = np.zeros((B, M, words * 32), dtype=bool)
+    bits[..., :n_vis] = dropped.numpy()
+    packed = (bits.reshape(B, M, words, 32) * (1 << np.arange(32, dtype=np.uint64))).sum(-1).astype(np.uint32)
+    bm = torch.from_numpy(packed.view(np.int32)).to(cuda)
+    scale = 1.0 / math.sqrt(D)
+    out = torch.full((B, M, H, D), 7.0, dtype=torch.bfloat16, device=cuda)
+    active = torch.tensor([1, 0, 1], dtype=torch.int32, device=cuda)
+    args = (q.to(cuda), k_new.to(cuda), v_new.to(cuda), kc.to(cuda), vc.to(cuda), seq_lens.to(cuda), vis_start.to(cuda),
+            bm, n_vis, scale)
+    ws = ops.attention_workspace(B, M, H, D, splits, cuda)
+    for m0, cnt in ((0, 8), (8, 1)):
+        ops.decode_attention(*args, num_splits=splits, out=out, workspace=ws, seq_active=active, member_offset=m0,
+                             members=cnt)
+    want = ref_attention(q.float(), k_new.float(), v_new.float(), kc.float(), vc.float(), seq_lens, vis_start, dropped,
+                         scale)
+    got = out.float().cpu()
+    for b in (0, 2):
+        err = (got[b] - want[b]).abs().max().item()
+        assert err <= 2 ** -8 * want.abs().max().item() + 1e-6, f"sequence {b}: max abs err {err}"
+    assert bool((got[1] == 7.0).all())                     # the waiting sequence was not touched
+    with pytest.raises(ops.DropDecError):                  # 9 members x 4 heads in one call: too many query rows
+        ops.decode_attention(*args, num_splits=splits, out=out, workspace=ws)
+    # per-sequence progress
+    tok = torch.tensor([11, 22, 33], dtype=torch.int32, device=cuda)
+    adv = torch.tensor([1, 0, 1], dtype=torch.int32, device=cuda)
+    hist = torch.zeros(B, 6, dtype=torch.int32, device=cuda)
+    seq = torch.tensor([5, 9, 2], dtype=torch.int32, device=cuda)
+    steps = torch.tensor([0, 3, 4], dtype=torch.int32, device=cuda)
+    ops.step_advance_seq(tok, adv, hist, seq, steps)
+    assert seq.tolist() == [6, 9, 3] and steps.tolist() == [1, 3, 5]
+    assert hist[0].tolist() == [0, 11, 0, 0, 0, 0] and hist[1].sum().item() == 0 and hist[2].tolist() == [0, 0, 0, 0, 0, 33]
+
+
 def test_commit_winner_and_step_advance(ops, cuda):
     L, B, M, H_kv, D, S_max = 3, 2, 3, 4, 64, 16
     g = torch.Generator().manual_seed(0)

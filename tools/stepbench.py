@@ -24,14 +24,17 @@ ap.add_argument("--probs", default="0.3,0.5,0.7")
 ap.add_argument("--mode", default="cumulative")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--no-graph", action="store_true")
+ap.add_argument("--vote-on", default="logits")
+ap.add_argument("--topk", type=int, default=5)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-cfg = {"7b": DecoderConfig.llava15_7b, "next": DecoderConfig.llava_next_mistral_7b, "tiny": DecoderConfig.tiny}[a.model]()
+cfg = {"7b": DecoderConfig.llava15_7b, "next": DecoderConfig.llava_next_mistral_7b, "tiny": DecoderConfig.tiny,
+       "iblip": lambda: DecoderConfig(32, 4096, 32, 32, 128, 11008, 32001, 1e-5, 10000.0)}[a.model]()
 probs = [float(p) for p in a.probs.split(",")]
 with torch.no_grad():
     w = DecoderWeights.random(cfg, dev)
-    eng = DropoutDecodeEngine(w, a.batch, a.n_vis, a.seq + a.steps + 8, probs=probs, mode=a.mode,
-                              max_steps=a.steps + 8, est_seq=a.seq + a.steps // 2)
+    eng = DropoutDecodeEngine(w, a.batch, a.n_vis, a.seq + a.steps + 8, probs=probs, mode=a.mode, topk=a.topk,
+                              max_steps=a.steps + 8, est_seq=a.seq + a.steps // 2, vote_on=a.vote_on)
     eng.k_cache.normal_(); eng.v_cache.normal_()
     eng.epi.uniform_(0.75, 0.95)
     eng.topk_ids.random_(0, cfg.vocab)
