@@ -178,7 +178,7 @@ def run_ours(args):
         for _ in range(args.warmup):
             hot_path()
         torch.cuda.synchronize()
-        eng.launch_count = eng.n_spec_steps = eng.n_fallbacks = 0
+        eng.launch_count = eng.n_spec_steps = eng.n_fallbacks = eng.n_chain = eng.n_chain_ok = 0
         if eng.spec_batch:
             eng._fb_total.zero_()
             eng._seq_steps_done = 0
@@ -204,6 +204,10 @@ def run_ours(args):
         spec = {"mode": "speculative single pass (K+1 contexts per weight stream; masked pass re-run only when y_init "
                         "restores a drawn visual token)" if (eng.spec_active or eng.spec_batch) else "two passes per token",
                 "steps": eng.n_spec_steps, "fallback_rate": round(eng.fallback_rate(), 4)}
+        if getattr(eng, "lookahead", False):
+            spec["lookahead"] = {"what": "the fallback pass of step t also carries the K+1 speculative contexts of step "
+                                         "t+1 (2K+1 contexts), built on the guessed vote of step t",
+                                 "passes": eng.n_chain, "guess_confirmed": eng.n_chain_ok}
 
         # ---- e2e: the public API, host tensors in, host tokens out ---------------------------------
         for _ in range(max(1, args.warmup - 1)):

@@ -266,6 +266,23 @@ class DropoutDecodeEngine:
             self.winner_p1 = torch.zeros(B, **i32)
             self.need_fb = torch.zeros(1, **i32)
             self.need_fb_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        # ---- lookahead inside the fallback pass (one sequence, see _spec_chain): 2K+1 contexts
+        la = os.environ.get("DD_LOOKAHEAD", "1") == "1"
+        self.lookahead = bool(la and fits and self.speculative != "off" and keep_relevant and 2 * self.K + 1 <= 16)
+        self.n_chain = self.n_chain_ok = 0
+        if self.lookahead:
+            K = self.K
+            self.pd = self._alloc_pass(2 * K + 1, est)
+            self.chain_mask = torch.zeros(B, 2 * K + 1, self.words, **i32)
+            self._g_tok, self._g_win = torch.zeros(B, **i32), torch.zeros(B, **i32)     # the guessed outcome of step t
+            self._g_ids = torch.zeros(B, K, **i32)
+            self._seq_p1, self._step_p1 = torch.zeros(B, **i32), torch.zeros(1, **i32)
+            self._ids_d = torch.zeros(B, K + 1, **i32)
+            self._win_d, self._tok_d = torch.zeros(B, **i32), torch.zeros(B, **i32)
+            self._win_pk = torch.zeros(B, **i32)
+            self.chain_flags = torch.zeros(2, **i32)                # {guess was right, step t+1 needs its fallback}
+            self.chain_flags_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self._g_out = (torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev) if aggregate == "mean" else None)
         self._sg_ws = None
         max_rows = B * (self.K + 1 if (self.spec_active or self.spec_batch) else self.K)
         if any(self._use_stream(r) for r in (B, max_rows)):
@@ -405,18 +422,20 @@ class DropoutDecodeEngine:
         return pb.logits
 
     # ------------------------------------------------------------------------------------
-    def _step_uniforms(self) -> Optional[torch.Tensor]:
+    def _step_uniforms(self, ahead: int = 0) -> Optional[torch.Tensor]:
         if self.uniforms is None:
             return None
         # parity mode: this step's pre-drawn numbers (device-side gather keeps the graph static)
-        self._u_step.copy_(self.uniforms.index_select(0, self.step_ctr.long().clamp(max=self.uniforms.shape[0] - 1))[0])
-        return self._u_step
+        buf = self._u_step if ahead == 0 else self._u_step1
+        buf.copy_(self.uniforms.index_select(0, (self.step_ctr.long() + ahead).clamp(max=self.uniforms.shape[0] - 1))[0])
+        return buf
 
-    def _sample(self, u, keep_relevant: bool, out, n_masked, per_seq: bool = False) -> None:
+    def _sample(self, u, keep_relevant: bool, out, n_masked, per_seq: bool = False, step=None) -> None:
+        if step is None:
+            step = self.seq_steps if per_seq else self.step_ctr
         ops.sample_masks(self.epi, self.topk_ids if keep_relevant else None, self.y_init if keep_relevant else None,
                          self.probs, mode=self.mode, keep_relevant=keep_relevant, uniforms=u, seed=self.seed, offset=0,
-                         step=self.seq_steps if per_seq else self.step_ctr, out=out, n_masked=n_masked,
-                         seq_base=self.seq_base, step_per_seq=per_seq)
+                         step=step, out=out, n_masked=n_masked, seq_base=self.seq_base, step_per_seq=per_seq)
         self.launches_per_step += 1
 
     def step(self) -> None:
@@ -495,7 +514,107 @@ class DropoutDecodeEngine:
             self.bitmask.copy_(self.spec_draw)
             self.n_masked.copy_(self._nm_spec)
             self.need_fb.zero_()
+        if self.lookahead:
+            self._guess_from(self.pc.logits, 1)
         self.need_fb_host.copy_(self.need_fb, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------
+    # Lookahead inside the fallback pass (one sequence).  When y_init restored a drawn token, step t needs a second
+    # weight stream for its K real-mask members anyway.  That stream also carries the K+1 speculative contexts of step
+    # t+1, built on a GUESS of step t's outcome: the token and the winning member voted by the wrong-mask members of
+    # the pass before (they differ from the real members only in the few restored tokens).  Rows 0..K-1: the members of
+    # step t (real masks, position S).  After the QKV projection of a layer the guessed winner's new K/V row is written
+    # to cache row S (the real commit overwrites it later); rows K..2K -- unmasked + the draws of step t+1, input =
+    # the guessed token, position S+1 -- then attend to rows [0, S] exactly as they would after a commit.  If the
+    # real vote confirms the guess, rows K..2K ARE step t+1's speculative pass, bit for bit, and its weight stream has
+    # been saved; if not, they are dropped.  Only views and existing kernels: two embed/rope/attention windows.
+    # ------------------------------------------------------------------------------------
+    def _guess_from(self, logits: torch.Tensor, first: int) -> None:
+        """Guess step t's (token, winner) from the wrong-mask members = rows first..first+K-1 of `logits`."""
+        ops.aggregate(logits, self.aggregate, member_ids=self._g_ids, winner=self._g_win, token=self._g_tok,
+                      out_logits=self._g_out, vocab=self.cfg.vocab, first_member=first, members=self.K)
+        self.launches_per_step += 1
+
+    def _attention_rows(self, pb: _PassBuffers, l: int, bitmask, seq_lens, m0: int, m1: int) -> None:
+        G = self.cfg.n_heads // self.cfg.n_kv_heads
+        per = max(1, 32 // G)
+        for a in range(m0, m1, per):
+            ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], seq_lens,
+                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws,
+                                 member_offset=a, members=min(per, m1 - a))
+            self.launches_per_step += 1 + (pb.splits == 1)
+
+    def _spec_chain(self) -> None:
+        self.launches_per_step = 0
+        cfg, K, pd = self.cfg, self.K, self.pd
+        H, Hkv, D, M = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, 2 * self.K + 1
+        torch.add(self.seq_lens, 1, out=self._seq_p1)
+        torch.add(self.step_ctr, 1, out=self._step_p1)
+        self._sample(self._step_uniforms(1), False, self.spec_draw, self._nm_spec, step=self._step_p1)   # draws of t+1
+        self.chain_mask[:, :K].copy_(self.bitmask)
+        self.chain_mask[:, K + 1:].copy_(self.spec_draw)
+        ops.embed_gather(self.w.embed, self.cur_token, K, pd.x[:K])
+        ops.embed_gather(self.w.embed, self._g_tok, K + 1, pd.x[K:])
+        x, x2 = pd.x, pd.x2
+        for l, lw in enumerate(self.w.layers):
+            ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pd.xn)
+            ops.decoder_linear(pd.xn, lw["wqkv"], ops.EPI_NONE, out=pd.qkv)
+            kn, vn = pd.k_new[l], pd.v_new[l]
+            ops.rope_stage(pd.qkv[:K], self.cos, self.sin, self.seq_lens, 1, K, H, Hkv, D, pd.q[:, :K], kn[:, :K],
+                           vn[:, :K])
+            ops.rope_stage(pd.qkv[K:], self.cos, self.sin, self._seq_p1, 1, K + 1, H, Hkv, D, pd.q[:, K:], kn[:, K:],
+                           vn[:, K:])
+            ops.commit_winner(pd.k_new[l:l + 1], pd.v_new[l:l + 1], self._g_win, self.seq_lens, self.k_cache[l:l + 1],
+                              self.v_cache[l:l + 1])
+            self._attention_rows(pd, l, self.chain_mask, self.seq_lens, 0, K)
+            self._attention_rows(pd, l, self.chain_mask, self._seq_p1, K, M)
+            ops.decoder_linear(pd.attn.view(M, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
+            ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pd.xn)
+            ops.decoder_linear(pd.xn, lw["wgu"], ops.EPI_SWIGLU, out=pd.act)
+            ops.decoder_linear(pd.act, lw["wd"], ops.EPI_RESIDUAL, residual=x2, out=x)
+            self.launches_per_step += 9
+        ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pd.xn)
+        ops.decoder_linear(pd.xn, self.w.lm_head_padded, ops.EPI_F32, out=pd.logits.view(M, self.Vp))
+        V, mean = cfg.vocab, self.aggregate == "mean"
+        # ---- step t: the reference's vote over its K real-mask members (rows 0..K-1)
+        ops.aggregate(pd.logits, self.aggregate, member_ids=self.member_ids, winner=self.winner, token=self.next_token,
+                      out_logits=self.out_logits if mean else None, vocab=V, first_member=0, members=K)
+        if mean:
+            ops.token_stats(self.out_logits, V, self.token_stats, slot=self.step_ctr, slot_offset=1)
+        else:
+            ops.token_stats(pd.logits, V, self.token_stats, member=self.winner, slot=self.step_ctr, slot_offset=1)
+        ops.commit_winner(pd.k_new, pd.v_new, self.winner, self.seq_lens, self.k_cache, self.v_cache)
+        ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
+        self.cur_token.copy_(self.next_token)
+        ok = (self.next_token == self._g_tok) & (self.winner == self._g_win)
+        # ---- step t+1 as _spec_head would see it (only meaningful when the guess was right)
+        ops.aggregate(pd.logits, "vote", member_ids=self._ids_d, winner=self._win_d, token=self._tok_d, vocab=V,
+                      first_member=K, members=K + 1)
+        self.y_init.copy_(self._ids_d[:, 0])
+        self._sample(self._step_uniforms(0), True, self.bitmask, self.n_masked)            # the reference's masks of t+1
+        fb = (self.bitmask != self.spec_draw).any()
+        self.chain_flags.copy_(torch.stack([ok.all(), fb]).to(torch.int32))
+        self.launches_per_step += 10
+        self._guess_from(pd.logits, K + 1)          # should step t+1 fall back too: its own guess
+        self.chain_flags_host.copy_(self.chain_flags, non_blocking=True)
+
+    def _spec_fin_chain(self) -> None:
+        """Step t+1 completed by the lookahead rows: members = rows K+1..2K of the chain pass."""
+        self.launches_per_step = 0
+        K, pd = self.K, self.pd
+        ops.aggregate(pd.logits, self.aggregate, member_ids=self.member_ids, winner=self.winner,
+                      token=self.next_token, out_logits=self.out_logits if self.aggregate == "mean" else None,
+                      vocab=self.cfg.vocab, first_member=K + 1, members=K)
+        torch.add(self.winner, K + 1, out=self._win_pk)
+        if self.aggregate == "mean":
+            ops.token_stats(self.out_logits, self.cfg.vocab, self.token_stats, slot=self.step_ctr, slot_offset=1)
+        else:
+            ops.token_stats(pd.logits, self.cfg.vocab, self.token_stats, member=self._win_pk, slot=self.step_ctr,
+                            slot_offset=1)
+        ops.commit_winner(pd.k_new, pd.v_new, self._win_pk, self.seq_lens, self.k_cache, self.v_cache)
+        ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
+        self.cur_token.copy_(self.next_token)
+        self.launches_per_step += 5
 
     def _spec_fin(self) -> None:
         """The speculated masks were the real ones: rows 1..K of the speculative pass are the K members."""
@@ -593,25 +712,67 @@ class DropoutDecodeEngine:
             return float(self._fb_total.item()) / max(1, self._seq_steps_done)
         return self.n_fallbacks / max(1, self.n_spec_steps)
 
-    def _spec_step(self, graphs: Optional[dict]) -> None:
-        """One ensemble step through the speculative path; `graphs` = captured pieces or None (eager)."""
-        def run(name, fn):
-            if graphs is not None:
-                graphs[name][0].replay()
-                self.launch_count += graphs[name][1]
-            else:
-                fn()
-                self.launch_count += self.launches_per_step
-        run("head", self._spec_head)
-        torch.cuda.current_stream().synchronize()          # the one host decision of the step
-        self.n_spec_steps += 1
-        if int(self.need_fb_host[0]):
-            self.n_fallbacks += 1
-            self._last_src = "pb"
-            run("fallback", self._spec_fallback)
+    def _run_piece(self, graphs: Optional[dict], name: str, fn) -> None:
+        if graphs is not None:
+            graphs[name][0].replay()
+            self.launch_count += graphs[name][1]
         else:
-            self._last_src = "pc"
-            run("fin", self._spec_fin)
+            fn()
+            self.launch_count += self.launches_per_step
+
+    def _spec_steps(self, n_steps: int, graphs: Optional[dict]) -> None:
+        """n_steps ensemble steps through the speculative path (one sequence); `graphs` = captured pieces or None
+        (eager).  One host decision (a stream synchronisation) per pass.  Lookahead state never outlives the call."""
+        run = lambda name, fn: self._run_piece(graphs, name, fn)
+        sync = torch.cuda.current_stream().synchronize
+        i, src, need_fb = 0, None, False        # src: which pass already served as step i's speculative pass
+        while i < n_steps:
+            if not self.spec_active:            # the adaptive switch fired: the reference's own order
+                if graphs is not None:
+                    if self._graph is None:
+                        self.capture()
+                    self._graph.replay()
+                else:
+                    self._two_pass_step()
+                self.launch_count += self.launches_per_step
+                self._last_src = "pb"
+                i += 1
+                continue
+            if src is None:
+                run("head", self._spec_head)
+                sync()
+                need_fb, src = bool(int(self.need_fb_host[0])), "pc"
+            self.n_spec_steps += 1
+            if not need_fb:
+                if src == "pc":
+                    run("fin", self._spec_fin)
+                    self._last_src = "pc"
+                else:
+                    run("fin_chain", self._spec_fin_chain)
+                    self._last_src = "pd1"
+                src = None
+            else:
+                self.n_fallbacks += 1
+                if self.lookahead and n_steps - i >= 2:
+                    run("chain", self._spec_chain)
+                    sync()
+                    self.n_chain += 1
+                    self._last_src = "pd0"
+                    if int(self.chain_flags_host[0]):
+                        self.n_chain_ok += 1
+                        need_fb, src = bool(int(self.chain_flags_host[1])), "pd"
+                    else:
+                        src = None
+                else:
+                    run("fallback", self._spec_fallback)
+                    self._last_src = "pb"
+                    src = None
+            i += 1
+            # adaptive: when almost every step needs the fallback (a checkpoint whose next token is nearly always one
+            # of the visual tokens' top-k ids) and the lookahead cannot absorb it, the reference's order is cheaper
+            n, f = self.n_spec_steps - self._spec_base[0], self.n_fallbacks - self._spec_base[1]
+            if self.speculative == "auto" and not self.lookahead and n >= 32 and f > 0.8 * n and src is None:
+                self.spec_active = False
 
     def capture(self) -> None:
         """Warm up once eagerly (restoring the state), then capture one step into a CUDA graph (two-pass path) or
@@ -624,6 +785,9 @@ class DropoutDecodeEngine:
                 self._spec_head(); self._spec_fin()
                 self._restore(snap)
                 self._spec_head(); self._spec_fallback()
+                if self.lookahead:
+                    self._restore(snap)
+                    self._spec_head(); self._spec_chain(); self._spec_fin_chain()
             else:
                 self.step()
         torch.cuda.current_stream().wait_stream(s)
@@ -631,7 +795,11 @@ class DropoutDecodeEngine:
         self._restore(snap)
         if self.spec_active:
             graphs = {}
-            for name, fn in (("head", self._spec_head), ("fin", self._spec_fin), ("fallback", self._spec_fallback)):
+            pieces = [("head", self._spec_head), ("fin", self._spec_fin), ("fallback", self._spec_fallback)]
+            if self.lookahead:
+                pieces += [("chain", self._spec_chain), ("fin_chain", self._spec_fin_chain)]
+            for name, fn in pieces:
+                self._restore(snap)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     fn()
@@ -640,6 +808,10 @@ class DropoutDecodeEngine:
             self._restore(snap)
             self._graphs = graphs
             return
+        self._capture_two_pass(snap)
+
+    def _capture_two_pass(self, snap=None) -> None:
+        snap = snap or self._snapshot()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.step()
@@ -670,22 +842,16 @@ class DropoutDecodeEngine:
             self.capture()
         if self.spec_batch:
             return self._decode_async(n_steps, use_graph)
+        if self.spec_active:
+            return self._spec_steps(n_steps, self._graphs if use_graph else None)
         for _ in range(n_steps):
-            if self.spec_active:
-                self._spec_step(self._graphs if use_graph else None)
-                # adaptive: when almost every step needs the fallback (a checkpoint whose next token is nearly always
-                # one of the visual tokens' top-k ids, or a large batch), the reference's own order is cheaper
-                n, f = self.n_spec_steps - self._spec_base[0], self.n_fallbacks - self._spec_base[1]
-                if self.speculative == "auto" and n >= 32 and f > 0.8 * n:
-                    self.spec_active = False
+            if use_graph:
+                if self._graph is None:
+                    self.capture()
+                self._graph.replay()
             else:
-                if use_graph:
-                    if self._graph is None:
-                        self.capture()
-                    self._graph.replay()
-                else:
-                    self.step()
-                self.launch_count += self.launches_per_step
+                self.step()
+            self.launch_count += self.launches_per_step
 
     def _decode_async(self, n_steps: int, use_graph: bool) -> None:
         """Passes of the asynchronous batch schedule until every sequence has advanced n_steps: n_steps passes, then
@@ -791,11 +957,12 @@ class DropoutDecodeEngine:
         if u is None:
             if self.uniforms is not None:
                 self._graph = self._graphs = None   # the captured step reads the uniforms buffer: re-capture without it
-            self.uniforms = self._u_step = None
+            self.uniforms = self._u_step = self._u_step1 = None
             return
         self._graph = self._graphs = None
         self.uniforms = u.to(self.dev, torch.float32).contiguous()
         self._u_step = torch.empty(self.B, self.K, self.n_vis, dtype=torch.float32, device=self.dev)
+        self._u_step1 = torch.empty_like(self._u_step)
 
     def step_logits(self) -> torch.Tensor:
         """fp32 [B, V]: what the reference's forward() returns after a decode step -- the winning
@@ -809,6 +976,10 @@ class DropoutDecodeEngine:
             return self.pa.logits[:, 0, :V]
         if self._last_src == "pc":          # the speculative pass was the real one: members are rows 1..K
             return self.pc.logits[self._rows(), self.winner.long() + 1, :V]
+        if self._last_src == "pd0":         # lookahead pass: the step's members are rows 0..K-1 ...
+            return self.pd.logits[self._rows(), self.winner.long(), :V]
+        if self._last_src == "pd1":         # ... and the following step's are rows K+1..2K
+            return self.pd.logits[self._rows(), self.winner.long() + self.K + 1, :V]
         return self.pb.logits[self._rows(), self.winner.long(), :V]
 
     def _rows(self) -> torch.Tensor:

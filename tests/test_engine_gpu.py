@@ -193,6 +193,45 @@ def test_speculative_pass_equals_two_pass_bit_for_bit(tiny, cuda):
 
 
 @pytest.mark.parametrize("aggregate", ["vote", "mean"])
+@pytest.mark.parametrize("use_graph", [True, False], ids=["cuda_graph", "eager"])
+def test_lookahead_in_fallback_pass_equals_two_pass(tiny, cuda, aggregate, use_graph):
+    """Multi-step decode calls let the fallback pass of step t carry the speculative contexts of step t+1 (2K+1 = 7
+    contexts, built on the guessed vote of step t, the guessed winner's K/V row written ahead into the cache).  Right
+    or wrong guess, the result equals the two-pass engine's bit for bit: tokens, the state of the last step, the
+    returned logits, the whole committed cache, the per-token statistics."""
+    tr = tiny["trace"]
+    engs = []
+    for spec in ("on", "off"):
+        eng = make_engine(tiny, cuda, speculative=spec, aggregate=aggregate)
+        inject_oracle_prefill(eng, tiny, cuda)
+        eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda))
+        eng.topk_ids.copy_(tr.topk_ids.to(cuda).int())
+        eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None])
+        engs.append(eng)
+    a, b = engs
+    assert a.spec_active and a.lookahead and not b.spec_active
+    left, chunks = TINY_T - 1, [6, 2, 1, 9, 3]
+    while left > 0:
+        n = min(chunks.pop(0) if chunks else left, left)
+        a.decode(n, use_graph=use_graph)
+        b.decode(n, use_graph=use_graph)
+        torch.cuda.synchronize()
+        left -= n
+        assert torch.equal(a.generated(), b.generated()), f"{left} steps left: tokens"
+        for name in ("y_init", "bitmask", "n_masked", "member_ids", "winner", "next_token", "seq_lens", "cur_token"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"{left} steps left: {name}"
+        assert torch.equal(a.step_logits(), b.step_logits()), f"{left} steps left: returned logits"
+        S = int(a.seq_lens[0])
+        assert torch.equal(a.k_cache[:, :, :, :S], b.k_cache[:, :, :, :S]), f"{left} steps left: K cache"
+        assert torch.equal(a.v_cache[:, :, :, :S], b.v_cache[:, :, :, :S]), f"{left} steps left: V cache"
+    assert torch.equal(a.token_stats[:TINY_T], b.token_stats[:TINY_T])
+    if aggregate == "vote":
+        assert a.generated()[0].tolist() == tr.tokens
+    assert a.n_spec_steps == TINY_T - 1 and 0 < a.n_chain <= a.n_fallbacks, (a.n_chain, a.n_fallbacks)
+    assert a.n_chain_ok > 0, "no lookahead was ever confirmed"
+
+
+@pytest.mark.parametrize("aggregate", ["vote", "mean"])
 def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate):
     """B=12 (48 contexts: above the small-batch kernels) runs the asynchronous batch schedule: one K+1-context pass
     per call, sequences whose speculated masks were wrong repeat the step with the real masks and fall behind.
