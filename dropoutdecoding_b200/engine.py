@@ -158,6 +158,8 @@ class DropoutDecodeEngine:
         self.probs, self.mode, self.keep_relevant = [float(p) for p in probs], mode, keep_relevant
         self.topk, self.aggregate, self.seed, self.round_logits = topk, aggregate, seed, round_logits
         self.fuse_norm = os.environ.get("DD_FUSE_NORM", "0") == "1"
+        self.prefill_graph = os.environ.get("DD_PREFILL_GRAPH", "1") == "1"
+        self._prefill_graphs: dict = {}
         # Weight GEMMs by row count (rows = sequences x members of a pass); measured on B200 (profiles/README.md 4):
         #   rows <= 16        dd_skinny_gemm / dd_decoder_linear (mma.sync, RoPE fused into the QKV epilogue)
         #   16 < rows <= 32   dd_stream_gemm (tcgen05, stream-K) -- 1.4-1.6x faster than the skinny kernel there
@@ -255,6 +257,31 @@ class DropoutDecodeEngine:
                 self._out_c = torch.zeros(B, V, dtype=torch.float32, device=dev)
             if vote_on == "hidden":
                 self._hid32c = torch.zeros(B, self.K + 1, cfg.d_model, dtype=torch.float32, device=dev)
+        # batches with lookahead (_spec_batch_la_step): 2K+1 context slots per sequence.  Measured on the bench workload
+        # (7B, fallback rate 0.37-0.41, tokens/s with / without): B=3 591/446, B=4 742/555, B=8 1502/1158, B=16 2435/2097,
+        # B=32 3226/3138; LLaVA-NeXT K=8 B=2 271/203; but B=2 K=3 399/426 (14 rows leave the fused <=16-row kernels) and
+        # no gain once the pass is compute-bound -> auto = 16 < rows <= 256.  DD_BATCH_LA=0|1 overrides.
+        bla = os.environ.get("DD_BATCH_LA", "auto")
+        self.batch_la = bool(self.spec_batch and vote_on == "logits" and keep_relevant and 2 * self.K + 1 <= 32
+                             and (bla == "1" or (bla == "auto" and 16 < B * (2 * self.K + 1) <= 256)))
+        if self.batch_la:
+            K, M = self.K, 2 * self.K + 1
+            self.pe = self._alloc_pass(M, est)
+            self.la_mask = torch.zeros(B, M, self.words, **i32)
+            self._g_tok, self._g_win = torch.zeros(B, **i32), torch.zeros(B, **i32)
+            self._gw = torch.zeros(B, **i32)
+            self._steps_spec, self._seq_p = torch.zeros(B, **i32), torch.zeros(B, **i32)
+            self._row_tok, self._row_pos = torch.zeros(B * M, **i32), torch.zeros(B * M, **i32)
+            self._act1, self._act2 = torch.zeros(B, **i32), torch.zeros(B, **i32)
+            self._y_new = torch.zeros(B, **i32)
+            self._ids_v, self._ids_s = torch.zeros(B, K, **i32), torch.zeros(B, K + 1, **i32)
+            self._win_v, self._tok_v = torch.zeros(B, **i32), torch.zeros(B, **i32)
+            self._win_s, self._tok_s = torch.zeros(B, **i32), torch.zeros(B, **i32)
+            self._w1, self._w2, self._tok1 = torch.zeros(B, **i32), torch.zeros(B, **i32), torch.zeros(B, **i32)
+            self._adv2 = torch.zeros(B, **i32)
+            if aggregate == "mean":
+                self._out_v = torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev)
+                self._out1 = torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev)
         if self.spec_active or self.spec_batch:
             self.pc = self._alloc_pass(self.K + 1, est)
             self.spec_draw = torch.zeros(B, self.K, self.words, **i32)
@@ -285,6 +312,8 @@ class DropoutDecodeEngine:
             self._g_out = (torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev) if aggregate == "mean" else None)
         self._sg_ws = None
         max_rows = B * (self.K + 1 if (self.spec_active or self.spec_batch) else self.K)
+        if self.batch_la:
+            max_rows = B * (2 * self.K + 1)
         if any(self._use_stream(r) for r in (B, max_rows)):
             d, dff, qkv_rows = cfg.d_model, cfg.d_ff, (H + 2 * Hkv) * D
             shapes = [(qkv_rows, d, ops.EPI_NONE), (d, H * D, ops.EPI_RESIDUAL), (dff, d, ops.EPI_SWIGLU),
@@ -430,10 +459,11 @@ class DropoutDecodeEngine:
         buf.copy_(self.uniforms.index_select(0, (self.step_ctr.long() + ahead).clamp(max=self.uniforms.shape[0] - 1))[0])
         return buf
 
-    def _sample(self, u, keep_relevant: bool, out, n_masked, per_seq: bool = False, step=None) -> None:
+    def _sample(self, u, keep_relevant: bool, out, n_masked, per_seq: bool = False, step=None, y=None) -> None:
         if step is None:
             step = self.seq_steps if per_seq else self.step_ctr
-        ops.sample_masks(self.epi, self.topk_ids if keep_relevant else None, self.y_init if keep_relevant else None,
+        y = self.y_init if y is None else y
+        ops.sample_masks(self.epi, self.topk_ids if keep_relevant else None, y if keep_relevant else None,
                          self.probs, mode=self.mode, keep_relevant=keep_relevant, uniforms=u, seed=self.seed, offset=0,
                          step=step, out=out, n_masked=n_masked, seq_base=self.seq_base, step_per_seq=per_seq)
         self.launches_per_step += 1
@@ -441,7 +471,7 @@ class DropoutDecodeEngine:
     def step(self) -> None:
         """One ensemble step for every sequence; asynchronous, no host sync, graph-capturable."""
         if self.spec_batch:
-            return self._spec_batch_step()
+            return self._spec_batch_la_step() if self.batch_la else self._spec_batch_step()
         return self._two_pass_step()
 
     def _two_pass_step(self) -> None:
@@ -535,13 +565,13 @@ class DropoutDecodeEngine:
                       out_logits=self._g_out, vocab=self.cfg.vocab, first_member=first, members=self.K)
         self.launches_per_step += 1
 
-    def _attention_rows(self, pb: _PassBuffers, l: int, bitmask, seq_lens, m0: int, m1: int) -> None:
+    def _attention_rows(self, pb: _PassBuffers, l: int, bitmask, seq_lens, m0: int, m1: int, seq_active=None) -> None:
         G = self.cfg.n_heads // self.cfg.n_kv_heads
         per = max(1, 32 // G)
         for a in range(m0, m1, per):
             ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], seq_lens,
                                  self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws,
-                                 member_offset=a, members=min(per, m1 - a))
+                                 seq_active=seq_active, member_offset=a, members=min(per, m1 - a))
             self.launches_per_step += 1 + (pb.splits == 1)
 
     def _spec_chain(self) -> None:
@@ -705,6 +735,126 @@ class DropoutDecodeEngine:
         self.in_fb.copy_((~ok & act).to(torch.int32))
         self._fb_total.add_(self.in_fb.sum())
         self.launches_per_step += 7
+
+    def _spec_batch_la_step(self) -> None:
+        """Asynchronous batch schedule with lookahead: 2K+1 context slots per sequence and pass.  Slots 0..K-1 ("verify")
+        run the real-mask members of a step whose speculated masks were wrong (idle otherwise); slots K..2K ("spec")
+        run the speculative contexts -- unmasked + draws -- of the sequence's next undecided step: the same step for a
+        sequence that is not repeating one, the FOLLOWING step, on the guessed outcome of the verify slots (token and
+        winning member voted by the wrong-mask members of the pass before; the guessed winner's K/V row is written
+        ahead into the cache, layer by layer), for one that is.  A confirmed guess makes the spec slots that following
+        step's speculative pass, so a sequence can complete two steps in one pass and a repeated step costs no extra
+        weight stream.  Everything is decided per sequence on the device; results equal the two-pass order bit for bit."""
+        self.launches_per_step = 0
+        cfg, B, K, pe = self.cfg, self.B, self.K, self.pe
+        V, M, mean = cfg.vocab, 2 * self.K + 1, self.aggregate == "mean"
+        H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
+        steps = self.seq_steps
+        act = steps < self.target
+        fb = self.in_fb.bool() & act
+        fb_i = fb.to(torch.int32)
+        self._steps_spec.copy_(steps + fb_i)
+        spec_on = act & (self._steps_spec < self.target)
+        u = None
+        if self.uniforms is not None:       # parity mode: the pre-drawn numbers of the step in the spec slots
+            idx = self._steps_spec.long().clamp(max=self.uniforms.shape[0] - 1)
+            self._u_step.copy_(self.uniforms[idx, self._rows()])
+            u = self._u_step
+        self._sample(u, False, self.spec_draw, self._nm_spec, per_seq=True, step=self._steps_spec)
+        self.la_mask[:, :K].copy_(self.bitmask)
+        self.la_mask[:, K + 1:].copy_(self.spec_draw)
+        rt, rp = self._row_tok.view(B, M), self._row_pos.view(B, M)
+        rt[:, :K] = self.cur_token[:, None]
+        rt[:, K:] = torch.where(fb, self._g_tok, self.cur_token)[:, None]
+        self._seq_p.copy_(self.seq_lens + fb_i)
+        rp[:, :K] = self.seq_lens[:, None]
+        rp[:, K:] = self._seq_p[:, None]
+        self._act1.copy_(fb_i)
+        self._act2.copy_(spec_on.to(torch.int32))
+        self._gw.copy_(torch.where(fb, self._g_win, self._minus1))
+        # ---- the pass
+        rows = B * M
+        ops.embed_gather(self.w.embed, self._row_tok, 1, pe.x)
+        x, x2 = pe.x, pe.x2
+        for l, lw in enumerate(self.w.layers):
+            ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pe.xn)
+            self._linear(pe.xn, lw["wqkv"], ops.EPI_NONE, pe.qkv)
+            ops.rope_stage(pe.qkv, self.cos, self.sin, self._row_pos, rows, 1, H, Hkv, D, pe.q, pe.k_new[l], pe.v_new[l])
+            ops.commit_winner(pe.k_new[l:l + 1], pe.v_new[l:l + 1], self._gw, self.seq_lens, self.k_cache[l:l + 1],
+                              self.v_cache[l:l + 1])                                   # the guessed winner's row, ahead
+            self._attention_rows(pe, l, self.la_mask, self.seq_lens, 0, K, seq_active=self._act1)
+            self._attention_rows(pe, l, self.la_mask, self._seq_p, K, M, seq_active=self._act2)
+            if rows <= 32 and self.gemm_backend == "auto":
+                ops.skinny_gemm(pe.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
+                self.launches_per_step += 1
+            else:
+                self._linear(pe.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, x2, residual=x)
+            ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pe.xn)
+            self._linear(pe.xn, lw["wgu"], ops.EPI_SWIGLU, pe.act)
+            self._linear(pe.act, lw["wd"], ops.EPI_RESIDUAL, x, residual=x2)
+            self.launches_per_step += 4
+        ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pe.xn)
+        self._linear(pe.xn, self.w.lm_head_padded, ops.EPI_F32, pe.logits.view(rows, self.Vp))
+        self.launches_per_step += 2
+        # ---- votes: verify slots, per-row argmax of the spec slots, members among the spec slots
+        ops.aggregate(pe.logits, self.aggregate, member_ids=self._ids_v, winner=self._win_v, token=self._tok_v,
+                      out_logits=self._out_v if mean else None, vocab=V, first_member=0, members=K)
+        ops.aggregate(pe.logits, "vote", member_ids=self._ids_s, winner=self._win_s, token=self._tok_s, vocab=V,
+                      first_member=K, members=K + 1)
+        self._y_new.copy_(self._ids_s[:, 0])
+        self._sample(u, True, self._mask_real, self._nm_real, per_seq=True, step=self._steps_spec, y=self._y_new)
+        eq = (self._mask_real == self.spec_draw).flatten(1).all(1)
+        ops.aggregate(pe.logits, self.aggregate, member_ids=self._ids_c, winner=self._win_c, token=self._tok_sc,
+                      out_logits=self._out_c if mean else None, vocab=V, first_member=K + 1, members=K)
+        self.launches_per_step += 5
+        chain_ok = fb & spec_on & (self._tok_v == self._g_tok) & (self._win_v == self._g_win)
+        valid = (act & ~fb) | chain_ok              # the spec slots were a real speculative pass of step _steps_spec
+        adv1 = fb | (valid & ~fb & eq)
+        adv2 = chain_ok & eq
+        win_m = self._win_c + (K + 1)
+        self._w1.copy_(torch.where(adv1, torch.where(fb, self._win_v, win_m), self._minus1))
+        self._w2.copy_(torch.where(adv2, win_m, self._minus1))
+        self._tok1.copy_(torch.where(fb, self._tok_v, self._tok_sc))
+        self.adv.copy_(adv1.to(torch.int32))
+        self._adv2.copy_(adv2.to(torch.int32))
+        # ---- per-step views: the step in the spec slots (completed or to be repeated) / the last completed step
+        self.y_init.copy_(torch.where(valid, self._y_new, self.y_init))
+        self.bitmask.copy_(torch.where(valid[:, None, None], self._mask_real, self.bitmask))
+        self.n_masked.copy_(torch.where(valid[:, None], self._nm_real, self.n_masked))
+        ids1 = torch.where(fb[:, None], self._ids_v, self._ids_c)
+        self.member_ids.copy_(torch.where(adv2[:, None], self._ids_c, torch.where(adv1[:, None], ids1, self.member_ids)))
+        self.winner.copy_(torch.where(adv2, self._win_c, torch.where(adv1, torch.where(fb, self._win_v, self._win_c),
+                                                                      self.winner)))
+        self.next_token.copy_(torch.where(adv2, self._tok_sc, torch.where(adv1, self._tok1, self.next_token)))
+        self.winner_p1.copy_(torch.where(adv2, self._w2, self._w1))       # row of the pass that holds the returned logits
+        if mean:
+            self._out1.copy_(torch.where(fb[:, None], self._out_v, self._out_c))
+            self.out_logits.copy_(torch.where(adv2[:, None], self._out_c,
+                                              torch.where(adv1[:, None], self._out1, self.out_logits)))
+            self.ret_logits.copy_(self.out_logits)
+            ops.token_stats(self._out1, V, self.token_stats, member=torch.where(adv1, self._zero, self._minus1),
+                            slot=steps, slot_offset=1, slot_per_seq=True)
+        else:
+            r = self.pe.logits[self._rows(), self.winner_p1.clamp(min=0).long(), :V]
+            self.ret_logits.copy_(torch.where((adv1 | adv2)[:, None], r, self.ret_logits))
+            ops.token_stats(pe.logits, V, self.token_stats, member=self._w1, slot=steps, slot_offset=1,
+                            slot_per_seq=True)
+        ops.commit_winner(pe.k_new, pe.v_new, self._w1, self.seq_lens, self.k_cache, self.v_cache)
+        ops.step_advance_seq(self._tok1, self.adv, self.tokens_out, self.seq_lens, steps)
+        if mean:
+            ops.token_stats(self._out_c, V, self.token_stats, member=torch.where(adv2, self._zero, self._minus1),
+                            slot=steps, slot_offset=1, slot_per_seq=True)
+        else:
+            ops.token_stats(pe.logits, V, self.token_stats, member=self._w2, slot=steps, slot_offset=1,
+                            slot_per_seq=True)
+        ops.commit_winner(pe.k_new, pe.v_new, self._w2, self.seq_lens, self.k_cache, self.v_cache)
+        ops.step_advance_seq(self._tok_sc, self._adv2, self.tokens_out, self.seq_lens, steps)
+        self.cur_token.copy_(torch.where(adv2, self._tok_sc, torch.where(adv1, self._tok1, self.cur_token)))
+        self._g_tok.copy_(self._tok_sc)
+        self._g_win.copy_(self._win_c)
+        self.in_fb.copy_((valid & ~eq).to(torch.int32))
+        self._fb_total.add_(self.in_fb.sum())
+        self.launches_per_step += 6
 
     def fallback_rate(self) -> float:
         """Fraction of (step, sequence) pairs whose masked pass had to be re-run with the real masks."""
@@ -870,7 +1020,7 @@ class DropoutDecodeEngine:
                 if use_graph:
                     self._graph.replay()
                 else:
-                    self._spec_batch_step()
+                    self.step()
                 self.launch_count += self.launches_per_step
                 self.n_spec_steps += 1
 
@@ -892,6 +1042,35 @@ class DropoutDecodeEngine:
     def prefill(self, embeds: torch.Tensor, vis_start: Sequence[int]) -> torch.Tensor:
         """embeds bf16 [B, S0, d] (merged text|visual|text).  Fills the cache and returns the
         final-norm hidden states [B, S0, d]."""
+        if self.prefill_graph and embeds.is_cuda:
+            # the ~1500 library launches of a prefill are host-bound when issued eagerly (7B, 593 positions: 16.0 ms
+            # eager, 13.0 ms replayed): one graph per prompt length, replayed on a static input buffer
+            ent = self._prefill_graphs.get(embeds.shape[1])
+            if ent is None:
+                if len(self._prefill_graphs) >= 4:
+                    self._prefill_graphs.clear()
+                buf = embeds.to(torch.bfloat16).clone()
+                s = torch.cuda.Stream(device=self.dev)
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._prefill_layers(buf)
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = self._prefill_layers(buf)
+                ent = self._prefill_graphs[embeds.shape[1]] = (g, buf, out)
+            g, buf, out = ent
+            buf.copy_(embeds)
+            g.replay()
+            hidden = out.clone()
+        else:
+            hidden = self._prefill_layers(embeds)
+        self.seq_lens.fill_(embeds.shape[1])
+        self.vis_start.copy_(torch.as_tensor(list(vis_start), dtype=torch.int32))
+        self.step_ctr.zero_()
+        return hidden
+
+    def _prefill_layers(self, embeds: torch.Tensor) -> torch.Tensor:
         cfg, B = self.cfg, self.B
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         S0 = embeds.shape[1]
@@ -917,9 +1096,6 @@ class DropoutDecodeEngine:
             h = self._norm_t(x, lw["ln2"])
             gu = F.linear(h, lw["wgu"])
             x = x + F.linear(F.silu(gu[..., :cfg.d_ff]) * gu[..., cfg.d_ff:], lw["wd"])
-        self.seq_lens.fill_(S0)
-        self.vis_start.copy_(torch.as_tensor(list(vis_start), dtype=torch.int32))
-        self.step_ctr.zero_()
         return self._norm_t(x, self.w.norm)
 
     def load_prefill(self, k: torch.Tensor, v: torch.Tensor, vis_start: Sequence[int]) -> None:

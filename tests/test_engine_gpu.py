@@ -231,15 +231,19 @@ def test_lookahead_in_fallback_pass_equals_two_pass(tiny, cuda, aggregate, use_g
     assert a.n_chain_ok > 0, "no lookahead was ever confirmed"
 
 
+@pytest.mark.parametrize("lookahead", ["lookahead", "plain"])
 @pytest.mark.parametrize("aggregate", ["vote", "mean"])
-def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate):
-    """B=12 (48 contexts: above the small-batch kernels) runs the asynchronous batch schedule: one K+1-context pass
+def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate, lookahead, monkeypatch):
+    """(lookahead: 2K+1 slots per sequence -- a sequence repeating a step with its real masks also runs the speculative
+    contexts of the following step on the guessed outcome and can complete two steps in one pass.)
+    B=12 (48 contexts: above the small-batch kernels) runs the asynchronous batch schedule: one K+1-context pass
     per call, sequences whose speculated masks were wrong repeat the step with the real masks and fall behind.
     Different sequences see different uniforms, so they drift apart; tokens, per-token statistics and the whole
     committed K/V cache still equal the two-pass engine's bit for bit, and every sequence decodes exactly what it
     decodes alone (sequence 0 replays the oracle trace)."""
     tr = tiny["trace"]
     B, T = 12, 18
+    monkeypatch.setenv("DD_BATCH_LA", "1" if lookahead == "lookahead" else "0")
     g = torch.Generator().manual_seed(99)
     U = torch.rand(T, B, 3, TINY_N_VIS, generator=g)
     U[:, 0] = tiny["U"][:T]                                    # sequence 0 replays the oracle trace
@@ -258,7 +262,7 @@ def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate):
         eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None].expand(B, -1).contiguous())
         engs.append(eng)
     a, b = engs
-    assert a.spec_batch and not a.spec_active and not b.spec_batch
+    assert a.spec_batch and not a.spec_active and not b.spec_batch and a.batch_la == (lookahead == "lookahead")
     for chunk, graph in ((1, False), (5, True), (1, True), (T - 8, True)):      # lockstep again after every call
         a.decode(chunk, use_graph=graph)
         b.decode(chunk, use_graph=True)

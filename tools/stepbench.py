@@ -61,4 +61,4 @@ with torch.no_grad():
                           tokens_per_s=round(a.batch * 1e3 / best, 1),
                           step_roofline_frac=round((wbytes + kv) / (best * 1e-3) / 6551.4e9, 3),
                           launches=eng.launches_per_step, spec=("host" if eng.spec_active else "batch" if eng.spec_batch else "off"),
-                          gemm=eng.gemm_backend, lookahead=([eng.n_chain, eng.n_chain_ok] if getattr(eng, "lookahead", False) else None), fallback_rate=round(eng.fallback_rate(), 3))))
+                          gemm=eng.gemm_backend, lookahead=([eng.n_chain, eng.n_chain_ok] if getattr(eng, "lookahead", False) else ("batch" if getattr(eng, "batch_la", False) else None)), passes=eng.n_spec_steps, fallback_rate=round(eng.fallback_rate(), 3))))
