@@ -225,6 +225,8 @@ class DropoutDecodeEngine:
         # one sequence: the host decides per step whether to fall back (the hidden-state vote of InstructBLIP always
         # takes the asynchronous schedule below, also at B = 1)
         fits = ok and B == 1 and vote_on == "logits"
+        if fits and keep_relevant and 16 < 2 * self.K + 1 <= 32 and os.environ.get("DD_BATCH_LA", "auto") != "0":
+            fits = False    # (K = 8: the 17 slots of the lookahead exceed the <= 16-row kernels; the batch schedule has it)
         if self.speculative == "on" and not ok:
             raise ops.DropDecError("speculative single pass needs K + 1 <= 16 contexts")
         self._spec_fits = fits

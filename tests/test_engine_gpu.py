@@ -282,14 +282,15 @@ def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate, lookahead, 
     assert 0.0 < a.fallback_rate() < 1.0 and a.n_spec_steps > T - 1, (a.fallback_rate(), a.n_spec_steps)
 
 
-def test_llava_next_shape_k8_gqa_speculative_equals_two_pass(cuda):
+@pytest.mark.parametrize("B", [2, 1])
+def test_llava_next_shape_k8_gqa_speculative_equals_two_pass(cuda, B):
     """LLaVA-NeXT-like head layout (4 query heads per kv head) with K=8 members: the 9-context pass has 36 query rows
     per kv head, served by two member windows of the attention kernel; independent masks (llavanext.py:546), Philox
     draws.  Equal to the two-pass engine bit for bit."""
     from dropoutdecoding_b200.engine import DecoderConfig, DecoderWeights, DropoutDecodeEngine
     cfg = DecoderConfig(2, 256, 8, 2, 64, 512, 32064, 1e-5, 1000000.0)
     w = DecoderWeights.random(cfg, cuda, seed=3, head_std=0.08)
-    probs, n_vis, S0, T, B = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], 700, 760, 10, 2
+    probs, n_vis, S0, T = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], 700, 760, 10
     engs = []
     for spec in ("auto", "off"):
         eng = DropoutDecodeEngine(w, B, n_vis, S0 + T + 4, probs=probs, mode="independent", topk=10, max_steps=32,
@@ -303,7 +304,7 @@ def test_llava_next_shape_k8_gqa_speculative_equals_two_pass(cuda):
         eng.cur_token.fill_(1234); eng.tokens_out[:, 0] = 1234
         engs.append(eng)
     a, b = engs
-    assert a.spec_batch and not b.spec_batch and not b.spec_active
+    assert a.spec_batch and a.batch_la and not b.spec_batch and not b.spec_active     # 17 slots per sequence
     for use_graph, n in ((False, 2), (True, T - 2)):
         a.decode(n, use_graph=use_graph)
         b.decode(n, use_graph=use_graph)
