@@ -597,8 +597,16 @@ static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   UncLayout L;
   L.n_strips = ceil_div(vocab, BN);
   L.n_chunks = ceil_div(n_vis, kMaxMT * BM);
-  int parts = ceil_div(num_sms(), (n_images > 0 ? n_images : 1) * L.n_chunks);
-  L.parts = parts < 1 ? 1 : (parts > L.n_strips ? L.n_strips : parts);
+  // CTAs per (image, row chunk): one CTA owns the whole TMEM, so a grid larger than the SM count runs in waves and
+  // 152 CTAs cost twice what 148 do.  Pick the split that minimises waves x strips-per-CTA (ties: fewer partials).
+  const int groups = (n_images > 0 ? n_images : 1) * L.n_chunks, sms = num_sms();
+  int best = 1;
+  long best_cost = -1;
+  for (int parts = 1; parts <= L.n_strips && parts <= sms; ++parts) {
+    const long cost = (long)ceil_div(parts * groups, sms) * ceil_div(L.n_strips, parts);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = parts; }
+  }
+  L.parts = best;
   const size_t rows = (size_t)n_images * L.parts * n_vis;
   size_t o = 0;
   L.off_stats = o; o = align_up(o + rows * 2 * sizeof(float), 256);

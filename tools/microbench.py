@@ -197,7 +197,8 @@ def bench_stream_gemm():
 
 
 def bench_uncertainty(only_first=False):
-    cases = [(1, 576, 4096, 32064, 5), (4, 576, 4096, 32064, 5), (8, 576, 4096, 32064, 5), (32, 32, 4096, 32001, 10)]
+    cases = [(1, 576, 4096, 32064, 5), (4, 576, 4096, 32064, 5), (8, 576, 4096, 32064, 5), (64, 576, 4096, 32064, 5),
+             (1, 2880, 4096, 32064, 10), (32, 32, 4096, 32001, 10)]
     for (n_img, n_vis, d, V, k) in cases[:1] if only_first else cases:
         h = torch.randn(n_img, n_vis, d, device=dev).bfloat16()
         w = (torch.randn(V, d, device=dev) * 0.02).bfloat16()
