@@ -61,6 +61,21 @@ constexpr float kEps = 1e-10f;  // models/llava.py:735,739
 
 constexpr uint32_t kIdesc = make_idesc_bf16(BM, BN);
 
+// The epilogue warps are alone on their scheduler (one warp per sub-partition), so the softmax sweeps are bound by
+// instructions issued per element.  exp2f / __logf carry a range fix-up for denormal results / arguments (4 extra
+// instructions each); here 2^x below 2^-126 may flush to zero (a probability < 1e-38) and the log argument is
+// >= 1e-10, so the bare MUFU forms are exact enough and identical in both sweeps.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ln_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * 0.6931471805599453f;
+}
+
 
 // ------------------------------------------------------------------------------------------
 struct UncParams {
@@ -318,11 +333,19 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (ok) {
               const int cbase = col0 + c * 32;
               float cmax = -INFINITY;
+              if (cbase + 32 <= p.vocab) {  // (CTA-uniform) all but the last strip: no per-element bound check
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (p.round_bf16) v[i] = bf16_round(v[i]);
-                if (cbase + i >= p.vocab) v[i] = -INFINITY;
-                cmax = fmaxf(cmax, v[i]);
+                for (int i = 0; i < 32; ++i) {
+                  if (p.round_bf16) v[i] = bf16_round(v[i]);
+                  cmax = fmaxf(cmax, v[i]);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  if (p.round_bf16) v[i] = bf16_round(v[i]);
+                  if (cbase + i >= p.vocab) v[i] = -INFINITY;
+                  cmax = fmaxf(cmax, v[i]);
+                }
               }
               smax = fmaxf(smax, cmax);
               if (cmax > st_m[mt]) {
@@ -332,7 +355,7 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               const float mneg = -st_m[mt] * kLog2e;
               float zs = 0.f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) zs += exp2f(fmaf(v[i], kLog2e, mneg));
+              for (int i = 0; i < 32; ++i) zs += ex2_ftz(fmaf(v[i], kLog2e, mneg));
               st_z[mt] += zs;
             }
           }
@@ -357,18 +380,23 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               tmem_ld32(lane_addr + mt * BN + c * 32, v);
               float cm = -INFINITY;  // chunk maximum of this row: any top-k candidate in here?
               if (ok) {
+                auto body = [&](auto padded) {  // padded: the chunk holds vocab columns past the end (last strip only)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  float x = v[i];
-                  if (p.round_bf16) x = bf16_round(x);
-                  cm = fmaxf(cm, x);
-                  float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
-                  float dv = pr - inv_v;
-                  if (col0 + c * 32 + i >= p.vocab) pr = dv = 0.f;  // padded vocab columns of the last strip
-                  colsum[i] += pr;
-                  acc_a[mt] = fmaf(pr, __logf(pr + kEps), acc_a[mt]);
-                  acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
-                }
+                  for (int i = 0; i < 32; ++i) {
+                    float x = v[i];
+                    if (p.round_bf16) x = bf16_round(x);
+                    cm = fmaxf(cm, x);
+                    float pr = ex2_ftz(fmaf(x, kLog2e, mneg)) * iz;
+                    float dv = pr - inv_v;
+                    if constexpr (decltype(padded)::value)
+                      if (col0 + c * 32 + i >= p.vocab) pr = dv = 0.f;
+                    colsum[i] += pr;
+                    acc_a[mt] = fmaf(pr, ln_ftz(pr + kEps), acc_a[mt]);
+                    acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
+                  }
+                };
+                if (col0 + c * 32 + 32 <= p.vocab) body(std::false_type{});
+                else body(std::true_type{});
               }
               if (__any_sync(0xffffffffu, cm >= st_tau[mt]))  // warp-uniform, ~1 chunk in 4
                 append_candidates(CandSink{p.cand_cnt, p.cand_val, p.cand_idx, p.cap, p.vocab, p.round_bf16},
@@ -416,14 +444,19 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               float v[32];
               tmem_ld32(lane_addr + mt * BN + c * 32, v);
               if (ok) {
+                auto body = [&](auto padded) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  float x = v[i];
-                  if (p.round_bf16) x = bf16_round(x);
-                  float pr = exp2f(fmaf(x, kLog2e, mneg)) * iz;
-                  if (col0 + c * 32 + i >= p.vocab) pr = 0.f;
-                  acc_c[mt] = fmaf(pr, s_logp[c * 32 + i], acc_c[mt]);
-                }
+                  for (int i = 0; i < 32; ++i) {
+                    float x = v[i];
+                    if (p.round_bf16) x = bf16_round(x);
+                    float pr = ex2_ftz(fmaf(x, kLog2e, mneg)) * iz;
+                    if constexpr (decltype(padded)::value)
+                      if (col0 + c * 32 + i >= p.vocab) pr = 0.f;
+                    acc_c[mt] = fmaf(pr, s_logp[c * 32 + i], acc_c[mt]);
+                  }
+                };
+                if (col0 + c * 32 + 32 <= p.vocab) body(std::false_type{});
+                else body(std::true_type{});
               }
             }
             tc_fence_before();
