@@ -30,6 +30,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
+from .schedules import SpeculativeSchedules
 
 
 @dataclass
@@ -140,7 +141,7 @@ class _PassBuffers:
     splits: int
 
 
-class DropoutDecodeEngine:
+class DropoutDecodeEngine(SpeculativeSchedules):
     """Static-shape engine for a batch of B sequences with the same number of visual tokens."""
 
     def __init__(self, weights: DecoderWeights, batch: int, n_vis: int, max_seq: int,
@@ -216,102 +217,7 @@ class DropoutDecodeEngine:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self.launch_count = 0           # kernels of this library launched by decode() so far (bench.py: gpu_launches)
-        # ---- speculative single pass (see _spec_head): "auto" = on whenever the K+1 contexts of all sequences fit the
-        #      small-batch kernels; DD_SPEC=off|on|auto overrides
-        self.speculative = speculative or os.environ.get("DD_SPEC", "auto")
-        if self.speculative not in ("auto", "on", "off"):
-            raise ValueError(self.speculative)
-        ok = self.K + 1 <= 16        # (more than 32 query rows per kv head: the attention runs in member groups)
-        # one sequence: the host decides per step whether to fall back (the hidden-state vote of InstructBLIP always
-        # takes the asynchronous schedule below, also at B = 1)
-        fits = ok and B == 1 and vote_on == "logits"
-        if fits and keep_relevant and 16 < 2 * self.K + 1 <= 32 and os.environ.get("DD_BATCH_LA", "auto") != "0":
-            fits = False    # (K = 8: the 17 slots of the lookahead exceed the <= 16-row kernels; the batch schedule has it)
-        if self.speculative == "on" and not ok:
-            raise ops.DropDecError("speculative single pass needs K + 1 <= 16 contexts")
-        self._spec_fits = fits
-        self.spec_active = fits and self.speculative != "off"
-        # batches: some sequence nearly always needs the fallback, so sequences advance independently instead
-        # (asynchronous batch schedule, _spec_batch_step; per-sequence flags on the device, no host decision)
-        self.spec_batch = ok and not fits and self.speculative != "off"
-        self.n_spec_steps = self.n_fallbacks = 0        # cumulative over the engine's life
-        self._seq_steps_done = 0
-        self._spec_base = (0, 0)                        # counters when the current sequence batch started
-        self._last_src = "pb"
-        self._graphs: Optional[dict] = None
-        if self.spec_batch:
-            V = cfg.vocab
-            self.seq_steps = torch.zeros(B, **i32)          # ensemble steps done, per sequence
-            self.in_fb = torch.zeros(B, **i32)              # 1: the next pass repeats this step with the real masks
-            self.target = torch.zeros(1, **i32)
-            self.active = torch.zeros(B, **i32)
-            self.adv = torch.zeros(B, **i32)
-            self._fb_total = torch.zeros(1, dtype=torch.int64, device=dev)
-            self._mask_tmp = torch.zeros(B, self.K, self.words, **i32)
-            self._mask_real = torch.zeros(B, self.K, self.words, **i32)
-            self._nm_real = torch.zeros(B, self.K, **i32)
-            self._ids_c = torch.zeros(B, self.K, **i32)
-            self._win_c, self._tok_sc = torch.zeros(B, **i32), torch.zeros(B, **i32)
-            self._minus1 = torch.full((B,), -1, **i32)
-            self._zero = torch.zeros(B, **i32)
-            self.ret_logits = torch.zeros(B, V, dtype=torch.float32, device=dev)
-            if aggregate == "mean":
-                self._out_c = torch.zeros(B, V, dtype=torch.float32, device=dev)
-            if vote_on == "hidden":
-                self._hid32c = torch.zeros(B, self.K + 1, cfg.d_model, dtype=torch.float32, device=dev)
-        # batches with lookahead (_spec_batch_la_step): 2K+1 context slots per sequence.  Measured on the bench workload
-        # (7B, fallback rate 0.37-0.41, tokens/s with / without): B=3 591/446, B=4 742/555, B=8 1502/1158, B=16 2435/2097,
-        # B=32 3226/3138; LLaVA-NeXT K=8 B=2 271/203; but B=2 K=3 399/426 (14 rows leave the fused <=16-row kernels) and
-        # no gain once the pass is compute-bound -> auto = 16 < rows <= 256.  DD_BATCH_LA=0|1 overrides.
-        bla = os.environ.get("DD_BATCH_LA", "auto")
-        self.batch_la = bool(self.spec_batch and vote_on == "logits" and keep_relevant and 2 * self.K + 1 <= 32
-                             and (bla == "1" or (bla == "auto" and 16 < B * (2 * self.K + 1) <= 256)))
-        if self.batch_la:
-            K, M = self.K, 2 * self.K + 1
-            self.pe = self._alloc_pass(M, est)
-            self.la_mask = torch.zeros(B, M, self.words, **i32)
-            self._g_tok, self._g_win = torch.zeros(B, **i32), torch.zeros(B, **i32)
-            self._gw = torch.zeros(B, **i32)
-            self._steps_spec, self._seq_p = torch.zeros(B, **i32), torch.zeros(B, **i32)
-            self._row_tok, self._row_pos = torch.zeros(B * M, **i32), torch.zeros(B * M, **i32)
-            self._act1, self._act2 = torch.zeros(B, **i32), torch.zeros(B, **i32)
-            self._y_new = torch.zeros(B, **i32)
-            self._ids_v, self._ids_s = torch.zeros(B, K, **i32), torch.zeros(B, K + 1, **i32)
-            self._win_v, self._tok_v = torch.zeros(B, **i32), torch.zeros(B, **i32)
-            self._win_s, self._tok_s = torch.zeros(B, **i32), torch.zeros(B, **i32)
-            self._w1, self._w2, self._tok1 = torch.zeros(B, **i32), torch.zeros(B, **i32), torch.zeros(B, **i32)
-            self._adv2 = torch.zeros(B, **i32)
-            if aggregate == "mean":
-                self._out_v = torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev)
-                self._out1 = torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev)
-        if self.spec_active or self.spec_batch:
-            self.pc = self._alloc_pass(self.K + 1, est)
-            self.spec_draw = torch.zeros(B, self.K, self.words, **i32)
-            self.spec_mask = torch.zeros(B, self.K + 1, self.words, **i32)       # member 0 = the unmasked context
-            self._nm_spec = torch.zeros(B, self.K, **i32)
-            self.member_ids_c = torch.zeros(B, self.K + 1, **i32)
-            self.winner_c = torch.zeros(B, **i32)
-            self._tok_c = torch.zeros(B, **i32)
-            self.winner_p1 = torch.zeros(B, **i32)
-            self.need_fb = torch.zeros(1, **i32)
-            self.need_fb_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-        # ---- lookahead inside the fallback pass (one sequence, see _spec_chain): 2K+1 contexts
-        la = os.environ.get("DD_LOOKAHEAD", "1") == "1"
-        self.lookahead = bool(la and fits and self.speculative != "off" and keep_relevant and 2 * self.K + 1 <= 16)
-        self.n_chain = self.n_chain_ok = 0
-        if self.lookahead:
-            K = self.K
-            self.pd = self._alloc_pass(2 * K + 1, est)
-            self.chain_mask = torch.zeros(B, 2 * K + 1, self.words, **i32)
-            self._g_tok, self._g_win = torch.zeros(B, **i32), torch.zeros(B, **i32)     # the guessed outcome of step t
-            self._g_ids = torch.zeros(B, K, **i32)
-            self._seq_p1, self._step_p1 = torch.zeros(B, **i32), torch.zeros(1, **i32)
-            self._ids_d = torch.zeros(B, K + 1, **i32)
-            self._win_d, self._tok_d = torch.zeros(B, **i32), torch.zeros(B, **i32)
-            self._win_pk = torch.zeros(B, **i32)
-            self.chain_flags = torch.zeros(2, **i32)                # {guess was right, step t+1 needs its fallback}
-            self.chain_flags_host = torch.zeros(2, dtype=torch.int32).pin_memory()
-            self._g_out = (torch.zeros(B, cfg.vocab, dtype=torch.float32, device=dev) if aggregate == "mean" else None)
+        self._init_schedules(speculative, est)
         self._sg_ws = None
         max_rows = B * (self.K + 1 if (self.spec_active or self.spec_batch) else self.K)
         if self.batch_la:
@@ -518,414 +424,6 @@ class DropoutDecodeEngine:
         self.cur_token.copy_(self.next_token)
         self.launches_per_step += 4
 
-    # ------------------------------------------------------------------------------------
-    # Speculative single pass.  The reference needs the preliminary forward only for y_init = argmax(unmasked
-    # logits), and y_init enters the masks only through the relevant set S = {i : y_init in topk_ids[i]} whose
-    # tokens are un-dropped (models/llava.py:443-482, 657-660).  The draws themselves do not depend on y_init.  So
-    # one pass runs K+1 contexts at once -- row 0 unmasked, rows 1..K with the draws as if S restored nothing -- at
-    # the cost of one weight stream instead of two.  y_init then comes out of row 0, the real masks are sampled, and
-    # if they equal the speculated ones (S empty, or none of its tokens was drawn: the common case) rows 1..K ARE
-    # the reference's K masked forwards, bit for bit.  Otherwise the masked pass is re-run with the real masks
-    # (the reference's own order).  With one sequence the host takes that decision per token (replacing the
-    # reference's >= 3K syncs); batches use the asynchronous schedule of _spec_batch_step instead.
-    # ------------------------------------------------------------------------------------
-    def _spec_head(self) -> None:
-        self.launches_per_step = 0
-        u = self._step_uniforms()
-        self._sample(u, False, self.spec_draw, self._nm_spec)
-        self.spec_mask[:, 1:].copy_(self.spec_draw)
-        logits_c = self._forward(self.pc, self.spec_mask)
-        ops.aggregate(logits_c, "vote", member_ids=self.member_ids_c, winner=self.winner_c, token=self._tok_c,
-                      vocab=self.cfg.vocab)                                        # per-row argmax of all K+1 contexts
-        self.launches_per_step += 1
-        self.y_init.copy_(self.member_ids_c[:, 0])
-        if self.keep_relevant:
-            self._sample(u, True, self.bitmask, self.n_masked)                     # the reference's masks
-            self.need_fb.copy_((self.bitmask != self.spec_draw).any().to(torch.int32).reshape(1))
-        else:                                                                      # epis_no_overlap: nothing to restore
-            self.bitmask.copy_(self.spec_draw)
-            self.n_masked.copy_(self._nm_spec)
-            self.need_fb.zero_()
-        if self.lookahead:
-            self._guess_from(self.pc.logits, 1)
-        self.need_fb_host.copy_(self.need_fb, non_blocking=True)
-
-    # ------------------------------------------------------------------------------------
-    # Lookahead inside the fallback pass (one sequence).  When y_init restored a drawn token, step t needs a second
-    # weight stream for its K real-mask members anyway.  That stream also carries the K+1 speculative contexts of step
-    # t+1, built on a GUESS of step t's outcome: the token and the winning member voted by the wrong-mask members of
-    # the pass before (they differ from the real members only in the few restored tokens).  Rows 0..K-1: the members of
-    # step t (real masks, position S).  After the QKV projection of a layer the guessed winner's new K/V row is written
-    # to cache row S (the real commit overwrites it later); rows K..2K -- unmasked + the draws of step t+1, input =
-    # the guessed token, position S+1 -- then attend to rows [0, S] exactly as they would after a commit.  If the
-    # real vote confirms the guess, rows K..2K ARE step t+1's speculative pass, bit for bit, and its weight stream has
-    # been saved; if not, they are dropped.  Only views and existing kernels: two embed/rope/attention windows.
-    # ------------------------------------------------------------------------------------
-    def _guess_from(self, logits: torch.Tensor, first: int) -> None:
-        """Guess step t's (token, winner) from the wrong-mask members = rows first..first+K-1 of `logits`."""
-        ops.aggregate(logits, self.aggregate, member_ids=self._g_ids, winner=self._g_win, token=self._g_tok,
-                      out_logits=self._g_out, vocab=self.cfg.vocab, first_member=first, members=self.K)
-        self.launches_per_step += 1
-
-    def _attention_rows(self, pb: _PassBuffers, l: int, bitmask, seq_lens, m0: int, m1: int, seq_active=None) -> None:
-        G = self.cfg.n_heads // self.cfg.n_kv_heads
-        per = max(1, 32 // G)
-        for a in range(m0, m1, per):
-            ops.decode_attention(pb.q, pb.k_new[l], pb.v_new[l], self.k_cache[l], self.v_cache[l], seq_lens,
-                                 self.vis_start, bitmask, self.n_vis, self.scale, pb.splits, pb.attn, pb.ws,
-                                 seq_active=seq_active, member_offset=a, members=min(per, m1 - a))
-            self.launches_per_step += 1 + (pb.splits == 1)
-
-    def _spec_chain(self) -> None:
-        self.launches_per_step = 0
-        cfg, K, pd = self.cfg, self.K, self.pd
-        H, Hkv, D, M = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, 2 * self.K + 1
-        torch.add(self.seq_lens, 1, out=self._seq_p1)
-        torch.add(self.step_ctr, 1, out=self._step_p1)
-        self._sample(self._step_uniforms(1), False, self.spec_draw, self._nm_spec, step=self._step_p1)   # draws of t+1
-        self.chain_mask[:, :K].copy_(self.bitmask)
-        self.chain_mask[:, K + 1:].copy_(self.spec_draw)
-        ops.embed_gather(self.w.embed, self.cur_token, K, pd.x[:K])
-        ops.embed_gather(self.w.embed, self._g_tok, K + 1, pd.x[K:])
-        x, x2 = pd.x, pd.x2
-        for l, lw in enumerate(self.w.layers):
-            ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pd.xn)
-            ops.decoder_linear(pd.xn, lw["wqkv"], ops.EPI_NONE, out=pd.qkv)
-            kn, vn = pd.k_new[l], pd.v_new[l]
-            ops.rope_stage(pd.qkv[:K], self.cos, self.sin, self.seq_lens, 1, K, H, Hkv, D, pd.q[:, :K], kn[:, :K],
-                           vn[:, :K])
-            ops.rope_stage(pd.qkv[K:], self.cos, self.sin, self._seq_p1, 1, K + 1, H, Hkv, D, pd.q[:, K:], kn[:, K:],
-                           vn[:, K:])
-            ops.commit_winner(pd.k_new[l:l + 1], pd.v_new[l:l + 1], self._g_win, self.seq_lens, self.k_cache[l:l + 1],
-                              self.v_cache[l:l + 1])
-            self._attention_rows(pd, l, self.chain_mask, self.seq_lens, 0, K)
-            self._attention_rows(pd, l, self.chain_mask, self._seq_p1, K, M)
-            ops.decoder_linear(pd.attn.view(M, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
-            ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pd.xn)
-            ops.decoder_linear(pd.xn, lw["wgu"], ops.EPI_SWIGLU, out=pd.act)
-            ops.decoder_linear(pd.act, lw["wd"], ops.EPI_RESIDUAL, residual=x2, out=x)
-            self.launches_per_step += 9
-        ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pd.xn)
-        ops.decoder_linear(pd.xn, self.w.lm_head_padded, ops.EPI_F32, out=pd.logits.view(M, self.Vp))
-        V, mean = cfg.vocab, self.aggregate == "mean"
-        # ---- step t: the reference's vote over its K real-mask members (rows 0..K-1)
-        ops.aggregate(pd.logits, self.aggregate, member_ids=self.member_ids, winner=self.winner, token=self.next_token,
-                      out_logits=self.out_logits if mean else None, vocab=V, first_member=0, members=K)
-        if mean:
-            ops.token_stats(self.out_logits, V, self.token_stats, slot=self.step_ctr, slot_offset=1)
-        else:
-            ops.token_stats(pd.logits, V, self.token_stats, member=self.winner, slot=self.step_ctr, slot_offset=1)
-        ops.commit_winner(pd.k_new, pd.v_new, self.winner, self.seq_lens, self.k_cache, self.v_cache)
-        ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
-        self.cur_token.copy_(self.next_token)
-        ok = (self.next_token == self._g_tok) & (self.winner == self._g_win)
-        # ---- step t+1 as _spec_head would see it (only meaningful when the guess was right)
-        ops.aggregate(pd.logits, "vote", member_ids=self._ids_d, winner=self._win_d, token=self._tok_d, vocab=V,
-                      first_member=K, members=K + 1)
-        self.y_init.copy_(self._ids_d[:, 0])
-        self._sample(self._step_uniforms(0), True, self.bitmask, self.n_masked)            # the reference's masks of t+1
-        fb = (self.bitmask != self.spec_draw).any()
-        self.chain_flags.copy_(torch.stack([ok.all(), fb]).to(torch.int32))
-        self.launches_per_step += 10
-        self._guess_from(pd.logits, K + 1)          # should step t+1 fall back too: its own guess
-        self.chain_flags_host.copy_(self.chain_flags, non_blocking=True)
-
-    def _spec_fin_chain(self) -> None:
-        """Step t+1 completed by the lookahead rows: members = rows K+1..2K of the chain pass."""
-        self.launches_per_step = 0
-        K, pd = self.K, self.pd
-        ops.aggregate(pd.logits, self.aggregate, member_ids=self.member_ids, winner=self.winner,
-                      token=self.next_token, out_logits=self.out_logits if self.aggregate == "mean" else None,
-                      vocab=self.cfg.vocab, first_member=K + 1, members=K)
-        torch.add(self.winner, K + 1, out=self._win_pk)
-        if self.aggregate == "mean":
-            ops.token_stats(self.out_logits, self.cfg.vocab, self.token_stats, slot=self.step_ctr, slot_offset=1)
-        else:
-            ops.token_stats(pd.logits, self.cfg.vocab, self.token_stats, member=self._win_pk, slot=self.step_ctr,
-                            slot_offset=1)
-        ops.commit_winner(pd.k_new, pd.v_new, self._win_pk, self.seq_lens, self.k_cache, self.v_cache)
-        ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
-        self.cur_token.copy_(self.next_token)
-        self.launches_per_step += 5
-
-    def _spec_fin(self) -> None:
-        """The speculated masks were the real ones: rows 1..K of the speculative pass are the K members."""
-        self.launches_per_step = 0
-        ops.aggregate(self.pc.logits, self.aggregate, member_ids=self.member_ids, winner=self.winner,
-                      token=self.next_token, out_logits=self.out_logits if self.aggregate == "mean" else None,
-                      vocab=self.cfg.vocab, first_member=1, members=self.K)
-        torch.add(self.winner, 1, out=self.winner_p1)
-        if self.aggregate == "mean":
-            ops.token_stats(self.out_logits, self.cfg.vocab, self.token_stats, slot=self.step_ctr, slot_offset=1)
-        else:
-            ops.token_stats(self.pc.logits, self.cfg.vocab, self.token_stats, member=self.winner_p1, slot=self.step_ctr,
-                            slot_offset=1)
-        ops.commit_winner(self.pc.k_new, self.pc.v_new, self.winner_p1, self.seq_lens, self.k_cache, self.v_cache)
-        ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
-        self.cur_token.copy_(self.next_token)
-        self.launches_per_step += 4
-
-    def _spec_fallback(self) -> None:
-        self.launches_per_step = 0
-        self._masked_pass_and_commit()
-
-    def _spec_batch_step(self) -> None:
-        """Asynchronous batch schedule (B >= 2; no host decision, ONE pass per call): every sequence runs K+1
-        contexts -- row 0 unmasked, rows 1..K with the draws of ITS current step, or, if its previous pass found
-        that y_init restores a drawn token, with the real masks of that step.  A sequence whose rows 1..K carried
-        its real masks votes, commits and advances; the others repeat the step in the next pass.  Sequences are
-        independent (per-sequence step counters key the Philox stream and every per-step buffer), so each one
-        produces exactly the tokens of the two-pass order while the batch pays ~(1 + fallback rate) weight and
-        K/V streams per token instead of two."""
-        self.launches_per_step = 0
-        V, K, mean = self.cfg.vocab, self.K, self.aggregate == "mean"
-        steps = self.seq_steps
-        u = None
-        if self.uniforms is not None:       # parity mode: sequence b uses the pre-drawn numbers of ITS step
-            idx = steps.long().clamp(max=self.uniforms.shape[0] - 1)
-            self._u_step.copy_(self.uniforms[idx, self._rows()])
-            u = self._u_step
-        self._sample(u, False, self.spec_draw, self._nm_spec, per_seq=True)
-        infb = self.in_fb.bool()
-        self._mask_tmp.copy_(torch.where(infb[:, None, None], self.bitmask, self.spec_draw))
-        self.spec_mask[:, 1:].copy_(self._mask_tmp)
-        act = steps < self.target
-        self.active.copy_(act.to(torch.int32))
-        logits_c = self._forward(self.pc, self.spec_mask, seq_active=self.active)
-        ops.aggregate(logits_c, "vote", member_ids=self.member_ids_c, winner=self.winner_c, token=self._tok_c, vocab=V)
-        # y_init / bitmask / n_masked stay what they were for sequences that are waiting at the target (they keep
-        # describing the sequence's last completed step) and for y_init of a sequence that is repeating its step
-        self.y_init.copy_(torch.where(act & ~infb, self.member_ids_c[:, 0], self.y_init))
-        if self.keep_relevant:
-            self._sample(u, True, self._mask_real, self._nm_real, per_seq=True)            # the reference's masks
-            ok = infb | (self._mask_real == self._mask_tmp).flatten(1).all(1)
-        else:                                                                          # epis_no_overlap
-            self._mask_real.copy_(self.spec_draw); self._nm_real.copy_(self._nm_spec)
-            ok = torch.ones_like(infb)
-        self.bitmask.copy_(torch.where(act[:, None, None], self._mask_real, self.bitmask))
-        self.n_masked.copy_(torch.where(act[:, None], self._nm_real, self.n_masked))
-        adv = ok & act
-        self.adv.copy_(adv.to(torch.int32))
-        if self.vote_on == "hidden":
-            # InstructBLIP (models/instructblip.py:125-140): the vote is taken on argmax of the members' final hidden
-            # states; the returned logits / token are lm_head of the winner = its row of the pass's logits
-            self._hid32c.copy_(self.pc.xn.view(self.B, K + 1, self.cfg.d_model))
-            ops.aggregate(self._hid32c, "vote", member_ids=self._ids_c, winner=self._win_c, token=self._tok_sc,
-                          first_member=1, members=K)
-            self._tok_sc.copy_(self.member_ids_c.gather(1, (self._win_c + 1).long()[:, None])[:, 0])
-        else:
-            ops.aggregate(self.pc.logits, self.aggregate, member_ids=self._ids_c, winner=self._win_c,
-                          token=self._tok_sc, out_logits=self._out_c if mean else None, vocab=V, first_member=1,
-                          members=K)
-        self.member_ids.copy_(torch.where(adv[:, None], self._ids_c, self.member_ids))
-        self.winner.copy_(torch.where(adv, self._win_c, self.winner))
-        self.next_token.copy_(torch.where(adv, self._tok_sc, self.next_token))
-        self.winner_p1.copy_(torch.where(adv, self._win_c + 1, self._minus1))
-        if mean:
-            self.out_logits.copy_(torch.where(adv[:, None], self._out_c, self.out_logits))
-            ops.token_stats(self._out_c, V, self.token_stats, member=torch.where(adv, self._zero, self._minus1),
-                            slot=steps, slot_offset=1, slot_per_seq=True)
-            self.ret_logits.copy_(self.out_logits)
-        else:
-            ops.token_stats(self.pc.logits, V, self.token_stats, member=self.winner_p1, slot=steps, slot_offset=1,
-                            slot_per_seq=True)
-            rows = self.pc.logits[self._rows(), self.winner_p1.clamp(min=0).long(), :V]
-            self.ret_logits.copy_(torch.where(adv[:, None], rows, self.ret_logits))
-        ops.commit_winner(self.pc.k_new, self.pc.v_new, self.winner_p1, self.seq_lens, self.k_cache, self.v_cache)
-        ops.step_advance_seq(self._tok_sc, self.adv, self.tokens_out, self.seq_lens, steps)
-        self.cur_token.copy_(torch.where(adv, self._tok_sc, self.cur_token))
-        self.in_fb.copy_((~ok & act).to(torch.int32))
-        self._fb_total.add_(self.in_fb.sum())
-        self.launches_per_step += 7
-
-    def _spec_batch_la_step(self) -> None:
-        """Asynchronous batch schedule with lookahead: 2K+1 context slots per sequence and pass.  Slots 0..K-1 ("verify")
-        run the real-mask members of a step whose speculated masks were wrong (idle otherwise); slots K..2K ("spec")
-        run the speculative contexts -- unmasked + draws -- of the sequence's next undecided step: the same step for a
-        sequence that is not repeating one, the FOLLOWING step, on the guessed outcome of the verify slots (token and
-        winning member voted by the wrong-mask members of the pass before; the guessed winner's K/V row is written
-        ahead into the cache, layer by layer), for one that is.  A confirmed guess makes the spec slots that following
-        step's speculative pass, so a sequence can complete two steps in one pass and a repeated step costs no extra
-        weight stream.  Everything is decided per sequence on the device; results equal the two-pass order bit for bit."""
-        self.launches_per_step = 0
-        cfg, B, K, pe = self.cfg, self.B, self.K, self.pe
-        V, M, mean = cfg.vocab, 2 * self.K + 1, self.aggregate == "mean"
-        H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
-        steps = self.seq_steps
-        act = steps < self.target
-        fb = self.in_fb.bool() & act
-        fb_i = fb.to(torch.int32)
-        self._steps_spec.copy_(steps + fb_i)
-        spec_on = act & (self._steps_spec < self.target)
-        u = None
-        if self.uniforms is not None:       # parity mode: the pre-drawn numbers of the step in the spec slots
-            idx = self._steps_spec.long().clamp(max=self.uniforms.shape[0] - 1)
-            self._u_step.copy_(self.uniforms[idx, self._rows()])
-            u = self._u_step
-        self._sample(u, False, self.spec_draw, self._nm_spec, per_seq=True, step=self._steps_spec)
-        self.la_mask[:, :K].copy_(self.bitmask)
-        self.la_mask[:, K + 1:].copy_(self.spec_draw)
-        rt, rp = self._row_tok.view(B, M), self._row_pos.view(B, M)
-        rt[:, :K] = self.cur_token[:, None]
-        rt[:, K:] = torch.where(fb, self._g_tok, self.cur_token)[:, None]
-        self._seq_p.copy_(self.seq_lens + fb_i)
-        rp[:, :K] = self.seq_lens[:, None]
-        rp[:, K:] = self._seq_p[:, None]
-        self._act1.copy_(fb_i)
-        self._act2.copy_(spec_on.to(torch.int32))
-        self._gw.copy_(torch.where(fb, self._g_win, self._minus1))
-        # ---- the pass
-        rows = B * M
-        ops.embed_gather(self.w.embed, self._row_tok, 1, pe.x)
-        x, x2 = pe.x, pe.x2
-        for l, lw in enumerate(self.w.layers):
-            ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pe.xn)
-            self._linear(pe.xn, lw["wqkv"], ops.EPI_NONE, pe.qkv)
-            ops.rope_stage(pe.qkv, self.cos, self.sin, self._row_pos, rows, 1, H, Hkv, D, pe.q, pe.k_new[l], pe.v_new[l])
-            ops.commit_winner(pe.k_new[l:l + 1], pe.v_new[l:l + 1], self._gw, self.seq_lens, self.k_cache[l:l + 1],
-                              self.v_cache[l:l + 1])                                   # the guessed winner's row, ahead
-            self._attention_rows(pe, l, self.la_mask, self.seq_lens, 0, K, seq_active=self._act1)
-            self._attention_rows(pe, l, self.la_mask, self._seq_p, K, M, seq_active=self._act2)
-            if rows <= 32 and self.gemm_backend == "auto":
-                ops.skinny_gemm(pe.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
-                self.launches_per_step += 1
-            else:
-                self._linear(pe.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, x2, residual=x)
-            ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pe.xn)
-            self._linear(pe.xn, lw["wgu"], ops.EPI_SWIGLU, pe.act)
-            self._linear(pe.act, lw["wd"], ops.EPI_RESIDUAL, x, residual=x2)
-            self.launches_per_step += 4
-        ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pe.xn)
-        self._linear(pe.xn, self.w.lm_head_padded, ops.EPI_F32, pe.logits.view(rows, self.Vp))
-        self.launches_per_step += 2
-        # ---- votes: verify slots, per-row argmax of the spec slots, members among the spec slots
-        ops.aggregate(pe.logits, self.aggregate, member_ids=self._ids_v, winner=self._win_v, token=self._tok_v,
-                      out_logits=self._out_v if mean else None, vocab=V, first_member=0, members=K)
-        ops.aggregate(pe.logits, "vote", member_ids=self._ids_s, winner=self._win_s, token=self._tok_s, vocab=V,
-                      first_member=K, members=K + 1)
-        self._y_new.copy_(self._ids_s[:, 0])
-        self._sample(u, True, self._mask_real, self._nm_real, per_seq=True, step=self._steps_spec, y=self._y_new)
-        eq = (self._mask_real == self.spec_draw).flatten(1).all(1)
-        ops.aggregate(pe.logits, self.aggregate, member_ids=self._ids_c, winner=self._win_c, token=self._tok_sc,
-                      out_logits=self._out_c if mean else None, vocab=V, first_member=K + 1, members=K)
-        self.launches_per_step += 5
-        chain_ok = fb & spec_on & (self._tok_v == self._g_tok) & (self._win_v == self._g_win)
-        valid = (act & ~fb) | chain_ok              # the spec slots were a real speculative pass of step _steps_spec
-        adv1 = fb | (valid & ~fb & eq)
-        adv2 = chain_ok & eq
-        win_m = self._win_c + (K + 1)
-        self._w1.copy_(torch.where(adv1, torch.where(fb, self._win_v, win_m), self._minus1))
-        self._w2.copy_(torch.where(adv2, win_m, self._minus1))
-        self._tok1.copy_(torch.where(fb, self._tok_v, self._tok_sc))
-        self.adv.copy_(adv1.to(torch.int32))
-        self._adv2.copy_(adv2.to(torch.int32))
-        # ---- per-step views: the step in the spec slots (completed or to be repeated) / the last completed step
-        self.y_init.copy_(torch.where(valid, self._y_new, self.y_init))
-        self.bitmask.copy_(torch.where(valid[:, None, None], self._mask_real, self.bitmask))
-        self.n_masked.copy_(torch.where(valid[:, None], self._nm_real, self.n_masked))
-        ids1 = torch.where(fb[:, None], self._ids_v, self._ids_c)
-        self.member_ids.copy_(torch.where(adv2[:, None], self._ids_c, torch.where(adv1[:, None], ids1, self.member_ids)))
-        self.winner.copy_(torch.where(adv2, self._win_c, torch.where(adv1, torch.where(fb, self._win_v, self._win_c),
-                                                                      self.winner)))
-        self.next_token.copy_(torch.where(adv2, self._tok_sc, torch.where(adv1, self._tok1, self.next_token)))
-        self.winner_p1.copy_(torch.where(adv2, self._w2, self._w1))       # row of the pass that holds the returned logits
-        if mean:
-            self._out1.copy_(torch.where(fb[:, None], self._out_v, self._out_c))
-            self.out_logits.copy_(torch.where(adv2[:, None], self._out_c,
-                                              torch.where(adv1[:, None], self._out1, self.out_logits)))
-            self.ret_logits.copy_(self.out_logits)
-            ops.token_stats(self._out1, V, self.token_stats, member=torch.where(adv1, self._zero, self._minus1),
-                            slot=steps, slot_offset=1, slot_per_seq=True)
-        else:
-            r = self.pe.logits[self._rows(), self.winner_p1.clamp(min=0).long(), :V]
-            self.ret_logits.copy_(torch.where((adv1 | adv2)[:, None], r, self.ret_logits))
-            ops.token_stats(pe.logits, V, self.token_stats, member=self._w1, slot=steps, slot_offset=1,
-                            slot_per_seq=True)
-        ops.commit_winner(pe.k_new, pe.v_new, self._w1, self.seq_lens, self.k_cache, self.v_cache)
-        ops.step_advance_seq(self._tok1, self.adv, self.tokens_out, self.seq_lens, steps)
-        if mean:
-            ops.token_stats(self._out_c, V, self.token_stats, member=torch.where(adv2, self._zero, self._minus1),
-                            slot=steps, slot_offset=1, slot_per_seq=True)
-        else:
-            ops.token_stats(pe.logits, V, self.token_stats, member=self._w2, slot=steps, slot_offset=1,
-                            slot_per_seq=True)
-        ops.commit_winner(pe.k_new, pe.v_new, self._w2, self.seq_lens, self.k_cache, self.v_cache)
-        ops.step_advance_seq(self._tok_sc, self._adv2, self.tokens_out, self.seq_lens, steps)
-        self.cur_token.copy_(torch.where(adv2, self._tok_sc, torch.where(adv1, self._tok1, self.cur_token)))
-        self._g_tok.copy_(self._tok_sc)
-        self._g_win.copy_(self._win_c)
-        self.in_fb.copy_((valid & ~eq).to(torch.int32))
-        self._fb_total.add_(self.in_fb.sum())
-        self.launches_per_step += 6
-
-    def fallback_rate(self) -> float:
-        """Fraction of (step, sequence) pairs whose masked pass had to be re-run with the real masks."""
-        if self.spec_batch:         # repeated (step, sequence) pairs / completed ones
-            return float(self._fb_total.item()) / max(1, self._seq_steps_done)
-        return self.n_fallbacks / max(1, self.n_spec_steps)
-
-    def _run_piece(self, graphs: Optional[dict], name: str, fn) -> None:
-        if graphs is not None:
-            graphs[name][0].replay()
-            self.launch_count += graphs[name][1]
-        else:
-            fn()
-            self.launch_count += self.launches_per_step
-
-    def _spec_steps(self, n_steps: int, graphs: Optional[dict]) -> None:
-        """n_steps ensemble steps through the speculative path (one sequence); `graphs` = captured pieces or None
-        (eager).  One host decision (a stream synchronisation) per pass.  Lookahead state never outlives the call."""
-        run = lambda name, fn: self._run_piece(graphs, name, fn)
-        sync = torch.cuda.current_stream().synchronize
-        i, src, need_fb = 0, None, False        # src: which pass already served as step i's speculative pass
-        while i < n_steps:
-            if not self.spec_active:            # the adaptive switch fired: the reference's own order
-                if graphs is not None:
-                    if self._graph is None:
-                        self.capture()
-                    self._graph.replay()
-                else:
-                    self._two_pass_step()
-                self.launch_count += self.launches_per_step
-                self._last_src = "pb"
-                i += 1
-                continue
-            if src is None:
-                run("head", self._spec_head)
-                sync()
-                need_fb, src = bool(int(self.need_fb_host[0])), "pc"
-            self.n_spec_steps += 1
-            if not need_fb:
-                if src == "pc":
-                    run("fin", self._spec_fin)
-                    self._last_src = "pc"
-                else:
-                    run("fin_chain", self._spec_fin_chain)
-                    self._last_src = "pd1"
-                src = None
-            else:
-                self.n_fallbacks += 1
-                if self.lookahead and n_steps - i >= 2:
-                    run("chain", self._spec_chain)
-                    sync()
-                    self.n_chain += 1
-                    self._last_src = "pd0"
-                    if int(self.chain_flags_host[0]):
-                        self.n_chain_ok += 1
-                        need_fb, src = bool(int(self.chain_flags_host[1])), "pd"
-                    else:
-                        src = None
-                else:
-                    run("fallback", self._spec_fallback)
-                    self._last_src = "pb"
-                    src = None
-            i += 1
-            # adaptive: when almost every step needs the fallback (a checkpoint whose next token is nearly always one
-            # of the visual tokens' top-k ids) and the lookahead cannot absorb it, the reference's order is cheaper
-            n, f = self.n_spec_steps - self._spec_base[0], self.n_fallbacks - self._spec_base[1]
-            if self.speculative == "auto" and not self.lookahead and n >= 32 and f > 0.8 * n and src is None:
-                self.spec_active = False
-
     def capture(self) -> None:
         """Warm up once eagerly (restoring the state), then capture one step into a CUDA graph (two-pass path) or
         its three pieces -- speculative pass, finish, fallback -- into three graphs (speculative path)."""
@@ -985,17 +483,19 @@ class DropoutDecodeEngine:
         self.seq_lens.copy_(s["seq"]); self.step_ctr.copy_(s["step"]); self.cur_token.copy_(s["cur"])
         self.tokens_out.copy_(s["tok"])
 
-    def decode(self, n_steps: int, use_graph: bool = True) -> None:
-        """Run n_steps ensemble steps.  Two-pass path: fully asynchronous.  Speculative path: one stream
-        synchronisation per step (the fallback decision)."""
+    def decode(self, n_steps: int, use_graph: bool = True, stop_token: Optional[int] = None) -> int:
+        """Run n_steps ensemble steps; returns the number done.  Two-pass path and batches: fully asynchronous, always
+        n_steps.  One sequence on the speculative path: one stream synchronisation per pass (the repeat decision), and
+        with stop_token the loop ends early once that token has been generated."""
         if int(self.seq_lens.max()) + n_steps > self.S_max:
             raise ops.DropDecError("decode would overflow the KV cache")
         if use_graph and (self._graphs is None if self.spec_active else self._graph is None):
             self.capture()
         if self.spec_batch:
-            return self._decode_async(n_steps, use_graph)
+            self._decode_async(n_steps, use_graph)
+            return n_steps
         if self.spec_active:
-            return self._spec_steps(n_steps, self._graphs if use_graph else None)
+            return self._spec_steps(n_steps, self._graphs if use_graph else None, stop_token)
         for _ in range(n_steps):
             if use_graph:
                 if self._graph is None:
@@ -1004,34 +504,7 @@ class DropoutDecodeEngine:
             else:
                 self.step()
             self.launch_count += self.launches_per_step
-
-    def _decode_async(self, n_steps: int, use_graph: bool) -> None:
-        """Passes of the asynchronous batch schedule until every sequence has advanced n_steps: n_steps passes, then
-        as many more as the sequence with the most repeated steps needs (the host looks at the counters between
-        those).  On return all sequences are in lockstep again."""
-        if use_graph and self._graph is None:
-            self.seq_steps.copy_(self.step_ctr.expand(self.B)); self.in_fb.zero_()
-            self.target.copy_(self.step_ctr + 1)
-            self.capture()
-        self.seq_steps.copy_(self.step_ctr.expand(self.B))
-        self.in_fb.zero_()
-        self.target.copy_(self.step_ctr + n_steps)
-
-        def run(k):
-            for _ in range(k):
-                if use_graph:
-                    self._graph.replay()
-                else:
-                    self.step()
-                self.launch_count += self.launches_per_step
-                self.n_spec_steps += 1
-
-        run(n_steps)
-        while not bool((self.seq_steps >= self.target).all()):
-            run(1 if self.B <= 8 else 2)
-        self.step_ctr.add_(n_steps)
-        self._seq_steps_done += n_steps * self.B
-        self._last_src = "mixed"
+        return n_steps
 
     # ------------------------------------------------------------------------------------
     # prefill: library ops (not the hot path, SURVEY.md 8f-3)

@@ -189,12 +189,14 @@ class DropoutDecodingMixin:
         steps_left = max_new_tokens - 1
         # EOS is checked between decode calls; the asynchronous batch schedule re-synchronises the sequences at the
         # end of every call, so it gets longer calls
-        chunk = (64 if eng.spec_batch else 16) if eos_token_id is not None else steps_left
+        # (one sequence on the speculative path: the host sees every pass's input token anyway -- no chunking)
+        host_stop = eng.spec_active and eos_token_id is not None
+        chunk = (64 if eng.spec_batch else 16) if (eos_token_id is not None and not host_stop) else steps_left
         while steps_left > 0:
             n = min(chunk, steps_left)
-            eng.decode(n, use_graph=use_cuda_graph)
+            done = eng.decode(n, use_graph=use_cuda_graph, stop_token=eos_token_id if host_stop else None)
             steps_left -= n
-            if eos_token_id is not None and bool((eng.generated() == eos_token_id).any(-1).all()):
+            if done < n or (eos_token_id is not None and bool((eng.generated() == eos_token_id).any(-1).all())):
                 break
         self.is_first_generation = False
         new = eng.generated().long()

@@ -77,6 +77,10 @@ def test_eos_stops_and_pads(llava, cuda):
     out = llava.generate(input_ids=ids, pixel_values=px, max_new_tokens=20, eos_token_id=eos, pad_token_id=0)
     new = out[0, 18:].tolist()
     assert new[:first + 1] == free[:first + 1] and len(new) == first + 1
+    # one sequence: the host sees every pass's input token, so decoding stops within one pass of EOS (not at the end
+    # of a 16-step chunk)
+    eng = next(iter(llava._engines.values()))
+    assert eng.spec_active and first <= int(eng.step_ctr) <= first + 1
 
 
 def test_settings_are_read_at_call_time(llava, cuda):
