@@ -117,6 +117,7 @@ class SpeculativeSchedules:
             self._g_tok, self._g_win = torch.zeros(B, **i32), torch.zeros(B, **i32)     # the guessed outcome of step t
             self._g_ids = torch.zeros(B, K, **i32)
             self._seq_p1, self._step_p1 = torch.zeros(B, **i32), torch.zeros(1, **i32)
+            self._row_tok_c, self._row_pos_c = torch.zeros(2 * K + 1, **i32), torch.zeros(2 * K + 1, **i32)
             self._ids_d = torch.zeros(B, K + 1, **i32)
             self._win_d, self._tok_d = torch.zeros(B, **i32), torch.zeros(B, **i32)
             self._win_pk = torch.zeros(B, **i32)
@@ -166,7 +167,8 @@ class SpeculativeSchedules:
     # to cache row S (the real commit overwrites it later); rows K..2K -- unmasked + the draws of step t+1, input =
     # the guessed token, position S+1 -- then attend to rows [0, S] exactly as they would after a commit.  If the
     # real vote confirms the guess, rows K..2K ARE step t+1's speculative pass, bit for bit, and its weight stream has
-    # been saved; if not, they are dropped.  Only views and existing kernels: two embed/rope/attention windows.
+    # been saved; if not, they are dropped.  Only views and existing kernels: per-row token / RoPE position tensors (the
+    # kernels see 2K+1 one-member sequences) and two attention windows.
     # ------------------------------------------------------------------------------------
     def _guess_from(self, logits: torch.Tensor, first: int) -> None:
         """Guess step t's (token, winner) from the wrong-mask members = rows first..first+K-1 of `logits`."""
@@ -193,17 +195,18 @@ class SpeculativeSchedules:
         self._sample(self._step_uniforms(1), False, self.spec_draw, self._nm_spec, step=self._step_p1)   # draws of t+1
         self.chain_mask[:, :K].copy_(self.bitmask)
         self.chain_mask[:, K + 1:].copy_(self.spec_draw)
-        ops.embed_gather(self.w.embed, self.cur_token, K, pd.x[:K])
-        ops.embed_gather(self.w.embed, self._g_tok, K + 1, pd.x[K:])
+        # per-row input token and RoPE position: the kernels see 2K+1 "sequences" of one member each
+        self._row_tok_c[:K] = self.cur_token
+        self._row_tok_c[K:] = self._g_tok
+        self._row_pos_c[:K] = self.seq_lens
+        self._row_pos_c[K:] = self._seq_p1
+        ops.embed_gather(self.w.embed, self._row_tok_c, 1, pd.x)
         x, x2 = pd.x, pd.x2
         for l, lw in enumerate(self.w.layers):
             ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pd.xn)
-            ops.decoder_linear(pd.xn, lw["wqkv"], ops.EPI_NONE, out=pd.qkv)
-            kn, vn = pd.k_new[l], pd.v_new[l]
-            ops.rope_stage(pd.qkv[:K], self.cos, self.sin, self.seq_lens, 1, K, H, Hkv, D, pd.q[:, :K], kn[:, :K],
-                           vn[:, :K])
-            ops.rope_stage(pd.qkv[K:], self.cos, self.sin, self._seq_p1, 1, K + 1, H, Hkv, D, pd.q[:, K:], kn[:, K:],
-                           vn[:, K:])
+            ops.decoder_linear(pd.xn, lw["wqkv"], ops.EPI_ROPE,
+                               rope=dict(cos=self.cos, sin=self.sin, seq_lens=self._row_pos_c, members=1, H=H, H_kv=Hkv,
+                                         D=D, q_out=pd.q, k_new=pd.k_new[l], v_new=pd.v_new[l]))
             ops.commit_winner(pd.k_new[l:l + 1], pd.v_new[l:l + 1], self._g_win, self.seq_lens, self.k_cache[l:l + 1],
                               self.v_cache[l:l + 1])
             self._attention_rows(pd, l, self.chain_mask, self.seq_lens, 0, K)
@@ -212,7 +215,7 @@ class SpeculativeSchedules:
             ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pd.xn)
             ops.decoder_linear(pd.xn, lw["wgu"], ops.EPI_SWIGLU, out=pd.act)
             ops.decoder_linear(pd.act, lw["wd"], ops.EPI_RESIDUAL, residual=x2, out=x)
-            self.launches_per_step += 9
+            self.launches_per_step += 7
         ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pd.xn)
         ops.decoder_linear(pd.xn, self.w.lm_head_padded, ops.EPI_F32, out=pd.logits.view(M, self.Vp))
         V, mean = cfg.vocab, self.aggregate == "mean"
