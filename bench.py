@@ -327,7 +327,11 @@ def profile_dominant_kernel(eng, hbm, peak_src):
                     "avg_launch_us": round(graph_ms * 1e3 / len(recs), 2)}
     return {"bound": "hbm", "kernel": "dd::skinny_gemm_kernel (all weight GEMMs of one ensemble step)",
             "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "in_graph": in_graph,
-            "traffic": "ncu dram__bytes_read+write per launch = 1.00-1.04 x the weight bytes (profiles/r01/ncu_full_summary.json)",
+            # ncu --set full (profiles/r01/ncu_full_summary.json, "gemm"): dram__bytes_read + write per launch are
+            # 33.6 / 105.2 / 184.3 / 94.0 MB for the o_proj / qkv / gate-up / down shapes = 1.03 x their weight bytes
+            "traffic": int(1.03 * byts / len(recs)),
+            "traffic_note": "bytes per launch, averaged over the step's shapes: ncu dram__bytes_read+write = 1.00-1.04 x "
+                            "the weight bytes per shape (profiles/r01/ncu_full_summary.json)",
             "peak_source": peak_src, "launches": len(recs), "algorithmic_bytes_per_step": int(byts),
             "avg_launch_us": round(secs / len(recs) * 1e6, 2),
             "share_of_eager_step": round(secs / (t_all0.elapsed_time(t_all1) * 1e-3), 3)}
