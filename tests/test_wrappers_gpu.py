@@ -37,6 +37,17 @@ def test_llava_generate_and_attributes(llava, cuda):
     assert torch.equal(out, again)
 
 
+def test_short_generations_pope_style(llava, cuda):
+    """pope_test/pope_test.py:242 asks for ONE new token (yes/no): no ensemble step runs, the token is the argmax of
+    the unmasked prefill (models/llava.py:382-388); two and three tokens are prefixes of the longer generation."""
+    ids, px = _inputs(1)
+    want = llava.generate(input_ids=ids, pixel_values=px, max_new_tokens=6)[0, 18:].tolist()
+    for n in (1, 2, 3):
+        out = llava.generate(input_ids=ids, pixel_values=px, max_new_tokens=n)
+        assert out.shape == (1, 18 + n) and out[0, 18:].tolist() == want[:n]
+    assert llava.vision_uncert_dict["epis_uncert_per_token"].shape == (1, 576)
+
+
 def test_forward_loop_equals_generate(llava, cuda):
     """Driving the reference's per-token forward() by hand (prefill iff input_ids.shape[-1] != 1,
     models/llava.py:218-226) gives the tokens generate() gives."""
