@@ -160,6 +160,7 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         self.topk, self.aggregate, self.seed, self.round_logits = topk, aggregate, seed, round_logits
         self.fuse_norm = os.environ.get("DD_FUSE_NORM", "0") == "1"
         self.prefill_graph = os.environ.get("DD_PREFILL_GRAPH", "1") == "1"
+        self.prefill_native = os.environ.get("DD_PREFILL_NATIVE", "1") == "1"
         self._prefill_graphs: dict = {}
         # Weight GEMMs by row count (rows = sequences x members of a pass); measured on B200 (profiles/README.md 4):
         #   rows <= 16        dd_skinny_gemm / dd_decoder_linear (mma.sync, RoPE fused into the QKV epilogue)
@@ -556,6 +557,8 @@ class DropoutDecodeEngine(SpeculativeSchedules):
             x1, x2 = t[..., :D // 2], t[..., D // 2:]
             return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], -1).to(torch.bfloat16)
 
+        if self.prefill_native:
+            return self._prefill_layers_native(embeds)
         x = embeds.to(torch.bfloat16)
         for l, lw in enumerate(self.w.layers):
             h = self._norm_t(x, lw["ln1"])
@@ -572,6 +575,33 @@ class DropoutDecodeEngine(SpeculativeSchedules):
             gu = F.linear(h, lw["wgu"])
             x = x + F.linear(F.silu(gu[..., :cfg.d_ff]) * gu[..., cfg.d_ff:], lw["wd"])
         return self._norm_t(x, self.w.norm)
+
+    def _prefill_layers_native(self, embeds: torch.Tensor) -> torch.Tensor:
+        """The same prefill with the elementwise chains on this library's kernels: dd_rmsnorm for the 2L+1 norms and
+        dd_rope_stage (every prompt position = a one-member sequence with its own RoPE position) for split + RoPE of
+        q / k / v -- the rounding points of the decode path, ~25 instead of ~60 launches per layer (7B, 593 positions:
+        13.0 -> 11 ms replayed).  GEMMs and the causal attention stay library calls."""
+        cfg, B = self.cfg, self.B
+        H, Hkv, D, d, eps = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cfg.d_model, cfg.rms_eps
+        S0 = embeds.shape[1]
+        rows = B * S0
+        bf = dict(dtype=torch.bfloat16, device=self.dev)
+        pos = torch.arange(S0, dtype=torch.int32, device=self.dev).repeat(B)
+        q = torch.empty(rows, 1, H, D, **bf)
+        k, v = torch.empty(rows, 1, Hkv, D, **bf), torch.empty(rows, 1, Hkv, D, **bf)
+        x = embeds.to(torch.bfloat16).reshape(rows, d).contiguous()
+        for l, lw in enumerate(self.w.layers):
+            qkv = F.linear(ops.rmsnorm(x, lw["ln1"], eps), lw["wqkv"])
+            ops.rope_stage(qkv, self.cos, self.sin, pos, rows, 1, H, Hkv, D, q, k, v)
+            kt, vt = k.view(B, S0, Hkv, D).transpose(1, 2), v.view(B, S0, Hkv, D).transpose(1, 2)
+            self.k_cache[l, :, :, :S0] = kt
+            self.v_cache[l, :, :, :S0] = vt
+            a = F.scaled_dot_product_attention(q.view(B, S0, H, D).transpose(1, 2), kt, vt, is_causal=True,
+                                               enable_gqa=(H != Hkv))
+            x = x + F.linear(a.transpose(1, 2).reshape(rows, H * D), lw["wo"])
+            gu = F.linear(ops.rmsnorm(x, lw["ln2"], eps), lw["wgu"])
+            x = x + F.linear(F.silu(gu[:, :cfg.d_ff]) * gu[:, cfg.d_ff:], lw["wd"])
+        return ops.rmsnorm(x, self.w.norm, eps).view(B, S0, d)
 
     def load_prefill(self, k: torch.Tensor, v: torch.Tensor, vis_start: Sequence[int]) -> None:
         """Inject an externally computed prefix cache: k, v [L, B, H_kv, S0, D] (parity tests)."""

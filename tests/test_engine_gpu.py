@@ -358,6 +358,28 @@ def test_full_gpu_pipeline_prefill_to_tokens(tiny, cuda):
     assert run(False) == got
 
 
+def test_native_prefill_matches_library_prefill(tiny, cuda, monkeypatch):
+    """The prefill with this library's norm / RoPE kernels (every prompt position a one-member sequence with its own
+    RoPE position) against the elementwise torch chains: the layer-0 keys -- norm, projection, RoPE only -- agree to a
+    bf16 ulp, values likewise, and the final hidden states stay within the rounding noise of two bf16 layers."""
+    emb = tiny["merged"].to(cuda).bfloat16()[None]
+    res = {}
+    for native in ("1", "0"):
+        monkeypatch.setenv("DD_PREFILL_NATIVE", native)
+        eng = make_engine(tiny, cuda)
+        assert eng.prefill_native == (native == "1")
+        h = eng.prefill(emb, [TINY_VIS_START])
+        torch.cuda.synchronize()
+        S0 = emb.shape[1]
+        res[native] = (h.float().cpu(), eng.k_cache[0, 0, :, :S0].float().cpu(), eng.v_cache[0, 0, :, :S0].float().cpu())
+    (h1, k1, v1), (h0, k0, v0) = res["1"], res["0"]
+    ulp = lambda t: torch.exp2(torch.floor(torch.log2(t.abs().clamp_min(1e-30))) - 7)
+    assert bool(((k1 - k0).abs() <= 2 * ulp(k0) + 1e-6).all()), f"layer-0 keys: {(k1 - k0).abs().max().item():.3e}"
+    assert bool(((v1 - v0).abs() <= 2 * ulp(v0) + 1e-6).all()), f"layer-0 values: {(v1 - v0).abs().max().item():.3e}"
+    assert (k1 != k0).float().mean().item() < 0.05
+    assert (h1 - h0).abs().mean().item() <= 0.01 * h0.abs().mean().item()
+
+
 def test_batch_is_independent_of_batch_size(tiny, cuda):
     """B=3 copies of the same image give three times the B=1 result (no cross-sequence leakage)."""
     tr = tiny["trace"]
