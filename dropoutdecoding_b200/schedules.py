@@ -23,7 +23,6 @@ from . import ops
 class SpeculativeSchedules:
     def _init_schedules(self, speculative: Optional[str], est: int) -> None:
         cfg, B, dev = self.cfg, self.B, self.dev
-        H, Hkv = cfg.n_heads, cfg.n_kv_heads
         vote_on, keep_relevant, aggregate = self.vote_on, self.keep_relevant, self.aggregate
         i32 = dict(dtype=torch.int32, device=dev)
         # ---- speculative single pass (see _spec_head): "auto" = on whenever the K+1 contexts of all sequences fit the
