@@ -46,25 +46,42 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_kernel(const float* __r
   const float* base = logits + (size_t)b * seq_stride;
   const bool vec = (V % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
 
-  for (int m = 0; m < K; ++m) {
-    const float* row = base + (size_t)m * ld;
-    ArgMax best{-INFINITY, 0x7fffffff};
+  // per-member argmax, four rows at a time: the four loads of an iteration are independent, so a single CTA (one
+  // sequence) keeps four times the bytes in flight of a row-by-row scan
+  for (int m0 = 0; m0 < K; m0 += 4) {
+    ArgMax best[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) best[r] = ArgMax{-INFINITY, 0x7fffffff};
     if (vec) {
-      const float4* row4 = reinterpret_cast<const float4*>(row);
       for (int j = tid; j < V / 4; j += kAggThreads) {
-        const float4 x = __ldg(row4 + j);
-        best = better(best, ArgMax{x.x, 4 * j});
-        best = better(best, ArgMax{x.y, 4 * j + 1});
-        best = better(best, ArgMax{x.z, 4 * j + 2});
-        best = better(best, ArgMax{x.w, 4 * j + 3});
+        float4 x[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (m0 + r < K) x[r] = __ldg(reinterpret_cast<const float4*>(base + (size_t)(m0 + r) * ld) + j);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (m0 + r < K) {
+            best[r] = better(best[r], ArgMax{x[r].x, 4 * j});
+            best[r] = better(best[r], ArgMax{x[r].y, 4 * j + 1});
+            best[r] = better(best[r], ArgMax{x[r].z, 4 * j + 2});
+            best[r] = better(best[r], ArgMax{x[r].w, 4 * j + 3});
+          }
       }
     } else {
-      for (int j = tid; j < V; j += kAggThreads) best = better(best, ArgMax{row[j], j});
+      for (int j = tid; j < V; j += kAggThreads)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (m0 + r < K) best[r] = better(best[r], ArgMax{base[(size_t)(m0 + r) * ld + j], j});
     }
-    best = block_argmax(best, s_warp);
-    if (tid == 0) {
-      s_ids[m] = best.i;
-      if (member_ids) member_ids[b * K + m] = best.i;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (m0 + r < K) {  // block-uniform
+        const ArgMax b4 = block_argmax(best[r], s_warp);
+        if (tid == 0) {
+          s_ids[m0 + r] = b4.i;
+          if (member_ids) member_ids[b * K + m0 + r] = b4.i;
+        }
+      }
     }
   }
   __syncthreads();
