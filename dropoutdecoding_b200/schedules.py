@@ -524,6 +524,8 @@ class SpeculativeSchedules:
                     sync()
                     self.n_chain += 1
                     self._last_src = "pd0"
+                    if stop_token is not None and int(self.tok_host[0]) == stop_token:
+                        return i + 1            # (EOS came out of the step before; this pass has committed one more)
                     if int(self.chain_flags_host[0]):
                         self.n_chain_ok += 1
                         need_fb, src = bool(int(self.chain_flags_host[1])), "pd"
