@@ -1,25 +1,38 @@
 // Weight-streaming GEMM on the tcgen05 tensor cores for the batched single-token forwards of the ensemble:
-//   y[m,n] = sum_k x[m,k] w[n,k],   16 < M = (#sequences x #members) <= 256 rows.
-// (dd_skinny_gemm covers M <= 16..32 with mma.sync; above that every CTA of that kernel re-reads more
-// activation bytes from L2 than weight bytes from HBM.)
+//   y[m,n] = sum_k x[m,k] w[n,k],   M = (#sequences x #contexts of a pass) <= 256 rows.
+// Replaces the weight GEMMs inside the reference's 1+K `self.language_model(...)` calls per token
+// (models/llava.py:294-303, 350-359; models/llama.py:27-47).
 //
-// The GEMM is still a pure weight stream (intensity = M FLOP/byte, below the B200 ridge), so it is organised
-// around HBM, with the tensor core as the only unit that can multiply a 32 KB weight block by up to 256 token
-// rows in the time the block takes to arrive:
-//   * swap-AB: the WEIGHTS are the M=128 operand of tcgen05.mma (128 output features per accumulator), the token
-//     rows are the N operand (Np = M rounded up to 16, <= 256).  D[feature, row] lives in TMEM.
-//   * a tile = two accumulators = 256 output features (SwiGLU: 128 gate + the matching 128 up features, so the
-//     activation is applied in the epilogue); per 64-wide k-block the CTA ingests 32 KB of W (HBM, L2 evict-first)
-//     and Np x 128 B of x (L2-resident) through TMA into a 3..6-stage mbarrier ring.
-//   * stream-K: the (tile, k-block) units are cut into 148 equal contiguous ranges, one persistent CTA per SM, so
-//     every SM pulls the same number of weight bytes whatever N and K are (o_proj has 16 tiles, gate/up 86).
-//     A tile that is split over several CTAs is reduced deterministically: every contributor writes its fp32
-//     partial to its own workspace slot and bumps the tile's counter; at the END of its range each contributor
-//     waits for the tile's other partials and reduces + finishes 1/n of the tile's token rows, always summing the
-//     slots in the same order.  (All CTAs are co-resident -- grid <= #SMs, one CTA per SM -- and every partial is
-//     written before its owner waits, so the wait cannot deadlock; it is bounded and traps.)
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-9 = epilogue (tcgen05.ld 32x32b:
-//     one thread = one output feature, 16 token rows per load) with the HF rounding points of dd_skinny_gemm.
+// The GEMM is a pure weight stream (intensity = M FLOP/byte, at or below the B200 ridge), so it is organised
+// around HBM: every SM must pull the same number of weight bytes, exactly once, with nothing serial behind the
+// stream.  Round 1 cut 256-feature tiles into K slices (stream-K) and paid for it with a reduction tail as long
+// as the main loop (fp32 partials through L2: flush, wait, reduce).  This version never sends a partial through L2:
+//   * the token rows are the M operand of tcgen05.mma (one accumulator per 128 rows, D[row, feature] in TMEM), the
+//     WEIGHTS are the N operand, so the feature width F of a tile is free in steps of 16 and is chosen per shape
+//     such that there are (just under) as many tiles as SMs: F = ceil16(N / #SMs), T = ceil(N / F) CTAs, each
+//     streaming its F x K slab of W once over the full K.  (qkv 12288 -> 128 x 96, gate|up 2 x 11008 -> 138 x
+//     (80+80), lm_head 32064 -> 144 x 224, o/down 4096 -> 128 x 32.)
+//   * per 64-wide k-block a CTA ingests F x 128 B of W (HBM, L2 evict-first) and Mp x 128 B of x (L2-resident,
+//     Mp = M rounded up to 16) through TMA into a 3..8-stage mbarrier ring.  FOUR producer warps: measured on
+//     B200 (tools/tma_probe.cu, profiles/r02/tma_probe.jsonl) one warp issues one bulk-tensor copy per ~600-670
+//     cycles whatever its size and warps scale linearly (1 warp x 16 KB boxes: 24 B/clk per SM, 4 warps: 97
+//     B/clk), so the copies of the ring are dealt round-robin to the producer warps.
+//   * a tcgen05.mma with operands in shared memory costs max(N/2, 32 + N/4) cycles (the tensor pipe, or reading the
+//     128-row A tile + the N-row B tile from shared memory; measured ~56 cycles at N=96), so a thin tile (o_proj /
+//     down: 4096 features over 148 SMs = 32 per SM) would be bound by MMA issue, not by HBM.  Shapes whose
+//     one-wave tile would be narrower than 128 features are therefore cut along K inside a thread-block CLUSTER of
+//     2 or 4 CTAs (qkv 12288 -> 70 tiles x 176 x 2 K-halves, o/down -> 32 x 128 x 4 K-quarters); after the main
+//     loop the CTAs of a cluster exchange their fp32 partials through distributed shared memory (each CTA owns a
+//     range of the tile's 16-feature chunks, the peers write their partial of those chunks into the idle operand
+//     ring of the owner, two cluster barriers), and the owner sums the ranks in rank order: deterministic, no
+//     global-memory round trip, no spinning on counters.
+//   * SwiGLU: the tile's W operand is [Fg gate rows | Fg up rows] (two boxes), so a thread of the epilogue holds
+//     gate and up of the same feature and applies the activation itself.
+//   * warps 0-3 = TMA producers, warp 4 = MMA issuer (one elected lane), warps 5-12 = epilogue (tcgen05.ld
+//     32x32b: one thread = one token row, 16 features per load = one 32-byte store) with the HF rounding points
+//     of dd_skinny_gemm.
+// Every output element is one fp32 accumulation over k in ascending order, whatever M is: results are
+// row-independent and bit-reproducible.  No workspace is used (the parameter is kept for ABI stability).
 // Algorithmic bytes per launch: N*K*2 (x2 for SwiGLU) -- the weights, read exactly once.
 #include <cstdlib>
 
@@ -28,28 +41,35 @@
 
 namespace dd {
 
-constexpr int SG_BF = 128;                     // output features per accumulator (UMMA M)
+constexpr int SG_BM = 128;                     // token rows per accumulator (UMMA M)
 constexpr int SG_BK = 64;                      // one 128-byte swizzle row of bf16
-constexpr int SG_WBYTES = SG_BF * SG_BK * 2;   // 16 KB
+constexpr int SG_PROD_WARPS = 4;
+constexpr int SG_MMA_WARP = SG_PROD_WARPS;
+constexpr int SG_EPI_WARP0 = SG_MMA_WARP + 1;
 constexpr int SG_EPI_WARPS = 8;
 constexpr int SG_EPI_THREADS = SG_EPI_WARPS * 32;
-constexpr int SG_THREADS = 64 + SG_EPI_THREADS;
-constexpr int SG_MAX_STAGES = 6;
-constexpr int SG_MAX_TILES = 2048;
-constexpr size_t SG_COUNTER_BYTES = (size_t)SG_MAX_TILES * 2 * sizeof(int);
+constexpr int SG_THREADS = (SG_EPI_WARP0 + SG_EPI_WARPS) * 32;
+constexpr int SG_MAX_STAGES = 8;
 constexpr int SG_SMEM_LIMIT = 227 * 1024;
+constexpr size_t SG_WS_BYTES = 16384;          // nominal (unused) workspace
 
 struct SgParams {
-  int M, Np, N, K, epi;
-  int w_rows;          // rows of the weight matrix (2N for SwiGLU)
-  int T, KB, G;        // tiles, k-blocks per tile, CTAs
+  int M, Mp, N, K, epi;
+  int F;               // output features per tile (SwiGLU: Fg gate + Fg up columns, F = Fg)
+  int Fw;              // N extent of the MMA = W rows per k-block (2F for SwiGLU)
+  int nacc;            // accumulators (128-row groups): 1 or 2
+  int T, KB, G;        // tiles, k-blocks (of this CTA's K slice), CTAs
+  int ring_bytes;      // operand ring (also the exchange buffer of the cluster reduction)
+  int S;               // CTAs per cluster = K slices per tile (1, 2, 4)
+  int max_own;         // 16-feature chunks a cluster rank owns at most
+  int bks;             // k-blocks per pipeline stage (one mbarrier round trip per stage)
+  int x_kb, x_bytes, w_kb, stage_bytes;   // smem: bytes per k-block of x / per stage of x / per k-block of W / per stage
   int stages, acc_stages, tmem_cols;
-  int dbg;             // DD_SG_DBG experiment bits: 1 no direct epilogue, 2 no partial flush, 4 no reduce, 8 no MMA
   const __nv_bfloat16* residual;
   void* y;
-  float* ws;           // [G][2 slots][2 acc][Np][128] fp32 partials
-  int* counters;       // [T][2]: partials arrived, slices finished
-  unsigned long long* ts;  // DD_SG_DBG & 16: [G][8] timestamps (experiment)
+#ifdef DD_SG_EXPERIMENT
+  long long* dbg;      // [G][8]: producer-0 {loop, wait} cycles, MMA {loop, wait} cycles, epilogue {wait, work} cycles
+#endif
 };
 
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
@@ -78,43 +98,78 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SG_EPI_THREADS) : "memory"); }
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
+#ifdef DD_SG_EXPERIMENT
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define SG_TS(slot) do { if (p.ts) p.ts[(size_t)cta * 8 + (slot)] = gtime(); } while (0)
-
-// first unit of CTA c; the CTA that owns unit u
-__device__ __forceinline__ long long sg_ubeg(int c, long long U, int G) { return (long long)c * U / G; }
-__device__ __forceinline__ int sg_owner(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
-
-// 128-feature group of accumulator a of tile t (row block of the weight matrix)
-__device__ __forceinline__ int sg_group(const SgParams& p, int tile, int a) {
-  return p.epi == DD_EPI_SWIGLU ? tile + a * (p.N / SG_BF) : 2 * tile + a;
+#endif
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
 }
 
-// one finished fp32 dot product -> the output, with the rounding points of the HF decoder (see dd_skinny_gemm)
-__device__ __forceinline__ void sg_store(const SgParams& p, int m, int f, float v0, float v1) {
+// 16 finished fp32 dot products of one token row (features f .. f+15) -> the output, with the rounding points of
+// the HF decoder (see dd_skinny_gemm): bf16(acc), + residual, fp32 logits, bf16(bf16(silu(g)) * u)
+__device__ __forceinline__ void sg_store16(const SgParams& p, int m, int f, const float (&v0)[16], const float (&v1)[16]) {
   const size_t o = (size_t)m * p.N + f;
-  const float r0 = bf16_round(v0);
-  if (p.epi == DD_EPI_NONE) {
-    reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r0);
-  } else if (p.epi == DD_EPI_RESIDUAL) {
-    reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r0 + __bfloat162float(p.residual[o]));
-  } else if (p.epi == DD_EPI_F32) {
-    reinterpret_cast<float*>(p.y)[o] = r0;
-  } else {  // SwiGLU: bf16( bf16(silu(g)) * u )
-    const float act = bf16_round(r0 / (1.f + __expf(-r0)));
-    reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(act * bf16_round(v1));
+  const int nvalid = min(16, p.N - f);   // N % 8 == 0: 16 or 8
+  if (p.epi == DD_EPI_F32) {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (4 * i < nvalid)
+        dst[i] = make_float4(bf16_round(v0[4 * i]), bf16_round(v0[4 * i + 1]), bf16_round(v0[4 * i + 2]),
+                             bf16_round(v0[4 * i + 3]));
+    return;
   }
+  float r[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = bf16_round(v0[i]);
+  if (p.epi == DD_EPI_RESIDUAL) {
+    const uint4* rs = reinterpret_cast<const uint4*>(p.residual + o);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (8 * h < nvalid) {
+        const uint4 q = rs[h];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = bf16x2_to_float2(w[i]);
+          r[8 * h + 2 * i] += t.x;
+          r[8 * h + 2 * i + 1] += t.y;
+        }
+      }
+    }
+  } else if (p.epi == DD_EPI_SWIGLU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = bf16_round(r[i] / (1.f + __expf(-r[i]))) * bf16_round(v1[i]);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + o);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (8 * h < nvalid)
+      dst[h] = make_uint4(pack_bf16x2(r[8 * h], r[8 * h + 1]), pack_bf16x2(r[8 * h + 2], r[8 * h + 3]),
+                          pack_bf16x2(r[8 * h + 4], r[8 * h + 5]), pack_bf16x2(r[8 * h + 6], r[8 * h + 7]));
 }
 
 __global__ void __launch_bounds__(SG_THREADS, 1)
@@ -122,25 +177,27 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                    const SgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int stage_bytes = 2 * SG_WBYTES + p.Np * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const int stage_bytes = p.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.ring_bytes);
   // bars: full[SG_MAX_STAGES] | empty[SG_MAX_STAGES] | tmem_full[2] | tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SG_MAX_STAGES + 4);
-  int* s_slot = reinterpret_cast<int*>(tmem_slot + 4);  // [<= 256] workspace slots of a split tile's contributors
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cta = blockIdx.x;
-  const long long U = (long long)p.T * p.KB;
-  const long long ubeg = sg_ubeg(cta, U, p.G), uend = sg_ubeg(cta + 1, U, p.G);
+  const int rank = p.S > 1 ? (int)cluster_ctarank() : 0;   // K slice of the tile
+  const int cta = blockIdx.x / p.S;                        // tile sequence index (clusters are consecutive CTAs)
+  const bool swiglu = p.epi == DD_EPI_SWIGLU;
+  const int n_stage_kb = p.KB / p.bks;   // pipeline stages per tile
 
-  if (threadIdx.x == 0) SG_TS(0);
+#ifdef DD_SG_EXPERIMENT
+  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cta * 8 + 6] = gtime_ns();
+#endif
   const uint32_t ring = smem_u32(smem);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * SG_MAX_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * SG_MAX_STAGES, bar_tempty = bar_tfull + 16;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SG_MAX_STAGES; ++i) {
-      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_full + 8 * i, 1);      // one arrive.expect_tx (all the stage's bytes) by the stage's producer
       mbar_init(bar_empty + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -149,7 +206,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == SG_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -159,232 +216,206 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) SG_TS(1);
+  const int my_tiles = cta < p.T ? (p.T - cta + p.G - 1) / p.G : 0;   // tiles cta, cta + G, ...
 
-  if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (elect_one()) {
+  if (warp < SG_PROD_WARPS) {
+    // =========================== TMA producers ===========================
+    // pipeline stage i of this CTA's tile sequence (bks k-blocks: x tile + W tile each) is filled by warp i % 4:
+    // one wait on the slot's empty barrier, one expect_tx, then bks * nops copies back to back (a copy costs the
+    // issuing thread ~170 cycles, a barrier wait ~190: tools/tma_probe2.cu)
+    if (warp == 0 && elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
     }
     const uint64_t pol = l2_policy_evict_first();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (long long u = ubeg; u < uend;) {
-      const int tile = (int)(u / p.KB), kb0 = (int)(u % p.KB);
-      const int kb1 = (int)min((long long)p.KB, kb0 + (uend - u));
-      const int g0 = sg_group(p, tile, 0);
-      int g1 = sg_group(p, tile, 1);
-      if (g1 * SG_BF >= p.w_rows) g1 = g0;  // odd number of groups: the second accumulator is padding
-      for (int kb = kb0; kb < kb1; ++kb) {
+    const int n_stage_total = my_tiles * n_stage_kb;
+    const uint32_t stage_tx = (uint32_t)(p.bks * (p.Mp + p.Fw) * 128);
+    // ring slot s always belongs to warp s % 4, so the uses of a slot are issued in order by ONE warp (with several
+    // warps per slot a warp two uses ahead would see the slot's empty barrier in the parity it waits for)
+#ifdef DD_SG_EXPERIMENT
+    long long dbg_wait = 0;
+    const long long dbg_t0 = clock64();
+#endif
+    for (int round = 0; round * p.stages < n_stage_total; ++round) {
+      const uint32_t phase = (uint32_t)(round & 1);
+      for (int stage = warp; stage < p.stages; stage += SG_PROD_WARPS) {
+        const int i = round * p.stages + stage;
+        if (i >= n_stage_total) break;
+        const int t = i / n_stage_kb, sk = i - t * n_stage_kb;
+        const int tile = cta + t * p.G;
+#ifdef DD_SG_EXPERIMENT
+        const long long dbg_w0 = clock64();
+#endif
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+#ifdef DD_SG_EXPERIMENT
+        dbg_wait += clock64() - dbg_w0;
+#endif
         if (elect_one()) {
           const uint32_t dst = ring + stage * stage_bytes, bar = bar_full + 8 * stage;
-          mbar_expect_tx(bar, (uint32_t)stage_bytes);
-          tma_load_2d_hint(dst, &tmap_w, bar, kb * SG_BK, g0 * SG_BF, pol);
-          tma_load_2d_hint(dst + SG_WBYTES, &tmap_w, bar, kb * SG_BK, g1 * SG_BF, pol);
-          tma_load_2d(dst + 2 * SG_WBYTES, &tmap_x, bar, kb * SG_BK, 0);
+          mbar_expect_tx(bar, stage_tx);
+          for (int b = 0; b < p.bks; ++b) {
+            const int kcol = ((rank * n_stage_kb + sk) * p.bks + b) * SG_BK;
+            tma_load_2d(dst + b * p.x_kb, &tmap_x, bar, kcol, 0);
+            const uint32_t wdst = dst + p.x_bytes + b * p.w_kb;
+            tma_load_2d_hint(wdst, &tmap_w, bar, kcol, tile * p.F, pol);      // (rows past the end of W are zero-filled)
+            if (swiglu)                                                       // [F gate rows | F up rows]
+              tma_load_2d_hint(wdst + p.F * 128, &tmap_w, bar, kcol, p.N + tile * p.F, pol);
+          }
         }
         __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      u += kb1 - kb0;
     }
-  } else if (warp == 1) {
+#ifdef DD_SG_EXPERIMENT
+    if (p.dbg && warp == 0 && lane == 0 && rank == 0) { p.dbg[cta * 8 + 0] = clock64() - dbg_t0; p.dbg[cta * 8 + 1] = dbg_wait; }
+#endif
+  } else if (warp == SG_MMA_WARP) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = make_idesc_bf16(SG_BF, p.Np);
+    const uint32_t idesc = make_idesc_bf16(SG_BM, p.Fw);
     int stage = 0, acc_stage = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (long long u = ubeg; u < uend;) {
-      const int kb0 = (int)(u % p.KB);
-      const int kb1 = (int)min((long long)p.KB, kb0 + (uend - u));
-      mbar_wait(bar_tempty + 8 * acc_stage, acc_phase ^ 1);  // the epilogue has drained this accumulator pair
+#ifdef DD_SG_EXPERIMENT
+    long long dbg_wait = 0;
+    const long long dbg_t0 = clock64();
+#endif
+    for (int t = 0; t < my_tiles; ++t) {
+      mbar_wait(bar_tempty + 8 * acc_stage, acc_phase ^ 1);  // the epilogue has drained this accumulator set
       tc_fence_after();
-      const uint32_t d0 = tmem_base + acc_stage * 2 * p.Np;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      const uint32_t d0 = tmem_base + acc_stage * p.nacc * p.Fw;
+      for (int sk = 0; sk < n_stage_kb; ++sk) {
+#ifdef DD_SG_EXPERIMENT
+        const long long dbg_w0 = clock64();
+#endif
         mbar_wait(bar_full + 8 * stage, phase);
+#ifdef DD_SG_EXPERIMENT
+        dbg_wait += clock64() - dbg_w0;
+#endif
         tc_fence_after();
         if (elect_one()) {
           const uint32_t base = ring + stage * stage_bytes;
-          const uint64_t b_desc = make_smem_desc(base + 2 * SG_WBYTES);
+          for (int b = 0; b < p.bks; ++b) {
+            const uint64_t b_desc = make_smem_desc(base + p.x_bytes + b * p.w_kb);
+            for (int a = 0; a < p.nacc; ++a) {
+              const uint64_t a_desc = make_smem_desc(base + b * p.x_kb + a * SG_BM * 128);
 #pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const uint64_t a_desc = make_smem_desc(base + a * SG_WBYTES);
-#pragma unroll
-            for (int k = 0; k < SG_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
-              if (!(p.dbg & 8)) umma_bf16(d0 + a * p.Np, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < SG_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+                umma_bf16(d0 + a * p.Fw, a_desc + 2 * k, b_desc + 2 * k, idesc, (sk > 0 || b > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(bar_empty + 8 * stage);
-          if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * acc_stage);
+          if (sk == n_stage_kb - 1) umma_commit(bar_tfull + 8 * acc_stage);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (++acc_stage == p.acc_stages) { acc_stage = 0; acc_phase ^= 1; }
-      u += kb1 - kb0;
     }
+#ifdef DD_SG_EXPERIMENT
+    if (p.dbg && lane == 0 && rank == 0) { p.dbg[cta * 8 + 2] = clock64() - dbg_t0; p.dbg[cta * 8 + 3] = dbg_wait; p.dbg[cta * 8 + 5] = gtime_ns(); }
+#endif
   } else {
-    // =========================== epilogue (warps 2..9) ===========================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int h = (warp - 2) >> 2;          // which half of the 16-row chunks
-    const int fl = q * 32 + lane;           // feature inside the 128-feature group
-    const int et = threadIdx.x - 64;        // 0..255
+    // =========================== epilogue (warps 5..12) ===========================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int g = (warp - SG_EPI_WARP0) >> 2;     // warp group 0 / 1
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int n_chunks = p.Np / 16;
-    const bool swiglu = p.epi == DD_EPI_SWIGLU;
-    int ptile[2], np = 0;
+    const int n_chunks = p.F / 16;
+    // two accumulators: group g owns accumulator g (rows g*128 ..); one: the groups alternate over the 16-feature chunks
+    const int a = p.nacc == 2 ? g : 0;
+    const int c0 = p.nacc == 2 ? 0 : g, cstep = p.nacc == 2 ? 1 : 2;
+    const int m = a * SG_BM + q * 32 + lane;     // token row of this thread
     int acc_stage = 0;
     uint32_t acc_phase = 0;
-    for (long long u = ubeg; u < uend;) {
-      const int tile = (int)(u / p.KB), kb0 = (int)(u % p.KB);
-      const int kb1 = (int)min((long long)p.KB, kb0 + (uend - u));
-      const bool complete = kb0 == 0 && kb1 == p.KB;
-      const int f0 = sg_group(p, tile, 0) * SG_BF + fl, f1 = sg_group(p, tile, 1) * SG_BF + fl;
-      const int fout0 = swiglu ? tile * SG_BF + fl : f0;  // SwiGLU writes feature tile*128+fl of [M, N]
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = cta + t * p.G;
+#ifdef DD_SG_EXPERIMENT
+      const long long dbg_e0 = clock64();
+#endif
       mbar_wait(bar_tfull + 8 * acc_stage, acc_phase);
+#ifdef DD_SG_EXPERIMENT
+      const long long dbg_e1 = clock64();
+#endif
       tc_fence_after();
-      if (et == 0) SG_TS(2);
-      const uint32_t t0 = lane_addr + acc_stage * 2 * p.Np;
-      if (complete) {
-        for (int c = h; c < n_chunks && !(p.dbg & 1); c += 2) {
-          float v0[16], v1[16];
-          tmem_ld16(t0 + c * 16, v0);
-          tmem_ld16(t0 + p.Np + c * 16, v1);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int m = c * 16 + i;
-            if (m < p.M) {
-              if (swiglu) {
-                if (fout0 < p.N) sg_store(p, m, fout0, v0[i], v1[i]);
-              } else {
-                if (f0 < p.N) sg_store(p, m, f0, v0[i], 0.f);
-                if (f1 < p.N) sg_store(p, m, f1, v1[i], 0.f);
-              }
-            }
-          }
-        }
-      } else {
-        // partial: slot 0 when this is the tile the CTA's range starts in, slot 1 otherwise
-        const int which = (tile == (int)(ubeg / p.KB)) ? 0 : 1;
-        // slot layout [accumulator][row][feature]: a warp store = 32 consecutive features of one row (128 B)
-        float* slot = p.ws + (size_t)(cta * 2 + which) * 2 * p.Np * SG_BF;
-        for (int c = h; c < n_chunks && !(p.dbg & 2); c += 2) {
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            float v[16];
-            tmem_ld16(t0 + a * p.Np + c * 16, v);
-            float* dst = slot + ((size_t)a * p.Np + c * 16) * SG_BF + fl;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c * 16 + i < p.M) __stcg(dst + i * SG_BF, v[i]);
-          }
-        }
-        ptile[np++] = tile;
+      if (p.S > 1) break;   // split tile (always the CTA's only one): the cluster reduction below finishes it
+      const uint32_t t0 = lane_addr + acc_stage * p.nacc * p.Fw + a * p.Fw;
+      for (int c = c0; c < n_chunks; c += cstep) {
+        float v0[16], v1[16];
+        tmem_ld16(t0 + c * 16, v0);
+        if (swiglu) tmem_ld16(t0 + p.F + c * 16, v1);
+        const int f = tile * p.F + c * 16;
+        if (m < p.M && f < p.N) sg_store16(p, m, f, v0, swiglu ? v1 : v0);
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc_stage);
-      if (!complete) {
-        __threadfence();
-        epi_bar_sync();
-        if (et == 0) atomicAdd(&p.counters[tile * 2], 1);
-      }
+#ifdef DD_SG_EXPERIMENT
+      if (p.dbg && threadIdx.x == SG_EPI_WARP0 * 32) { p.dbg[cta * 8 + 4] = clock64() - dbg_e1; }
+#endif
       if (++acc_stage == p.acc_stages) { acc_stage = 0; acc_phase ^= 1; }
-      u += kb1 - kb0;
     }
+  }
 
-    if (et == 0) SG_TS(3);
-    // ---- split tiles: wait for the other contributors, then reduce and finish this CTA's share of the rows ----
-    for (int i = 0; i < np; ++i) {
-      const int tile = ptile[i];
-      const int c_first = sg_owner((long long)tile * p.KB, U, p.G);
-      const int c_last = sg_owner((long long)(tile + 1) * p.KB - 1, U, p.G);
-      const int nseg = c_last - c_first + 1, j = cta - c_first;
-      epi_bar_sync();  // the previous tile's readers are done with s_slot
-      if (et < nseg) {  // workspace slot of every contributor: 2*cta + (0: the tile its range starts in, 1: otherwise)
-        const int cs = c_first + et;
-        s_slot[et] = cs * 2 + ((tile == (int)(sg_ubeg(cs, U, p.G) / p.KB)) ? 0 : 1);
-      }
-      if (et == 0) {
-        const long long t_start = clock64();
-        while (ld_acquire_gpu(&p.counters[tile * 2]) < nseg) {
-          __nanosleep(64);
-          if (clock64() - t_start > (1ll << 33)) __trap();  // a protocol bug must not hang the GPU
-        }
-      }
-      epi_bar_sync();
-      __threadfence();
-      if (et == 0) SG_TS(4 + i);
-      // this CTA's share: rows [m_beg, m_end) of the tile.  256 threads = 32 feature quads x 8 rows; a thread owns
-      // (quad, row) and (quad, row + 8) at once and sums the nseg slots in slot order, the loads of up to 8 slots
-      // (32 x 16 B) issued before the first add -- they are independent, only the adds are ordered.
-      const int m_beg = (int)((long long)j * p.M / nseg), m_end = (int)((long long)(j + 1) * p.M / nseg);
-      const int fq = (et & 31) * 4, rsub = et >> 5;
-      const int gbase0 = sg_group(p, tile, 0) * SG_BF, gbase1 = sg_group(p, tile, 1) * SG_BF;
-      const size_t slot_stride = (size_t)2 * p.Np * SG_BF, acc_stride = (size_t)p.Np * SG_BF;
-      for (int m = m_beg + rsub; m < m_end && !(p.dbg & 4); m += 16) {
-        const bool two = m + 8 < m_end;
-        float4 s[4];
+  if (p.S > 1) {
+    // ---- split-K inside the cluster: exchange the fp32 partials through distributed shared memory ----
+    // rank r owns chunks [r*nc/S, (r+1)*nc/S) of the tile's nc 16-feature chunks.  Buffer in the (now idle) operand
+    // ring of the owner: [source rank (own slot skipped)][own chunk][16 features][rows] floats, so that the 32 lanes
+    // of a warp (32 token rows) write / read 128 contiguous bytes.
+    const int n_chunks = p.F / 16, rows = p.nacc * SG_BM;
+    const bool epi = warp >= SG_EPI_WARP0;
+    const int q = warp & 3, g = (warp - SG_EPI_WARP0) >> 2;
+    const int a = p.nacc == 2 ? g : 0;
+    const int c0 = p.nacc == 2 ? 0 : g, cstep = p.nacc == 2 ? 1 : 2;
+    const int row = a * SG_BM + q * 32 + lane;
+    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.Fw;
+    tc_fence_before();
+    cluster_sync_all();     // #1: every CTA's accumulators are complete and its operand ring is idle
+    tc_fence_after();
+    if (epi) {
+      for (int c = c0; c < n_chunks; c += cstep) {
+        const int owner = ((c + 1) * p.S - 1) / n_chunks;          // the rank r with r*nc/S <= c < (r+1)*nc/S
+        if (owner == rank) continue;
+        const int lc = c - owner * n_chunks / p.S;
+        const int src = rank < owner ? rank : rank - 1;
+        float v[16];
+        tmem_ld16(t0 + c * 16, v);
+        const uint32_t dst = mapa_cluster(ring + (uint32_t)(((src * p.max_own + lc) * 16 * rows + row) * 4), (uint32_t)owner);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) s[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sb = 0; sb < nseg; sb += 8) {
-          float4 t[8][4];
+        for (int e = 0; e < 16; ++e) st_cluster_f32(dst + e * rows * 4, v[e]);
+      }
+    }
+    cluster_sync_all();     // #2: the peers' partials of my chunks have landed in my shared memory
+    if (epi) {
+      const int own_b = rank * n_chunks / p.S, own_e = (rank + 1) * n_chunks / p.S;
+      for (int c = own_b + c0; c < own_e; c += cstep) {
+        const int lc = c - own_b;
+        float acc[16];
+        for (int r = 0; r < p.S; ++r) {                            // rank order, whoever sums
+          float v[16];
+          if (r == rank) {
+            tmem_ld16(t0 + c * 16, v);
+          } else {
+            const int src = r < rank ? r : r - 1;
+            const uint32_t srca = ring + (uint32_t)(((src * p.max_own + lc) * 16 * rows + row) * 4);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (sb + i < nseg) {
-              const float* src = p.ws + (size_t)s_slot[sb + i] * slot_stride + (size_t)m * SG_BF + fq;
-              t[i][0] = __ldcg(reinterpret_cast<const float4*>(src));
-              t[i][1] = __ldcg(reinterpret_cast<const float4*>(src + acc_stride));
-              if (two) {
-                t[i][2] = __ldcg(reinterpret_cast<const float4*>(src + 8 * SG_BF));
-                t[i][3] = __ldcg(reinterpret_cast<const float4*>(src + acc_stride + 8 * SG_BF));
-              }
-            }
+            for (int e = 0; e < 16; ++e) v[e] = ld_shared_f32(srca + e * rows * 4);
           }
+          if (r == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (sb + i < nseg) {
+            for (int e = 0; e < 16; ++e) acc[e] = v[e];
+          } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (e < 2 || two) {
-                  s[e].x += t[i][e].x; s[e].y += t[i][e].y; s[e].z += t[i][e].z; s[e].w += t[i][e].w;
-                }
-              }
-            }
+            for (int e = 0; e < 16; ++e) acc[e] += v[e];
           }
         }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          if (r == 1 && !two) break;
-          const int mm = m + 8 * r;
-          const float a0[4] = {s[2 * r].x, s[2 * r].y, s[2 * r].z, s[2 * r].w};
-          const float a1[4] = {s[2 * r + 1].x, s[2 * r + 1].y, s[2 * r + 1].z, s[2 * r + 1].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (swiglu) {
-              if (tile * SG_BF + fq + e < p.N) sg_store(p, mm, tile * SG_BF + fq + e, a0[e], a1[e]);
-            } else {
-              if (gbase0 + fq + e < p.N) sg_store(p, mm, gbase0 + fq + e, a0[e], 0.f);
-              if (gbase1 + fq + e < p.N) sg_store(p, mm, gbase1 + fq + e, a1[e], 0.f);
-            }
-          }
-        }
-      }
-      epi_bar_sync();
-      if (et == 0) {
-        const int old = atomicAdd(&p.counters[tile * 2 + 1], 1);
-        if (old == nseg - 1) {  // every contributor has passed its wait: re-arm the tile for the next launch
-          p.counters[tile * 2] = 0;
-          p.counters[tile * 2 + 1] = 0;
-        }
+        const int f = cta * p.F + c * 16;
+        if (row < p.M && f < p.N) sg_store16(p, row, f, acc, acc);
       }
     }
   }
 
-  if (threadIdx.x == 64) SG_TS(6);
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) SG_TS(7);
-  if (warp == 1) {
+#ifdef DD_SG_EXPERIMENT
+  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cta * 8 + 7] = gtime_ns();
+#endif
+  if (warp == SG_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -392,46 +423,81 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 }
 
 static int sg_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  static int cache[64];
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
 }
 
 struct SgPlan {
-  int Np, T, KB, G, stages, acc_stages, tmem_cols;
-  size_t smem, ws_bytes;
+  int Mp, F, Fw, nacc, S, max_own, T, KB, G, bks, x_kb, x_bytes, w_kb, stage_bytes, stages, acc_stages, tmem_cols;
+  size_t smem;
 };
 static SgPlan sg_plan(int M, int N, int K, int epi) {
   SgPlan s;
-  s.Np = (M + 15) / 16 * 16;
-  const int groups = ceil_div(N, SG_BF);
-  s.T = epi == DD_EPI_SWIGLU ? groups : ceil_div(groups, 2);
-  s.KB = K / SG_BK;
-  const long long U = (long long)s.T * s.KB;
+  const bool swiglu = epi == DD_EPI_SWIGLU;
   const int sms = sg_num_sms();
-  s.G = (int)(U < sms ? U : sms);
-  // Few tiles: cut every tile into the same number of K slices (G = T * slices), so that a CTA holds exactly ONE
-  // partial and the tail of the kernel is one flush + one reduction, as long as that idles < 8 % of the SMs.
-  // Otherwise (e.g. 86 gate/up tiles) plain stream-K over all SMs: some CTAs then straddle two tiles.
-  if (s.T <= sms && s.KB >= sms / s.T) {
-    const int slices = sms / s.T;
-    if ((sms - s.T * slices) * 100 <= 8 * sms && !getenv("DD_SG_NOALIGN")) s.G = s.T * slices;
+  s.Mp = (M + 15) / 16 * 16;
+  s.nacc = M > SG_BM ? 2 : 1;
+  // Tile width F (multiple of 16, MMA N extent = F or 2F <= 256) and K slices S per tile (cluster size): the
+  // smallest S in {1, 2, 4} whose one-wave tile is at least 128 features wide -- below that the MMA issue rate, not
+  // HBM, bounds the stream.  Clusters of 4 only place on 132 of the 148 SMs (GPC boundaries).  The choice depends
+  // on N and K only, never on M: a token row sums the same products in the same order whatever rides in the pass.
+  const int total_kb = K / SG_BK;
+  const int fmax = swiglu ? 128 : 256;
+  s.S = 1;
+  for (int S = 1; S <= 4; S *= 2) {
+    if (total_kb % S) break;
+    s.S = S;
+    const int slots = (S == 4 ? sms / 37 * 33 : sms) / S;        // clusters that are co-resident
+    int F = (ceil_div(N, slots > 0 ? slots : 1) + 15) / 16 * 16;
+    if (F > fmax) F = fmax;
+    s.F = F;
+    if ((swiglu ? 2 * F : F) >= 128 || swiglu) break;              // (SwiGLU pairs gate / up columns: never split)
   }
-  const int stage_bytes = 2 * SG_WBYTES + s.Np * 128;
-  const int fixed = 1024 + (2 * SG_MAX_STAGES + 4) * 8 + 16 + 256 * 4;
+  s.Fw = swiglu ? 2 * s.F : s.F;
+  s.T = ceil_div(N, s.F);
+  s.KB = total_kb / s.S;
+  {
+    const int slots = (s.S == 4 ? sms / 37 * 33 : sms) / s.S;
+    if (s.S > 1 && s.T > slots) {   // more tiles than one wave of clusters: fall back to whole-K tiles
+      s.S = 1;
+      s.KB = total_kb;
+    }
+    s.G = s.T < slots || s.S > 1 ? s.T : (s.T < sms ? s.T : sms);
+  }
+  s.max_own = ceil_div(s.F / 16, s.S);
+  // k-blocks per pipeline stage: a stage costs the producer and the MMA issuer one mbarrier round trip each
+  // (~300 cycles in all), so thin operands ride several k-blocks per stage; a stage stays <= 48 KB and the ring at
+  // least 4 deep
+  s.x_kb = s.Mp * 128;
+  s.w_kb = s.Fw * 128;
+  const int slack = (s.nacc * SG_BM - s.Mp) * 128;   // the last k-block's MMA reads 128-row tiles past Mp rows
+  s.bks = 1;
+  for (int b = 8; b > 1; b >>= 1) {
+    if (s.KB % b) continue;
+    const int sb = b * (s.x_kb + s.w_kb) + slack;
+    if (sb <= 48 * 1024 && (SG_SMEM_LIMIT - 2048) / sb >= 4) { s.bks = b; break; }
+  }
+  s.x_bytes = (s.bks * s.x_kb + slack + 1023) & ~1023;
+  s.stage_bytes = s.x_bytes + s.bks * s.w_kb;
+  const int stage_bytes = s.stage_bytes;
+  const int fixed = 1024 + (2 * SG_MAX_STAGES + 4) * 8 + 16;
   int st = (SG_SMEM_LIMIT - fixed) / stage_bytes;
   s.stages = st > SG_MAX_STAGES ? SG_MAX_STAGES : st;
-  s.smem = (size_t)fixed + (size_t)s.stages * stage_bytes;
-  s.acc_stages = 4 * s.Np <= 512 ? 2 : 1;
+  // the cluster reduction parks (S - 1) x max_own chunks of fp32 partials in the ring
+  const size_t xchg = s.S > 1 ? (size_t)(s.S - 1) * s.max_own * 16 * s.nacc * SG_BM * 4 : 0;
+  size_t ring = (size_t)s.stages * stage_bytes;
+  if (ring < xchg) ring = xchg;
+  s.smem = (size_t)fixed + ring;
+  s.acc_stages = (s.S == 1 && s.T > s.G && 2 * s.nacc * s.Fw <= 512) ? 2 : 1;
   int cols = 32;
-  while (cols < s.acc_stages * 2 * s.Np) cols *= 2;
+  while (cols < s.acc_stages * s.nacc * s.Fw) cols *= 2;
   s.tmem_cols = cols;
-  s.ws_bytes = SG_COUNTER_BYTES + (size_t)s.G * 2 * 2 * s.Np * SG_BF * sizeof(float) + (size_t)s.G * 8 * 8;
   return s;
 }
 
@@ -440,17 +506,19 @@ static int sg_check(const char* fn, int M, int N, int K, int epi) {
   DD_CHECK_ARG(K >= SG_BK && K % SG_BK == 0, "%s: K=%d must be a positive multiple of %d", fn, K, SG_BK);
   DD_CHECK_ARG(N >= 8 && N % 8 == 0, "%s: N=%d must be a positive multiple of 8", fn, N);
   DD_CHECK_ARG(epi >= DD_EPI_NONE && epi <= DD_EPI_SWIGLU, "%s: bad epilogue %d", fn, epi);
-  DD_CHECK_ARG(epi != DD_EPI_SWIGLU || N % SG_BF == 0, "%s: SwiGLU needs N %% %d == 0 (N=%d)", fn, SG_BF, N);
-  DD_CHECK_ARG(ceil_div(N, SG_BF) <= SG_MAX_TILES, "%s: N=%d too large", fn, N);
   return DD_OK;
 }
 
 }  // namespace dd
 
+#ifdef DD_SG_EXPERIMENT
+extern "C" int dd_stream_gemm_debug_ctas(int M, int N, int K, int epilogue) { return dd::sg_plan(M, N, K, epilogue).G; }
+#endif
+
 extern "C" size_t dd_stream_gemm_workspace_bytes(int M, int N, int K, int epilogue) {
   using namespace dd;
   if (sg_check("dd_stream_gemm_workspace_bytes", M, N, K, epilogue)) return 0;
-  return sg_plan(M, N, K, epilogue).ws_bytes;
+  return SG_WS_BYTES;
 }
 
 extern "C" int dd_stream_gemm(const void* x, const void* w, const void* residual, int M, int N, int K, int epilogue,
@@ -460,46 +528,67 @@ extern "C" int dd_stream_gemm(const void* x, const void* w, const void* residual
   if (int rc = sg_check("dd_stream_gemm", M, N, K, epilogue)) return rc;
   DD_CHECK_ARG(x && w && y && workspace, "dd_stream_gemm: null pointer");
   DD_CHECK_ARG(epilogue != DD_EPI_RESIDUAL || residual, "dd_stream_gemm: residual epilogue needs residual");
-  DD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+  DD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
+                   ((uintptr_t)residual & 15) == 0,
                "dd_stream_gemm: operands must be 16-byte aligned");
-  const SgPlan s = sg_plan(M, N, K, epilogue);
-  if (workspace_bytes < s.ws_bytes) {
-    set_error("dd_stream_gemm: workspace %zu < %zu bytes", workspace_bytes, s.ws_bytes);
+  if (workspace_bytes < SG_WS_BYTES) {
+    set_error("dd_stream_gemm: workspace %zu < %zu bytes", workspace_bytes, SG_WS_BYTES);
     return DD_ERR_WORKSPACE;
   }
-  DD_CHECK_ARG(s.stages >= 2, "dd_stream_gemm: M=%d leaves no room for a 2-stage ring", M);
+  const SgPlan s = sg_plan(M, N, K, epilogue);
+  DD_CHECK_ARG(s.stages >= 2, "dd_stream_gemm: M=%d, N=%d leave no room for a 2-stage ring", M, N);
   const int w_rows = epilogue == DD_EPI_SWIGLU ? 2 * N : N;
   CUtensorMap tw, tx;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)w_rows};
     const uint64_t strides[1] = {(uint64_t)K * 2};
-    const uint32_t box[2] = {SG_BK, SG_BF};
+    const uint32_t box[2] = {SG_BK, (uint32_t)s.F};
     if (int rc = make_tmap_bf16_sw128(&tw, w, 2, dims, strides, box, "dd_stream_gemm(w)")) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)K * 2};
-    const uint32_t box[2] = {SG_BK, (uint32_t)s.Np};
+    const uint32_t box[2] = {SG_BK, (uint32_t)s.Mp};
     if (int rc = make_tmap_bf16_sw128(&tx, x, 2, dims, strides, box, "dd_stream_gemm(x)")) return rc;
   }
   SgParams p{};
-  p.M = M; p.Np = s.Np; p.N = N; p.K = K; p.epi = epilogue; p.w_rows = w_rows;
+  p.M = M; p.Mp = s.Mp; p.N = N; p.K = K; p.epi = epilogue; p.F = s.F; p.Fw = s.Fw; p.nacc = s.nacc;
+  p.bks = s.bks; p.x_kb = s.x_kb; p.x_bytes = s.x_bytes; p.w_kb = s.w_kb; p.stage_bytes = s.stage_bytes;
+  p.S = s.S; p.max_own = s.max_own; p.ring_bytes = (int)(s.smem - (1024 + (2 * SG_MAX_STAGES + 4) * 8 + 16));
   p.T = s.T; p.KB = s.KB; p.G = s.G; p.stages = s.stages; p.acc_stages = s.acc_stages; p.tmem_cols = s.tmem_cols;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.y = y;
+#ifdef DD_SG_EXPERIMENT
+  p.dbg = (getenv("DD_SG_DBG") && workspace_bytes >= (size_t)s.G * 64 && s.G * 64 <= 16384) ? static_cast<long long*>(workspace) : nullptr;
+  if (getenv("DD_SG_DBG")) fprintf(stderr, "[sg] M=%d N=%d K=%d epi=%d: F=%d T=%d S=%d bks=%d stage=%d B x %d stages, tmem %d\n", M, N, K, epilogue, s.F, s.T, s.S, s.bks, s.stage_bytes, s.stages, s.tmem_cols);
+#endif
   {
-    static const int dbg = [] { const char* e = getenv("DD_SG_DBG"); return e ? atoi(e) : 0; }();
-    p.dbg = dbg;
-    p.ts = (dbg & 16) ? reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + s.ws_bytes - (size_t)s.G * 8 * 8) : nullptr;
+    // the opt-in for > 48 KB of dynamic shared memory is a per-device attribute
+    static bool attr_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      DD_CHECK_CUDA(cudaFuncSetAttribute(stream_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_LIMIT));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
-  p.counters = static_cast<int*>(workspace);
-  p.ws = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + SG_COUNTER_BYTES);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DD_CHECK_CUDA(cudaFuncSetAttribute(stream_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_LIMIT));
-    attr_set = true;
+  if (s.S == 1) {
+    stream_gemm_kernel<<<s.G, SG_THREADS, s.smem, (cudaStream_t)stream>>>(tw, tx, p);
+    DD_CHECK_LAUNCH();
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(s.G * s.S);
+    cfg.blockDim = dim3(SG_THREADS);
+    cfg.dynamicSmemBytes = s.smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = s.S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, stream_gemm_kernel, tw, tx, p));
   }
-  stream_gemm_kernel<<<s.G, SG_THREADS, s.smem, (cudaStream_t)stream>>>(tw, tx, p);
-  DD_CHECK_LAUNCH();
   return DD_OK;
 }

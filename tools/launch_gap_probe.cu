@@ -1,0 +1,114 @@
+// What does one kernel node of a CUDA graph cost on B200 when the kernel itself does nothing?  Variants: grid size,
+// dynamic shared memory, TMEM alloc/dealloc, 128-byte __grid_constant__ tensor maps, thread-block clusters, and a
+// kernel that ends with outstanding global stores.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 tools/launch_gap_probe.cu -o tools/_bin/launch_gap_probe
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#define CK(x)                                                                              \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess) {                                                               \
+      fprintf(stderr, "%s failed: %s (line %d)\n", #x, cudaGetErrorString(e_), __LINE__); \
+      exit(1);                                                                             \
+    }                                                                                      \
+  } while (0)
+
+struct Big { unsigned char b[256]; };
+
+__global__ void k_empty(int* sink) {
+  if (sink && threadIdx.x == 1000) *sink = 1;
+}
+__global__ void k_params(const __grid_constant__ Big a, int* sink) {
+  if (sink && threadIdx.x == 1000) *sink = a.b[3];
+}
+__global__ void k_smem(int* sink) {
+  extern __shared__ unsigned char sm[];
+  if (sink && threadIdx.x == 1000) *sink = sm[5];
+}
+__global__ void k_tmem(int* sink, int cols) {
+  __shared__ uint32_t slot;
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&slot)),
+                 "r"((uint32_t)cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t base = slot;
+  if ((threadIdx.x >> 5) == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"((uint32_t)cols) : "memory");
+  if (sink && threadIdx.x == 1000) *sink = 1;
+}
+__global__ void k_store(float* out, int n_per_thread) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = 0; j < n_per_thread; ++j) out[i + (size_t)j * gridDim.x * blockDim.x] = (float)j;
+}
+
+template <typename F>
+static float time_graph(cudaStream_t st, int n, F&& launch) {
+  cudaGraph_t g;
+  cudaGraphExec_t ge;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  for (int r = 0; r < n; ++r) launch();
+  CK(cudaStreamEndCapture(st, &g));
+  CK(cudaGraphInstantiate(&ge, g, 0));
+  CK(cudaGraphLaunch(ge, st));
+  CK(cudaStreamSynchronize(st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e9f;
+  for (int it = 0; it < 5; ++it) {
+    CK(cudaEventRecord(e0, st));
+    CK(cudaGraphLaunch(ge, st));
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGraphExecDestroy(ge));
+  CK(cudaGraphDestroy(g));
+  return best * 1e3f / n;
+}
+
+int main() {
+  CK(cudaSetDevice(0));
+  cudaStream_t st;
+  CK(cudaStreamCreate(&st));
+  const int n = 200;
+  float* out;
+  CK(cudaMalloc(&out, 256 << 20));
+  Big big{};
+  CK(cudaFuncSetAttribute(k_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  auto report = [&](const char* name, float us) { printf("{\"probe\": \"%s\", \"us_per_node\": %.2f}\n", name, us); fflush(stdout); };
+  report("empty_1x32", time_graph(st, n, [&] { k_empty<<<1, 32, 0, st>>>(nullptr); }));
+  report("empty_148x416", time_graph(st, n, [&] { k_empty<<<148, 416, 0, st>>>(nullptr); }));
+  report("empty_148x1024", time_graph(st, n, [&] { k_empty<<<148, 1024, 0, st>>>(nullptr); }));
+  report("params256B_148x416", time_graph(st, n, [&] { k_params<<<148, 416, 0, st>>>(big, nullptr); }));
+  report("smem200KB_148x416", time_graph(st, n, [&] { k_smem<<<148, 416, 200 * 1024, st>>>(nullptr); }));
+  report("tmem512_148x416", time_graph(st, n, [&] { k_tmem<<<148, 416, 0, st>>>(nullptr, 512); }));
+  report("tmem128_148x416", time_graph(st, n, [&] { k_tmem<<<148, 416, 0, st>>>(nullptr, 128); }));
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148); cfg.blockDim = dim3(416); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    report("cluster2_148x416", time_graph(st, n, [&] { CK(cudaLaunchKernelEx(&cfg, k_empty, (int*)nullptr)); }));
+    cfg.gridDim = dim3(128);
+    attr[0].val.clusterDim.x = 4;
+    report("cluster4_128x416", time_graph(st, n, [&] { CK(cudaLaunchKernelEx(&cfg, k_empty, (int*)nullptr)); }));
+  }
+  report("store_148x416_x1", time_graph(st, n, [&] { k_store<<<148, 416, 0, st>>>(out, 1); }));
+  report("store_148x416_x64(16MB)", time_graph(st, n, [&] { k_store<<<148, 416, 0, st>>>(out, 64); }));
+  return 0;
+}
