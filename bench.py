@@ -226,6 +226,13 @@ def run_ours(args):
         #      events around every dd_skinny_gemm launch on the launching stream
         roof = profile_dominant_kernel(eng, hbm, peak_src)
         stages = profile_stages(eng, vis_hidden, S0, hbm, tf)
+        sched = schedule_check(model, eng, vis_hidden, last_hidden, S0, T, start, tokens_check)
+        del eng
+        model._engines.clear()
+        torch.cuda.empty_cache()
+    target = None
+    if not args.no_target and not args.tiny:
+        target = run_target(model, args, rank, world, local, dist, hbm, tf)
 
     if dist is not None:
         t = torch.tensor([dt, dt_e2e], device=dev, dtype=torch.float64)
@@ -251,13 +258,176 @@ def run_ours(args):
         "ms_per_token": round(dt / args.steps / T * 1e3, 4),
         "clocks": clk, "roofline": roof, "stage_rooflines": stages,
         "token_checksum": int(tokens_check.long().sum().item()),
+        "schedule_check": sched,
     }
+    if target is not None:
+        line["target_config"] = target
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_sample_steps)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _fresh_engine(model, eng, B, n_vis, max_seq, est_seq, speculative=None, seq_base=0, gemm_backend=None):
+    """An engine on the model's weights with `eng`'s algorithm settings (own KV cache)."""
+    from dropoutdecoding_b200.engine import DropoutDecodeEngine
+    return DropoutDecodeEngine(model.decoder_weights(), B, n_vis, max_seq, probs=eng.probs, mode=eng.mode,
+                               keep_relevant=eng.keep_relevant, topk=eng.topk, aggregate=eng.aggregate, seed=eng.seed,
+                               max_steps=max_seq, est_seq=est_seq, vote_on=eng.vote_on, seq_base=seq_base,
+                               speculative=speculative, gemm_backend=gemm_backend)
+
+
+def schedule_check(model, eng, vis_hidden, last_hidden, S0, T, start, tokens_timed, reps=2):
+    """Re-decode the timed inputs in the REFERENCE'S OWN ORDER (preliminary pass, then the K masked contexts:
+    models/llava.py:294-305, 336-361; speculative="off") on a second engine fed the same prefix cache, and compare the
+    token sequences with what the timed (speculative + lookahead) schedule produced."""
+    B, n_vis = eng.B, eng.n_vis
+    e2 = _fresh_engine(model, eng, B, n_vis, S0 + T, S0 + T // 2, speculative="off", seq_base=eng.seq_base)
+    e2.load_prefill(eng.k_cache[:, :, :, :S0], eng.v_cache[:, :, :, :S0], [start] * B)
+
+    def run():
+        e2.seq_lens.fill_(S0)
+        e2.uncertainty_stage(vis_hidden)
+        e2.first_token(last_hidden)
+        e2.decode(T - 1, use_graph=True)
+
+    run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    dt = a.elapsed_time(b) * 1e-3 / reps
+    tok2 = e2.generated()
+    equal = bool(torch.equal(tok2, tokens_timed))
+    first_diff = None
+    if not equal:
+        d = (tok2 != tokens_timed).nonzero()
+        first_diff = [int(d[0, 0]), int(d[0, 1])]
+    del e2
+    return {"what": "the same inputs decoded again in the reference's two-pass order (speculative off) on a second engine",
+            "two_pass_tokens_equal": equal, "first_difference_seq_pos": first_diff,
+            "two_pass_value": round(B * T / dt, 2), "two_pass_ms_per_token": round(dt / T * 1e3, 4)}
+
+
+def run_target(model, args, rank, world, local, dist, hbm, tf):
+    """north_star target / BASELINE configs[2]: 64 synthetic images (64 / N per GPU), K=3, 512 new tokens, EOS ignored.
+    Sequences are sharded over the ranks with no per-step collective (the Philox stream is keyed by the global
+    sequence index); the final token matrix is all-gathered inside the timed region."""
+    from dropoutdecoding_b200 import ops
+    dev = torch.device(f"cuda:{local}")
+    total, T = args.target_batch, args.target_tokens
+    B = total // world
+    ids_h, px_h = synthetic_inputs(B, seed0=1001 + rank * B)
+    out = {}
+    with torch.no_grad():
+        merged, start, n_vis = model._merge(ids_h.to(dev), px_h.to(dev, torch.bfloat16))
+        S0 = merged.shape[1]
+        probe = model._engine(1, n_vis, S0 + 8, est_seq=S0 + 4)          # algorithm settings of the wrapper
+        eng = _fresh_engine(model, probe, B, n_vis, S0 + T, S0 + T // 2, seq_base=rank * B)
+        model._engines.clear()
+        del probe
+        hidden = eng.prefill(merged.to(torch.bfloat16), [start] * B)
+        vis_hidden = hidden[:, start:start + n_vis].contiguous()
+        last_hidden = hidden[:, -1].contiguous()
+        del hidden, merged
+        gathered = [torch.zeros(B, T, dtype=torch.int32, device=dev) for _ in range(world)] if dist is not None else None
+
+        def hot_path():
+            eng.seq_lens.fill_(S0)
+            eng.uncertainty_stage(vis_hidden)
+            eng.first_token(last_hidden)
+            eng.decode(T - 1, use_graph=True)
+            if dist is not None:
+                dist.all_gather(gathered, eng.generated().contiguous())
+
+        def barrier():
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        hot_path()                               # warm-up (captures the step graph)
+        barrier()
+        eng.launch_count = eng.n_spec_steps = 0
+        if eng.spec_batch:
+            eng._fb_total.zero_(); eng._seq_steps_done = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hot_path()
+        e1.record()
+        barrier()
+        dt_rank = e0.elapsed_time(e1) * 1e-3
+        times = torch.tensor([dt_rank], device=dev, dtype=torch.float64)
+        per_rank = [times.clone() for _ in range(world)]
+        if dist is not None:
+            dist.all_gather(per_rank, times)
+        per_rank_ms = [round(float(t.item()) * 1e3, 2) for t in per_rank]
+        dt = max(per_rank_ms) * 1e-3
+        toks = eng.generated()
+        cfg = eng.cfg
+        rows = B * ((2 * eng.K + 1) if eng.batch_la else (eng.K + 1 if (eng.spec_batch or eng.spec_active) else eng.K))
+        passes = eng.n_spec_steps
+        # per-pass roofline: weights once + K/V of every sequence once, at the measured HBM peak
+        S_mean = S0 + T / 2
+        pass_bytes = eng.w.stream_bytes_per_pass() + B * S_mean * 2 * cfg.n_layers * cfg.n_kv_heads * cfg.head_dim * 2
+        out = {"workload": f"llava-1.5-7b random-init bf16, {total} synthetic images ({B} per GPU), K=3 masks, {T} new "
+                           f"tokens, EOS ignored; north_star target at 1 GPU, BASELINE configs[2] at 2/4/8",
+               "value": round(total * T / dt, 2), "unit": "tokens/s", "n_gpus": world, "batch_per_gpu": B,
+               "new_tokens": T, "ms_per_token": round(dt / T * 1e3, 4), "per_rank_ms": per_rank_ms,
+               "rows_per_pass": rows, "passes": passes,
+               "gemm": "dd::stream_gemm_kernel" if eng._use_stream(rows) else ("dd::skinny_gemm_kernel" if rows <= 32 else "library"),
+               "fallback_rate": round(eng.fallback_rate(), 4), "gpu_launches": int(eng.launch_count),
+               "pass_roofline": {"bound": "hbm", "bytes_per_pass": int(pass_bytes), "passes": passes,
+                                 "achieved": round(pass_bytes * passes / dt_rank / 1e9, 1), "peak": hbm, "unit": "GB/s",
+                                 "frac": round(pass_bytes * passes / dt_rank / 1e9 / hbm, 4)},
+               "token_checksum": int(toks.long().sum().item())}
+        # ---- stage rooflines at this batch: decode attention, the widest GEMM of the pass, the uncertainty stage
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def timeit(fn, iters=5):
+            fn(); torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(iters):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b) * 1e-3)
+            return best
+
+        pbuf = eng.pe if eng.batch_la else (eng.pc if (eng.spec_batch or eng.spec_active) else eng.pb)
+        S_att = int(S_mean)
+        eng.seq_lens.fill_(S_att)
+        mask = eng.la_mask if eng.batch_la else (eng.spec_mask if (eng.spec_batch or eng.spec_active) else eng.bitmask)
+        G = cfg.n_heads // cfg.n_kv_heads
+        mem = min(pbuf.M, max(1, 32 // G))
+        t_att = timeit(lambda: ops.decode_attention(pbuf.q, pbuf.k_new[0], pbuf.v_new[0], eng.k_cache[0], eng.v_cache[0],
+                                                    eng.seq_lens, eng.vis_start, mask, eng.n_vis, eng.scale, pbuf.splits,
+                                                    pbuf.attn, pbuf.ws, member_offset=0, members=mem))
+        kv = 2 * S_att * cfg.n_kv_heads * cfg.head_dim * 2 * B
+        out["decode_attention"] = {"bound": "hbm", "kernel": "dd::attn_partial_kernel", "us": round(t_att * 1e6, 2),
+                                   "members": mem, "seq_len": S_att, "achieved": round(kv / t_att / 1e9, 1), "peak": hbm,
+                                   "unit": "GB/s", "frac": round(kv / t_att / 1e9 / hbm, 4), "algorithmic_bytes": kv}
+        if eng._use_stream(rows):
+            lw = eng.w.layers[0]
+            x = pbuf.xn[:rows]
+            t_g = timeit(lambda: ops.stream_gemm(x, lw["wgu"], ops.EPI_SWIGLU, out=pbuf.act[:rows], workspace=eng._sg_ws))
+            wb = lw["wgu"].numel() * 2
+            out["stream_gemm_gate_up"] = {"bound": "hbm", "kernel": "dd::stream_gemm_kernel", "rows": rows,
+                                          "us": round(t_g * 1e6, 2), "achieved": round(wb / t_g / 1e9, 1), "peak": hbm,
+                                          "unit": "GB/s", "frac": round(wb / t_g / 1e9 / hbm, 4), "algorithmic_bytes": wb}
+        t_unc = timeit(lambda: eng.uncertainty_stage(vis_hidden), iters=3)
+        flops = 2.0 * B * n_vis * cfg.d_model * cfg.vocab
+        out["uncertainty_stage"] = {"bound": "tensor", "images": B, "ms": round(t_unc * 1e3, 3),
+                                    "achieved": round(flops / t_unc / 1e12, 1), "peak": tf, "unit": "TFLOP/s",
+                                    "frac": round(flops / t_unc / 1e12 / tf, 4), "algorithmic_flops": flops}
+        del eng
+        torch.cuda.empty_cache()
+    return out
 
 
 def profile_dominant_kernel(eng, hbm, peak_src):
@@ -465,6 +635,9 @@ def main():
     ap.add_argument("--new-tokens", type=int, default=NEW_TOKENS)
     ap.add_argument("--tiny", action="store_true", help="tiny shapes (debugging; not a valid bench line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-target", action="store_true", help="skip the 64-image / 512-token target configuration")
+    ap.add_argument("--target-batch", type=int, default=64, help="images of the target configuration, all GPUs together")
+    ap.add_argument("--target-tokens", type=int, default=512)
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "dd_version": (C.c_int, []),
     "dd_last_error": (C.c_char_p, []),
     "dd_uncertainty_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "dd_uncertainty_overflow_offset": (C.c_size_t, [C.c_int] * 4),
     "dd_uncertainty_project": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "dd_sample_masks": (C.c_int, [_P, _P, C.c_int, _P, C.POINTER(C.c_double), C.c_int, _P, C.c_uint64,
@@ -55,7 +56,7 @@ _SIGNATURES = {
     "dd_decoder_linear": (C.c_int, [_P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                     C.POINTER(RopeArgs), _P]),
     "dd_rope_stage": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
-    "dd_embed_gather": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dd_embed_gather": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dd_step_advance": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
 }
 

@@ -13,9 +13,13 @@ struct ArgMax {
   float v;
   int i;
 };
-// torch.argmax: the first index of the maximum
+// torch.argmax: the first index of the maximum; NaN counts as the maximum (so a row of NaNs, like a row of -inf,
+// still yields a valid index and never the 0x7fffffff start value)
 __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
-  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+  const bool an = a.v != a.v, bn = b.v != b.v;
+  const bool gt = bn ? !an : (!an && b.v > a.v);
+  const bool eq = (an && bn) || b.v == a.v;
+  return (gt || (eq && b.i < a.i)) ? b : a;
 }
 __device__ __forceinline__ ArgMax block_argmax(ArgMax x, ArgMax* s_warp) {
 #pragma unroll

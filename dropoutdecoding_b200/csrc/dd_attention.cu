@@ -429,11 +429,16 @@ static int launch_attn(const AttnParams& p, const void* k_new, const void* v_new
     if (int rc = make_tmap_bf16_sw128(&tmap_v, p.v_cache, 3, dims, strides, box, "dd_decode_attention(v_cache)")) return rc;
   }
   const size_t smem = attn_smem_bytes<D, QT>(p.M, p.bitmask ? p.mask_words : 0);
-  static size_t configured = 0;  // opt in to > 48 KB dynamic smem once per instantiation (grow-only)
-  if (smem > configured) {
-    DD_CHECK_CUDA(cudaFuncSetAttribute(attn_partial_kernel<D, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    configured = smem;
+  {
+    // opt in to > 48 KB dynamic smem: a per-DEVICE attribute, cached per device and instantiation (grow-only)
+    static size_t configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+      DD_CHECK_CUDA(cudaFuncSetAttribute(attn_partial_kernel<D, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+      if (dev >= 0 && dev < 64) configured[dev] = smem;
+    }
   }
   DD_LAUNCH_CHAIN(attn_partial_kernel<D, QT>, dim3(p.num_splits, p.H_kv, p.B), dim3(kAttnThreads), smem, st, tmap_k,
                   tmap_v, p);

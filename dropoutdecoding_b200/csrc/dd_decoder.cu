@@ -82,11 +82,11 @@ __global__ void rope_stage_kernel(const __nv_bfloat16* __restrict__ qkv, const f
 }
 
 __global__ void embed_gather_kernel(const uint4* __restrict__ embed, const int32_t* __restrict__ token, int M,
-                                    int dvec, uint4* __restrict__ x) {
+                                    int dvec, int vocab, uint4* __restrict__ x) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x;  // b*M + m
-  const int t = token[row / M];
+  const int t = min(max(token[row / M], 0), vocab - 1);   // a caller-supplied id never indexes outside the table
   for (int j = threadIdx.x; j < dvec; j += blockDim.x) x[(size_t)row * dvec + j] = embed[(size_t)t * dvec + j];
 }
 
@@ -127,7 +127,7 @@ __global__ void commit_winner_kernel(const uint4* __restrict__ k_new, const uint
   pdl_wait();
   const int l = blockIdx.x, b = blockIdx.y;
   const int w = winner[b], pos = seq_lens[b];
-  if (pos >= S_max || w < 0) return;  // w < 0: this sequence commits from another staging buffer
+  if (pos >= S_max || w < 0 || w >= M) return;  // w < 0: this sequence commits from another staging buffer
   const size_t src = (((size_t)l * B + b) * M + w) * H_kv * dvec;
   for (int idx = threadIdx.x; idx < H_kv * dvec; idx += blockDim.x) {
     const int h = idx / dvec, j = idx % dvec;
@@ -162,14 +162,15 @@ extern "C" int dd_rope_stage(const void* qkv, const float* cos_tab, const float*
   return DD_OK;
 }
 
-extern "C" int dd_embed_gather(const void* embed, const int32_t* token, int B, int M, int d, void* x,
+extern "C" int dd_embed_gather(const void* embed, const int32_t* token, int B, int M, int d, int vocab, void* x,
                                dd_stream_t stream) {
   using namespace dd;
   DD_CHECK_ARG(embed && token && x, "dd_embed_gather: null pointer");
   DD_CHECK_ARG(d % 8 == 0, "dd_embed_gather: d=%d must be a multiple of 8", d);
+  DD_CHECK_ARG(vocab >= 1, "dd_embed_gather: vocab=%d", vocab);
   if (B * M == 0) return DD_OK;
   DD_LAUNCH_CHAIN(embed_gather_kernel, dim3(B * M), dim3(128), 0, (cudaStream_t)stream, (const uint4*)embed, token,
-                  M, d / 8, (uint4*)x);
+                  M, d / 8, vocab, (uint4*)x);
   return DD_OK;
 }
 

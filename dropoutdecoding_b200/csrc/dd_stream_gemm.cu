@@ -373,17 +373,21 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         if (owner == rank) continue;
         const int lc = c - owner * n_chunks / p.S;
         const int src = rank < owner ? rank : rank - 1;
+        if (a * SG_BM + q * 32 >= p.M) continue;                   // (warp-uniform) no token row in this warp
         float v[16];
         tmem_ld16(t0 + c * 16, v);
         const uint32_t dst = mapa_cluster(ring + (uint32_t)(((src * p.max_own + lc) * 16 * rows + row) * 4), (uint32_t)owner);
+        if (row < p.M) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) st_cluster_f32(dst + e * rows * 4, v[e]);
+          for (int e = 0; e < 16; ++e) st_cluster_f32(dst + e * rows * 4, v[e]);
+        }
       }
     }
     cluster_sync_all();     // #2: the peers' partials of my chunks have landed in my shared memory
     if (epi) {
       const int own_b = rank * n_chunks / p.S, own_e = (rank + 1) * n_chunks / p.S;
       for (int c = own_b + c0; c < own_e; c += cstep) {
+        if (a * SG_BM + q * 32 >= p.M) break;                      // (warp-uniform) no token row in this warp
         const int lc = c - own_b;
         float acc[16];
         for (int r = 0; r < p.S; ++r) {                            // rank order, whoever sums

@@ -94,6 +94,8 @@ struct UncParams {
   int n_chunks;            // row chunks of kMaxMT*128 rows per image (> 1 when n_vis > 640)
   float* colpart;          // [img][chunk][n_strips*BN]   column sums of p over one row chunk (COLSUM -> logpavg)
   float* logpavg;          // [img][n_strips*BN]          log(p_avg + eps)                    (CROSS input)
+  int32_t* overflow;       // [1] rows whose top-k candidate list overflowed (ties at the threshold): the ids of such a
+                           //     row may miss a tied candidate, so the host treats a non-zero count as an error
 };
 
 // Rare path of sweep 2 (whole warp, warp-uniform call): some row of this warp has a top-k candidate inside the
@@ -505,6 +507,7 @@ __global__ void __launch_bounds__(kFinWarps * 32)
 stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats, float* __restrict__ tau) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kFinWarps + (threadIdx.x >> 5), img = blockIdx.y;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.overflow = 0;
   if (row >= p.n_vis) return;  // warp-uniform
   float m = -INFINITY;
   for (int q = lane; q < p.parts; q += 32)
@@ -569,6 +572,7 @@ fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restr
   const size_t r = (size_t)img * p.n_vis + row;
   {  // top-k ids from the candidate list: k selection rounds, value descending, id ascending on ties
     const int n = min(p.cand_cnt[r], p.cap);
+    if (lane == 0 && p.cand_cnt[r] > p.cap) atomicAdd(p.overflow, 1);
     const float* cv = p.cand_val + r * p.cap;
     const int32_t* ci = p.cand_idx + r * p.cap;
     float pv = INFINITY;
@@ -624,7 +628,7 @@ static int num_sms() {
 struct UncLayout {
   int n_strips, parts, n_chunks;
   int cap;
-  size_t off_stats, off_smax, off_tau, off_ccnt, off_cval, off_cidx, off_rowstats, off_acq, off_colpart, off_logpavg, total;
+  size_t off_stats, off_smax, off_tau, off_ccnt, off_cval, off_cidx, off_rowstats, off_acq, off_colpart, off_logpavg, off_ovf, total;
 };
 static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   UncLayout L;
@@ -655,6 +659,7 @@ static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   const size_t vp = (size_t)L.n_strips * BN;
   L.off_colpart = o; o = align_up(o + (L.n_chunks > 1 ? (size_t)n_images * L.n_chunks * vp * sizeof(float) : 0), 256);
   L.off_logpavg = o; o = align_up(o + (L.n_chunks > 1 ? (size_t)n_images * vp * sizeof(float) : 0), 256);
+  L.off_ovf = o; o = align_up(o + sizeof(int32_t), 256);
   L.total = o;
   return L;
 }
@@ -692,6 +697,11 @@ static int launch_unc_any(int num_mt, const CUtensorMap& ta, const CUtensorMap& 
 extern "C" size_t dd_uncertainty_workspace_bytes(int n_images, int n_vis, int vocab, int topk) {
   if (n_images <= 0 || n_vis <= 0 || vocab <= 0 || topk <= 0) return 0;
   return dd::unc_layout(n_images, n_vis, vocab, topk).total;
+}
+
+extern "C" size_t dd_uncertainty_overflow_offset(int n_images, int n_vis, int vocab, int topk) {
+  if (n_images <= 0 || n_vis <= 0 || vocab <= 0 || topk <= 0) return 0;
+  return dd::unc_layout(n_images, n_vis, vocab, topk).off_ovf;
 }
 
 extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n_images, int n_vis, int d,
@@ -745,6 +755,7 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
   float* row_stats = reinterpret_cast<float*>(ws + L.off_rowstats);
   p.row_stats = row_stats;
   p.part_acq = reinterpret_cast<float*>(ws + L.off_acq);
+  p.overflow = reinterpret_cast<int32_t*>(ws + L.off_ovf);
   cudaStream_t st = (cudaStream_t)stream;
   const int num_mt = L.n_chunks > 1 ? kMaxMT : ceil_div(n_vis, BM);
   const dim3 fgrid(ceil_div(n_vis, kFinWarps), n_images);

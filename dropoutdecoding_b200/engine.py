@@ -14,9 +14,9 @@ single shared cache, with no host sync at all, replayed as one CUDA graph:
     vote / mean             member argmax ids, winner, next token                 (dd_aggregate)
     commit                  winner's staged K/V rows -> cache row seq_len, seq_len += 1
 
-Weight GEMMs: <= 16 rows dd_skinny_gemm (mma.sync weight stream), 17..32 rows dd_stream_gemm (tcgen05,
-stream-K), above that library GEMMs unless gemm_backend="stream" (dd_stream_gemm up to 256 rows); the
-prompt prefill, which is not part of the hot path, uses library ops.  All tensors are bf16 with fp32 accumulation; rounding points follow the HF
+Weight GEMMs: <= 16 rows dd_skinny_gemm (mma.sync weight stream), 17..256 rows dd_stream_gemm (tcgen05 / TMEM / TMA,
+one-wave tiles, cluster split-K); only passes of more than 256 rows (none of the BASELINE configurations) and the
+prompt prefill, which is not part of the hot path, use library GEMMs.  All tensors are bf16 with fp32 accumulation; rounding points follow the HF
 Llama decoder so that the CPU oracle's 'bf16-faithful' mode is comparable token for token.
 """
 from __future__ import annotations
@@ -164,9 +164,11 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         self._prefill_graphs: dict = {}
         # Weight GEMMs by row count (rows = sequences x members of a pass); measured on B200 (profiles/README.md 4):
         #   rows <= 16        dd_skinny_gemm / dd_decoder_linear (mma.sync, RoPE fused into the QKV epilogue)
-        #   16 < rows <= 32   dd_stream_gemm (tcgen05, stream-K) -- 1.4-1.6x faster than the skinny kernel there
-        #   rows > 32         library GEMM by default; DD_GEMM=stream (gemm_backend="stream") runs dd_stream_gemm for every
-        #                     pass of up to 256 rows: fully native, currently 15-45 % behind cuBLAS at 64-192 rows
+        #   16 < rows <= 256  dd_stream_gemm (tcgen05; profiles/r02/stream_gemm_v4.jsonl: 0.85-1.0x cuBLAS up to 128 rows,
+        #                     0.5-0.9x at 192-256 rows where the GEMM sits on the HBM / tensor ridge)
+        #   rows > 256        library GEMM
+        #   DD_GEMM=library (gemm_backend="library") sends every pass of more than 32 rows to the library instead;
+        #   DD_GEMM=stream forces dd_stream_gemm for every pass of up to 256 rows (also <= 16 rows)
         self.gemm_backend = gemm_backend or os.environ.get("DD_GEMM", "auto")
         if self.gemm_backend not in ("auto", "stream", "library", "skinny"):
             raise ValueError(self.gemm_backend)
@@ -204,6 +206,7 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         self.alea = torch.zeros_like(self.epi)
         self.var = torch.zeros_like(self.epi)
         self.topk_ids = torch.zeros(B, n_vis, topk, **i32)
+        self._unc_overflow = torch.zeros(1, **i32)      # rows whose top-k candidate list overflowed in stage (1)
         cos, sin = rope_table(D, cfg.rope_theta, max_seq + 1)
         self.cos, self.sin = cos.to(dev), sin.to(dev)
         self.scale = 1.0 / math.sqrt(D)
@@ -256,6 +259,8 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         if self.gemm_backend == "stream":
             return rows <= 256
         if self.gemm_backend == "auto":
+            return 16 < rows <= 256
+        if self.gemm_backend == "library":
             return 16 < rows <= 32
         return False
 
@@ -614,9 +619,10 @@ class DropoutDecodeEngine(SpeculativeSchedules):
 
     def uncertainty_stage(self, vis_hidden: torch.Tensor) -> None:
         """vis_hidden bf16 [B, n_vis, d] (final-norm hidden states of the visual rows)."""
-        e, a, v, ids = ops.uncertainty_project(vis_hidden.contiguous(), self.w.lm_head, topk=self.topk,
-                                               round_logits=self.round_logits)
+        e, a, v, ids, ovf = ops.uncertainty_project(vis_hidden.contiguous(), self.w.lm_head, topk=self.topk,
+                                                    round_logits=self.round_logits, return_overflow=True)
         self.epi.copy_(e); self.alea.copy_(a); self.var.copy_(v); self.topk_ids.copy_(ids)
+        self._unc_overflow.copy_(ovf)      # checked at the next host synchronisation (generated())
 
     def first_token(self, last_hidden: torch.Tensor) -> None:
         """The first generated token is the plain argmax of the unmasked prefill
@@ -676,5 +682,8 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         return t[:, 0].tolist(), t[:, 1].tolist(), t[:, 2].tolist()
 
     def generated(self) -> torch.Tensor:
-        """Tokens generated so far, int32 [B, n]."""
-        return self.tokens_out[:, :int(self.step_ctr.item()) + 1]
+        """Tokens generated so far, int32 [B, n].  (A host synchronisation point: also where an overflow of the
+        uncertainty stage's candidate lists surfaces as an error.)"""
+        n = int(self.step_ctr.item()) + 1
+        ops.raise_on_overflow(self._unc_overflow)
+        return self.tokens_out[:, :n]

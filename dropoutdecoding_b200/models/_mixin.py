@@ -5,6 +5,8 @@ where the decoder / vision features live and which flavour of the algorithm the 
 (top-k size, mask mode, vote target)."""
 from __future__ import annotations
 
+import os
+import warnings
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -14,9 +16,36 @@ from .. import ops
 from ..engine import DecoderConfig, DecoderWeights, DropoutDecodeEngine
 from .config import settings
 
+def resolve_device_map(device_map) -> Optional[torch.device]:
+    """The reference drivers load with `device_map="auto"` (accelerate's layer placement over all visible GPUs,
+    chair_test/chair_test.py:189-213).  This engine keeps one whole model per GPU (one process per GPU), so every form
+    that names ONE device is honoured, "auto" / "balanced" / "sequential" / "cuda" mean this process's GPU
+    (LOCAL_RANK, default 0), and a map that spreads modules over several devices is refused."""
+    if device_map is None:
+        return None
+    if isinstance(device_map, torch.device):
+        return device_map
+    if isinstance(device_map, int):
+        return torch.device(f"cuda:{device_map}")
+    if isinstance(device_map, str):
+        if device_map in ("auto", "balanced", "balanced_low_0", "sequential", "cuda"):
+            return torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}")
+        return torch.device(device_map)
+    if isinstance(device_map, dict):
+        devs = {torch.device(f"cuda:{v}") if isinstance(v, int) else torch.device(v) for v in device_map.values()}
+        if len(devs) == 1:
+            return devs.pop()
+        raise ValueError(f"device_map places the model on {len(devs)} devices {sorted(map(str, devs))}: Dropout Decoding "
+                         f"keeps the whole model on one GPU (shard sequences or ensemble members over GPUs with "
+                         f"dropoutdecoding_b200.distributed instead)")
+    raise ValueError(f"unsupported device_map {device_map!r}")
+
+
 def decoder_weights_from_hf(lm, lm_head, device) -> DecoderWeights:
     """Fuse q|k|v and gate|up of an HF Llama/Mistral decoder into single weight streams.  The HF
-    parameters are re-pointed at views of the fused tensors, so no weight exists twice."""
+    parameters are re-pointed at views of the fused tensors, so no weight exists twice.  (The caller has made
+    the whole model bf16 first -- DropoutDecodingMixin.decoder_weights -- so the aliased parameters keep the
+    dtype of their neighbours.)"""
     c = lm.config
     D = getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads
     rope_theta = getattr(c, "rope_theta", None)
@@ -107,8 +136,28 @@ class DropoutDecodingMixin:
             if dev.type != "cuda":
                 raise ops.DropDecError("Dropout Decoding runs on a CUDA device only (no CPU path): move the "
                                        "model to cuda first")
+            if self._head().weight.dtype != torch.bfloat16:
+                # chair_test / pope_test load with torch_dtype=torch.float16 (chair_test/chair_test.py:189-213).  The
+                # engine computes in bf16 (fp32 accumulation); the WHOLE model is converted once, so that the HF
+                # modules the wrapper still calls (vision tower, projector, text-only fallbacks) and the fused decoder
+                # weights agree on one dtype.  fp16 -> bf16 drops 3 mantissa bits of every weight.
+                warnings.warn(f"Dropout Decoding runs in bfloat16: converting the model from "
+                              f"{self._head().weight.dtype} to torch.bfloat16 (weights are rounded once)", stacklevel=3)
+                self.to(torch.bfloat16)
             self._weights = decoder_weights_from_hf(self._lm(), self._head(), dev)
         return self._weights
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *model_args, device_map=None, **kwargs):
+        """`Custom*.from_pretrained(path, torch_dtype=torch.float16, device_map="auto")` of the reference drivers
+        (chair_test/chair_test.py:185-214, pope_test/pope_test.py:180-197): torch_dtype is passed through (fp16 / fp32
+        checkpoints are converted to bf16 at the first Dropout-Decoding call, with a warning), device_map is resolved
+        to ONE device (resolve_device_map) and the model is moved there."""
+        dev = resolve_device_map(device_map)
+        model = super().from_pretrained(pretrained_model_name_or_path, *model_args, **kwargs)
+        if dev is not None:
+            model = model.to(dev)
+        return model
 
     def _engine(self, batch: int, n_vis: int, max_seq: int, est_seq: int) -> DropoutDecodeEngine:
         probs = tuple(float(p) for p in settings['voting_numbers'])

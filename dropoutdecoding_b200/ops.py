@@ -14,6 +14,8 @@ import torch
 from . import _lib
 from ._lib import DropDecError, check
 
+check_rc = check
+
 MASK_CUMULATIVE, MASK_INDEPENDENT, MASK_QUANTILE = 0, 1, 2
 AGG_VOTE, AGG_MEAN = 0, 1
 EPI_NONE, EPI_RESIDUAL, EPI_F32, EPI_SWIGLU, EPI_ROPE = 0, 1, 2, 3, 4
@@ -44,8 +46,13 @@ def mask_words(n_vis: int) -> int:
 
 # --------------------------------------------------------------------------------------------
 def uncertainty_project(h_vis: torch.Tensor, w_lm: torch.Tensor, topk: int = 5, round_logits: bool = False,
-                        workspace: Optional[torch.Tensor] = None):
-    """h_vis bf16 [n_img, n_vis, d], w_lm bf16 [V, d] -> (epi, alea, var fp32 [n_img, n_vis], topk_ids int32)."""
+                        workspace: Optional[torch.Tensor] = None, check: bool = True, return_overflow: bool = False):
+    """h_vis bf16 [n_img, n_vis, d], w_lm bf16 [V, d] -> (epi, alea, var fp32 [n_img, n_vis], topk_ids int32).
+
+    A row whose top-k candidate list overflowed on the device (more logits tied at its threshold than the list holds)
+    is an error, never a silently shorter list: check=True reads the device counter (one stream synchronisation) and
+    raises; return_overflow=True appends the int32 [1] device counter to the result instead, for callers that check
+    it at their next synchronisation point (the decode engine)."""
     L = _lib.load()
     _need(h_vis, torch.bfloat16, "h_vis"); _need(w_lm, torch.bfloat16, "w_lm")
     if h_vis.dim() == 2:
@@ -61,11 +68,24 @@ def uncertainty_project(h_vis: torch.Tensor, w_lm: torch.Tensor, topk: int = 5, 
     need = L.dd_uncertainty_workspace_bytes(n_img, n_vis, V, topk)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
-    check(L.dd_uncertainty_project(_ptr(h_vis), _ptr(w_lm), n_img, n_vis, d, V, topk, int(round_logits),
-                                   _ptr(epi), _ptr(alea), _ptr(var), _ptr(ids), _ptr(workspace),
-                                   workspace.numel() * workspace.element_size(), _stream()),
-          "dd_uncertainty_project")
+    check_rc(L.dd_uncertainty_project(_ptr(h_vis), _ptr(w_lm), n_img, n_vis, d, V, topk, int(round_logits),
+                                      _ptr(epi), _ptr(alea), _ptr(var), _ptr(ids), _ptr(workspace),
+                                      workspace.numel() * workspace.element_size(), _stream()),
+             "dd_uncertainty_project")
+    off = L.dd_uncertainty_overflow_offset(n_img, n_vis, V, topk)
+    overflow = workspace[off:off + 4].view(torch.int32)
+    if return_overflow:
+        return epi, alea, var, ids, overflow
+    if check:
+        raise_on_overflow(overflow)
     return epi, alea, var, ids
+
+
+def raise_on_overflow(overflow: torch.Tensor) -> None:
+    n = int(overflow.item())
+    if n:
+        raise DropDecError(f"dd_uncertainty_project: the top-k candidate list of {n} visual row(s) overflowed "
+                           f"(DD_ERR_OVERFLOW): too many logits tied at the k-th largest value")
 
 
 def sample_masks(epi: torch.Tensor, topk_ids: Optional[torch.Tensor], y_init: Optional[torch.Tensor],
@@ -314,7 +334,7 @@ def rope_stage(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_lens
 def embed_gather(embed: torch.Tensor, token: torch.Tensor, M: int, out: torch.Tensor) -> torch.Tensor:
     L = _lib.load()
     _need(embed, torch.bfloat16, "embed"); _need(token, torch.int32, "token")
-    check(L.dd_embed_gather(_ptr(embed), _ptr(token), token.shape[0], M, embed.shape[1], _ptr(out), _stream()),
+    check(L.dd_embed_gather(_ptr(embed), _ptr(token), token.shape[0], M, embed.shape[1], embed.shape[0], _ptr(out), _stream()),
           "dd_embed_gather")
     return out
 

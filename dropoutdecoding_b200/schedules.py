@@ -105,6 +105,7 @@ class SpeculativeSchedules:
             self.need_fb = torch.zeros(1, **i32)
             self.need_fb_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             self.tok_host = torch.zeros(B, dtype=torch.int32).pin_memory()     # input token of the pass (EOS check)
+            self.tok2_host = torch.zeros(B, dtype=torch.int32).pin_memory()    # token a lookahead pass committed (EOS check)
         # ---- lookahead inside the fallback pass (one sequence, see _spec_chain): 2K+1 contexts
         la = os.environ.get("DD_LOOKAHEAD", "1") == "1"
         self.lookahead = bool(la and fits and self.speculative != "off" and keep_relevant and 2 * self.K + 1 <= 16)
@@ -228,6 +229,7 @@ class SpeculativeSchedules:
         ops.commit_winner(pd.k_new, pd.v_new, self.winner, self.seq_lens, self.k_cache, self.v_cache)
         ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
         self.cur_token.copy_(self.next_token)
+        self.tok2_host.copy_(self.next_token, non_blocking=True)   # step t's result: the host must not chain past an EOS
         ok = (self.next_token == self._g_tok) & (self.winner == self._g_win)
         # ---- step t+1 as _spec_head would see it (only meaningful when the guess was right)
         ops.aggregate(pd.logits, "vote", member_ids=self._ids_d, winner=self._win_d, token=self._tok_d, vocab=V,
@@ -492,6 +494,11 @@ class SpeculativeSchedules:
         i, src, need_fb = 0, None, False        # src: which pass already served as step i's speculative pass
         while i < n_steps:
             if not self.spec_active:            # the adaptive switch fired: the reference's own order
+                if stop_token is not None:      # (one synchronisation per token in this mode, like every other pass)
+                    self.tok_host.copy_(self.cur_token, non_blocking=True)
+                    sync()
+                    if int(self.tok_host[0]) == stop_token:
+                        return i
                 if graphs is not None:
                     if self._graph is None:
                         self.capture()
@@ -524,8 +531,10 @@ class SpeculativeSchedules:
                     sync()
                     self.n_chain += 1
                     self._last_src = "pd0"
-                    if stop_token is not None and int(self.tok_host[0]) == stop_token:
-                        return i + 1            # (EOS came out of the step before; this pass has committed one more)
+                    if stop_token is not None and stop_token in (int(self.tok_host[0]), int(self.tok2_host[0])):
+                        # EOS came out of the step before (this pass has committed one more), or out of the step this
+                        # pass completed: either way stop here -- the lookahead rows must not be finished past an EOS
+                        return i + 1
                     if int(self.chain_flags_host[0]):
                         self.n_chain_ok += 1
                         need_fb, src = bool(int(self.chain_flags_host[1])), "pd"

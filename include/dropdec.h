@@ -34,6 +34,7 @@ typedef void* dd_stream_t; /* cudaStream_t */
 #define DD_ERR_UNSUPPORTED (-2)
 #define DD_ERR_WORKSPACE (-3)
 #define DD_ERR_CUDA (-4)
+#define DD_ERR_OVERFLOW (-5) /* a bounded on-device list overflowed (dd_uncertainty_project candidate lists) */
 
 #define DD_MAX_MEMBERS 16  /* K, the number of masked ensemble members        */
 #define DD_MAX_TOPK 16     /* k of the per-visual-token top-k id table         */
@@ -69,8 +70,13 @@ const char* dd_last_error(void);
  * (models/llama.py:46-47).
  * Limits: d % 64 == 0, n_vis <= 8192 per image, topk <= DD_MAX_TOPK.  Images of up to 640 visual tokens
  * take two GEMM sweeps; larger ones (LLaVA-NeXT anyres) three, because p_avg then needs its own sweep.
+ * Top-k ids come from a per-row candidate list of bounded size; a row whose list overflows (more than
+ * 96*topk + 64 logits tied at or above its threshold) is counted in an int32 at byte offset
+ * dd_uncertainty_overflow_offset(...) of the workspace, valid once the stream has reached the end of the call.
+ * Callers must treat a non-zero count as an error (DD_ERR_OVERFLOW): the ids of such a row may miss a tied id.
  * ------------------------------------------------------------------------------------------ */
 size_t dd_uncertainty_workspace_bytes(int n_images, int n_vis, int vocab, int topk);
+size_t dd_uncertainty_overflow_offset(int n_images, int n_vis, int vocab, int topk);
 int dd_uncertainty_project(const void* h_vis /* bf16 [n_images, n_vis, d] */,
                            const void* w_lm /* bf16 [vocab, d] */, int n_images, int n_vis, int d,
                            int vocab, int topk, int round_logits_bf16,
@@ -268,7 +274,8 @@ int dd_rope_stage(const void* qkv, const float* cos_tab, const float* sin_tab, c
 
 /* x[b*M + m, :] = embed[token[b], :]  for m < M */
 int dd_embed_gather(const void* embed /* bf16 [V, d] */, const int32_t* token /* [B] */, int B, int M,
-                    int d, void* x /* bf16 [B*M, d] */, dd_stream_t stream);
+                    int d, int vocab /* rows of embed: ids are clamped to [0, vocab) */,
+                    void* x /* bf16 [B*M, d] */, dd_stream_t stream);
 
 /* End of one ensemble step (*step = ensemble steps done so far, 0-based):
  * tokens_out[b, *step + 1] = token[b]  (column 0 holds the un-ensembled first token,

@@ -134,3 +134,26 @@ def test_calculate_vision_uncertainty_helper_matches_oracle():
     a, b = m.calculate_vision_uncertainty(logits), oracle.calculate_vision_uncertainty(logits)
     for k in b:
         assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-7), k
+
+
+def test_device_map_and_dtype_of_the_reference_drivers_are_resolved_explicitly(tmp_path):
+    """chair_test/chair_test.py:185-214 loads `Custom*.from_pretrained(path, torch_dtype=torch.float16,
+    device_map="auto")`: device_map forms that name one device are honoured, maps over several devices are refused
+    loudly (no silent single-device fallback), torch_dtype is passed through to transformers."""
+    import bench
+    from dropoutdecoding_b200.models._mixin import resolve_device_map
+    from models.llava import CustomLlavaForConditionalGeneration       # the drop-in alias at the repo root
+    assert resolve_device_map(None) is None
+    assert resolve_device_map("auto") == torch.device("cuda:0") and resolve_device_map(1) == torch.device("cuda:1")
+    assert resolve_device_map({"": 0}) == torch.device("cuda:0") and resolve_device_map("cuda:3") == torch.device("cuda:3")
+    with pytest.raises(ValueError, match="2 devices"):
+        resolve_device_map({"model.vision_tower": 0, "model.language_model": 1})
+    with pytest.raises(ValueError):
+        resolve_device_map(3.5)
+    tiny = bench.build_llava15_7b("cpu", tiny=True)
+    tiny.save_pretrained(tmp_path)
+    m = CustomLlavaForConditionalGeneration.from_pretrained(tmp_path, torch_dtype=torch.float16)
+    assert m.lm_head.weight.dtype == torch.float16 and m.lm_head.weight.device.type == "cpu"
+    assert m.masked_numbers == [] and m.vision_uncert_dict is None          # state of models/llava.py:57-72 is there
+    with pytest.raises(Exception, match="CUDA"):                              # no CPU path: loud, not a fallback
+        m.decoder_weights()

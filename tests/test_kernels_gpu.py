@@ -521,3 +521,36 @@ def test_uncertainty_more_rows_than_tmem_holds(ops, cuda, n_img, n_vis, d, V, k)
         want_ids = torch.sort(topk_token_ids(logits[None], k)[1][0], -1).values
         got_ids = torch.sort(ids[i].cpu().long(), -1).values
         assert torch.equal(got_ids[safe], want_ids[safe])
+
+
+def test_uncertainty_candidate_overflow_is_an_error(ops, cuda):
+    """All-equal logits tie every vocabulary entry at the k-th largest value: the per-row candidate list cannot hold
+    them, and that is reported (DD_ERR_OVERFLOW through the workspace counter), never a silently truncated list."""
+    h = torch.zeros(1, 64, 128, dtype=torch.bfloat16, device=cuda)
+    w = torch.randn(4096, 128, generator=torch.Generator().manual_seed(0)).to(cuda).bfloat16()
+    with pytest.raises(ops.DropDecError, match="overflow"):
+        ops.uncertainty_project(h, w, topk=5, round_logits=True)
+    *_, ovf = ops.uncertainty_project(h, w, topk=5, round_logits=True, return_overflow=True)
+    assert int(ovf.item()) == 64
+    hr = torch.randn(1, 64, 128, generator=torch.Generator().manual_seed(1)).to(cuda).bfloat16()
+    *_, ovf = ops.uncertainty_project(hr, w, topk=5, round_logits=True, return_overflow=True)
+    assert int(ovf.item()) == 0
+
+
+def test_aggregate_of_nan_and_minus_inf_rows_yields_valid_ids(ops, cuda):
+    """torch.argmax treats NaN as the maximum and returns index 0 for a row of -inf; the kernel used to return its
+    0x7fffffff start value for such rows, which the next step's embedding gather would have read out of bounds."""
+    V = 1000
+    l = torch.randn(2, 3, V, generator=torch.Generator().manual_seed(3))
+    l[0, 0] = float("nan")
+    l[0, 1] = float("-inf")
+    l[1, 2, 17] = float("nan")
+    ids, winner, token, _ = ops.aggregate(l.to(cuda), "vote")
+    want = torch.argmax(l, dim=-1)
+    assert ids.cpu().tolist() == want.tolist()
+    assert bool((token >= 0).all()) and bool((token < V).all())
+    # an out-of-range id handed to the embedding gather is clamped, not dereferenced
+    emb = torch.arange(8 * 16, dtype=torch.float32).reshape(8, 16).to(cuda).bfloat16()
+    out = torch.empty(2, 16, dtype=torch.bfloat16, device=cuda)
+    ops.embed_gather(emb, torch.tensor([0x7fffffff, -5], dtype=torch.int32, device=cuda), 1, out)
+    assert torch.equal(out[0], emb[7]) and torch.equal(out[1], emb[0])

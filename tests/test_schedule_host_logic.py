@@ -19,7 +19,7 @@ class FakeEngine(SpeculativeSchedules):
     def __init__(self, fb, ok, tok, first=7, lookahead=True):
         self.fb, self.ok, self.tok, self.first = fb, ok, tok, first
         self.spec_active, self.lookahead, self.speculative = True, lookahead, "auto"
-        self.need_fb_host, self.chain_flags_host, self.tok_host = [0], [0, 0], [0]
+        self.need_fb_host, self.chain_flags_host, self.tok_host, self.tok2_host = [0], [0, 0], [0], [0]
         self.n_spec_steps = self.n_fallbacks = self.n_chain = self.n_chain_ok = 0
         self._spec_base = (0, 0)
         self.launch_count = self.launches_per_step = 0
@@ -37,6 +37,7 @@ class FakeEngine(SpeculativeSchedules):
             self.tok_host[0] = self._cur()
             t = self.done
             self.done += 1
+            self.tok2_host[0] = self.tok[t]          # the token the pass's own step produced
             nxt = self.fb[t + 1] if t + 1 < len(self.fb) else 0
             self.chain_flags_host[:] = [int(self.ok[t]), int(nxt)]
         else:
@@ -102,11 +103,22 @@ def test_eos_stops_within_one_pass():
     eng = FakeEngine(fb, [1] * 6, tok)
     done = eng._spec_steps(6, None, stop_token=2)
     assert done == eng.done == 3 and eng.log == ["head", "fin"] * 3 + ["head"]      # the 4th head only sees the EOS
-    # EOS out of a step that is followed by chained lookahead passes: one more token at most
+    # EOS out of the step a lookahead pass completes: the chain stops right there
     fb, tok = [1, 1, 1, 0, 0, 0], [2, 101, 102, 103, 104, 105]           # step 0 produces EOS inside a chain
     eng = FakeEngine(fb, [1] * 6, tok)
     done = eng._spec_steps(6, None, stop_token=2)
-    assert done == eng.done == 2 and eng.log == ["head", "chain", "chain"]
+    assert done == eng.done == 1 and eng.log == ["head", "chain"]
+    # ... also when the guess was confirmed and the following step needs no repeat (chain -> fin_chain): the lookahead
+    # rows are NOT finished past the EOS (round-1 bug: decoding ran on to max_new_tokens)
+    fb, tok = [1, 0, 0, 0, 0, 0], [2, 101, 102, 103, 104, 105]
+    eng = FakeEngine(fb, [1] * 6, tok)
+    done = eng._spec_steps(6, None, stop_token=2)
+    assert done == eng.done == 1 and eng.log == ["head", "chain"]
+    # EOS out of the step finished by fin_chain is seen by the next head
+    fb, tok = [1, 0, 0, 0, 0, 0], [100, 2, 102, 103, 104, 105]
+    eng = FakeEngine(fb, [1] * 6, tok)
+    done = eng._spec_steps(6, None, stop_token=2)
+    assert done == eng.done == 2 and eng.log == ["head", "chain", "fin_chain", "head"]
     # the call starts on EOS: nothing is decoded
     eng = FakeEngine([0, 0], [1, 1], [100, 101], first=2)
     assert eng._spec_steps(2, None, stop_token=2) == 0 and eng.done == 0 and eng.log == ["head"]

@@ -176,3 +176,33 @@ def test_instructblip_wrapper(cuda):
     n_new = out.shape[1] - 1                                   # a13 bookkeeping: one entry per generated token
     assert len(m.logits_mask_prob) == len(m.token_entropies) == len(m.token_ventropies) >= n_new >= 1
     assert all(0.0 < e < 15.0 for e in m.token_entropies)
+
+
+def test_reference_driver_call_sequence(cuda, tmp_path):
+    """The calls chair_test/chair_test.py makes (185-214: from_pretrained(path, torch_dtype=torch.float16,
+    device_map="auto"); 163-175: settings[...] = ...; 341-354: generate(**inputs, max_new_tokens, num_beams=1,
+    pad_token_id=eos) and slicing off the prompt) against the drop-in alias `models/` at the repo root.  The fp16
+    checkpoint is converted to bf16 as a whole (one warning), so the stock text-only path still works afterwards."""
+    import bench
+    from models.config import settings
+    from models.llava import CustomLlavaForConditionalGeneration
+    bench.build_llava15_7b("cpu", tiny=True).save_pretrained(tmp_path)
+    model = CustomLlavaForConditionalGeneration.from_pretrained(tmp_path, torch_dtype=torch.float16, device_map="auto")
+    assert model.lm_head.weight.device == cuda and model.lm_head.weight.dtype == torch.float16
+    old = dict(settings)
+    try:
+        settings['voting_numbers'] = [0.5, 0.3]           # --voting-numbers 2 (chair_test/chair_test.py:167-168)
+        settings['use_avg'] = False
+        ids, px = _inputs(1)
+        inputs = {"input_ids": ids.to(cuda), "attention_mask": torch.ones_like(ids).to(cuda), "pixel_values": px.to(cuda).half()}
+        with pytest.warns(UserWarning, match="bfloat16"):
+            out = model.generate(**inputs, max_new_tokens=10, num_beams=1, pad_token_id=2)
+        new = out[0][inputs["input_ids"].shape[1]:]      # chair_test.py:348-354 decodes only the new tokens
+        assert out.shape[0] == 1 and 1 <= new.numel() <= 10
+        assert len(model.masked_numbers) == 2
+        assert {p.dtype for p in model.parameters()} == {torch.bfloat16}            # one dtype everywhere
+        # the stock HF path (no pixel_values) still runs on the converted model
+        txt = model.generate(input_ids=ids.to(cuda)[:, :5], max_new_tokens=3, do_sample=False, pad_token_id=2)
+        assert txt.shape == (1, 8)
+    finally:
+        settings.clear(); settings.update(old)

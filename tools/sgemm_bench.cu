@@ -193,9 +193,36 @@ int main(int argc, char** argv) {
         CK(cudaGraphDestroy(g));
         return best * 1e3f / (nrot * passes);  // us per launch
       };
+#ifdef DD_SG_EXPERIMENT
+      uint8_t* wsr;
+      CK(cudaMalloc(&wsr, wsb * nrot));
+      CK(cudaMemsetAsync(wsr, 0, wsb * nrot, st));
+#endif
       const float us = time_graph([&](const __nv_bfloat16* wr) {
-        if (dd_stream_gemm(x, wr, res, M, sh.N, sh.K, sh.epi, y, ws, wsb, st)) { fprintf(stderr, "%s\n", dd_last_error()); exit(1); }
+        void* wsl = ws;
+#ifdef DD_SG_EXPERIMENT
+        wsl = wsr + (size_t)((wr - w) / ((size_t)w_rows * sh.K)) * wsb;
+#endif
+        if (dd_stream_gemm(x, wr, res, M, sh.N, sh.K, sh.epi, y, wsl, wsb, st)) { fprintf(stderr, "%s\n", dd_last_error()); exit(1); }
       });
+#ifdef DD_SG_EXPERIMENT
+      if (getenv("DD_SG_DBG")) {   // consecutive launches of the last pass: entry / done stamps -> kernel time and gap
+        const int G = dd_stream_gemm_debug_ctas(M, sh.N, sh.K, sh.epi);
+        std::vector<long long> h((size_t)G * 8);
+        long long prev_done = 0, first_entry0 = 0;
+        printf("%s M=%d launch-to-launch (us):", sh.name, M);
+        for (int r = 0; r < nrot; ++r) {
+          CK(cudaMemcpy(h.data(), wsr + (size_t)r * wsb, (size_t)G * 64, cudaMemcpyDeviceToHost));
+          long long e0 = h[6], e1 = h[6], d1 = h[7], m1 = h[5];
+          for (int c = 0; c < G; ++c) { e0 = std::min(e0, h[c * 8 + 6]); e1 = std::max(e1, h[c * 8 + 6]); d1 = std::max(d1, h[c * 8 + 7]); m1 = std::max(m1, h[c * 8 + 5]); }
+          if (r == 0) first_entry0 = e0;
+          printf("  [gap %.1f | entry-spread %.1f | mma %.1f | dur %.1f]", r ? (e0 - prev_done) * 1e-3 : 0.0, (e1 - e0) * 1e-3, (m1 - e0) * 1e-3, (d1 - e0) * 1e-3);
+          prev_done = d1;
+        }
+        printf("  total %.1f per launch\n", (prev_done - first_entry0) * 1e-3 / nrot);
+      }
+      CK(cudaFree(wsr));
+#endif
 #ifdef DD_SG_EXPERIMENT
       if (getenv("DD_SG_DBG")) dump_timeline(ws, wsb, dd_stream_gemm_debug_ctas(M, sh.N, sh.K, sh.epi), sh.name, M);
 #endif
