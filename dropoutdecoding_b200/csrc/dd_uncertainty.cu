@@ -11,28 +11,30 @@
 //   That is what makes the epistemic term single-sweep: it needs p_avg[v] = mean_i p[i,v], a
 //   column reduction over every row of the image, before sum_v p[i,v] log(p_avg[v]) can be formed.
 //
-//   warp 4   : TMA producer.  Per k-block (64 bf16 = one 128B-swizzle row) it loads the W strip tile
-//              [96 x 64] (HBM stream) and the activation tile of the LAST row tile into a 3-stage ring.
-//   warps 6-9: cp.async loaders for the other (up to 4) activation tiles [128 x 64] per k-block, written
-//              in the SWIZZLE_128B layout by hand (16-byte chunk c of row r -> chunk c ^ (r & 7)).
-//              Measured on B200 (tools/umma_probe.cu, profiles/r01): one SM ingests 35 B/clk through TMA
-//              boxes of this shape but 57-65 B/clk through cp.async, and this kernel needs 81 B/clk to
-//              keep the tensor core busy -- so the L2-resident activations use both paths at once.
-//   warp 5   : MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128 N=96 K=16,
+//   warps 8-10: TMA producers.  Per k-block (64 bf16 = one 128B-swizzle row) the CTA ingests the W strip tile
+//              [96 x 64] (HBM stream, 4-deep ring) and NUM_MT activation tiles [128 x 64] (L2-resident, 2 k-blocks
+//              deep): 92 KB per k-block, 82 B/clk at the rate the tensor core consumes them.  Round 1 fed four of the
+//              five activation tiles through cp.async because "an SM ingests 35 B/clk through TMA"; that ceiling was
+//              the issue loop of ONE producer thread (a barrier wait + a copy per box: ~350-670 cycles each,
+//              tools/tma_probe2.cu) -- three producer warps with two boxes each per k-block keep the ring full
+//              (measured: 97-126 B/clk per SM from four issuing warps).  Every ring slot belongs to one warp.
+//   warp 11  : MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128 N=96 K=16,
 //              both operands K-major SWIZZLE_128B; slots are released with tcgen05.commit.
-//   warps 0-3: epilogue.  tcgen05.ld 32x32b: one thread = one visual row, so softmax statistics are
-//              thread-local; the column sums are a butterfly over the warp plus 4 smem rows.
+//   warps 0-7: epilogue, two warps per TMEM lane quarter: warp w reads lanes 32*(w&3).. and the 48 columns
+//              [48*(w>>2), +48) of the strip.  tcgen05.ld 32x32b: one thread = one visual row, so softmax
+//              statistics are thread-local; the column sums are a butterfly over the warp plus 4 smem rows.  The two
+//              halves never talk to each other: every per-row partial simply exists once per (CTA, half).
 //
 // Two sweeps of the same pipeline (the row normaliser Z_i must be complete before p exists):
-//   STATS : per row running max / sum-exp, and the row's maximum inside every strip       (sweep 1)
+//   STATS : per row running max / sum-exp, and the row's maximum inside every half strip  (sweep 1)
 //   FUSED : p = exp(l - m)/Z;  A_i = sum p log(p+eps), Q_i = sum (p-1/V)^2, column sums ->
 //           log(p_avg+eps) -> C_i = sum p log(p_avg+eps)                        (sweep 2)
 //   finalize: alea = -A, epi = A - C, var = Q/(V-1).
-// Top-k ids without per-thread sorted lists in the hot loop: tau_i = the k-th largest of row i's per-strip
+// Top-k ids without per-thread sorted lists in the hot loop: tau_i = the k-th largest of row i's per-half-strip
 // maxima is a lower bound of its k-th largest logit, so sweep 2 (which recomputes bit-identical logits)
 // only has to append the few elements >= tau_i to a per-row candidate list (one predictable compare per
 // element); the finalize kernel sorts the candidates (value descending, id ascending).  Without ties at
-// most 96*k elements can pass the threshold; the list holds 96*k + 64.
+// most 48*k elements can pass the threshold; the list holds 96*k + 64 and an overflow is reported.
 // Algorithmic FLOPs = 2*n_vis*d*V per image, counted once although two sweeps run.
 #include <cuda.h>
 
@@ -44,24 +46,28 @@
 namespace dd {
 
 constexpr int BM = 128, BN = 96, BK = 64, UMMA_K = 16;
+constexpr int BNH = BN / 2;              // columns per epilogue half
 constexpr int kSlotBytes = BM * BK * 2;  // 16 KB: one [128 x 64] bf16 activation tile
 constexpr int kWBytes = BN * BK * 2;     // 12 KB: one [96 x 64] bf16 W tile
-constexpr int kCpTiles = 4;              // row tiles 0..3 of a k-block arrive through cp.async, the rest through TMA
-constexpr int kCpSlots = 8;              // cp.async ring (16 KB slots): two k-blocks deep
-constexpr int kTmaStages = 3;            // TMA ring: stage = W tile + one activation tile
-constexpr int kTmaStageBytes = kWBytes + kSlotBytes;
-constexpr int kCpThreads = 128;
-constexpr int kEpiThreads = 128;
-constexpr int kUncThreads = 192 + kCpThreads;
-constexpr int kNumBars = 2 * kCpSlots + 2 * kTmaStages + 1 + 5;
+constexpr int kMaxMT = 5;                // row tiles of 128 per image (n_vis <= 640)
+constexpr int kActStages = 2;            // activation ring: k-blocks in flight
+constexpr int kWStages = 4;              // W ring
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kHalfThreads = kEpiThreads / 2;
+constexpr int kProdWarp0 = kEpiWarps, kProdWarps = 3;
+constexpr int kMmaWarp = kProdWarp0 + kProdWarps;
+constexpr int kUncThreads = (kMmaWarp + 1) * 32;
+// barriers: act_full[kActStages] | act_empty[kActStages][kMaxMT] | w_full[kWStages] | w_empty[kWStages] | tmem_full |
+//           tmem_empty[kMaxMT]
+constexpr int kNumBars = kActStages + kActStages * kMaxMT + 2 * kWStages + 1 + kMaxMT;
 constexpr int kTmemCols = 512;
-constexpr int kMaxMT = 5;  // row tiles of 128 per image (n_vis <= 640)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kEps = 1e-10f;  // models/llava.py:735,739
 
 constexpr uint32_t kIdesc = make_idesc_bf16(BM, BN);
 
-// The epilogue warps are alone on their scheduler (one warp per sub-partition), so the softmax sweeps are bound by
+// The epilogue warps are alone on their scheduler (two warps per sub-partition), so the softmax sweeps are bound by
 // instructions issued per element.  exp2f / __logf carry a range fix-up for denormal results / arguments (4 extra
 // instructions each); here 2^x below 2^-126 may flush to zero (a probability < 1e-38) and the log argument is
 // >= 1e-10, so the bare MUFU forms are exact enough and identical in both sweeps.
@@ -75,22 +81,24 @@ __device__ __forceinline__ float ln_ftz(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y * 0.6931471805599453f;
 }
-
+__device__ __forceinline__ void half_bar_sync(int half) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(kHalfThreads) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 struct UncParams {
   int n_images, n_vis, d, vocab, topk, round_bf16;
-  int n_strips, parts;     // strips per image; CTAs (partials) per image
-  float* part_stats;       // [img][parts][n_vis][2]      (m, z)
-  float* strip_max;        // [img][n_strips][n_vis]      STATS output: row maximum inside each strip
+  int n_strips, parts;     // strips per image; CTAs per image.  Per-row partials exist per (CTA, half): 2*parts;
+                           // strip maxima per half strip: 2*n_strips
+  float* part_stats;       // [img][2*parts][n_vis][2]    (m, z)
+  float* strip_max;        // [img][2*n_strips][n_vis]    STATS output: row maximum inside each half strip
   const float* tau;        // [img][n_vis]                candidate threshold (FUSED / COLSUM input)
   int32_t* cand_cnt;       // [img][n_vis]
   float* cand_val;         // [img][n_vis][cap]
   int32_t* cand_idx;       // [img][n_vis][cap]
   int cap;
   const float* row_stats;  // [img][n_vis][2]             (m, 1/Z)  FUSED input
-  float* part_acq;         // [img][parts][n_vis][3]      (A, Q, C) FUSED output
-  const __nv_bfloat16* h_vis;  // [img][n_vis][d] (cp.async path of the activation tiles)
+  float* part_acq;         // [img][2*parts][n_vis][3]    (A, Q, C) FUSED output
   int n_chunks;            // row chunks of kMaxMT*128 rows per image (> 1 when n_vis > 640)
   float* colpart;          // [img][chunk][n_strips*BN]   column sums of p over one row chunk (COLSUM -> logpavg)
   float* logpavg;          // [img][n_strips*BN]          log(p_avg + eps)                    (CROSS input)
@@ -99,7 +107,7 @@ struct UncParams {
 };
 
 // Rare path of sweep 2 (whole warp, warp-uniform call): some row of this warp has a top-k candidate inside the
-// 32 columns at `taddr`.  Re-reads them from TMEM 8 at a time and appends every logit >= the row's threshold.
+// 16 columns at `taddr`.  Re-reads them from TMEM 8 at a time and appends every logit >= the row's threshold.
 struct CandSink {
   int32_t* cnt;
   float* val;
@@ -108,7 +116,7 @@ struct CandSink {
 };
 __device__ __noinline__ void append_candidates(const CandSink p, uint32_t taddr, float tau, int col_base, size_t r) {
 #pragma unroll 1
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 2; ++j) {
     float v[8];
     tmem_ld8(taddr + j * 8, v);
 #pragma unroll
@@ -138,11 +146,8 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles (the dynamic smem base is only 16-byte aligned by contract)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int NCP = NUM_MT < kCpTiles ? NUM_MT : kCpTiles;  // row tiles per k-block through cp.async
-  constexpr bool kTmaA = NUM_MT > NCP;                          // the last row tile rides with the W tile
-  uint8_t* tma_ring_p = smem + kCpSlots * kSlotBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tma_ring_p + kTmaStages * kTmaStageBytes);
-  // bars: cp_full[kCpSlots] | cp_empty[kCpSlots] | tma_full[kTmaStages] | tma_empty[kTmaStages] | tmem_full | tmem_empty[5]
+  uint8_t* w_ring_p = smem + kActStages * kMaxMT * kSlotBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring_p + kWStages * kWBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   float* s_col = reinterpret_cast<float*>(tmem_slot + 4);  // [4][BN]
   float* s_logp = s_col + 4 * BN;                            // [BN]
@@ -155,25 +160,27 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int strip_end = min(p.n_strips, strip_beg + spc);
   const int num_kb = p.d / BK;
 
-  const uint32_t cp_ring = smem_u32(smem), tma_ring = smem_u32(tma_ring_p);
-  const uint32_t bar_cpfull = smem_u32(bars), bar_cpempty = bar_cpfull + 8 * kCpSlots;
-  const uint32_t bar_full = bar_cpempty + 8 * kCpSlots, bar_empty = bar_full + 8 * kTmaStages;
-  const uint32_t bar_tfull = bar_empty + 8 * kTmaStages, bar_tempty = bar_tfull + 8;
+  const uint32_t act_ring = smem_u32(smem), w_ring = smem_u32(w_ring_p);
+  const uint32_t bar_afull = smem_u32(bars), bar_aempty = bar_afull + 8 * kActStages;
+  const uint32_t bar_wfull = bar_aempty + 8 * kActStages * kMaxMT, bar_wempty = bar_wfull + 8 * kWStages;
+  const uint32_t bar_tfull = bar_wempty + 8 * kWStages, bar_tempty = bar_tfull + 8;
+  // producer warp pw owns activation tiles 2*pw and 2*pw + 1 (those below NUM_MT); the last producer also owns W
+  constexpr int kActProducers = (NUM_MT + 1) / 2;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kCpSlots; ++i) {
-      mbar_init(bar_cpfull + 8 * i, kCpThreads);  // (first 2 used) one cp.async-completion arrival per loader thread per k-block
-      mbar_init(bar_cpempty + 8 * i, 1);
+    for (int i = 0; i < kActStages; ++i) {
+      mbar_init(bar_afull + 8 * i, kActProducers);  // one arrive.expect_tx per producer warp that owns activation tiles
+      for (int m = 0; m < kMaxMT; ++m) mbar_init(bar_aempty + 8 * (i * kMaxMT + m), 1);
     }
-    for (int i = 0; i < kTmaStages; ++i) {
-      mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(bar_wfull + 8 * i, 1);
+      mbar_init(bar_wempty + 8 * i, 1);
     }
     mbar_init(bar_tfull, 1);
     for (int i = 0; i < kMaxMT; ++i) mbar_init(bar_tempty + 8 * i, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {  // TMEM: 512 columns, whole warp, then give the permit back
+  if (warp == kMmaWarp) {  // TMEM: 512 columns, whole warp, then give the permit back
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(kTmemCols)
                  : "memory");
@@ -184,114 +191,96 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    // =========================== TMA producer (warp-converged, one elected lane issues) =========
+  if (warp >= kProdWarp0 && warp < kMmaWarp) {
+    // =========================== TMA producers (warp-converged, one elected lane issues) =========
+    const int pw = warp - kProdWarp0;
+    const int mt0 = 2 * pw, n_mine = max(0, min(NUM_MT - mt0, 2));
+    const bool w_mine = pw == kProdWarps - 1;
     if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     }
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int strip = strip_beg; strip < strip_end; ++strip) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        if (elect_one()) {
-          const uint32_t dst = tma_ring + stage * kTmaStageBytes;
-          mbar_expect_tx(bar_full + 8 * stage, kWBytes + (kTmaA ? kSlotBytes : 0));
-          tma_load_2d(dst, &tmap_w, bar_full + 8 * stage, kb * BK, strip * BN);
-          if (kTmaA) tma_load_3d(dst + kWBytes, &tmap_a, bar_full + 8 * stage, kb * BK, row0 + NCP * BM, img);
-        }
-        __syncwarp();
-        if (++stage == kTmaStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp >= 6) {
-    // =========================== cp.async loaders (warps 6-9): row tiles 0..NCP-1 ================
-    const int t = threadIdx.x - 192;   // 0..127
-    const int c = t & 7, r_in = t >> 3;  // 16-byte chunk of the 128 B row; row inside a group of 16
-    const __nv_bfloat16* gbase = p.h_vis + (size_t)img * p.n_vis * p.d + c * 8;
-    // group = the NCP tiles of one k-block: per-tile empty barriers (fine-grained refill), ONE full barrier per
-    // group (the MMA warp pays one wait + one proxy fence per k-block instead of one per tile)
     uint32_t g = 0;
     for (int strip = strip_beg; strip < strip_end; ++strip) {
       for (int kb = 0; kb < num_kb; ++kb, ++g) {
-        const uint32_t gslot = g & 1, gphase = (g >> 1) & 1;
-#pragma unroll
-        for (int mt = 0; mt < NCP; ++mt) {
-          const uint32_t slot = gslot * kCpTiles + mt;
-          mbar_wait(bar_cpempty + 8 * slot, gphase ^ 1);
-          const uint32_t dst = cp_ring + slot * kSlotBytes;
-#pragma unroll
-          for (int i = 0; i < BM / 16; ++i) {
-            const int row = i * 16 + r_in, grow = row0 + mt * BM + row;
-            const bool ok = grow < p.n_vis;
-            cp_async_16_zfill(dst + row * 128 + ((c ^ (row & 7)) << 4),
-                              gbase + (size_t)(ok ? grow : 0) * p.d + kb * BK, ok ? 16u : 0u);
+        const uint32_t as = g % kActStages, aphase = (g / kActStages) & 1;
+        if (w_mine) {
+          const uint32_t ws = g % kWStages, wphase = (g / kWStages) & 1;
+          mbar_wait(bar_wempty + 8 * ws, wphase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bar_wfull + 8 * ws, kWBytes);
+            tma_load_2d(w_ring + ws * kWBytes, &tmap_w, bar_wfull + 8 * ws, kb * BK, strip * BN);
           }
+          __syncwarp();
         }
-        cp_async_arrive_noinc(bar_cpfull + 8 * gslot);
+        if (n_mine > 0) {
+          for (int j = 0; j < n_mine; ++j) mbar_wait(bar_aempty + 8 * (as * kMaxMT + mt0 + j), aphase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bar_afull + 8 * as, (uint32_t)(n_mine * kSlotBytes));
+            for (int j = 0; j < n_mine; ++j)   // rows past n_vis are zero-filled by the tensor map
+              tma_load_3d(act_ring + (as * kMaxMT + mt0 + j) * kSlotBytes, &tmap_a, bar_afull + 8 * as, kb * BK,
+                          row0 + (mt0 + j) * BM, img);
+          }
+          __syncwarp();
+        }
       }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // =========================== MMA issuer (warp-converged, one elected lane issues) ==========
     // The issuing thread must stay ahead of a tensor pipe that retires one M128 x N96 x K16 MMA every ~57
-    // cycles, so the body of a k-block is instantiated for each (cp.async slot pair, TMA stage) combination:
+    // cycles, so the body of a k-block is instantiated for each (activation stage, W stage) combination:
     // every shared-memory descriptor is then "ring base + compile-time constant", one elected region issues
-    // all NUM_MT x 4 MMAs of the k-block, and the per-k-block cost is two mbarrier waits and one proxy fence.
-    auto issue_group = [&](auto GS, auto ST, uint32_t gphase, uint32_t tphase, bool first_kb, bool last_kb,
+    // all NUM_MT x 4 MMAs of the k-block, and the per-k-block cost is two mbarrier waits.
+    auto issue_group = [&](auto AS, auto WS, uint32_t aphase, uint32_t wphase, bool first_kb, bool last_kb,
                            uint32_t tempty_parity) {
-      constexpr uint32_t gslot = decltype(GS)::value, stage = decltype(ST)::value;
-      mbar_wait(bar_full + 8 * stage, tphase);
-      mbar_wait(bar_cpfull + 8 * gslot, gphase);
-      fence_proxy_async();  // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+      constexpr uint32_t as = decltype(AS)::value, ws = decltype(WS)::value;
+      mbar_wait(bar_wfull + 8 * ws, wphase);
+      mbar_wait(bar_afull + 8 * as, aphase);
       if (first_kb) {       // the epilogue must have drained the previous strip's accumulators
 #pragma unroll
         for (int mt = 0; mt < NUM_MT; ++mt) mbar_wait(bar_tempty + 8 * mt, tempty_parity);
       }
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t wbase = tma_ring + stage * kTmaStageBytes;
-        const uint64_t b_desc = make_smem_desc(wbase);
+        const uint64_t b_desc = make_smem_desc(w_ring + ws * kWBytes);
         const uint32_t acc = first_kb ? 0u : 1u;
 #pragma unroll
         for (int mt = 0; mt < NUM_MT; ++mt) {
-          const uint32_t abase = mt < NCP ? cp_ring + (gslot * kCpTiles + mt) * kSlotBytes : wbase + kWBytes;
-          const uint64_t a_desc = make_smem_desc(abase);
+          const uint64_t a_desc = make_smem_desc(act_ring + (as * kMaxMT + mt) * kSlotBytes);
           umma_bf16(tmem_base + mt * BN, a_desc, b_desc, kIdesc, acc);
 #pragma unroll
           for (int k = 1; k < BK / UMMA_K; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
             umma_bf16(tmem_base + mt * BN, a_desc + 2 * k, b_desc + 2 * k, kIdesc, 1u);
-          if (mt < NCP) umma_commit(bar_cpempty + 8 * (gslot * kCpTiles + mt));  // activation slot free once read
+          umma_commit(bar_aempty + 8 * (as * kMaxMT + mt));  // activation slot free once read
         }
-        umma_commit(bar_empty + 8 * stage);     // W (+ last activation) stage free
+        umma_commit(bar_wempty + 8 * ws);       // W slot free
         if (last_kb) umma_commit(bar_tfull);    // strip accumulators complete
       }
       __syncwarp();
     };
     using std::integral_constant;
-    uint32_t it = 0, g = 0, g6 = 0, g3 = 0, tphase = 0;  // g6 = g % 6, g3 = g % 3
+    static_assert(kActStages == 2 && kWStages == 4, "the switch below enumerates g % 4");
+    uint32_t it = 0, g = 0;
     for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
       for (int kb = 0; kb < num_kb; ++kb, ++g) {
-        const uint32_t gphase = (g >> 1) & 1, tp = (it & 1) ^ 1;
+        const uint32_t aphase = (g / kActStages) & 1, wphase = (g / kWStages) & 1, tp = (it & 1) ^ 1;
         const bool f = kb == 0, l = kb == num_kb - 1;
-        switch (g6) {
-          case 0: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 0>{}, gphase, tphase, f, l, tp); break;
-          case 1: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 1>{}, gphase, tphase, f, l, tp); break;
-          case 2: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 2>{}, gphase, tphase, f, l, tp); break;
-          case 3: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 0>{}, gphase, tphase, f, l, tp); break;
-          case 4: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 1>{}, gphase, tphase, f, l, tp); break;
-          default: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 2>{}, gphase, tphase, f, l, tp); break;
+        switch (g & 3) {
+          case 0: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 0>{}, aphase, wphase, f, l, tp); break;
+          case 1: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 1>{}, aphase, wphase, f, l, tp); break;
+          case 2: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 2>{}, aphase, wphase, f, l, tp); break;
+          default: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 3>{}, aphase, wphase, f, l, tp); break;
         }
-        if (++g6 == 6) g6 = 0;
-        if (++g3 == 3) { g3 = 0; tphase ^= 1; }
       }
     }
   } else {
-    // =========================== epilogue (warps 0-3) ===========================
-    const int tid = threadIdx.x;  // 0..127 = TMEM lane = row inside each 128-row tile
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // =========================== epilogue (warps 0-7) ===========================
+    const int q = warp & 3, half = warp >> 2;
+    const int tid = q * 32 + lane;       // 0..127 = TMEM lane = row inside each 128-row tile
+    const int hb = half * BNH;           // first column of this warp's half of the strip
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + hb;
     const float inv_v = 1.0f / (float)p.vocab;
+    const int parts_e = 2 * p.parts, part_e = 2 * part + half;
 
     float st_m[NUM_MT], st_z[NUM_MT];          // STATS: running max, sum-exp | FUSED: m, 1/Z
     float acc_a[NUM_MT], acc_q[NUM_MT], acc_c[NUM_MT];
@@ -314,126 +303,132 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
     uint32_t it = 0;
     for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
-      const int col0 = strip * BN;
+      const int col0 = strip * BN + hb;   // first vocabulary column of this warp's half strip
       mbar_wait(bar_tfull, it & 1);
       tc_fence_after();
 
-#ifdef DD_UNC_NO_EPI
-      for (int mt = 0; mt < NUM_MT; ++mt) { tc_fence_before(); mbar_arrive(bar_tempty + 8 * mt); }
-      continue;
-#endif
       if (MODE == MODE_STATS) {
 #pragma unroll
         for (int mt = 0; mt < NUM_MT; ++mt) {
           const int row = row0 + mt * BM + tid;
           const bool ok = row < p.n_vis;
-          float smax = -INFINITY;  // this row's maximum inside the strip
+          float smax = -INFINITY;  // this row's maximum inside the half strip
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            float v[32];
-            tmem_ld32(lane_addr + mt * BN + c * 32, v);
+          for (int c = 0; c < BNH / 16; ++c) {
+            float v[16];
+            tmem_ld16(lane_addr + mt * BN + c * 16, v);
             if (ok) {
-              const int cbase = col0 + c * 32;
+              const int cbase = col0 + c * 16;
               float cmax = -INFINITY;
-              if (cbase + 32 <= p.vocab) {  // (CTA-uniform) all but the last strip: no per-element bound check
+              if (cbase + 16 <= p.vocab) {  // (CTA-uniform) all but the last strip: no per-element bound check
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 16; ++i) {
                   if (p.round_bf16) v[i] = bf16_round(v[i]);
                   cmax = fmaxf(cmax, v[i]);
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 16; ++i) {
                   if (p.round_bf16) v[i] = bf16_round(v[i]);
                   if (cbase + i >= p.vocab) v[i] = -INFINITY;
                   cmax = fmaxf(cmax, v[i]);
                 }
               }
-              smax = fmaxf(smax, cmax);
-              if (cmax > st_m[mt]) {
-                st_z[mt] *= exp2f((st_m[mt] - cmax) * kLog2e);
-                st_m[mt] = cmax;
-              }
-              const float mneg = -st_m[mt] * kLog2e;
-              float zs = 0.f;
+              if (cmax > -INFINITY) {   // (a chunk wholly past the vocabulary contributes nothing)
+                smax = fmaxf(smax, cmax);
+                if (cmax > st_m[mt]) {
+                  st_z[mt] *= exp2f((st_m[mt] - cmax) * kLog2e);
+                  st_m[mt] = cmax;
+                }
+                const float mneg = -st_m[mt] * kLog2e;
+                float zs0 = 0.f, zs1 = 0.f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) zs += ex2_ftz(fmaf(v[i], kLog2e, mneg));
-              st_z[mt] += zs;
+                for (int i = 0; i < 16; i += 2) {
+                  zs0 += ex2_ftz(fmaf(v[i], kLog2e, mneg));
+                  zs1 += ex2_ftz(fmaf(v[i + 1], kLog2e, mneg));
+                }
+                st_z[mt] += zs0 + zs1;
+              }
             }
           }
-          if (ok) p.strip_max[((size_t)img * p.n_strips + strip) * p.n_vis + row] = smax;
+          if (ok) p.strip_max[((size_t)img * 2 * p.n_strips + 2 * strip + half) * p.n_vis + row] = smax;
           tc_fence_before();
           mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
         }
       } else {
         if (MODE == MODE_FUSED || MODE == MODE_COLSUM) {
-          // ---- pass 1: p, A, Q and the column sums (32 columns at a time over all row tiles, so that
-          //      the running column sums stay in 32 registers) ------------------------------------
+          // ---- pass 1: p, A, Q and the column sums (16 columns at a time over all row tiles, so that
+          //      the running column sums stay in 16 registers) ------------------------------------
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            float colsum[32];
+          for (int c = 0; c < BNH / 16; ++c) {
+            float colsum[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) colsum[i] = 0.f;
+            for (int i = 0; i < 16; ++i) colsum[i] = 0.f;
 #pragma unroll
             for (int mt = 0; mt < NUM_MT; ++mt) {
               const bool ok = row0 + mt * BM + tid < p.n_vis;
               const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
-              float v[32];
-              tmem_ld32(lane_addr + mt * BN + c * 32, v);
+              float v[16];
+              tmem_ld16(lane_addr + mt * BN + c * 16, v);
               float cm = -INFINITY;  // chunk maximum of this row: any top-k candidate in here?
               if (ok) {
                 auto body = [&](auto padded) {  // padded: the chunk holds vocab columns past the end (last strip only)
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) {
+                  for (int i = 0; i < 16; ++i) {
                     float x = v[i];
                     if (p.round_bf16) x = bf16_round(x);
-                    cm = fmaxf(cm, x);
+                    if constexpr (decltype(padded)::value) {
+                      if (col0 + c * 16 + i < p.vocab) cm = fmaxf(cm, x);
+                    } else {
+                      cm = fmaxf(cm, x);
+                    }
                     float pr = ex2_ftz(fmaf(x, kLog2e, mneg)) * iz;
                     float dv = pr - inv_v;
                     if constexpr (decltype(padded)::value)
-                      if (col0 + c * 32 + i >= p.vocab) pr = dv = 0.f;
+                      if (col0 + c * 16 + i >= p.vocab) pr = dv = 0.f;
                     colsum[i] += pr;
                     acc_a[mt] = fmaf(pr, ln_ftz(pr + kEps), acc_a[mt]);
                     acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
                   }
                 };
-                if (col0 + c * 32 + 32 <= p.vocab) body(std::false_type{});
+                if (col0 + c * 16 + 16 <= p.vocab) body(std::false_type{});
                 else body(std::true_type{});
               }
-              if (__any_sync(0xffffffffu, cm >= st_tau[mt]))  // warp-uniform, ~1 chunk in 4
+              if (__any_sync(0xffffffffu, cm >= st_tau[mt]))  // warp-uniform, rare
                 append_candidates(CandSink{p.cand_cnt, p.cand_val, p.cand_idx, p.cap, p.vocab, p.round_bf16},
-                                  lane_addr + mt * BN + c * 32, st_tau[mt], col0 + c * 32,
+                                  lane_addr + mt * BN + c * 16, st_tau[mt], col0 + c * 16,
                                   (size_t)img * p.n_vis + row0 + mt * BM + tid);
-              if (MODE == MODE_COLSUM && c == BN / 32 - 1) {  // no second pass over TMEM in this mode
+              if (MODE == MODE_COLSUM && c == BNH / 16 - 1) {  // no second pass over TMEM in this mode
                 tc_fence_before();
                 mbar_arrive(bar_tempty + 8 * mt);
               }
             }
             // column sums over the rows held by this CTA: warp butterfly, then 4 smem rows
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
               float s = colsum[i];
               s += __shfl_xor_sync(0xffffffffu, s, 16);
               s += __shfl_xor_sync(0xffffffffu, s, 8);
               s += __shfl_xor_sync(0xffffffffu, s, 4);
               s += __shfl_xor_sync(0xffffffffu, s, 2);
               s += __shfl_xor_sync(0xffffffffu, s, 1);
-              if (lane == i) s_col[warp * BN + c * 32 + i] = s;
+              if (lane == i) s_col[q * BN + hb + c * 16 + i] = s;
             }
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-          if (tid < BN) {
-            const float tot = s_col[tid] + s_col[BN + tid] + s_col[2 * BN + tid] + s_col[3 * BN + tid];
+          half_bar_sync(half);
+          if (tid < BNH) {
+            const int cc = hb + tid;
+            const float tot = s_col[cc] + s_col[BN + cc] + s_col[2 * BN + cc] + s_col[3 * BN + cc];
             if (MODE == MODE_FUSED)
-              s_logp[tid] = __logf(tot / (float)p.n_vis + kEps);  // log(p_avg + eps), models/llava.py:732-735
+              s_logp[cc] = __logf(tot / (float)p.n_vis + kEps);  // log(p_avg + eps), models/llava.py:732-735
             else
               p.colpart[((size_t)img * p.n_chunks + chunk) * ((size_t)p.n_strips * BN) + col0 + tid] = tot;
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          half_bar_sync(half);
         }
         if (MODE == MODE_CROSS) {
-          if (tid < BN) s_logp[tid] = p.logpavg[(size_t)img * ((size_t)p.n_strips * BN) + col0 + tid];
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          if (tid < BNH) s_logp[hb + tid] = p.logpavg[(size_t)img * ((size_t)p.n_strips * BN) + col0 + tid];
+          half_bar_sync(half);
         }
         if (MODE == MODE_FUSED || MODE == MODE_CROSS) {
           // ---- pass 2: C_i = sum_v p log(p_avg + eps) ---------------------------------------
@@ -442,39 +437,39 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const bool ok = row0 + mt * BM + tid < p.n_vis;
             const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-              float v[32];
-              tmem_ld32(lane_addr + mt * BN + c * 32, v);
+            for (int c = 0; c < BNH / 16; ++c) {
+              float v[16];
+              tmem_ld16(lane_addr + mt * BN + c * 16, v);
               if (ok) {
                 auto body = [&](auto padded) {
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) {
+                  for (int i = 0; i < 16; ++i) {
                     float x = v[i];
                     if (p.round_bf16) x = bf16_round(x);
                     float pr = ex2_ftz(fmaf(x, kLog2e, mneg)) * iz;
                     if constexpr (decltype(padded)::value)
-                      if (col0 + c * 32 + i >= p.vocab) pr = 0.f;
-                    acc_c[mt] = fmaf(pr, s_logp[c * 32 + i], acc_c[mt]);
+                      if (col0 + c * 16 + i >= p.vocab) pr = 0.f;
+                    acc_c[mt] = fmaf(pr, s_logp[hb + c * 16 + i], acc_c[mt]);
                   }
                 };
-                if (col0 + c * 32 + 32 <= p.vocab) body(std::false_type{});
+                if (col0 + c * 16 + 16 <= p.vocab) body(std::false_type{});
                 else body(std::true_type{});
               }
             }
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // s_col / s_logp reusable
+          half_bar_sync(half);  // s_col / s_logp reusable
         }
       }
     }
 
-    // ---- per-CTA partials --------------------------------------------------------------------
+    // ---- per-(CTA, half) partials ------------------------------------------------------------
 #pragma unroll
     for (int mt = 0; mt < NUM_MT; ++mt) {
       const int row = row0 + mt * BM + tid;
       if (row >= p.n_vis) continue;
-      const size_t pr = ((size_t)img * p.parts + part) * p.n_vis + row;
+      const size_t pr = ((size_t)img * parts_e + part_e) * p.n_vis + row;
       if (MODE == MODE_STATS) {
         p.part_stats[pr * 2] = st_m[mt];
         p.part_stats[pr * 2 + 1] = st_z[mt];
@@ -490,7 +485,7 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
@@ -509,13 +504,14 @@ stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats, float* _
   const int row = blockIdx.x * kFinWarps + (threadIdx.x >> 5), img = blockIdx.y;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.overflow = 0;
   if (row >= p.n_vis) return;  // warp-uniform
+  const int parts_e = 2 * p.parts, strips_e = 2 * p.n_strips;   // per-row partials / strip maxima exist per half strip
   float m = -INFINITY;
-  for (int q = lane; q < p.parts; q += 32)
-    m = fmaxf(m, p.part_stats[(((size_t)img * p.parts + q) * p.n_vis + row) * 2]);
+  for (int q = lane; q < parts_e; q += 32)
+    m = fmaxf(m, p.part_stats[(((size_t)img * parts_e + q) * p.n_vis + row) * 2]);
   m = warp_max(m);
   float z = 0.f;
-  for (int q = lane; q < p.parts; q += 32) {
-    const size_t pr = ((size_t)img * p.parts + q) * p.n_vis + row;
+  for (int q = lane; q < parts_e; q += 32) {
+    const size_t pr = ((size_t)img * parts_e + q) * p.n_vis + row;
     const float pm = p.part_stats[pr * 2];
     if (pm > -INFINITY) z += p.part_stats[pr * 2 + 1] * exp2f((pm - m) * kLog2e);
   }
@@ -525,8 +521,8 @@ stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats, float* _
   float tv[DD_MAX_TOPK];
 #pragma unroll
   for (int j = 0; j < DD_MAX_TOPK; ++j) tv[j] = -INFINITY;
-  for (int s = lane; s < p.n_strips; s += 32) {
-    float v = p.strip_max[((size_t)img * p.n_strips + s) * p.n_vis + row];
+  for (int s = lane; s < strips_e; s += 32) {
+    float v = p.strip_max[((size_t)img * strips_e + s) * p.n_vis + row];
 #pragma unroll
     for (int j = 0; j < DD_MAX_TOPK; ++j) {  // insertion by a chain of swaps keeps tv[] in registers
       const float hi = fmaxf(tv[j], v);
@@ -597,8 +593,8 @@ fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restr
     }
   }
   float a = 0.f, q = 0.f, c = 0.f;
-  for (int s = lane; s < p.parts; s += 32) {
-    const size_t pr = ((size_t)img * p.parts + s) * p.n_vis + row;
+  for (int s = lane; s < 2 * p.parts; s += 32) {
+    const size_t pr = ((size_t)img * 2 * p.parts + s) * p.n_vis + row;
     a += p.part_acq[pr * 3];
     q += p.part_acq[pr * 3 + 1];
     c += p.part_acq[pr * 3 + 2];
@@ -644,12 +640,12 @@ static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = parts; }
   }
   L.parts = best;
-  const size_t rows = (size_t)n_images * L.parts * n_vis;
+  const size_t rows = (size_t)n_images * 2 * L.parts * n_vis;   // partials per (CTA, epilogue half)
   size_t o = 0;
   L.off_stats = o; o = align_up(o + rows * 2 * sizeof(float), 256);
   const size_t nrow = (size_t)n_images * n_vis;
   L.cap = BN * topk + 64;  // without ties at most BN*topk elements reach the threshold
-  L.off_smax = o; o = align_up(o + nrow * L.n_strips * sizeof(float), 256);
+  L.off_smax = o; o = align_up(o + nrow * 2 * L.n_strips * sizeof(float), 256);
   L.off_tau = o; o = align_up(o + nrow * sizeof(float), 256);
   L.off_ccnt = o; o = align_up(o + nrow * sizeof(int32_t), 256);
   L.off_cval = o; o = align_up(o + nrow * L.cap * sizeof(float), 256);
@@ -664,7 +660,7 @@ static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   return L;
 }
 
-constexpr size_t kUncSmem = 1024 + (size_t)kCpSlots * kSlotBytes + (size_t)kTmaStages * kTmaStageBytes + kNumBars * 8 + 16 +
+constexpr size_t kUncSmem = 1024 + (size_t)kActStages * kMaxMT * kSlotBytes + (size_t)kWStages * kWBytes + kNumBars * 8 + 16 +
                             5 * BN * sizeof(float);
 
 template <int NUM_MT, int MODE, int KT>
@@ -741,7 +737,6 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
   UncParams p{};
   p.n_images = n_images; p.n_vis = n_vis; p.d = d; p.vocab = vocab; p.topk = topk; p.round_bf16 = round_logits_bf16;
   p.n_strips = L.n_strips; p.parts = L.parts; p.n_chunks = L.n_chunks;
-  p.h_vis = static_cast<const __nv_bfloat16*>(h_vis);
   p.colpart = reinterpret_cast<float*>(ws + L.off_colpart);
   p.logpavg = reinterpret_cast<float*>(ws + L.off_logpavg);
   p.part_stats = reinterpret_cast<float*>(ws + L.off_stats);

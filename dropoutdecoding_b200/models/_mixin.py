@@ -280,13 +280,18 @@ class DropoutDecodingMixin:
                 vision_feature_layer=None, vision_feature_select_strategy: Optional[str] = None,
                 labels: Optional[torch.LongTensor] = None, use_cache: Optional[bool] = None,
                 output_attentions: Optional[bool] = None, output_hidden_states: Optional[bool] = None,
-                return_dict: Optional[bool] = None, **kwargs):
+                return_dict: Optional[bool] = None, cache_position: Optional[torch.LongTensor] = None,
+                logits_to_keep=0, **kwargs):
         is_dd_cache = isinstance(past_key_values, DropoutDecodeCache)
         if (pixel_values is None and not is_dd_cache) or labels is not None or inputs_embeds is not None:
-            # not a Dropout-Decoding call (text-only / training): the stock LLaVA forward
+            # not a Dropout-Decoding call (text-only / training): the stock forward, with everything transformers'
+            # generate() hands over (it picks cache_position / logits_to_keep by looking at THIS signature)
+            if cache_position is not None:
+                kwargs["cache_position"] = cache_position
             return super().forward(input_ids=input_ids, pixel_values=pixel_values, attention_mask=attention_mask,
                                    position_ids=position_ids, past_key_values=past_key_values,
-                                   inputs_embeds=inputs_embeds, labels=labels, use_cache=use_cache, **kwargs)
+                                   inputs_embeds=inputs_embeds, labels=labels, use_cache=use_cache,
+                                   logits_to_keep=logits_to_keep, **kwargs)
         dev = self._head().weight.device
         input_ids = input_ids.to(dev)
         if input_ids.shape[-1] != 1:                                       # ---- prefill branch

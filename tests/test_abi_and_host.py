@@ -157,3 +157,14 @@ def test_device_map_and_dtype_of_the_reference_drivers_are_resolved_explicitly(t
     assert m.masked_numbers == [] and m.vision_uncert_dict is None          # state of models/llava.py:57-72 is there
     with pytest.raises(Exception, match="CUDA"):                              # no CPU path: loud, not a fallback
         m.decoder_weights()
+
+
+def test_text_only_calls_fall_through_to_the_stock_model():
+    """generate() / forward() without pixel_values are the parent class's (models/llava.py keeps the HF behaviour for
+    text-only input); transformers' generate() chooses its kwargs from the wrapper's forward() signature."""
+    import bench
+    m = bench.build_llava15_7b("cpu", tiny=True)
+    ids = torch.randint(3, 30000, (1, 5), generator=torch.Generator().manual_seed(0))
+    out = m.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=3, do_sample=False, pad_token_id=2)
+    assert out.shape == (1, 8) and torch.equal(out[:, :5], ids)
+    assert m(input_ids=ids).logits.shape == (1, 5, 32064)
