@@ -230,9 +230,13 @@ def run_ours(args):
         del eng
         model._engines.clear()
         torch.cuda.empty_cache()
-    target = None
+    target = members = None
     if not args.no_target and not args.tiny:
         target = run_target(model, args, rank, world, local, dist, hbm, tf)
+    if (args.shard_members == "on" or (args.shard_members == "auto" and world > 1)) and 8 % world == 0 and not args.tiny:
+        del model
+        torch.cuda.empty_cache()
+        members = run_member_sharded(args, rank, world, local, dist, hbm)
 
     if dist is not None:
         t = torch.tensor([dt, dt_e2e], device=dev, dtype=torch.float64)
@@ -262,6 +266,8 @@ def run_ours(args):
     }
     if target is not None:
         line["target_config"] = target
+    if members is not None:
+        line["member_sharded_config"] = members
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_sample_steps)
     if rank == 0:
@@ -426,6 +432,86 @@ def run_target(model, args, rank, world, local, dist, hbm, tf):
                                     "achieved": round(flops / t_unc / 1e12, 1), "peak": tf, "unit": "TFLOP/s",
                                     "frac": round(flops / t_unc / 1e12 / tf, 4), "algorithmic_flops": flops}
         del eng
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_member_sharded(args, rank, world, local, dist, hbm):
+    """BASELINE configs[4]: LLaVA-NeXT-Mistral-7B decoder shapes (GQA, 8 kv heads), up to 2880 anyres visual tokens, K=8
+    masks, batch 16, the ensemble MEMBERS sharded over the GPUs (K/N members per rank; preliminary pass replicated), one
+    NCCL all-gather per step, the whole step one CUDA graph.  The reference defines no K=8 mask rates
+    (chair_test/chair_test.py:165-174 supports 1-4): linspace(0.1, 0.8, 8).  Visual embeddings are synthetic (the anyres
+    vision tower is not part of the path)."""
+    from dropoutdecoding_b200 import distributed as dd_dist
+    from dropoutdecoding_b200.engine import DecoderConfig, DecoderWeights
+    dev = torch.device(f"cuda:{local}")
+    cfg = DecoderConfig.llava_next_mistral_7b()
+    K, B, n_vis, T = 8, args.member_batch, 2880, args.member_tokens
+    probs = [round(0.1 + 0.1 * i, 2) for i in range(K)]
+    S0 = n_vis + 20
+    with torch.no_grad():
+        w = DecoderWeights.random(cfg, dev, seed=0, std=0.02, head_std=0.02)
+        eng = dd_dist.make_member_sharded_engine(w, B, n_vis, S0 + T, probs, mode="independent", topk=10, seed=506,
+                                                 max_steps=S0 + T, est_seq=S0 + T // 2)
+        g = torch.Generator(device=dev).manual_seed(7)               # same seed on every rank: replicated inputs
+        embeds = (torch.randn(B, S0, cfg.d_model, generator=g, device=dev) * 0.02).to(torch.bfloat16)
+        hidden = eng.prefill(embeds, [10] * B)
+        vis_hidden = hidden[:, 10:10 + n_vis].contiguous()
+        last_hidden = hidden[:, -1].contiguous()
+        del hidden, embeds
+
+        def hot_path():
+            eng.seq_lens.fill_(S0)
+            eng.uncertainty_stage(vis_hidden)
+            eng.first_token(last_hidden)
+            eng.decode(T - 1)
+
+        def barrier():
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        hot_path()
+        barrier()
+        eng.launch_count = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hot_path()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        toks = eng.generated()
+        # the collective alone (eager, back to back): microseconds per all-gather of the exchange records
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(5):
+            eng._exchange()
+        c0.record()
+        for _ in range(50):
+            eng._exchange()
+        c1.record()
+        barrier()
+        coll_us = c0.elapsed_time(c1) * 1e3 / 50
+        S_mean = S0 + T / 2
+        kv_tok = 2 * cfg.n_layers * cfg.n_kv_heads * cfg.head_dim * 2
+        step_bytes = 2 * eng.w.stream_bytes_per_pass() + 2 * B * S_mean * kv_tok     # two passes per token on every rank
+        out = {"workload": f"llava-next-mistral-7b decoder shapes random-init bf16, {B} sequences x {n_vis} synthetic visual "
+                           f"tokens, K={K} masks {probs} (independent), {T} new tokens; ensemble members sharded over {world} "
+                           f"GPU(s), {K // world} per rank",
+               "value": round(B * T / dt, 2), "unit": "tokens/s", "n_gpus": world, "ms_per_token": round(dt / T * 1e3, 4),
+               "members_per_rank": K // world, "record_bytes_per_rank": int(eng._rec),
+               "collective": {"what": "all_gather_into_tensor of one exchange record per rank (member ids, token statistics, "
+                                      "staged K/V rows), consumed by dd_member_finish", "us_per_step_alone": round(coll_us, 1),
+                              "bytes_gathered_per_step": int(eng._rec * world)},
+               "step_in_cuda_graph": bool(eng.use_graph), "gpu_launches": int(eng.launch_count),
+               "step_roofline": {"bound": "hbm", "bytes_per_step_per_gpu": int(step_bytes),
+                                 "achieved": round(step_bytes * (T - 1) / dt / 1e9, 1), "peak": hbm, "unit": "GB/s",
+                                 "frac": round(step_bytes * (T - 1) / dt / 1e9 / hbm, 4)},
+               "token_checksum": int(toks.long().sum().item())}
+        del eng, w
         torch.cuda.empty_cache()
     return out
 
@@ -638,6 +724,10 @@ def main():
     ap.add_argument("--no-target", action="store_true", help="skip the 64-image / 512-token target configuration")
     ap.add_argument("--target-batch", type=int, default=64, help="images of the target configuration, all GPUs together")
     ap.add_argument("--target-tokens", type=int, default=512)
+    ap.add_argument("--shard-members", default="auto", choices=["auto", "on", "off"],
+                    help="also run BASELINE configs[4] with the K=8 ensemble members sharded over the GPUs (auto: when N > 1)")
+    ap.add_argument("--member-batch", type=int, default=16)
+    ap.add_argument("--member-tokens", type=int, default=48)
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":

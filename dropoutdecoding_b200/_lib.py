@@ -58,6 +58,9 @@ _SIGNATURES = {
     "dd_rope_stage": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "dd_embed_gather": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dd_step_advance": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
+    "dd_member_finish": (C.c_int, [_P, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int,
+                                   _P, _P, _P, _P, _P, _P, _P]),
 }
 
 EXPORTED = tuple(_SIGNATURES)

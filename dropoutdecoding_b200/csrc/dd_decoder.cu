@@ -137,6 +137,69 @@ __global__ void commit_winner_kernel(const uint4* __restrict__ k_new, const uint
   }
 }
 
+// Member-sharded decode (ensemble members on different GPUs): ONE launch after the per-step all-gather.
+// Every rank has written one exchange record -- { member argmax ids [B, mpr] | token statistics [mpr, B, 3] |
+// staged K rows [L, B, mpr, H_kv, D] | staged V rows } -- straight from its kernels into the collective's send buffer;
+// `recv` holds the G records.  This kernel votes over the gathered ids (select_by_vote, models/llava.py:22-36:
+// most frequent id, ties to the id seen first, winner = first member holding it), publishes ids / winner / token and
+// the winner's token statistics, and commits the winner's K/V rows from the gathered buffer into the cache row
+// seq_lens[b] -- the caches of all ranks stay bit-identical.  forced_winner >= 0 (logit-mean mode: member 0's cache
+// survives, models/llava.py:39,50) skips the vote and takes the token from forced_token.
+__global__ void member_finish_kernel(const uint8_t* __restrict__ recv, long long rank_stride, long long ids_off,
+                                     long long stats_off, long long k_off, long long v_off, int G, int mpr, int B, int H_kv,
+                                     int dvec, int S_max, int forced_winner, const int32_t* __restrict__ forced_token,
+                                     const int32_t* __restrict__ seq_lens, const int32_t* __restrict__ step, int n_slots,
+                                     int32_t* member_ids, int32_t* winner, int32_t* token, float* token_stats,
+                                     uint4* __restrict__ k_cache, uint4* __restrict__ v_cache) {
+  __shared__ int s_w;
+  pdl_trigger();
+  pdl_wait();
+  const int l = blockIdx.x, b = blockIdx.y, K = G * mpr;
+  if (threadIdx.x == 0) {
+    int ids[DD_MAX_MEMBERS];
+    for (int m = 0; m < K; ++m)
+      ids[m] = reinterpret_cast<const int32_t*>(recv + (size_t)(m / mpr) * rank_stride + ids_off)[b * mpr + m % mpr];
+    int w = 0, tok = ids[0];
+    if (forced_winner >= 0) {
+      w = forced_winner;
+      tok = forced_token[b];
+    } else {
+      int best_cnt = 0;
+      for (int m = 0; m < K; ++m) {
+        int c = 0;
+        for (int j = 0; j < K; ++j) c += (ids[j] == ids[m]);
+        if (c > best_cnt) { best_cnt = c; tok = ids[m]; }
+      }
+      while (ids[w] != tok) ++w;
+    }
+    s_w = w;
+    if (l == 0) {
+      for (int m = 0; m < K; ++m) member_ids[b * K + m] = ids[m];
+      winner[b] = w;
+      token[b] = tok;
+      const int slot = *step + 1;
+      if (token_stats && forced_winner < 0 && slot >= 0 && slot < n_slots) {
+        const float* st = reinterpret_cast<const float*>(recv + (size_t)(w / mpr) * rank_stride + stats_off) +
+                          ((size_t)(w % mpr) * B + b) * 3;
+        float* o = token_stats + ((size_t)slot * B + b) * 3;
+        o[0] = st[0]; o[1] = st[1]; o[2] = st[2];
+      }
+    }
+  }
+  __syncthreads();
+  const int w = s_w, pos = seq_lens[b];
+  if (pos >= S_max) return;
+  const size_t row = ((((size_t)l * B + b) * mpr + w % mpr) * H_kv) * dvec;
+  const uint4* ks = reinterpret_cast<const uint4*>(recv + (size_t)(w / mpr) * rank_stride + k_off) + row;
+  const uint4* vs = reinterpret_cast<const uint4*>(recv + (size_t)(w / mpr) * rank_stride + v_off) + row;
+  for (int idx = threadIdx.x; idx < H_kv * dvec; idx += blockDim.x) {
+    const int h = idx / dvec, j = idx % dvec;
+    const size_t dst = ((((size_t)l * B + b) * H_kv + h) * S_max + pos) * dvec + j;
+    k_cache[dst] = ks[idx];
+    v_cache[dst] = vs[idx];
+  }
+}
+
 }  // namespace dd
 
 extern "C" int dd_rmsnorm(const void* x, const void* w, int M, int d, float eps, void* y, dd_stream_t stream) {
@@ -205,5 +268,26 @@ extern "C" int dd_commit_winner(const void* k_new_all, const void* v_new_all, co
   DD_LAUNCH_CHAIN(commit_winner_kernel, dim3(L, B), dim3(128), 0, (cudaStream_t)stream, (const uint4*)k_new_all,
                   (const uint4*)v_new_all, winner, seq_lens, (uint4*)k_cache_all, (uint4*)v_cache_all, B, M, H_kv,
                   D / 8, S_max);
+  return DD_OK;
+}
+
+extern "C" int dd_member_finish(const void* recv, long long rank_stride, long long ids_off, long long stats_off,
+                                long long k_off, long long v_off, int G, int mpr, int L, int B, int H_kv, int D, int S_max,
+                                int forced_winner, const int32_t* forced_token, const int32_t* seq_lens,
+                                const int32_t* step, int n_slots, int32_t* member_ids, int32_t* winner, int32_t* token,
+                                float* token_stats, void* k_cache_all, void* v_cache_all, dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(recv && seq_lens && step && member_ids && winner && token && k_cache_all && v_cache_all,
+               "dd_member_finish: null pointer");
+  DD_CHECK_ARG(G >= 1 && mpr >= 1 && G * mpr <= DD_MAX_MEMBERS, "dd_member_finish: %d ranks x %d members out of [1,%d]",
+               G, mpr, DD_MAX_MEMBERS);
+  DD_CHECK_ARG(D % 8 == 0 && L >= 1 && H_kv >= 1 && S_max >= 1, "dd_member_finish: bad shape");
+  DD_CHECK_ARG((rank_stride | ids_off | stats_off | k_off | v_off) % 16 == 0 && ((uintptr_t)recv & 15) == 0,
+               "dd_member_finish: the exchange record must be 16-byte aligned");
+  DD_CHECK_ARG(forced_winner < G * mpr && (forced_winner < 0 || forced_token), "dd_member_finish: bad forced winner");
+  if (B == 0) return DD_OK;
+  DD_LAUNCH_CHAIN(member_finish_kernel, dim3(L, B), dim3(128), 0, (cudaStream_t)stream, (const uint8_t*)recv, rank_stride,
+                  ids_off, stats_off, k_off, v_off, G, mpr, B, H_kv, D / 8, S_max, forced_winner, forced_token, seq_lens,
+                  step, n_slots, member_ids, winner, token, token_stats, (uint4*)k_cache_all, (uint4*)v_cache_all);
   return DD_OK;
 }

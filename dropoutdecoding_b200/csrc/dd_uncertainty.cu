@@ -38,10 +38,15 @@
 // Algorithmic FLOPs = 2*n_vis*d*V per image, counted once although two sweeps run.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "dd_common.cuh"
 #include "dd_tcgen05.cuh"
+
+#ifdef DD_UNC_EXPERIMENT
+long long* g_unc_dbg = nullptr;
+#endif
 
 namespace dd {
 
@@ -102,6 +107,9 @@ struct UncParams {
   int n_chunks;            // row chunks of kMaxMT*128 rows per image (> 1 when n_vis > 640)
   float* colpart;          // [img][chunk][n_strips*BN]   column sums of p over one row chunk (COLSUM -> logpavg)
   float* logpavg;          // [img][n_strips*BN]          log(p_avg + eps)                    (CROSS input)
+#ifdef DD_UNC_EXPERIMENT
+  long long* dbg;          // [ctas][8] cycle counters (experiment builds)
+#endif
   int32_t* overflow;       // [1] rows whose top-k candidate list overflowed (ties at the threshold): the ids of such a
                            //     row may miss a tied candidate, so the host treats a non-zero count as an error
 };
@@ -231,15 +239,31 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // cycles, so the body of a k-block is instantiated for each (activation stage, W stage) combination:
     // every shared-memory descriptor is then "ring base + compile-time constant", one elected region issues
     // all NUM_MT x 4 MMAs of the k-block, and the per-k-block cost is two mbarrier waits.
+#ifdef DD_UNC_EXPERIMENT
+    long long dbg_w = 0, dbg_a = 0, dbg_t = 0;
+    const long long dbg_t0 = clock64();
+#endif
     auto issue_group = [&](auto AS, auto WS, uint32_t aphase, uint32_t wphase, bool first_kb, bool last_kb,
                            uint32_t tempty_parity) {
       constexpr uint32_t as = decltype(AS)::value, ws = decltype(WS)::value;
+#ifdef DD_UNC_EXPERIMENT
+      const long long c0 = clock64();
+#endif
       mbar_wait(bar_wfull + 8 * ws, wphase);
+#ifdef DD_UNC_EXPERIMENT
+      const long long c1 = clock64();
+#endif
       mbar_wait(bar_afull + 8 * as, aphase);
+#ifdef DD_UNC_EXPERIMENT
+      const long long c2 = clock64();
+#endif
       if (first_kb) {       // the epilogue must have drained the previous strip's accumulators
 #pragma unroll
         for (int mt = 0; mt < NUM_MT; ++mt) mbar_wait(bar_tempty + 8 * mt, tempty_parity);
       }
+#ifdef DD_UNC_EXPERIMENT
+      dbg_w += c1 - c0; dbg_a += c2 - c1; dbg_t += clock64() - c2;
+#endif
       tc_fence_after();
       if (elect_one()) {
         const uint64_t b_desc = make_smem_desc(w_ring + ws * kWBytes);
@@ -273,6 +297,12 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       }
     }
+#ifdef DD_UNC_EXPERIMENT
+    if (p.dbg && lane == 0) {
+      long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      o[0] = clock64() - dbg_t0; o[1] = dbg_w; o[2] = dbg_a; o[3] = dbg_t;
+    }
+#endif
   } else {
     // =========================== epilogue (warps 0-7) ===========================
     const int q = warp & 3, half = warp >> 2;
@@ -301,10 +331,21 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
 
+#ifdef DD_UNC_EXPERIMENT
+    long long dbg_ewait = 0;
+    const long long dbg_e0 = clock64();
+#endif
     uint32_t it = 0;
     for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
       const int col0 = strip * BN + hb;   // first vocabulary column of this warp's half strip
+#ifdef DD_UNC_EXPERIMENT
+      const long long e0 = clock64();
+#endif
       mbar_wait(bar_tfull, it & 1);
+#ifdef DD_UNC_EXPERIMENT
+      const long long e1 = clock64();
+      dbg_ewait += e1 - e0;
+#endif
       tc_fence_after();
 
       if (MODE == MODE_STATS) {
@@ -464,6 +505,12 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
 
+#ifdef DD_UNC_EXPERIMENT
+    if (p.dbg && warp == 0 && lane == 0) {
+      long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      o[4] = clock64() - dbg_e0; o[5] = dbg_ewait;
+    }
+#endif
     // ---- per-(CTA, half) partials ------------------------------------------------------------
 #pragma unroll
     for (int mt = 0; mt < NUM_MT; ++mt) {
@@ -695,6 +742,18 @@ extern "C" size_t dd_uncertainty_workspace_bytes(int n_images, int n_vis, int vo
   return dd::unc_layout(n_images, n_vis, vocab, topk).total;
 }
 
+#ifdef DD_UNC_EXPERIMENT
+// host copy of the cycle counters of the last sweep: [ctas][8] = mma {loop, wait W, wait act, wait tmem-empty}, epilogue {loop, wait tmem-full}
+extern "C" int dd_uncertainty_debug_read(long long* host, int n_ctas) {
+  long long* buf = nullptr;
+  cudaDeviceSynchronize();
+  // the static in dd_uncertainty_project is not visible here: re-derive through a second static set by a first call
+  buf = g_unc_dbg;
+  if (!buf) return -1;
+  return cudaMemcpy(host, buf, (size_t)n_ctas * 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 extern "C" size_t dd_uncertainty_overflow_offset(int n_images, int n_vis, int vocab, int topk) {
   if (n_images <= 0 || n_vis <= 0 || vocab <= 0 || topk <= 0) return 0;
   return dd::unc_layout(n_images, n_vis, vocab, topk).off_ovf;
@@ -751,6 +810,10 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
   p.row_stats = row_stats;
   p.part_acq = reinterpret_cast<float*>(ws + L.off_acq);
   p.overflow = reinterpret_cast<int32_t*>(ws + L.off_ovf);
+#ifdef DD_UNC_EXPERIMENT
+  if (getenv("DD_UNC_DBG") && !g_unc_dbg) cudaMalloc(&g_unc_dbg, 4096 * 64);
+  p.dbg = g_unc_dbg;
+#endif
   cudaStream_t st = (cudaStream_t)stream;
   const int num_mt = L.n_chunks > 1 ? kMaxMT : ceil_div(n_vis, BM);
   const dim3 fgrid(ceil_div(n_vis, kFinWarps), n_images);

@@ -8,11 +8,12 @@ the path nevertheless shards along two independent axes, one process per GPU, `t
    members co-located, so the shared prefix K/V is still read once per pass; weights are replicated; there
    is NO per-step collective.  The sampler's Philox stream is keyed by the global sequence index
    (`seq_base`), so the tokens do not depend on G.  One `all_gather` of the [B/G, T] token block at the end.
-2. **ensemble members** (`MemberShardedEngine`, for B < G -- BASELINE.json configs 2 and 5): every rank runs
-   the preliminary pass (replicated) and K/G of the masked members; per step ONE exchange:
-   `all_gather` of the member argmax ids (vote) or `all_reduce(sum)` of the [B, V] fp32 logits (mean),
-   then an `all_gather` of the members' staged new-token K/V rows from which every rank commits the
-   winner's -- the caches stay bit-identical on all ranks.
+2. **ensemble members** (`make_member_sharded_engine`, for B < G -- BASELINE.json configs 2 and 5): every rank runs
+   the preliminary pass (replicated) and K/G of the masked members; per step ONE collective: an all-gather of
+   each rank's exchange record {member argmax ids, token statistics, staged new-token K/V rows (and the logits in
+   mean mode)}, which the rank's kernels write directly into the send buffer and `dd_member_finish` consumes
+   directly (vote + commit of the winner's rows) -- the caches stay bit-identical on all ranks; the step is one
+   CUDA graph.
 
 The combine rules restate `select_by_vote` / `select_by_average` (models/llava.py:22-52) on gathered
 tensors; they run on whatever device the tensors live on (CUDA in production, CPU under gloo in tests).
@@ -141,9 +142,33 @@ def gather_member_rows(rows_local: torch.Tensor, group=None) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # member-sharded engine (CUDA only; imported lazily so that the helpers above work without the library)
 # ------------------------------------------------------------------------------------------------
+def exchange_layout(B: int, mpr: int, n_layers: int, h_kv: int, d: int):
+    """Byte layout of one rank's per-step exchange record (dd_member_finish, include/dropdec.h):
+    ids int32 [B, mpr] | token statistics fp32 [mpr, B, 3] | staged K rows bf16 [L, B, mpr, H_kv, D] | staged V rows.
+    Returns (ids_off, stats_off, k_off, v_off, record_bytes), every offset a multiple of 256."""
+    al = lambda x: -(-x // 256) * 256
+    ids_off = 0
+    stats_off = al(ids_off + B * mpr * 4)
+    k_off = al(stats_off + mpr * B * 3 * 4)
+    rows = n_layers * B * mpr * h_kv * d * 2
+    v_off = al(k_off + rows)
+    return ids_off, stats_off, k_off, v_off, al(v_off + rows)
+
+
 def make_member_sharded_engine(weights, batch: int, n_vis: int, max_seq: int, probs: Sequence[float], group=None,
                                **kw):
-    """A DropoutDecodeEngine whose masked pass runs only this rank's K/G members; see the module docstring."""
+    """A DropoutDecodeEngine whose masked pass runs only this rank's K/G members (B < G: BASELINE configs 2 and 5).
+
+    Per step and rank: the preliminary pass (replicated -- every rank needs y_init for the masks), all K masks
+    (replicated, cheap; cumulative masks depend on the earlier members), the rank's K/G masked contexts, then ONE
+    collective: an all-gather of the rank's exchange record.  The record IS the output buffer of the rank's kernels --
+    the QKV projection's RoPE epilogue stages the members' new K/V rows in it, dd_aggregate writes the member argmax
+    ids into it, dd_token_stats the per-member statistics -- so nothing is packed or copied before the collective, and
+    dd_member_finish consumes the gathered records directly: vote, winner, token, statistics and the commit of the
+    winner's K/V rows into the cache, in one launch.  The whole step (both passes, the NCCL all-gather, the finish) is
+    one CUDA graph; the caches stay bit-identical on all ranks, and the tokens equal the single-GPU engine's.
+    Logit-mean mode (select_by_average) gathers the members' logits as well and sums them in member order, i.e. exactly
+    the sequential fp32 sum of the single-GPU kernel and of the reference's numpy mean."""
     from . import ops
     from .engine import DropoutDecodeEngine
 
@@ -153,54 +178,81 @@ def make_member_sharded_engine(weights, batch: int, n_vis: int, max_seq: int, pr
             self.world, self.rank = world_size(group), rank_of(group)
             self.K_total = len(probs)
             self.m_lo, self.m_hi = member_slice(self.K_total, self.world, self.rank)
-            kw.setdefault("speculative", "off")     # members live on different ranks: the reference's two-pass order
+            self.mpr = self.m_hi - self.m_lo
+            kw["speculative"] = "off"       # members live on different ranks: the reference's two-pass order
             super().__init__(weights, batch, n_vis, max_seq, probs=probs, **kw)
             if self.vote_on != "logits":
                 raise ops.DropDecError("member sharding votes on logits (the InstructBLIP hidden-state vote is not sharded)")
-            # pass B buffers for the local members only
-            self.pb = self._alloc_pass(self.m_hi - self.m_lo, kw.get("est_seq") or max_seq)
-            self._ids_local = torch.zeros(batch, self.m_hi - self.m_lo, dtype=torch.int32, device=self.dev)
-            self._win_local = torch.zeros(batch, dtype=torch.int32, device=self.dev)
-            self._tok_local = torch.zeros(batch, dtype=torch.int32, device=self.dev)
-            self._sum_local = torch.zeros(batch, self.cfg.vocab, dtype=torch.float32, device=self.dev)
+            cfg, dev, B, mpr = self.cfg, self.dev, batch, self.mpr
+            L, Hkv, D, V = cfg.n_layers, cfg.n_kv_heads, cfg.head_dim, cfg.vocab
+            self._ids_off, self._stats_off, self._k_off, self._v_off, self._rec = exchange_layout(B, mpr, L, Hkv, D)
+            mean = self.aggregate == "mean"
+            self._logit_off = self._rec
+            if mean:                        # the members' logits ride along: fp32 [B, mpr, V]
+                self._rec += -(-B * mpr * V * 4 // 256) * 256
+            self._send = torch.zeros(self._rec, dtype=torch.uint8, device=dev)
+            self._recv = torch.zeros(self.world * self._rec, dtype=torch.uint8, device=dev)
+            view = lambda off, n, dt, shape: self._send[off:off + n].view(dt).view(*shape)
+            self._ids_local = view(self._ids_off, B * mpr * 4, torch.int32, (B, mpr))
+            self._stats_local = view(self._stats_off, mpr * B * 3 * 4, torch.float32, (mpr, B, 3))
+            rows = L * B * mpr * Hkv * D * 2
+            # pass B of the local members: its K/V staging buffers live inside the send buffer
+            self.pb = self._alloc_pass(mpr, kw.get("est_seq") or max_seq)
+            self.pb.k_new = view(self._k_off, rows, torch.bfloat16, (L, B, mpr, Hkv, D))
+            self.pb.v_new = view(self._v_off, rows, torch.bfloat16, (L, B, mpr, Hkv, D))
+            if mean:
+                self._logits_local = view(self._logit_off, B * mpr * V * 4, torch.float32, (B, mpr, V))
+                self._logits_all = torch.zeros(B, self.K_total, V, dtype=torch.float32, device=dev)
+            self._win_local = torch.zeros(B, dtype=torch.int32, device=dev)
+            self._tok_local = torch.zeros(B, dtype=torch.int32, device=dev)
+            self._members = [torch.full((B,), j, dtype=torch.int32, device=dev) for j in range(mpr)]
+            self._local_mask = torch.zeros(B, mpr, self.words, dtype=torch.int32, device=dev)
+            self.use_graph = os.environ.get("DD_MEMBER_GRAPH", "1") == "1"
+
+        def _exchange(self) -> None:
+            if self.world > 1:
+                dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+            else:
+                self._recv.copy_(self._send)
 
         def step(self) -> None:
             self.launches_per_step = 0
+            V, mean = self.cfg.vocab, self.aggregate == "mean"
             logits_a = self._forward(self.pa, None)                       # replicated preliminary pass
             ops.aggregate(logits_a, "vote", member_ids=self.member_ids_a, winner=self.winner_a, token=self.y_init,
-                          vocab=self.cfg.vocab)
-            u = None
-            if self.uniforms is not None:
-                self._u_step.copy_(self.uniforms.index_select(
-                    0, self.step_ctr.long().clamp(max=self.uniforms.shape[0] - 1))[0])
-                u = self._u_step
-            # all K masks are sampled everywhere (cumulative masks depend on the earlier members); cheap
-            ops.sample_masks(self.epi, self.topk_ids, self.y_init, self.probs, mode=self.mode,
-                             keep_relevant=self.keep_relevant, uniforms=u, seed=self.seed, offset=0,
-                             step=self.step_ctr, out=self.bitmask, n_masked=self.n_masked, seq_base=self.seq_base)
-            local_mask = self.bitmask[:, self.m_lo:self.m_hi].contiguous()
-            logits_b = self._forward(self.pb, local_mask)                 # this rank's members
-            V = self.cfg.vocab
-            if self.aggregate == "vote":
-                ops.aggregate(logits_b, "vote", member_ids=self._ids_local, winner=self._win_local,
-                              token=self._tok_local, vocab=V)
-                self.member_ids.copy_(gather_member_ids(self._ids_local, self.group))      # the per-step exchange
-                winner, token = vote_from_ids(self.member_ids)
-                self.winner.copy_(winner)
-                self.next_token.copy_(token)
-            else:
-                self._sum_local.copy_(logits_b[:, :, :V].sum(1))
-                self.out_logits.copy_(mean_logits(self._sum_local, self.K_total, self.group))
-                self.next_token.copy_(torch.argmax(self.out_logits, dim=-1).to(torch.int32))
-                self.winner.zero_()
-            k_all = gather_member_rows(self.pb.k_new, self.group)         # [L, B, K, H_kv, D]
-            v_all = gather_member_rows(self.pb.v_new, self.group)
-            ops.commit_winner(k_all, v_all, self.winner, self.seq_lens, self.k_cache, self.v_cache)
+                          vocab=V)
+            self._sample(self._step_uniforms(), self.keep_relevant, self.bitmask, self.n_masked)   # all K masks
+            self._local_mask.copy_(self.bitmask[:, self.m_lo:self.m_hi])
+            logits_b = self._forward(self.pb, self._local_mask)           # this rank's members
+            # the rank's record: ids, per-member statistics (and logits in mean mode) go straight into the send buffer
+            ops.aggregate(logits_b, "vote", member_ids=self._ids_local, winner=self._win_local, token=self._tok_local,
+                          vocab=V)
+            for j in range(self.mpr):
+                ops.token_stats(logits_b, V, self._stats_local, member=self._members[j], slot_offset=j)
+            if mean:
+                self._logits_local.copy_(logits_b[:, :, :V])
+            self._exchange()                                              # the per-step collective
+            if mean:
+                rec = self._recv.view(self.world, self._rec)
+                for r in range(self.world):     # member order = rank order x local order
+                    self._logits_all[:, r * self.mpr:(r + 1) * self.mpr] = \
+                        rec[r, self._logit_off:self._logit_off + self._logits_local.numel() * 4].view(torch.float32).view(
+                            self.B, self.mpr, V)
+                ops.aggregate(self._logits_all, "mean", member_ids=self.member_ids, winner=self.winner,
+                              token=self.next_token, out_logits=self.out_logits, vocab=V)
+                ops.token_stats(self.out_logits, V, self.token_stats, slot=self.step_ctr, slot_offset=1)
+            ops.member_finish(self._recv, self._rec, self._ids_off, self._stats_off, self._k_off, self._v_off, self.world,
+                              self.mpr, self.seq_lens, self.step_ctr, self.member_ids, self.winner, self.next_token,
+                              None if mean else self.token_stats, self.k_cache, self.v_cache,
+                              forced_winner=0 if mean else -1, forced_token=self.next_token if mean else None)
             ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
             self.cur_token.copy_(self.next_token)
+            self.launches_per_step += 6 + self.mpr
 
-        def decode(self, n_steps: int, use_graph: bool = False) -> None:
-            # eager: the per-step NCCL exchange is enqueued on the compute stream between the kernels
-            super().decode(n_steps, use_graph=False)
+        def decode(self, n_steps: int, use_graph: Optional[bool] = None, stop_token: Optional[int] = None) -> int:
+            """n_steps ensemble steps on every rank (the ranks must call this together); returns the steps done.
+            stop_token is accepted for interface parity and ignored: the step count is fixed so that the ranks stay in
+            lock step (callers trim at EOS afterwards, as generate() does)."""
+            return super().decode(n_steps, use_graph=self.use_graph if use_graph is None else use_graph)
 
     return MemberShardedEngine()

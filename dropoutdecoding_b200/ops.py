@@ -356,3 +356,25 @@ def step_advance(token: torch.Tensor, tokens_out: Optional[torch.Tensor], seq_le
     max_steps = 0 if tokens_out is None else tokens_out.shape[1]
     check(L.dd_step_advance(_ptr(token), _ptr(tokens_out), max_steps, _ptr(seq_lens), _ptr(step), token.shape[0],
                             _stream()), "dd_step_advance")
+
+
+def member_finish(recv: torch.Tensor, rank_stride: int, ids_off: int, stats_off: int, k_off: int, v_off: int, G: int,
+                  mpr: int, seq_lens: torch.Tensor, step: torch.Tensor, member_ids: torch.Tensor, winner: torch.Tensor,
+                  token: torch.Tensor, token_stats: Optional[torch.Tensor], k_cache: torch.Tensor, v_cache: torch.Tensor,
+                  forced_winner: int = -1, forced_token: Optional[torch.Tensor] = None) -> None:
+    """The finish step of the member-sharded engine after its per-step all-gather (dd_member_finish): vote over the
+    gathered ids, publish ids / winner / token / statistics, commit the winner's K/V rows from `recv` (uint8, G
+    exchange records of rank_stride bytes) into k_cache / v_cache [L, B, H_kv, S_max, D]."""
+    L_ = _lib.load()
+    _need(recv, torch.uint8, "recv")
+    for t, n in ((seq_lens, "seq_lens"), (step, "step"), (member_ids, "member_ids"), (winner, "winner"), (token, "token")):
+        _need(t, torch.int32, n)
+    _need(k_cache, torch.bfloat16, "k_cache"); _need(v_cache, torch.bfloat16, "v_cache")
+    nl, B, H_kv, S_max, D = k_cache.shape
+    if recv.numel() < G * rank_stride:
+        raise DropDecError("member_finish: recv is smaller than G records")
+    n_slots = 0 if token_stats is None else token_stats.shape[0]
+    check(L_.dd_member_finish(_ptr(recv), rank_stride, ids_off, stats_off, k_off, v_off, G, mpr, nl, B, H_kv, D, S_max,
+                              forced_winner, _ptr(forced_token), _ptr(seq_lens), _ptr(step), n_slots, _ptr(member_ids),
+                              _ptr(winner), _ptr(token), _ptr(token_stats), _ptr(k_cache), _ptr(v_cache), _stream()),
+          "dd_member_finish")

@@ -290,6 +290,20 @@ int dd_step_advance_seq(const int32_t* token /* [B] */, const int32_t* advance /
                         int32_t* tokens_out /* [B, max_steps] */, int max_steps, int32_t* seq_lens /* [B] */,
                         int32_t* seq_steps /* [B] */, int B, dd_stream_t stream);
 
+/* Member-sharded decode (ensemble members on different GPUs; the reference runs them sequentially on one,
+ * models/llava.py:342-361): the finish step after the per-step all-gather.  `recv` holds G exchange records of
+ * rank_stride bytes; a record = member argmax ids int32 [B, mpr] at ids_off | token statistics fp32 [mpr, B, 3] at
+ * stats_off | staged K rows bf16 [L, B, mpr, H_kv, D] at k_off | staged V rows at v_off, all written by the rank's
+ * kernels directly into the collective's send buffer.  Votes over the gathered ids (select_by_vote, models/llava.py:
+ * 22-36), writes member_ids [B, G*mpr] / winner [B] / token [B] and token_stats[*step + 1] of the winner, and commits the
+ * winner's K/V rows into cache row seq_lens[b] of k_cache_all / v_cache_all [L, B, H_kv, S_max, D].
+ * forced_winner >= 0: no vote (logit-mean mode: member 0's cache survives, models/llava.py:39,50), token = forced_token. */
+int dd_member_finish(const void* recv, long long rank_stride, long long ids_off, long long stats_off, long long k_off,
+                     long long v_off, int G, int mpr, int L, int B, int H_kv, int D, int S_max, int forced_winner,
+                     const int32_t* forced_token, const int32_t* seq_lens, const int32_t* step, int n_slots,
+                     int32_t* member_ids, int32_t* winner, int32_t* token, float* token_stats, void* k_cache_all,
+                     void* v_cache_all, dd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,3 +27,41 @@ def test_sequence_sharding_is_independent_of_the_split_single_gpu(cuda):
                        text=True, timeout=900, env={**os.environ, "WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0"})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert '"sequence_sharding_tokens_equal": true' in r.stdout
+
+
+@pytest.mark.parametrize("aggregate", ["vote", "mean"])
+@pytest.mark.parametrize("use_graph", [True, False], ids=["cuda_graph", "eager"])
+def test_member_exchange_record_and_finish_kernel_on_one_gpu(cuda, aggregate, use_graph):
+    """The member-sharded engine with a world of one rank runs the whole mechanism -- kernels writing ids / statistics /
+    staged K/V rows into the exchange record, the (degenerate) gather, dd_member_finish voting and committing from the
+    gathered buffer -- and must reproduce the plain two-pass engine bit for bit: tokens, caches, per-token statistics."""
+    from dropoutdecoding_b200 import distributed as dd_dist
+    from dropoutdecoding_b200.engine import DecoderConfig, DecoderWeights, DropoutDecodeEngine
+    cfg = DecoderConfig.tiny()
+    w = DecoderWeights.random(cfg, cuda, seed=0, head_std=0.08)
+    probs, n_vis, S0, T, B = [0.1, 0.3, 0.5, 0.7], 576, 593, 10, 2
+    g = torch.Generator(device=cuda).manual_seed(5)
+    kc = torch.randn(cfg.n_layers, B, cfg.n_kv_heads, S0, cfg.head_dim, generator=g, device=cuda)
+    vc = torch.randn(cfg.n_layers, B, cfg.n_kv_heads, S0, cfg.head_dim, generator=g, device=cuda)
+    epi = torch.rand(B, n_vis, generator=g, device=cuda) * 0.2 + 0.75
+    ids = torch.randint(0, cfg.vocab, (B, n_vis, 5), generator=g, device=cuda, dtype=torch.int32)
+
+    def prime(eng):
+        eng.load_prefill(kc, vc, [5] * B)
+        eng.epi.copy_(epi); eng.topk_ids.copy_(ids)
+        eng.cur_token.fill_(1234); eng.tokens_out[:, 0] = 1234
+
+    ref = DropoutDecodeEngine(w, B, n_vis, S0 + T + 4, probs=probs, max_steps=32, seed=24, aggregate=aggregate,
+                              speculative="off")
+    prime(ref)
+    ref.decode(T, use_graph=False)
+    sh = dd_dist.make_member_sharded_engine(w, B, n_vis, S0 + T + 4, probs, max_steps=32, seed=24, aggregate=aggregate)
+    prime(sh)
+    assert sh.decode(T, use_graph=use_graph) == T
+    torch.cuda.synchronize()
+    assert torch.equal(ref.generated(), sh.generated())
+    assert torch.equal(ref.k_cache, sh.k_cache) and torch.equal(ref.v_cache, sh.v_cache)
+    assert torch.equal(ref.member_ids, sh.member_ids) and torch.equal(ref.winner, sh.winner)
+    assert torch.equal(ref.token_stats[:T + 1], sh.token_stats[:T + 1])
+    a, b, c = sh.token_bookkeeping(0)
+    assert len(a) == T + 1 and any(x != 0 for x in b[1:])

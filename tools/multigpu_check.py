@@ -45,16 +45,19 @@ def main():
 
     with torch.no_grad():
         # ---- 1. members over ranks (B = 2 sequences on every rank) ----------------------------------------
-        ref = DropoutDecodeEngine(w, 2, n_vis, S0 + T + 4, probs=probs, max_steps=32, seed=24)
+        ref = DropoutDecodeEngine(w, 2, n_vis, S0 + T + 4, probs=probs, max_steps=32, seed=24, speculative="off")
         prime(ref, 2)
         ref.decode(T, use_graph=False)
-        shard = dd_dist.make_member_sharded_engine(w, 2, n_vis, S0 + T + 4, probs, max_steps=32, seed=24)
-        prime(shard, 2)
-        shard.decode(T)
-        torch.cuda.synchronize()
-        same = torch.equal(ref.generated(), shard.generated()) and torch.equal(ref.k_cache, shard.k_cache)
-        report["member_sharding_tokens_equal"] = bool(same)
-        ok &= same
+        for graph in (True, False):       # the whole step incl. the NCCL all-gather as one CUDA graph, and eagerly
+            shard = dd_dist.make_member_sharded_engine(w, 2, n_vis, S0 + T + 4, probs, max_steps=32, seed=24)
+            prime(shard, 2)
+            shard.decode(T, use_graph=graph)
+            torch.cuda.synchronize()
+            same = (torch.equal(ref.generated(), shard.generated()) and torch.equal(ref.k_cache, shard.k_cache)
+                    and torch.equal(ref.token_stats[:T + 1], shard.token_stats[:T + 1]))
+            report["member_sharding_tokens_equal" + ("_graph" if graph else "_eager")] = bool(same)
+            ok &= same
+            del shard
         # ---- 2. sequences over ranks (B = 8 in total) ------------------------------------------------------
         full = DropoutDecodeEngine(w, 8, n_vis, S0 + T + 4, probs=probs[:3], max_steps=32, seed=24)
         prime(full, 8)
