@@ -69,7 +69,10 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
 struct AttnParams {
   const __nv_bfloat16 *q, *k_cache, *v_cache;
   const int32_t *seq_lens, *vis_start;
-  const int32_t* seq_active;  // [B] or NULL: sequences with 0 are skipped (their output rows stay untouched)
+  const int32_t* seq_active;  // [B] or NULL: sequences with 0 are skipped (their output rows stay untouched) ...
+  const int32_t* seq_active2; // ... unless this second flag (or NULL) is set: a pass with two member windows
+  const int32_t* len_extra;   // [B, Mt] or NULL: member m of sequence b attends keys [0, seq_lens[b] + len_extra[b,m])
+                              //   (0 / 1: the lookahead contexts of a pass also see the row committed ahead)
   const uint32_t* bitmask;
   float *part_o, *part_ml;  // [B,H_kv,splits,R,D], [B,H_kv,splits,R,2]
   int* tickets;             // [B,H_kv] zero on entry, zero again on exit
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
   uint8_t* sV = smem + kStages * TILE_B;        // [kStages][64][D]
   uint8_t* sQ = smem + 2 * kStages * TILE_B;    // [16*QT][D]
   uint32_t* sMask = reinterpret_cast<uint32_t*>(sQ + 16 * QT * ROW_B);  // [M][mask_words]
+  __shared__ int s_ext[DD_MAX_MEMBERS];                                  // per member: 1 = also attends key S0
 
   const int split = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -115,8 +119,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
   const int G = p.H / p.H_kv, R = p.M * G;
   pdl_trigger_stream_entry();
   pdl_wait();
-  if (p.seq_active && p.seq_active[b] == 0) return;  // CTA-uniform: nothing of this sequence is read
-  const int S = p.seq_lens[b];
+  if (p.seq_active && p.seq_active[b] == 0 && !(p.seq_active2 && p.seq_active2[b] != 0))
+    return;  // CTA-uniform: nothing of this sequence is read
+  const int S0 = p.seq_lens[b];
+  int any_extra = 0;
+  if (p.len_extra)
+    for (int m = 0; m < p.M; ++m) any_extra |= p.len_extra[(size_t)b * p.Mt + p.m0 + m];
+  const int S = S0 + (any_extra ? 1 : 0);   // keys streamed; a member without the extra key masks it below
   const int vis0 = p.vis_start ? p.vis_start[b] : 0;
   const int vis1 = p.bitmask ? vis0 + p.n_vis : vis0;  // empty span when unmasked
 
@@ -164,6 +173,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
   if (p.bitmask)
     for (int idx = tid; idx < p.M * p.mask_words; idx += kAttnThreads)
       sMask[idx] = p.bitmask[((size_t)b * p.Mt + p.m0) * p.mask_words + idx];
+  if (tid < p.M) s_ext[tid] = p.len_extra ? (p.len_extra[(size_t)b * p.Mt + p.m0 + tid] != 0) : 0;
 
   float o[QT][D / 8][4];
   float m_run[QT][2], l_run[QT][2];
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
     const uint32_t kb = smem_u32(sK + stage * TILE_B), vb = smem_u32(sV + stage * TILE_B);
     const int key0 = k_beg + tile * kTileKeys + warp * 16;  // this warp's 16 keys
     if (key0 >= k_end) continue;                            // warp-uniform
-    const bool need_mask = (key0 + 16 > k_end) || (key0 < vis1 && key0 + 16 > vis0);
+    const bool need_mask = (key0 + 16 > (any_extra ? min(k_end, S0) : k_end)) || (key0 < vis1 && key0 + 16 > vis0);
 
 #pragma unroll
     for (int qt = 0; qt < QT; ++qt) {
@@ -224,13 +234,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
 #pragma unroll
         for (int hr = 0; hr < 2; ++hr) {
           const int r = qt * 16 + g + hr * 8;
-          const uint32_t* mw = sMask + (r < R ? r / G : 0) * p.mask_words;
+          const int mrow = r < R ? r / G : 0;
+          const uint32_t* mw = sMask + mrow * p.mask_words;
+          const int k_row = any_extra ? min(k_end, S0 + s_ext[mrow]) : k_end;   // this member's last key + 1
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int key = key0 + 8 * j + 2 * t + e;
-              bool dead = key >= k_end;
+              bool dead = key >= k_row;
               const int vp = key - vis0;
               if (key < vis1 && vp >= 0) dead |= (mw[vp >> 5] >> (vp & 31)) & 1u;
               if (dead) s[j][hr * 2 + e] = -INFINITY;
@@ -387,7 +399,7 @@ __global__ void __launch_bounds__(D) attn_merge_kernel(const AttnParams p) {
   pdl_trigger();
   pdl_wait();
   const int h = blockIdx.x, m = blockIdx.y, b = blockIdx.z, d = threadIdx.x;
-  if (p.seq_active && p.seq_active[b] == 0) return;
+  if (p.seq_active && p.seq_active[b] == 0 && !(p.seq_active2 && p.seq_active2[b] != 0)) return;
   const int G = p.H / p.H_kv, hkv = h / G, r = m * G + (h % G), R = p.M * G;
   const size_t qoff = (((size_t)b * p.Mt + p.m0 + m) * p.H + h) * D;
   const size_t kvoff = (((size_t)b * p.Mt + p.m0 + m) * p.H_kv + hkv) * D;
@@ -470,7 +482,22 @@ extern "C" int dd_decode_attention_active(const void* q, const void* k_new, cons
                                           int member_offset, int members_total, int H, int H_kv, int D, int S_max,
                                           int n_vis, int mask_words, float scale, int num_splits, void* out,
                                           void* workspace, size_t workspace_bytes, dd_stream_t stream) {
+  return dd_decode_attention_windows(q, k_new, v_new, k_cache, v_cache, seq_lens, vis_start, bitmask, seq_active, nullptr,
+                                     nullptr, B, M, member_offset, members_total, H, H_kv, D, S_max, n_vis, mask_words,
+                                     scale, num_splits, out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int dd_decode_attention_windows(const void* q, const void* k_new, const void* v_new, const void* k_cache,
+                                           const void* v_cache, const int32_t* seq_lens, const int32_t* vis_start,
+                                           const uint32_t* bitmask, const int32_t* seq_active,
+                                           const int32_t* seq_active2, const int32_t* len_extra, int B, int M,
+                                           int member_offset, int members_total, int H, int H_kv, int D, int S_max,
+                                           int n_vis, int mask_words, float scale, int num_splits, void* out,
+                                           void* workspace, size_t workspace_bytes, dd_stream_t stream) {
   using namespace dd;
+  DD_CHECK_ARG(!len_extra || num_splits == 1,
+               "dd_decode_attention: per-member key windows (len_extra) need num_splits == 1 (the split points of a "
+               "sequence depend on its length, so members of different lengths cannot share split partials bit-exactly)");
   DD_CHECK_ARG(member_offset >= 0 && member_offset + M <= members_total,
                "dd_decode_attention: members [%d, %d) outside the %d stored per sequence", member_offset,
                member_offset + M, members_total);
@@ -497,6 +524,7 @@ extern "C" int dd_decode_attention_active(const void* q, const void* k_new, cons
   AttnParams p{};
   p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
   p.seq_lens = seq_lens; p.vis_start = vis_start; p.bitmask = bitmask; p.seq_active = seq_active;
+  p.seq_active2 = seq_active2; p.len_extra = len_extra;
   p.part_o = (float*)workspace;
   p.part_ml = p.part_o + (size_t)B * members_total * H * num_splits * D;
   p.tickets = reinterpret_cast<int*>(p.part_ml + (size_t)B * members_total * H * num_splits * 2);

@@ -148,7 +148,8 @@ class DropoutDecodeEngine(SpeculativeSchedules):
                  probs: Sequence[float] = (0.3, 0.5, 0.7), mode: str = "cumulative", keep_relevant: bool = True,
                  topk: int = 5, aggregate: str = "vote", seed: int = 24, max_steps: int = 1024,
                  round_logits: bool = True, est_seq: Optional[int] = None, vote_on: str = "logits",
-                 seq_base: int = 0, gemm_backend: Optional[str] = None, speculative: Optional[str] = None):
+                 seq_base: int = 0, gemm_backend: Optional[str] = None, speculative: Optional[str] = None,
+                 attn_splits: Optional[int] = None):
         cfg = weights.cfg
         if cfg.d_model % 256 or cfg.d_ff % 256:
             raise ops.DropDecError("engine needs d_model % 256 == 0 and d_ff % 256 == 0")
@@ -172,6 +173,7 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         self.gemm_backend = gemm_backend or os.environ.get("DD_GEMM", "auto")
         if self.gemm_backend not in ("auto", "stream", "library", "skinny"):
             raise ValueError(self.gemm_backend)
+        self.attn_splits = attn_splits  # None: chosen per pass from the measured sweep (_alloc_pass); tests pin it
         self.seq_base = int(seq_base)   # global index of sequence 0 (batch sharded over GPUs)
         self.vote_on = vote_on          # "hidden": InstructBLIP votes on the argmax of the final hidden state
         self.Vp = weights.vocab_padded
@@ -246,6 +248,8 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         splits = max(1, min(int(sms / pairs + 0.5), max(1, tiles // 3), 32))
         if splits == 1 and pairs < sms and tiles >= 16:
             splits = 2
+        if self.attn_splits is not None:
+            splits = int(self.attn_splits)
         return _PassBuffers(
             M=M, x=torch.empty(rows, cfg.d_model, **bf), x2=torch.empty(rows, cfg.d_model, **bf),
             xn=torch.empty(rows, cfg.d_model, **bf), qkv=torch.empty(rows, (H + 2 * Hkv) * D, **bf),

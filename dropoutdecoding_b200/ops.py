@@ -145,10 +145,13 @@ def decode_attention(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, 
                      bitmask: Optional[torch.Tensor], n_vis: int, scale: float, num_splits: int = 1,
                      out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
                      seq_active: Optional[torch.Tensor] = None, member_offset: int = 0,
-                     members: Optional[int] = None) -> torch.Tensor:
+                     members: Optional[int] = None, seq_active2: Optional[torch.Tensor] = None,
+                     len_extra: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q [B,M,H,D], k_new/v_new [B,M,H_kv,D], caches [B,H_kv,S_max,D] (bf16) -> out [B,M,H,D] bf16.
-    seq_active int32 [B]: sequences with 0 are skipped (their rows of `out` stay untouched).
-    member_offset / members: serve only members [member_offset, member_offset + members) of the M stored."""
+    seq_active int32 [B]: sequences with 0 are skipped (their rows of `out` stay untouched) unless seq_active2 is set.
+    member_offset / members: serve only members [member_offset, member_offset + members) of the M stored.
+    len_extra int32 [B, M] in {0, 1}: member m attends keys [0, seq_lens[b] + len_extra[b, m]) -- two member windows
+    (verify + lookahead contexts) in one launch, the K/V read once; needs num_splits == 1."""
     L = _lib.load()
     for t, n in ((q, "q"), (k_new, "k_new"), (v_new, "v_new"), (k_cache, "k_cache"), (v_cache, "v_cache")):
         _need(t, torch.bfloat16, n)
@@ -165,11 +168,18 @@ def decode_attention(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, 
         workspace = attention_workspace(B, M, H, D, num_splits, q.device)
     if seq_active is not None:
         _need(seq_active, torch.int32, "seq_active")
+    if seq_active2 is not None:
+        _need(seq_active2, torch.int32, "seq_active2")
+    if len_extra is not None:
+        _need(len_extra, torch.int32, "len_extra")
+        if tuple(len_extra.shape) != (B, M):
+            raise DropDecError(f"len_extra must be [{B},{M}]")
     Mc = M - member_offset if members is None else members
-    check(L.dd_decode_attention_active(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(k_cache), _ptr(v_cache), _ptr(seq_lens),
-                                       _ptr(vis_start), _ptr(bitmask), _ptr(seq_active), B, Mc, member_offset, M, H, H_kv,
-                                       D, S_max, n_vis, words, float(scale), num_splits, _ptr(out), _ptr(workspace),
-                                       workspace.numel() * workspace.element_size(), _stream()), "dd_decode_attention")
+    check(L.dd_decode_attention_windows(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(k_cache), _ptr(v_cache), _ptr(seq_lens),
+                                        _ptr(vis_start), _ptr(bitmask), _ptr(seq_active), _ptr(seq_active2),
+                                        _ptr(len_extra), B, Mc, member_offset, M, H, H_kv, D, S_max, n_vis, words,
+                                        float(scale), num_splits, _ptr(out), _ptr(workspace),
+                                        workspace.numel() * workspace.element_size(), _stream()), "dd_decode_attention")
     return out
 
 

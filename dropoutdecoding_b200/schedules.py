@@ -84,6 +84,11 @@ class SpeculativeSchedules:
             self._steps_spec, self._seq_p = torch.zeros(B, **i32), torch.zeros(B, **i32)
             self._row_tok, self._row_pos = torch.zeros(B * M, **i32), torch.zeros(B * M, **i32)
             self._act1, self._act2 = torch.zeros(B, **i32), torch.zeros(B, **i32)
+            # both member windows in ONE attention launch (K/V read once for all 2K+1 contexts) when the pass is
+            # unsplit and the contexts fit the kernel's 32 query rows per kv head; DD_LA_ONE_ATTN=0 keeps two launches
+            self._len_extra = torch.zeros(B, M, **i32)
+            self._la_one_attn = (self.pe.splits == 1 and M * (cfg.n_heads // cfg.n_kv_heads) <= 32
+                                 and os.environ.get("DD_LA_ONE_ATTN", "1") == "1")
             self._y_new = torch.zeros(B, **i32)
             self._ids_v, self._ids_s = torch.zeros(B, K, **i32), torch.zeros(B, K + 1, **i32)
             self._win_v, self._tok_v = torch.zeros(B, **i32), torch.zeros(B, **i32)
@@ -386,6 +391,8 @@ class SpeculativeSchedules:
         self._act1.copy_(fb_i)
         self._act2.copy_(spec_on.to(torch.int32))
         self._gw.copy_(torch.where(fb, self._g_win, self._minus1))
+        if self._la_one_attn:
+            self._len_extra[:, K:] = fb_i[:, None]      # the spec slots of a repeating sequence see the row committed ahead
         # ---- the pass
         rows = B * M
         ops.embed_gather(self.w.embed, self._row_tok, 1, pe.x)
@@ -396,8 +403,14 @@ class SpeculativeSchedules:
             ops.rope_stage(pe.qkv, self.cos, self.sin, self._row_pos, rows, 1, H, Hkv, D, pe.q, pe.k_new[l], pe.v_new[l])
             ops.commit_winner(pe.k_new[l:l + 1], pe.v_new[l:l + 1], self._gw, self.seq_lens, self.k_cache[l:l + 1],
                               self.v_cache[l:l + 1])                                   # the guessed winner's row, ahead
-            self._attention_rows(pe, l, self.la_mask, self.seq_lens, 0, K, seq_active=self._act1)
-            self._attention_rows(pe, l, self.la_mask, self._seq_p, K, M, seq_active=self._act2)
+            if self._la_one_attn:
+                ops.decode_attention(pe.q, pe.k_new[l], pe.v_new[l], self.k_cache[l], self.v_cache[l], self.seq_lens,
+                                     self.vis_start, self.la_mask, self.n_vis, self.scale, 1, pe.attn, pe.ws,
+                                     seq_active=self._act1, seq_active2=self._act2, len_extra=self._len_extra)
+                self.launches_per_step += 2
+            else:
+                self._attention_rows(pe, l, self.la_mask, self.seq_lens, 0, K, seq_active=self._act1)
+                self._attention_rows(pe, l, self.la_mask, self._seq_p, K, M, seq_active=self._act2)
             if rows <= 32 and self.gemm_backend == "auto":
                 ops.skinny_gemm(pe.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
                 self.launches_per_step += 1

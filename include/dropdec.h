@@ -157,6 +157,17 @@ int dd_decode_attention_active(const void* q, const void* k_new, const void* v_n
                                int member_offset, int members_total, int H, int H_kv, int D, int S_max, int n_vis,
                                int mask_words, float scale, int num_splits, void* out, void* workspace,
                                size_t workspace_bytes, dd_stream_t stream);
+/* dd_decode_attention_active with TWO member windows in one launch (the lookahead schedules: "verify" contexts of a
+ * repeated step next to the speculative contexts of the following step): the sequence is processed when
+ * seq_active[b] or seq_active2[b] is set, and member m attends keys [0, seq_lens[b] + len_extra[b, m]) with
+ * len_extra int32 [B, members_total] in {0, 1} -- the speculative contexts also see the row committed ahead at
+ * seq_lens[b].  The prefix K/V is still read ONCE for all members.  Needs num_splits == 1. */
+int dd_decode_attention_windows(const void* q, const void* k_new, const void* v_new, const void* k_cache,
+                                const void* v_cache, const int32_t* seq_lens, const int32_t* vis_start,
+                                const uint32_t* bitmask, const int32_t* seq_active, const int32_t* seq_active2,
+                                const int32_t* len_extra, int B, int M, int member_offset, int members_total, int H,
+                                int H_kv, int D, int S_max, int n_vis, int mask_words, float scale, int num_splits,
+                                void* out, void* workspace, size_t workspace_bytes, dd_stream_t stream);
 
 /* Commit the winning member's new-token K/V rows of every layer into the shared cache at
  * position seq_lens[b] (replaces "the winner's cache becomes the live cache",

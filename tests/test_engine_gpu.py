@@ -231,7 +231,7 @@ def test_lookahead_in_fallback_pass_equals_two_pass(tiny, cuda, aggregate, use_g
     assert a.n_chain_ok > 0, "no lookahead was ever confirmed"
 
 
-@pytest.mark.parametrize("lookahead", ["lookahead", "plain"])
+@pytest.mark.parametrize("lookahead", ["lookahead", "plain", "lookahead_one_attention_launch"])
 @pytest.mark.parametrize("aggregate", ["vote", "mean"])
 def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate, lookahead, monkeypatch):
     """(lookahead: 2K+1 slots per sequence -- a sequence repeating a step with its real masks also runs the speculative
@@ -243,6 +243,10 @@ def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate, lookahead, 
     decodes alone (sequence 0 replays the oracle trace)."""
     tr = tiny["trace"]
     B, T = 12, 18
+    # "..._one_attention_launch": unsplit K/V (what batches of >= 5 sequences x 32 kv heads use on the 7B shapes), where
+    # the verify and the lookahead contexts share ONE attention launch with per-member key extents (len_extra)
+    one_attn = lookahead.endswith("one_attention_launch")
+    lookahead = "lookahead" if one_attn else lookahead
     monkeypatch.setenv("DD_BATCH_LA", "1" if lookahead == "lookahead" else "0")
     g = torch.Generator().manual_seed(99)
     U = torch.rand(T, B, 3, TINY_N_VIS, generator=g)
@@ -251,6 +255,7 @@ def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate, lookahead, 
     for spec in ("auto", "off"):
         eng = tiny["Engine"](tiny["weights"], batch=B, n_vis=TINY_N_VIS, max_seq=640, probs=TINY_PROBS,
                              mode="cumulative", topk=5, seed=24, max_steps=64, aggregate=aggregate, speculative=spec,
+                             attn_splits=1 if one_attn else None,
                              gemm_backend="stream")    # row-independent GEMMs: a library GEMM may sum a row in another
         #                                                order when the row count of the pass changes (36 vs 48 rows)
         k = torch.stack(tr.prefill_cache.k)[:, None].expand(-1, B, -1, -1, -1)
@@ -263,6 +268,7 @@ def test_async_batch_schedule_equals_two_pass(tiny, cuda, aggregate, lookahead, 
         engs.append(eng)
     a, b = engs
     assert a.spec_batch and not a.spec_active and not b.spec_batch and a.batch_la == (lookahead == "lookahead")
+    assert not one_attn or a._la_one_attn
     for chunk, graph in ((1, False), (5, True), (1, True), (T - 8, True)):      # lockstep again after every call
         a.decode(chunk, use_graph=graph)
         b.decode(chunk, use_graph=True)
