@@ -89,9 +89,12 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap
 #ifdef DD_SG_EXPERIMENT
 __device__ __forceinline__ long long gtime_ns() {
   long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
   return t;
 }
+#define SG_STAMP(i) do { if (p.dbg && (threadIdx.x == SG_EPI_WARP0 * 32) && rank == 0) p.dbg[cta * 16 + 8 + (i)] = gtime_ns(); } while (0)
+#else
+#define SG_STAMP(i) do { } while (0)
 #endif
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -176,7 +179,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int n_stage_kb = p.KB / p.bks;   // pipeline stages per tile
 
 #ifdef DD_SG_EXPERIMENT
-  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cta * 8 + 6] = gtime_ns();
+  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cta * 16 + 6] = gtime_ns();
 #endif
   const uint32_t ring = smem_u32(smem);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * SG_MAX_STAGES;
@@ -253,7 +256,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       }
     }
 #ifdef DD_SG_EXPERIMENT
-    if (p.dbg && warp == 0 && lane == 0 && rank == 0) { p.dbg[cta * 8 + 0] = clock64() - dbg_t0; p.dbg[cta * 8 + 1] = dbg_wait; }
+    if (p.dbg && warp == 0 && lane == 0 && rank == 0) { p.dbg[cta * 16 + 0] = clock64() - dbg_t0; p.dbg[cta * 16 + 1] = dbg_wait; }
 #endif
   } else if (warp == SG_MMA_WARP) {
     // =========================== MMA issuer ===========================
@@ -297,7 +300,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       if (++acc_stage == p.acc_stages) { acc_stage = 0; acc_phase ^= 1; }
     }
 #ifdef DD_SG_EXPERIMENT
-    if (p.dbg && lane == 0 && rank == 0) { p.dbg[cta * 8 + 2] = clock64() - dbg_t0; p.dbg[cta * 8 + 3] = dbg_wait; p.dbg[cta * 8 + 5] = gtime_ns(); }
+    if (p.dbg && lane == 0 && rank == 0) { p.dbg[cta * 16 + 2] = clock64() - dbg_t0; p.dbg[cta * 16 + 3] = dbg_wait; p.dbg[cta * 16 + 5] = gtime_ns(); }
 #endif
   } else {
     // =========================== epilogue (warps 5..12) ===========================
@@ -321,6 +324,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       const long long dbg_e1 = clock64();
 #endif
       tc_fence_after();
+      SG_STAMP(0);          // accumulators complete
       if (p.S > 1) break;   // split tile (always the CTA's only one): the cluster reduction below finishes it
       const uint32_t t0 = lane_addr + acc_stage * p.nacc * p.Fw + a * p.Fw;
       for (int c = c0; c < n_chunks; c += cstep) {
@@ -333,7 +337,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc_stage);
 #ifdef DD_SG_EXPERIMENT
-      if (p.dbg && threadIdx.x == SG_EPI_WARP0 * 32) { p.dbg[cta * 8 + 4] = clock64() - dbg_e1; }
+      if (p.dbg && threadIdx.x == SG_EPI_WARP0 * 32) { p.dbg[cta * 16 + 4] = clock64() - dbg_e1; }
 #endif
       if (++acc_stage == p.acc_stages) { acc_stage = 0; acc_phase ^= 1; }
     }
@@ -354,6 +358,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     tc_fence_before();
     cluster_sync_all();     // #1: every CTA's accumulators are complete and its operand ring is idle
     tc_fence_after();
+    SG_STAMP(1);
     if (epi) {
       for (int c = c0; c < n_chunks; c += cstep) {
         const int owner = ((c + 1) * p.S - 1) / n_chunks;          // the rank r with r*nc/S <= c < (r+1)*nc/S
@@ -370,7 +375,9 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         }
       }
     }
+    SG_STAMP(2);
     cluster_sync_all();     // #2: the peers' partials of my chunks have landed in my shared memory
+    SG_STAMP(3);
     if (epi) {
       const int own_b = rank * n_chunks / p.S, own_e = (rank + 1) * n_chunks / p.S;
       for (int c = own_b + c0; c < own_e; c += cstep) {
@@ -401,10 +408,11 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
   }
 
+  SG_STAMP(4);            // outputs stored
   tc_fence_before();
   __syncthreads();
 #ifdef DD_SG_EXPERIMENT
-  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cta * 8 + 7] = gtime_ns();
+  if (p.dbg && threadIdx.x == 0 && rank == 0) p.dbg[cta * 16 + 7] = gtime_ns();
 #endif
   if (warp == SG_MMA_WARP) {
     tc_fence_after();
@@ -550,7 +558,7 @@ extern "C" int dd_stream_gemm(const void* x, const void* w, const void* residual
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.y = y;
 #ifdef DD_SG_EXPERIMENT
-  p.dbg = (getenv("DD_SG_DBG") && workspace_bytes >= (size_t)s.G * 64 && s.G * 64 <= 16384) ? static_cast<long long*>(workspace) : nullptr;
+  p.dbg = (getenv("DD_SG_DBG") && workspace_bytes >= (size_t)s.G * 128 && s.G * 128 <= 16384) ? static_cast<long long*>(workspace) : nullptr;
   if (getenv("DD_SG_DBG")) fprintf(stderr, "[sg] M=%d N=%d K=%d epi=%d: F=%d T=%d S=%d bks=%d stage=%d B x %d stages, tmem %d\n", M, N, K, epilogue, s.F, s.T, s.S, s.bks, s.stage_bytes, s.stages, s.tmem_cols);
 #endif
   {

@@ -358,12 +358,27 @@ class DropoutDecodingMixin:
         hit = (ids == max_id.reshape(-1)[-1]).any(dim=1)
         return torch.nonzero(hit).squeeze() + self.start_image_pos[0]
 
+    def lowest_percent_kl_indices(self, image_logits, logits, percent=0.1):
+        """models/llava.py:758-776 / models/instructblip.py:559-578: indices (inside the visual span) of the
+        int(percent * N) visual tokens whose projected distribution is closest in KL to the current one.  Needs the
+        materialised image logits [1, N, V] (`self.image_logits`, which only the reference-style forward() prefill
+        builds -- the generate() hot path never does); an ablation helper, evaluated with torch ops."""
+        il = image_logits.squeeze(0).float()
+        cur = logits.reshape(1, -1).float()
+        kl = torch.nn.functional.kl_div(torch.log_softmax(il, dim=-1), torch.softmax(cur, dim=-1).expand_as(il),
+                                        reduction="none").sum(dim=-1)
+        return torch.topk(kl, int(percent * kl.numel()), largest=False).indices
+
     def get_image_attention_mask(self, logits, attention_mask, method="epis", prob=0.5, ids=[]):
-        """'epis' / 'epis_no_overlap' of the reference (models/llava.py:589-683) for ONE member, on the
-        device sampler: zeros `attention_mask` in place at the drawn visual positions (cumulative with
-        whatever is already zero) and restores the relevant tokens."""
-        if method not in ("epis", "epis_no_overlap"):
+        """'epis' / 'epis_no_overlap' / 'epis_kl' of the reference (models/llava.py:589-683, instructblip.py:464-485)
+        for ONE member, on the device sampler: zeros `attention_mask` in place at the drawn visual positions (cumulative
+        with whatever is already zero) and restores the relevant tokens ('epis': those whose top-k ids contain the
+        preliminary argmax; 'epis_kl': the lowest-KL tenth, from the materialised `self.image_logits`)."""
+        if method not in ("epis", "epis_no_overlap", "epis_kl"):
             raise NotImplementedError(f"mask method {method!r} is dead code in the reference and not provided")
+        if method == "epis_kl" and self.image_logits is None:
+            raise ValueError("'epis_kl' needs the materialised image logits: run the reference-style forward() prefill "
+                             "(generate() never builds them)")
         epi = self.vision_uncert_dict["epis_uncert_per_token"][:1].float().contiguous()
         n_vis, start = epi.shape[1], self.start_image_pos[0]
         y = torch.argmax(logits.reshape(-1, logits.shape[-1])[-1:], dim=-1).int()
@@ -381,4 +396,7 @@ class DropoutDecodingMixin:
             rel = self.get_overlap_image_tokens(logits).reshape(-1)
             attention_mask[:, rel] = 1
             self.masked_numbers.append(int((attention_mask[0] == 0).sum()))
+        elif method == "epis_kl":
+            low = self.lowest_percent_kl_indices(self.image_logits[:1], logits.reshape(1, 1, -1)[:, -1:])
+            attention_mask[:, (low + start).to(attention_mask.device)] = 1
         return attention_mask

@@ -32,7 +32,7 @@ __all__ = [
     "LMConfig", "init_lm_weights", "OracleLM", "OracleCache",
     "calculate_vision_uncertainty", "topk_token_ids", "relevant_visual_tokens",
     "drop_probabilities", "sample_mask_epis", "quantile_threshold",
-    "sample_mask_quantile", "select_by_vote", "select_by_average",
+    "sample_mask_quantile", "lowest_percent_kl_indices", "sample_mask_epis_kl", "select_by_vote", "select_by_average",
     "entropy_varentropy", "dropout_decode", "ensemble_steps", "DecodeTrace", "bf16r",
     "rope_table",
 ]
@@ -134,6 +134,27 @@ def sample_mask_quantile(epis: torch.Tensor, prob: float, relevant: Optional[tor
     if relevant is not None and relevant.numel() > 0:
         out = out.clone()
         out[relevant] = False                             # :460
+    return out
+
+
+# (f2) "epis_kl" mask (a dead-code method of the reference, kept as an ablation knob)
+#      models/llava.py:758-776, models/instructblip.py:464-485, 559-578
+def lowest_percent_kl_indices(image_logits: torch.Tensor, logits: torch.Tensor, percent: float = 0.1) -> torch.Tensor:
+    """image_logits [1, N, V], logits [1, 1, V] -> indices of the int(percent*N) visual tokens whose projected
+    distribution is closest to the current one: F.kl_div(log_softmax(image), softmax(cur).expand, 'none').sum(-1),
+    then topk(largest=False) (models/llava.py:763-776)."""
+    il = image_logits.squeeze(0)
+    cur = logits.squeeze(0)
+    kl = F.kl_div(F.log_softmax(il, dim=-1), F.softmax(cur, dim=-1).expand_as(il), reduction='none').sum(dim=-1)
+    n = int(percent * kl.numel())
+    return torch.topk(kl, n, largest=False).indices
+
+
+def sample_mask_epis_kl(epis: torch.Tensor, prob: float, uniforms: torch.Tensor, image_logits: torch.Tensor,
+                        logits: torch.Tensor) -> torch.Tensor:
+    """models/instructblip.py:464-485: the 'epis' draw, then the lowest-KL tenth of the visual tokens restored."""
+    out = (uniforms < drop_probabilities(epis, prob)).clone()
+    out[lowest_percent_kl_indices(image_logits, logits)] = False
     return out
 
 

@@ -461,9 +461,43 @@ def gold_decode_blip():
     np.savez_compressed(os.path.join(HERE, "decode_blip_tiny.npz"), **out)
 
 
+def gold_epis_kl():
+    """lowest_percent_kl_indices (models/llava.py:758-776; instructblip.py:559-578) and the 'epis_kl' mask method
+    (instructblip.py:464-485) of the reference itself on seeded inputs."""
+    out = {}
+    for name, n_vis, V, start in (("llava", 576, 4096, 5), ("blip", 32, 1000, 0)):
+        g = torch.Generator().manual_seed(77 + n_vis)
+        image_logits = torch.randn(1, n_vis, V, generator=g) * 1.3
+        logits = torch.randn(1, 1, V, generator=g) * 1.3
+        epis = torch.rand(n_vis, generator=g) * 0.2 + 0.75
+        u = torch.rand(n_vis, generator=g)
+        ref_idx = RL.lowest_percent_kl_indices(SimpleNamespace(), image_logits, logits)
+        eq(oracle.lowest_percent_kl_indices(image_logits, logits), ref_idx, f"epis_kl/{name} indices")
+        eq(RB.lowest_percent_kl_indices(SimpleNamespace(), image_logits, logits), ref_idx, f"epis_kl/{name} blip twin")
+        # the whole mask method: InstructBLIP's get_image_attention_mask(method="epis_kl") with rand_like pinned to u
+        stub = SimpleNamespace(vision_uncert_dict={"epis_uncert_per_token": epis[None]}, image_logits=image_logits,
+                               start_image_pos=[start], masked_numbers=[],
+                               image_features=(None, torch.zeros(1, n_vis, 10, dtype=torch.long)))
+        stub.lowest_percent_kl_indices = lambda il, l, percent=0.1: RB.lowest_percent_kl_indices(stub, il, l, percent)
+        stub.get_overlap_image_tokens = lambda *a, **k: torch.zeros(0, dtype=torch.long)
+        mask = torch.ones(1, start + n_vis + 12, dtype=torch.long)
+        real_rand = torch.rand_like
+        torch.rand_like = lambda t, *a, **k: u.to(t.dtype)
+        try:
+            got = RB.get_image_attention_mask(stub, logits, mask, method="epis_kl", prob=0.5)
+        finally:
+            torch.rand_like = real_rand
+        dropped_ref = (got[0, start:start + n_vis] == 0)
+        eq(oracle.sample_mask_epis_kl(epis, 0.5, u, image_logits, logits), dropped_ref, f"epis_kl/{name} mask")
+        print(f"[epis_kl/{name}] {int(ref_idx.numel())} lowest-KL tokens restored, {int(dropped_ref.sum())} dropped")
+        out[f"{name}.indices"] = ref_idx.numpy().astype(np.int64)
+        out[f"{name}.dropped"] = dropped_ref.numpy()
+    np.savez_compressed(os.path.join(HERE, "epis_kl.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["uncertainty", "masks", "aggregate", "decode", "decode_blip"]
+    which = sys.argv[1:] or ["uncertainty", "masks", "aggregate", "decode", "decode_blip", "epis_kl"]
     with torch.no_grad():
         for wname in which:
             globals()["gold_" + wname]()

@@ -95,3 +95,23 @@ def test_decode_tiny_config1(tag, faithful, golden_dir):
     # cumulative masks only grow from member to member (models/llava.py:344 is commented out)
     assert all(a <= b <= c for a, b, c in tr.masked_numbers)
     np.testing.assert_allclose(tr.uncert["epis_uncert_per_token"][0].numpy(), z[f"{tag}.epi"], rtol=1e-4)
+
+
+def test_epis_kl_restatement_and_wrapper_helper_match_the_reference(golden_dir):
+    """`lowest_percent_kl_indices` / the 'epis_kl' mask (models/llava.py:758-776, instructblip.py:464-485, 559-578): the
+    oracle restatement and the wrapper's public helper against what the reference's own functions returned
+    (tests/golden/make_golden.py epis_kl)."""
+    import oracle
+    from dropoutdecoding_b200.models._mixin import DropoutDecodingMixin
+    z = np.load(os.path.join(golden_dir, "epis_kl.npz"))
+    for name, n_vis, V in (("llava", 576, 4096), ("blip", 32, 1000)):
+        g = torch.Generator().manual_seed(77 + n_vis)
+        image_logits = torch.randn(1, n_vis, V, generator=g) * 1.3
+        logits = torch.randn(1, 1, V, generator=g) * 1.3
+        epis = torch.rand(n_vis, generator=g) * 0.2 + 0.75
+        u = torch.rand(n_vis, generator=g)
+        want = z[f"{name}.indices"]
+        assert oracle.lowest_percent_kl_indices(image_logits, logits).numpy().tolist() == want.tolist()
+        got = DropoutDecodingMixin.lowest_percent_kl_indices(None, image_logits, logits)
+        assert sorted(got.tolist()) == sorted(want.tolist())
+        assert np.array_equal(oracle.sample_mask_epis_kl(epis, 0.5, u, image_logits, logits).numpy(), z[f"{name}.dropped"])

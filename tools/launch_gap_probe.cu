@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <vector>
 
 #define CK(x)                                                                              \
   do {                                                                                     \
@@ -45,6 +47,15 @@ __global__ void k_tmem(int* sink, int cols) {
   if ((threadIdx.x >> 5) == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"((uint32_t)cols) : "memory");
   if (sink && threadIdx.x == 1000) *sink = 1;
+}
+// a kernel that is busy for `ns` nanoseconds (globaltimer) and then exits: is the boundary between two LONG kernels as
+// cheap as between two empty ones?  out[2*blockIdx.x] = entry time, out[2*blockIdx.x+1] = exit time
+__global__ void k_spin(long long ns, long long* out, int slot) {
+  long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0) :: "memory");
+  long long t = t0;
+  while (t - t0 < ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+  if (threadIdx.x == 0 && out) { out[(size_t)slot * 512 + 2 * blockIdx.x] = t0; out[(size_t)slot * 512 + 2 * blockIdx.x + 1] = t; }
 }
 __global__ void k_store(float* out, int n_per_thread) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,6 +118,27 @@ int main() {
     cfg.gridDim = dim3(128);
     attr[0].val.clusterDim.x = 4;
     report("cluster4_128x416", time_graph(st, n, [&] { CK(cudaLaunchKernelEx(&cfg, k_empty, (int*)nullptr)); }));
+  }
+  {
+    long long* stamps;
+    CK(cudaMalloc(&stamps, 64 * 512 * 8));
+    for (long long ns : {2000ll, 20000ll}) {
+      for (int smem : {0, 200 * 1024}) {
+        CK(cudaFuncSetAttribute(k_spin, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaMemset(stamps, 0, 64 * 512 * 8));
+        int slot = 0;
+        const float us = time_graph(st, 32, [&] { k_spin<<<148, 416, smem, st>>>(ns, stamps, slot); slot = (slot + 1) % 32; });
+        std::vector<long long> h(32 * 512);
+        CK(cudaMemcpy(h.data(), stamps, 32 * 512 * 8, cudaMemcpyDeviceToHost));
+        double gap = 0;
+        for (int k = 1; k < 32; ++k) {
+          long long last_exit = 0, first_entry = h[k * 512];
+          for (int c = 0; c < 148; ++c) { last_exit = std::max(last_exit, h[(k - 1) * 512 + 2 * c + 1]); first_entry = std::min(first_entry, h[k * 512 + 2 * c]); }
+          gap += (first_entry - last_exit) * 1e-3;
+        }
+        printf("{\"probe\": \"spin_%lldus_smem%dKB\", \"us_per_node\": %.2f, \"gap_last_exit_to_first_entry_us\": %.2f}\n", ns / 1000, smem / 1024, us, gap / 31);
+      }
+    }
   }
   report("store_148x416_x1", time_graph(st, n, [&] { k_store<<<148, 416, 0, st>>>(out, 1); }));
   report("store_148x416_x64(16MB)", time_graph(st, n, [&] { k_store<<<148, 416, 0, st>>>(out, 64); }));

@@ -76,7 +76,7 @@ extern "C" int dd_stream_gemm_debug_ctas(int M, int N, int K, int epilogue);
 // per-CTA %globaltimer stamps of the last launch (DD_SG_DBG=16): min / median / max per phase, us since the first entry
 static void dump_timeline(const void* ws, size_t wsb, int G, const char* name, int M) {
   std::vector<long long> h((size_t)G * 8);
-  CK(cudaMemcpy(h.data(), ws, (size_t)G * 64, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h.data(), ws, (size_t)G * 64, cudaMemcpyDeviceToHost)); return;
   const char* names[5] = {"prod0_loop", "prod0_wait_empty", "mma_loop", "mma_wait_full", "epi_work"};
   printf("%s M=%d G=%d  cycles (min / median / max over CTAs)\n", name, M, G);
   for (int s = 0; s < 5; ++s) {
@@ -206,20 +206,20 @@ int main(int argc, char** argv) {
         if (dd_stream_gemm(x, wr, res, M, sh.N, sh.K, sh.epi, y, wsl, wsb, st)) { fprintf(stderr, "%s\n", dd_last_error()); exit(1); }
       });
 #ifdef DD_SG_EXPERIMENT
-      if (getenv("DD_SG_DBG")) {   // consecutive launches of the last pass: entry / done stamps -> kernel time and gap
+      if (getenv("DD_SG_DBG")) {   // consecutive launches of the last pass: per-phase stamps (us since the launch's first CTA entry)
         const int G = dd_stream_gemm_debug_ctas(M, sh.N, sh.K, sh.epi);
-        std::vector<long long> h((size_t)G * 8);
-        long long prev_done = 0, first_entry0 = 0;
-        printf("%s M=%d launch-to-launch (us):", sh.name, M);
-        for (int r = 0; r < nrot; ++r) {
-          CK(cudaMemcpy(h.data(), wsr + (size_t)r * wsb, (size_t)G * 64, cudaMemcpyDeviceToHost));
-          long long e0 = h[6], e1 = h[6], d1 = h[7], m1 = h[5];
-          for (int c = 0; c < G; ++c) { e0 = std::min(e0, h[c * 8 + 6]); e1 = std::max(e1, h[c * 8 + 6]); d1 = std::max(d1, h[c * 8 + 7]); m1 = std::max(m1, h[c * 8 + 5]); }
-          if (r == 0) first_entry0 = e0;
-          printf("  [gap %.1f | entry-spread %.1f | mma %.1f | dur %.1f]", r ? (e0 - prev_done) * 1e-3 : 0.0, (e1 - e0) * 1e-3, (m1 - e0) * 1e-3, (d1 - e0) * 1e-3);
-          prev_done = d1;
+        std::vector<long long> h((size_t)G * 16);
+        long long prev_entry = 0;
+        printf("%s M=%d G=%d phases (median over CTAs, us since first entry): entry->entry | mma_issued | acc_complete | sync1 | xchg_written | sync2 | stored | exit\n", sh.name, M, G);
+        for (int r = 0; r < nrot && r < 6; ++r) {
+          CK(cudaMemcpy(h.data(), wsr + (size_t)r * wsb, (size_t)G * 128, cudaMemcpyDeviceToHost));
+          long long e0 = h[6];
+          for (int c = 0; c < G; ++c) e0 = std::min(e0, h[c * 16 + 6]);
+          auto med = [&](int slot) { std::vector<long long> v; for (int c = 0; c < G; ++c) if (h[c * 16 + slot]) v.push_back(h[c * 16 + slot] - e0); if (v.empty()) return -1.0; std::sort(v.begin(), v.end()); return v[v.size() / 2] * 1e-3; };
+          auto mx = [&](int slot) { long long m = 0; for (int c = 0; c < G; ++c) m = std::max(m, h[c * 16 + slot] - e0); return m * 1e-3; };
+          printf("   [%5.1f | %5.1f | %5.1f | %5.1f | %5.1f | %5.1f | %5.1f | %5.1f (max %.1f)]\n", r ? (e0 - prev_entry) * 1e-3 : 0.0, med(5), med(8), med(9), med(10), med(11), med(12), med(7), mx(7));
+          prev_entry = e0;
         }
-        printf("  total %.1f per launch\n", (prev_done - first_entry0) * 1e-3 / nrot);
       }
       CK(cudaFree(wsr));
 #endif
