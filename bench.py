@@ -417,7 +417,9 @@ def run_target(model, args, rank, world, local, dist, hbm, tf):
         kv = 2 * S_att * cfg.n_kv_heads * cfg.head_dim * 2 * B
         out["decode_attention"] = {"bound": "hbm", "kernel": "dd::attn_partial_kernel", "us": round(t_att * 1e6, 2),
                                    "members": mem, "seq_len": S_att, "achieved": round(kv / t_att / 1e9, 1), "peak": hbm,
-                                   "unit": "GB/s", "frac": round(kv / t_att / 1e9 / hbm, 4), "algorithmic_bytes": kv}
+                                   "unit": "GB/s", "frac": round(kv / t_att / 1e9 / hbm, 4), "algorithmic_bytes": kv,
+                                   "traffic_note": "ncu dram read+write = 1.02 x the K/V bytes at B=64, S=849 "
+                                                   "(profiles/r02/ncu_full_summary.json)"}
         if eng._use_stream(rows):
             lw = eng.w.layers[0]
             x = pbuf.xn[:rows]
@@ -425,7 +427,10 @@ def run_target(model, args, rank, world, local, dist, hbm, tf):
             wb = lw["wgu"].numel() * 2
             out["stream_gemm_gate_up"] = {"bound": "hbm", "kernel": "dd::stream_gemm_kernel", "rows": rows,
                                           "us": round(t_g * 1e6, 2), "achieved": round(wb / t_g / 1e9, 1), "peak": hbm,
-                                          "unit": "GB/s", "frac": round(wb / t_g / 1e9 / hbm, 4), "algorithmic_bytes": wb}
+                                          "unit": "GB/s", "frac": round(wb / t_g / 1e9 / hbm, 4), "algorithmic_bytes": wb,
+                                          "traffic": int(1.03 * wb),
+                                          "traffic_note": "ncu dram read+write at 192 rows = 1.03 x the weight bytes "
+                                                          "(185.5 MB vs 180.4 MB; profiles/r02/ncu_full_summary.json)"}
         t_unc = timeit(lambda: eng.uncertainty_stage(vis_hidden), iters=3)
         flops = 2.0 * B * n_vis * cfg.d_model * cfg.vocab
         out["uncertainty_stage"] = {"bound": "tensor", "images": B, "ms": round(t_unc * 1e3, 3),

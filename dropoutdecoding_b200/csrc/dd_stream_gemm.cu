@@ -449,6 +449,10 @@ static SgPlan sg_plan(int M, int N, int K, int epi) {
   const int total_kb = K / SG_BK;
   const int fmax = swiglu ? 128 : 256;
   s.S = 1;
+  int force_s = 0;
+#ifdef DD_SG_EXPERIMENT
+  if (const char* e = getenv("DD_SG_S")) force_s = atoi(e);
+#endif
   for (int S = 1; S <= 4; S *= 2) {
     if (total_kb % S) break;
     s.S = S;
@@ -456,7 +460,7 @@ static SgPlan sg_plan(int M, int N, int K, int epi) {
     int F = (ceil_div(N, slots > 0 ? slots : 1) + 15) / 16 * 16;
     if (F > fmax) F = fmax;
     s.F = F;
-    if ((swiglu ? 2 * F : F) >= 128 || swiglu) break;              // (SwiGLU pairs gate / up columns: never split)
+    if (force_s ? (S == force_s || swiglu) : ((swiglu ? 2 * F : F) >= 128 || swiglu)) break;   // (SwiGLU pairs gate / up columns: never split)
   }
   s.Fw = swiglu ? 2 * s.F : s.F;
   s.T = ceil_div(N, s.F);

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel launches,
-total device time and share.  Usage: python tools/summarize_launches.py launches.csv [> summary.md]"""
+total device time and share.  Usage: python tools/summarize_launches.py launches.csv [--from-first dd::] [> summary.md]
+(--from-first PREFIX drops everything before the first kernel whose name starts with PREFIX, e.g. weight initialisation)"""
 import collections
 import csv
 import re
@@ -16,6 +17,10 @@ for r in csv.DictReader(lines):
             ns *= 1e3
         name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")
         rows.append((name, ns))
+if "--from-first" in sys.argv:
+    pre = sys.argv[sys.argv.index("--from-first") + 1]
+    first = next((i for i, (n, _) in enumerate(rows) if n.startswith(pre)), 0)
+    rows = rows[first:]
 tot = sum(ns for _, ns in rows)
 agg = collections.OrderedDict()
 for name, ns in rows:
