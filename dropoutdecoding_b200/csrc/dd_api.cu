@@ -46,16 +46,21 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
   return DD_OK;
 }
 
+// 0 / 1 once decided; -1 = not yet (then the DD_PDL environment variable, else off)
+static int g_pdl = -1;
 bool pdl_enabled() {
-  static const bool on = [] {
-    // Off by default: inside a CUDA graph the kernel-to-kernel gap is already ~1 us and programmatic
-    // launch measured 1-5 % SLOWER on the 7B decode step (profiles/README.md); DD_PDL=1 turns it on.
+  if (g_pdl < 0) {
     const char* e = getenv("DD_PDL");
-    return e && e[0] == '1';
-  }();
-  return on;
+    g_pdl = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl == 1;
 }
 }  // namespace dd
 
 extern "C" int dd_version(void) { return 100; }  // 0.1.0
+extern "C" int dd_set_chain_launch(int on) {
+  const int was = dd::pdl_enabled() ? 1 : 0;
+  dd::g_pdl = on ? 1 : 0;
+  return was;
+}
 extern "C" const char* dd_last_error(void) { return dd::g_last_error.c_str(); }

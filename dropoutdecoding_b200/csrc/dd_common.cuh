@@ -48,7 +48,10 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // while its predecessor is still running, do work that does not depend on it (address setup, the
 // first batch of weight loads) and then block in pdl_wait() until the predecessor has completed
 // and flushed.  Rule: nothing written by an earlier kernel is touched before pdl_wait(), and
-// nothing is written before it either.  Opt-in with DD_PDL=1 (measured: no gain inside CUDA graphs).
+// nothing is written before it either.  The host chooses per pass (dd_set_chain_launch): it pays where the
+// dependent kernel has a deep prefetch to run ahead with -- dd_stream_gemm fills its whole shared-memory ring
+// with weight tiles before the wait (7B pass of 56 rows: 4.99 -> 4.55 ms) -- and costs 1-3 % on the
+// register-streamed skinny GEMMs of a 4-row pass, where it stays off (profiles/README.md).
 // ---------------------------------------------------------------------------------------------
 bool pdl_enabled();
 

@@ -226,13 +226,40 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     long long dbg_wait = 0;
     const long long dbg_t0 = clock64();
 #endif
-    for (int round = 0; round * p.stages < n_stage_total; ++round) {
+    // one pipeline stage: its expect_tx, then the W boxes and / or the x boxes of its bks k-blocks
+    auto fill = [&](int i, int stage, bool arm, bool do_w, bool do_x) {
+      const int t = i / n_stage_kb, sk = i - t * n_stage_kb;
+      const int tile = cta + t * p.G;
+      const uint32_t dst = ring + stage * stage_bytes, bar = bar_full + 8 * stage;
+      if (arm) mbar_expect_tx(bar, stage_tx);
+      for (int b = 0; b < p.bks; ++b) {
+        const int kcol = ((rank * n_stage_kb + sk) * p.bks + b) * SG_BK;
+        if (do_x) tma_load_2d(dst + b * p.x_kb, &tmap_x, bar, kcol, 0);
+        if (do_w) {
+          const uint32_t wdst = dst + p.x_bytes + b * p.w_kb;
+          tma_load_2d_hint(wdst, &tmap_w, bar, kcol, tile * p.F, pol);      // (rows past the end of W are zero-filled)
+          if (swiglu)                                                       // [F gate rows | F up rows]
+            tma_load_2d_hint(wdst + p.F * 128, &tmap_w, bar, kcol, p.N + tile * p.F, pol);
+        }
+      }
+    };
+    // Round 0 (the ring is empty).  The weights do not depend on the previous kernel of the stream: under a
+    // programmatic dependent launch the whole ring of W tiles is put in flight BEFORE griddepcontrol.wait, the
+    // activation tiles after it.
+    for (int stage = warp; stage < p.stages && stage < n_stage_total; stage += SG_PROD_WARPS) {
+      if (elect_one()) fill(stage, stage, true, true, false);
+      __syncwarp();
+    }
+    pdl_wait();
+    for (int stage = warp; stage < p.stages && stage < n_stage_total; stage += SG_PROD_WARPS) {
+      if (elect_one()) fill(stage, stage, false, false, true);
+      __syncwarp();
+    }
+    for (int round = 1; round * p.stages < n_stage_total; ++round) {
       const uint32_t phase = (uint32_t)(round & 1);
       for (int stage = warp; stage < p.stages; stage += SG_PROD_WARPS) {
         const int i = round * p.stages + stage;
         if (i >= n_stage_total) break;
-        const int t = i / n_stage_kb, sk = i - t * n_stage_kb;
-        const int tile = cta + t * p.G;
 #ifdef DD_SG_EXPERIMENT
         const long long dbg_w0 = clock64();
 #endif
@@ -240,26 +267,17 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 #ifdef DD_SG_EXPERIMENT
         dbg_wait += clock64() - dbg_w0;
 #endif
-        if (elect_one()) {
-          const uint32_t dst = ring + stage * stage_bytes, bar = bar_full + 8 * stage;
-          mbar_expect_tx(bar, stage_tx);
-          for (int b = 0; b < p.bks; ++b) {
-            const int kcol = ((rank * n_stage_kb + sk) * p.bks + b) * SG_BK;
-            tma_load_2d(dst + b * p.x_kb, &tmap_x, bar, kcol, 0);
-            const uint32_t wdst = dst + p.x_bytes + b * p.w_kb;
-            tma_load_2d_hint(wdst, &tmap_w, bar, kcol, tile * p.F, pol);      // (rows past the end of W are zero-filled)
-            if (swiglu)                                                       // [F gate rows | F up rows]
-              tma_load_2d_hint(wdst + p.F * 128, &tmap_w, bar, kcol, p.N + tile * p.F, pol);
-          }
-        }
+        if (elect_one()) fill(i, stage, true, true, true);
         __syncwarp();
       }
     }
+    pdl_trigger_stream_tail();   // every load of this CTA is issued: the next kernel of the chain may take its place
 #ifdef DD_SG_EXPERIMENT
     if (p.dbg && warp == 0 && lane == 0 && rank == 0) { p.dbg[cta * 16 + 0] = clock64() - dbg_t0; p.dbg[cta * 16 + 1] = dbg_wait; }
 #endif
   } else if (warp == SG_MMA_WARP) {
     // =========================== MMA issuer ===========================
+    pdl_wait();
     const uint32_t idesc = make_idesc_bf16(SG_BM, p.Fw);
     int stage = 0, acc_stage = 0;
     uint32_t phase = 0, acc_phase = 0;
@@ -304,6 +322,7 @@ stream_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 #endif
   } else {
     // =========================== epilogue (warps 5..12) ===========================
+    pdl_wait();   // (reads the residual, writes y)
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int g = (warp - SG_EPI_WARP0) >> 2;     // warp group 0 / 1
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -575,23 +594,27 @@ extern "C" int dd_stream_gemm(const void* x, const void* w, const void* residual
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
-  if (s.S == 1) {
-    stream_gemm_kernel<<<s.G, SG_THREADS, s.smem, (cudaStream_t)stream>>>(tw, tx, p);
-    DD_CHECK_LAUNCH();
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(s.G * s.S);
-    cfg.blockDim = dim3(SG_THREADS);
-    cfg.dynamicSmemBytes = s.smem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = s.S;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    DD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, stream_gemm_kernel, tw, tx, p));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(s.G * s.S);
+  cfg.blockDim = dim3(SG_THREADS);
+  cfg.dynamicSmemBytes = s.smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (s.S > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = s.S;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  DD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, stream_gemm_kernel, tw, tx, p));
   return DD_OK;
 }

@@ -173,6 +173,8 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         self.gemm_backend = gemm_backend or os.environ.get("DD_GEMM", "auto")
         if self.gemm_backend not in ("auto", "stream", "library", "skinny"):
             raise ValueError(self.gemm_backend)
+        # programmatic dependent launch of the pass kernels: None = per pass (on for dd_stream_gemm passes); DD_PDL=0/1 pins it
+        self.chain_launch = {"0": False, "1": True}.get(os.environ.get("DD_PDL", ""), None)
         self.attn_splits = attn_splits  # None: chosen per pass from the measured sweep (_alloc_pass); tests pin it
         self.seq_base = int(seq_base)   # global index of sequence 0 (batch sharded over GPUs)
         self.vote_on = vote_on          # "hidden": InstructBLIP votes on the argmax of the final hidden state
@@ -268,6 +270,12 @@ class DropoutDecodeEngine(SpeculativeSchedules):
             return 16 < rows <= 32
         return False
 
+    def _set_chain(self, rows: int) -> None:
+        """Programmatic dependent launch for the kernels of the pass that follows: it pays where dd_stream_gemm can
+        prefetch its ring of weight tiles under the previous kernel's tail (7B, 56 rows: 5.01 -> 4.57 ms per pass) and
+        costs 3-4 % on the register-streamed skinny GEMMs of a 4-row pass."""
+        ops.set_chain_launch(self._use_stream(rows) if self.chain_launch is None else self.chain_launch)
+
     def _linear(self, x, w, epi, out, residual=None):
         self.launches_per_step += 1
         rows = x.shape[0]
@@ -303,6 +311,7 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         cfg, B, M = self.cfg, self.B, pb.M
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         rows = B * M
+        self._set_chain(rows)
         ops.embed_gather(self.w.embed, self.cur_token, M, pb.x)
         x, x2 = pb.x, pb.x2
         if rows <= 32 and not self._use_stream(rows):

@@ -40,6 +40,12 @@ def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
+def set_chain_launch(on: bool) -> bool:
+    """dd_set_chain_launch: programmatic dependent launch for the dd_* kernels launched from now on (returns the
+    previous setting)."""
+    return bool(_lib.load().dd_set_chain_launch(1 if on else 0))
+
+
 def mask_words(n_vis: int) -> int:
     return (n_vis + 31) // 32
 

@@ -205,6 +205,7 @@ class SpeculativeSchedules:
         self._row_tok_c[K:] = self._g_tok
         self._row_pos_c[:K] = self.seq_lens
         self._row_pos_c[K:] = self._seq_p1
+        self._set_chain(M)
         ops.embed_gather(self.w.embed, self._row_tok_c, 1, pd.x)
         x, x2 = pd.x, pd.x2
         for l, lw in enumerate(self.w.layers):
@@ -395,6 +396,7 @@ class SpeculativeSchedules:
             self._len_extra[:, K:] = fb_i[:, None]      # the spec slots of a repeating sequence see the row committed ahead
         # ---- the pass
         rows = B * M
+        self._set_chain(rows)
         ops.embed_gather(self.w.embed, self._row_tok, 1, pe.x)
         x, x2 = pe.x, pe.x2
         for l, lw in enumerate(self.w.layers):

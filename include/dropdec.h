@@ -51,6 +51,14 @@ typedef void* dd_stream_t; /* cudaStream_t */
 int dd_version(void);
 const char* dd_last_error(void);
 
+/* Programmatic dependent launch for the kernels of a decoder pass (host choice, process-wide; returns the previous
+ * setting).  On: every dd_* kernel launched from now on may become resident while its predecessor in the stream is
+ * still draining and run its independent prologue -- dd_stream_gemm puts its whole ring of weight tiles in flight --
+ * before it waits for the predecessor's results (griddepcontrol.wait).  Results are identical either way.  Default:
+ * the DD_PDL environment variable ("1" = on), else off.  No reference counterpart (the reference's forward is a
+ * sequence of stream-ordered torch kernels, models/llama.py:16-69). */
+int dd_set_chain_launch(int on);
+
 /* ------------------------------------------------------------------------------------------
  * (1) Visual-token uncertainty stage.
  * Replaces: lm_head over the visual rows + get_image_logits (models/llava.py:412-426),

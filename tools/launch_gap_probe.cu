@@ -57,6 +57,21 @@ __global__ void k_spin(long long ns, long long* out, int slot) {
   while (t - t0 < ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
   if (threadIdx.x == 0 && out) { out[(size_t)slot * 512 + 2 * blockIdx.x] = t0; out[(size_t)slot * 512 + 2 * blockIdx.x + 1] = t; }
 }
+// the same busy kernel as a programmatic dependent launch: entry stamp, griddepcontrol.wait, post-wait stamp, spin, exit
+// stamp.  trigger: 0 = never (implicit at exit), 1 = at entry, 2 = after the spin
+__global__ void k_spin_pdl(long long ns, long long* out, int slot, int trigger) {
+  long long te, t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(te) :: "memory");
+  if (trigger == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0) :: "memory");
+  long long t = t0;
+  while (t - t0 < ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+  if (trigger == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0 && out) {
+    out[(size_t)slot * 512 + 3 * blockIdx.x] = te; out[(size_t)slot * 512 + 3 * blockIdx.x + 1] = t0; out[(size_t)slot * 512 + 3 * blockIdx.x + 2] = t;
+  }
+}
 __global__ void k_store(float* out, int n_per_thread) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int j = 0; j < n_per_thread; ++j) out[i + (size_t)j * gridDim.x * blockDim.x] = (float)j;
@@ -137,6 +152,42 @@ int main() {
           gap += (first_entry - last_exit) * 1e-3;
         }
         printf("{\"probe\": \"spin_%lldus_smem%dKB\", \"us_per_node\": %.2f, \"gap_last_exit_to_first_entry_us\": %.2f}\n", ns / 1000, smem / 1024, us, gap / 31);
+      }
+    }
+  }
+  {
+    long long* stamps;
+    CK(cudaMalloc(&stamps, 64 * 512 * 8));
+    CK(cudaFuncSetAttribute(k_spin_pdl, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (long long ns : {2000ll, 20000ll}) {
+      for (int smem : {0, 200 * 1024}) {
+        for (int trigger : {0, 1, 2}) {
+          CK(cudaMemset(stamps, 0, 64 * 512 * 8));
+          int slot = 0;
+          cudaLaunchConfig_t cfg{};
+          cfg.gridDim = dim3(148); cfg.blockDim = dim3(416); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[0].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          const float us = time_graph(st, 32, [&] { CK(cudaLaunchKernelEx(&cfg, k_spin_pdl, ns, stamps, slot, trigger)); slot = (slot + 1) % 32; });
+          std::vector<long long> h(32 * 512);
+          CK(cudaMemcpy(h.data(), stamps, 32 * 512 * 8, cudaMemcpyDeviceToHost));
+          double gap = 0, early = 0;
+          for (int k = 1; k < 32; ++k) {
+            long long last_exit = 0, first_go = h[k * 512 + 1], first_entry = h[k * 512];
+            for (int c = 0; c < 148; ++c) {
+              last_exit = std::max(last_exit, h[(k - 1) * 512 + 3 * c + 2]);
+              first_go = std::min(first_go, h[k * 512 + 3 * c + 1]);
+              first_entry = std::min(first_entry, h[k * 512 + 3 * c]);
+            }
+            gap += (first_go - last_exit) * 1e-3;
+            early += (last_exit - first_entry) * 1e-3;
+          }
+          printf("{\"probe\": \"pdl_spin_%lldus_smem%dKB_trigger%d\", \"us_per_node\": %.2f, \"gap_last_exit_to_first_go_us\": %.2f, "
+                 "\"entry_before_prev_exit_us\": %.2f}\n", ns / 1000, smem / 1024, trigger, us, gap / 31, early / 31);
+          fflush(stdout);
+        }
       }
     }
   }
