@@ -2,40 +2,35 @@
 // Replaces lm_head over the visual rows + get_image_logits + get_topk_token_id +
 // calculate_vision_uncertainty (models/llava.py:412-441, 710-756), see include/dropdec.h.
 //
-// logits[i,v] = <h_vis[i,:], w_lm[v,:]> is a [n_vis x vocab] GEMM (151 GFLOP per LLaVA-1.5 image)
-// whose result the reference materialises in fp32 (74 MB + >=6 same-size temporaries).  Here the
-// logits only ever exist as TMEM accumulators:
+// logits[i,v] = <h_vis[i,:], w_lm[v,:]> is a [rows x vocab] GEMM (151 GFLOP per LLaVA-1.5 image) whose result the
+// reference materialises in fp32 (74 MB + >=6 same-size temporaries per image).  The statistics need the logits
+// three times -- the row normaliser Z_i must be complete before p = exp(l - m)/Z exists, and p_avg[v] = mean_i p[i,v]
+// (a column reduction over every row of the image) must be complete before sum_v p[i,v] log p_avg[v] can be
+// formed -- but the GEMM is needed ONCE: round 1 / early round 2 recomputed it per sweep (two tensor-core sweeps,
+// 0.20 of the tensor peak); now the one GEMM sweep parks its logits in a scratch ("stash", bf16 when the caller asks
+// for the reference's bf16-rounded logits, else fp32 -- lossless either way) and the later passes are element-wise
+// kernels over that stash, which is L2-sized for a few images (37 MB per LLaVA-1.5 image in bf16).
 //
-//   work item = (image, vocab strip of BN=96 columns); the CTA holds the strip for ALL visual rows
-//   of the image at once -- NUM_MT row tiles of 128 -> NUM_MT*96 <= 480 of the 512 TMEM columns.
-//   That is what makes the epistemic term single-sweep: it needs p_avg[v] = mean_i p[i,v], a
-//   column reduction over every row of the image, before sum_v p[i,v] log(p_avg[v]) can be formed.
-//
-//   warps 8-10: TMA producers.  Per k-block (64 bf16 = one 128B-swizzle row) the CTA ingests the W strip tile
-//              [96 x 64] (HBM stream, 4-deep ring) and NUM_MT activation tiles [128 x 64] (L2-resident, 2 k-blocks
-//              deep): 92 KB per k-block, 82 B/clk at the rate the tensor core consumes them.  Round 1 fed four of the
-//              five activation tiles through cp.async because "an SM ingests 35 B/clk through TMA"; that ceiling was
-//              the issue loop of ONE producer thread (a barrier wait + a copy per box: ~350-670 cycles each,
-//              tools/tma_probe2.cu) -- three producer warps with two boxes each per k-block keep the ring full
-//              (measured: 97-126 B/clk per SM from four issuing warps).  Every ring slot belongs to one warp.
-//   warp 11  : MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128 N=96 K=16,
-//              both operands K-major SWIZZLE_128B; slots are released with tcgen05.commit.
-//   warps 0-7: epilogue, two warps per TMEM lane quarter: warp w reads lanes 32*(w&3).. and the 48 columns
-//              [48*(w>>2), +48) of the strip.  tcgen05.ld 32x32b: one thread = one visual row, so softmax
-//              statistics are thread-local; the column sums are a butterfly over the warp plus 4 smem rows.  The two
-//              halves never talk to each other: every per-row partial simply exists once per (CTA, half).
-//
-// Two sweeps of the same pipeline (the row normaliser Z_i must be complete before p exists):
-//   STATS : per row running max / sum-exp, and the row's maximum inside every half strip  (sweep 1)
-//   FUSED : p = exp(l - m)/Z;  A_i = sum p log(p+eps), Q_i = sum (p-1/V)^2, column sums ->
-//           log(p_avg+eps) -> C_i = sum p log(p_avg+eps)                        (sweep 2)
-//   finalize: alea = -A, epi = A - C, var = Q/(V-1).
-// Top-k ids without per-thread sorted lists in the hot loop: tau_i = the k-th largest of row i's per-half-strip
-// maxima is a lower bound of its k-th largest logit, so sweep 2 (which recomputes bit-identical logits)
-// only has to append the few elements >= tau_i to a per-row candidate list (one predictable compare per
-// element); the finalize kernel sorts the candidates (value descending, id ascending).  Without ties at
-// most 48*k elements can pass the threshold; the list holds 96*k + 64 and an overflow is reported.
-// Algorithmic FLOPs = 2*n_vis*d*V per image, counted once although two sweeps run.
+//   logits_stats_kernel   persistent tcgen05 GEMM, CTA tile 256 rows x 256 vocabulary columns (two 128-lane TMEM
+//                         accumulators of 256 columns = the whole TMEM), K in 64-wide blocks through a 3-stage TMA
+//                         ring (A tile 32 KB + W tile 32 KB per block: 62 B/clk per SM at the tensor rate, under the
+//                         ~100 B/clk an SM ingests).  M=128 N=256 K=16 MMAs run at the full tensor rate (N=96 of
+//                         the old strip design issued at 56 instead of 48 clk).  Rows of all images of a group are
+//                         one M dimension, so a batch has no per-image tile waste.  Epilogue (8 warps, one thread =
+//                         one row): running max / sum-exp of the row over the tile's 256 columns, the row's maximum
+//                         inside every 64-column chunk, and the logits themselves -> stash.
+//   stats_finalize        per row: merge the per-tile (m, sum-exp) partials -> (m, 1/Z); tau = k-th largest chunk
+//                         maximum (a lower bound of the row's k-th largest logit).
+//   entropy_kernel        element-wise over the stash, CTA = (image, strip of 256 columns) over ALL rows of the image:
+//                         pass A: p, A_i = sum p log(p+eps), Q_i = sum (p-1/V)^2, the column sums of p, and the few
+//                         logits >= tau_i appended to the row's top-k candidate list (at most 64*k without ties; the
+//                         list holds 96*k + 64, an overflow is reported); then log(p_avg + eps) of the strip's
+//                         columns (the CTA has seen every row); pass B over the same (now L2-hot) logits:
+//                         C_i = sum_v p log(p_avg+eps).  MUFU-bound (3 per logit).
+//   fused_finalize        alea = -A, epi = A - C, var = Q/(V-1); top-k ids = the candidates sorted (value
+//                         descending, id ascending).
+// Images are processed in groups whose stash stays <= ~600 MB.  Every partial is summed in a fixed order: results
+// are bit-identical run to run.  Algorithmic FLOPs = 2*n_vis*d*V per image.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -44,38 +39,31 @@
 #include "dd_common.cuh"
 #include "dd_tcgen05.cuh"
 
-#ifdef DD_UNC_EXPERIMENT
-long long* g_unc_dbg = nullptr;
-#endif
-
 namespace dd {
 
-constexpr int BM = 128, BN = 96, BK = 64, UMMA_K = 16;
-constexpr int BNH = BN / 2;              // columns per epilogue half
-constexpr int kSlotBytes = BM * BK * 2;  // 16 KB: one [128 x 64] bf16 activation tile
-constexpr int kWBytes = BN * BK * 2;     // 12 KB: one [96 x 64] bf16 W tile
-constexpr int kMaxMT = 5;                // row tiles of 128 per image (n_vis <= 640)
-constexpr int kActStages = 2;            // activation ring: k-blocks in flight
-constexpr int kWStages = 4;              // W ring
-constexpr int kEpiWarps = 8;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int GM = 256;                  // rows per CTA tile (two accumulators of BM)
+constexpr int GN = 256;                  // vocabulary columns per CTA tile (MMA N)
+constexpr int kChunk = 64;               // columns per "row maximum" chunk (top-k threshold granularity)
+constexpr int kATile = GM * BK * 2;      // 32 KB
+constexpr int kWTile = GN * BK * 2;      // 32 KB
+constexpr int kStageBytes = kATile + kWTile;
+constexpr int kStages = 3;
+constexpr int kProdWarpA = 0, kProdWarpW = 1, kMmaWarp = 2, kEpiWarp0 = 4, kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kHalfThreads = kEpiThreads / 2;
-constexpr int kProdWarp0 = kEpiWarps, kProdWarps = 3;
-constexpr int kMmaWarp = kProdWarp0 + kProdWarps;
-constexpr int kUncThreads = (kMmaWarp + 1) * 32;
-// barriers: act_full[kActStages] | act_empty[kActStages][kMaxMT] | w_full[kWStages] | w_empty[kWStages] | tmem_full |
-//           tmem_empty[kMaxMT]
-constexpr int kNumBars = kActStages + kActStages * kMaxMT + 2 * kWStages + 1 + kMaxMT;
+constexpr int kGemmThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kNumBars = 2 * kStages + 2;   // full[kStages] | empty[kStages] | tmem_full | tmem_empty
 constexpr int kTmemCols = 512;
+constexpr size_t kGemmSmem = 1024 + (size_t)kStages * kStageBytes + kNumBars * 8 + 16;
+constexpr int kRowsCap = 4608;           // rows per image group (8 LLaVA-1.5 images): bounds the stash
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kEps = 1e-10f;  // models/llava.py:735,739
 
-constexpr uint32_t kIdesc = make_idesc_bf16(BM, BN);
+constexpr uint32_t kIdesc = make_idesc_bf16(BM, GN);
 
-// The epilogue warps are alone on their scheduler (two warps per sub-partition), so the softmax sweeps are bound by
-// instructions issued per element.  exp2f / __logf carry a range fix-up for denormal results / arguments (4 extra
-// instructions each); here 2^x below 2^-126 may flush to zero (a probability < 1e-38) and the log argument is
-// >= 1e-10, so the bare MUFU forms are exact enough and identical in both sweeps.
+// exp2f / __logf carry a range fix-up for denormal results / arguments (4 extra instructions each); here 2^x below
+// 2^-126 may flush to zero (a probability < 1e-38) and the log argument is >= 1e-10, so the bare MUFU forms are
+// exact enough and identical in every pass.
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -86,106 +74,56 @@ __device__ __forceinline__ float ln_ftz(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y * 0.6931471805599453f;
 }
-__device__ __forceinline__ void half_bar_sync(int half) {
-  asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(kHalfThreads) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------
 struct UncParams {
-  int n_images, n_vis, d, vocab, topk, round_bf16;
-  int n_strips, parts;     // strips per image; CTAs per image.  Per-row partials exist per (CTA, half): 2*parts;
-                           // strip maxima per half strip: 2*n_strips
-  float* part_stats;       // [img][2*parts][n_vis][2]    (m, z)
-  float* strip_max;        // [img][2*n_strips][n_vis]    STATS output: row maximum inside each half strip
-  const float* tau;        // [img][n_vis]                candidate threshold (FUSED / COLSUM input)
-  int32_t* cand_cnt;       // [img][n_vis]
-  float* cand_val;         // [img][n_vis][cap]
-  int32_t* cand_idx;       // [img][n_vis][cap]
+  int R;                   // rows of this image group (n_img * n_vis)
+  int n_img, n_vis, d, vocab, topk, round_bf16;
+  int n_cs, n_rg;          // column strips of GN, row groups of GM (over R)
+  int n_es;                // column strips of EC (element-wise passes)
+  int Vs;                  // stash row length = n_cs * GN
+  void* stash;             // [R][Vs] bf16 (round_bf16) or fp32
+  float* part_stats;       // [R][n_cs][2]            (m, sum-exp) of the row inside the strip
+  float* strip_max;        // [R][n_cs * GN/kChunk]   row maximum inside each 64-column chunk
+  float* row_stats;        // [R][4]                  (m, 1/Z, tau = top-k candidate threshold, -)
+  int32_t* cand_cnt;       // [R]
+  float* cand_val;         // [R][cap]
+  int32_t* cand_idx;       // [R][cap]
   int cap;
-  const float* row_stats;  // [img][n_vis][2]             (m, 1/Z)  FUSED input
-  float* part_acq;         // [img][2*parts][n_vis][3]    (A, Q, C) FUSED output
-  int n_chunks;            // row chunks of kMaxMT*128 rows per image (> 1 when n_vis > 640)
-  float* colpart;          // [img][chunk][n_strips*BN]   column sums of p over one row chunk (COLSUM -> logpavg)
-  float* logpavg;          // [img][n_strips*BN]          log(p_avg + eps)                    (CROSS input)
-#ifdef DD_UNC_EXPERIMENT
-  long long* dbg;          // [ctas][8] cycle counters (experiment builds)
-#endif
+  float* part_aq;          // [n_es][R][2]            (A, Q) of the row inside the strip
+  float* part_c;           // [n_es][R]               C of the row inside the strip
   int32_t* overflow;       // [1] rows whose top-k candidate list overflowed (ties at the threshold): the ids of such a
                            //     row may miss a tied candidate, so the host treats a non-zero count as an error
+  int reset_overflow;      // first group of a call
 };
 
-// Rare path of sweep 2 (whole warp, warp-uniform call): some row of this warp has a top-k candidate inside the
-// 16 columns at `taddr`.  Re-reads them from TMEM 8 at a time and appends every logit >= the row's threshold.
-struct CandSink {
-  int32_t* cnt;
-  float* val;
-  int32_t* idx;
-  int cap, vocab, round_bf16;
-};
-__device__ __noinline__ void append_candidates(const CandSink p, uint32_t taddr, float tau, int col_base, size_t r) {
-#pragma unroll 1
-  for (int j = 0; j < 2; ++j) {
-    float v[8];
-    tmem_ld8(taddr + j * 8, v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float x = p.round_bf16 ? bf16_round(v[i]) : v[i];
-      const int col = col_base + j * 8 + i;
-      if (col < p.vocab && x >= tau) {
-        const int slot = atomicAdd(&p.cnt[r], 1);
-        if (slot < p.cap) {
-          p.val[r * p.cap + slot] = x;
-          p.idx[r * p.cap + slot] = col;
-        }
-      }
-    }
-  }
-}
-
-// n_vis <= 640: STATS, FUSED.  Larger images (LLaVA-NeXT anyres, up to ~2.9k rows) do not fit the 512
-// TMEM columns, so the column mean needs its own sweep: STATS, COLSUM (p, A, Q, per-chunk column sums),
-// a tiny log(p_avg) kernel, CROSS (C = sum_v p log(p_avg+eps)).
-enum { MODE_STATS = 0, MODE_FUSED = 1, MODE_COLSUM = 2, MODE_CROSS = 3 };
-
-template <int NUM_MT, int MODE, int KT>
-__global__ void __launch_bounds__(kUncThreads, 1)
-uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                   const UncParams p) {
+// ------------------------------------------------------------------------------------------
+// The GEMM sweep
+// ------------------------------------------------------------------------------------------
+template <bool BF16_STASH>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+logits_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const UncParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles (the dynamic smem base is only 16-byte aligned by contract)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* w_ring_p = smem + kActStages * kMaxMT * kSlotBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring_p + kWStages * kWBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
-  float* s_col = reinterpret_cast<float*>(tmem_slot + 4);  // [4][BN]
-  float* s_logp = s_col + 4 * BN;                            // [BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.y / p.n_chunks, chunk = blockIdx.y % p.n_chunks, part = blockIdx.x;
-  const int row0 = chunk * (kMaxMT * BM);  // first row of this CTA's row chunk
-  const int spc = (p.n_strips + p.parts - 1) / p.parts;
-  const int strip_beg = part * spc;
-  const int strip_end = min(p.n_strips, strip_beg + spc);
   const int num_kb = p.d / BK;
-
-  const uint32_t act_ring = smem_u32(smem), w_ring = smem_u32(w_ring_p);
-  const uint32_t bar_afull = smem_u32(bars), bar_aempty = bar_afull + 8 * kActStages;
-  const uint32_t bar_wfull = bar_aempty + 8 * kActStages * kMaxMT, bar_wempty = bar_wfull + 8 * kWStages;
-  const uint32_t bar_tfull = bar_wempty + 8 * kWStages, bar_tempty = bar_tfull + 8;
-  // producer warp pw owns activation tiles 2*pw and 2*pw + 1 (those below NUM_MT); the last producer also owns W
-  constexpr int kActProducers = (NUM_MT + 1) / 2;
+  const int n_tiles = p.n_cs * p.n_rg;
+  const uint32_t ring = smem_u32(smem);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 8;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kActStages; ++i) {
-      mbar_init(bar_afull + 8 * i, kActProducers);  // one arrive.expect_tx per producer warp that owns activation tiles
-      for (int m = 0; m < kMaxMT; ++m) mbar_init(bar_aempty + 8 * (i * kMaxMT + m), 1);
-    }
-    for (int i = 0; i < kWStages; ++i) {
-      mbar_init(bar_wfull + 8 * i, 1);
-      mbar_init(bar_wempty + 8 * i, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bar_full + 8 * i, 2);    // one arrive.expect_tx by each of the two producer warps
+      mbar_init(bar_empty + 8 * i, 1);   // tcgen05.commit
     }
     mbar_init(bar_tfull, 1);
-    for (int i = 0; i < kMaxMT; ++i) mbar_init(bar_tempty + 8 * i, kEpiThreads);
+    mbar_init(bar_tempty, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {  // TMEM: 512 columns, whole warp, then give the permit back
@@ -199,334 +137,132 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= kProdWarp0 && warp < kMmaWarp) {
-    // =========================== TMA producers (warp-converged, one elected lane issues) =========
-    const int pw = warp - kProdWarp0;
-    const int mt0 = 2 * pw, n_mine = max(0, min(NUM_MT - mt0, 2));
-    const bool w_mine = pw == kProdWarps - 1;
-    if (elect_one()) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
-    }
+  // tile t = (column strip t / n_rg, row group t % n_rg): the row groups of one W strip run at the same time on
+  // neighbouring CTAs, so the strip is read from HBM once and from L2 after that
+  if (warp == kProdWarpA || warp == kProdWarpW) {
+    // =========================== TMA producers (one elected lane issues) ===========================
+    const bool is_a = warp == kProdWarpA;
+    if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(is_a ? &tmap_a : &tmap_w) : "memory");
     uint32_t g = 0;
-    for (int strip = strip_beg; strip < strip_end; ++strip) {
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int cs = t / p.n_rg, rg = t - cs * p.n_rg;
       for (int kb = 0; kb < num_kb; ++kb, ++g) {
-        const uint32_t as = g % kActStages, aphase = (g / kActStages) & 1;
-        if (w_mine) {
-          const uint32_t ws = g % kWStages, wphase = (g / kWStages) & 1;
-          mbar_wait(bar_wempty + 8 * ws, wphase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(bar_wfull + 8 * ws, kWBytes);
-            tma_load_2d(w_ring + ws * kWBytes, &tmap_w, bar_wfull + 8 * ws, kb * BK, strip * BN);
+        const uint32_t s = g % kStages, phase = (g / kStages) & 1;
+        mbar_wait(bar_empty + 8 * s, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t dst = ring + s * kStageBytes, bar = bar_full + 8 * s;
+          if (is_a) {      // rows past R are zero-filled by the tensor map
+            mbar_expect_tx(bar, kATile);
+            tma_load_2d(dst, &tmap_a, bar, kb * BK, rg * GM);
+          } else {         // rows past the vocabulary are zero-filled
+            mbar_expect_tx(bar, kWTile);
+            tma_load_2d(dst + kATile, &tmap_w, bar, kb * BK, cs * GN);
           }
-          __syncwarp();
         }
-        if (n_mine > 0) {
-          for (int j = 0; j < n_mine; ++j) mbar_wait(bar_aempty + 8 * (as * kMaxMT + mt0 + j), aphase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(bar_afull + 8 * as, (uint32_t)(n_mine * kSlotBytes));
-            for (int j = 0; j < n_mine; ++j)   // rows past n_vis are zero-filled by the tensor map
-              tma_load_3d(act_ring + (as * kMaxMT + mt0 + j) * kSlotBytes, &tmap_a, bar_afull + 8 * as, kb * BK,
-                          row0 + (mt0 + j) * BM, img);
-          }
-          __syncwarp();
-        }
+        __syncwarp();
       }
     }
   } else if (warp == kMmaWarp) {
-    // =========================== MMA issuer (warp-converged, one elected lane issues) ==========
-    // The issuing thread must stay ahead of a tensor pipe that retires one M128 x N96 x K16 MMA every ~57
-    // cycles, so the body of a k-block is instantiated for each (activation stage, W stage) combination:
-    // every shared-memory descriptor is then "ring base + compile-time constant", one elected region issues
-    // all NUM_MT x 4 MMAs of the k-block, and the per-k-block cost is two mbarrier waits.
-#ifdef DD_UNC_EXPERIMENT
-    long long dbg_w = 0, dbg_a = 0, dbg_t = 0;
-    const long long dbg_t0 = clock64();
-#endif
-    auto issue_group = [&](auto AS, auto WS, uint32_t aphase, uint32_t wphase, bool first_kb, bool last_kb,
-                           uint32_t tempty_parity) {
-      constexpr uint32_t as = decltype(AS)::value, ws = decltype(WS)::value;
-#ifdef DD_UNC_EXPERIMENT
-      const long long c0 = clock64();
-#endif
-      mbar_wait(bar_wfull + 8 * ws, wphase);
-#ifdef DD_UNC_EXPERIMENT
-      const long long c1 = clock64();
-#endif
-      mbar_wait(bar_afull + 8 * as, aphase);
-#ifdef DD_UNC_EXPERIMENT
-      const long long c2 = clock64();
-#endif
-      if (first_kb) {       // the epilogue must have drained the previous strip's accumulators
-#pragma unroll
-        for (int mt = 0; mt < NUM_MT; ++mt) mbar_wait(bar_tempty + 8 * mt, tempty_parity);
-      }
-#ifdef DD_UNC_EXPERIMENT
-      dbg_w += c1 - c0; dbg_a += c2 - c1; dbg_t += clock64() - c2;
-#endif
+    // =========================== MMA issuer (one elected lane issues) ===========================
+    uint32_t g = 0, it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int cs = t / p.n_rg, rg = t - cs * p.n_rg;
+      const int nacc = (rg * GM + BM < p.R) ? 2 : 1;   // the second accumulator's rows may all lie past R
+      mbar_wait(bar_tempty, (it & 1) ^ 1);             // the epilogue has drained the previous tile
       tc_fence_after();
-      if (elect_one()) {
-        const uint64_t b_desc = make_smem_desc(w_ring + ws * kWBytes);
-        const uint32_t acc = first_kb ? 0u : 1u;
-#pragma unroll
-        for (int mt = 0; mt < NUM_MT; ++mt) {
-          const uint64_t a_desc = make_smem_desc(act_ring + (as * kMaxMT + mt) * kSlotBytes);
-          umma_bf16(tmem_base + mt * BN, a_desc, b_desc, kIdesc, acc);
-#pragma unroll
-          for (int k = 1; k < BK / UMMA_K; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
-            umma_bf16(tmem_base + mt * BN, a_desc + 2 * k, b_desc + 2 * k, kIdesc, 1u);
-          umma_commit(bar_aempty + 8 * (as * kMaxMT + mt));  // activation slot free once read
-        }
-        umma_commit(bar_wempty + 8 * ws);       // W slot free
-        if (last_kb) umma_commit(bar_tfull);    // strip accumulators complete
-      }
-      __syncwarp();
-    };
-    using std::integral_constant;
-    static_assert(kActStages == 2 && kWStages == 4, "the switch below enumerates g % 4");
-    uint32_t it = 0, g = 0;
-    for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
       for (int kb = 0; kb < num_kb; ++kb, ++g) {
-        const uint32_t aphase = (g / kActStages) & 1, wphase = (g / kWStages) & 1, tp = (it & 1) ^ 1;
-        const bool f = kb == 0, l = kb == num_kb - 1;
-        switch (g & 3) {
-          case 0: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 0>{}, aphase, wphase, f, l, tp); break;
-          case 1: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 1>{}, aphase, wphase, f, l, tp); break;
-          case 2: issue_group(integral_constant<uint32_t, 0>{}, integral_constant<uint32_t, 2>{}, aphase, wphase, f, l, tp); break;
-          default: issue_group(integral_constant<uint32_t, 1>{}, integral_constant<uint32_t, 3>{}, aphase, wphase, f, l, tp); break;
-        }
-      }
-    }
-#ifdef DD_UNC_EXPERIMENT
-    if (p.dbg && lane == 0) {
-      long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
-      o[0] = clock64() - dbg_t0; o[1] = dbg_w; o[2] = dbg_a; o[3] = dbg_t;
-    }
-#endif
-  } else {
-    // =========================== epilogue (warps 0-7) ===========================
-    const int q = warp & 3, half = warp >> 2;
-    const int tid = q * 32 + lane;       // 0..127 = TMEM lane = row inside each 128-row tile
-    const int hb = half * BNH;           // first column of this warp's half of the strip
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + hb;
-    const float inv_v = 1.0f / (float)p.vocab;
-    const int parts_e = 2 * p.parts, part_e = 2 * part + half;
-
-    float st_m[NUM_MT], st_z[NUM_MT];          // STATS: running max, sum-exp | FUSED: m, 1/Z
-    float acc_a[NUM_MT], acc_q[NUM_MT], acc_c[NUM_MT];
-    float st_tau[NUM_MT];                      // FUSED / COLSUM: top-k candidate threshold of the row
+        const uint32_t s = g % kStages, phase = (g / kStages) & 1;
+        mbar_wait(bar_full + 8 * s, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t base = ring + s * kStageBytes;
+          const uint64_t b_desc = make_smem_desc(base + kATile);
+          for (int a = 0; a < nacc; ++a) {
+            const uint64_t a_desc = make_smem_desc(base + a * BM * 128);
 #pragma unroll
-    for (int mt = 0; mt < NUM_MT; ++mt) {
-      const int row = row0 + mt * BM + tid;
-      acc_a[mt] = acc_q[mt] = acc_c[mt] = 0.f;
-      st_tau[mt] = INFINITY;
-      if (MODE == MODE_STATS) {
-        st_m[mt] = -INFINITY;
-        st_z[mt] = 0.f;
-      } else {
-        const bool ok = row < p.n_vis;
-        st_m[mt] = ok ? p.row_stats[((size_t)img * p.n_vis + row) * 2] : 0.f;
-        st_z[mt] = ok ? p.row_stats[((size_t)img * p.n_vis + row) * 2 + 1] : 0.f;
-        if (ok && MODE != MODE_CROSS) st_tau[mt] = p.tau[(size_t)img * p.n_vis + row];
+            for (int k = 0; k < BK / UMMA_K; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+              umma_bf16(tmem_base + a * GN, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (kb == num_kb - 1) umma_commit(bar_tfull);
+        }
+        __syncwarp();
       }
     }
-
-#ifdef DD_UNC_EXPERIMENT
-    long long dbg_ewait = 0;
-    const long long dbg_e0 = clock64();
-#endif
+  } else if (warp >= kEpiWarp0) {
+    // =========================== epilogue (warps 4-11): one thread = one row ===========================
+    const int q = warp & 3, a = (warp - kEpiWarp0) >> 2;   // TMEM lane quarter, accumulator
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * GN;
     uint32_t it = 0;
-    for (int strip = strip_beg; strip < strip_end; ++strip, ++it) {
-      const int col0 = strip * BN + hb;   // first vocabulary column of this warp's half strip
-#ifdef DD_UNC_EXPERIMENT
-      const long long e0 = clock64();
-#endif
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int cs = t / p.n_rg, rg = t - cs * p.n_rg;
+      const int nacc = (rg * GM + BM < p.R) ? 2 : 1;
+      const int row = rg * GM + a * BM + q * 32 + lane;
+      const bool ok = row < p.R;
       mbar_wait(bar_tfull, it & 1);
-#ifdef DD_UNC_EXPERIMENT
-      const long long e1 = clock64();
-      dbg_ewait += e1 - e0;
-#endif
       tc_fence_after();
-
-      if (MODE == MODE_STATS) {
-#pragma unroll
-        for (int mt = 0; mt < NUM_MT; ++mt) {
-          const int row = row0 + mt * BM + tid;
-          const bool ok = row < p.n_vis;
-          float smax = -INFINITY;  // this row's maximum inside the half strip
+      if (a < nacc) {   // (warp-uniform)
+        float m = -INFINITY, z = 0.f, smax = -INFINITY;
 #pragma unroll 1
-          for (int c = 0; c < BNH / 16; ++c) {
-            float v[16];
-            tmem_ld16(lane_addr + mt * BN + c * 16, v);
-            if (ok) {
-              const int cbase = col0 + c * 16;
-              float cmax = -INFINITY;
-              if (cbase + 16 <= p.vocab) {  // (CTA-uniform) all but the last strip: no per-element bound check
+        for (int c = 0; c < GN / 32; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          if (ok) {
+            const int cbase = cs * GN + c * 32;
+            float cmax = -INFINITY;
+            if (cbase + 32 <= p.vocab) {  // all but the last strip: no per-element bound check
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  if (p.round_bf16) v[i] = bf16_round(v[i]);
-                  cmax = fmaxf(cmax, v[i]);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  if (p.round_bf16) v[i] = bf16_round(v[i]);
-                  if (cbase + i >= p.vocab) v[i] = -INFINITY;
-                  cmax = fmaxf(cmax, v[i]);
-                }
+              for (int i = 0; i < 32; ++i) {
+                if (p.round_bf16) v[i] = bf16_round(v[i]);
+                cmax = fmaxf(cmax, v[i]);
               }
-              if (cmax > -INFINITY) {   // (a chunk wholly past the vocabulary contributes nothing)
-                smax = fmaxf(smax, cmax);
-                if (cmax > st_m[mt]) {
-                  st_z[mt] *= exp2f((st_m[mt] - cmax) * kLog2e);
-                  st_m[mt] = cmax;
-                }
-                const float mneg = -st_m[mt] * kLog2e;
-                float zs0 = 0.f, zs1 = 0.f;
+            } else {
 #pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                  zs0 += ex2_ftz(fmaf(v[i], kLog2e, mneg));
-                  zs1 += ex2_ftz(fmaf(v[i + 1], kLog2e, mneg));
-                }
-                st_z[mt] += zs0 + zs1;
+              for (int i = 0; i < 32; ++i) {
+                if (p.round_bf16) v[i] = bf16_round(v[i]);
+                if (cbase + i >= p.vocab) v[i] = -INFINITY;
+                cmax = fmaxf(cmax, v[i]);
               }
             }
+            smax = fmaxf(smax, cmax);
+            if (c & 1) {   // a 64-column chunk is complete
+              p.strip_max[(size_t)row * (p.n_cs * (GN / kChunk)) + cs * (GN / kChunk) + (c >> 1)] = smax;
+              smax = -INFINITY;
+            }
+            if (cmax > -INFINITY) {   // (32 columns wholly past the vocabulary contribute nothing)
+              if (cmax > m) {
+                z *= ex2_ftz((m - cmax) * kLog2e);
+                m = cmax;
+              }
+              const float mneg = -m * kLog2e;
+              float zs0 = 0.f, zs1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                zs0 += ex2_ftz(fmaf(v[i], kLog2e, mneg));
+                zs1 += ex2_ftz(fmaf(v[i + 1], kLog2e, mneg));
+              }
+              z += zs0 + zs1;
+            }
+            // the logits themselves (columns past the vocabulary hold -inf; the readers mask them anyway)
+            if constexpr (BF16_STASH) {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.stash) + (size_t)row * p.Vs + cbase);
+#pragma unroll
+              for (int h = 0; h < 4; ++h)
+                dst[h] = make_uint4(pack_bf16x2(v[8 * h], v[8 * h + 1]), pack_bf16x2(v[8 * h + 2], v[8 * h + 3]),
+                                    pack_bf16x2(v[8 * h + 4], v[8 * h + 5]), pack_bf16x2(v[8 * h + 6], v[8 * h + 7]));
+            } else {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.stash) + (size_t)row * p.Vs + cbase);
+#pragma unroll
+              for (int h = 0; h < 8; ++h) dst[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+            }
           }
-          if (ok) p.strip_max[((size_t)img * 2 * p.n_strips + 2 * strip + half) * p.n_vis + row] = smax;
-          tc_fence_before();
-          mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
         }
-      } else {
-        if (MODE == MODE_FUSED || MODE == MODE_COLSUM) {
-          // ---- pass 1: p, A, Q and the column sums (16 columns at a time over all row tiles, so that
-          //      the running column sums stay in 16 registers) ------------------------------------
-#pragma unroll 1
-          for (int c = 0; c < BNH / 16; ++c) {
-            float colsum[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) colsum[i] = 0.f;
-#pragma unroll
-            for (int mt = 0; mt < NUM_MT; ++mt) {
-              const bool ok = row0 + mt * BM + tid < p.n_vis;
-              const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
-              float v[16];
-              tmem_ld16(lane_addr + mt * BN + c * 16, v);
-              float cm = -INFINITY;  // chunk maximum of this row: any top-k candidate in here?
-              if (ok) {
-                auto body = [&](auto padded) {  // padded: the chunk holds vocab columns past the end (last strip only)
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    float x = v[i];
-                    if (p.round_bf16) x = bf16_round(x);
-                    if constexpr (decltype(padded)::value) {
-                      if (col0 + c * 16 + i < p.vocab) cm = fmaxf(cm, x);
-                    } else {
-                      cm = fmaxf(cm, x);
-                    }
-                    float pr = ex2_ftz(fmaf(x, kLog2e, mneg)) * iz;
-                    float dv = pr - inv_v;
-                    if constexpr (decltype(padded)::value)
-                      if (col0 + c * 16 + i >= p.vocab) pr = dv = 0.f;
-                    colsum[i] += pr;
-                    acc_a[mt] = fmaf(pr, ln_ftz(pr + kEps), acc_a[mt]);
-                    acc_q[mt] = fmaf(dv, dv, acc_q[mt]);
-                  }
-                };
-                if (col0 + c * 16 + 16 <= p.vocab) body(std::false_type{});
-                else body(std::true_type{});
-              }
-              if (__any_sync(0xffffffffu, cm >= st_tau[mt]))  // warp-uniform, rare
-                append_candidates(CandSink{p.cand_cnt, p.cand_val, p.cand_idx, p.cap, p.vocab, p.round_bf16},
-                                  lane_addr + mt * BN + c * 16, st_tau[mt], col0 + c * 16,
-                                  (size_t)img * p.n_vis + row0 + mt * BM + tid);
-              if (MODE == MODE_COLSUM && c == BNH / 16 - 1) {  // no second pass over TMEM in this mode
-                tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * mt);
-              }
-            }
-            // column sums over the rows held by this CTA: warp butterfly, then 4 smem rows
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float s = colsum[i];
-              s += __shfl_xor_sync(0xffffffffu, s, 16);
-              s += __shfl_xor_sync(0xffffffffu, s, 8);
-              s += __shfl_xor_sync(0xffffffffu, s, 4);
-              s += __shfl_xor_sync(0xffffffffu, s, 2);
-              s += __shfl_xor_sync(0xffffffffu, s, 1);
-              if (lane == i) s_col[q * BN + hb + c * 16 + i] = s;
-            }
-          }
-          half_bar_sync(half);
-          if (tid < BNH) {
-            const int cc = hb + tid;
-            const float tot = s_col[cc] + s_col[BN + cc] + s_col[2 * BN + cc] + s_col[3 * BN + cc];
-            if (MODE == MODE_FUSED)
-              s_logp[cc] = __logf(tot / (float)p.n_vis + kEps);  // log(p_avg + eps), models/llava.py:732-735
-            else
-              p.colpart[((size_t)img * p.n_chunks + chunk) * ((size_t)p.n_strips * BN) + col0 + tid] = tot;
-          }
-          half_bar_sync(half);
-        }
-        if (MODE == MODE_CROSS) {
-          if (tid < BNH) s_logp[hb + tid] = p.logpavg[(size_t)img * ((size_t)p.n_strips * BN) + col0 + tid];
-          half_bar_sync(half);
-        }
-        if (MODE == MODE_FUSED || MODE == MODE_CROSS) {
-          // ---- pass 2: C_i = sum_v p log(p_avg + eps) ---------------------------------------
-#pragma unroll
-          for (int mt = 0; mt < NUM_MT; ++mt) {
-            const bool ok = row0 + mt * BM + tid < p.n_vis;
-            const float mneg = -st_m[mt] * kLog2e, iz = st_z[mt];
-#pragma unroll 1
-            for (int c = 0; c < BNH / 16; ++c) {
-              float v[16];
-              tmem_ld16(lane_addr + mt * BN + c * 16, v);
-              if (ok) {
-                auto body = [&](auto padded) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    float x = v[i];
-                    if (p.round_bf16) x = bf16_round(x);
-                    float pr = ex2_ftz(fmaf(x, kLog2e, mneg)) * iz;
-                    if constexpr (decltype(padded)::value)
-                      if (col0 + c * 16 + i >= p.vocab) pr = 0.f;
-                    acc_c[mt] = fmaf(pr, s_logp[hb + c * 16 + i], acc_c[mt]);
-                  }
-                };
-                if (col0 + c * 16 + 16 <= p.vocab) body(std::false_type{});
-                else body(std::true_type{});
-              }
-            }
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * mt);  // this row tile's accumulators may be overwritten
-          }
-          half_bar_sync(half);  // s_col / s_logp reusable
+        if (ok) {
+          reinterpret_cast<float2*>(p.part_stats)[(size_t)row * p.n_cs + cs] = make_float2(m, z);
         }
       }
-    }
-
-#ifdef DD_UNC_EXPERIMENT
-    if (p.dbg && warp == 0 && lane == 0) {
-      long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
-      o[4] = clock64() - dbg_e0; o[5] = dbg_ewait;
-    }
-#endif
-    // ---- per-(CTA, half) partials ------------------------------------------------------------
-#pragma unroll
-    for (int mt = 0; mt < NUM_MT; ++mt) {
-      const int row = row0 + mt * BM + tid;
-      if (row >= p.n_vis) continue;
-      const size_t pr = ((size_t)img * parts_e + part_e) * p.n_vis + row;
-      if (MODE == MODE_STATS) {
-        p.part_stats[pr * 2] = st_m[mt];
-        p.part_stats[pr * 2 + 1] = st_z[mt];
-      } else {
-        if (MODE != MODE_CROSS) {
-          p.part_acq[pr * 3] = acc_a[mt];
-          p.part_acq[pr * 3 + 1] = acc_q[mt];
-        }
-        if (MODE != MODE_COLSUM) p.part_acq[pr * 3 + 2] = acc_c[mt];
-      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty);   // the accumulators may be overwritten
     }
   }
 
@@ -542,34 +278,32 @@ uncertainty_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // hundreds of dependent L2 loads and take longer than a GEMM sweep.
 constexpr int kFinWarps = 8;
 
-// merge the per-CTA (m, z) partials of one row: row_stats = (m, 1/Z); tau = k-th largest per-strip maximum
-// (a lower bound of the row's k-th largest logit; -inf when there are fewer than k strips); reset the
-// candidate counter for sweep 2
-__global__ void __launch_bounds__(kFinWarps * 32)
-stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats, float* __restrict__ tau) {
+// merge the per-strip (m, z) partials of one row: row_stats = (m, 1/Z); tau = k-th largest chunk maximum
+// (a lower bound of the row's k-th largest logit; -inf when there are fewer than k chunks); reset the
+// candidate counter
+__global__ void __launch_bounds__(kFinWarps * 32) stats_finalize_kernel(const UncParams p) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kFinWarps + (threadIdx.x >> 5), img = blockIdx.y;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.overflow = 0;
-  if (row >= p.n_vis) return;  // warp-uniform
-  const int parts_e = 2 * p.parts, strips_e = 2 * p.n_strips;   // per-row partials / strip maxima exist per half strip
+  const int row = blockIdx.x * kFinWarps + (threadIdx.x >> 5);
+  if (p.reset_overflow && blockIdx.x == 0 && threadIdx.x == 0) *p.overflow = 0;
+  if (row >= p.R) return;  // warp-uniform
+  const float2* ps = reinterpret_cast<const float2*>(p.part_stats) + (size_t)row * p.n_cs;
   float m = -INFINITY;
-  for (int q = lane; q < parts_e; q += 32)
-    m = fmaxf(m, p.part_stats[(((size_t)img * parts_e + q) * p.n_vis + row) * 2]);
+  for (int s = lane; s < p.n_cs; s += 32) m = fmaxf(m, ps[s].x);
   m = warp_max(m);
   float z = 0.f;
-  for (int q = lane; q < parts_e; q += 32) {
-    const size_t pr = ((size_t)img * parts_e + q) * p.n_vis + row;
-    const float pm = p.part_stats[pr * 2];
-    if (pm > -INFINITY) z += p.part_stats[pr * 2 + 1] * exp2f((pm - m) * kLog2e);
+  for (int s = lane; s < p.n_cs; s += 32) {
+    const float2 pr = ps[s];
+    if (pr.x > -INFINITY) z += pr.y * exp2f((pr.x - m) * kLog2e);
   }
   z = warp_sum(z);
-  // k-th largest strip maximum: every lane keeps its own values sorted (descending), then k rounds of
+  // k-th largest chunk maximum: every lane keeps its own values sorted (descending), then k rounds of
   // "largest head over the warp, its owner pops"
   float tv[DD_MAX_TOPK];
 #pragma unroll
   for (int j = 0; j < DD_MAX_TOPK; ++j) tv[j] = -INFINITY;
-  for (int s = lane; s < strips_e; s += 32) {
-    float v = p.strip_max[((size_t)img * strips_e + s) * p.n_vis + row];
+  const int n_chunks = p.n_cs * (GN / kChunk);
+  for (int s = lane; s < n_chunks; s += 32) {
+    float v = p.strip_max[(size_t)row * n_chunks + s];
 #pragma unroll
     for (int j = 0; j < DD_MAX_TOPK; ++j) {  // insertion by a chain of swaps keeps tv[] in registers
       const float hi = fmaxf(tv[j], v);
@@ -588,32 +322,246 @@ stats_finalize_kernel(const UncParams p, float* __restrict__ row_stats, float* _
     }
   }
   if (lane == 0) {
-    const size_t o = (size_t)img * p.n_vis + row;
-    row_stats[o * 2] = m;
-    row_stats[o * 2 + 1] = 1.0f / z;
-    tau[o] = kth;
-    p.cand_cnt[o] = 0;
+    reinterpret_cast<float4*>(p.row_stats)[row] = make_float4(m, 1.0f / z, kth, 0.f);
+    p.cand_cnt[row] = 0;
   }
 }
 
-// log(p_avg + eps) from the per-chunk column sums (n_vis > 640 path)
-__global__ void logpavg_kernel(const UncParams p) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
-  const int vp = p.n_strips * BN;
-  if (v >= vp) return;
-  float tot = 0.f;
-  for (int c = 0; c < p.n_chunks; ++c) tot += p.colpart[((size_t)img * p.n_chunks + c) * vp + v];
-  p.logpavg[(size_t)img * vp + v] = __logf(tot / (float)p.n_vis + kEps);
+// ------------------------------------------------------------------------------------------
+// The element-wise passes over the stash
+// ------------------------------------------------------------------------------------------
+// CTA = (image, strip of EC = 64 vocabulary columns), 256 threads.  The strip is walked in tiles of 256 rows: a tile
+// is copied stash -> shared memory with cp.async (coalesced 128-byte rows; two CTAs per SM overlap copy and math), then ONE THREAD OWNS ONE
+// ROW: its 64 logits come out of shared memory as 128-bit loads and the row sums A, Q, C are thread-local (a warp per
+// row spends as many instructions on the shuffle reductions and per-row bookkeeping as on the math: measured 20
+// instructions per logit and pass, 65 us per image).  The column sums are the transposed reduction: p goes to a padded
+// fp32 tile in shared memory and thread (column, row quarter) adds it up in row order -- fixed order, deterministic.
+constexpr int EC = 64;                       // columns per strip
+constexpr int ER = 256;                      // rows per tile = threads per CTA
+constexpr int kPLd = EC + 4;                 // padded row of the p tile (floats): 128-bit row stores and column reads
+                                             // are both conflict-free
+template <bool BF16_STASH>
+struct EwCfg {
+  static constexpr int kElem = BF16_STASH ? 2 : 4;
+  static constexpr int kRowBytes = EC * kElem;           // 128 / 256
+  static constexpr int kLd = kRowBytes + 16;             // padded row of the logits tile (bytes)
+  static constexpr int kTileBytes = ER * kLd;
+  static constexpr int kChunksPerRow = kRowBytes / 16;   // 8 / 16
+  static constexpr size_t kSmem = (size_t)kTileBytes + (size_t)ER * kPLd * 4 + 4 * EC * 4 + EC * 4 + 16;
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows [t0, t0 + ER) of the strip -> tile buffer (rows past n_vis are not touched)
+template <bool BF16_STASH>
+__device__ __forceinline__ void load_tile(const UncParams& p, uint32_t buf, size_t row_base, int t0, int c0) {
+  using C = EwCfg<BF16_STASH>;
+  const uint8_t* src0 = static_cast<const uint8_t*>(p.stash) + ((row_base + t0) * p.Vs + c0) * C::kElem;
+#pragma unroll
+  for (int i = 0; i < C::kChunksPerRow; ++i) {
+    const int q = i * ER + threadIdx.x;
+    const int r = q / C::kChunksPerRow, part = q % C::kChunksPerRow;
+    if (t0 + r < p.n_vis) cp_async_16(buf + r * C::kLd + part * 16, src0 + (size_t)r * p.Vs * C::kElem + part * 16);
+  }
+  cp_async_commit();
 }
 
-__global__ void __launch_bounds__(kFinWarps * 32)
+// 8 consecutive logits of the thread's row from the tile
+template <bool BF16_STASH>
+__device__ __forceinline__ void tile_logits8(const uint8_t* row, int g, float (&x)[8]) {
+  if constexpr (BF16_STASH) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + g * 16);
+    const float2 a = bf16x2_to_float2(u.x), b = bf16x2_to_float2(u.y), c = bf16x2_to_float2(u.z), d = bf16x2_to_float2(u.w);
+    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y; x[6] = d.x; x[7] = d.y;
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(row + g * 32);
+    const float4 b = *reinterpret_cast<const float4*>(row + g * 32 + 16);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  }
+}
+
+// Rare path of pass A (noinline keeps it out of the hot loop): some of the 8 logits at column `col` reach the row's
+// top-k threshold.
+__device__ __noinline__ void append_candidates8(int32_t* cand_cnt, float* cand_val, int32_t* cand_idx, int cap, int vocab,
+                                                size_t grow, float4 xa, float4 xb, float tau, int col) {
+  const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+  const struct { int32_t* cand_cnt; float* cand_val; int32_t* cand_idx; int cap, vocab; } p{cand_cnt, cand_val, cand_idx, cap, vocab};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (col + i < p.vocab && x[i] >= tau) {
+      const int slot = atomicAdd(&p.cand_cnt[grow], 1);
+      if (slot < p.cap) {
+        p.cand_val[grow * p.cap + slot] = x[i];
+        p.cand_idx[grow * p.cap + slot] = col + i;
+      }
+    }
+  }
+}
+
+template <bool BF16_STASH>
+__global__ void __launch_bounds__(ER, BF16_STASH ? 2 : 1) entropy_kernel(const UncParams p) {
+  using C = EwCfg<BF16_STASH>;
+  extern __shared__ __align__(16) uint8_t ew_smem[];
+  uint8_t* s_tile = ew_smem;                                          // [ER][kLd]
+  float* s_p = reinterpret_cast<float*>(ew_smem + C::kTileBytes);     // [ER][kPLd]
+  float* s_red = s_p + ER * kPLd;                                     // [4][EC]
+  float* s_lp = s_red + 4 * EC;                                       // [EC]
+  const int tid = threadIdx.x;
+  const int es = blockIdx.x, img = blockIdx.y;
+  const int c0 = es * EC;
+  const size_t row_base = (size_t)img * p.n_vis;
+  const int n_tiles = (p.n_vis + ER - 1) / ER;
+  const float inv_v = 1.0f / (float)p.vocab;
+  const bool full = c0 + EC <= p.vocab;        // (CTA-uniform) no column of the strip lies past the vocabulary
+  const uint32_t tile_u32 = smem_u32(s_tile);
+  const size_t R = (size_t)p.R;
+  const uint8_t* xrow = s_tile + tid * C::kLd;
+  float* prow = s_p + tid * kPLd;
+
+  // ---- pass A: p, A, Q, top-k candidates, column sums ----
+  float colsum = 0.f;                          // threads 0..EC-1: column tid, over the tiles in order
+  for (int t = 0; t < n_tiles; ++t) {
+    load_tile<BF16_STASH>(p, tile_u32, row_base, t * ER, c0);
+    cp_async_wait<0>();
+    __syncthreads();                           // tile t has landed
+    const int r = t * ER + tid;
+    if (r < p.n_vis) {
+      const size_t grow = row_base + r;
+      const float4 st = reinterpret_cast<const float4*>(p.row_stats)[grow];
+      const float mneg = -st.x * kLog2e, iz = st.y, tau = st.z;
+      float acc_a = 0.f, acc_q = 0.f;          // acc_a in units of log2
+      auto body = [&](auto padded) {           // padded: the strip holds columns past the vocabulary (last strip only)
+#pragma unroll 2
+        for (int g = 0; g < EC / 8; ++g) {
+          float x[8], pr[8];
+          tile_logits8<BF16_STASH>(xrow, g, x);
+          float cm = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            pr[i] = ex2_ftz(fmaf(x[i], kLog2e, mneg)) * iz;
+            float dv = pr[i] - inv_v;
+            if constexpr (decltype(padded)::value) {
+              if (c0 + g * 8 + i >= p.vocab) pr[i] = dv = 0.f;
+              else cm = fmaxf(cm, x[i]);
+            } else {
+              cm = fmaxf(cm, x[i]);
+            }
+            float lg;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(pr[i] + kEps));
+            acc_a = fmaf(pr[i], lg, acc_a);
+            acc_q = fmaf(dv, dv, acc_q);
+          }
+          *reinterpret_cast<float4*>(prow + g * 8) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+          *reinterpret_cast<float4*>(prow + g * 8 + 4) = make_float4(pr[4], pr[5], pr[6], pr[7]);
+          if (cm >= tau)   // rare
+            append_candidates8(p.cand_cnt, p.cand_val, p.cand_idx, p.cap, p.vocab, grow, make_float4(x[0], x[1], x[2], x[3]),
+                               make_float4(x[4], x[5], x[6], x[7]), tau, c0 + g * 8);
+        }
+      };
+      if (full) body(std::false_type{});
+      else body(std::true_type{});
+      reinterpret_cast<float2*>(p.part_aq)[(size_t)es * R + grow] = make_float2(acc_a * 0.6931471805599453f, acc_q);
+    } else {
+#pragma unroll
+      for (int c = 0; c < EC; c += 4) *reinterpret_cast<float4*>(prow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    {  // column sums of the tile: thread (column, row quarter) in row order, then the quarters in order
+      const int c = tid & (EC - 1), rq = tid / EC;
+      const float* col = s_p + (rq * (ER / 4)) * kPLd + c;
+      float sum = 0.f;
+#pragma unroll 16
+      for (int i = 0; i < ER / 4; ++i) sum += col[i * kPLd];
+      s_red[rq * EC + c] = sum;
+    }
+    __syncthreads();                           // (also: every read of the logits tile and of s_p is done)
+    if (tid < EC) colsum += ((s_red[tid] + s_red[EC + tid]) + s_red[2 * EC + tid]) + s_red[3 * EC + tid];
+  }
+  // ---- log(p_avg + eps) of the strip's columns, models/llava.py:732-735 ----
+  if (tid < EC) s_lp[tid] = __logf(colsum / (float)p.n_vis + kEps);
+  __syncthreads();
+
+  // ---- pass B: C = sum_v p log(p_avg + eps); one tile: its logits are still in shared memory ----
+  for (int t = 0; t < n_tiles; ++t) {
+    if (n_tiles > 1) {
+      load_tile<BF16_STASH>(p, tile_u32, row_base, t * ER, c0);
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    const int r = t * ER + tid;
+    if (r < p.n_vis) {
+      const size_t grow = row_base + r;
+      const float4 st = reinterpret_cast<const float4*>(p.row_stats)[grow];
+      const float mneg = -st.x * kLog2e, iz = st.y;
+      float acc_c = 0.f;
+      auto body = [&](auto padded) {
+#pragma unroll 2
+        for (int g = 0; g < EC / 8; ++g) {
+          float x[8];
+          tile_logits8<BF16_STASH>(xrow, g, x);
+          const float4 l0 = *reinterpret_cast<const float4*>(s_lp + g * 8), l1 = *reinterpret_cast<const float4*>(s_lp + g * 8 + 4);
+          const float lp[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float pr = ex2_ftz(fmaf(x[i], kLog2e, mneg));
+            if constexpr (decltype(padded)::value)
+              if (c0 + g * 8 + i >= p.vocab) pr = 0.f;
+            acc_c = fmaf(pr, lp[i], acc_c);
+          }
+        }
+      };
+      if (full) body(std::false_type{});
+      else body(std::true_type{});
+      p.part_c[(size_t)es * R + grow] = acc_c * iz;
+    }
+    if (n_tiles > 1) __syncthreads();          // the tile buffer is refilled next iteration
+  }
+}
+
+// alea / epi / var from the per-strip partials, top-k ids from the candidate lists.  CTA = 32 rows: thread
+// (group g of 16, row r of 32) adds the strips g, g+16, ... of its row (coalesced over the rows), the groups are added
+// in order; then each warp sorts the candidates of 2 rows.
+constexpr int kFinRows = 32, kFinGroups = 16;
+__global__ void __launch_bounds__(kFinRows * kFinGroups)
 fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restrict__ alea, float* __restrict__ var,
                       int32_t* __restrict__ topk_ids) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kFinWarps + (threadIdx.x >> 5), img = blockIdx.y;
-  if (row >= p.n_vis) return;  // warp-uniform
-  const size_t r = (size_t)img * p.n_vis + row;
-  {  // top-k ids from the candidate list: k selection rounds, value descending, id ascending on ties
+  __shared__ float s_acc[kFinGroups][kFinRows][3];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * kFinRows;
+  {
+    const int row = row0 + lane;
+    float a = 0.f, q = 0.f, c = 0.f;
+    if (row < p.R) {
+#pragma unroll 8
+      for (int s = g; s < p.n_es; s += kFinGroups) {
+        const float2 aq = reinterpret_cast<const float2*>(p.part_aq)[(size_t)s * p.R + row];
+        a += aq.x;
+        q += aq.y;
+        c += p.part_c[(size_t)s * p.R + row];
+      }
+    }
+    s_acc[g][lane][0] = a; s_acc[g][lane][1] = q; s_acc[g][lane][2] = c;
+  }
+  __syncthreads();
+  if (g == 0 && row0 + lane < p.R) {
+    float a = 0.f, q = 0.f, c = 0.f;
+#pragma unroll
+    for (int k = 0; k < kFinGroups; ++k) { a += s_acc[k][lane][0]; q += s_acc[k][lane][1]; c += s_acc[k][lane][2]; }
+    const size_t r = (size_t)(row0 + lane);
+    alea[r] = -a;                         // models/llava.py:739
+    epi[r] = a - c;                       // models/llava.py:735
+    var[r] = q / (float)(p.vocab - 1);    // torch.var (unbiased), models/llava.py:728
+  }
+  // top-k ids from the candidate list: k selection rounds, value descending, id ascending on ties
+  for (int rr = 0; rr < kFinRows / kFinGroups; ++rr) {
+    const int row = row0 + g * (kFinRows / kFinGroups) + rr;
+    if (row >= p.R) break;   // warp-uniform
+    const size_t r = (size_t)row;
     const int n = min(p.cand_cnt[r], p.cap);
     if (lane == 0 && p.cand_cnt[r] > p.cap) atomicAdd(p.overflow, 1);
     const float* cv = p.cand_val + r * p.cap;
@@ -639,100 +587,79 @@ fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restr
       pv = bv; pi = bi;
     }
   }
-  float a = 0.f, q = 0.f, c = 0.f;
-  for (int s = lane; s < 2 * p.parts; s += 32) {
-    const size_t pr = ((size_t)img * 2 * p.parts + s) * p.n_vis + row;
-    a += p.part_acq[pr * 3];
-    q += p.part_acq[pr * 3 + 1];
-    c += p.part_acq[pr * 3 + 2];
-  }
-  a = warp_sum(a); q = warp_sum(q); c = warp_sum(c);
-  if (lane == 0) {
-    alea[r] = -a;                         // models/llava.py:739
-    epi[r] = a - c;                       // models/llava.py:735
-    var[r] = q / (float)(p.vocab - 1);    // torch.var (unbiased), models/llava.py:728
-  }
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  static int cache[64];
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
 }
 
 struct UncLayout {
-  int n_strips, parts, n_chunks;
-  int cap;
-  size_t off_stats, off_smax, off_tau, off_ccnt, off_cval, off_cidx, off_rowstats, off_acq, off_colpart, off_logpavg, off_ovf, total;
+  int group;        // images per group
+  int n_cs, n_es, Vs, cap;
+  size_t off_stash, off_stats, off_smax, off_ccnt, off_cval, off_cidx, off_rowstats, off_aq, off_c, off_ovf, total;
 };
 static UncLayout unc_layout(int n_images, int n_vis, int vocab, int topk) {
   UncLayout L;
-  L.n_strips = ceil_div(vocab, BN);
-  L.n_chunks = ceil_div(n_vis, kMaxMT * BM);
-  // CTAs per (image, row chunk): one CTA owns the whole TMEM, so a grid larger than the SM count runs in waves and
-  // 152 CTAs cost twice what 148 do.  Pick the split that minimises waves x strips-per-CTA (ties: fewer partials).
-  const int groups = (n_images > 0 ? n_images : 1) * L.n_chunks, sms = num_sms();
-  int best = 1;
-  long best_cost = -1;
-  for (int parts = 1; parts <= L.n_strips && parts <= sms; ++parts) {
-    const long cost = (long)ceil_div(parts * groups, sms) * ceil_div(L.n_strips, parts);
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = parts; }
-  }
-  L.parts = best;
-  const size_t rows = (size_t)n_images * 2 * L.parts * n_vis;   // partials per (CTA, epilogue half)
+  L.group = kRowsCap / n_vis;
+  if (L.group < 1) L.group = 1;
+  if (L.group > n_images) L.group = n_images > 0 ? n_images : 1;
+  L.n_cs = ceil_div(vocab, GN);
+  L.n_es = ceil_div(vocab, 64);
+  L.Vs = L.n_cs * GN;
+  L.cap = 96 * topk + 64;  // without ties at most kChunk*topk elements reach the threshold
+  const size_t R = (size_t)L.group * n_vis;
   size_t o = 0;
-  L.off_stats = o; o = align_up(o + rows * 2 * sizeof(float), 256);
-  const size_t nrow = (size_t)n_images * n_vis;
-  L.cap = BN * topk + 64;  // without ties at most BN*topk elements reach the threshold
-  L.off_smax = o; o = align_up(o + nrow * 2 * L.n_strips * sizeof(float), 256);
-  L.off_tau = o; o = align_up(o + nrow * sizeof(float), 256);
-  L.off_ccnt = o; o = align_up(o + nrow * sizeof(int32_t), 256);
-  L.off_cval = o; o = align_up(o + nrow * L.cap * sizeof(float), 256);
-  L.off_cidx = o; o = align_up(o + nrow * L.cap * sizeof(int32_t), 256);
-  L.off_rowstats = o; o = align_up(o + (size_t)n_images * n_vis * 2 * sizeof(float), 256);
-  L.off_acq = o; o = align_up(o + rows * 3 * sizeof(float), 256);
-  const size_t vp = (size_t)L.n_strips * BN;
-  L.off_colpart = o; o = align_up(o + (L.n_chunks > 1 ? (size_t)n_images * L.n_chunks * vp * sizeof(float) : 0), 256);
-  L.off_logpavg = o; o = align_up(o + (L.n_chunks > 1 ? (size_t)n_images * vp * sizeof(float) : 0), 256);
+  L.off_stash = o; o = align_up(o + R * L.Vs * sizeof(float), 256);   // (bf16 logits use half of it)
+  L.off_stats = o; o = align_up(o + (size_t)L.n_cs * R * 2 * sizeof(float), 256);
+  L.off_smax = o; o = align_up(o + (size_t)L.n_cs * (GN / kChunk) * R * sizeof(float), 256);
+  L.off_ccnt = o; o = align_up(o + R * sizeof(int32_t), 256);
+  L.off_cval = o; o = align_up(o + R * L.cap * sizeof(float), 256);
+  L.off_cidx = o; o = align_up(o + R * L.cap * sizeof(int32_t), 256);
+  L.off_rowstats = o; o = align_up(o + R * 4 * sizeof(float), 256);
+  L.off_aq = o; o = align_up(o + (size_t)L.n_es * R * 2 * sizeof(float), 256);
+  L.off_c = o; o = align_up(o + (size_t)L.n_es * R * sizeof(float), 256);
   L.off_ovf = o; o = align_up(o + sizeof(int32_t), 256);
   L.total = o;
   return L;
 }
 
-constexpr size_t kUncSmem = 1024 + (size_t)kActStages * kMaxMT * kSlotBytes + (size_t)kWStages * kWBytes + kNumBars * 8 + 16 +
-                            5 * BN * sizeof(float);
-
-template <int NUM_MT, int MODE, int KT>
-static int launch_unc(const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, cudaStream_t st) {
-  auto kern = uncertainty_kernel<NUM_MT, MODE, KT>;
-  DD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUncSmem));
-  kern<<<dim3(p.parts, p.n_images * p.n_chunks), kUncThreads, kUncSmem, st>>>(ta, tw, p);
+template <bool BF16_STASH>
+static int run_group(const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, float* epi, float* alea,
+                     float* var, int32_t* topk_ids, cudaStream_t st) {
+  {
+    // the opt-in for > 48 KB of dynamic shared memory is a per-device attribute
+    static bool attr_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      DD_CHECK_CUDA(cudaFuncSetAttribute(logits_stats_kernel<BF16_STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kGemmSmem));
+      DD_CHECK_CUDA(cudaFuncSetAttribute(entropy_kernel<BF16_STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)EwCfg<BF16_STASH>::kSmem));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+  }
+  const int tiles = p.n_cs * p.n_rg, sms = num_sms();
+  logits_stats_kernel<BF16_STASH><<<tiles < sms ? tiles : sms, kGemmThreads, kGemmSmem, st>>>(ta, tw, p);
+  DD_CHECK_LAUNCH();
+  const dim3 fgrid(ceil_div(p.R, kFinWarps));
+  stats_finalize_kernel<<<fgrid, kFinWarps * 32, 0, st>>>(p);
+  DD_CHECK_LAUNCH();
+  entropy_kernel<BF16_STASH><<<dim3(p.n_es, p.n_img), ER, EwCfg<BF16_STASH>::kSmem, st>>>(p);
+  DD_CHECK_LAUNCH();
+  fused_finalize_kernel<<<ceil_div(p.R, kFinRows), kFinRows * kFinGroups, 0, st>>>(p, epi, alea, var, topk_ids);
   DD_CHECK_LAUNCH();
   return DD_OK;
-}
-
-template <int NUM_MT>
-static int launch_unc_mt(const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, int mode,
-                         cudaStream_t st) {
-  if (mode == MODE_FUSED) return launch_unc<NUM_MT, MODE_FUSED, 1>(ta, tw, p, st);
-  if (mode == MODE_COLSUM) return launch_unc<NUM_MT, MODE_COLSUM, 1>(ta, tw, p, st);
-  if (mode == MODE_CROSS) return launch_unc<NUM_MT, MODE_CROSS, 1>(ta, tw, p, st);
-  return launch_unc<NUM_MT, MODE_STATS, 1>(ta, tw, p, st);
-}
-
-static int launch_unc_any(int num_mt, const CUtensorMap& ta, const CUtensorMap& tw, const UncParams& p, int mode,
-                          cudaStream_t st) {
-  if (num_mt == 1) return launch_unc_mt<1>(ta, tw, p, mode, st);
-  if (num_mt <= 3) return launch_unc_mt<3>(ta, tw, p, mode, st);
-  return launch_unc_mt<5>(ta, tw, p, mode, st);
 }
 
 }  // namespace dd
@@ -741,18 +668,6 @@ extern "C" size_t dd_uncertainty_workspace_bytes(int n_images, int n_vis, int vo
   if (n_images <= 0 || n_vis <= 0 || vocab <= 0 || topk <= 0) return 0;
   return dd::unc_layout(n_images, n_vis, vocab, topk).total;
 }
-
-#ifdef DD_UNC_EXPERIMENT
-// host copy of the cycle counters of the last sweep: [ctas][8] = mma {loop, wait W, wait act, wait tmem-empty}, epilogue {loop, wait tmem-full}
-extern "C" int dd_uncertainty_debug_read(long long* host, int n_ctas) {
-  long long* buf = nullptr;
-  cudaDeviceSynchronize();
-  // the static in dd_uncertainty_project is not visible here: re-derive through a second static set by a first call
-  buf = g_unc_dbg;
-  if (!buf) return -1;
-  return cudaMemcpy(host, buf, (size_t)n_ctas * 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
-}
-#endif
 
 extern "C" size_t dd_uncertainty_overflow_offset(int n_images, int n_vis, int vocab, int topk) {
   if (n_images <= 0 || n_vis <= 0 || vocab <= 0 || topk <= 0) return 0;
@@ -779,60 +694,48 @@ extern "C" int dd_uncertainty_project(const void* h_vis, const void* w_lm, int n
     set_error("dd_uncertainty_project: workspace %zu < %zu bytes", workspace_bytes, L.total);
     return DD_ERR_WORKSPACE;
   }
-  CUtensorMap ta, tw;
-  {
-    const uint64_t dims[3] = {(uint64_t)d, (uint64_t)n_vis, (uint64_t)n_images};
-    const uint64_t strides[2] = {(uint64_t)d * 2, (uint64_t)n_vis * d * 2};
-    const uint32_t box[3] = {BK, BM, 1};
-    if (int rc = make_tmap_bf16_sw128(&ta, h_vis, 3, dims, strides, box, "dd_uncertainty_project(h_vis)")) return rc;
-  }
+  CUtensorMap tw;
   {
     const uint64_t dims[2] = {(uint64_t)d, (uint64_t)vocab};
     const uint64_t strides[1] = {(uint64_t)d * 2};
-    const uint32_t box[2] = {BK, BN};
+    const uint32_t box[2] = {BK, GN};
     if (int rc = make_tmap_bf16_sw128(&tw, w_lm, 2, dims, strides, box, "dd_uncertainty_project(w_lm)")) return rc;
   }
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   UncParams p{};
-  p.n_images = n_images; p.n_vis = n_vis; p.d = d; p.vocab = vocab; p.topk = topk; p.round_bf16 = round_logits_bf16;
-  p.n_strips = L.n_strips; p.parts = L.parts; p.n_chunks = L.n_chunks;
-  p.colpart = reinterpret_cast<float*>(ws + L.off_colpart);
-  p.logpavg = reinterpret_cast<float*>(ws + L.off_logpavg);
+  p.n_vis = n_vis; p.d = d; p.vocab = vocab; p.topk = topk; p.round_bf16 = round_logits_bf16;
+  p.n_cs = L.n_cs; p.n_es = L.n_es; p.Vs = L.Vs; p.cap = L.cap;
+  p.stash = ws + L.off_stash;
   p.part_stats = reinterpret_cast<float*>(ws + L.off_stats);
   p.strip_max = reinterpret_cast<float*>(ws + L.off_smax);
-  float* tau = reinterpret_cast<float*>(ws + L.off_tau);
-  p.tau = tau;
   p.cand_cnt = reinterpret_cast<int32_t*>(ws + L.off_ccnt);
   p.cand_val = reinterpret_cast<float*>(ws + L.off_cval);
   p.cand_idx = reinterpret_cast<int32_t*>(ws + L.off_cidx);
-  p.cap = L.cap;
-  float* row_stats = reinterpret_cast<float*>(ws + L.off_rowstats);
-  p.row_stats = row_stats;
-  p.part_acq = reinterpret_cast<float*>(ws + L.off_acq);
+  p.row_stats = reinterpret_cast<float*>(ws + L.off_rowstats);
+  p.part_aq = reinterpret_cast<float*>(ws + L.off_aq);
+  p.part_c = reinterpret_cast<float*>(ws + L.off_c);
   p.overflow = reinterpret_cast<int32_t*>(ws + L.off_ovf);
-#ifdef DD_UNC_EXPERIMENT
-  if (getenv("DD_UNC_DBG") && !g_unc_dbg) cudaMalloc(&g_unc_dbg, 4096 * 64);
-  p.dbg = g_unc_dbg;
-#endif
   cudaStream_t st = (cudaStream_t)stream;
-  const int num_mt = L.n_chunks > 1 ? kMaxMT : ceil_div(n_vis, BM);
-  const dim3 fgrid(ceil_div(n_vis, kFinWarps), n_images);
-  int rc = launch_unc_any(num_mt, ta, tw, p, MODE_STATS, st);
-  if (rc) return rc;
-  stats_finalize_kernel<<<fgrid, kFinWarps * 32, 0, st>>>(p, row_stats, tau);
-  DD_CHECK_LAUNCH();
-  if (L.n_chunks == 1) {
-    rc = launch_unc_any(num_mt, ta, tw, p, MODE_FUSED, st);
-    if (rc) return rc;
-  } else {
-    rc = launch_unc_any(num_mt, ta, tw, p, MODE_COLSUM, st);
-    if (rc) return rc;
-    logpavg_kernel<<<dim3(ceil_div(L.n_strips * BN, 256), n_images), 256, 0, st>>>(p);
-    DD_CHECK_LAUNCH();
-    rc = launch_unc_any(num_mt, ta, tw, p, MODE_CROSS, st);
+  for (int i0 = 0; i0 < n_images; i0 += L.group) {
+    const int gi = n_images - i0 < L.group ? n_images - i0 : L.group;
+    p.n_img = gi;
+    p.R = gi * n_vis;
+    p.n_rg = ceil_div(p.R, GM);
+    p.reset_overflow = i0 == 0;
+    const size_t row0 = (size_t)i0 * n_vis;
+    CUtensorMap ta;
+    {
+      const uint64_t dims[2] = {(uint64_t)d, (uint64_t)p.R};
+      const uint64_t strides[1] = {(uint64_t)d * 2};
+      const uint32_t box[2] = {BK, GM};
+      if (int rc = make_tmap_bf16_sw128(&ta, static_cast<const __nv_bfloat16*>(h_vis) + row0 * d, 2, dims, strides, box,
+                                        "dd_uncertainty_project(h_vis)"))
+        return rc;
+    }
+    const int rc = round_logits_bf16
+                       ? run_group<true>(ta, tw, p, epi + row0, alea + row0, var + row0, topk_ids + row0 * topk, st)
+                       : run_group<false>(ta, tw, p, epi + row0, alea + row0, var + row0, topk_ids + row0 * topk, st);
     if (rc) return rc;
   }
-  fused_finalize_kernel<<<fgrid, kFinWarps * 32, 0, st>>>(p, epi, alea, var, topk_ids);
-  DD_CHECK_LAUNCH();
   return DD_OK;
 }

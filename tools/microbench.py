@@ -202,7 +202,8 @@ def bench_uncertainty(only_first=False):
     for (n_img, n_vis, d, V, k) in cases[:1] if only_first else cases:
         h = torch.randn(n_img, n_vis, d, device=dev).bfloat16()
         w = (torch.randn(V, d, device=dev) * 0.02).bfloat16()
-        one = lambda: ops.uncertainty_project(h, w, topk=k)
+        # the engine's call: bf16-rounded logits (the reference's lm_head output), overflow flag read later (no host sync)
+        one = lambda: ops.uncertainty_project(h, w, topk=k, round_logits=True, return_overflow=True)
         med1, _ = timeit(one, iters=10)                      # one call: includes the host latency before the first launch
 
         def fn():                                            # 4 calls back to back: the GPU never waits for the host
@@ -226,7 +227,7 @@ def one_shot(which):
         h = torch.randn(1, 576, 4096, device=dev).bfloat16()
         w = (torch.randn(32064, 4096, device=dev) * 0.02).bfloat16()
         for _ in range(2):
-            ops.uncertainty_project(h, w, topk=5)
+            ops.uncertainty_project(h, w, topk=5, round_logits=True, return_overflow=True)
     elif which == "attention64":
         B, M, H, D, S = 64, 3, 32, 128, 849
         q = torch.randn(B, M, H, D, device=dev).bfloat16()
