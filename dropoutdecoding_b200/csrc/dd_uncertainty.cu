@@ -100,6 +100,28 @@ struct UncParams {
 // ------------------------------------------------------------------------------------------
 // The GEMM sweep
 // ------------------------------------------------------------------------------------------
+// Tile order.  A row group whose second 128 rows lie past R costs half the MMAs (one accumulator): those tiles come
+// last, and the tile list is dealt to the CTAs in snake order (round 0: CTA 0..G-1, round 1: G-1..0, ...), so the CTAs
+// that took an extra full tile are not the ones that take the extra half tiles (one LLaVA-1.5 image = 252 full + 126
+// half tiles on 148 SMs: makespan 2.25 full tiles instead of 2.5).  Inside each class the row groups of one W strip are
+// adjacent: they run at the same time on neighbouring CTAs, the strip is read from HBM once and from L2 after that.
+struct TileOrder {
+  int n_tiles, n_full, n_rg_full;
+  __device__ __forceinline__ bool get(int round, int& cs, int& rg) const {
+    const int G = gridDim.x, c = blockIdx.x;
+    const int i = round * G + ((round & 1) ? G - 1 - c : c);
+    if (i >= n_tiles) return false;
+    if (i < n_full) {
+      cs = i / n_rg_full;
+      rg = i - cs * n_rg_full;
+    } else {
+      cs = i - n_full;
+      rg = n_rg_full;
+    }
+    return true;
+  }
+  __device__ __forceinline__ int rounds() const { return (n_tiles + gridDim.x - 1) / gridDim.x; }
+};
 template <bool BF16_STASH>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 logits_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -112,7 +134,10 @@ logits_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.d / BK;
-  const int n_tiles = p.n_cs * p.n_rg;
+  // (row groups whose second accumulator has rows: all but possibly the last)
+  const int n_rg_full = p.R > BM ? (p.R - BM + GM - 1) / GM : 0;
+  const TileOrder order{p.n_cs * p.n_rg, p.n_cs * n_rg_full, n_rg_full};
+  const int n_rounds = order.rounds();
   const uint32_t ring = smem_u32(smem);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
   const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 8;
@@ -137,15 +162,14 @@ logits_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile t = (column strip t / n_rg, row group t % n_rg): the row groups of one W strip run at the same time on
-  // neighbouring CTAs, so the strip is read from HBM once and from L2 after that
   if (warp == kProdWarpA || warp == kProdWarpW) {
     // =========================== TMA producers (one elected lane issues) ===========================
     const bool is_a = warp == kProdWarpA;
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(is_a ? &tmap_a : &tmap_w) : "memory");
     uint32_t g = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int cs = t / p.n_rg, rg = t - cs * p.n_rg;
+    for (int round = 0; round < n_rounds; ++round) {
+      int cs, rg;
+      if (!order.get(round, cs, rg)) continue;
       for (int kb = 0; kb < num_kb; ++kb, ++g) {
         const uint32_t s = g % kStages, phase = (g / kStages) & 1;
         mbar_wait(bar_empty + 8 * s, phase ^ 1);
@@ -165,8 +189,9 @@ logits_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer (one elected lane issues) ===========================
     uint32_t g = 0, it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int cs = t / p.n_rg, rg = t - cs * p.n_rg;
+    for (int round = 0; round < n_rounds; ++round) {
+      int cs, rg;
+      if (!order.get(round, cs, rg)) continue;
       const int nacc = (rg * GM + BM < p.R) ? 2 : 1;   // the second accumulator's rows may all lie past R
       mbar_wait(bar_tempty, (it & 1) ^ 1);             // the epilogue has drained the previous tile
       tc_fence_after();
@@ -188,14 +213,16 @@ logits_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         __syncwarp();
       }
+      ++it;
     }
   } else if (warp >= kEpiWarp0) {
     // =========================== epilogue (warps 4-11): one thread = one row ===========================
     const int q = warp & 3, a = (warp - kEpiWarp0) >> 2;   // TMEM lane quarter, accumulator
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * GN;
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int cs = t / p.n_rg, rg = t - cs * p.n_rg;
+    for (int round = 0; round < n_rounds; ++round) {
+      int cs, rg;
+      if (!order.get(round, cs, rg)) continue;
       const int nacc = (rg * GM + BM < p.R) ? 2 : 1;
       const int row = rg * GM + a * BM + q * 32 + lane;
       const bool ok = row < p.R;
@@ -263,6 +290,7 @@ logits_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       tc_fence_before();
       mbar_arrive(bar_tempty);   // the accumulators may be overwritten
+      ++it;
     }
   }
 
@@ -523,21 +551,22 @@ __global__ void __launch_bounds__(ER, BF16_STASH ? 2 : 1) entropy_kernel(const U
   }
 }
 
-// alea / epi / var from the per-strip partials, top-k ids from the candidate lists.  CTA = 32 rows: thread
-// (group g of 16, row r of 32) adds the strips g, g+16, ... of its row (coalesced over the rows), the groups are added
-// in order; then each warp sorts the candidates of 2 rows.
-constexpr int kFinRows = 32, kFinGroups = 16;
+// alea / epi / var from the per-strip partials, top-k ids from the candidate lists.  CTA = 8 rows: thread
+// (group g of 32, row r of 8) adds the strips g, g+32, ... of its row, the groups are added in order; then each warp
+// sorts the candidates of one row.
+constexpr int kFinRows = 8, kFinGroups = 32;
 __global__ void __launch_bounds__(kFinRows * kFinGroups)
 fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restrict__ alea, float* __restrict__ var,
                       int32_t* __restrict__ topk_ids) {
   __shared__ float s_acc[kFinGroups][kFinRows][3];
-  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rr = threadIdx.x & (kFinRows - 1), g = threadIdx.x / kFinRows;
   const int row0 = blockIdx.x * kFinRows;
   {
-    const int row = row0 + lane;
+    const int row = row0 + rr;
     float a = 0.f, q = 0.f, c = 0.f;
     if (row < p.R) {
-#pragma unroll 8
+#pragma unroll 4
       for (int s = g; s < p.n_es; s += kFinGroups) {
         const float2 aq = reinterpret_cast<const float2*>(p.part_aq)[(size_t)s * p.R + row];
         a += aq.x;
@@ -545,47 +574,45 @@ fused_finalize_kernel(const UncParams p, float* __restrict__ epi, float* __restr
         c += p.part_c[(size_t)s * p.R + row];
       }
     }
-    s_acc[g][lane][0] = a; s_acc[g][lane][1] = q; s_acc[g][lane][2] = c;
+    s_acc[g][rr][0] = a; s_acc[g][rr][1] = q; s_acc[g][rr][2] = c;
   }
   __syncthreads();
-  if (g == 0 && row0 + lane < p.R) {
+  if (threadIdx.x < kFinRows && row0 + threadIdx.x < p.R) {
     float a = 0.f, q = 0.f, c = 0.f;
 #pragma unroll
-    for (int k = 0; k < kFinGroups; ++k) { a += s_acc[k][lane][0]; q += s_acc[k][lane][1]; c += s_acc[k][lane][2]; }
-    const size_t r = (size_t)(row0 + lane);
+    for (int k = 0; k < kFinGroups; ++k) { a += s_acc[k][threadIdx.x][0]; q += s_acc[k][threadIdx.x][1]; c += s_acc[k][threadIdx.x][2]; }
+    const size_t r = (size_t)(row0 + threadIdx.x);
     alea[r] = -a;                         // models/llava.py:739
     epi[r] = a - c;                       // models/llava.py:735
     var[r] = q / (float)(p.vocab - 1);    // torch.var (unbiased), models/llava.py:728
   }
   // top-k ids from the candidate list: k selection rounds, value descending, id ascending on ties
-  for (int rr = 0; rr < kFinRows / kFinGroups; ++rr) {
-    const int row = row0 + g * (kFinRows / kFinGroups) + rr;
-    if (row >= p.R) break;   // warp-uniform
-    const size_t r = (size_t)row;
-    const int n = min(p.cand_cnt[r], p.cap);
-    if (lane == 0 && p.cand_cnt[r] > p.cap) atomicAdd(p.overflow, 1);
-    const float* cv = p.cand_val + r * p.cap;
-    const int32_t* ci = p.cand_idx + r * p.cap;
-    float pv = INFINITY;
-    int pi = -1;
-    for (int j = 0; j < p.topk; ++j) {
-      float bv = -INFINITY;
-      int bi = 0x7fffffff;
-      for (int e = lane; e < n; e += 32) {
-        const float v = cv[e];
-        const int id = ci[e];
-        const bool after_prev = v < pv || (v == pv && id > pi);   // strictly after the previous pick
-        if (after_prev && (v > bv || (v == bv && id < bi))) { bv = v; bi = id; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if (lane == 0) topk_ids[r * p.topk + j] = bi == 0x7fffffff ? 0 : bi;
-      pv = bv; pi = bi;
+  const int row = row0 + warp;
+  if (row >= p.R) return;   // warp-uniform
+  const size_t r = (size_t)row;
+  const int n = min(p.cand_cnt[r], p.cap);
+  if (lane == 0 && p.cand_cnt[r] > p.cap) atomicAdd(p.overflow, 1);
+  const float* cv = p.cand_val + r * p.cap;
+  const int32_t* ci = p.cand_idx + r * p.cap;
+  float pv = INFINITY;
+  int pi = -1;
+  for (int j = 0; j < p.topk; ++j) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int e = lane; e < n; e += 32) {
+      const float v = cv[e];
+      const int id = ci[e];
+      const bool after_prev = v < pv || (v == pv && id > pi);   // strictly after the previous pick
+      if (after_prev && (v > bv || (v == bv && id < bi))) { bv = v; bi = id; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) topk_ids[r * p.topk + j] = bi == 0x7fffffff ? 0 : bi;
+    pv = bv; pi = bi;
   }
 }
 
