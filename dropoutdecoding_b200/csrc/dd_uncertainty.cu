@@ -358,14 +358,17 @@ __global__ void __launch_bounds__(kFinWarps * 32) stats_finalize_kernel(const Un
 // ------------------------------------------------------------------------------------------
 // The element-wise passes over the stash
 // ------------------------------------------------------------------------------------------
-// CTA = (image, strip of EC = 64 vocabulary columns), 256 threads.  The strip is walked in tiles of 256 rows: a tile
-// is copied stash -> shared memory with cp.async (coalesced 128-byte rows; two CTAs per SM overlap copy and math), then ONE THREAD OWNS ONE
-// ROW: its 64 logits come out of shared memory as 128-bit loads and the row sums A, Q, C are thread-local (a warp per
-// row spends as many instructions on the shuffle reductions and per-row bookkeeping as on the math: measured 20
-// instructions per logit and pass, 65 us per image).  The column sums are the transposed reduction: p goes to a padded
-// fp32 tile in shared memory and thread (column, row quarter) adds it up in row order -- fixed order, deterministic.
+// CTA = (image, strip of EC = 64 vocabulary columns), 256 threads.  The strip is walked in tiles of ER = 128 rows: a
+// tile is copied stash -> shared memory with cp.async (coalesced 128-byte rows, double buffered), then TWO THREADS OWN
+// ONE ROW (32 columns each; lanes 0-15 / 16-31 of a warp hold the two halves of 16 rows, so a quarter-warp touches 8
+// consecutive padded rows: conflict-free 128-bit accesses): the logits come out of shared memory as 128-bit loads and
+// the row sums A, Q, C are thread-local plus one shuffle (a warp per row spends as many instructions on the shuffle
+// reductions and per-row bookkeeping as on the math: measured 40 instructions per logit, 65 us per image).  The column
+// sums are the transposed reduction: p goes to a padded fp32 tile in shared memory and thread (column, row quarter)
+// adds it up in row order -- fixed order, deterministic.  72 KB of shared memory: three CTAs per SM.
 constexpr int EC = 64;                       // columns per strip
-constexpr int ER = 256;                      // rows per tile = threads per CTA
+constexpr int ER = 128;                      // rows per tile
+constexpr int kEwThreads = 2 * ER;
 constexpr int kPLd = EC + 4;                 // padded row of the p tile (floats): 128-bit row stores and column reads
                                              // are both conflict-free
 template <bool BF16_STASH>
@@ -375,7 +378,8 @@ struct EwCfg {
   static constexpr int kLd = kRowBytes + 16;             // padded row of the logits tile (bytes)
   static constexpr int kTileBytes = ER * kLd;
   static constexpr int kChunksPerRow = kRowBytes / 16;   // 8 / 16
-  static constexpr size_t kSmem = (size_t)kTileBytes + (size_t)ER * kPLd * 4 + 4 * EC * 4 + EC * 4 + 16;
+  static constexpr size_t kSmem = 2 * (size_t)kTileBytes + (size_t)ER * kPLd * 4 + 4 * EC * 4 + EC * 4 + 16;
+  static constexpr int kCtasPerSm = BF16_STASH ? 3 : 2;
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
@@ -391,15 +395,15 @@ __device__ __forceinline__ void load_tile(const UncParams& p, uint32_t buf, size
   using C = EwCfg<BF16_STASH>;
   const uint8_t* src0 = static_cast<const uint8_t*>(p.stash) + ((row_base + t0) * p.Vs + c0) * C::kElem;
 #pragma unroll
-  for (int i = 0; i < C::kChunksPerRow; ++i) {
-    const int q = i * ER + threadIdx.x;
+  for (int i = 0; i < ER * C::kChunksPerRow / kEwThreads; ++i) {
+    const int q = i * kEwThreads + threadIdx.x;
     const int r = q / C::kChunksPerRow, part = q % C::kChunksPerRow;
     if (t0 + r < p.n_vis) cp_async_16(buf + r * C::kLd + part * 16, src0 + (size_t)r * p.Vs * C::kElem + part * 16);
   }
   cp_async_commit();
 }
 
-// 8 consecutive logits of the thread's row from the tile
+// 8 consecutive logits (column group g of the strip) of a row of the tile
 template <bool BF16_STASH>
 __device__ __forceinline__ void tile_logits8(const uint8_t* row, int g, float (&x)[8]) {
   if constexpr (BF16_STASH) {
@@ -418,28 +422,29 @@ __device__ __forceinline__ void tile_logits8(const uint8_t* row, int g, float (&
 __device__ __noinline__ void append_candidates8(int32_t* cand_cnt, float* cand_val, int32_t* cand_idx, int cap, int vocab,
                                                 size_t grow, float4 xa, float4 xb, float tau, int col) {
   const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-  const struct { int32_t* cand_cnt; float* cand_val; int32_t* cand_idx; int cap, vocab; } p{cand_cnt, cand_val, cand_idx, cap, vocab};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    if (col + i < p.vocab && x[i] >= tau) {
-      const int slot = atomicAdd(&p.cand_cnt[grow], 1);
-      if (slot < p.cap) {
-        p.cand_val[grow * p.cap + slot] = x[i];
-        p.cand_idx[grow * p.cap + slot] = col + i;
+    if (col + i < vocab && x[i] >= tau) {
+      const int slot = atomicAdd(&cand_cnt[grow], 1);
+      if (slot < cap) {
+        cand_val[grow * cap + slot] = x[i];
+        cand_idx[grow * cap + slot] = col + i;
       }
     }
   }
 }
 
 template <bool BF16_STASH>
-__global__ void __launch_bounds__(ER, BF16_STASH ? 2 : 1) entropy_kernel(const UncParams p) {
+__global__ void __launch_bounds__(kEwThreads, EwCfg<BF16_STASH>::kCtasPerSm) entropy_kernel(const UncParams p) {
   using C = EwCfg<BF16_STASH>;
   extern __shared__ __align__(16) uint8_t ew_smem[];
-  uint8_t* s_tile = ew_smem;                                          // [ER][kLd]
-  float* s_p = reinterpret_cast<float*>(ew_smem + C::kTileBytes);     // [ER][kPLd]
-  float* s_red = s_p + ER * kPLd;                                     // [4][EC]
-  float* s_lp = s_red + 4 * EC;                                       // [EC]
-  const int tid = threadIdx.x;
+  uint8_t* s_tile = ew_smem;                                              // [2][ER][kLd]
+  float* s_p = reinterpret_cast<float*>(ew_smem + 2 * C::kTileBytes);     // [ER][kPLd]
+  float* s_red = s_p + ER * kPLd;                                         // [4][EC]
+  float* s_lp = s_red + 4 * EC;                                           // [EC]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int trow = warp * 16 + (lane & 15);    // row of the tile
+  const int half = lane >> 4;                  // columns [32*half, 32*half + 32) of the strip
   const int es = blockIdx.x, img = blockIdx.y;
   const int c0 = es * EC;
   const size_t row_base = (size_t)img * p.n_vis;
@@ -448,24 +453,30 @@ __global__ void __launch_bounds__(ER, BF16_STASH ? 2 : 1) entropy_kernel(const U
   const bool full = c0 + EC <= p.vocab;        // (CTA-uniform) no column of the strip lies past the vocabulary
   const uint32_t tile_u32 = smem_u32(s_tile);
   const size_t R = (size_t)p.R;
-  const uint8_t* xrow = s_tile + tid * C::kLd;
-  float* prow = s_p + tid * kPLd;
+  float* prow = s_p + trow * kPLd + half * 32;
 
   // ---- pass A: p, A, Q, top-k candidates, column sums ----
   float colsum = 0.f;                          // threads 0..EC-1: column tid, over the tiles in order
+  load_tile<BF16_STASH>(p, tile_u32, row_base, 0, c0);
   for (int t = 0; t < n_tiles; ++t) {
-    load_tile<BF16_STASH>(p, tile_u32, row_base, t * ER, c0);
-    cp_async_wait<0>();
+    if (t + 1 < n_tiles) {
+      load_tile<BF16_STASH>(p, tile_u32 + ((t + 1) & 1) * C::kTileBytes, row_base, (t + 1) * ER, c0);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();                           // tile t has landed
-    const int r = t * ER + tid;
+    const int r = t * ER + trow;
+    const uint8_t* xrow = s_tile + (t & 1) * C::kTileBytes + trow * C::kLd;
+    const size_t grow = row_base + r;
+    float acc_a = 0.f, acc_q = 0.f;            // acc_a in units of log2
     if (r < p.n_vis) {
-      const size_t grow = row_base + r;
       const float4 st = reinterpret_cast<const float4*>(p.row_stats)[grow];
       const float mneg = -st.x * kLog2e, iz = st.y, tau = st.z;
-      float acc_a = 0.f, acc_q = 0.f;          // acc_a in units of log2
       auto body = [&](auto padded) {           // padded: the strip holds columns past the vocabulary (last strip only)
 #pragma unroll 2
-        for (int g = 0; g < EC / 8; ++g) {
+        for (int gi = 0; gi < 4; ++gi) {
+          const int g = half * 4 + gi;
           float x[8], pr[8];
           tile_logits8<BF16_STASH>(xrow, g, x);
           float cm = -INFINITY;
@@ -484,8 +495,8 @@ __global__ void __launch_bounds__(ER, BF16_STASH ? 2 : 1) entropy_kernel(const U
             acc_a = fmaf(pr[i], lg, acc_a);
             acc_q = fmaf(dv, dv, acc_q);
           }
-          *reinterpret_cast<float4*>(prow + g * 8) = make_float4(pr[0], pr[1], pr[2], pr[3]);
-          *reinterpret_cast<float4*>(prow + g * 8 + 4) = make_float4(pr[4], pr[5], pr[6], pr[7]);
+          *reinterpret_cast<float4*>(prow + gi * 8) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+          *reinterpret_cast<float4*>(prow + gi * 8 + 4) = make_float4(pr[4], pr[5], pr[6], pr[7]);
           if (cm >= tau)   // rare
             append_candidates8(p.cand_cnt, p.cand_val, p.cand_idx, p.cap, p.vocab, grow, make_float4(x[0], x[1], x[2], x[3]),
                                make_float4(x[4], x[5], x[6], x[7]), tau, c0 + g * 8);
@@ -493,11 +504,14 @@ __global__ void __launch_bounds__(ER, BF16_STASH ? 2 : 1) entropy_kernel(const U
       };
       if (full) body(std::false_type{});
       else body(std::true_type{});
-      reinterpret_cast<float2*>(p.part_aq)[(size_t)es * R + grow] = make_float2(acc_a * 0.6931471805599453f, acc_q);
     } else {
 #pragma unroll
-      for (int c = 0; c < EC; c += 4) *reinterpret_cast<float4*>(prow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(prow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    acc_a += __shfl_xor_sync(0xffffffffu, acc_a, 16);     // the row's two halves (whole warp: converged here)
+    acc_q += __shfl_xor_sync(0xffffffffu, acc_q, 16);
+    if (half == 0 && r < p.n_vis)
+      reinterpret_cast<float2*>(p.part_aq)[(size_t)es * R + grow] = make_float2(acc_a * 0.6931471805599453f, acc_q);
     __syncthreads();
     {  // column sums of the tile: thread (column, row quarter) in row order, then the quarters in order
       const int c = tid & (EC - 1), rq = tid / EC;
@@ -507,7 +521,7 @@ __global__ void __launch_bounds__(ER, BF16_STASH ? 2 : 1) entropy_kernel(const U
       for (int i = 0; i < ER / 4; ++i) sum += col[i * kPLd];
       s_red[rq * EC + c] = sum;
     }
-    __syncthreads();                           // (also: every read of the logits tile and of s_p is done)
+    __syncthreads();                           // (also: every read of this logits tile and of s_p is done)
     if (tid < EC) colsum += ((s_red[tid] + s_red[EC + tid]) + s_red[2 * EC + tid]) + s_red[3 * EC + tid];
   }
   // ---- log(p_avg + eps) of the strip's columns, models/llava.py:732-735 ----
@@ -515,21 +529,29 @@ __global__ void __launch_bounds__(ER, BF16_STASH ? 2 : 1) entropy_kernel(const U
   __syncthreads();
 
   // ---- pass B: C = sum_v p log(p_avg + eps); one tile: its logits are still in shared memory ----
+  if (n_tiles > 1) load_tile<BF16_STASH>(p, tile_u32, row_base, 0, c0);
   for (int t = 0; t < n_tiles; ++t) {
     if (n_tiles > 1) {
-      load_tile<BF16_STASH>(p, tile_u32, row_base, t * ER, c0);
-      cp_async_wait<0>();
+      if (t + 1 < n_tiles) {
+        load_tile<BF16_STASH>(p, tile_u32 + ((t + 1) & 1) * C::kTileBytes, row_base, (t + 1) * ER, c0);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
       __syncthreads();
     }
-    const int r = t * ER + tid;
+    const int r = t * ER + trow;
+    const uint8_t* xrow = s_tile + (t & 1) * C::kTileBytes + trow * C::kLd;
+    const size_t grow = row_base + r;
+    float acc_c = 0.f, iz = 0.f;
     if (r < p.n_vis) {
-      const size_t grow = row_base + r;
       const float4 st = reinterpret_cast<const float4*>(p.row_stats)[grow];
-      const float mneg = -st.x * kLog2e, iz = st.y;
-      float acc_c = 0.f;
+      const float mneg = -st.x * kLog2e;
+      iz = st.y;
       auto body = [&](auto padded) {
 #pragma unroll 2
-        for (int g = 0; g < EC / 8; ++g) {
+        for (int gi = 0; gi < 4; ++gi) {
+          const int g = half * 4 + gi;
           float x[8];
           tile_logits8<BF16_STASH>(xrow, g, x);
           const float4 l0 = *reinterpret_cast<const float4*>(s_lp + g * 8), l1 = *reinterpret_cast<const float4*>(s_lp + g * 8 + 4);
@@ -545,9 +567,10 @@ __global__ void __launch_bounds__(ER, BF16_STASH ? 2 : 1) entropy_kernel(const U
       };
       if (full) body(std::false_type{});
       else body(std::true_type{});
-      p.part_c[(size_t)es * R + grow] = acc_c * iz;
     }
-    if (n_tiles > 1) __syncthreads();          // the tile buffer is refilled next iteration
+    acc_c += __shfl_xor_sync(0xffffffffu, acc_c, 16);
+    if (half == 0 && r < p.n_vis) p.part_c[(size_t)es * R + grow] = acc_c * iz;
+    if (n_tiles > 1) __syncthreads();          // the buffer of tile t is refilled by the load issued next iteration
   }
 }
 
@@ -682,7 +705,7 @@ static int run_group(const CUtensorMap& ta, const CUtensorMap& tw, const UncPara
   const dim3 fgrid(ceil_div(p.R, kFinWarps));
   stats_finalize_kernel<<<fgrid, kFinWarps * 32, 0, st>>>(p);
   DD_CHECK_LAUNCH();
-  entropy_kernel<BF16_STASH><<<dim3(p.n_es, p.n_img), ER, EwCfg<BF16_STASH>::kSmem, st>>>(p);
+  entropy_kernel<BF16_STASH><<<dim3(p.n_es, p.n_img), kEwThreads, EwCfg<BF16_STASH>::kSmem, st>>>(p);
   DD_CHECK_LAUNCH();
   fused_finalize_kernel<<<ceil_div(p.R, kFinRows), kFinRows * kFinGroups, 0, st>>>(p, epi, alea, var, topk_ids);
   DD_CHECK_LAUNCH();
