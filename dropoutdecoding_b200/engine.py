@@ -211,6 +211,7 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         self.var = torch.zeros_like(self.epi)
         self.topk_ids = torch.zeros(B, n_vis, topk, **i32)
         self._unc_overflow = torch.zeros(1, **i32)      # rows whose top-k candidate list overflowed in stage (1)
+        self._unc_ws = None                             # scratch of stage (1) (logits stash), allocated at first use
         cos, sin = rope_table(D, cfg.rope_theta, max_seq + 1)
         self.cos, self.sin = cos.to(dev), sin.to(dev)
         self.scale = 1.0 / math.sqrt(D)
@@ -632,9 +633,11 @@ class DropoutDecodeEngine(SpeculativeSchedules):
 
     def uncertainty_stage(self, vis_hidden: torch.Tensor) -> None:
         """vis_hidden bf16 [B, n_vis, d] (final-norm hidden states of the visual rows)."""
-        e, a, v, ids, ovf = ops.uncertainty_project(vis_hidden.contiguous(), self.w.lm_head, topk=self.topk,
-                                                    round_logits=self.round_logits, return_overflow=True)
-        self.epi.copy_(e); self.alea.copy_(a); self.var.copy_(v); self.topk_ids.copy_(ids)
+        if self._unc_ws is None:
+            self._unc_ws = ops.uncertainty_workspace(self.B, self.n_vis, self.w.lm_head.shape[0], self.topk, self.epi.device)
+        *_, ovf = ops.uncertainty_project(vis_hidden.contiguous(), self.w.lm_head, topk=self.topk,
+                                          round_logits=self.round_logits, return_overflow=True, workspace=self._unc_ws,
+                                          out=(self.epi, self.alea, self.var, self.topk_ids))
         self._unc_overflow.copy_(ovf)      # checked at the next host synchronisation (generated())
 
     def first_token(self, last_hidden: torch.Tensor) -> None:

@@ -51,9 +51,18 @@ def mask_words(n_vis: int) -> int:
 
 
 # --------------------------------------------------------------------------------------------
+def uncertainty_workspace(n_img: int, n_vis: int, vocab: int, topk: int, device) -> torch.Tensor:
+    """Scratch of dd_uncertainty_project (dd_uncertainty_workspace_bytes): the logits stash of one image group plus the
+    per-row partials; reusable across calls of the same shape."""
+    need = _lib.load().dd_uncertainty_workspace_bytes(n_img, n_vis, vocab, topk)
+    return torch.empty(max(need, 1), dtype=torch.uint8, device=device)
+
+
 def uncertainty_project(h_vis: torch.Tensor, w_lm: torch.Tensor, topk: int = 5, round_logits: bool = False,
-                        workspace: Optional[torch.Tensor] = None, check: bool = True, return_overflow: bool = False):
+                        workspace: Optional[torch.Tensor] = None, check: bool = True, return_overflow: bool = False,
+                        out: Optional[Sequence[torch.Tensor]] = None):
     """h_vis bf16 [n_img, n_vis, d], w_lm bf16 [V, d] -> (epi, alea, var fp32 [n_img, n_vis], topk_ids int32).
+    out = (epi, alea, var, topk_ids): contiguous result tensors to write into (the engine's own state).
 
     A row whose top-k candidate list overflowed on the device (more logits tied at its threshold than the list holds)
     is an error, never a silently shorter list: check=True reads the device counter (one stream synchronisation) and
@@ -68,9 +77,19 @@ def uncertainty_project(h_vis: torch.Tensor, w_lm: torch.Tensor, topk: int = 5, 
     if w_lm.shape[1] != d:
         raise DropDecError("w_lm and h_vis disagree on d")
     dev = h_vis.device
-    epi = torch.empty(n_img, n_vis, dtype=torch.float32, device=dev)
-    alea, var = torch.empty_like(epi), torch.empty_like(epi)
-    ids = torch.empty(n_img, n_vis, topk, dtype=torch.int32, device=dev)
+    if out is not None:
+        epi, alea, var, ids = out
+        for t, name in ((epi, "epi"), (alea, "alea"), (var, "var")):
+            _need(t, torch.float32, name)
+            if tuple(t.shape) != (n_img, n_vis):
+                raise DropDecError(f"{name} must be [{n_img}, {n_vis}]")
+        _need(ids, torch.int32, "topk_ids")
+        if tuple(ids.shape) != (n_img, n_vis, topk):
+            raise DropDecError(f"topk_ids must be [{n_img}, {n_vis}, {topk}]")
+    else:
+        epi = torch.empty(n_img, n_vis, dtype=torch.float32, device=dev)
+        alea, var = torch.empty_like(epi), torch.empty_like(epi)
+        ids = torch.empty(n_img, n_vis, topk, dtype=torch.int32, device=dev)
     need = L.dd_uncertainty_workspace_bytes(n_img, n_vis, V, topk)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)

@@ -501,8 +501,8 @@ def test_uncertainty_batched_images_and_bf16_rounding(ops, cuda):
 @pytest.mark.parametrize("n_img,n_vis,d,V,k", [(1, 1500, 128, 3000, 10), (2, 700, 64, 1111, 5)],
                          ids=["next_1500_rows_3_chunks", "two_images_700_rows"])
 def test_uncertainty_more_rows_than_tmem_holds(ops, cuda, n_img, n_vis, d, V, k):
-    """LLaVA-NeXT anyres yields up to ~2.9k visual tokens; beyond 640 rows the column mean p_avg is
-    formed in its own sweep (STATS -> COLSUM -> CROSS) instead of inside one TMEM-resident strip."""
+    """LLaVA-NeXT anyres yields up to ~2.9k visual tokens: several 256-row GEMM tiles and 128-row entropy tiles per
+    image, a last row group that fills only one accumulator, a last vocabulary strip that is partly padding."""
     from oracle import calculate_vision_uncertainty, topk_token_ids
     g = torch.Generator().manual_seed(n_vis)
     h = r16(torch.randn(n_img, n_vis, d, generator=g))
@@ -516,6 +516,46 @@ def test_uncertainty_more_rows_than_tmem_holds(ops, cuda, n_img, n_vis, d, V, k)
             want = ref[key][0]
             rel = ((got[i].cpu() - want).abs() - atol) / want.abs()
             assert rel.max() <= 1e-3, f"{key}: {rel.max():.2e}"
+        srt = torch.sort(logits, dim=-1, descending=True).values
+        safe = (srt[:, k - 1] - srt[:, k]) > 1e-4 * srt[:, 0].abs().clamp(min=1)
+        want_ids = torch.sort(topk_token_ids(logits[None], k)[1][0], -1).values
+        got_ids = torch.sort(ids[i].cpu().long(), -1).values
+        assert torch.equal(got_ids[safe], want_ids[safe])
+
+
+@pytest.mark.parametrize("n_img,n_vis,d,V,k,rnd", [(1, 1, 64, 100, 5, False), (1, 129, 64, 257, 3, True),
+                                                   (5, 1200, 64, 700, 5, True), (3, 2000, 64, 320, 4, False),
+                                                   (2, 128, 128, 32001, 10, True)],
+                         ids=["one_row", "129_rows_257_cols", "two_image_groups_bf16", "three_image_groups_fp32",
+                              "instructblip_vocab"])
+def test_uncertainty_groups_edges_and_determinism(ops, cuda, n_img, n_vis, d, V, k, rnd):
+    """Image groups (the stash holds <= 4608 rows: 5 x 1200 rows = 3 + 2 images, 3 x 2000 rows = 2 + 1), a single
+    row, tiles with one valid row, a vocabulary that ends inside a 64-column strip; results written into caller
+    tensors (out=) equal the returned ones and a second run is bit-identical (every partial is summed in a fixed
+    order)."""
+    from oracle import calculate_vision_uncertainty, topk_token_ids
+    g = torch.Generator().manual_seed(1000 * n_img + n_vis)
+    h = r16(torch.randn(n_img, n_vis, d, generator=g))
+    w = r16(torch.randn(V, d, generator=g) * 0.3)
+    hd, wd = h.to(cuda).bfloat16(), w.to(cuda).bfloat16()
+    epi, alea, var, ids = ops.uncertainty_project(hd, wd, topk=k, round_logits=rnd)
+    out = (torch.empty_like(epi), torch.empty_like(alea), torch.empty_like(var), torch.empty_like(ids))
+    ws = ops.uncertainty_workspace(n_img, n_vis, V, k, cuda)
+    ws.fill_(0x7f)                                             # stale scratch must not matter
+    ops.uncertainty_project(hd, wd, topk=k, round_logits=rnd, out=out, workspace=ws)
+    for a, b in zip((epi, alea, var, ids), out):
+        assert torch.equal(a, b)
+    for i in range(n_img):
+        logits = h[i] @ w.T
+        if rnd:
+            logits = r16(logits)
+        ref = calculate_vision_uncertainty(logits[None])
+        # (a single row is its own average: epi = A - C is a difference of two O(1) fp32 sums around zero)
+        for got, key, atol in ((epi, "epis_uncert_per_token", 5e-6), (alea, "alea_uncert_per_token", 2e-6),
+                               (var, "variance_per_token", 1e-9)):
+            want = ref[key][0]
+            rel = ((got[i].cpu() - want).abs() - atol) / want.abs().clamp_min(1e-30)
+            assert rel.max() <= 1e-3, f"image {i} {key}: {rel.max():.2e}"
         srt = torch.sort(logits, dim=-1, descending=True).values
         safe = (srt[:, k - 1] - srt[:, k]) > 1e-4 * srt[:, 0].abs().clamp(min=1)
         want_ids = torch.sort(topk_token_ids(logits[None], k)[1][0], -1).values
