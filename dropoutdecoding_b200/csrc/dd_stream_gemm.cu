@@ -523,6 +523,297 @@ static SgPlan sg_plan(int M, int N, int K, int epi) {
   return s;
 }
 
+// =============================================================================================
+// 129..256 rows, wide shapes (qkv, gate|up, lm_head): CTA PAIRS (tcgen05 cta_group::2).
+// At 256 rows a single CTA needs two accumulators, i.e. two MMAs per W tile and k-step: the stream is bound by the
+// tensor pipe of the SM (qkv: 704 cycles per 22 KB of W), not by HBM, and every CTA re-reads all 256 rows of x.  A pair
+// of CTAs (two SMs of one TPC) shares one tile instead: MMA M = 256 with rows [0,128) in the leader's TMEM and
+// [128,256) in its peer's, the W tile (B operand) split by rows between the two shared memories, x split by rows.  Per
+// k-block a CTA now ingests 128 rows of x (16 KB) + HALF the W tile and its tensor pipe does one MMA per k-step: twice
+// the W bytes per tensor-pipe cycle and per ingested byte.  74 pairs, tile width F = ceil16(N / (74 r)) <= 256.
+//   * both CTAs run TMA producers; the peer's copies signal the LEADER's full barrier (cp.async.bulk.tensor
+//     .cta_group::2, the barrier address mapped to rank 0), the leader arms it with the bytes of both;
+//   * the leader's MMA warp issues tcgen05.mma.cta_group::2; tcgen05.commit.multicast releases the ring slot / hands
+//     the accumulators over in BOTH CTAs; the peer's epilogue threads arrive on the leader's tmem_empty barrier
+//     through the cluster;
+//   * SwiGLU: one MMA for the gate rows and one for the up rows of a tile (each split between the CTAs), gate and up
+//     columns of a feature in the same TMEM lane as before.
+// Same per-element arithmetic as the single-CTA kernel: one fp32 accumulation over k in ascending order.
+// =============================================================================================
+constexpr int PG_PAIRS_MAX = 74;
+struct PgParams {
+  int M, N, K, epi;
+  int F;               // output features per tile (SwiGLU: gate features = up features = F)
+  int Fw;              // accumulator columns per tile (2F for SwiGLU)
+  int T, KB, G;        // tiles, k-blocks, pairs
+  int w_half;          // W bytes per k-block and CTA
+  int bks;             // k-blocks per pipeline stage (one mbarrier round trip per stage)
+  int stage_bytes, stages, acc_stages;
+  int S;               // K slices accumulated separately and added in slice order (1, 2, 4): the same summation order as
+                       // the single-CTA kernel's cluster split-K of this shape, so a row's result does not depend on M
+  const __nv_bfloat16* residual;
+  void* y;
+};
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far
+// have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+__device__ __forceinline__ void pg_store16(const PgParams& p, int m, int f, const float (&v0)[16], const float (&v1)[16]) {
+  SgParams q{};
+  q.N = p.N; q.epi = p.epi; q.residual = p.residual; q.y = p.y;
+  sg_store16(q, m, f, v0, v1);
+}
+
+__global__ void __launch_bounds__(SG_THREADS, 1)
+pair_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, const PgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  // bars: full[SG_MAX_STAGES] | empty[SG_MAX_STAGES] | tmem_full[2] | tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SG_MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();       // 0 = leader (rows 0..127, first half of the W tile)
+  const int pair = blockIdx.x >> 1;
+  const bool swiglu = p.epi == DD_EPI_SWIGLU;
+  constexpr int kXBytes = SG_BM * 128;           // 128 rows x 64 bf16
+
+  const uint32_t ring = smem_u32(smem);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * SG_MAX_STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * SG_MAX_STAGES, bar_tempty = bar_tfull + 16;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SG_MAX_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);      // (leader's is used) one arrive.expect_tx with the bytes of both CTAs
+      mbar_init(bar_empty + 8 * i, 1);     // tcgen05.commit (multicast)
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 2 * SG_EPI_THREADS);   // (leader's is used) the epilogue threads of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == SG_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs initialised, TMEM of both allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = pair < p.T ? (p.T - pair + p.G - 1) / p.G : 0;   // tiles pair, pair + G, ...
+
+  if (warp < SG_PROD_WARPS) {
+    // =========================== TMA producers (both CTAs; slot s belongs to warp s % 4) ===========================
+    if (warp == 0 && elect_one()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    }
+    const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
+    const uint32_t stage_tx = (uint32_t)(2 * p.bks * (kXBytes + p.w_half));
+    const int half_rows = p.F / 2;               // W rows of the tile held by one CTA (per gate / up part)
+    const int n_stage_kb = p.KB / p.bks;         // pipeline stages per tile
+    const int n_stage_total = my_tiles * n_stage_kb;
+    const uint32_t sub = (uint32_t)(kXBytes + p.w_half);
+    // one pipeline stage: (leader) its expect_tx, then the W boxes and / or the x boxes of its bks k-blocks
+    auto fill = [&](int i, int stage, bool arm, bool do_w, bool do_x) {
+      const int t = i / n_stage_kb, sk = i - t * n_stage_kb;
+      const int tile = pair + t * p.G;
+      const uint32_t dst = ring + stage * p.stage_bytes;
+      const uint32_t bar = mapa_cluster(bar_full + 8 * stage, 0);
+      if (arm && rank == 0) mbar_expect_tx(bar_full + 8 * stage, stage_tx);
+      const int wrow = tile * p.F + rank * half_rows;
+      for (int b = 0; b < p.bks; ++b) {
+        const int kcol = (sk * p.bks + b) * SG_BK;
+        if (do_x) tma_load_2d_pair(dst + b * sub, &tmap_x, bar, kcol, rank * SG_BM, pol_x);   // rows past M: zero-filled
+        if (do_w) {
+          tma_load_2d_pair(dst + b * sub + kXBytes, &tmap_w, bar, kcol, wrow, pol_w);   // (rows past the end of W too)
+          if (swiglu) tma_load_2d_pair(dst + b * sub + kXBytes + half_rows * 128, &tmap_w, bar, kcol, p.N + wrow, pol_w);
+        }
+      }
+    };
+    // round 0 (empty ring): the weights do not depend on the previous kernel of the stream -- under a programmatic
+    // dependent launch the whole ring of W tiles is in flight BEFORE griddepcontrol.wait, the activation tiles after
+    for (int stage = warp; stage < p.stages && stage < n_stage_total; stage += SG_PROD_WARPS) {
+      if (elect_one()) fill(stage, stage, true, true, false);
+      __syncwarp();
+    }
+    pdl_wait();
+    for (int stage = warp; stage < p.stages && stage < n_stage_total; stage += SG_PROD_WARPS) {
+      if (elect_one()) fill(stage, stage, false, false, true);
+      __syncwarp();
+    }
+    for (int round = 1; round * p.stages < n_stage_total; ++round) {
+      const uint32_t phase = (uint32_t)(round & 1);
+      for (int stage = warp; stage < p.stages; stage += SG_PROD_WARPS) {
+        const int i = round * p.stages + stage;
+        if (i >= n_stage_total) break;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (elect_one()) fill(i, stage, true, true, true);
+        __syncwarp();
+      }
+    }
+    pdl_trigger_stream_tail();
+  } else if (warp == SG_MMA_WARP) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    pdl_wait();
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(2 * SG_BM, p.F);
+      const int half_rows = p.F / 2;
+      int stage = 0, acc_stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        mbar_wait(bar_tempty + 8 * acc_stage, acc_phase ^ 1);  // both epilogues have drained this accumulator set
+        tc_fence_after();
+        const int kb_slice = p.KB / p.S;
+        const int n_stage_kb = p.KB / p.bks;
+        const uint32_t sub = (uint32_t)(kXBytes + p.w_half);
+        for (int sk = 0; sk < n_stage_kb; ++sk) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t base = ring + stage * p.stage_bytes;
+            for (int b = 0; b < p.bks; ++b) {
+              const int kb = sk * p.bks + b;
+              const int slice = kb / kb_slice;
+              const bool first = kb - slice * kb_slice == 0;      // first k-block of its K slice: overwrite
+              const uint32_t d0 = tmem_base + (acc_stage * p.S + slice) * p.Fw;
+              const uint64_t a_desc = make_smem_desc(base + b * sub);
+              const uint64_t b_desc = make_smem_desc(base + b * sub + kXBytes);
+#pragma unroll
+              for (int k = 0; k < SG_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+                umma_bf16_pair(d0, a_desc + 2 * k, b_desc + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+              if (swiglu) {
+                const uint64_t u_desc = make_smem_desc(base + b * sub + kXBytes + half_rows * 128);
+#pragma unroll
+                for (int k = 0; k < SG_BK / 16; ++k)
+                  umma_bf16_pair(d0 + p.F, a_desc + 2 * k, u_desc + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit_pair(bar_empty + 8 * stage);
+            if (sk == n_stage_kb - 1) umma_commit_pair(bar_tfull + 8 * acc_stage);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc_stage == p.acc_stages) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 5..12 of both CTAs) ===========================
+    pdl_wait();   // (reads the residual, writes y)
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int g = (warp - SG_EPI_WARP0) >> 2;     // warp group 0 / 1: the groups alternate over the 16-feature chunks
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int n_chunks = p.F / 16;
+    const int m = rank * SG_BM + q * 32 + lane;   // token row of this thread
+    const uint32_t leader_tempty = mapa_cluster(bar_tempty, 0);
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = pair + t * p.G;
+      mbar_wait(bar_tfull + 8 * acc_stage, acc_phase);
+      tc_fence_after();
+      const uint32_t t0 = lane_addr + acc_stage * p.S * p.Fw;
+      for (int c = g; c < n_chunks; c += 2) {
+        float v0[16], v1[16];
+        tmem_ld16(t0 + c * 16, v0);
+        if (swiglu) tmem_ld16(t0 + p.F + c * 16, v1);
+        for (int sl = 1; sl < p.S; ++sl) {   // (never SwiGLU) the further K slices, added in slice order
+          tmem_ld16(t0 + sl * p.Fw + c * 16, v1);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v0[e] += v1[e];
+        }
+        const int f = tile * p.F + c * 16;
+        if (m < p.M && f < p.N) pg_store16(p, m, f, v0, swiglu ? v1 : v0);
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(leader_tempty + 8 * acc_stage);
+      if (++acc_stage == p.acc_stages) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();      // nobody still reads the peer's shared memory / TMEM
+  if (warp == SG_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+struct PgPlan {
+  int F, Fw, T, G, w_half, bks, stage_bytes, stages, acc_stages, S;
+  size_t smem;
+  bool ok;
+};
+static PgPlan pg_plan(int M, int N, int K, int epi) {
+  PgPlan s{};
+  const bool swiglu = epi == DD_EPI_SWIGLU;
+  const int pairs = sg_num_sms() / 2 < PG_PAIRS_MAX ? sg_num_sms() / 2 : PG_PAIRS_MAX;
+  // tile width: the fewest rounds r of `pairs` tiles whose tiles are at most 256 features wide (an MMA's N), and
+  // narrow enough that the accumulators fit the TMEM (SwiGLU: gate + up)
+  const int fmax = 256;
+  int r = 1, F = 0;
+  for (;; ++r) {
+    F = (ceil_div(N, pairs * r) + 15) / 16 * 16;
+    if (F <= fmax && (swiglu ? 2 * F : F) <= 512) break;
+  }
+  if (F < 32) F = 32;
+  s.F = F;
+  s.Fw = swiglu ? 2 * F : F;
+  s.T = ceil_div(N, F);
+  s.G = s.T < pairs ? s.T : pairs;
+  s.w_half = (s.Fw / 2) * 128;
+  s.S = sg_plan(M, N, K, epi).S;                   // the K slicing of the single-CTA kernel for this (N, K)
+  const int fixed = 1024 + (2 * SG_MAX_STAGES + 4) * 8 + 16;
+  const int kb_bytes = SG_BM * 128 + s.w_half;     // (a multiple of 1024: F % 16 == 0)
+  // two k-blocks per stage when that still leaves a ring of >= 3 stages: the MMA issuer pays one barrier round trip
+  // (~300 cycles) per stage, as much as the 4 MMAs of a narrow k-block take
+  s.bks = 1;
+  if ((K / SG_BK / (s.S > 0 ? s.S : 1)) % 2 == 0 && (SG_SMEM_LIMIT - fixed) / (2 * kb_bytes) >= 3) s.bks = 2;
+  s.stage_bytes = s.bks * kb_bytes;
+  int st = (SG_SMEM_LIMIT - fixed) / s.stage_bytes;
+  s.stages = st > SG_MAX_STAGES ? SG_MAX_STAGES : st;
+  s.acc_stages = (s.T > s.G && 2 * s.S * s.Fw <= 512) ? 2 : 1;
+  s.smem = (size_t)fixed + (size_t)s.stages * s.stage_bytes;
+  // when M needs the second accumulator and the shape is wide: the 4096-wide o_proj / down tiles would be 64 features
+  // (x dominates the ingest, N=64 MMAs are issue-bound) -- measured 22.1 / 60.7 us against 22.9 / 36.5 us on the cluster
+  // split-K path, where they stay
+  s.ok = M > SG_BM && N >= 8192 && s.stages >= 3 && (s.F / 2) % 8 == 0 && s.S * s.Fw <= 512 && (K / SG_BK) % s.S == 0;
+  return s;
+}
+
 static int sg_check(const char* fn, int M, int N, int K, int epi) {
   DD_CHECK_ARG(M >= 1 && M <= 256, "%s: M=%d out of [1,256]", fn, M);
   DD_CHECK_ARG(K >= SG_BK && K % SG_BK == 0, "%s: K=%d must be a positive multiple of %d", fn, K, SG_BK);
@@ -557,9 +848,58 @@ extern "C" int dd_stream_gemm(const void* x, const void* w, const void* residual
     set_error("dd_stream_gemm: workspace %zu < %zu bytes", workspace_bytes, SG_WS_BYTES);
     return DD_ERR_WORKSPACE;
   }
+  const int w_rows = epilogue == DD_EPI_SWIGLU ? 2 * N : N;
+  {
+    static const bool pair_on = [] { const char* e = getenv("DD_PAIR_GEMM"); return !(e && e[0] == '0'); }();
+    const PgPlan g = pg_plan(M, N, K, epilogue);
+    if (pair_on && g.ok) {
+      CUtensorMap tw, tx;
+      {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)w_rows};
+        const uint64_t strides[1] = {(uint64_t)K * 2};
+        const uint32_t box[2] = {SG_BK, (uint32_t)(g.F / 2)};
+        if (int rc = make_tmap_bf16_sw128(&tw, w, 2, dims, strides, box, "dd_stream_gemm(w, pair)")) return rc;
+      }
+      {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        const uint64_t strides[1] = {(uint64_t)K * 2};
+        const uint32_t box[2] = {SG_BK, (uint32_t)SG_BM};
+        if (int rc = make_tmap_bf16_sw128(&tx, x, 2, dims, strides, box, "dd_stream_gemm(x, pair)")) return rc;
+      }
+      PgParams p{};
+      p.M = M; p.N = N; p.K = K; p.epi = epilogue; p.F = g.F; p.Fw = g.Fw; p.T = g.T; p.KB = K / SG_BK; p.G = g.G;
+      p.w_half = g.w_half; p.bks = g.bks; p.stage_bytes = g.stage_bytes; p.stages = g.stages; p.acc_stages = g.acc_stages; p.S = g.S;
+      p.residual = static_cast<const __nv_bfloat16*>(residual);
+      p.y = y;
+      {
+        static bool attr_set[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+          DD_CHECK_CUDA(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_LIMIT));
+          if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+      }
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * g.G);
+      cfg.blockDim = dim3(SG_THREADS);
+      cfg.dynamicSmemBytes = g.smem;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl_enabled() ? 2 : 1;
+      DD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pair_gemm_kernel, tw, tx, p));
+      return DD_OK;
+    }
+  }
   const SgPlan s = sg_plan(M, N, K, epilogue);
   DD_CHECK_ARG(s.stages >= 2, "dd_stream_gemm: M=%d, N=%d leave no room for a 2-stage ring", M, N);
-  const int w_rows = epilogue == DD_EPI_SWIGLU ? 2 * N : N;
   CUtensorMap tw, tx;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)w_rows};
