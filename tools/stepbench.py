@@ -57,7 +57,7 @@ with torch.no_grad():
         best = min(best, e0.elapsed_time(e1) / a.steps)
     wbytes = 2 * w.stream_bytes_per_pass()
     kv = 2 * a.batch * (a.seq + a.steps / 2) * cfg.n_layers * cfg.n_kv_heads * cfg.head_dim * 2 * 2
-    print(json.dumps(dict(lib=os.environ.get("DD_LIB", "default"), pdl=os.environ.get("DD_PDL", "auto"), model=a.model,
+    print(json.dumps(dict(lib=os.environ.get("DD_LIB", "default"), pdl=os.environ.get("DD_PDL", "auto"), pair_gemm=os.environ.get("DD_PAIR_GEMM", "1"), model=a.model,
                           batch=a.batch, K=len(probs), ms_per_step=round(best, 4),
                           tokens_per_s=round(a.batch * 1e3 / best, 1),
                           step_roofline_frac=round((wbytes + kv) / (best * 1e-3) / 6551.4e9, 3),
