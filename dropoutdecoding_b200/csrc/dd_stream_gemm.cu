@@ -31,7 +31,8 @@
 //   * warps 0-3 = TMA producers, warp 4 = MMA issuer (one elected lane), warps 5-12 = epilogue (tcgen05.ld
 //     32x32b: one thread = one token row, 16 features per load = one 32-byte store) with the HF rounding points
 //     of dd_skinny_gemm.
-// Every output element is one fp32 accumulation over k in ascending order, whatever M is: results are
+//   * 129..256 rows on the wide shapes: CTA pairs (cta_group::2), see pair_gemm_kernel below.
+// Every output element is one fp32 accumulation over k in ascending order (per K slice), whatever M is: results are
 // row-independent and bit-reproducible.  No workspace is used (the parameter is kept for ABI stability).
 // Algorithmic bytes per launch: N*K*2 (x2 for SwiGLU) -- the weights, read exactly once.
 #include <cstdlib>
