@@ -385,7 +385,9 @@ def run_target(model, args, rank, world, local, dist, hbm, tf):
                "value": round(total * T / dt, 2), "unit": "tokens/s", "n_gpus": world, "batch_per_gpu": B,
                "new_tokens": T, "ms_per_token": round(dt / T * 1e3, 4), "per_rank_ms": per_rank_ms,
                "rows_per_pass": rows, "passes": passes,
-               "gemm": "dd::stream_gemm_kernel" if eng._use_stream(rows) else ("dd::skinny_gemm_kernel" if rows <= 32 else "library"),
+               "gemm": (("dd::pair_gemm_kernel (qkv, gate/up, lm_head) + dd::stream_gemm_kernel (o_proj, down)" if rows > 128
+                         else "dd::stream_gemm_kernel") if eng._use_stream(rows)
+                        else ("dd::skinny_gemm_kernel" if rows <= 32 else "library")),
                "fallback_rate": round(eng.fallback_rate(), 4), "gpu_launches": int(eng.launch_count),
                "pass_roofline": {"bound": "hbm", "bytes_per_pass": int(pass_bytes), "passes": passes,
                                  "achieved": round(pass_bytes * passes / dt_rank / 1e9, 1), "peak": hbm, "unit": "GB/s",
@@ -425,7 +427,9 @@ def run_target(model, args, rank, world, local, dist, hbm, tf):
             x = pbuf.xn[:rows]
             t_g = timeit(lambda: ops.stream_gemm(x, lw["wgu"], ops.EPI_SWIGLU, out=pbuf.act[:rows], workspace=eng._sg_ws))
             wb = lw["wgu"].numel() * 2
-            out["stream_gemm_gate_up"] = {"bound": "hbm", "kernel": "dd::stream_gemm_kernel", "rows": rows,
+            out["stream_gemm_gate_up"] = {"bound": "hbm",
+                                          "kernel": "dd::pair_gemm_kernel" if rows > 128 else "dd::stream_gemm_kernel",
+                                          "rows": rows,
                                           "us": round(t_g * 1e6, 2), "achieved": round(wb / t_g / 1e9, 1), "peak": hbm,
                                           "unit": "GB/s", "frac": round(wb / t_g / 1e9 / hbm, 4), "algorithmic_bytes": wb,
                                           "traffic": int(1.03 * wb),

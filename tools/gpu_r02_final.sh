@@ -12,6 +12,7 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_r
 timeout 300 python tools/microbench.py uncertainty > $OUT/uncertainty_onesweep.jsonl 2> $OUT/microbench.err; echo "microbench unc rc=$?"; cut -c1-200 $OUT/uncertainty_onesweep.jsonl
 timeout 300 python tools/microbench.py attention > $OUT/attention_microbench.jsonl 2>> $OUT/microbench.err; echo "microbench attn rc=$?"
 timeout 300 ./tools/_bin/sgemm_bench 4 16 24 32 64 128 192 256 > $OUT/stream_gemm_v5.jsonl 2> $OUT/sgemm.err; echo "sgemm rc=$?"
+DD_PDL=1 timeout 300 ./tools/_bin/sgemm_bench 32 64 128 192 256 > $OUT/stream_gemm_v5_chain_launch.jsonl 2>> $OUT/sgemm.err; echo "sgemm (dependent launch) rc=$?"
 for b in 1 2 4 8 16 32 64; do timeout 300 python tools/stepbench.py --batch $b --steps 63 >> $OUT/stepbench.jsonl 2>> $OUT/stepbench.err; done
 for b in 8 64; do DD_PDL=0 timeout 300 python tools/stepbench.py --batch $b --steps 63 >> $OUT/stepbench.jsonl 2>> $OUT/stepbench.err; DD_PAIR_GEMM=0 timeout 300 python tools/stepbench.py --batch $b --steps 63 >> $OUT/stepbench.jsonl 2>> $OUT/stepbench.err; DD_GEMM=library timeout 300 python tools/stepbench.py --batch $b --steps 63 >> $OUT/stepbench.jsonl 2>> $OUT/stepbench.err; done
 timeout 300 python tools/stepbench.py --model next --batch 16 --probs 0.1,0.2,0.3,0.4,0.5,0.6,0.7,0.8 --mode independent --seq 2900 --n-vis 2880 --topk 10 --steps 32 >> $OUT/stepbench.jsonl 2>> $OUT/stepbench.err
