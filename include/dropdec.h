@@ -65,9 +65,11 @@ int dd_set_chain_launch(int on);
  * get_topk_token_id (models/llava.py:428-441) and calculate_vision_uncertainty
  * (models/llava.py:710-756; twins llavanext.py:878-924, instructblip.py:511-557).
  *
- * logits[i,v] = <h_vis[img,i,:], w_lm[v,:]> is produced tile by tile on the tcgen05 tensor
- * cores (TMA -> smem -> UMMA -> TMEM) and reduced in the epilogue; the [n_vis x vocab]
- * logits never exist in HBM.  Per image:
+ * logits[i,v] = <h_vis[img,i,:], w_lm[v,:]> is produced ONCE, tile by tile on the tcgen05 tensor
+ * cores (TMA -> smem -> UMMA -> TMEM); the epilogue keeps the softmax statistics and parks the logits
+ * (bf16 if round_logits_bf16, else fp32) in a scratch inside the workspace that element-wise kernels
+ * then walk for the entropy / KL terms -- no fp32 [n_vis x vocab] temporaries, 37 MB per
+ * LLaVA-1.5 image (L2-sized), at most ~0.6 GB per call whatever the batch.  Per image:
  *   p = softmax(logits), p_avg[v] = mean_i p[i,v]
  *   epi[i]  = sum_v p (log(p+1e-10) - log(p_avg+1e-10))
  *   alea[i] = -sum_v p log(p+1e-10)
@@ -76,8 +78,7 @@ int dd_set_chain_launch(int on);
  * round_logits_bf16 != 0 rounds each logit to bf16 before the softmax, which is what the
  * reference's `lm_head(...)` in half precision followed by `.float()` does
  * (models/llama.py:46-47).
- * Limits: d % 64 == 0, n_vis <= 8192 per image, topk <= DD_MAX_TOPK.  Images of up to 640 visual tokens
- * take two GEMM sweeps; larger ones (LLaVA-NeXT anyres) three, because p_avg then needs its own sweep.
+ * Limits: d % 64 == 0, n_vis <= 8192 per image, topk <= DD_MAX_TOPK.
  * Top-k ids come from a per-row candidate list of bounded size; a row whose list overflows (more than
  * 96*topk + 64 logits tied at or above its threshold) is counted in an int32 at byte offset
  * dd_uncertainty_overflow_offset(...) of the workspace, valid once the stream has reached the end of the call.
