@@ -351,16 +351,17 @@ __global__ void __launch_bounds__(kFinWarps * 32) stats_finalize_kernel(const Un
 // ------------------------------------------------------------------------------------------
 // The element-wise passes over the stash
 // ------------------------------------------------------------------------------------------
-// CTA = (image, strip of EC = 64 vocabulary columns), 256 threads.  The strip is walked in tiles of ER = 128 rows: a
+// CTA = (image, strip of EC = 64 vocabulary columns), 128 threads.  The strip is walked in tiles of ER = 64 rows: a
 // tile is copied stash -> shared memory with cp.async (coalesced 128-byte rows, double buffered), then TWO THREADS OWN
 // ONE ROW (32 columns each; lanes 0-15 / 16-31 of a warp hold the two halves of 16 rows, so a quarter-warp touches 8
 // consecutive padded rows: conflict-free 128-bit accesses): the logits come out of shared memory as 128-bit loads and
 // the row sums A, Q, C are thread-local plus one shuffle (a warp per row spends as many instructions on the shuffle
 // reductions and per-row bookkeeping as on the math: measured 40 instructions per logit, 65 us per image).  The column
-// sums are the transposed reduction: p goes to a padded fp32 tile in shared memory and thread (column, row quarter)
-// adds it up in row order -- fixed order, deterministic.  72 KB of shared memory: three CTAs per SM.
+// sums are the transposed reduction: p goes to a padded fp32 tile in shared memory and thread (column, row half)
+// adds it up in row order -- fixed order, deterministic.  36 KB of shared memory: six CTAs per SM, so the 501 CTAs of one
+// LLaVA-1.5 image are resident at once (with 256-thread CTAs at three per SM they ran as a full wave plus an eighth).
 constexpr int EC = 64;                       // columns per strip
-constexpr int ER = 128;                      // rows per tile
+constexpr int ER = 64;                       // rows per tile
 constexpr int kEwThreads = 2 * ER;
 constexpr int kPLd = EC + 4;                 // padded row of the p tile (floats): 128-bit row stores and column reads
                                              // are both conflict-free
@@ -371,8 +372,8 @@ struct EwCfg {
   static constexpr int kLd = kRowBytes + 16;             // padded row of the logits tile (bytes)
   static constexpr int kTileBytes = ER * kLd;
   static constexpr int kChunksPerRow = kRowBytes / 16;   // 8 / 16
-  static constexpr size_t kSmem = 2 * (size_t)kTileBytes + (size_t)ER * kPLd * 4 + 4 * EC * 4 + EC * 4 + 16;
-  static constexpr int kCtasPerSm = BF16_STASH ? 3 : 2;
+  static constexpr size_t kSmem = 2 * (size_t)kTileBytes + (size_t)ER * kPLd * 4 + 2 * EC * 4 + EC * 4 + 16;
+  static constexpr int kCtasPerSm = BF16_STASH ? 6 : 4;
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
@@ -433,8 +434,8 @@ __global__ void __launch_bounds__(kEwThreads, EwCfg<BF16_STASH>::kCtasPerSm) ent
   extern __shared__ __align__(16) uint8_t ew_smem[];
   uint8_t* s_tile = ew_smem;                                              // [2][ER][kLd]
   float* s_p = reinterpret_cast<float*>(ew_smem + 2 * C::kTileBytes);     // [ER][kPLd]
-  float* s_red = s_p + ER * kPLd;                                         // [4][EC]
-  float* s_lp = s_red + 4 * EC;                                           // [EC]
+  float* s_red = s_p + ER * kPLd;                                         // [2][EC]
+  float* s_lp = s_red + 2 * EC;                                           // [EC]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int trow = warp * 16 + (lane & 15);    // row of the tile
   const int half = lane >> 4;                  // columns [32*half, 32*half + 32) of the strip
@@ -506,16 +507,16 @@ __global__ void __launch_bounds__(kEwThreads, EwCfg<BF16_STASH>::kCtasPerSm) ent
     if (half == 0 && r < p.n_vis)
       reinterpret_cast<float2*>(p.part_aq)[(size_t)es * R + grow] = make_float2(acc_a * 0.6931471805599453f, acc_q);
     __syncthreads();
-    {  // column sums of the tile: thread (column, row quarter) in row order, then the quarters in order
-      const int c = tid & (EC - 1), rq = tid / EC;
-      const float* col = s_p + (rq * (ER / 4)) * kPLd + c;
+    {  // column sums of the tile: thread (column, row half) in row order, then the halves in order
+      const int c = tid & (EC - 1), rh = tid / EC;
+      const float* col = s_p + (rh * (ER / 2)) * kPLd + c;
       float sum = 0.f;
 #pragma unroll 16
-      for (int i = 0; i < ER / 4; ++i) sum += col[i * kPLd];
-      s_red[rq * EC + c] = sum;
+      for (int i = 0; i < ER / 2; ++i) sum += col[i * kPLd];
+      s_red[rh * EC + c] = sum;
     }
     __syncthreads();                           // (also: every read of this logits tile and of s_p is done)
-    if (tid < EC) colsum += ((s_red[tid] + s_red[EC + tid]) + s_red[2 * EC + tid]) + s_red[3 * EC + tid];
+    if (tid < EC) colsum += s_red[tid] + s_red[EC + tid];
   }
   // ---- log(p_avg + eps) of the strip's columns, models/llava.py:732-735 ----
   if (tid < EC) s_lp[tid] = __logf(colsum / (float)p.n_vis + kEps);
