@@ -1,3 +1,5 @@
+"""Two calls of dd_uncertainty_project for ncu (no timing loop).
+Usage: ncu --metrics gpu__time_duration.sum ... python tools/unc_prof.py <n_images> <n_vis>"""
 import sys, torch, math
 sys.path.insert(0, '.')
 from dropoutdecoding_b200 import ops
