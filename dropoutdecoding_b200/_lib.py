@@ -27,6 +27,7 @@ _SIGNATURES = {
     "dd_version": (C.c_int, []),
     "dd_last_error": (C.c_char_p, []),
     "dd_set_chain_launch": (C.c_int, [C.c_int]),
+    "dd_hint_l2_prefetch": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t]),
     "dd_uncertainty_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "dd_uncertainty_overflow_offset": (C.c_size_t, [C.c_int] * 4),
     "dd_uncertainty_project": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -55,7 +55,24 @@ bool pdl_enabled() {
   }
   return g_pdl == 1;
 }
+
+static thread_local L2Prefetch g_l2_prefetch{};
+L2Prefetch take_l2_prefetch() {
+  const L2Prefetch pf = g_l2_prefetch;
+  g_l2_prefetch = L2Prefetch{};
+  return pf;
+}
 }  // namespace dd
+
+extern "C" int dd_hint_l2_prefetch(const void* p0, size_t bytes0, const void* p1, size_t bytes1) {
+  using namespace dd;
+  DD_CHECK_ARG((bytes0 == 0 || p0) && (bytes1 == 0 || p1), "dd_hint_l2_prefetch: null range");
+  DD_CHECK_ARG(((uintptr_t)p0 & 15) == 0 && ((uintptr_t)p1 & 15) == 0 && bytes0 % 16 == 0 && bytes1 % 16 == 0,
+               "dd_hint_l2_prefetch: ranges must be 16-byte aligned and a multiple of 16 bytes long");
+  g_l2_prefetch.ptr[0] = (const char*)p0; g_l2_prefetch.bytes[0] = bytes0;
+  g_l2_prefetch.ptr[1] = (const char*)p1; g_l2_prefetch.bytes[1] = bytes1;
+  return DD_OK;
+}
 
 extern "C" int dd_version(void) { return 100; }  // 0.1.0
 extern "C" int dd_set_chain_launch(int on) {

@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t swz_kv(int row, int chunk) {
 template <int D, int QT>
 __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid_constant__ CUtensorMap tmap_k,
                                                                     const __grid_constant__ CUtensorMap tmap_v,
-                                                                    const AttnParams p) {
+                                                                    const AttnParams p, const L2Prefetch pf) {
   constexpr int CH = D / 8;            // 16-byte chunks per row
   constexpr int ROW_B = D * 2;         // bytes per row
   constexpr int TILE_B = kTileKeys * ROW_B;
@@ -119,8 +119,12 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
   const int G = p.H / p.H_kv, R = p.M * G;
   pdl_trigger_stream_entry();
   pdl_wait();
-  if (p.seq_active && p.seq_active[b] == 0 && !(p.seq_active2 && p.seq_active2[b] != 0))
+  const unsigned cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const unsigned n_cta = gridDim.x * gridDim.y * gridDim.z;
+  if (p.seq_active && p.seq_active[b] == 0 && !(p.seq_active2 && p.seq_active2[b] != 0)) {
+    if (warp) l2_prefetch_slice(pf, cta_lin * (kAttnWarps - 1) + (warp - 1), n_cta * (kAttnWarps - 1));
     return;  // CTA-uniform: nothing of this sequence is read
+  }
   const int S0 = p.seq_lens[b];
   int any_extra = 0;
   if (p.len_extra)
@@ -161,6 +165,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
     for (int s = 0; s < kStages - 1; ++s)
       if (s < ntiles) load_tile(s, s);
   }
+  // L2 prefetch hint (dd_hint_l2_prefetch): warps 1.. issue it behind the ring's first K/V tiles
+  if (warp) l2_prefetch_slice(pf, cta_lin * (kAttnWarps - 1) + (warp - 1), n_cta * (kAttnWarps - 1));
   for (int idx = tid; idx < 16 * QT * CH; idx += kAttnThreads) {
     const int r = idx / CH, c = idx % CH;
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -430,7 +436,8 @@ static size_t attn_smem_bytes(int M, int mask_words) {
 }
 
 template <int D, int QT>
-static int launch_attn(const AttnParams& p, const void* k_new, const void* v_new, void* out, cudaStream_t st) {
+static int launch_attn(const AttnParams& p, const L2Prefetch& pf, const void* k_new, const void* v_new, void* out,
+                       cudaStream_t st) {
   // K / V of one layer as [B*H_kv][S_max][D]; a box is 64 keys x 64 dims (128 B rows, SWIZZLE_128B)
   CUtensorMap tmap_k, tmap_v;
   {
@@ -453,7 +460,7 @@ static int launch_attn(const AttnParams& p, const void* k_new, const void* v_new
     }
   }
   DD_LAUNCH_CHAIN(attn_partial_kernel<D, QT>, dim3(p.num_splits, p.H_kv, p.B), dim3(kAttnThreads), smem, st, tmap_k,
-                  tmap_v, p);
+                  tmap_v, p, pf);
   (void)k_new; (void)v_new; (void)out;
   if (p.num_splits == 1) DD_LAUNCH_CHAIN(attn_merge_kernel<D>, dim3(p.H, p.M, p.B), dim3(D), 0, st, p);
   return DD_OK;
@@ -495,6 +502,7 @@ extern "C" int dd_decode_attention_windows(const void* q, const void* k_new, con
                                            int n_vis, int mask_words, float scale, int num_splits, void* out,
                                            void* workspace, size_t workspace_bytes, dd_stream_t stream) {
   using namespace dd;
+  const L2Prefetch pf = take_l2_prefetch();  // one-shot: consumed even when the call is refused below
   DD_CHECK_ARG(!len_extra || num_splits == 1,
                "dd_decode_attention: per-member key windows (len_extra) need num_splits == 1 (the split points of a "
                "sequence depend on its length, so members of different lengths cannot share split partials bit-exactly)");
@@ -534,6 +542,7 @@ extern "C" int dd_decode_attention_windows(const void* q, const void* k_new, con
   p.scale_log2 = scale * 1.4426950408889634f;
   const int R = M * (H / H_kv);
   cudaStream_t st = (cudaStream_t)stream;
-  if (D == 128) return R <= 16 ? launch_attn<128, 1>(p, k_new, v_new, out, st) : launch_attn<128, 2>(p, k_new, v_new, out, st);
-  return R <= 16 ? launch_attn<64, 1>(p, k_new, v_new, out, st) : launch_attn<64, 2>(p, k_new, v_new, out, st);
+  if (D == 128)
+    return R <= 16 ? launch_attn<128, 1>(p, pf, k_new, v_new, out, st) : launch_attn<128, 2>(p, pf, k_new, v_new, out, st);
+  return R <= 16 ? launch_attn<64, 1>(p, pf, k_new, v_new, out, st) : launch_attn<64, 2>(p, pf, k_new, v_new, out, st);
 }

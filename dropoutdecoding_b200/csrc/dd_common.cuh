@@ -95,6 +95,39 @@ __device__ __forceinline__ void pdl_trigger_stream_tail() {
   if (DD_PDL_TRIGGER == 2) pdl_trigger_now();
 }
 
+// ---------------------------------------------------------------------------------------------
+// L2 prefetch riding on the latency-bound kernels of a small pass (dd_hint_l2_prefetch, include/dropdec.h).
+// With 4-16 rows the pass is one long HBM stream of weights, interrupted by kernels that leave HBM idle (decode
+// attention: ~14 us on ~10 MB of K/V; RMSNorm: ~4 us on a few rows).  Those kernels carry up to two address
+// ranges -- the head of the weight stream of the GEMMs that follow -- and their otherwise idle threads issue
+// cp.async.bulk.prefetch.L2 over them (fire and forget: no registers, no shared memory, no completion to wait
+// for), so the stream keeps running into the 126 MB L2 and the next GEMM starts on L2 hits.
+// ---------------------------------------------------------------------------------------------
+struct L2Prefetch {
+  const char* ptr[2];
+  unsigned long long bytes[2];  // multiples of 16; 0 = unused
+};
+// the hint left by dd_hint_l2_prefetch on this host thread; reading it clears it
+L2Prefetch take_l2_prefetch();
+
+constexpr unsigned kPrefetchChunk = 16384;  // bytes per prefetch instruction
+// The instruction takes its operands from uniform registers, so a warp is the natural worker (one lane issues; per-lane
+// addresses would be serialised by the compiler anyway): warp w of n_warps across the grid covers chunks
+// w, w + n_warps, ... of both ranges.  Call with all lanes of the warp.
+__device__ __forceinline__ void l2_prefetch_slice(const L2Prefetch& pf, unsigned warp_idx, unsigned n_warps) {
+  if ((threadIdx.x & 31) != 0) return;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const unsigned long long bytes = pf.bytes[r];
+    for (unsigned long long off = (unsigned long long)warp_idx * kPrefetchChunk; off < bytes;
+         off += (unsigned long long)n_warps * kPrefetchChunk) {
+      const unsigned long long left = bytes - off;
+      const unsigned sz = left < kPrefetchChunk ? (unsigned)left : kPrefetchChunk;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.ptr[r] + off), "r"(sz) : "memory");
+    }
+  }
+}
+
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -11,12 +11,18 @@ namespace dd {
 // RMSNorm: y = bf16( bf16(x * rsqrt(mean(x^2) + eps)) * w )   (LlamaRMSNorm rounding points)
 // ---------------------------------------------------------------------------------------------
 constexpr int kNormThreads = 256;
+constexpr int kPrefetchCtas = 144;
 
 __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
                                                               const __nv_bfloat16* __restrict__ w, int d,
-                                                              float eps, __nv_bfloat16* __restrict__ y) {
+                                                              float eps, __nv_bfloat16* __restrict__ y, int M,
+                                                              const L2Prefetch pf) {
   __shared__ float s_part[kNormThreads / 32];
   pdl_trigger();
+  if ((int)blockIdx.x >= M) {  // prefetch-only CTAs (dd_hint_l2_prefetch): the weights do not depend on earlier kernels
+    l2_prefetch_slice(pf, (blockIdx.x - M) * (kNormThreads / 32) + (threadIdx.x >> 5), (gridDim.x - M) * (kNormThreads / 32));
+    return;
+  }
   pdl_wait();
   const int row = blockIdx.x, tid = threadIdx.x;
   const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)row * d);
@@ -206,9 +212,12 @@ extern "C" int dd_rmsnorm(const void* x, const void* w, int M, int d, float eps,
   using namespace dd;
   DD_CHECK_ARG(x && w && y, "dd_rmsnorm: null pointer");
   DD_CHECK_ARG(M >= 0 && d > 0 && d % 8 == 0, "dd_rmsnorm: d=%d must be a positive multiple of 8", d);
+  const L2Prefetch pf = take_l2_prefetch();
   if (M == 0) return DD_OK;
-  DD_LAUNCH_CHAIN(rmsnorm_kernel, dim3(M), dim3(kNormThreads), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x,
-                  (const __nv_bfloat16*)w, d, eps, (__nv_bfloat16*)y);
+  // with a prefetch hint: ~one extra CTA per SM that only issues the bulk prefetches (the row CTAs stay as they are)
+  const int extra = (pf.bytes[0] | pf.bytes[1]) ? kPrefetchCtas : 0;
+  DD_LAUNCH_CHAIN(rmsnorm_kernel, dim3(M + extra), dim3(kNormThreads), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x,
+                  (const __nv_bfloat16*)w, d, eps, (__nv_bfloat16*)y, M, pf);
   return DD_OK;
 }
 

@@ -160,6 +160,11 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         self.probs, self.mode, self.keep_relevant = [float(p) for p in probs], mode, keep_relevant
         self.topk, self.aggregate, self.seed, self.round_logits = topk, aggregate, seed, round_logits
         self.fuse_norm = os.environ.get("DD_FUSE_NORM", "0") == "1"
+        # L2 prefetch riding on the latency-bound kernels of a <= 16-row pass (dd_hint_l2_prefetch): MB of the
+        # following GEMM's weights hinted to {RMSNorm before QKV, attention (after all of o_proj), RMSNorm before gate/up};
+        # off by default (DD_PF_MB="24,48,24" turns it on): measured neutral to -3 % on the launch chain -- profiles/r02/l2_prefetch_sweep.jsonl
+        pf = [int(float(v) * (1 << 20)) for v in os.environ.get("DD_PF_MB", "0").split(",")]
+        self.l2_prefetch = tuple(pf) if len(pf) == 3 and any(pf) else None
         self.prefill_graph = os.environ.get("DD_PREFILL_GRAPH", "1") == "1"
         self.prefill_native = os.environ.get("DD_PREFILL_NATIVE", "1") == "1"
         self._prefill_graphs: dict = {}
@@ -348,19 +353,26 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         rows = B * M
         x, x2 = pb.x, pb.x2
         fuse = self.fuse_norm
+        pf = self.l2_prefetch
         for l, lw in enumerate(self.w.layers):
             rope = dict(cos=self.cos, sin=self.sin, seq_lens=self.seq_lens, members=M, H=H, H_kv=Hkv, D=D, q_out=pb.q,
                         k_new=pb.k_new[l], v_new=pb.v_new[l])
             if fuse:
                 ops.decoder_linear(x, lw["wqkv"], ops.EPI_ROPE, norm_w=lw["ln1"], eps=cfg.rms_eps, rope=rope)
             else:
+                if pf:
+                    ops.hint_l2_prefetch(lw["wqkv"], 0, pf[0])
                 ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pb.xn)
                 ops.decoder_linear(pb.xn, lw["wqkv"], ops.EPI_ROPE, rope=rope)
+            if pf:
+                ops.hint_l2_prefetch(lw["wo"], 0, 1 << 40, lw["wgu"], 0, pf[1])
             self._attention(pb, l, bitmask, seq_active)
             ops.decoder_linear(pb.attn.view(rows, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
             if fuse:
                 ops.decoder_linear(x2, lw["wgu"], ops.EPI_SWIGLU, norm_w=lw["ln2"], eps=cfg.rms_eps, out=pb.act)
             else:
+                if pf:
+                    ops.hint_l2_prefetch(lw["wgu"], pf[1], pf[2])
                 ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pb.xn)
                 ops.decoder_linear(pb.xn, lw["wgu"], ops.EPI_SWIGLU, out=pb.act)
             ops.decoder_linear(pb.act, lw["wd"], ops.EPI_RESIDUAL, residual=x2, out=x)
@@ -371,6 +383,8 @@ class DropoutDecodeEngine(SpeculativeSchedules):
                                out=pb.logits.view(rows, self.Vp))
             self.launches_per_step += 1
         else:
+            if pf and head:
+                ops.hint_l2_prefetch(self.w.lm_head_padded, 0, pf[0])
             ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pb.xn)     # (InstructBLIP votes on this final-norm hidden state)
             self.launches_per_step += 1
             if head:

@@ -46,6 +46,23 @@ def set_chain_launch(on: bool) -> bool:
     return bool(_lib.load().dd_set_chain_launch(1 if on else 0))
 
 
+def hint_l2_prefetch(t0: Optional[torch.Tensor], off0: int = 0, bytes0: int = 0, t1: Optional[torch.Tensor] = None,
+                     off1: int = 0, bytes1: int = 0) -> None:
+    """dd_hint_l2_prefetch: the next rmsnorm / decode_attention call also prefetches bytes [off, off + bytes) of up to
+    two (contiguous) tensors into L2; ranges are clipped to the tensors."""
+    def rng(t, off, n):
+        if t is None or n <= 0:
+            return None, 0
+        total = t.numel() * t.element_size()
+        off = min(off, total) & ~15
+        return t.data_ptr() + off, (min(n, total - off) & ~15)
+    p0, b0 = rng(t0, off0, bytes0)
+    p1, b1 = rng(t1, off1, bytes1)
+    if b0 == 0 and b1 == 0:
+        return
+    check(_lib.load().dd_hint_l2_prefetch(p0 if b0 else None, b0, p1 if b1 else None, b1), "dd_hint_l2_prefetch")
+
+
 def mask_words(n_vis: int) -> int:
     return (n_vis + 31) // 32
 

@@ -59,6 +59,15 @@ const char* dd_last_error(void);
  * sequence of stream-ordered torch kernels, models/llama.py:16-69). */
 int dd_set_chain_launch(int on);
 
+/* L2 prefetch hint for the NEXT dd_rmsnorm / dd_decode_attention* call of this host thread (one-shot: that call
+ * consumes it, also when it fails).  In a pass of a few rows the decoder is one long HBM stream of weights that the
+ * latency-bound kernels interrupt (attention over ~10 MB of K/V, RMSNorm over a few rows): the hinted call's kernel
+ * also issues cp.async.bulk.prefetch.L2 over up to two address ranges -- the head of the weights of the GEMMs that
+ * follow it -- so the stream keeps running into the 126 MB L2 while HBM would idle.  Results are unaffected.
+ * Ranges: 16-byte aligned, a multiple of 16 bytes long, readable device memory; bytes = 0 disables a range.
+ * No reference counterpart (models/llama.py:16-69 is a sequence of stream-ordered torch kernels). */
+int dd_hint_l2_prefetch(const void* range0, size_t bytes0, const void* range1, size_t bytes1);
+
 /* ------------------------------------------------------------------------------------------
  * (1) Visual-token uncertainty stage.
  * Replaces: lm_head over the visual rows + get_image_logits (models/llava.py:412-426),

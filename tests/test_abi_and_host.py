@@ -58,6 +58,11 @@ def test_argument_validation_never_touches_the_gpu(lib):
     assert lib.dd_stream_gemm_workspace_bytes(300, 4096, 4096, 0) == 0
     rc = lib.dd_uncertainty_project(one, one, 1, 9000, 4096, 32064, 5, 0, one, one, one, one, one, 1 << 30, None)
     assert rc == -1 and b"n_vis=9000" in lib.dd_last_error()
+    rc = lib.dd_hint_l2_prefetch(C.c_void_p(24), 64, None, 0)
+    assert rc == -1 and b"16-byte aligned" in lib.dd_last_error()
+    rc = lib.dd_hint_l2_prefetch(None, 64, None, 0)
+    assert rc == -1 and b"null range" in lib.dd_last_error()
+    assert lib.dd_hint_l2_prefetch(None, 0, None, 0) == 0
     rc = lib.dd_aggregate(one, 1, 17, 100, 100, 0, one, one, one, None, None)
     assert rc == -1 and b"K=17" in lib.dd_last_error()
     assert lib.dd_attention_workspace_bytes(2, 3, 32, 128, 4) == 2 * 3 * 32 * 4 * 130 * 4 + 2 * 32 * 4   # partials + tickets

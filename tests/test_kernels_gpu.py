@@ -594,3 +594,32 @@ def test_aggregate_of_nan_and_minus_inf_rows_yields_valid_ids(ops, cuda):
     out = torch.empty(2, 16, dtype=torch.bfloat16, device=cuda)
     ops.embed_gather(emb, torch.tensor([0x7fffffff, -5], dtype=torch.int32, device=cuda), 1, out)
     assert torch.equal(out[0], emb[7]) and torch.equal(out[1], emb[0])
+
+
+def test_l2_prefetch_hint_leaves_results_untouched(ops, cuda):
+    """dd_hint_l2_prefetch: the hinted rmsnorm / decode_attention launch also issues bulk L2 prefetches over the given
+    ranges (odd sizes, a range shorter than one chunk, a second range) -- outputs are bit-identical to the unhinted call
+    and the hint is one-shot."""
+    g = torch.Generator().manual_seed(11)
+    w_big = torch.randn(3 * 1024 * 1024 + 40, generator=g).to(cuda).bfloat16()      # ~6 MB
+    w_small = torch.randn(1000, generator=g).to(cuda).bfloat16()
+    M, d = 5, 4096
+    x, w = torch.randn(M, d, generator=g).to(cuda).bfloat16(), torch.rand(d, generator=g).to(cuda).bfloat16()
+    base = ops.rmsnorm(x, w, 1e-5)
+    ops.hint_l2_prefetch(w_big, 48, 5 * 1024 * 1024 + 16, w_small, 0, 1 << 30)
+    assert torch.equal(ops.rmsnorm(x, w, 1e-5), base)
+    assert torch.equal(ops.rmsnorm(x, w, 1e-5), base)            # the hint is gone: plain launch again
+
+    B, Mm, H, D, S_max = 2, 4, 8, 128, 300
+    bf = lambda *s: torch.randn(*s, generator=g).to(cuda).bfloat16()
+    q, k_new, v_new, kc, vc = bf(B, Mm, H, D), bf(B, Mm, H, D), bf(B, Mm, H, D), bf(B, H, S_max, D), bf(B, H, S_max, D)
+    lens = torch.tensor([257, 64], dtype=torch.int32, device=cuda)
+    for splits in (1, 3):
+        want = ops.decode_attention(q, k_new, v_new, kc, vc, lens, None, None, 0, 0.088, num_splits=splits)
+        ops.hint_l2_prefetch(w_big, 0, 1 << 40, w_big, 1 << 20, 4096)
+        got = ops.decode_attention(q, k_new, v_new, kc, vc, lens, None, None, 0, 0.088, num_splits=splits)
+        assert torch.equal(got, want)
+    torch.cuda.synchronize()
+    from dropoutdecoding_b200 import _lib
+    with pytest.raises(ops.DropDecError):                        # misaligned range
+        ops.check_rc(_lib.load().dd_hint_l2_prefetch(w_big.data_ptr() + 2, 32, None, 0), "dd_hint_l2_prefetch")
