@@ -23,6 +23,22 @@ class RopeArgs(C.Structure):
                 ("q_out", C.c_void_p), ("k_new", C.c_void_p), ("v_new", C.c_void_p)]
 
 
+class PassArgs(C.Structure):
+    """dd_pass_args of include/dropdec.h"""
+    _fields_ = [("plan", C.c_void_p), ("n_layers", C.c_int), ("rows", C.c_int), ("members_total", C.c_int),
+                ("d_model", C.c_int), ("d_ff", C.c_int), ("H", C.c_int), ("H_kv", C.c_int), ("D", C.c_int),
+                ("S_max", C.c_int), ("vocab", C.c_int), ("vocab_padded", C.c_int), ("eps", C.c_float),
+                ("scale", C.c_float), ("embed", C.c_void_p), ("tok", C.c_void_p), ("tok_div", C.c_int),
+                ("pos", C.c_void_p), ("pos_div", C.c_int), ("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p),
+                ("x", C.c_void_p), ("x2", C.c_void_p), ("act", C.c_void_p), ("q", C.c_void_p), ("attn", C.c_void_p),
+                ("xn_out", C.c_void_p), ("final_norm", C.c_void_p), ("lm_head", C.c_void_p), ("logits", C.c_void_p),
+                ("vis_start", C.c_void_p), ("bitmask", C.c_void_p), ("n_vis", C.c_int), ("mask_words", C.c_int),
+                ("num_splits", C.c_int), ("n_windows", C.c_int), ("win_first", C.c_int * 2),
+                ("win_members", C.c_int * 2), ("win_seq_lens", C.c_void_p * 2), ("guess_winner", C.c_void_p),
+                ("guess_pos", C.c_void_p), ("prefetch_gate_up_bytes", C.c_size_t), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t), ("timeline", C.c_void_p)]
+
+
 _SIGNATURES = {
     "dd_version": (C.c_int, []),
     "dd_last_error": (C.c_char_p, []),
@@ -63,6 +79,11 @@ _SIGNATURES = {
     "dd_rope_stage": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "dd_embed_gather": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dd_step_advance": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
+    "dd_pass_plan_bytes": (C.c_size_t, [C.c_int]),
+    "dd_pass_plan_fill": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
+                                    C.c_int]),
+    "dd_pass_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
+    "dd_decoder_pass": (C.c_int, [C.POINTER(PassArgs), _P]),
     "dd_member_finish": (C.c_int, [_P, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int,
                                    _P, _P, _P, _P, _P, _P, _P]),

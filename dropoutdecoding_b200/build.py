@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "_build")
 LIB = os.path.join(OUT, "libdropdec.so")
 SOURCES = ["dd_api.cu", "dd_sampler.cu", "dd_aggregate.cu", "dd_decoder.cu", "dd_skinny_gemm.cu", "dd_stream_gemm.cu",
-           "dd_attention.cu", "dd_uncertainty.cu"]
+           "dd_attention.cu", "dd_uncertainty.cu", "dd_pass.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -139,6 +139,7 @@ class _PassBuffers:
     logits: torch.Tensor    # fp32 [B, M, V]
     ws: torch.Tensor
     splits: int
+    plan: Optional[object] = None      # ops.DecoderPassPlan of the persistent pass kernel (built at first use)
 
 
 class DropoutDecodeEngine(SpeculativeSchedules):
@@ -165,6 +166,10 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         # off by default (DD_PF_MB="24,48,24" turns it on): measured neutral to -3 % on the launch chain -- profiles/r02/l2_prefetch_sweep.jsonl
         pf = [int(float(v) * (1 << 20)) for v in os.environ.get("DD_PF_MB", "0").split(",")]
         self.l2_prefetch = tuple(pf) if len(pf) == 3 and any(pf) else None
+        # <= 16-row passes as ONE persistent kernel (dd_decoder_pass); DD_PASS=0 keeps the launch chain.  DD_PASS_PF_MB: MB
+        # of gate/up weights prefetched into L2 by the idle warps of its attention phase (o_proj's always are)
+        self.pass_kernel = os.environ.get("DD_PASS", "1") == "1"
+        self.pass_pf_bytes = int(float(os.environ.get("DD_PASS_PF_MB", "48")) * (1 << 20))
         self.prefill_graph = os.environ.get("DD_PREFILL_GRAPH", "1") == "1"
         self.prefill_native = os.environ.get("DD_PREFILL_NATIVE", "1") == "1"
         self._prefill_graphs: dict = {}
@@ -318,6 +323,10 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         rows = B * M
         self._set_chain(rows)
+        if self._pass_kernel_ok(pb, rows, M) and head and seq_active is None:
+            self._run_pass_kernel(pb, tok=self.cur_token, tok_div=M, pos=self.seq_lens, pos_div=M, bitmask=bitmask,
+                                  windows=[(0, M, self.seq_lens)])
+            return pb.logits
         ops.embed_gather(self.w.embed, self.cur_token, M, pb.x)
         x, x2 = pb.x, pb.x2
         if rows <= 32 and not self._use_stream(rows):
@@ -341,6 +350,29 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         if head:
             self._linear(pb.xn, self.w.lm_head_padded, ops.EPI_F32, pb.logits.view(rows, self.Vp))
         return pb.logits
+
+    def _pass_kernel_ok(self, pb: _PassBuffers, rows: int, window_members: int) -> bool:
+        """dd_decoder_pass serves passes of <= 16 rows whose attention is split (small batches) and whose member windows
+        fit one 16-row query tile."""
+        cfg = self.cfg
+        return (self.pass_kernel and not self.fuse_norm and rows <= 16 and not self._use_stream(rows) and pb.splits >= 2
+                and window_members * (cfg.n_heads // cfg.n_kv_heads) <= 16 and cfg.head_dim in (64, 128))
+
+    def _run_pass_kernel(self, pb: _PassBuffers, *, tok, tok_div, pos, pos_div, bitmask, windows, guess_winner=None,
+                         guess_pos=None) -> None:
+        cfg = self.cfg
+        if pb.plan is None:
+            pb.plan = ops.DecoderPassPlan(self.w.layers, pb.k_new, pb.v_new, self.k_cache, self.v_cache, pb.M,
+                                          cfg.n_heads, pb.splits)
+        rows = self.B * pb.M
+        ops.decoder_pass(pb.plan, d_model=cfg.d_model, d_ff=cfg.d_ff, vocab=cfg.vocab, eps=cfg.rms_eps, scale=self.scale,
+                         embed=self.w.embed, tok=tok, tok_div=tok_div, pos=pos, pos_div=pos_div, cos=self.cos,
+                         sin=self.sin, x=pb.x, x2=pb.x2, act=pb.act, q=pb.q, attn=pb.attn, final_norm=self.w.norm,
+                         lm_head=self.w.lm_head_padded, logits=pb.logits.view(rows, self.Vp), windows=windows,
+                         vis_start=self.vis_start if bitmask is not None else None, bitmask=bitmask, n_vis=self.n_vis,
+                         xn_out=pb.xn, guess_winner=guess_winner, guess_pos=guess_pos,
+                         prefetch_gate_up_bytes=self.pass_pf_bytes, timeline=getattr(self, "pass_timeline", None))
+        self.launches_per_step += 1
 
     def _forward_fused(self, pb: _PassBuffers, bitmask: Optional[torch.Tensor], head: bool,
                        seq_active: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -430,3 +430,74 @@ def member_finish(recv: torch.Tensor, rank_stride: int, ids_off: int, stats_off:
                               forced_winner, _ptr(forced_token), _ptr(seq_lens), _ptr(step), n_slots, _ptr(member_ids),
                               _ptr(winner), _ptr(token), _ptr(token_stats), _ptr(k_cache), _ptr(v_cache), _stream()),
           "dd_member_finish")
+
+
+# --------------------------------------------------------------------------------------------
+class DecoderPassPlan:
+    """Device-side plan of dd_decoder_pass for one set of pass buffers: per-layer weights, staging rows, caches and the
+    caches' TMA descriptors (dd_pass_plan_fill), plus the kernel's zeroed workspace."""
+
+    def __init__(self, layers, k_new: torch.Tensor, v_new: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
+                 members_total: int, n_heads: int, num_splits: int):
+        L = _lib.load()
+        n_layers, B, H_kv, S_max, D = k_cache.shape
+        for t in (k_new, v_new, k_cache, v_cache):
+            _need(t, torch.bfloat16, "cache / staging")
+        host = (C.c_uint8 * L.dd_pass_plan_bytes(n_layers))()
+        for l, lw in enumerate(layers):
+            check(L.dd_pass_plan_fill(host, l, _ptr(lw["ln1"]), _ptr(lw["wqkv"]), _ptr(lw["wo"]), _ptr(lw["ln2"]),
+                                      _ptr(lw["wgu"]), _ptr(lw["wd"]), _ptr(k_new[l]), _ptr(v_new[l]), _ptr(k_cache[l]),
+                                      _ptr(v_cache[l]), B, H_kv, S_max, D), "dd_pass_plan_fill")
+        self.plan = torch.frombuffer(bytearray(host), dtype=torch.uint8).to(k_cache.device)
+        self.n_layers, self.B, self.H_kv, self.S_max, self.D = n_layers, B, H_kv, S_max, D
+        self.members_total, self.H, self.num_splits = members_total, n_heads, num_splits
+        need = L.dd_pass_workspace_bytes(B, members_total, n_heads, D, num_splits)
+        self.workspace = torch.zeros(need, dtype=torch.uint8, device=k_cache.device)
+        self._keep = (layers, k_new, v_new, k_cache, v_cache)
+
+
+def decoder_pass(plan: DecoderPassPlan, *, d_model: int, d_ff: int, vocab: int, eps: float, scale: float,
+                 embed: torch.Tensor, tok: torch.Tensor, tok_div: int, pos: torch.Tensor, pos_div: int,
+                 cos: torch.Tensor, sin: torch.Tensor, x: torch.Tensor, x2: torch.Tensor, act: torch.Tensor,
+                 q: torch.Tensor, attn: torch.Tensor, final_norm: torch.Tensor, lm_head: Optional[torch.Tensor],
+                 logits: Optional[torch.Tensor], windows, vis_start: Optional[torch.Tensor] = None,
+                 bitmask: Optional[torch.Tensor] = None, n_vis: int = 0, xn_out: Optional[torch.Tensor] = None,
+                 guess_winner: Optional[torch.Tensor] = None, guess_pos: Optional[torch.Tensor] = None,
+                 prefetch_gate_up_bytes: int = 0, timeline: Optional[torch.Tensor] = None) -> None:
+    """dd_decoder_pass: the whole single-token forward of rows = x.shape[0] <= 16 rows in one persistent kernel.
+    windows: [(first_member, members, seq_lens int32 [B]), ...] (1 or 2, tiling the members of a sequence)."""
+    L = _lib.load()
+    a = _lib.PassArgs()
+    rows = x.shape[0]
+    a.plan, a.n_layers, a.rows, a.members_total = _ptr(plan.plan), plan.n_layers, rows, plan.members_total
+    a.d_model, a.d_ff, a.H, a.H_kv, a.D, a.S_max = d_model, d_ff, plan.H, plan.H_kv, plan.D, plan.S_max
+    a.vocab, a.vocab_padded = vocab, (lm_head.shape[0] if lm_head is not None else 0)
+    a.eps, a.scale = float(eps), float(scale)
+    for t, name in ((embed, "embed"), (x, "x"), (x2, "x2"), (act, "act"), (q, "q"), (attn, "attn"),
+                    (final_norm, "final_norm")):
+        _need(t, torch.bfloat16, name)
+    _need(tok, torch.int32, "tok"); _need(pos, torch.int32, "pos")
+    _need(cos, torch.float32, "cos"); _need(sin, torch.float32, "sin")
+    a.embed, a.tok, a.tok_div, a.pos, a.pos_div = _ptr(embed), _ptr(tok), tok_div, _ptr(pos), pos_div
+    a.cos_tab, a.sin_tab = _ptr(cos), _ptr(sin)
+    a.x, a.x2, a.act, a.q, a.attn, a.xn_out = _ptr(x), _ptr(x2), _ptr(act), _ptr(q), _ptr(attn), _ptr(xn_out)
+    a.final_norm, a.lm_head, a.logits = _ptr(final_norm), _ptr(lm_head), _ptr(logits)
+    if logits is not None:
+        _need(logits, torch.float32, "logits"); _need(lm_head, torch.bfloat16, "lm_head")
+    if bitmask is not None:
+        _need(bitmask, torch.int32, "bitmask"); _need(vis_start, torch.int32, "vis_start")
+        a.mask_words = bitmask.shape[-1]
+    a.vis_start, a.bitmask, a.n_vis, a.num_splits = _ptr(vis_start), _ptr(bitmask), n_vis, plan.num_splits
+    a.n_windows = len(windows)
+    for i, (first, members, lens) in enumerate(windows):
+        _need(lens, torch.int32, "seq_lens")
+        a.win_first[i], a.win_members[i], a.win_seq_lens[i] = first, members, _ptr(lens)
+    a.guess_winner, a.guess_pos = _ptr(guess_winner), _ptr(guess_pos)
+    a.prefetch_gate_up_bytes = int(prefetch_gate_up_bytes)
+    a.workspace, a.workspace_bytes = _ptr(plan.workspace), plan.workspace.numel()
+    if timeline is not None:
+        _need(timeline, torch.int64, "timeline")
+        if timeline.numel() < 2 * (5 * plan.n_layers + 2):
+            raise DropDecError("decoder_pass: timeline needs 2 * (5 * n_layers + 2) int64 slots")
+        a.timeline = _ptr(timeline)
+    check(L.dd_decoder_pass(C.byref(a), _stream()), "dd_decoder_pass")

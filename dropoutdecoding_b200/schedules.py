@@ -190,22 +190,10 @@ class SpeculativeSchedules:
                                  seq_active=seq_active, member_offset=a, members=min(per, m1 - a))
             self.launches_per_step += 1 + (pb.splits == 1)
 
-    def _spec_chain(self) -> None:
-        self.launches_per_step = 0
-        cfg, K, pd = self.cfg, self.K, self.pd
-        H, Hkv, D, M = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, 2 * self.K + 1
-        self.tok_host.copy_(self.cur_token, non_blocking=True)
-        torch.add(self.seq_lens, 1, out=self._seq_p1)
-        torch.add(self.step_ctr, 1, out=self._step_p1)
-        self._sample(self._step_uniforms(1), False, self.spec_draw, self._nm_spec, step=self._step_p1)   # draws of t+1
-        self.chain_mask[:, :K].copy_(self.bitmask)
-        self.chain_mask[:, K + 1:].copy_(self.spec_draw)
-        # per-row input token and RoPE position: the kernels see 2K+1 "sequences" of one member each
-        self._row_tok_c[:K] = self.cur_token
-        self._row_tok_c[K:] = self._g_tok
-        self._row_pos_c[:K] = self.seq_lens
-        self._row_pos_c[K:] = self._seq_p1
-        self._set_chain(M)
+    def _chain_forward_launches(self, pd, K: int, M: int) -> None:
+        """The forward of the chain pass as a chain of launches (passes dd_decoder_pass does not serve)."""
+        cfg = self.cfg
+        H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         ops.embed_gather(self.w.embed, self._row_tok_c, 1, pd.x)
         x, x2 = pd.x, pd.x2
         for l, lw in enumerate(self.w.layers):
@@ -224,6 +212,31 @@ class SpeculativeSchedules:
             self.launches_per_step += 7
         ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pd.xn)
         ops.decoder_linear(pd.xn, self.w.lm_head_padded, ops.EPI_F32, out=pd.logits.view(M, self.Vp))
+
+    def _spec_chain(self) -> None:
+        self.launches_per_step = 0
+        cfg, K, pd = self.cfg, self.K, self.pd
+        H, Hkv, D, M = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, 2 * self.K + 1
+        self.tok_host.copy_(self.cur_token, non_blocking=True)
+        torch.add(self.seq_lens, 1, out=self._seq_p1)
+        torch.add(self.step_ctr, 1, out=self._step_p1)
+        self._sample(self._step_uniforms(1), False, self.spec_draw, self._nm_spec, step=self._step_p1)   # draws of t+1
+        self.chain_mask[:, :K].copy_(self.bitmask)
+        self.chain_mask[:, K + 1:].copy_(self.spec_draw)
+        # per-row input token and RoPE position: the kernels see 2K+1 "sequences" of one member each
+        self._row_tok_c[:K] = self.cur_token
+        self._row_tok_c[K:] = self._g_tok
+        self._row_pos_c[:K] = self.seq_lens
+        self._row_pos_c[K:] = self._seq_p1
+        self._set_chain(M)
+        if self._pass_kernel_ok(pd, M, K + 1):
+            # one persistent kernel: per-row tokens / positions, two member windows, the guessed winner's row written
+            # to cache row S by the QKV epilogue
+            self._run_pass_kernel(pd, tok=self._row_tok_c, tok_div=1, pos=self._row_pos_c, pos_div=1,
+                                  bitmask=self.chain_mask, windows=[(0, K, self.seq_lens), (K, K + 1, self._seq_p1)],
+                                  guess_winner=self._g_win, guess_pos=self.seq_lens)
+        else:
+            self._chain_forward_launches(pd, K, M)
         V, mean = cfg.vocab, self.aggregate == "mean"
         # ---- step t: the reference's vote over its K real-mask members (rows 0..K-1)
         ops.aggregate(pd.logits, self.aggregate, member_ids=self.member_ids, winner=self.winner, token=self.next_token,

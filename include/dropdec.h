@@ -319,6 +319,56 @@ int dd_step_advance_seq(const int32_t* token /* [B] */, const int32_t* advance /
                         int32_t* tokens_out /* [B, max_steps] */, int max_steps, int32_t* seq_lens /* [B] */,
                         int32_t* seq_steps /* [B] */, int B, dd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Persistent decoder pass: ONE kernel for a whole single-token forward of <= 16 rows (rows = sequences x members) --
+ * embedding gather, n_layers x {RMSNorm, QKV + RoPE + staging, masked decode attention, o_proj, RMSNorm, gate/up +
+ * SwiGLU, down}, final RMSNorm, lm_head -- i.e. one `self.language_model(...)` call of the reference
+ * (models/llava.py:294-303, 350-359; models/llama.py:27-47) for all members at once.  One CTA per SM stays resident;
+ * grid barriers replace the ~230 kernel boundaries of the launch chain, the first weight batch of every GEMM phase is
+ * put in flight before the barrier, the RMSNorms are computed per CTA into shared memory, idle warps prefetch the next
+ * weights into L2 during the attention phase.  Results are bit-identical to the chain dd_embed_gather / dd_rmsnorm /
+ * dd_decoder_linear / dd_decode_attention (same arithmetic, same order).
+ *
+ * Plan: one record per layer in DEVICE memory (weights, staging rows, caches and the caches' TMA descriptors);
+ * dd_pass_plan_fill writes record `layer` of a HOST copy (dd_pass_plan_bytes(n_layers) bytes) that the caller then
+ * copies to the device.  k_new / v_new: that layer's staging rows [rows, H_kv, D]; k_cache / v_cache: that layer's
+ * cache [B, H_kv, S_max, D].
+ *
+ * Rows: row r embeds token tok[r / tok_div] and rotates with position pos[r / pos_div] (tok_div = pos_div =
+ * members_total with per-sequence arrays, 1 with per-row arrays).  Attention: the members of a sequence form 1 or 2
+ * windows [win_first, win_first + win_members) that attend keys [0, win_seq_lens[w][b]) of the shared cache under
+ * their bitmask rows, plus their own new row (as dd_decode_attention_active with member_offset).  guess_winner (or
+ * NULL): the new K/V rows of member guess_winner[b] are also written to cache row guess_pos[b] before the attention
+ * (the lookahead's guessed commit, dd_commit_winner of one layer).  logits NULL: no lm_head; xn_out (or NULL) receives
+ * the final-norm hidden state [rows, d_model].  workspace: dd_pass_workspace_bytes, ZEROED once by the caller (the
+ * kernel leaves its counters at zero).  Needs num_splits >= 2 and win_members * (H / H_kv) <= 16.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dd_pass_args {
+  const void* plan; int n_layers;
+  int rows, members_total;
+  int d_model, d_ff, H, H_kv, D, S_max, vocab, vocab_padded;
+  float eps, scale;
+  const void* embed /* bf16 [vocab, d_model] */; const int32_t* tok; int tok_div; const int32_t* pos; int pos_div;
+  const float *cos_tab, *sin_tab;
+  void *x, *x2 /* bf16 [rows, d_model] */, *act /* [rows, d_ff] */, *q /* [rows, H, D] */, *attn /* [rows, H, D] */,
+      *xn_out;
+  const void *final_norm, *lm_head /* bf16 [vocab_padded, d_model] */; float* logits /* [rows, vocab_padded] */;
+  const int32_t* vis_start; const uint32_t* bitmask /* [B, members_total, mask_words] or NULL */;
+  int n_vis, mask_words, num_splits;
+  int n_windows; int win_first[2], win_members[2]; const int32_t* win_seq_lens[2];
+  const int32_t *guess_winner, *guess_pos;
+  size_t prefetch_gate_up_bytes; /* bytes of gate/up prefetched to L2 during the attention phase (o_proj always is) */
+  void* workspace; size_t workspace_bytes;
+  void* timeline; /* or NULL: uint64 [2 * (5 * n_layers + 2)] device buffer; CTA 0 stamps %globaltimer (ns) at the start
+                     and the end of its work in every phase {embed, L x {qkv, attention, o_proj, gate/up, down}, head} */
+} dd_pass_args;
+size_t dd_pass_plan_bytes(int n_layers);
+int dd_pass_plan_fill(void* host_plan, int layer, const void* ln1, const void* wqkv, const void* wo, const void* ln2,
+                      const void* wgu, const void* wd, void* k_new, void* v_new, void* k_cache, void* v_cache, int B,
+                      int H_kv, int S_max, int D);
+size_t dd_pass_workspace_bytes(int B, int members_total, int H, int D, int num_splits);
+int dd_decoder_pass(const dd_pass_args* args, dd_stream_t stream);
+
 /* Member-sharded decode (ensemble members on different GPUs; the reference runs them sequentially on one,
  * models/llava.py:342-361): the finish step after the per-step all-gather.  `recv` holds G exchange records of
  * rank_stride bytes; a record = member argmax ids int32 [B, mpr] at ids_off | token statistics fp32 [mpr, B, 3] at

@@ -494,3 +494,45 @@ def test_instructblip_flavour_bit_exact(cuda, golden_dir):
     z = np.load(os.path.join(golden_dir, "decode_blip_tiny.npz"))
     assert tr.tokens == z["bf16.tokens"].tolist() and tr.winner == z["bf16.winner"].tolist()
     assert tr.masked_numbers[0] == [10, 16, 22]
+
+
+@pytest.mark.parametrize("use_graph", [True, False], ids=["cuda_graph", "eager"])
+@pytest.mark.parametrize("spec", ["on", "off"])
+def test_persistent_pass_kernel_equals_launch_chain_bit_for_bit(tiny, cuda, monkeypatch, use_graph, spec):
+    """dd_decoder_pass (one persistent kernel per pass: grid barriers, per-CTA RMSNorm in shared memory, the attention
+    body on four warps, the guessed winner's row committed by the QKV epilogue, two member windows in the chain pass)
+    runs the arithmetic of the launch chain in the same order: every pass buffer, the caches, the tokens and the
+    per-token statistics are bit-identical, for the speculative (4 rows), chain (7 rows) and two-pass (1 + 3 rows)
+    forms."""
+    tr = tiny["trace"]
+    engs = []
+    for on in ("1", "0"):
+        monkeypatch.setenv("DD_PASS", on)
+        eng = make_engine(tiny, cuda, speculative=spec)
+        inject_oracle_prefill(eng, tiny, cuda)
+        eng.epi.copy_(tr.uncert["epis_uncert_per_token"].to(cuda))
+        eng.topk_ids.copy_(tr.topk_ids.to(cuda).int())
+        eng.first_token(tr.last_hidden.to(cuda).bfloat16()[None])
+        engs.append(eng)
+    a, b = engs
+    assert a.pass_kernel and not b.pass_kernel and a.pc.splits >= 2 if spec == "on" else a.pb.splits >= 2
+    left, chunks = TINY_T - 1, [1, 5, 2, 1, 9]
+    while left > 0:
+        n = min(chunks.pop(0) if chunks else left, left)
+        a.decode(n, use_graph=use_graph)
+        b.decode(n, use_graph=use_graph)
+        torch.cuda.synchronize()
+        left -= n
+        assert torch.equal(a.generated(), b.generated()), f"{left} steps left: tokens"
+        for name in ("y_init", "bitmask", "member_ids", "winner", "next_token", "seq_lens", "cur_token"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"{left} steps left: {name}"
+        for pbn in (("pc", "pd") if spec == "on" else ("pa", "pb")):
+            pa_, pb_ = getattr(a, pbn), getattr(b, pbn)
+            for f in ("logits", "k_new", "v_new", "x", "x2", "act", "attn", "q", "xn"):
+                assert torch.equal(getattr(pa_, f), getattr(pb_, f)), f"{left} steps left: {pbn}.{f}"
+        S = int(a.seq_lens[0])
+        assert torch.equal(a.k_cache[:, :, :, :S], b.k_cache[:, :, :, :S]), f"{left} steps left: K cache"
+        assert torch.equal(a.v_cache[:, :, :, :S], b.v_cache[:, :, :, :S]), f"{left} steps left: V cache"
+    assert torch.equal(a.token_stats[:TINY_T], b.token_stats[:TINY_T])
+    assert a.generated()[0].tolist() == tr.tokens
+    assert a.pc.plan is not None if spec == "on" else a.pb.plan is not None
