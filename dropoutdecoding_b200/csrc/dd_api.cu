@@ -48,12 +48,12 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
 
 // 0 / 1 once decided; -1 = not yet (then the DD_PDL environment variable, else off)
 static int g_pdl = -1;
-bool pdl_enabled() {
+bool pdl_enabled(bool weight_gemm) {
   if (g_pdl < 0) {
     const char* e = getenv("DD_PDL");
-    g_pdl = (e && e[0] == '1') ? 1 : 0;
+    g_pdl = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
   }
-  return g_pdl == 1;
+  return g_pdl == 1 || (g_pdl == 2 && weight_gemm);
 }
 
 static thread_local L2Prefetch g_l2_prefetch{};
@@ -76,8 +76,9 @@ extern "C" int dd_hint_l2_prefetch(const void* p0, size_t bytes0, const void* p1
 
 extern "C" int dd_version(void) { return 100; }  // 0.1.0
 extern "C" int dd_set_chain_launch(int on) {
-  const int was = dd::pdl_enabled() ? 1 : 0;
-  dd::g_pdl = on ? 1 : 0;
+  dd::pdl_enabled();   // (resolves the environment default)
+  const int was = dd::g_pdl;
+  dd::g_pdl = (on == 1 || on == 2) ? on : 0;
   return was;
 }
 extern "C" const char* dd_last_error(void) { return dd::g_last_error.c_str(); }

@@ -31,11 +31,18 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
   __shared__ int s_ext[DD_MAX_MEMBERS];                                  // per member: 1 = also attends key S0
   __shared__ int s_last;
   pdl_trigger_stream_entry();
+  if ((int)blockIdx.x >= p.num_splits) {
+    // prefetch-only CTAs (dd_hint_l2_prefetch): they land on SMs the split grid leaves idle, issue their share of the
+    // bulk L2 prefetches and leave -- the TMA queues of the SMs that stream K/V stay free.  (The weights do not
+    // depend on earlier kernels: no griddepcontrol.wait.)
+    const unsigned extra = gridDim.x - p.num_splits;
+    const unsigned idx = (blockIdx.z * gridDim.y + blockIdx.y) * extra + (blockIdx.x - p.num_splits);
+    l2_prefetch_slice(pf, idx * kAttnWarps + (threadIdx.x >> 5), extra * gridDim.y * gridDim.z * kAttnWarps);
+    return;
+  }
   pdl_wait();
-  const unsigned cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  const unsigned n_cta = gridDim.x * gridDim.y * gridDim.z;
-  attn_partial_body<D, QT, true>(&tmap_k, &tmap_v, p, pf, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, cta_lin, n_cta,
-                                 smem, s_full, s_ext, &s_last, [] { __syncthreads(); });
+  attn_partial_body<D, QT, true>(&tmap_k, &tmap_v, p, L2Prefetch{}, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, 0u,
+                                 1u, smem, s_full, s_ext, &s_last, [] { __syncthreads(); });
 }
 
 // Unsplit case: out[b,m,h,:] = merge(the partial, own new-token row).  One CTA of D threads per (b,m,h).
@@ -91,8 +98,19 @@ static int launch_attn(const AttnParams& p, const L2Prefetch& pf, const void* k_
       if (dev >= 0 && dev < 64) configured[dev] = smem;
     }
   }
-  DD_LAUNCH_CHAIN(attn_partial_kernel<D, QT>, dim3(p.num_splits, p.H_kv, p.B), dim3(kAttnThreads), smem, st, tmap_k,
-                  tmap_v, p, pf);
+  // with a prefetch hint: extra CTAs along x (about one per SM the split grid leaves idle, at least one per (b, kv head))
+  int extra = 0;
+  if (pf.bytes[0] | pf.bytes[1]) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int pairs = p.H_kv * p.B, idle = sms - (p.num_splits * pairs) % sms;
+    extra = (idle + pairs - 1) / pairs;
+    if (extra < 1) extra = 1;
+    if (extra > 8) extra = 8;
+  }
+  DD_LAUNCH_CHAIN(attn_partial_kernel<D, QT>, dim3(p.num_splits + extra, p.H_kv, p.B), dim3(kAttnThreads), smem, st,
+                  tmap_k, tmap_v, p, pf);
   (void)k_new; (void)v_new; (void)out;
   if (p.num_splits == 1) DD_LAUNCH_CHAIN(attn_merge_kernel<D>, dim3(p.H, p.M, p.B), dim3(D), 0, st, p);
   return DD_OK;

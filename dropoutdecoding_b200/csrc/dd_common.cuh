@@ -53,9 +53,10 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // with weight tiles before the wait (7B pass of 56 rows: 4.99 -> 4.55 ms) -- and costs 1-3 % on the
 // register-streamed skinny GEMMs of a 4-row pass, where it stays off (profiles/README.md).
 // ---------------------------------------------------------------------------------------------
-bool pdl_enabled();
+// weight_gemm: the launch is a weight-streaming GEMM (mode 2 of dd_set_chain_launch chains only those)
+bool pdl_enabled(bool weight_gemm = false);
 
-template <typename... KArgs, typename... Args>
+template <bool kWeightGemm = false, typename... KArgs, typename... Args>
 static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                        cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg{};
@@ -67,11 +68,12 @@ static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_enabled(kWeightGemm) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 #define DD_LAUNCH_CHAIN(...) DD_CHECK_CUDA(::dd::launch_chain(__VA_ARGS__))
+#define DD_LAUNCH_CHAIN_GEMM(...) DD_CHECK_CUDA(::dd::launch_chain<true>(__VA_ARGS__))
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // DD_PDL_TRIGGER: where kernels let their dependents start (build-time knob for experiments)

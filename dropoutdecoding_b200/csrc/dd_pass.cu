@@ -161,10 +161,10 @@ __device__ __forceinline__ void tile_prefetch(const __nv_bfloat16* w, int N, int
   }
 }
 #ifndef DD_PASS_TILES_AHEAD
-#define DD_PASS_TILES_AHEAD 2
+#define DD_PASS_TILES_AHEAD 0
 #endif
 #ifndef DD_PASS_TILES_PRE
-#define DD_PASS_TILES_PRE 2
+#define DD_PASS_TILES_PRE 0
 #endif
 constexpr int kTilesAhead = DD_PASS_TILES_AHEAD;   // L2 prefetch distance inside a phase, in tiles of this CTA (0: off)
 constexpr int kTilesPre = DD_PASS_TILES_PRE;       // tiles of the next phase prefetched before the grid barrier
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(kPassThreads, 1) decoder_pass_kernel(const __g
       attention_phase<D>(p, ly, smem, s_full, s_ext, &s_last);
     } else {
       L2Prefetch pf{};
-      pf.ptr[0] = reinterpret_cast<const char*>(ly.wo); pf.bytes[0] = (unsigned long long)d * HD * 2;
+      pf.ptr[0] = reinterpret_cast<const char*>(ly.wo); pf.bytes[0] = p.pf_gu_bytes ? (unsigned long long)d * HD * 2 : 0;
       pf.ptr[1] = reinterpret_cast<const char*>(ly.wgu); pf.bytes[1] = p.pf_gu_bytes;
       constexpr int kIdleWarps = (kPassThreads - kAttnThreads) / 32;
       l2_prefetch_slice(pf, cta * kIdleWarps + (tid - kAttnThreads) / 32, G * kIdleWarps);

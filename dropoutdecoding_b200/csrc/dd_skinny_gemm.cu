@@ -309,11 +309,11 @@ template <int MT, bool NORM>
 static int launch_mt(const GemmArgs& a, int epi, cudaStream_t st) {
   const dim3 grid(a.N / 16), block(kGemmThreads);
   switch (epi) {
-    case DD_EPI_NONE: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_NONE, NORM>, grid, block, 0, st, a); break;
-    case DD_EPI_RESIDUAL: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_RESIDUAL, NORM>, grid, block, 0, st, a); break;
-    case DD_EPI_F32: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_F32, NORM>, grid, block, 0, st, a); break;
-    case DD_EPI_SWIGLU: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_SWIGLU, NORM>, grid, block, 0, st, a); break;
-    case DD_EPI_ROPE: DD_LAUNCH_CHAIN(skinny_gemm_kernel<MT, DD_EPI_ROPE, NORM>, grid, block, 0, st, a); break;
+    case DD_EPI_NONE: DD_LAUNCH_CHAIN_GEMM(skinny_gemm_kernel<MT, DD_EPI_NONE, NORM>, grid, block, 0, st, a); break;
+    case DD_EPI_RESIDUAL: DD_LAUNCH_CHAIN_GEMM(skinny_gemm_kernel<MT, DD_EPI_RESIDUAL, NORM>, grid, block, 0, st, a); break;
+    case DD_EPI_F32: DD_LAUNCH_CHAIN_GEMM(skinny_gemm_kernel<MT, DD_EPI_F32, NORM>, grid, block, 0, st, a); break;
+    case DD_EPI_SWIGLU: DD_LAUNCH_CHAIN_GEMM(skinny_gemm_kernel<MT, DD_EPI_SWIGLU, NORM>, grid, block, 0, st, a); break;
+    case DD_EPI_ROPE: DD_LAUNCH_CHAIN_GEMM(skinny_gemm_kernel<MT, DD_EPI_ROPE, NORM>, grid, block, 0, st, a); break;
     default: set_error("dd_skinny_gemm: bad epilogue %d", epi); return DD_ERR_INVALID_ARG;
   }
   return DD_OK;

@@ -166,10 +166,11 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         # off by default (DD_PF_MB="24,48,24" turns it on): measured neutral to -3 % on the launch chain -- profiles/r02/l2_prefetch_sweep.jsonl
         pf = [int(float(v) * (1 << 20)) for v in os.environ.get("DD_PF_MB", "0").split(",")]
         self.l2_prefetch = tuple(pf) if len(pf) == 3 and any(pf) else None
-        # <= 16-row passes as ONE persistent kernel (dd_decoder_pass); DD_PASS=0 keeps the launch chain.  DD_PASS_PF_MB: MB
-        # of gate/up weights prefetched into L2 by the idle warps of its attention phase (o_proj's always are)
-        self.pass_kernel = os.environ.get("DD_PASS", "1") == "1"
-        self.pass_pf_bytes = int(float(os.environ.get("DD_PASS_PF_MB", "48")) * (1 << 20))
+        # <= 16-row passes as ONE persistent kernel (dd_decoder_pass): DD_PASS=1.  Bit-identical to the launch chain but
+        # measured slower on B200 so far (4.9 vs 3.4 ms per 7B pass, profiles/README.md), so the chain is the default.
+        # DD_PASS_PF_MB: MB of o_proj + gate/up weights prefetched into L2 by the idle warps of its attention phase
+        self.pass_kernel = os.environ.get("DD_PASS", "0") == "1"
+        self.pass_pf_bytes = int(float(os.environ.get("DD_PASS_PF_MB", "0")) * (1 << 20))
         self.prefill_graph = os.environ.get("DD_PREFILL_GRAPH", "1") == "1"
         self.prefill_native = os.environ.get("DD_PREFILL_NATIVE", "1") == "1"
         self._prefill_graphs: dict = {}
@@ -184,7 +185,9 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         if self.gemm_backend not in ("auto", "stream", "library", "skinny"):
             raise ValueError(self.gemm_backend)
         # programmatic dependent launch of the pass kernels: None = per pass (on for dd_stream_gemm passes); DD_PDL=0/1 pins it
-        self.chain_launch = {"0": False, "1": True}.get(os.environ.get("DD_PDL", ""), None)
+        self.chain_launch = {"0": 0, "1": 1, "2": 2}.get(os.environ.get("DD_PDL", ""), None)
+        # mode of the <= 16-row passes (skinny GEMMs): DD_PDL_SKINNY = 0 | 1 | 2 (2: only the GEMM launches are dependent)
+        self.chain_launch_skinny = int(os.environ.get("DD_PDL_SKINNY", "0"))
         self.attn_splits = attn_splits  # None: chosen per pass from the measured sweep (_alloc_pass); tests pin it
         self.seq_base = int(seq_base)   # global index of sequence 0 (batch sharded over GPUs)
         self.vote_on = vote_on          # "hidden": InstructBLIP votes on the argmax of the final hidden state
@@ -285,7 +288,10 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         """Programmatic dependent launch for the kernels of the pass that follows: it pays where dd_stream_gemm can
         prefetch its ring of weight tiles under the previous kernel's tail (7B, 56 rows: 5.01 -> 4.57 ms per pass) and
         costs 3-4 % on the register-streamed skinny GEMMs of a 4-row pass."""
-        ops.set_chain_launch(self._use_stream(rows) if self.chain_launch is None else self.chain_launch)
+        if self.chain_launch is not None:
+            ops.set_chain_launch(self.chain_launch)
+        else:
+            ops.set_chain_launch(1 if self._use_stream(rows) else self.chain_launch_skinny)
 
     def _linear(self, x, w, epi, out, residual=None):
         self.launches_per_step += 1

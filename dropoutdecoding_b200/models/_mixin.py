@@ -122,9 +122,43 @@ class DropoutDecodingMixin:
         return self.config.image_token_id if hasattr(self.config, "image_token_id") else self.config.image_token_index
 
     def _visual_features(self, pixel_values: torch.Tensor, **kw) -> torch.Tensor:
-        """[B, n_vis, d] projected visual tokens."""
-        feats = self.model.get_image_features(pixel_values=pixel_values, return_dict=True, **kw).pooler_output
-        return torch.stack(list(feats)) if not torch.is_tensor(feats) else feats
+        """[B, n_vis, d] projected visual tokens.  The vision tower + projector are library modules and
+        launch-bound when run eagerly (~6 ms for one 336 px image on B200 against < 1 ms of math), so their forward is
+        captured once per input shape and replayed from a CUDA graph (DD_VISION_GRAPH=0: eager)."""
+        def eager(px):
+            feats = self.model.get_image_features(pixel_values=px, return_dict=True, **kw).pooler_output
+            return torch.stack(list(feats)) if not torch.is_tensor(feats) else feats
+
+        if not pixel_values.is_cuda or os.environ.get("DD_VISION_GRAPH", "1") != "1" or torch.is_grad_enabled():
+            return eager(pixel_values)
+        graphs = self.__dict__.setdefault("_vision_graphs", {})
+        key = (tuple(pixel_values.shape), pixel_values.dtype, pixel_values.device.index,
+               tuple(sorted((k, str(v)) for k, v in kw.items())))
+        entry = graphs.get(key)
+        if entry is None:
+            try:
+                static_in = pixel_values.clone()
+                side = torch.cuda.Stream(device=pixel_values.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):                      # warm-up off the capture (lazy inits, autotuning)
+                    for _ in range(2):
+                        eager(static_in)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = eager(static_in)
+                entry = (static_in, graph, static_out)
+            except Exception as e:                                  # a tower that cannot be captured stays eager
+                warnings.warn(f"vision tower not captured in a CUDA graph ({type(e).__name__}: {e}); running it eagerly")
+                torch.cuda.synchronize()
+                entry = False
+            graphs[key] = entry
+        if entry is False:
+            return eager(pixel_values)
+        static_in, graph, static_out = entry
+        static_in.copy_(pixel_values)
+        graph.replay()
+        return static_out
 
     def _keep_relevant(self) -> bool:
         return True

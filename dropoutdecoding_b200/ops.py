@@ -40,10 +40,10 @@ def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
-def set_chain_launch(on: bool) -> bool:
-    """dd_set_chain_launch: programmatic dependent launch for the dd_* kernels launched from now on (returns the
-    previous setting)."""
-    return bool(_lib.load().dd_set_chain_launch(1 if on else 0))
+def set_chain_launch(mode) -> int:
+    """dd_set_chain_launch: programmatic dependent launch for the dd_* kernels launched from now on -- False / 0 off,
+    True / 1 every kernel, 2 only the skinny weight GEMMs (returns the previous mode)."""
+    return int(_lib.load().dd_set_chain_launch(int(mode)))
 
 
 def hint_l2_prefetch(t0: Optional[torch.Tensor], off0: int = 0, bytes0: int = 0, t1: Optional[torch.Tensor] = None,

@@ -52,12 +52,14 @@ int dd_version(void);
 const char* dd_last_error(void);
 
 /* Programmatic dependent launch for the kernels of a decoder pass (host choice, process-wide; returns the previous
- * setting).  On: every dd_* kernel launched from now on may become resident while its predecessor in the stream is
- * still draining and run its independent prologue -- dd_stream_gemm puts its whole ring of weight tiles in flight --
- * before it waits for the predecessor's results (griddepcontrol.wait).  Results are identical either way.  Default:
- * the DD_PDL environment variable ("1" = on), else off.  No reference counterpart (the reference's forward is a
- * sequence of stream-ordered torch kernels, models/llama.py:16-69). */
-int dd_set_chain_launch(int on);
+ * mode).  1: every dd_* kernel launched from now on may become resident while its predecessor in the stream is still
+ * draining and run its independent prologue -- dd_stream_gemm puts its whole ring of weight tiles in flight --
+ * before it waits for the predecessor's results (griddepcontrol.wait).  2: only the skinny weight GEMMs
+ * (dd_skinny_gemm / dd_decoder_linear) are launched that way: their first weight batch and launch latency overlap the
+ * small kernel in front of them (RMSNorm, attention), while no small kernel queues up behind a GEMM's tail.  0: off.
+ * Results are identical in every mode.  Default: the DD_PDL environment variable ("1" / "2"), else off.  No reference
+ * counterpart (the reference's forward is a sequence of stream-ordered torch kernels, models/llama.py:16-69). */
+int dd_set_chain_launch(int mode);
 
 /* L2 prefetch hint for the NEXT dd_rmsnorm / dd_decode_attention* call of this host thread (one-shot: that call
  * consumes it, also when it fails).  In a pass of a few rows the decoder is one long HBM stream of weights that the

@@ -206,3 +206,20 @@ def test_reference_driver_call_sequence(cuda, tmp_path):
         assert txt.shape == (1, 8)
     finally:
         settings.clear(); settings.update(old)
+
+
+def test_vision_tower_graph_replay_equals_eager(llava, cuda, monkeypatch):
+    """The vision tower + projector replayed from a CUDA graph give the eager features bit for bit, for a second image
+    through the same graph and for another batch size (a second graph)."""
+    import bench
+    with torch.no_grad():
+        for B, seed in ((1, 1), (1, 7), (2, 3)):
+            _, px = bench.synthetic_inputs(B, seed0=seed)
+            px = px.to(cuda).to(llava.dtype)
+            monkeypatch.setenv("DD_VISION_GRAPH", "0")
+            want = llava._visual_features(px).clone()
+            monkeypatch.setenv("DD_VISION_GRAPH", "1")
+            got = llava._visual_features(px)
+            assert got.shape == (B, 576, llava.config.text_config.hidden_size) and torch.equal(got, want)
+    graphs = llava.__dict__["_vision_graphs"]
+    assert len(graphs) >= 2 and all(e is not False for e in graphs.values()), "the tower was not captured"

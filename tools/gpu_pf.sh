@@ -4,11 +4,7 @@ mkdir -p gpurun_out/pf
 python -m pytest tests/test_kernels_gpu.py -q -x -m gpu -k "l2_prefetch or rmsnorm or decode_attention" > gpurun_out/pf/pytest.log 2>&1
 tail -3 gpurun_out/pf/pytest.log
 : > gpurun_out/pf/sweep.jsonl
-for pf in 0 24,48,24 16,32,16 32,64,32 0,48,0 24,0,24 48,80,40 8,16,8 24,90,0; do
+for pf in ${PF_LIST:-0 0,48,0 0,24,0 0,0.01,0 0,80,0 24,48,24}; do
   echo "pf=$pf" | tee -a gpurun_out/pf/sweep.jsonl
   DD_PF_MB=$pf python tools/stepbench.py --batch 1 2>&1 | tail -1 | tee -a gpurun_out/pf/sweep.jsonl
-done
-for pf in 0 24,48,24; do
-  echo "B=2 pf=$pf" | tee -a gpurun_out/pf/sweep.jsonl
-  DD_PF_MB=$pf python tools/stepbench.py --batch 2 2>&1 | tail -1 | tee -a gpurun_out/pf/sweep.jsonl
 done
