@@ -29,15 +29,40 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const __nv_bfloat
   const uint4* w4 = reinterpret_cast<const uint4*>(w);
   uint4* y4 = reinterpret_cast<uint4*>(y + (size_t)row * d);
   const int nvec = d / 8;
+  // rows of up to kNormKeep * 256 * 8 elements (d <= 8192) stay in registers between the two passes, and the norm
+  // weights are fetched together with them: one memory round trip instead of two dependent ones
+  constexpr int kNormKeep = 4;
+  const bool keep = nvec <= kNormKeep * kNormThreads;
+  uint4 xv[kNormKeep], gv[kNormKeep];
   float ss = 0.f;
-  for (int j = tid; j < nvec; j += kNormThreads) {
-    const uint4 v = x4[j];
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  if (keep) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = bf16x2_to_float2(u[k]);
-      ss = fmaf(f.x, f.x, ss);
-      ss = fmaf(f.y, f.y, ss);
+    for (int i = 0; i < kNormKeep; ++i) {
+      const int j = tid + i * kNormThreads;
+      if (j < nvec) { xv[i] = x4[j]; gv[i] = w4[j]; }
+    }
+#pragma unroll
+    for (int i = 0; i < kNormKeep; ++i) {
+      if (tid + i * kNormThreads < nvec) {
+        const uint32_t u[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = bf16x2_to_float2(u[k]);
+          ss = fmaf(f.x, f.x, ss);
+          ss = fmaf(f.y, f.y, ss);
+        }
+      }
+    }
+  } else {
+    for (int j = tid; j < nvec; j += kNormThreads) {
+      const uint4 v = x4[j];
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = bf16x2_to_float2(u[k]);
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
+      }
     }
   }
   ss = warp_sum(ss);
@@ -47,8 +72,7 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const __nv_bfloat
 #pragma unroll
   for (int k = 0; k < kNormThreads / 32; ++k) tot += s_part[k];
   const float rstd = rsqrtf(tot / (float)d + eps);
-  for (int j = tid; j < nvec; j += kNormThreads) {
-    const uint4 v = x4[j], g = w4[j];
+  auto scale = [&](const uint4& v, const uint4& g) {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w}, gw[4] = {g.x, g.y, g.z, g.w};
     uint32_t o[4];
 #pragma unroll
@@ -56,7 +80,16 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const __nv_bfloat
       const float2 f = bf16x2_to_float2(u[k]), ww = bf16x2_to_float2(gw[k]);
       o[k] = pack_bf16x2(bf16_round(f.x * rstd) * ww.x, bf16_round(f.y * rstd) * ww.y);
     }
-    y4[j] = make_uint4(o[0], o[1], o[2], o[3]);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  if (keep) {
+#pragma unroll
+    for (int i = 0; i < kNormKeep; ++i) {
+      const int j = tid + i * kNormThreads;
+      if (j < nvec) y4[j] = scale(xv[i], gv[i]);
+    }
+  } else {
+    for (int j = tid; j < nvec; j += kNormThreads) y4[j] = scale(x4[j], w4[j]);
   }
 }
 
