@@ -266,6 +266,8 @@ class DropoutDecodeEngine(SpeculativeSchedules):
             splits = 2
         if self.attn_splits is not None:
             splits = int(self.attn_splits)
+        elif os.environ.get("DD_ATTN_SPLITS"):          # experiments (tools/stepbench.py sweeps)
+            splits = int(os.environ["DD_ATTN_SPLITS"])
         return _PassBuffers(
             M=M, x=torch.empty(rows, cfg.d_model, **bf), x2=torch.empty(rows, cfg.d_model, **bf),
             xn=torch.empty(rows, cfg.d_model, **bf), qkv=torch.empty(rows, (H + 2 * Hkv) * D, **bf),

@@ -536,3 +536,41 @@ def test_persistent_pass_kernel_equals_launch_chain_bit_for_bit(tiny, cuda, monk
     assert torch.equal(a.token_stats[:TINY_T], b.token_stats[:TINY_T])
     assert a.generated()[0].tolist() == tr.tokens
     assert a.pc.plan is not None if spec == "on" else a.pb.plan is not None
+
+
+@pytest.mark.parametrize("rows_case", ["speculative_4_rows", "chain_7_rows"])
+def test_persistent_pass_kernel_7b_layer_shapes_bit_identical(cuda, monkeypatch, rows_case):
+    """The same comparison at the 7B layer shapes (d 4096, d_ff 11008: 16 and 43 k-steps per warp, i.e. full and ragged
+    batches through the three-slot weight pipeline, 768 / 256 / 688 / 256 / 2004 tiles over the CTAs), two layers."""
+    from dropoutdecoding_b200.engine import DecoderConfig, DecoderWeights, DropoutDecodeEngine
+    cfg = DecoderConfig(2, 4096, 32, 32, 128, 11008, 32064, 1e-5, 10000.0)
+    w = DecoderWeights.random(cfg, cuda, seed=3)
+    engs = []
+    for on in ("1", "0"):
+        monkeypatch.setenv("DD_PASS", on)
+        eng = DropoutDecodeEngine(w, 1, 576, 700, max_steps=16, est_seq=640)
+        g = torch.Generator(device=cuda).manual_seed(5)
+        eng.k_cache.copy_(torch.randn(eng.k_cache.shape, generator=g, device=cuda).to(torch.bfloat16))
+        eng.v_cache.copy_(torch.randn(eng.v_cache.shape, generator=g, device=cuda).to(torch.bfloat16))
+        eng.seq_lens.fill_(601); eng.vis_start.fill_(5); eng.cur_token.fill_(4321)
+        eng.epi.uniform_(0.75, 0.95, generator=g)
+        eng.topk_ids.random_(0, cfg.vocab, generator=g)
+        engs.append(eng)
+    a, b = engs
+    assert a.pass_kernel and not b.pass_kernel and a.pc.splits >= 2
+    if rows_case == "speculative_4_rows":
+        for e in engs:
+            e.spec_mask.random_(generator=torch.Generator(device=cuda).manual_seed(9))
+            e._forward(e.pc, e.spec_mask)
+        pa_, pb_ = a.pc, b.pc
+    else:
+        for e in engs:
+            e._g_win.fill_(1); e._g_tok.fill_(777)
+            e.bitmask.random_(generator=torch.Generator(device=cuda).manual_seed(11))
+            e._spec_chain()
+        pa_, pb_ = a.pd, b.pd
+        assert torch.equal(a.k_cache[:, :, :, 601], b.k_cache[:, :, :, 601]), "guessed winner's row"
+    torch.cuda.synchronize()
+    assert pa_.plan is not None and pb_.plan is None
+    for f in ("x", "x2", "act", "q", "attn", "k_new", "v_new", "xn", "logits"):
+        assert torch.equal(getattr(pa_, f), getattr(pb_, f)), f
