@@ -20,7 +20,9 @@ class RopeArgs(C.Structure):
     """dd_rope_args of include/dropdec.h"""
     _fields_ = [("cos_tab", C.c_void_p), ("sin_tab", C.c_void_p), ("seq_lens", C.c_void_p),
                 ("members", C.c_int), ("H", C.c_int), ("H_kv", C.c_int), ("D", C.c_int),
-                ("q_out", C.c_void_p), ("k_new", C.c_void_p), ("v_new", C.c_void_p)]
+                ("q_out", C.c_void_p), ("k_new", C.c_void_p), ("v_new", C.c_void_p),
+                ("guess_winner", C.c_void_p), ("guess_pos", C.c_void_p), ("guess_members", C.c_int), ("S_max", C.c_int),
+                ("k_cache", C.c_void_p), ("v_cache", C.c_void_p)]
 
 
 class PassArgs(C.Structure):
@@ -63,6 +65,9 @@ _SIGNATURES = {
     "dd_decode_attention_windows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                               _P, _P, C.c_size_t, _P]),
+    "dd_decode_attention_two_windows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P,
+                                                  C.c_size_t, _P]),
     "dd_commit_winner": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, _P]),
     "dd_aggregate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

@@ -41,6 +41,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
     return;
   }
   pdl_wait();
+  if (p.M2 > 0 && (int)blockIdx.z >= p.B) {
+    // second member window: its own members, key range and split partials; everything else is shared
+    AttnParams w = p;
+    w.M = p.M2; w.m0 = p.m02; w.seq_lens = p.seq_lens2;
+    w.part_o = p.part_o2; w.part_ml = p.part_ml2; w.tickets = p.tickets2;
+    attn_partial_body<D, QT, true>(&tmap_k, &tmap_v, w, L2Prefetch{}, blockIdx.x, blockIdx.y, blockIdx.z - p.B,
+                                   threadIdx.x, 0u, 1u, smem, s_full, s_ext, &s_last, [] { __syncthreads(); });
+    return;
+  }
   attn_partial_body<D, QT, true>(&tmap_k, &tmap_v, p, L2Prefetch{}, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, 0u,
                                  1u, smem, s_full, s_ext, &s_last, [] { __syncthreads(); });
 }
@@ -86,7 +95,7 @@ static int launch_attn(const AttnParams& p, const L2Prefetch& pf, const void* k_
     if (int rc = make_tmap_bf16_sw128(&tmap_k, p.k_cache, 3, dims, strides, box, "dd_decode_attention(k_cache)")) return rc;
     if (int rc = make_tmap_bf16_sw128(&tmap_v, p.v_cache, 3, dims, strides, box, "dd_decode_attention(v_cache)")) return rc;
   }
-  const size_t smem = attn_smem_bytes<D, QT>(p.M, p.bitmask ? p.mask_words : 0);
+  const size_t smem = attn_smem_bytes<D, QT>(p.M > p.M2 ? p.M : p.M2, p.bitmask ? p.mask_words : 0);
   {
     // opt in to > 48 KB dynamic smem: a per-DEVICE attribute, cached per device and instantiation (grow-only)
     static size_t configured[64];
@@ -109,8 +118,8 @@ static int launch_attn(const AttnParams& p, const L2Prefetch& pf, const void* k_
     if (extra < 1) extra = 1;
     if (extra > 8) extra = 8;
   }
-  DD_LAUNCH_CHAIN(attn_partial_kernel<D, QT>, dim3(p.num_splits + extra, p.H_kv, p.B), dim3(kAttnThreads), smem, st,
-                  tmap_k, tmap_v, p, pf);
+  DD_LAUNCH_CHAIN(attn_partial_kernel<D, QT>, dim3(p.num_splits + extra, p.H_kv, p.B * (p.M2 > 0 ? 2 : 1)),
+                  dim3(kAttnThreads), smem, st, tmap_k, tmap_v, p, pf);
   (void)k_new; (void)v_new; (void)out;
   if (p.num_splits == 1) DD_LAUNCH_CHAIN(attn_merge_kernel<D>, dim3(p.H, p.M, p.B), dim3(D), 0, st, p);
   return DD_OK;
@@ -191,6 +200,59 @@ extern "C" int dd_decode_attention_windows(const void* q, const void* k_new, con
   p.num_splits = num_splits;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int R = M * (H / H_kv);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 128)
+    return R <= 16 ? launch_attn<128, 1>(p, pf, k_new, v_new, out, st) : launch_attn<128, 2>(p, pf, k_new, v_new, out, st);
+  return R <= 16 ? launch_attn<64, 1>(p, pf, k_new, v_new, out, st) : launch_attn<64, 2>(p, pf, k_new, v_new, out, st);
+}
+
+extern "C" int dd_decode_attention_two_windows(const void* q, const void* k_new, const void* v_new, const void* k_cache,
+                                               const void* v_cache, const int32_t* seq_lens_a, const int32_t* seq_lens_b,
+                                               const int32_t* vis_start, const uint32_t* bitmask, int B, int members_a,
+                                               int members_b, int H, int H_kv, int D, int S_max, int n_vis,
+                                               int mask_words, float scale, int num_splits, void* out, void* workspace,
+                                               size_t workspace_bytes, dd_stream_t stream) {
+  using namespace dd;
+  const L2Prefetch pf = take_l2_prefetch();
+  const int Mt = members_a + members_b;
+  DD_CHECK_ARG(q && k_new && v_new && k_cache && v_cache && seq_lens_a && seq_lens_b && out && workspace,
+               "dd_decode_attention_two_windows: null pointer");
+  DD_CHECK_ARG(D == 64 || D == 128, "dd_decode_attention_two_windows: D=%d unsupported (64 or 128)", D);
+  DD_CHECK_ARG(((uintptr_t)k_cache & 15) == 0 && ((uintptr_t)v_cache & 15) == 0,
+               "dd_decode_attention_two_windows: the caches must be 16-byte aligned (TMA)");
+  DD_CHECK_ARG(H_kv >= 1 && H % H_kv == 0, "dd_decode_attention_two_windows: H=%d not a multiple of H_kv=%d", H, H_kv);
+  DD_CHECK_ARG(members_a >= 1 && members_b >= 1 && Mt <= DD_MAX_MEMBERS && members_a * (H / H_kv) <= 32 &&
+                   members_b * (H / H_kv) <= 32,
+               "dd_decode_attention_two_windows: windows of %d and %d members (at most 32 query rows per kv head each)",
+               members_a, members_b);
+  DD_CHECK_ARG(num_splits >= 2 && num_splits <= 256,
+               "dd_decode_attention_two_windows: num_splits=%d out of [2,256] (unsplit: dd_decode_attention_windows with "
+               "len_extra)", num_splits);
+  DD_CHECK_ARG(!bitmask || (vis_start && mask_words * 32 >= n_vis && mask_words <= kMaxMaskWords),
+               "dd_decode_attention_two_windows: bitmask needs vis_start and n_vis <= 32*mask_words <= %d",
+               32 * kMaxMaskWords);
+  const size_t one = (dd_attention_workspace_bytes(B, Mt, H, D, num_splits) + 255) / 256 * 256;
+  if (workspace_bytes < 2 * one) {
+    set_error("dd_decode_attention_two_windows: workspace %zu < %zu bytes", workspace_bytes, 2 * one);
+    return DD_ERR_WORKSPACE;
+  }
+  if (B == 0) return DD_OK;
+  AttnParams p{};
+  p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
+  p.seq_lens = seq_lens_a; p.vis_start = vis_start; p.bitmask = bitmask;
+  const size_t n_o = (size_t)B * Mt * H * num_splits * D, n_ml = (size_t)B * Mt * H * num_splits * 2;
+  p.part_o = (float*)workspace;
+  p.part_ml = p.part_o + n_o;
+  p.tickets = reinterpret_cast<int*>(p.part_ml + n_ml);
+  p.part_o2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + one);
+  p.part_ml2 = p.part_o2 + n_o;
+  p.tickets2 = reinterpret_cast<int*>(p.part_ml2 + n_ml);
+  p.k_new = (const __nv_bfloat16*)k_new; p.v_new = (const __nv_bfloat16*)v_new; p.out = (__nv_bfloat16*)out;
+  p.B = B; p.M = members_a; p.Mt = Mt; p.m0 = 0; p.H = H; p.H_kv = H_kv; p.S_max = S_max; p.n_vis = n_vis;
+  p.mask_words = mask_words; p.num_splits = num_splits;
+  p.M2 = members_b; p.m02 = members_a; p.seq_lens2 = seq_lens_b;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const int R = (members_a > members_b ? members_a : members_b) * (H / H_kv);
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 128)
     return R <= 16 ? launch_attn<128, 1>(p, pf, k_new, v_new, out, st) : launch_attn<128, 2>(p, pf, k_new, v_new, out, st);

@@ -66,6 +66,12 @@ struct AttnParams {
   int B, M, H, H_kv, S_max, n_vis, mask_words, num_splits;
   int Mt, m0;  // the M members of this call are members m0..m0+M-1 of the Mt stored per sequence (q, k_new, v_new, out, bitmask)
   float scale_log2;  // scale * log2(e)
+  // second member window of the same launch (dd_decode_attention_two_windows; M2 == 0: none): members m02..m02+M2-1
+  // attend keys [0, seq_lens2[b]) with their own split partials -- the grid's z index runs over (window, sequence)
+  int M2, m02;
+  const int32_t* seq_lens2;
+  float *part_o2, *part_ml2;
+  int* tickets2;
 };
 
 // Q rows (staged by the threads): one row of D bf16 = D/8 chunks of 16 B; chunk c of row r lives at

@@ -102,6 +102,10 @@ struct GemmArgs {
   const int32_t* seq_lens;
   int members, H, H_kv, D;
   __nv_bfloat16 *q_out, *k_new, *v_new;
+  // commit ahead (lookahead pass): row b * guess_members + guess_winner[b] also goes to cache row guess_pos[b]
+  const int32_t *guess_winner, *guess_pos;
+  int guess_members, S_max;
+  __nv_bfloat16 *k_cache, *v_cache;
 };
 
 template <int MT, int EPI, bool NORM>
@@ -264,15 +268,30 @@ __global__ void __launch_bounds__(kGemmThreads) skinny_gemm_kernel(const GemmArg
         const float c = a.cos_tab[(size_t)pos * half + i], sn = a.sin_tab[(size_t)pos * half + i];
         __nv_bfloat16* dst = head < a.H ? a.q_out + ((size_t)tok * a.H + head) * a.D
                                         : a.k_new + ((size_t)tok * a.H_kv + (head - a.H)) * a.D;
-        dst[i] = __float2bfloat16_rn(x1 * c - x2 * sn);
-        dst[i + half] = __float2bfloat16_rn(x2 * c + x1 * sn);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(x1 * c - x2 * sn), hi = __float2bfloat16_rn(x2 * c + x1 * sn);
+        dst[i] = lo;
+        dst[i + half] = hi;
+        if (a.guess_winner && head >= a.H) {
+          const int b = tok / a.guess_members, gp = a.guess_pos[b];
+          if (tok - b * a.guess_members == a.guess_winner[b] && gp < a.S_max) {
+            __nv_bfloat16* c2 = a.k_cache + (((size_t)b * a.H_kv + (head - a.H)) * a.S_max + gp) * a.D;
+            c2[i] = lo;
+            c2[i + half] = hi;
+          }
+        }
       }
     } else {
       for (int o = tid; o < MT * 8 * 16; o += kGemmThreads) {
         const int r = o & 15, tok = o >> 4;
         if (tok >= M) continue;
         const int n = n0 + r - (a.H + a.H_kv) * a.D;  // feature inside the v block
-        a.v_new[(size_t)tok * a.H_kv * a.D + n] = __float2bfloat16_rn(red(tok >> 3, r, tok & 7));
+        const __nv_bfloat16 v = __float2bfloat16_rn(red(tok >> 3, r, tok & 7));
+        a.v_new[(size_t)tok * a.H_kv * a.D + n] = v;
+        if (a.guess_winner) {
+          const int b = tok / a.guess_members, gp = a.guess_pos[b];
+          if (tok - b * a.guess_members == a.guess_winner[b] && gp < a.S_max)
+            a.v_cache[(((size_t)b * a.H_kv + n / a.D) * a.S_max + gp) * a.D + n % a.D] = v;
+        }
       }
     }
     return;
@@ -374,6 +393,14 @@ extern "C" int dd_decoder_linear(const void* x, const void* norm_w, float eps, c
     a.cos_tab = rope->cos_tab; a.sin_tab = rope->sin_tab; a.seq_lens = rope->seq_lens;
     a.members = rope->members; a.H = rope->H; a.H_kv = rope->H_kv; a.D = rope->D;
     a.q_out = (__nv_bfloat16*)rope->q_out; a.k_new = (__nv_bfloat16*)rope->k_new; a.v_new = (__nv_bfloat16*)rope->v_new;
+    if (rope->guess_winner) {
+      DD_CHECK_ARG(rope->guess_pos && rope->k_cache && rope->v_cache && rope->guess_members >= 1 && rope->S_max >= 1 &&
+                       M % rope->guess_members == 0,
+                   "dd_decoder_linear: the commit ahead needs guess_pos, the layer's caches, S_max and guess_members "
+                   "dividing M=%d", M);
+      a.guess_winner = rope->guess_winner; a.guess_pos = rope->guess_pos; a.guess_members = rope->guess_members;
+      a.S_max = rope->S_max; a.k_cache = (__nv_bfloat16*)rope->k_cache; a.v_cache = (__nv_bfloat16*)rope->v_cache;
+    }
   }
   if (M == 0) return DD_OK;
   return norm_w ? launch_any<true>(a, epilogue, (cudaStream_t)stream)

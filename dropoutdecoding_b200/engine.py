@@ -140,6 +140,7 @@ class _PassBuffers:
     ws: torch.Tensor
     splits: int
     plan: Optional[object] = None      # ops.DecoderPassPlan of the persistent pass kernel (built at first use)
+    ws2: Optional[torch.Tensor] = None  # workspace of the two-window attention launch of the lookahead pass (first use)
 
 
 class DropoutDecodeEngine(SpeculativeSchedules):
@@ -256,12 +257,14 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         rows = B * M
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         bf = dict(dtype=torch.bfloat16, device=dev)
-        # split-KV factor (measured sweep, profiles/README.md 2): about one CTA per SM, never fewer than ~3 key tiles
-        # per CTA; (sequence, kv head) pairs that already fill the SMs stay unsplit (B >= 5 at 32 kv heads), and a
-        # long context on fewer pairs than SMs is cut at least in two so that two CTAs share an SM
+        # split-KV factor (measured sweeps, profiles/README.md 0 and 2): as many splits as keep the grid in ONE wave of one
+        # CTA per SM (floor, not round: 4 x 32 = 128 CTAs beat 3 x 32 and 5 x 32 for one 7B sequence, 3.22 vs 3.36 ms per
+        # token), never fewer than ~2 key tiles per CTA; (sequence, kv head) pairs that already fill the SMs stay unsplit
+        # (B >= 5 at 32 kv heads), and a long context on fewer pairs than SMs is cut at least in two so that two CTAs
+        # share an SM
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         pairs, tiles = B * Hkv, max(1, -(-est_seq // 64))
-        splits = max(1, min(int(sms / pairs + 0.5), max(1, tiles // 3), 32))
+        splits = max(1, min(sms // pairs, max(1, tiles // 2), 32))
         if splits == 1 and pairs < sms and tiles >= 16:
             splits = 2
         if self.attn_splits is not None:

@@ -225,6 +225,37 @@ def decode_attention(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, 
     return out
 
 
+def decode_attention_two_windows(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, k_cache: torch.Tensor,
+                                 v_cache: torch.Tensor, seq_lens_a: torch.Tensor, seq_lens_b: torch.Tensor,
+                                 members_a: int, vis_start: Optional[torch.Tensor], bitmask: Optional[torch.Tensor],
+                                 n_vis: int, scale: float, num_splits: int, out: torch.Tensor,
+                                 workspace: torch.Tensor) -> torch.Tensor:
+    """dd_decode_attention_two_windows: members [0, members_a) attend keys [0, seq_lens_a), the rest [0, seq_lens_b), split
+    key ranges, one launch.  workspace: two_window_attention_workspace."""
+    L = _lib.load()
+    for t, n in ((q, "q"), (k_new, "k_new"), (v_new, "v_new"), (k_cache, "k_cache"), (v_cache, "v_cache"), (out, "out")):
+        _need(t, torch.bfloat16, n)
+    _need(seq_lens_a, torch.int32, "seq_lens_a"); _need(seq_lens_b, torch.int32, "seq_lens_b")
+    B, M, H, D = q.shape
+    H_kv, S_max = k_cache.shape[1], k_cache.shape[2]
+    words = 0
+    if bitmask is not None:
+        _need(bitmask, torch.int32, "bitmask"); _need(vis_start, torch.int32, "vis_start")
+        words = bitmask.shape[-1]
+    check(L.dd_decode_attention_two_windows(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(k_cache), _ptr(v_cache),
+                                            _ptr(seq_lens_a), _ptr(seq_lens_b), _ptr(vis_start), _ptr(bitmask), B,
+                                            members_a, M - members_a, H, H_kv, D, S_max, n_vis, words, float(scale),
+                                            num_splits, _ptr(out), _ptr(workspace),
+                                            workspace.numel() * workspace.element_size(), _stream()),
+          "dd_decode_attention_two_windows")
+    return out
+
+
+def two_window_attention_workspace(B: int, M: int, H: int, D: int, num_splits: int, device) -> torch.Tensor:
+    one = (_lib.load().dd_attention_workspace_bytes(B, M, H, D, num_splits) + 255) // 256 * 256
+    return torch.zeros(2 * one, dtype=torch.uint8, device=device)
+
+
 def commit_winner(k_new_all: torch.Tensor, v_new_all: torch.Tensor, winner: torch.Tensor, seq_lens: torch.Tensor,
                   k_cache_all: torch.Tensor, v_cache_all: torch.Tensor) -> None:
     """k_new_all [L,B,M,H_kv,D] -> caches [L,B,H_kv,S_max,D] at row seq_lens[b] of the winner member."""
@@ -366,6 +397,12 @@ def decoder_linear(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_NONE, *
         ra = _lib.RopeArgs(_ptr(rope["cos"]), _ptr(rope["sin"]), _ptr(rope["seq_lens"]), int(rope["members"]),
                            int(rope["H"]), int(rope["H_kv"]), int(rope["D"]), _ptr(rope["q_out"]),
                            _ptr(rope["k_new"]), _ptr(rope["v_new"]))
+        if rope.get("guess_winner") is not None:      # commit ahead of the lookahead pass (dd_rope_args)
+            _need(rope["guess_winner"], torch.int32, "guess_winner"); _need(rope["guess_pos"], torch.int32, "guess_pos")
+            _need(rope["k_cache"], torch.bfloat16, "k_cache"); _need(rope["v_cache"], torch.bfloat16, "v_cache")
+            ra.guess_winner, ra.guess_pos = _ptr(rope["guess_winner"]), _ptr(rope["guess_pos"])
+            ra.guess_members, ra.S_max = int(rope["guess_members"]), rope["k_cache"].shape[-2]
+            ra.k_cache, ra.v_cache = _ptr(rope["k_cache"]), _ptr(rope["v_cache"])
     elif out is None:
         out = torch.empty(M, N, dtype=torch.float32 if epilogue == EPI_F32 else torch.bfloat16, device=x.device)
     import ctypes

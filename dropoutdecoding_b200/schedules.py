@@ -196,20 +196,33 @@ class SpeculativeSchedules:
         H, Hkv, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
         ops.embed_gather(self.w.embed, self._row_tok_c, 1, pd.x)
         x, x2 = pd.x, pd.x2
+        G = H // Hkv
+        two_windows = (pd.splits >= 2 and (K + 1) * G <= 32 and os.environ.get("DD_TWO_WINDOW_ATTN", "1") == "1")
+        if two_windows and pd.ws2 is None:
+            pd.ws2 = ops.two_window_attention_workspace(self.B, M, H, D, pd.splits, self.dev)
         for l, lw in enumerate(self.w.layers):
             ops.rmsnorm(x, lw["ln1"], cfg.rms_eps, pd.xn)
+            # (the guessed winner's new K/V row goes to cache row S from the projection's epilogue: no commit launch)
             ops.decoder_linear(pd.xn, lw["wqkv"], ops.EPI_ROPE,
                                rope=dict(cos=self.cos, sin=self.sin, seq_lens=self._row_pos_c, members=1, H=H, H_kv=Hkv,
-                                         D=D, q_out=pd.q, k_new=pd.k_new[l], v_new=pd.v_new[l]))
-            ops.commit_winner(pd.k_new[l:l + 1], pd.v_new[l:l + 1], self._g_win, self.seq_lens, self.k_cache[l:l + 1],
-                              self.v_cache[l:l + 1])
-            self._attention_rows(pd, l, self.chain_mask, self.seq_lens, 0, K)
-            self._attention_rows(pd, l, self.chain_mask, self._seq_p1, K, M)
+                                         D=D, q_out=pd.q, k_new=pd.k_new[l], v_new=pd.v_new[l],
+                                         guess_winner=self._g_win, guess_pos=self.seq_lens, guess_members=M,
+                                         k_cache=self.k_cache[l], v_cache=self.v_cache[l]))
+            if two_windows:
+                # both member windows in ONE launch (split key ranges, each with its own partials): side by side instead
+                # of one latency-bound launch after the other
+                ops.decode_attention_two_windows(pd.q, pd.k_new[l], pd.v_new[l], self.k_cache[l], self.v_cache[l],
+                                                 self.seq_lens, self._seq_p1, K, self.vis_start, self.chain_mask,
+                                                 self.n_vis, self.scale, pd.splits, pd.attn, pd.ws2)
+                self.launches_per_step += 1
+            else:
+                self._attention_rows(pd, l, self.chain_mask, self.seq_lens, 0, K)
+                self._attention_rows(pd, l, self.chain_mask, self._seq_p1, K, M)
             ops.decoder_linear(pd.attn.view(M, H * D), lw["wo"], ops.EPI_RESIDUAL, residual=x, out=x2)
             ops.rmsnorm(x2, lw["ln2"], cfg.rms_eps, pd.xn)
             ops.decoder_linear(pd.xn, lw["wgu"], ops.EPI_SWIGLU, out=pd.act)
             ops.decoder_linear(pd.act, lw["wd"], ops.EPI_RESIDUAL, residual=x2, out=x)
-            self.launches_per_step += 7
+            self.launches_per_step += 6
         ops.rmsnorm(x, self.w.norm, cfg.rms_eps, pd.xn)
         ops.decoder_linear(pd.xn, self.w.lm_head_padded, ops.EPI_F32, out=pd.logits.view(M, self.Vp))
 

@@ -189,6 +189,19 @@ int dd_decode_attention_windows(const void* q, const void* k_new, const void* v_
                                 int H_kv, int D, int S_max, int n_vis, int mask_words, float scale, int num_splits,
                                 void* out, void* workspace, size_t workspace_bytes, dd_stream_t stream);
 
+/* Two member windows in ONE launch with a SPLIT key range (the lookahead pass of one sequence: members [0, members_a) --
+ * the repeated step -- attend keys [0, seq_lens_a[b]), members [members_a, members_a + members_b) -- the next step's
+ * contexts -- attend keys [0, seq_lens_b[b])).  Each window keeps the split points, partials and merge of its own
+ * dd_decode_attention_active call (bit-identical results), but the two grids run side by side instead of one after the
+ * other: at one sequence both are latency-bound and a quarter of the lookahead pass.  workspace: 2 x
+ * dd_attention_workspace_bytes(B, members_a + members_b, H, D, num_splits), each rounded up to 256 bytes.  num_splits >= 2
+ * (unsplit ranges: dd_decode_attention_windows with len_extra). */
+int dd_decode_attention_two_windows(const void* q, const void* k_new, const void* v_new, const void* k_cache,
+                                    const void* v_cache, const int32_t* seq_lens_a, const int32_t* seq_lens_b,
+                                    const int32_t* vis_start, const uint32_t* bitmask, int B, int members_a, int members_b,
+                                    int H, int H_kv, int D, int S_max, int n_vis, int mask_words, float scale,
+                                    int num_splits, void* out, void* workspace, size_t workspace_bytes, dd_stream_t stream);
+
 /* Commit the winning member's new-token K/V rows of every layer into the shared cache at
  * position seq_lens[b] (replaces "the winner's cache becomes the live cache",
  * models/llava.py:370-376).  seq_lens is NOT advanced here (see dd_step_advance).  winner[b] < 0 skips sequence b
@@ -290,6 +303,15 @@ typedef struct dd_rope_args {
   void* q_out; /* bf16 [B, members, H, D]    */
   void* k_new; /* bf16 [B, members, H_kv, D] */
   void* v_new;
+  /* optional "commit ahead" of the lookahead pass (guess_winner NULL: off): the new K/V rows of row
+   * b * guess_members + guess_winner[b] are ALSO written to row guess_pos[b] of this layer's cache [B, H_kv, S_max, D] --
+   * dd_commit_winner of one layer folded into the projection's epilogue (guess_winner[b] outside [0, guess_members) or
+   * guess_pos[b] >= S_max: nothing is written for that sequence) */
+  const int32_t* guess_winner; /* [B] */
+  const int32_t* guess_pos;    /* [B] */
+  int guess_members, S_max;
+  void* k_cache; /* bf16 [B, H_kv, S_max, D] */
+  void* v_cache;
 } dd_rope_args;
 int dd_decoder_linear(const void* x /* bf16 [M, K] */, const void* norm_w /* bf16 [K] or NULL */, float eps,
                       const void* w /* bf16 [N(,2N), K] */, const void* residual /* bf16 [M, N] or NULL */,

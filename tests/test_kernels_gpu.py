@@ -146,6 +146,40 @@ def test_aggregate_batched_unaligned_vocab(ops, cuda):
     assert tok[2].item() == 31
 
 
+@pytest.mark.parametrize("B,K,V,ld", [(3, 2, 7, 7), (1, 16, 5, 12), (70, 4, 1000, 1000), (2, 3, 32064, 32064)])
+@pytest.mark.parametrize("mode", ["vote", "mean"])
+def test_aggregate_cluster_slices_edges(ops, cuda, B, K, V, ld, mode):
+    """The 8-CTA cluster per sequence: vocabularies smaller than the cluster (empty slices), 16 members, padded rows,
+    more sequences than SMs, ties that straddle two slices, the winner's row / the mean gathered from all slices, and
+    run-to-run bit equality."""
+    g = torch.Generator().manual_seed(B * 131 + K * 17 + V)
+    full = torch.randn(B, K, ld, generator=g)
+    full[..., V:] = 50.0                                   # padding columns must never win
+    if V >= 1000:
+        per = -(-(V // 4 if V % 4 == 0 and ld % 4 == 0 else V) // 8) * (4 if V % 4 == 0 and ld % 4 == 0 else 1)
+        full[0, 0, per - 1] = full[0, 0, per] = 20.0       # the same maximum on both sides of a slice boundary
+    dev = full.to(cuda)
+    mids, win, tok, out = ops.aggregate(dev, mode, want_logits=True, vocab=V)
+    l = full[..., :V]
+    assert torch.equal(mids.cpu().long(), torch.argmax(l, dim=-1))
+    if V >= 1000:
+        assert mids[0, 0].item() == per - 1
+    if mode == "vote":
+        for b in range(B):
+            ids = mids[b].tolist()
+            best = max(ids, key=lambda t: (ids.count(t), -ids.index(t)))
+            assert tok[b].item() == best and win[b].item() == ids.index(best)
+            assert torch.equal(out[b].cpu(), l[b, win[b].item()])
+    else:
+        mean = l[:, 0].clone()
+        for m in range(1, K):
+            mean = mean + l[:, m]
+        mean = mean / K
+        assert torch.equal(out.cpu(), mean) and torch.equal(tok.cpu().long(), torch.argmax(mean, dim=-1))
+    again = ops.aggregate(dev, mode, want_logits=True, vocab=V)
+    assert all(torch.equal(x, y) for x, y in zip((mids, win, tok, out), again))
+
+
 # ---------------------------------------------------------------------------------------------
 # (3) decode attention vs an fp32 restatement of K+1 masked single-query SDPA calls
 # ---------------------------------------------------------------------------------------------

@@ -152,7 +152,9 @@ def test_engine_7b_teacher_forced_steps(seven_b, cuda, spec):
         if int(eng.y_init[0]) != tr.y_init[s]:
             # the preliminary argmax may land on the runner-up only inside the 32-layer noise floor; that selects another
             # relevant set, i.e. other masks, so the rest of this step is not comparable (the next one is: teacher-forced)
-            assert int(eng.y_init[0]) == i2 and v1 - v2 <= 0.3, f"step {s}: y_init {int(eng.y_init[0])} vs {i1} (gap {v1 - v2:.3f})"
+            # (either of the oracle's top two: on an exact tie its argmax -- the lower index -- need not be top2's first)
+            assert int(eng.y_init[0]) in (i1, i2) and v1 - v2 <= 0.3, \
+                f"step {s}: y_init {int(eng.y_init[0])} vs {tr.y_init[s]} (top two {i1}, {i2}; gap {v1 - v2:.3f})"
             step_flips += 1
         else:
             assert eng.n_masked[0].tolist() == tr.masked_numbers[s], f"step {s}: masked_numbers"
