@@ -64,7 +64,11 @@ def main():
         full.decode(T, use_graph=True)
         # on one GPU emulate rank 1 of 2: sequences 4..7 decoded on their own
         lo, hi = dd_dist.shard_range(8, world, rank) if world > 1 else (4, 8)
-        part = DropoutDecodeEngine(w, hi - lo, n_vis, S0 + T + 4, probs=probs[:3], max_steps=32, seed=24, seq_base=lo)
+        # (the split-KV factor of the attention is chosen from the number of (sequence, kv head) pairs on the GPU and is
+        #  part of the numerics -- another split, another fp32 summation order; a shard that has to reproduce the unsharded
+        #  tokens bit for bit pins it.  Unsplit ranges -- every batch that fills the SMs -- need nothing.)
+        part = DropoutDecodeEngine(w, hi - lo, n_vis, S0 + T + 4, probs=probs[:3], max_steps=32, seed=24, seq_base=lo,
+                                   attn_splits=full.pb.splits)
         prime(part, hi - lo, seq0=lo)
         part.decode(T, use_graph=True)
         torch.cuda.synchronize()
