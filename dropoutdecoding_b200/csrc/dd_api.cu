@@ -51,9 +51,9 @@ static int g_pdl = -1;
 bool pdl_enabled(bool weight_gemm) {
   if (g_pdl < 0) {
     const char* e = getenv("DD_PDL");
-    g_pdl = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    g_pdl = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0;
   }
-  return g_pdl == 1 || (g_pdl == 2 && weight_gemm);
+  return g_pdl == 1 || (g_pdl == 2 && weight_gemm) || (g_pdl == 3 && !weight_gemm);
 }
 
 static thread_local L2Prefetch g_l2_prefetch{};
@@ -78,7 +78,7 @@ extern "C" int dd_version(void) { return 100; }  // 0.1.0
 extern "C" int dd_set_chain_launch(int on) {
   dd::pdl_enabled();   // (resolves the environment default)
   const int was = dd::g_pdl;
-  dd::g_pdl = (on == 1 || on == 2) ? on : 0;
+  dd::g_pdl = (on >= 1 && on <= 3) ? on : 0;
   return was;
 }
 extern "C" const char* dd_last_error(void) { return dd::g_last_error.c_str(); }

@@ -186,9 +186,12 @@ class DropoutDecodeEngine(SpeculativeSchedules):
         if self.gemm_backend not in ("auto", "stream", "library", "skinny"):
             raise ValueError(self.gemm_backend)
         # programmatic dependent launch of the pass kernels: None = per pass (on for dd_stream_gemm passes); DD_PDL=0/1 pins it
-        self.chain_launch = {"0": 0, "1": 1, "2": 2}.get(os.environ.get("DD_PDL", ""), None)
-        # mode of the <= 16-row passes (skinny GEMMs): DD_PDL_SKINNY = 0 | 1 | 2 (2: only the GEMM launches are dependent)
-        self.chain_launch_skinny = int(os.environ.get("DD_PDL_SKINNY", "0"))
+        self.chain_launch = {"0": 0, "1": 1, "2": 2, "3": 3}.get(os.environ.get("DD_PDL", ""), None)
+        # mode of the <= 16-row passes (skinny GEMMs): DD_PDL_SKINNY = 0 | 1 | 2 | 3.  3 (default): only the SMALL kernels
+        # (RMSNorm, attention, vote ...) are programmatic dependents -- their launch latency overlaps the drain of the GEMM
+        # in front of them, while no GEMM's CTAs queue up behind anything: 3.232 -> 3.208 ms per token, 2.993 -> 2.966 ms
+        # per 4-row pass in back-to-back pairs; every kernel (1): 3.60 vs 3.45, only the GEMMs (2): 3.66 (profiles/README.md)
+        self.chain_launch_skinny = int(os.environ.get("DD_PDL_SKINNY", "3"))
         self.attn_splits = attn_splits  # None: chosen per pass from the measured sweep (_alloc_pass); tests pin it
         self.seq_base = int(seq_base)   # global index of sequence 0 (batch sharded over GPUs)
         self.vote_on = vote_on          # "hidden": InstructBLIP votes on the argmax of the final hidden state

@@ -42,7 +42,7 @@ def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 
 def set_chain_launch(mode) -> int:
     """dd_set_chain_launch: programmatic dependent launch for the dd_* kernels launched from now on -- False / 0 off,
-    True / 1 every kernel, 2 only the skinny weight GEMMs (returns the previous mode)."""
+    True / 1 every kernel, 2 only the skinny weight GEMMs, 3 every kernel but those (returns the previous mode)."""
     return int(_lib.load().dd_set_chain_launch(int(mode)))
 
 

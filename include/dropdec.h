@@ -56,8 +56,10 @@ const char* dd_last_error(void);
  * draining and run its independent prologue -- dd_stream_gemm puts its whole ring of weight tiles in flight --
  * before it waits for the predecessor's results (griddepcontrol.wait).  2: only the skinny weight GEMMs
  * (dd_skinny_gemm / dd_decoder_linear) are launched that way: their first weight batch and launch latency overlap the
- * small kernel in front of them (RMSNorm, attention), while no small kernel queues up behind a GEMM's tail.  0: off.
- * Results are identical in every mode.  Default: the DD_PDL environment variable ("1" / "2"), else off.  No reference
+ * small kernel in front of them (RMSNorm, attention), while no small kernel queues up behind a GEMM's tail.  3: the
+ * opposite -- every kernel EXCEPT the skinny weight GEMMs: the small kernels' launch latency overlaps the drain of the
+ * GEMM in front of them (the engine's choice for passes of <= 16 rows).  0: off.
+ * Results are identical in every mode.  Default: the DD_PDL environment variable ("1" / "2" / "3"), else off.  No reference
  * counterpart (the reference's forward is a sequence of stream-ordered torch kernels, models/llama.py:16-69). */
 int dd_set_chain_launch(int mode);
 
