@@ -40,18 +40,18 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const __grid
     l2_prefetch_slice(pf, idx * kAttnWarps + (threadIdx.x >> 5), extra * gridDim.y * gridDim.z * kAttnWarps);
     return;
   }
-  pdl_wait();
+  auto wait = [] { pdl_wait(); };
   if (p.M2 > 0 && (int)blockIdx.z >= p.B) {
     // second member window: its own members, key range and split partials; everything else is shared
     AttnParams w = p;
     w.M = p.M2; w.m0 = p.m02; w.seq_lens = p.seq_lens2;
     w.part_o = p.part_o2; w.part_ml = p.part_ml2; w.tickets = p.tickets2;
     attn_partial_body<D, QT, true>(&tmap_k, &tmap_v, w, L2Prefetch{}, blockIdx.x, blockIdx.y, blockIdx.z - p.B,
-                                   threadIdx.x, 0u, 1u, smem, s_full, s_ext, &s_last, [] { __syncthreads(); });
+                                   threadIdx.x, 0u, 1u, smem, s_full, s_ext, &s_last, [] { __syncthreads(); }, wait);
     return;
   }
   attn_partial_body<D, QT, true>(&tmap_k, &tmap_v, p, L2Prefetch{}, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, 0u,
-                                 1u, smem, s_full, s_ext, &s_last, [] { __syncthreads(); });
+                                 1u, smem, s_full, s_ext, &s_last, [] { __syncthreads(); }, wait);
 }
 
 // Unsplit case: out[b,m,h,:] = merge(the partial, own new-token row).  One CTA of D threads per (b,m,h).

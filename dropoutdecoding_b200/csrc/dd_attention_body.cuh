@@ -93,11 +93,17 @@ __device__ __forceinline__ uint32_t swz_kv(int row, int chunk) {
 // s_ext / s_last_p: small shared scratch owned by the caller.  May be called again (next item) after it returns: the
 // mbarriers are re-initialised on entry, every thread has passed the last sync of the previous item by then.
 // Warps 1.. issue the L2 prefetch hint `pf` behind the ring's first tiles (cta_lin / n_cta: this CTA in the grid).
-template <int D, int QT, bool kChainTrigger, typename Sync>
+// wait_for_predecessor: griddepcontrol.wait of a programmatic dependent launch (a no-op functor elsewhere).  It is
+// called AFTER the mbarrier set-up and after the loads of the first tiles that end before the range's last key have
+// been issued: those cache rows were final before the kernel in front of this one started (the only cache row a pass
+// writes ahead of its attention is the lookahead's commit at the LAST key of a window), while q, k_new, v_new and the
+// masks are only touched after the wait.
+template <int D, int QT, bool kChainTrigger, typename Sync, typename Wait>
 __device__ __forceinline__ void attn_partial_body(const CUtensorMap* tmap_k_p, const CUtensorMap* tmap_v_p,
                                                   const AttnParams& p, const L2Prefetch& pf, int split, int hkv, int b,
                                                   int tid, unsigned cta_lin, unsigned n_cta, uint8_t* smem,
-                                                  uint64_t* s_full, int* s_ext, int* s_last_p, Sync sync) {
+                                                  uint64_t* s_full, int* s_ext, int* s_last_p, Sync sync,
+                                                  Wait wait_for_predecessor) {
   constexpr int CH = D / 8;            // 16-byte chunks per row
   constexpr int ROW_B = D * 2;         // bytes per row
   constexpr int TILE_B = kTileKeys * ROW_B;
@@ -146,11 +152,21 @@ __device__ __forceinline__ void attn_partial_body(const CUtensorMap* tmap_k_p, c
     }
   };
 
-  // ---- prologue: start the ring, stage Q and the member bitmasks -------------------------------
+  // ---- prologue: start the ring (early tiles before the dependency wait), stage Q and the member bitmasks --------
+  int early = 0;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s)
-      if (s < ntiles) load_tile(s, s);
+      if (early == s && s < ntiles && k_beg + (s + 1) * kTileKeys <= S - 1) {
+        load_tile(s, s);
+        early = s + 1;
+      }
+  }
+  wait_for_predecessor();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s)
+      if (s >= early && s < ntiles) load_tile(s, s);
   }
   // L2 prefetch hint (dd_hint_l2_prefetch): warps 1.. issue it behind the ring's first K/V tiles
   if (warp) l2_prefetch_slice(pf, cta_lin * (kAttnWarps - 1) + (warp - 1), n_cta * (kAttnWarps - 1));

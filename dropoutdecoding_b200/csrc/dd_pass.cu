@@ -480,7 +480,7 @@ __device__ __forceinline__ void attention_phase(const PassParams& p, const PassL
       const int split = it % ap.num_splits, hkv = (it / ap.num_splits) % ap.H_kv, b = it / (ap.num_splits * ap.H_kv);
       attn_partial_body<D, 1, false>(&ly.tmap_k, &ly.tmap_v, ap, L2Prefetch{}, split, hkv, b, tid, 0u, 1u, smem, s_full,
                                      s_ext, s_last,
-                                     [] { asm volatile("bar.sync 1, %0;" ::"n"(kAttnThreads) : "memory"); });
+                                     [] { asm volatile("bar.sync 1, %0;" ::"n"(kAttnThreads) : "memory"); }, [] {});
       asm volatile("bar.sync 1, %0;" ::"n"(kAttnThreads) : "memory");   // s_last / the ring are free again
     }
     base += items;
