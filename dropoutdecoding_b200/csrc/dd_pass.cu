@@ -5,22 +5,26 @@
 //
 // Why: with 4-7 rows the pass is a 13 GB weight stream (2.07 ms at the measured HBM peak) that the launch chain cuts
 // into ~230 kernels; every boundary drains the stream (launch gap, pipeline ramp, tail), and the latency-bound
-// kernels between the GEMMs (attention, RMSNorm) leave HBM idle: 3.4 ms per pass.  Here one CTA per SM stays resident
-// for the pass:
-//   * phases are separated by a grid barrier (one atomic + one acquire spin, ~1 us) instead of a kernel boundary, and
-//     every CTA puts the first weight batch of its next GEMM tile in flight BEFORE it arrives at the barrier -- the
-//     weights never depend on the previous phase, so the stream restarts before the barrier resolves;
-//   * a CTA is two groups of 8 warps; a group owns 16 output features (16 + 16 for SwiGLU) at a time and runs the
-//     arithmetic of dd_skinny_gemm (same k split over the warps, same MMA order, same cross-warp sum, same epilogue
-//     rounding points), so the pass is bit-identical to the launch chain;
+// kernels between the GEMMs (attention, RMSNorm) leave HBM idle: 3.4 ms per pass.  Here one CTA of 8 warps per SM stays
+// resident for the pass (cooperative launch):
+//   * phases are separated by a grid barrier (one release atomic + one acquire spin per CTA, bounded) instead of a
+//     kernel boundary;
+//   * a CTA owns 16 output features (16 + 16 for SwiGLU) at a time and runs the arithmetic of dd_skinny_gemm (same k
+//     split over the 8 warps, same MMA order, same cross-warp sum, same epilogue rounding points), so the pass is
+//     bit-identical to the launch chain; the flat (tile, batch) sequence of a phase is software-pipelined over two
+//     register batches per thread, so a tile's reduction / epilogue runs under the next tile's loads;
 //   * the RMSNorms disappear into the GEMM that consumes them: every CTA normalises the (<= 16) rows once into shared
-//     memory (rmsnorm_kernel's arithmetic) while its first weight batch is in flight, and the B fragments of all its
-//     tiles come from there;
+//     memory (rmsnorm_kernel's arithmetic, all rows in one L2 round trip) and the B fragments of all its tiles come
+//     from there;
 //   * attention: warps 0-3 of a CTA run the work items of dd_attention.cu's body (split x kv head x sequence x member
-//     window; the chain pass of the lookahead schedule has two windows with different lengths); the other twelve warps
-//     of every CTA issue bulk L2 prefetches of o_proj's weights and the head of gate/up, so HBM keeps streaming;
+//     window; the chain pass of the lookahead schedule has two windows with different lengths);
 //   * the lookahead's "guessed winner" K/V row goes to its cache row from the QKV epilogue (no commit launch).
 // Algorithmic bytes per pass: the decoder weights once + the K/V prefix once per attention window.
+// STATUS (profiles/README.md 0): correct and bit-identical to the chain (tests), but measured SLOWER --
+// 4.8 vs 3.2 ms per 7B pass: 128 KB of registers in flight per SM bound the steady state at 4.5-5.5 TB/s and every phase
+// opens with a 13-16 us bubble (row staging + the first tile's latency with all SMs starting cold at once).  Bulk L2
+// prefetches (kept behind DD_PASS_TILES_AHEAD / DD_PASS_TILES_PRE / prefetch_gate_up_bytes, all 0) and cp.async
+// shared-memory slots made it slower still.  The engine uses it only with DD_PASS=1.
 #include <cstring>
 
 #include "dd_attention_body.cuh"

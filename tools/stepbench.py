@@ -26,6 +26,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--no-graph", action="store_true")
 ap.add_argument("--vote-on", default="logits")
 ap.add_argument("--topk", type=int, default=5)
+ap.add_argument("--stop-token", type=int, default=None, help="decode with an EOS id the model never emits (host-side EOS checks on)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 cfg = {"7b": DecoderConfig.llava15_7b, "next": DecoderConfig.llava_next_mistral_7b, "tiny": DecoderConfig.tiny,
@@ -51,7 +52,7 @@ with torch.no_grad():
         reset()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.decode(a.steps, use_graph=not a.no_graph)
+        eng.decode(a.steps, use_graph=not a.no_graph, stop_token=a.stop_token)
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / a.steps)
