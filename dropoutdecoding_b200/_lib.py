@@ -54,6 +54,7 @@ _SIGNATURES = {
                                   C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "dd_sample_masks_seq": (C.c_int, [_P, _P, C.c_int, _P, C.POINTER(C.c_double), C.c_int, _P, C.c_uint64,
                                       C.c_uint64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
+    "dd_schedule_flags": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P, _P]),
     "dd_philox_uniform": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, _P, _P]),
     "dd_attention_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "dd_decode_attention": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,

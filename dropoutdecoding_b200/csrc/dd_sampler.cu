@@ -185,6 +185,33 @@ __global__ void philox_uniform_kernel(uint64_t seed, uint64_t offset, int n, flo
   if (i < n) out[i] = philox_uniform(seed, (uint64_t)i, offset);
 }
 
+
+// Host-decision flags of the one-sequence speculative schedule (schedules.py), one launch instead of ~9 elementwise ones:
+//   flags[0] = (tok_a == tok_b) && (win_a == win_b) for every sequence  -- the lookahead's guess was right (1 when NULL)
+//   flags[1] = any word of mask_a differs from mask_b                   -- the speculated masks were not the real ones
+__global__ void schedule_flags_kernel(const int32_t* __restrict__ tok_a, const int32_t* __restrict__ tok_b,
+                                      const int32_t* __restrict__ win_a, const int32_t* __restrict__ win_b, int B,
+                                      const int32_t* __restrict__ mask_a, const int32_t* __restrict__ mask_b, int n_words,
+                                      int32_t* __restrict__ flags) {
+  __shared__ int s_bad, s_diff;
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x == 0) s_bad = s_diff = 0;
+  __syncthreads();
+  int bad = 0, diff = 0;
+  if (tok_a)
+    for (int b = threadIdx.x; b < B; b += blockDim.x) bad |= (tok_a[b] != tok_b[b]) | (win_a[b] != win_b[b]);
+  if (mask_a)
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) diff |= mask_a[i] != mask_b[i];
+  if (bad) s_bad = 1;
+  if (diff) s_diff = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    flags[0] = s_bad ? 0 : 1;
+    flags[1] = s_diff;
+  }
+}
+
 }  // namespace dd
 
 static int sample_masks_impl(const float* epi, const int32_t* topk_ids, int topk, const int32_t* y_init,
@@ -243,5 +270,17 @@ extern "C" int dd_philox_uniform(uint64_t seed, uint64_t offset, int n, float* o
   if (n == 0) return DD_OK;
   philox_uniform_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(seed, offset, n, out);
   DD_CHECK_LAUNCH();
+  return DD_OK;
+}
+
+extern "C" int dd_schedule_flags(const int32_t* tok_a, const int32_t* tok_b, const int32_t* win_a, const int32_t* win_b,
+                                 int B, const int32_t* mask_a, const int32_t* mask_b, int n_words, int32_t* flags,
+                                 dd_stream_t stream) {
+  using namespace dd;
+  DD_CHECK_ARG(flags, "dd_schedule_flags: null flags");
+  DD_CHECK_ARG(!tok_a || (tok_b && win_a && win_b && B >= 1), "dd_schedule_flags: the guess check needs both pairs");
+  DD_CHECK_ARG(!mask_a || (mask_b && n_words >= 1), "dd_schedule_flags: the mask check needs both masks");
+  DD_LAUNCH_CHAIN(schedule_flags_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, tok_a, tok_b, win_a, win_b, B, mask_a,
+                  mask_b, n_words, flags);
   return DD_OK;
 }

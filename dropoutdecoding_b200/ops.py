@@ -168,6 +168,26 @@ def sample_masks(epi: torch.Tensor, topk_ids: Optional[torch.Tensor], y_init: Op
     return out, n_masked
 
 
+def schedule_flags(flags: torch.Tensor, mask_a: Optional[torch.Tensor] = None, mask_b: Optional[torch.Tensor] = None,
+                   tok_a: Optional[torch.Tensor] = None, tok_b: Optional[torch.Tensor] = None,
+                   win_a: Optional[torch.Tensor] = None, win_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dd_schedule_flags: flags int32 [2] <- {all(tok_a == tok_b) & all(win_a == win_b), any(mask_a != mask_b)}."""
+    _need(flags, torch.int32, "flags")
+    for t, n in ((mask_a, "mask_a"), (mask_b, "mask_b"), (tok_a, "tok_a"), (tok_b, "tok_b"), (win_a, "win_a"),
+                 (win_b, "win_b")):
+        if t is not None:
+            _need(t, torch.int32, n)
+            if not t.is_contiguous():
+                raise DropDecError(f"schedule_flags: {n} must be contiguous")
+    if mask_a is not None and mask_a.numel() != mask_b.numel():
+        raise DropDecError("schedule_flags: masks of different sizes")
+    check(_lib.load().dd_schedule_flags(_ptr(tok_a), _ptr(tok_b), _ptr(win_a), _ptr(win_b),
+                                        tok_a.numel() if tok_a is not None else 0, _ptr(mask_a), _ptr(mask_b),
+                                        mask_a.numel() if mask_a is not None else 0, _ptr(flags), _stream()),
+          "dd_schedule_flags")
+    return flags
+
+
 def philox_uniform(seed: int, offset: int, n: int, device="cuda") -> torch.Tensor:
     L = _lib.load()
     out = torch.empty(n, dtype=torch.float32, device=device)

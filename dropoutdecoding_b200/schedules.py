@@ -107,8 +107,16 @@ class SpeculativeSchedules:
             self.winner_c = torch.zeros(B, **i32)
             self._tok_c = torch.zeros(B, **i32)
             self.winner_p1 = torch.zeros(B, **i32)
-            self.need_fb = torch.zeros(1, **i32)
+            self._spec_flags = torch.zeros(2, **i32)                # dd_schedule_flags: {-, the step must be repeated}
+            self.need_fb = self._spec_flags[1:2]
             self.need_fb_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            if self.spec_active:
+                # one sequence: ONE mask buffer [real masks of the step (K) | unmasked context | draws (K)] -- the
+                # speculative pass reads rows K..2K, the lookahead pass all 2K+1, nothing is copied between them
+                self._mask_all = torch.zeros(B, 2 * self.K + 1, self.words, **i32)
+                self.bitmask = self._mask_all[:, :self.K]
+                self.spec_mask = self._mask_all[:, self.K:]
+                self.spec_draw = self._mask_all[:, self.K + 1:]
             self.tok_host = torch.zeros(B, dtype=torch.int32).pin_memory()     # input token of the pass (EOS check)
             self.tok2_host = torch.zeros(B, dtype=torch.int32).pin_memory()    # token a lookahead pass committed (EOS check)
         # ---- lookahead inside the fallback pass (one sequence, see _spec_chain): 2K+1 contexts
@@ -118,7 +126,7 @@ class SpeculativeSchedules:
         if self.lookahead:
             K = self.K
             self.pd = self._alloc_pass(2 * K + 1, est)
-            self.chain_mask = torch.zeros(B, 2 * K + 1, self.words, **i32)
+            self.chain_mask = self._mask_all
             self._g_tok, self._g_win = torch.zeros(B, **i32), torch.zeros(B, **i32)     # the guessed outcome of step t
             self._g_ids = torch.zeros(B, K, **i32)
             self._seq_p1, self._step_p1 = torch.zeros(B, **i32), torch.zeros(1, **i32)
@@ -144,8 +152,7 @@ class SpeculativeSchedules:
     def _spec_head(self) -> None:
         self.launches_per_step = 0
         u = self._step_uniforms()
-        self._sample(u, False, self.spec_draw, self._nm_spec)
-        self.spec_mask[:, 1:].copy_(self.spec_draw)
+        self._sample(u, False, self.spec_draw, self._nm_spec)        # (the draws ARE rows 1..K of spec_mask)
         logits_c = self._forward(self.pc, self.spec_mask)
         ops.aggregate(logits_c, "vote", member_ids=self.member_ids_c, winner=self.winner_c, token=self._tok_c,
                       vocab=self.cfg.vocab)                                        # per-row argmax of all K+1 contexts
@@ -153,7 +160,7 @@ class SpeculativeSchedules:
         self.y_init.copy_(self.member_ids_c[:, 0])
         if self.keep_relevant:
             self._sample(u, True, self.bitmask, self.n_masked)                     # the reference's masks
-            self.need_fb.copy_((self.bitmask != self.spec_draw).any().to(torch.int32).reshape(1))
+            ops.schedule_flags(self._spec_flags, mask_a=self.bitmask, mask_b=self.spec_draw)   # need_fb
         else:                                                                      # epis_no_overlap: nothing to restore
             self.bitmask.copy_(self.spec_draw)
             self.n_masked.copy_(self._nm_spec)
@@ -234,8 +241,7 @@ class SpeculativeSchedules:
         torch.add(self.seq_lens, 1, out=self._seq_p1)
         torch.add(self.step_ctr, 1, out=self._step_p1)
         self._sample(self._step_uniforms(1), False, self.spec_draw, self._nm_spec, step=self._step_p1)   # draws of t+1
-        self.chain_mask[:, :K].copy_(self.bitmask)
-        self.chain_mask[:, K + 1:].copy_(self.spec_draw)
+        # (chain_mask = [bitmask | unmasked | spec_draw] is one buffer: nothing to copy)
         # per-row input token and RoPE position: the kernels see 2K+1 "sequences" of one member each
         self._row_tok_c[:K] = self.cur_token
         self._row_tok_c[K:] = self._g_tok
@@ -262,15 +268,15 @@ class SpeculativeSchedules:
         ops.step_advance(self.next_token, self.tokens_out, self.seq_lens, self.step_ctr)
         self.cur_token.copy_(self.next_token)
         self.tok2_host.copy_(self.next_token, non_blocking=True)   # step t's result: the host must not chain past an EOS
-        ok = (self.next_token == self._g_tok) & (self.winner == self._g_win)
         # ---- step t+1 as _spec_head would see it (only meaningful when the guess was right)
         ops.aggregate(pd.logits, "vote", member_ids=self._ids_d, winner=self._win_d, token=self._tok_d, vocab=V,
                       first_member=K, members=K + 1)
         self.y_init.copy_(self._ids_d[:, 0])
         self._sample(self._step_uniforms(0), True, self.bitmask, self.n_masked)            # the reference's masks of t+1
-        fb = (self.bitmask != self.spec_draw).any()
-        self.chain_flags.copy_(torch.stack([ok.all(), fb]).to(torch.int32))
-        self.launches_per_step += 10
+        # {the guessed (token, winner) of step t was right, step t+1 must be repeated}: one launch
+        ops.schedule_flags(self.chain_flags, mask_a=self.bitmask, mask_b=self.spec_draw, tok_a=self.next_token,
+                           tok_b=self._g_tok, win_a=self.winner, win_b=self._g_win)
+        self.launches_per_step += 11
         self._guess_from(pd.logits, K + 1)          # should step t+1 fall back too: its own guess
         self.chain_flags_host.copy_(self.chain_flags, non_blocking=True)
 

@@ -143,6 +143,16 @@ int dd_sample_masks_seq(const float* epi, const int32_t* topk_ids, int topk, con
  * torch.rand(n, device="cuda") uses for n <= 256 * #blocks. */
 int dd_philox_uniform(uint64_t seed, uint64_t offset, int n, float* out, dd_stream_t stream);
 
+/* Host-decision flags of the one-sequence speculative schedule in one launch (no reference counterpart: the reference
+ * takes these decisions with `.item()` calls, models/llava.py:22-36, 443-482):
+ *   flags[0] = 1 iff tok_a[b] == tok_b[b] and win_a[b] == win_b[b] for every b < B (NULL tok_a: 1) -- the guessed vote of
+ *              the lookahead pass was the real one;
+ *   flags[1] = 1 iff any of the n_words mask words differ (NULL mask_a: 0) -- the speculated masks were not the real
+ *              ones (y_init restored a drawn visual token), i.e. the step has to be repeated. */
+int dd_schedule_flags(const int32_t* tok_a, const int32_t* tok_b, const int32_t* win_a, const int32_t* win_b, int B,
+                      const int32_t* mask_a, const int32_t* mask_b, int n_words, int32_t* flags /* [2] */,
+                      dd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (3) Decode attention for the M masked contexts over one shared prefix KV cache.
  * Replaces: the K+1 `copy.deepcopy(past_key_values)` (models/llava.py:292,343) and the masked
