@@ -657,3 +657,73 @@ def test_l2_prefetch_hint_leaves_results_untouched(ops, cuda):
     from dropoutdecoding_b200 import _lib
     with pytest.raises(ops.DropDecError):                        # misaligned range
         ops.check_rc(_lib.load().dd_hint_l2_prefetch(w_big.data_ptr() + 2, 32, None, 0), "dd_hint_l2_prefetch")
+
+
+def test_two_window_attention_equals_two_calls(ops, cuda):
+    """dd_decode_attention_two_windows (the lookahead pass: members [0, Ma) over keys [0, S), members [Ma, M) over keys
+    [0, S + 1), split key ranges, ONE launch) is bit-identical to two dd_decode_attention_active calls, masks included."""
+    g = torch.Generator().manual_seed(21)
+    B, Ma, Mb, H, D, S_max, n_vis, splits = 2, 3, 4, 8, 128, 700, 576, 3
+    M = Ma + Mb
+    bf = lambda *s: torch.randn(*s, generator=g).to(cuda).bfloat16()
+    q, k_new, v_new, kc, vc = bf(B, M, H, D), bf(B, M, H, D), bf(B, M, H, D), bf(B, H, S_max, D), bf(B, H, S_max, D)
+    lens_a = torch.tensor([601, 640], dtype=torch.int32, device=cuda)
+    lens_b = lens_a + 1
+    vs = torch.tensor([5, 9], dtype=torch.int32, device=cuda)
+    bm = torch.randint(-2 ** 31, 2 ** 31 - 1, (B, M, ops.mask_words(n_vis)), generator=g, dtype=torch.int64).to(torch.int32).to(cuda)
+    scale = 1.0 / math.sqrt(D)
+    want = torch.zeros_like(q)
+    ws = ops.attention_workspace(B, M, H, D, splits, cuda)
+    ops.decode_attention(q, k_new, v_new, kc, vc, lens_a, vs, bm, n_vis, scale, splits, want, ws, member_offset=0, members=Ma)
+    ops.decode_attention(q, k_new, v_new, kc, vc, lens_b, vs, bm, n_vis, scale, splits, want, ws, member_offset=Ma, members=Mb)
+    got = torch.zeros_like(q)
+    ws2 = ops.two_window_attention_workspace(B, M, H, D, splits, cuda)
+    for _ in range(2):                                            # the tickets are left at zero: callable again
+        got.zero_()
+        ops.decode_attention_two_windows(q, k_new, v_new, kc, vc, lens_a, lens_b, Ma, vs, bm, n_vis, scale, splits, got, ws2)
+        assert torch.equal(got, want)
+    with pytest.raises(ops.DropDecError):                         # unsplit ranges take the len_extra path instead
+        ops.decode_attention_two_windows(q, k_new, v_new, kc, vc, lens_a, lens_b, Ma, vs, bm, n_vis, scale, 1, got, ws2)
+
+
+def test_rope_epilogue_commits_the_guessed_row(ops, cuda):
+    """dd_rope_args.guess_winner: the QKV projection's epilogue also writes the new K/V rows of member guess_winner[b] to
+    cache row guess_pos[b] -- exactly what dd_commit_winner of that layer writes; a winner outside the members or a position
+    past the cache writes nothing; everything else of the projection is unchanged."""
+    from oracle import rope_table
+    g = torch.Generator().manual_seed(4)
+    B, Mm, H, H_kv, D, K, S_max = 2, 7, 8, 8, 128, 1024, 40
+    rows, N = B * Mm, (H + 2 * H_kv) * D
+    cos, sin = rope_table(D, 10000.0, 64, faithful=True)
+    x = (torch.randn(rows, K, generator=g) * 0.5).to(cuda).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(cuda).bfloat16()
+    pos = torch.randint(0, 30, (rows,), generator=g, dtype=torch.int32).to(cuda)
+    mk = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=cuda)
+    outs = []
+    for guess in (None, torch.tensor([2, 9], dtype=torch.int32, device=cuda)):      # 9: outside the 7 members
+        q, kn, vn, kc, vc = mk(B, Mm, H, D), mk(B, Mm, H_kv, D), mk(B, Mm, H_kv, D), mk(B, H_kv, S_max, D), mk(B, H_kv, S_max, D)
+        rope = dict(cos=cos.to(cuda), sin=sin.to(cuda), seq_lens=pos, members=1, H=H, H_kv=H_kv, D=D, q_out=q, k_new=kn, v_new=vn)
+        if guess is not None:
+            rope.update(guess_winner=guess, guess_pos=torch.tensor([17, 3], dtype=torch.int32, device=cuda),
+                        guess_members=Mm, k_cache=kc, v_cache=vc)
+        ops.decoder_linear(x, w, ops.EPI_ROPE, rope=rope)
+        outs.append((q, kn, vn, kc, vc))
+    (q0, kn0, vn0, kc0, vc0), (q1, kn1, vn1, kc1, vc1) = outs
+    assert torch.equal(q0, q1) and torch.equal(kn0, kn1) and torch.equal(vn0, vn1)
+    assert int(kc0.abs().sum()) == 0 and int(vc0.abs().sum()) == 0
+    want_k, want_v = torch.zeros_like(kc1), torch.zeros_like(vc1)
+    want_k[0, :, 17], want_v[0, :, 17] = kn1[0, 2], vn1[0, 2]                       # sequence 1's winner is out of range
+    assert torch.equal(kc1, want_k) and torch.equal(vc1, want_v)
+    assert float(kn1[0, 2].abs().sum()) > 0
+
+
+def test_schedule_flags(ops, cuda):
+    a = torch.randint(0, 2 ** 31 - 1, (1, 3, 18), dtype=torch.int64).to(torch.int32).to(cuda)
+    b = a.clone()
+    tok, win = torch.tensor([77], dtype=torch.int32, device=cuda), torch.tensor([1], dtype=torch.int32, device=cuda)
+    f = torch.full((2,), -1, dtype=torch.int32, device=cuda)
+    assert ops.schedule_flags(f, mask_a=a, mask_b=b).tolist() == [1, 0]
+    b[0, 2, 17] ^= 1
+    assert ops.schedule_flags(f, mask_a=a, mask_b=b, tok_a=tok, tok_b=tok.clone(), win_a=win, win_b=win.clone()).tolist() == [1, 1]
+    assert ops.schedule_flags(f, mask_a=a, mask_b=a, tok_a=tok, tok_b=tok + 1, win_a=win, win_b=win).tolist() == [0, 0]
+    assert ops.schedule_flags(f, tok_a=tok, tok_b=tok, win_a=win, win_b=win + 1).tolist() == [0, 0]
