@@ -221,6 +221,19 @@ def run_ours(args):
         barrier()
         dt_e2e = f0.elapsed_time(f1) * 1e-3
         assert out.shape == (B, PROMPT_LEN + T)
+        # ---- a POPE-style answer (pope_test/pope_test.py:242 asks for ONE new token): all prompt side -- vision tower,
+        #      prefill, uncertainty stage, first token; host tensors in, host tokens out
+        pope = None
+        if rank == 0 and not args.tiny:
+            for _ in range(2):
+                model.generate(input_ids=ids_h, pixel_values=px_h, max_new_tokens=1).cpu()
+            torch.cuda.synchronize()
+            t_p = time.perf_counter()
+            for _ in range(5):
+                one = model.generate(input_ids=ids_h, pixel_values=px_h, max_new_tokens=1).cpu()
+            pope = {"what": "model.generate(max_new_tokens=1), host tensors in / out, mean of 5 calls",
+                    "e2e_ms": round((time.perf_counter() - t_p) * 1e3 / 5, 3), "new_tokens": 1,
+                    "token_equals_first_of_the_long_answer": bool(torch.equal(one[:, -1], out[:, PROMPT_LEN]))}
 
         # ---- roofline of the dominant kernel, measured live: one eager ensemble step with CUDA
         #      events around every dd_skinny_gemm launch on the launching stream
@@ -260,7 +273,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(ids_h.numel() * ids_h.element_size() + px_h.numel() * px_h.element_size()),
                 "d2h_bytes_per_step": int(out.numel() * out.element_size())},
         "gpu_launches": int(ens_launches + args.steps * 6), "decode_schedule": spec,
-        "prefill_ms": round(prefill_ms, 2),
+        "prefill_ms": round(prefill_ms, 2), "pope_style": pope,
         "ms_per_token": round(dt / args.steps / T * 1e3, 4),
         "clocks": clk, "roofline": roof, "stage_rooflines": stages,
         "token_checksum": int(tokens_check.long().sum().item()),
